@@ -1,0 +1,79 @@
+"""ctypes binding of libunetk.so (the C ABI declared in include/unetk.h).
+
+There is deliberately NO fallback: if the shared object is missing, or a call returns an error, this
+module raises.  A silent eager-PyTorch path would void every parity and performance claim.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libunetk.so"
+HEADER = PKG.parent / "include" / "unetk.h"
+
+_lib = None
+
+_vp, _i, _i64, _sz, _fp, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_void_p, C.c_float
+
+# name -> (restype, argtypes); must mirror include/unetk.h exactly (tests/test_abi.py checks the set).
+SIGNATURES = {
+    "unetk_abi_version": (_i, []),
+    "unetk_last_error": (C.c_char_p, []),
+    "unetk_pack_weight": (_i, [_fp, _vp, _vp, _i, _i, _i, _vp]),
+    "unetk_conv3x3_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv3x3_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv_wgrad_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "unetk_conv3x3_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "unetk_conv1x1_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv1x1_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv1x1_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "unetk_convT2x2_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_convT2x2_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_convT2x2_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "unetk_probe_umma": (_i, [_vp, _vp, _fp, _i, _i, _i, _vp]),
+}
+
+
+def header_symbols() -> list[str]:
+    """Every function name declared in include/unetk.h."""
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(unetk_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m jcfszxc_unet_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU / eager fallback for the U-Net hot path."
+        )
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.unetk_abi_version()
+    if got != 1:
+        raise RuntimeError(f"libunetk.so ABI version {got}, expected 1")
+    _lib = lib
+    return lib
+
+
+class UnetkError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().unetk_last_error()
+        raise UnetkError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point and raise on error."""
+    check(getattr(load(), name)(*args), name)

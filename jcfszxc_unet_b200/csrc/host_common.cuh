@@ -1,0 +1,42 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and TMA tensor maps.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+namespace unetk {
+
+// Error slot returned by unetk_last_error(); written only on failure.
+void set_error(const char* fmt, ...);
+
+#define UNETK_CHECK(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::unetk::set_error(__VA_ARGS__); \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define UNETK_CUDA(call)                                                              \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      ::unetk::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                         __LINE__);                                                   \
+      return -3;                                                                      \
+    }                                                                                 \
+  } while (0)
+
+int num_sms();
+const char* last_error();
+
+// A bf16 tensor map with up to 5 dims. dims[0] is the contiguous one; strides_bytes[i] is the stride
+// of dims[i+1]. OOB elements read as zero. Returns 0 or a negative code (error text set).
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                   bool swizzle128);
+
+}  // namespace unetk

@@ -1,0 +1,289 @@
+// Weight-gradient GEMM on tcgen05: D_tap[m, n] = sum_pixels P[pix + offP(tap)][m] * Q[pix + offQ(tap)][n].
+// The reduction dimension is the pixel index, which is the SLOW dimension of NHWC, so both operands
+// are "MN-major" UMMA tiles: a TMA box of (64 channels, TW, TH, 1) lands as [64 pixels][64 ch] with
+// 128B swizzle, which is exactly the canonical MN-major SW128 atom sequence (8 pixel rows per atom).
+// Split over pixel ranges (deterministic: fp32 partials + ordered reduce in wgrad_reduce_kernel).
+// Reference semantics replaced: autograd's weight gradient of nn.Conv2d(k=3,p=1 / k=1) and
+// nn.ConvTranspose2d(k=2,s=2) (UNetFamily/utils/unet_parts.py:24-31,56-58 in the reference).
+#include "host_common.cuh"
+#include "ptx.cuh"
+#include "wgrad.cuh"
+
+namespace unetk {
+
+namespace {
+
+constexpr int kPix = 64;      // pixels per k-block
+constexpr int kThreads = 192;
+constexpr uint32_t kBoxBytes = kPix * 64 * 2;  // one [64 pix][64 ch] box = 8 KB
+
+template <int BN>
+struct WCfg {
+  static constexpr int kBoxes = 2 + BN / 64;
+  static constexpr uint32_t kStageBytes = kBoxes * kBoxBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 7);
+  static constexpr uint32_t kTmemCols = 2 * BN;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using C = WCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tfull_bar = bars + 2 * C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmP);
+    tma_prefetch_desc(&p.tmQ);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int items_per_split = p.taps * p.m_tiles * p.n_tiles;
+  const int num_items = items_per_split * p.ksplit;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int nt = item % p.n_tiles;
+        const int mt = (item / p.n_tiles) % p.m_tiles;
+        const int tap = (item / (p.n_tiles * p.m_tiles)) % p.taps;
+        const int ks = item / items_per_split;
+        const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
+        const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
+        for (int kt = kt0; kt < kt1; ++kt) {
+          const int tw = kt % p.tiles_w;
+          const int th = (kt / p.tiles_w) % p.tiles_h;
+          const int img = kt / (p.tiles_w * p.tiles_h);
+          const int h0 = th * p.TH, w0 = tw * p.TW;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sp = smem + stage * C::kStageBytes;
+          uint8_t* sq = sp + 2 * kBoxBytes;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          const int ph = p.p_step * h0 + p.p_dh[tap], pw = p.p_step * w0 + p.p_dw[tap];
+          const int qh = p.q_step * h0 + p.q_dh[tap], qw = p.q_step * w0 + p.q_dw[tap];
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            tma_load_4d(sp + b * kBoxBytes, &p.tmP, &full_bar[stage], mt * 128 + b * 64, pw, ph, img);
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_4d(sq + b * kBoxBytes, &p.tmQ, &full_bar[stage], nt * BN + b * 64, qw, qh, img);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int ks = item / items_per_split;
+        const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
+        const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kt = kt0; kt < kt1; ++kt) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t p_base = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t q_base = p_base + 2 * kBoxBytes;
+#pragma unroll
+          for (int k = 0; k < kPix / 16; ++k) {
+            // 16 pixel rows per MMA = 2 swizzle atoms of 8 rows (SBO 1024 B); 64-channel boxes are
+            // kBoxBytes apart (LBO).
+            const uint64_t da = make_smem_desc(p_base + k * 2048, kBoxBytes, 1024, kLayoutSW128);
+            const uint64_t db = make_smem_desc(q_base + k * 2048, kBoxBytes, 1024, kLayoutSW128);
+            umma_bf16(d_tmem, da, db, idesc, (kt > kt0) || (k != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int nt = item % p.n_tiles;
+      const int mt = (item / p.n_tiles) % p.m_tiles;
+      const int tap = (item / (p.n_tiles * p.m_tiles)) % p.taps;
+      const int ks = item / items_per_split;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m = mt * 128 + row;
+      float* dst = p.partial + ((static_cast<size_t>(ks) * p.taps + tap) * p.M + m) * p.Nn + nt * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (m < p.M) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const int col = nt * BN + c * 32 + v * 4;
+            if (col < p.Nn) {
+              float4 o = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
+                                     __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+              *reinterpret_cast<float4*>(dst + c * 32 + v * 4) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// dw[m*sm + n*sn + tap*st] (+)= sum_ks partial[ks][tap][m][n]   (fixed order -> deterministic)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ksplit,
+                                    int taps, int M, int Nn, int64_t sm, int64_t sn, int64_t st,
+                                    int accumulate) {
+  const int64_t total = static_cast<int64_t>(taps) * M * Nn;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i % Nn);
+    const int m = static_cast<int>((i / Nn) % M);
+    const int tap = static_cast<int>(i / (static_cast<int64_t>(Nn) * M));
+    float s = 0.f;
+    for (int k = 0; k < ksplit; ++k) s += partial[k * total + i];
+    float* o = dw + m * sm + n * sn + tap * st;
+    *o = accumulate ? (*o + s) : s;
+  }
+}
+
+template <int BN>
+int launch(const WgradParams& p, cudaStream_t stream) {
+  using C = WCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    UNETK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::kSmemBytes));
+    configured = true;
+  }
+  const int items = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
+  const int grid = items < num_sms() ? items : num_sms();
+  wgrad_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+void plan(const WgradDesc& d, int* BN, int* ksplit, int* TH, int* TW, int* pix_tiles) {
+  *BN = d.Nn >= 256 ? 256 : (d.Nn > 64 ? 128 : 64);
+  int tw = 64;
+  while (tw > d.W) tw >>= 1;
+  if (tw < 1) tw = 1;
+  *TW = tw;
+  *TH = kPix / tw;
+  const int tiles_h = (d.H + *TH - 1) / *TH, tiles_w = (d.W + tw - 1) / tw;
+  *pix_tiles = d.N * tiles_h * tiles_w;
+  const int m_tiles = (d.M + 127) / 128, n_tiles = (d.Nn + *BN - 1) / *BN;
+  const int base = d.taps * m_tiles * n_tiles;
+  int ks = (2 * num_sms() + base - 1) / base;
+  const int cap = *pix_tiles / 8 > 0 ? *pix_tiles / 8 : 1;
+  if (ks > cap) ks = cap;
+  if (ks < 1) ks = 1;
+  *ksplit = ks;
+}
+
+}  // namespace
+
+size_t wgrad_workspace_bytes(const WgradDesc& d) {
+  int BN, ks, TH, TW, pt;
+  plan(d, &BN, &ks, &TH, &TW, &pt);
+  return static_cast<size_t>(ks) * d.taps * d.M * d.Nn * sizeof(float);
+}
+
+int wgrad_run(const WgradDesc& d, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  UNETK_CHECK(d.M % 8 == 0 && d.Nn % 8 == 0, -1, "wgrad: channel counts must be multiples of 8 (M=%d N=%d)", d.M, d.Nn);
+  UNETK_CHECK(d.p_ld % 8 == 0 && d.q_ld % 8 == 0, -1, "wgrad: pixel strides must be multiples of 8");
+  UNETK_CHECK(d.taps >= 1 && d.taps <= 9, -1, "wgrad: taps=%d", d.taps);
+  WgradParams p{};
+  int BN;
+  plan(d, &BN, &p.ksplit, &p.TH, &p.TW, &p.pix_tiles);
+  const size_t need = static_cast<size_t>(p.ksplit) * d.taps * d.M * d.Nn * sizeof(float);
+  UNETK_CHECK(workspace != nullptr && ws_bytes >= need, -1, "wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
+  p.tiles_h = (d.H + p.TH - 1) / p.TH;
+  p.tiles_w = (d.W + p.TW - 1) / p.TW;
+  p.m_tiles = (d.M + 127) / 128;
+  p.n_tiles = (d.Nn + BN - 1) / BN;
+  p.taps = d.taps;
+  p.M = d.M; p.Nn = d.Nn;
+  p.p_step = d.p_step; p.q_step = d.q_step;
+  for (int t = 0; t < d.taps; ++t) {
+    p.p_dh[t] = d.p_dh[t]; p.p_dw[t] = d.p_dw[t]; p.q_dh[t] = d.q_dh[t]; p.q_dw[t] = d.q_dw[t];
+  }
+  p.partial = static_cast<float*>(workspace);
+  UNETK_CHECK(p.TW * d.p_step <= 256 && p.TH * d.p_step <= 256 && p.TW * d.q_step <= 256 && p.TH * d.q_step <= 256,
+              -1, "wgrad: TMA box too large");
+  auto mk = [&](CUtensorMap* tm, const void* base, int64_t ld, int C, int step) -> int {
+    const int AH = d.H * step, AW = d.W * step;
+    uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(AW), static_cast<uint64_t>(AH),
+                        static_cast<uint64_t>(d.N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * AW,
+                           static_cast<uint64_t>(ld) * 2 * AW * AH};
+    uint32_t box[4] = {64, static_cast<uint32_t>(p.TW * step), static_cast<uint32_t>(p.TH * step), 1};
+    uint32_t es[4] = {1, static_cast<uint32_t>(step), static_cast<uint32_t>(step), 1};
+    return make_tmap_bf16(tm, base, 4, dims, strides, box, es, true);
+  };
+  if (int rc = mk(&p.tmP, d.p, d.p_ld, d.M, d.p_step)) return rc;
+  if (int rc = mk(&p.tmQ, d.q, d.q_ld, d.Nn, d.q_step)) return rc;
+  int rc;
+  switch (BN) {
+    case 256: rc = launch<256>(p, stream); break;
+    case 128: rc = launch<128>(p, stream); break;
+    default: rc = launch<64>(p, stream); break;
+  }
+  if (rc) return rc;
+  const int64_t total = static_cast<int64_t>(d.taps) * d.M * d.Nn;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, d.dw, p.ksplit, d.taps, d.M, d.Nn, d.dw_sm,
+                                                  d.dw_sn, d.dw_st, d.accumulate);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace unetk

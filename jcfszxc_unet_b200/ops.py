@@ -1,0 +1,133 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, raw pointers + current stream out.
+
+All activations are NHWC bf16 tensors of shape [N, H, W, C] whose channel stride is 1; the pixel stride
+(`ld`) may exceed C, i.e. a tensor may be a channel slice of a wider (concat) buffer.
+PyTorch here is plumbing only (device memory + streams); every FLOP runs in libunetk.so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_ws_cache: dict[tuple[int, int], torch.Tensor] = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def nhwc(t: torch.Tensor) -> tuple[int, int]:
+    """(data_ptr, ld) of an NHWC view; validates the layout the kernels assume."""
+    if t.dim() != 4 or t.dtype != torch.bfloat16 or not t.is_cuda:
+        raise ValueError(f"expected a 4-D CUDA bf16 NHWC tensor, got {tuple(t.shape)} {t.dtype} {t.device}")
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    ld = sw
+    if sc != 1 or sh != w * ld or (n > 1 and sn != h * w * ld) or ld < c:
+        raise ValueError(f"not an NHWC (channel-sliced) view: shape {tuple(t.shape)} stride {t.stride()}")
+    return t.data_ptr(), ld
+
+
+def _f32(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError("expected a contiguous CUDA fp32 tensor")
+    return t.data_ptr()
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream); owned by the host side, never by the library."""
+    key = (device.index or 0, _stream())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def pack_weight(w: torch.Tensor, want_ab: bool = True, want_ba: bool = True):
+    """fp32 [A,B,kh,kw] -> (bf16 [T,A,B] | None, bf16 [T,B,A] | None)."""
+    a, b = w.shape[0], w.shape[1]
+    t = w.numel() // (a * b)
+    ab = torch.empty((t, a, b), dtype=torch.bfloat16, device=w.device) if want_ab else None
+    ba = torch.empty((t, b, a), dtype=torch.bfloat16, device=w.device) if want_ba else None
+    _lib.call("unetk_pack_weight", _f32(w.detach()), ab.data_ptr() if ab is not None else None,
+              ba.data_ptr() if ba is not None else None, a, b, t, _stream())
+    return ab, ba
+
+
+def conv_fwd(x, w_pack, bias, y, ksize: int = 3):
+    """y <- conv(x): x [N,H,W,Cin], w_pack bf16 [k*k,Cout,Cin], y [N,H,W,Cout] (raw conv output)."""
+    n, h, w, cin = x.shape
+    cout = y.shape[3]
+    assert w_pack.shape == (ksize * ksize, cout, cin) and y.shape[:3] == x.shape[:3]
+    xp, xld = nhwc(x)
+    yp, yld = nhwc(y)
+    name = "unetk_conv3x3_fwd" if ksize == 3 else "unetk_conv1x1_fwd"
+    _lib.call(name, xp, xld, w_pack.data_ptr(), _f32(bias), yp, yld, n, h, w, cin, cout, _stream())
+    return y
+
+
+def conv_dgrad(dy, w_pack_t, dx, ksize: int = 3):
+    """dx <- conv^T(dy): dy [N,H,W,Cout], w_pack_t bf16 [k*k,Cin,Cout], dx [N,H,W,Cin]."""
+    n, h, w, cout = dy.shape
+    cin = dx.shape[3]
+    assert w_pack_t.shape == (ksize * ksize, cin, cout)
+    dyp, dyld = nhwc(dy)
+    dxp, dxld = nhwc(dx)
+    name = "unetk_conv3x3_dgrad" if ksize == 3 else "unetk_conv1x1_dgrad"
+    _lib.call(name, dyp, dyld, w_pack_t.data_ptr(), dxp, dxld, n, h, w, cin, cout, _stream())
+    return dx
+
+
+def conv_wgrad(x, dy, dw, ksize: int = 3, accumulate: bool = False):
+    """dw (fp32 [Cout,Cin,k,k]) <- sum_pixels dy (x) x."""
+    n, h, w, cin = x.shape
+    cout = dy.shape[3]
+    assert dw.shape == (cout, cin, ksize, ksize) and dw.dtype == torch.float32 and dw.is_contiguous()
+    need = _lib.load().unetk_conv_wgrad_workspace(n, h, w, cin, cout, ksize * ksize)
+    ws = workspace(need, x.device)
+    xp, xld = nhwc(x)
+    dyp, dyld = nhwc(dy)
+    name = "unetk_conv3x3_wgrad" if ksize == 3 else "unetk_conv1x1_wgrad"
+    _lib.call(name, xp, xld, dyp, dyld, dw.data_ptr(), int(accumulate), n, h, w, cin, cout, ws.data_ptr(),
+              ws.numel(), _stream())
+    return dw
+
+
+def convT_fwd(x, w_pack, bias, y):
+    """y [N,2H,2W,Cout] <- ConvTranspose2d(k=2,s=2)(x [N,H,W,Cin]); w_pack bf16 [4,Cout,Cin]."""
+    n, h, w, cin = x.shape
+    cout = y.shape[3]
+    assert w_pack.shape == (4, cout, cin) and y.shape[1] == 2 * h and y.shape[2] == 2 * w
+    xp, xld = nhwc(x)
+    yp, yld = nhwc(y)
+    _lib.call("unetk_convT2x2_fwd", xp, xld, w_pack.data_ptr(), _f32(bias), yp, yld, n, h, w, cin, cout, _stream())
+    return y
+
+
+def convT_dgrad(dy, w_pack_t, dx):
+    """dx [N,H,W,Cin] <- dy [N,2H,2W,Cout]; w_pack_t bf16 [4,Cin,Cout]."""
+    n, h, w, cin = dx.shape
+    cout = dy.shape[3]
+    assert w_pack_t.shape == (4, cin, cout) and dy.shape[1] == 2 * h and dy.shape[2] == 2 * w
+    dyp, dyld = nhwc(dy)
+    dxp, dxld = nhwc(dx)
+    _lib.call("unetk_convT2x2_dgrad", dyp, dyld, w_pack_t.data_ptr(), dxp, dxld, n, h, w, cin, cout, _stream())
+    return dx
+
+
+def convT_wgrad(x, dy, dw, accumulate: bool = False):
+    """dw (fp32 [Cin,Cout,2,2]) <- sum_pixels x (x) dy."""
+    n, h, w, cin = x.shape
+    cout = dy.shape[3]
+    assert dw.shape == (cin, cout, 2, 2) and dw.dtype == torch.float32 and dw.is_contiguous()
+    need = _lib.load().unetk_conv_wgrad_workspace(n, h, w, cin, cout, 4)
+    ws = workspace(need, x.device)
+    xp, xld = nhwc(x)
+    dyp, dyld = nhwc(dy)
+    _lib.call("unetk_convT2x2_wgrad", xp, xld, dyp, dyld, dw.data_ptr(), int(accumulate), n, h, w, cin, cout,
+              ws.data_ptr(), ws.numel(), _stream())
+    return dw

@@ -1,0 +1,168 @@
+"""Kernel-level parity of the tcgen05 tap-GEMM / weight-gradient kernels, called through the C ABI.
+
+Checker: torch.nn.functional in fp32 (TF32 disabled) on the SAME bf16-rounded inputs, i.e. the
+arithmetic the reference's nn.Conv2d / nn.ConvTranspose2d perform under bf16 autocast
+(reference UNetFamily/utils/unet_parts.py:24-31,56-58,77) with fp32 accumulation.
+Tolerance: one bf16 rounding of the output (2^-8 relative) plus accumulation-order noise.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _exact_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _ops():
+    from jcfszxc_unet_b200 import ops
+
+    return ops
+
+
+def _nhwc_slice(n, h, w, c, dev, pad_lo=0, pad_hi=0, fill=None):
+    """An NHWC bf16 tensor that is a channel slice of a wider buffer (ld = pad_lo + c + pad_hi)."""
+    buf = torch.zeros(n, h, w, pad_lo + c + pad_hi, device=dev, dtype=torch.bfloat16)
+    if fill is not None:
+        buf.fill_(fill)
+    return buf, buf[..., pad_lo:pad_lo + c]
+
+
+def _close(got, ref, what):
+    got, ref = got.float(), ref.float()
+    scale = ref.abs().max().item() + 1e-6
+    err = (got - ref).abs().max().item()
+    assert err <= 1.2e-2 * scale, f"{what}: max err {err:.4g} vs scale {scale:.4g}"
+
+
+CONV_SHAPES = [
+    # n, h, w, cin, cout, x_pad(lo,hi), y_pad(lo,hi)
+    (2, 32, 32, 64, 64, (0, 0), (0, 0)),       # BN=64, TW=32
+    (1, 64, 64, 128, 256, (0, 0), (0, 0)),     # BN=256, multi k-chunk
+    (2, 16, 16, 256, 128, (64, 0), (0, 128)),  # BN=128, sliced in/out (concat-buffer views)
+    (1, 8, 256, 64, 64, (0, 0), (64, 0)),      # TW=128, two w tiles
+    (1, 20, 24, 72, 72, (0, 0), (0, 0)),       # ragged: H,W not tile multiples; C not a multiple of 64
+    (3, 5, 7, 8, 8, (0, 0), (0, 0)),           # tiny
+    (1, 32, 32, 512, 320, (0, 0), (0, 0)),     # BN=256 with a masked N tail (320 = 256 + 64)
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,xpad,ypad", CONV_SHAPES)
+def test_conv3x3_fwd(n, h, w, cin, cout, xpad, ypad):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(1234 + cin + cout)
+    xbuf, x = _nhwc_slice(n, h, w, cin, dev, *xpad, fill=7.0)
+    x.copy_(torch.randn(n, h, w, cin, device=dev, generator=g))
+    wt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * (1.0 / (3 * cin ** 0.5))
+    bias = torch.randn(cout, device=dev, generator=g)
+    ybuf, y = _nhwc_slice(n, h, w, cout, dev, *ypad, fill=-3.0)
+    w_pack, _ = ops.pack_weight(wt, True, False)
+    for b in (None, bias):
+        ops.conv_fwd(x, w_pack, b, y, 3)
+        torch.cuda.synchronize()
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float(), b, padding=1).permute(0, 2, 3, 1)
+        _close(y, ref, f"conv3x3_fwd bias={b is not None}")
+    # neighbouring channels of the wider buffer must be untouched
+    if ypad != (0, 0):
+        lo, hi = ypad
+        assert (ybuf[..., :lo] == -3.0).all() and (ybuf[..., lo + cout:] == -3.0).all()
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,xpad,ypad", CONV_SHAPES)
+def test_conv3x3_dgrad(n, h, w, cin, cout, xpad, ypad):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(99 + cin + cout)
+    _, dy = _nhwc_slice(n, h, w, cout, dev, *ypad)
+    dy.copy_(torch.randn(n, h, w, cout, device=dev, generator=g))
+    wt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * (1.0 / (3 * cout ** 0.5))
+    _, dx = _nhwc_slice(n, h, w, cin, dev, *xpad)
+    _, w_pack_t = ops.pack_weight(wt, False, True)
+    ops.conv_dgrad(dy, w_pack_t, dx, 3)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt.bfloat16().float(), padding=1).permute(0, 2, 3, 1)
+    _close(dx, ref, "conv3x3_dgrad")
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,xpad,ypad", CONV_SHAPES)
+def test_conv3x3_wgrad(n, h, w, cin, cout, xpad, ypad):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(7 + cin + cout)
+    _, x = _nhwc_slice(n, h, w, cin, dev, *xpad)
+    x.copy_(torch.randn(n, h, w, cin, device=dev, generator=g))
+    _, dy = _nhwc_slice(n, h, w, cout, dev, *ypad)
+    dy.copy_(torch.randn(n, h, w, cout, device=dev, generator=g))
+    dw = torch.full((cout, cin, 3, 3), float("nan"), device=dev)
+    ops.conv_wgrad(x, dy, dw, 3)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3),
+                                      dy.float().permute(0, 3, 1, 2), padding=1)
+    scale = ref.abs().max().item()
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-3 * scale, f"conv3x3_wgrad: err {err:.4g} scale {scale:.4g}"
+    # accumulate mode adds on top (shared-weight recurrences, unet_parts.py:125-132)
+    ops.conv_wgrad(x, dy, dw, 3, accumulate=True)
+    torch.cuda.synchronize()
+    err2 = (dw - 2 * ref).abs().max().item()
+    assert err2 <= 4e-3 * scale
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 128, 64), (1, 32, 32, 1024, 512), (1, 8, 8, 64, 128)])
+def test_conv1x1(n, h, w, cin, cout):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(n, h, w, cin, device=dev, generator=g).bfloat16()
+    wt = torch.randn(cout, cin, 1, 1, device=dev, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, device=dev, generator=g)
+    y = torch.empty(n, h, w, cout, device=dev, dtype=torch.bfloat16)
+    w_pack, w_pack_t = ops.pack_weight(wt)
+    ops.conv_fwd(x, w_pack, bias, y, 1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float(), bias).permute(0, 2, 3, 1)
+    _close(y, ref, "conv1x1_fwd")
+    dy = torch.randn(n, h, w, cout, device=dev, generator=g).bfloat16()
+    dx = torch.empty_like(x)
+    ops.conv_dgrad(dy, w_pack_t, dx, 1)
+    ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt.bfloat16().float()).permute(0, 2, 3, 1)
+    _close(dx, ref, "conv1x1_dgrad")
+    dw = torch.empty(cout, cin, 1, 1, device=dev)
+    ops.conv_wgrad(x, dy, dw, 1)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 1, 1), dy.float().permute(0, 3, 1, 2))
+    assert (dw - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,ypad", [(2, 16, 16, 128, 64, (64, 0)), (1, 32, 32, 1024, 512, (0, 0)),
+                                                 (1, 6, 10, 64, 64, (0, 0)), (1, 64, 64, 256, 128, (128, 0))])
+def test_convT2x2(n, h, w, cin, cout, ypad):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(11)
+    x = torch.randn(n, h, w, cin, device=dev, generator=g).bfloat16()
+    wt = torch.randn(cin, cout, 2, 2, device=dev, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, device=dev, generator=g)
+    ybuf, y = _nhwc_slice(n, 2 * h, 2 * w, cout, dev, *ypad, fill=5.0)
+    w_dgrad, w_fwd = ops.pack_weight(wt)  # [4,Cin,Cout] (dgrad), [4,Cout,Cin] (fwd)
+    ops.convT_fwd(x, w_fwd, bias, y)
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float(), bias, stride=2).permute(0, 2, 3, 1)
+    _close(y, ref, "convT_fwd")
+    if ypad[0]:
+        assert (ybuf[..., :ypad[0]] == 5.0).all()
+    _, dy = _nhwc_slice(n, 2 * h, 2 * w, cout, dev, *ypad)
+    dy.copy_(torch.randn(n, 2 * h, 2 * w, cout, device=dev, generator=g))
+    dx = torch.empty_like(x)
+    ops.convT_dgrad(dy, w_dgrad, dx)
+    ref = F.conv2d(dy.float().permute(0, 3, 1, 2), wt.bfloat16().float(), stride=2).permute(0, 2, 3, 1)
+    _close(dx, ref, "convT_dgrad")
+    dw = torch.empty(cin, cout, 2, 2, device=dev)
+    ops.convT_wgrad(x, dy, dw)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+    wr = wt.clone().requires_grad_(True)
+    F.conv_transpose2d(xr, wr, None, stride=2).backward(dy.float().permute(0, 3, 1, 2))
+    assert (dw - wr.grad).abs().max().item() <= 2e-3 * wr.grad.abs().max().item()
