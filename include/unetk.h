@@ -67,7 +67,7 @@ int unetk_conv1x1_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_
 /* ---- ConvTranspose2d kernel 2, stride 2 (unet_parts.py:56-58 Up.up, :481 Upsample) ---------------
  * x is [N,H,W,Cin]; y is [N,2H,2W,Cout] (y_ld lets it be the upper slice of the concat buffer).
  * fwd:   y[n,2h+a,2w+b,co] = bias[co] + sum_ci x[n,h,w,ci] * w[ci,co,a,b]
- *        w_pack = bf16 [4][Cout][Cin] (dst_ba of pack with A=Cin,B=Cout,T=4); Cout multiple of 64.
+ *        w_pack = bf16 [4][Cout][Cin] (dst_ba of pack with A=Cin,B=Cout,T=4).
  * dgrad: dx[n,h,w,ci] = sum_{a,b,co} dy[n,2h+a,2w+b,co] * w[ci,co,a,b];  w_pack_t = bf16 [4][Cin][Cout].
  * wgrad: dw[ci,co,a,b] fp32 = sum_{n,h,w} x[n,h,w,ci] * dy[n,2h+a,2w+b,co]. */
 int unetk_convT2x2_fwd(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y,
@@ -77,6 +77,94 @@ int unetk_convT2x2_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, vo
 int unetk_convT2x2_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw,
                          int accumulate, int N, int H, int W, int Cin, int Cout, void* workspace,
                          size_t ws_bytes, void* stream);
+
+/* ---- stem convolution (network input, Cin <= 4; UNet.py:21 -> unet_parts.py:24) -------------------
+ * Reads the fp32 image through arbitrary element strides (sn,sc,sh,sw) — NCHW or channels_last — rounds
+ * operands to bf16 like autocast, writes NHWC bf16.  w is the fp32 master weight [Cout][Cin][3][3].
+ * wgrad: dw fp32 [Cout][Cin][3][3]; workspace >= unetk_stem_wgrad_workspace bytes. */
+int unetk_stem_conv3x3_fwd(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w,
+                           const float* bias, void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout,
+                           void* stream);
+size_t unetk_stem_wgrad_workspace(int N, int H, int W, int Cin);
+int unetk_stem_conv3x3_wgrad(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy,
+                             int64_t dy_ld, float* dw, int accumulate, int N, int H, int W, int Cin, int Cout,
+                             void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- BatchNorm2d (+ReLU) (+MaxPool2d(2)), training and eval (unet_parts.py:25-26,28-29,42-44) -----
+ * Two-phase in training because scale/shift depend on whole-batch statistics:
+ *   unetk_bn_stats    : sums = double[2][C] (sum, sum of squares) of the raw conv output.
+ *                       (data-parallel ranks may all-reduce `sums` here = SyncBN-exact statistics)
+ *   unetk_bn_finalize : count = pixels behind `sums`; writes scale = gamma*invstd, shift = beta - mean*scale,
+ *                       mean, invstd and updates running_mean/var (momentum, unbiased var) and
+ *                       num_batches_tracked (+1) when those pointers are non-NULL.
+ *   unetk_bn_eval_fold: eval mode, scale/shift from the running statistics.
+ *   unetk_bn_apply    : out = relu?(bf16(raw*scale+shift)); if pooled != NULL also writes the 2x2 max-pool.
+ * partial: fp32 scratch of >= unetk_chan_partial_floats(units, C) floats (units = pixels). */
+size_t unetk_chan_partial_floats(int64_t units, int C);
+int unetk_bn_stats(const void* x, int64_t x_ld, int64_t npix, int C, float* partial, double* sums, void* stream);
+int unetk_bn_finalize(const double* sums, int C, double count, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float* scale, float* shift, float* mean, float* invstd, void* stream);
+int unetk_bn_eval_fold(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
+                       const float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                       void* stream);
+int unetk_bn_apply(const void* raw, int64_t raw_ld, const float* scale, const float* shift, void* out,
+                   int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W, int C, int relu,
+                   void* stream);
+/* Backward of out = relu?(bn(raw)).  Incoming gradient = g1 (same resolution; may be NULL) + the scatter of
+ * gp (gradient of the 2x2 max-pool of `out`; may be NULL) through the recomputed argmax (first max wins).
+ *   unetk_bn_bwd_reduce: sums = double[2][C] (sum g, sum g*xhat)      (SyncBN: all-reduce here)
+ *   unetk_bn_bwd_apply : dgamma/dbeta (fp32, optional, accumulate!=0 adds), coef = fp32 scratch [2][C],
+ *                        draw = gradient w.r.t. the raw conv output (bf16 NHWC). count = pixels behind sums. */
+int unetk_bn_bwd_reduce(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp,
+                        int64_t gp_ld, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, float* partial, double* sums, int N, int H, int W, int C, int relu,
+                        void* stream);
+int unetk_bn_bwd_apply(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp,
+                       int64_t gp_ld, const float* scale, const float* shift, const float* mean,
+                       const float* invstd, const double* sums, double count, float* dgamma, float* dbeta,
+                       int accumulate, float* coef, void* draw, int64_t draw_ld, int N, int H, int W, int C,
+                       int relu, void* stream);
+
+/* ---- MaxPool2d(2) standalone (unet_parts.py:43; indices as F.max_pool2d(return_indices=True)) ----
+ * idx (optional) is int64 [N][C][H/2][W/2] holding h*W+w of the selected input element:
+ * first maximum in row-major window order, NaN always taken (last NaN wins) — bit-exact with ATen. */
+int unetk_maxpool2x2_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t* idx, int N, int H, int W,
+                         int C, void* stream);
+int unetk_maxpool2x2_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
+                         int N, int H, int W, int C, void* stream);
+
+/* ---- per-channel column sum (bias gradients of ConvTranspose2d / biased convs) -------------------- */
+int unetk_colsum(const void* x, int64_t x_ld, int64_t npix, int C, float* partial, float* out, int accumulate,
+                 void* stream);
+
+/* ---- segmentation head + loss (unet_parts.py:73-79, train.py:264-278, utils/dice_score.py:13-59) ----
+ * head_fwd : logits[pix] = bias + sum_c x[pix][c]*w[c] (fp32 out).  With labels != NULL also accumulates
+ *            sums = double[4] {sum BCE-with-logits, sum p*y, sum p, sum y}, p = clamp(sigmoid, 1e-7, 1-1e-7).
+ *            (data-parallel ranks all-reduce `sums`: the reference's dice is one ratio over the batch)
+ * loss_finalize: fin = fp32[8] {loss, bce, dice, 1/npix, cA, cB, -, -}; loss = 0.5*bce + 0.5*(1-dice).
+ * head_bwd : dz from (logits, labels, fin) — or from dlogits when the loss was computed outside —
+ *            dx[pix][c] = dz*w[c] (bf16), dw[c] = sum dz*x[pix][c], db = sum dz.  gscale multiplies dz.
+ * C power of two in [8,256]; partial >= unetk_head_partial_floats(npix, C) floats. */
+size_t unetk_head_partial_floats(int64_t npix, int C);
+int unetk_head_fwd(const void* x, int64_t x_ld, const float* w, const float* bias, const float* labels,
+                   float* logits, int64_t npix, int C, float* partial, double* sums, void* stream);
+int unetk_loss_finalize(const double* sums, double npix_total, float* fin, void* stream);
+int unetk_head_bwd(const void* x, int64_t x_ld, const float* w, const float* labels, const float* logits,
+                   const float* fin, const float* dlogits, float gscale, void* dx, int64_t dx_ld, float* dw,
+                   float* db, int accumulate, int64_t npix, int C, float* partial, void* stream);
+
+/* ---- optimizer tail on flat fp32 buffers (train.py:107-112,299-300) -------------------------------
+ * grad_clip_coef: out[0] = gscale*||g||_2, out[1] = gscale*min(1, max_norm/(out[0]+1e-6)); partial >=
+ *                 unetk_sqnorm_partial_floats(n) floats.
+ * rmsprop_step  : torch.optim.RMSprop (momentum, weight decay, not centered); the gradient is first
+ *                 multiplied by clip[1] when clip != NULL. */
+size_t unetk_sqnorm_partial_floats(int64_t n);
+int unetk_grad_clip_coef(const float* g, int64_t n, float gscale, float max_norm, float* partial, float* out,
+                         void* stream);
+int unetk_rmsprop_step(float* p, const float* g, float* square_avg, float* momentum_buf, int64_t n, float lr,
+                       float alpha, float eps, float weight_decay, float momentum, const float* clip,
+                       void* stream);
 
 /* ---- test infrastructure: tcgen05 descriptor-semantics probe (not on the product path) ---------- */
 int unetk_probe_umma(const void* a, const void* b, float* d, int mode, int shift, int base_offset,

@@ -9,6 +9,50 @@ namespace unetk {
 const char* last_error();
 int probe_run(const void* a, const void* b, float* d, int mode, int shift, int bo, cudaStream_t stream);
 int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, cudaStream_t stream);
+// stem.cu
+int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
+                 void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
+size_t stem_wgrad_workspace(int N, int H, int W, int Cin);
+int stem_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy, int64_t dy_ld,
+                   float* dw, int accumulate, int N, int H, int W, int Cin, int Cout, void* ws, size_t ws_bytes,
+                   cudaStream_t s);
+// elementwise.cu
+size_t chan_partial_floats(int64_t units, int C);
+int bn_stats_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, double* sums, cudaStream_t s);
+int bn_finalize_run(const double* sums, int C, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* rm, float* rv, long long* nbt, float* scale, float* shift, float* mean,
+                    float* invstd, cudaStream_t s);
+int bn_eval_fold_run(int C, const float* gamma, const float* beta, float eps, const float* rm, const float* rv,
+                     float* scale, float* shift, float* mean, float* invstd, cudaStream_t s);
+int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, float* out, int accumulate,
+               cudaStream_t s);
+int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const float* shift, void* out, int64_t out_ld,
+                 void* pooled, int64_t pooled_ld, int N, int H, int W, int C, int relu, cudaStream_t s);
+int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long long* idx, int N, int H, int W, int C,
+                    cudaStream_t s);
+int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int N, int H,
+                    int W, int C, cudaStream_t s);
+int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
+                      const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
+                      double* sums, int N, int H, int W, int C, int relu, cudaStream_t s);
+int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
+                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                     const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
+                     void* draw, int64_t draw_ld, int N, int H, int W, int C, int relu, cudaStream_t s);
+// loss.cu
+size_t head_partial_floats(int64_t npix, int C);
+int head_loss_fwd_run(const void* x, int64_t ld, const float* w, const float* bias, const float* labels, float* logits,
+                      int64_t npix, int C, float* partial, double* sums, cudaStream_t s);
+int loss_finalize_run(const double* sums, double npix_total, float* out, cudaStream_t s);
+int head_loss_bwd_run(const void* x, int64_t ld, const float* w, const float* labels, const float* logits,
+                      const float* fin, const float* dlogits, float gscale, void* dx, int64_t dx_ld, float* dw,
+                      float* db, int accumulate, int64_t npix, int C, float* partial, cudaStream_t s);
+// optim.cu
+int sqnorm_blocks(int64_t n);
+int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, float* partial, float* out,
+                       cudaStream_t s);
+int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, float lr, float alpha, float eps, float wd,
+                float momentum, const float* clip, cudaStream_t s);
 }  // namespace unetk
 
 using namespace unetk;
@@ -110,7 +154,6 @@ int unetk_conv1x1_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_
 int unetk_convT2x2_fwd(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y, int64_t y_ld,
                        int N, int H, int W, int Cin, int Cout, void* stream) {
   UNETK_CHECK(x && w_pack && y, -1, "convT2x2_fwd: null pointer");
-  UNETK_CHECK(Cout % 64 == 0, -1, "convT2x2_fwd: Cout=%d must be a multiple of 64", Cout);
   ConvGemmDesc d{};
   d.a = x; d.a_ld = x_ld; d.b = w_pack; d.b_taps = 1; d.out = y; d.out_ld = y_ld; d.bias = bias;
   d.N = N; d.H = H; d.W = W; d.K = Cin; d.ncols = Cout; d.q_groups = 4;
@@ -138,6 +181,116 @@ int unetk_convT2x2_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy
   d.dw = dw; d.accumulate = accumulate;
   d.dw_sm = static_cast<int64_t>(Cout) * 4; d.dw_sn = 4; d.dw_st = 1;
   return wgrad_run(d, workspace, ws_bytes, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ stem
+int unetk_stem_conv3x3_fwd(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w,
+                           const float* bias, void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout,
+                           void* stream) {
+  UNETK_CHECK(x && w && y, -1, "stem_fwd: null pointer");
+  return stem_fwd_run(x, sn, sc, sh, sw, w, bias, y, y_ld, N, H, W, Cin, Cout, S(stream));
+}
+size_t unetk_stem_wgrad_workspace(int N, int H, int W, int Cin) { return stem_wgrad_workspace(N, H, W, Cin); }
+int unetk_stem_conv3x3_wgrad(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy,
+                             int64_t dy_ld, float* dw, int accumulate, int N, int H, int W, int Cin, int Cout,
+                             void* workspace, size_t ws_bytes, void* stream) {
+  UNETK_CHECK(x && dy && dw, -1, "stem_wgrad: null pointer");
+  return stem_wgrad_run(x, sn, sc, sh, sw, dy, dy_ld, dw, accumulate, N, H, W, Cin, Cout, workspace, ws_bytes,
+                        S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ BN / pool
+size_t unetk_chan_partial_floats(int64_t units, int C) {
+  if (C < 8 || C % 8) return 0;
+  return chan_partial_floats(units, C);
+}
+int unetk_bn_stats(const void* x, int64_t x_ld, int64_t npix, int C, float* partial, double* sums, void* stream) {
+  UNETK_CHECK(x && partial && sums && npix > 0, -1, "bn_stats: bad arguments");
+  return bn_stats_run(x, x_ld, npix, C, partial, sums, S(stream));
+}
+int unetk_bn_finalize(const double* sums, int C, double count, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float* scale, float* shift, float* mean, float* invstd, void* stream) {
+  UNETK_CHECK(sums && scale && shift && mean && invstd && count > 0, -1, "bn_finalize: bad arguments");
+  return bn_finalize_run(sums, C, count, gamma, beta, eps, momentum, running_mean, running_var,
+                         reinterpret_cast<long long*>(num_batches_tracked), scale, shift, mean, invstd, S(stream));
+}
+int unetk_bn_eval_fold(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
+                       const float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                       void* stream) {
+  UNETK_CHECK(running_mean && running_var && scale && shift && mean && invstd, -1, "bn_eval_fold: null pointer");
+  return bn_eval_fold_run(C, gamma, beta, eps, running_mean, running_var, scale, shift, mean, invstd, S(stream));
+}
+int unetk_bn_apply(const void* raw, int64_t raw_ld, const float* scale, const float* shift, void* out, int64_t out_ld,
+                   void* pooled, int64_t pooled_ld, int N, int H, int W, int C, int relu, void* stream) {
+  UNETK_CHECK(raw && scale && shift && out, -1, "bn_apply: null pointer");
+  return bn_apply_run(raw, raw_ld, scale, shift, out, out_ld, pooled, pooled_ld, N, H, W, C, relu, S(stream));
+}
+int unetk_bn_bwd_reduce(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
+                        const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
+                        double* sums, int N, int H, int W, int C, int relu, void* stream) {
+  UNETK_CHECK(raw && scale && shift && mean && invstd && partial && sums, -1, "bn_bwd_reduce: null pointer");
+  return bn_bwd_reduce_run(raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, partial, sums, N, H, W, C,
+                           relu, S(stream));
+}
+int unetk_bn_bwd_apply(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
+                       const float* scale, const float* shift, const float* mean, const float* invstd,
+                       const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
+                       void* draw, int64_t draw_ld, int N, int H, int W, int C, int relu, void* stream) {
+  UNETK_CHECK(raw && scale && shift && mean && invstd && sums && coef && draw && count > 0, -1,
+              "bn_bwd_apply: bad arguments");
+  return bn_bwd_apply_run(raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, sums, count, dgamma, dbeta,
+                          accumulate, coef, draw, draw_ld, N, H, W, C, relu, S(stream));
+}
+int unetk_maxpool2x2_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t* idx, int N, int H, int W, int C,
+                         void* stream) {
+  UNETK_CHECK(x && y, -1, "maxpool_fwd: null pointer");
+  return maxpool_fwd_run(x, x_ld, y, y_ld, reinterpret_cast<long long*>(idx), N, H, W, C, S(stream));
+}
+int unetk_maxpool2x2_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int N,
+                         int H, int W, int C, void* stream) {
+  UNETK_CHECK(x && dy && dx, -1, "maxpool_bwd: null pointer");
+  return maxpool_bwd_run(x, x_ld, dy, dy_ld, dx, dx_ld, N, H, W, C, S(stream));
+}
+int unetk_colsum(const void* x, int64_t x_ld, int64_t npix, int C, float* partial, float* out, int accumulate,
+                 void* stream) {
+  UNETK_CHECK(x && partial && out && npix > 0, -1, "colsum: bad arguments");
+  return colsum_run(x, x_ld, npix, C, partial, out, accumulate, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ head / loss
+size_t unetk_head_partial_floats(int64_t npix, int C) {
+  if (C < 8 || C % 8) return 0;
+  return head_partial_floats(npix, C);
+}
+int unetk_head_fwd(const void* x, int64_t x_ld, const float* w, const float* bias, const float* labels, float* logits,
+                   int64_t npix, int C, float* partial, double* sums, void* stream) {
+  UNETK_CHECK(x && w && logits && partial && npix > 0, -1, "head_fwd: bad arguments");
+  return head_loss_fwd_run(x, x_ld, w, bias, labels, logits, npix, C, partial, sums, S(stream));
+}
+int unetk_loss_finalize(const double* sums, double npix_total, float* fin, void* stream) {
+  UNETK_CHECK(sums && fin && npix_total > 0, -1, "loss_finalize: bad arguments");
+  return loss_finalize_run(sums, npix_total, fin, S(stream));
+}
+int unetk_head_bwd(const void* x, int64_t x_ld, const float* w, const float* labels, const float* logits,
+                   const float* fin, const float* dlogits, float gscale, void* dx, int64_t dx_ld, float* dw, float* db,
+                   int accumulate, int64_t npix, int C, float* partial, void* stream) {
+  UNETK_CHECK(x && w && dx && partial && npix > 0, -1, "head_bwd: bad arguments");
+  return head_loss_bwd_run(x, x_ld, w, labels, logits, fin, dlogits, gscale, dx, dx_ld, dw, db, accumulate, npix, C,
+                           partial, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ optimizer
+size_t unetk_sqnorm_partial_floats(int64_t n) { return static_cast<size_t>(sqnorm_blocks(n)); }
+int unetk_grad_clip_coef(const float* g, int64_t n, float gscale, float max_norm, float* partial, float* out,
+                         void* stream) {
+  UNETK_CHECK(g && partial && out && n > 0, -1, "grad_clip_coef: bad arguments");
+  return grad_clip_coef_run(g, n, gscale, max_norm, partial, out, S(stream));
+}
+int unetk_rmsprop_step(float* p, const float* g, float* square_avg, float* momentum_buf, int64_t n, float lr,
+                       float alpha, float eps, float weight_decay, float momentum, const float* clip, void* stream) {
+  UNETK_CHECK(p && g && square_avg && n > 0 && (momentum <= 0.f || momentum_buf), -1, "rmsprop_step: bad arguments");
+  return rmsprop_run(p, g, square_avg, momentum_buf, n, lr, alpha, eps, weight_decay, momentum, clip, S(stream));
 }
 
 int unetk_probe_umma(const void* a, const void* b, float* d, int mode, int shift, int base_offset, void* stream) {

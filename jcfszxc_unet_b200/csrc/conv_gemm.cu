@@ -235,8 +235,8 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   int BN;
   if (d.q_groups > 1) {
     // ConvTranspose fwd: an N tile must not straddle two output phases q.
+    // (a ragged last tile reads the next phase's weight rows; those columns are masked in the epilogue)
     BN = (d.ncols % 256 == 0) ? 256 : (d.ncols % 128 == 0 ? 128 : 64);
-    UNETK_CHECK(d.ncols % BN == 0, -1, "convT: Cout=%d must be a multiple of 64", d.ncols);
   } else {
     BN = d.ncols >= 256 ? 256 : (d.ncols > 64 ? 128 : 64);
   }

@@ -1,0 +1,602 @@
+// HBM-bound kernels of the U-Net step: BatchNorm statistics / finalize / apply(+ReLU)(+MaxPool),
+// their backward (with the max-pool scatter and the skip-gradient add folded in), MaxPool2d(2) with
+// PyTorch-exact argmax, per-channel column sums (bias gradients).
+// All of them stream NHWC bf16 as 16-byte vectors (8 channels per thread), reduce with registers ->
+// shared memory -> per-block partials, and finish with an ordered (deterministic) second stage.
+// Reference semantics replaced: nn.BatchNorm2d + nn.ReLU(inplace) + nn.MaxPool2d(2) inside
+// DoubleConv/Down (UNetFamily/utils/unet_parts.py:24-31,42-44) and their autograd backward.
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace unetk {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stg16(__nv_bfloat16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// Thread layout shared by the per-channel reductions: cg = C/8 channel groups, ppb = kThreads/cg unit lanes.
+struct Lanes {
+  int cg, ppb, g, pl;
+  bool active;
+  __device__ Lanes(int C) {
+    cg = C >> 3;
+    ppb = kThreads / cg;
+    if (ppb < 1) ppb = 1;
+    g = threadIdx.x % cg;
+    pl = threadIdx.x / cg;
+    active = pl < ppb;
+  }
+};
+
+// Sum K*8 per-thread accumulators over the unit lanes of the block and write partial[blockIdx][k][C].
+template <int K>
+__device__ __forceinline__ void block_reduce_store(float (&acc)[K][8], const Lanes& L, int C, float* partial) {
+  extern __shared__ float red[];  // [ppb][K][C]
+  if (L.active) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[(L.pl * K + k) * C + L.g * 8 + j] = acc[k][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * C; i += kThreads) {
+    float s = 0.f;
+    for (int pl = 0; pl < L.ppb; ++pl) s += red[pl * K * C + i];
+    partial[static_cast<size_t>(blockIdx.x) * K * C + i] = s;
+  }
+}
+
+// ------------------------------------------------------------------ forward statistics
+__global__ void __launch_bounds__(kThreads) stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld,
+                                                         int64_t npix, int C, float* __restrict__ partial) {
+  Lanes L(C);
+  float acc[2][8] = {};
+  if (L.active) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+    int64_t pix = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
+    for (; pix + 3 * stride < npix; pix += 4 * stride) {
+      uint4 u[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) u[i] = ldg16(x + (pix + i * stride) * ld + L.g * 8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float f[8];
+        unpack8(u[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] = fmaf(f[j], f[j], acc[1][j]); }
+      }
+    }
+    for (; pix < npix; pix += stride) {
+      float f[8];
+      unpack8(ldg16(x + pix * ld + L.g * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] = fmaf(f[j], f[j], acc[1][j]); }
+    }
+  }
+  block_reduce_store<2>(acc, L, C, partial);
+}
+
+// One thread per channel: ordered sum over the block partials in double, then the BN bookkeeping of
+// nn.BatchNorm2d (biased variance to normalise, unbiased for running_var, momentum 0.1).
+// Ordered (deterministic) second stage: sums[k][c] = sum over block partials, in double.
+__global__ void chan_sums_kernel(const float* __restrict__ partial, int nblk, int C, double* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * C) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[static_cast<size_t>(b) * 2 * C + i];
+  sums[i] = s;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var,
+                                   long long* num_batches_tracked, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+  if (c >= C) return;
+  const double s = sums[c], ss = sums[C + c];
+  const double mean = s / count;
+  double var = ss / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = b - static_cast<float>(mean) * g * invstd;
+  mean_out[c] = static_cast<float>(mean);
+  invstd_out[c] = invstd;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// Eval mode: fold running statistics into (scale, shift).
+__global__ void bn_eval_fold_kernel(int C, const float* gamma, const float* beta, float eps, const float* rm,
+                                    const float* rv, float* scale, float* shift, float* mean_out,
+                                    float* invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.f / sqrtf(rv[c] + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = b - rm[c] * g * invstd;
+  mean_out[c] = rm[c];
+  invstd_out[c] = invstd;
+}
+
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out,
+                                       int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[(static_cast<size_t>(b) * 2 + 0) * C + c];
+  out[c] = accumulate ? out[c] + static_cast<float>(s) : static_cast<float>(s);
+}
+
+// ------------------------------------------------------------------ forward apply
+// act = relu(bf16(raw*scale + shift)); optional fused 2x2 max-pool of act (first-max-wins like ATen).
+__device__ __forceinline__ void bn_relu8(const uint4& raw, const float* sc, const float* sh, float* a, bool relu) {
+  float f[8];
+  unpack8(raw, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
+    a[j] = relu ? fmaxf(z, 0.f) : z;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift,
+                                                            __nv_bfloat16* __restrict__ out, int64_t out_ld,
+                                                            int64_t npix, int C, int relu) {
+  const int cg = C >> 3;
+  const int64_t total = npix * cg;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const int g = static_cast<int>(i % cg);
+    const int64_t pix = i / cg;
+    float sc[8], sh[8], a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
+    bn_relu8(ldg16(raw + pix * raw_ld + g * 8), sc, sh, a, relu != 0);
+    stg16(out + pix * out_ld + g * 8, pack8(a));
+  }
+}
+
+// Window order (0,0),(0,1),(1,0),(1,1); take `v > best || isnan(v)` -> first max wins, last NaN wins.
+__device__ __forceinline__ void argmax4(const float (&a)[4][8], float* best, int* arg) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float b = a[0][j];
+    int k = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      const float v = a[q][j];
+      if (v > b || v != v) { b = v; k = q; }
+    }
+    best[j] = b;
+    arg[j] = k;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld, const float* __restrict__ scale,
+                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int64_t out_ld,
+                     __nv_bfloat16* __restrict__ pooled, int64_t pooled_ld, int N, int H, int W, int C) {
+  const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cg;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const int g = static_cast<int>(i % cg);
+    int64_t t = i / cg;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
+    float a[4][8];
+    uint4 u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t pix = (static_cast<int64_t>(n) * H + 2 * ho + (q >> 1)) * W + 2 * wo + (q & 1);
+      u[q] = ldg16(raw + pix * raw_ld + g * 8);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t pix = (static_cast<int64_t>(n) * H + 2 * ho + (q >> 1)) * W + 2 * wo + (q & 1);
+      bn_relu8(u[q], sc, sh, a[q], true);
+      stg16(out + pix * out_ld + g * 8, pack8(a[q]));
+    }
+    float best[8];
+    int arg[8];
+    argmax4(a, best, arg);
+    const int64_t opix = (static_cast<int64_t>(n) * Ho + ho) * Wo + wo;
+    stg16(pooled + opix * pooled_ld + g * 8, pack8(best));
+  }
+}
+
+// ------------------------------------------------------------------ MaxPool2d(2) standalone
+// idx (optional): int64 NCHW-logical [N,C,Ho,Wo] holding h*W+w, exactly F.max_pool2d(return_indices=True).
+__global__ void __launch_bounds__(kThreads)
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, __nv_bfloat16* __restrict__ y, int64_t y_ld,
+                   long long* __restrict__ idx, int N, int H, int W, int C) {
+  const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cg;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const int g = static_cast<int>(i % cg);
+    int64_t t = i / cg;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float a[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t pix = (static_cast<int64_t>(n) * H + 2 * ho + (q >> 1)) * W + 2 * wo + (q & 1);
+      unpack8(ldg16(x + pix * x_ld + g * 8), a[q]);
+    }
+    float best[8];
+    int arg[8];
+    argmax4(a, best, arg);
+    const int64_t opix = (static_cast<int64_t>(n) * Ho + ho) * Wo + wo;
+    stg16(y + opix * y_ld + g * 8, pack8(best));
+    if (idx != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        idx[((static_cast<int64_t>(n) * C + c) * Ho + ho) * Wo + wo] =
+            static_cast<long long>(2 * ho + (arg[j] >> 1)) * W + 2 * wo + (arg[j] & 1);
+      }
+    }
+  }
+}
+
+// dx[window pos] = (pos == argmax) ? dy : 0, argmax recomputed from x with the forward rule.
+__global__ void __launch_bounds__(kThreads)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, const __nv_bfloat16* __restrict__ dy,
+                   int64_t dy_ld, __nv_bfloat16* __restrict__ dx, int64_t dx_ld, int N, int H, int W, int C) {
+  const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cg;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const int g = static_cast<int>(i % cg);
+    int64_t t = i / cg;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float a[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t pix = (static_cast<int64_t>(n) * H + 2 * ho + (q >> 1)) * W + 2 * wo + (q & 1);
+      unpack8(ldg16(x + pix * x_ld + g * 8), a[q]);
+    }
+    float best[8], gy[8];
+    int arg[8];
+    argmax4(a, best, arg);
+    const int64_t opix = (static_cast<int64_t>(n) * Ho + ho) * Wo + wo;
+    unpack8(ldg16(dy + opix * dy_ld + g * 8), gy);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t pix = (static_cast<int64_t>(n) * H + 2 * ho + (q >> 1)) * W + 2 * wo + (q & 1);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (arg[j] == q) ? gy[j] : 0.f;
+      stg16(dx + pix * dx_ld + g * 8, pack8(o));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward of BN(+ReLU)(+pool,+skip add)
+// Incoming gradient of the activation a = relu(bn(raw)):   g = g1 (same resolution, optional)
+//                                                            + scatter(gp) through the 2x2 max-pool (optional).
+// Unit of work: one 2x2 window x 8 channels when gp is given, else one pixel x 8 channels.
+struct BnBwdArgs {
+  const __nv_bfloat16* raw; int64_t raw_ld;
+  const __nv_bfloat16* g1; int64_t g1_ld;   // may be null
+  const __nv_bfloat16* gp; int64_t gp_ld;   // may be null (pooled-resolution gradient)
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  int N, H, W, C, relu;
+};
+
+// Loads one unit; returns masked gradients gm[q][8] and xhat[q][8] for nq pixels.
+template <bool POOL>
+__device__ __forceinline__ void bn_bwd_unit(const BnBwdArgs& A, int n, int hu, int wu, int g, float (&gm)[POOL ? 4 : 1][8],
+                                            float (&xh)[POOL ? 4 : 1][8], int64_t (&pixs)[POOL ? 4 : 1]) {
+  constexpr int NQ = POOL ? 4 : 1;
+  float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(A.scale + g * 8 + j); sh[j] = __ldg(A.shift + g * 8 + j);
+    mu[j] = __ldg(A.mean + g * 8 + j); is[j] = __ldg(A.invstd + g * 8 + j);
+  }
+  uint4 ur[NQ], ug[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int h = POOL ? 2 * hu + (q >> 1) : hu, w = POOL ? 2 * wu + (q & 1) : wu;
+    pixs[q] = (static_cast<int64_t>(n) * A.H + h) * A.W + w;
+    ur[q] = ldg16(A.raw + pixs[q] * A.raw_ld + g * 8);
+    ug[q] = A.g1 ? ldg16(A.g1 + pixs[q] * A.g1_ld + g * 8) : make_uint4(0, 0, 0, 0);
+  }
+  float r[NQ][8], a[NQ][8];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    unpack8(ur[q], r[q]);
+    unpack8(ug[q], gm[q]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = bf16_round(fmaf(r[q][j], sc[j], sh[j]));
+      a[q][j] = A.relu ? fmaxf(z, 0.f) : z;
+      xh[q][j] = (r[q][j] - mu[j]) * is[j];
+    }
+  }
+  if constexpr (POOL) {
+    float best[8], gy[8];
+    int arg[8];
+    argmax4(a, best, arg);
+    const int64_t opix = (static_cast<int64_t>(n) * (A.H >> 1) + hu) * (A.W >> 1) + wu;
+    unpack8(ldg16(A.gp + opix * A.gp_ld + g * 8), gy);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (arg[j] == q) gm[q][j] += gy[j];
+  }
+  if (A.relu) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!(a[q][j] > 0.f)) gm[q][j] = 0.f;
+  }
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BnBwdArgs A, float* __restrict__ partial) {
+  Lanes L(A.C);
+  const int Hu = POOL ? A.H >> 1 : A.H, Wu = POOL ? A.W >> 1 : A.W;
+  const int64_t units = static_cast<int64_t>(A.N) * Hu * Wu;
+  float acc[2][8] = {};
+  if (L.active) {
+    for (int64_t u = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl; u < units;
+         u += static_cast<int64_t>(gridDim.x) * L.ppb) {
+      const int wu = static_cast<int>(u % Wu);
+      const int hu = static_cast<int>((u / Wu) % Hu);
+      const int n = static_cast<int>(u / (static_cast<int64_t>(Wu) * Hu));
+      float gm[POOL ? 4 : 1][8], xh[POOL ? 4 : 1][8];
+      int64_t pixs[POOL ? 4 : 1];
+      bn_bwd_unit<POOL>(A, n, hu, wu, L.g, gm, xh, pixs);
+#pragma unroll
+      for (int q = 0; q < (POOL ? 4 : 1); ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[0][j] += gm[q][j]; acc[1][j] = fmaf(gm[q][j], xh[q][j], acc[1][j]); }
+    }
+  }
+  block_reduce_store<2>(acc, L, A.C, partial);
+}
+
+// dbeta = sum gm, dgamma = sum gm*xhat; coef[0][c] = dbeta/M, coef[1][c] = dgamma/M (used by the apply pass).
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int C, double count, float* dgamma,
+                                       float* dbeta, int accumulate, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s = sums[c], sx = sums[C + c];
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(s) : static_cast<float>(s);
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(sx) : static_cast<float>(sx);
+  coef[c] = static_cast<float>(s / count);
+  coef[C + c] = static_cast<float>(sx / count);
+}
+
+// draw = scale * (gm - dbeta/M - xhat * dgamma/M)      (scale = gamma * invstd)
+template <bool POOL>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_kernel(const BnBwdArgs A, const float* __restrict__ coef, __nv_bfloat16* __restrict__ draw,
+                    int64_t draw_ld) {
+  const int cg = A.C >> 3;
+  const int Hu = POOL ? A.H >> 1 : A.H, Wu = POOL ? A.W >> 1 : A.W;
+  const int64_t total = static_cast<int64_t>(A.N) * Hu * Wu * cg;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const int g = static_cast<int>(i % cg);
+    int64_t u = i / cg;
+    const int wu = static_cast<int>(u % Wu);
+    const int hu = static_cast<int>((u / Wu) % Hu);
+    const int n = static_cast<int>(u / (static_cast<int64_t>(Wu) * Hu));
+    float gm[POOL ? 4 : 1][8], xh[POOL ? 4 : 1][8];
+    int64_t pixs[POOL ? 4 : 1];
+    bn_bwd_unit<POOL>(A, n, hu, wu, g, gm, xh, pixs);
+    float sc[8], cb[8], cgm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(A.scale + g * 8 + j);
+      cb[j] = __ldg(coef + g * 8 + j);
+      cgm[j] = __ldg(coef + A.C + g * 8 + j);
+    }
+#pragma unroll
+    for (int q = 0; q < (POOL ? 4 : 1); ++q) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = sc[j] * (gm[q][j] - cb[j] - xh[q][j] * cgm[j]);
+      stg16(draw + pixs[q] * draw_ld + g * 8, pack8(o));
+    }
+  }
+}
+
+int reduce_grid(int64_t units, int C) {
+  const int cg = C / 8;
+  int ppb = kThreads / cg;
+  if (ppb < 1) ppb = 1;
+  int64_t want = (units + ppb * 8 - 1) / (ppb * 8);  // >= 8 units per lane
+  int64_t cap = static_cast<int64_t>(num_sms()) * 4;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+size_t reduce_smem(int C, int K) {
+  const int cg = C / 8;
+  int ppb = kThreads / cg;
+  if (ppb < 1) ppb = 1;
+  return static_cast<size_t>(ppb) * K * C * sizeof(float);
+}
+int flat_grid(int64_t total) {
+  int64_t b = (total + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- host side
+#define CHECK_C(C) UNETK_CHECK((C) % 8 == 0 && (C) >= 8 && (C) <= 2048, -1, "channel count %d must be a multiple of 8 in [8,2048]", (C))
+
+size_t chan_partial_floats(int64_t units, int C) { return static_cast<size_t>(reduce_grid(units, C)) * 2 * C; }
+
+static int launch_sums(const float* partial, int nblk, int C, double* sums, cudaStream_t s) {
+  chan_sums_kernel<<<(2 * C + 127) / 128, 128, 0, s>>>(partial, nblk, C, sums);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// sums (double [2][C]): per-channel sum and sum of squares over npix pixels
+int bn_stats_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, double* sums, cudaStream_t s) {
+  CHECK_C(C);
+  const int grid = reduce_grid(npix, C);
+  stats_kernel<<<grid, kThreads, reduce_smem(C, 2), s>>>(static_cast<const __nv_bfloat16*>(x), ld, npix, C, partial);
+  UNETK_CUDA(cudaGetLastError());
+  return launch_sums(partial, grid, C, sums, s);
+}
+
+int bn_finalize_run(const double* sums, int C, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* rm, float* rv, long long* nbt, float* scale, float* shift, float* mean,
+                    float* invstd, cudaStream_t s) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, gamma, beta, eps, momentum, rm, rv, nbt, scale,
+                                                    shift, mean, invstd);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bn_eval_fold_run(int C, const float* gamma, const float* beta, float eps, const float* rm, const float* rv,
+                     float* scale, float* shift, float* mean, float* invstd, cudaStream_t s) {
+  bn_eval_fold_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, gamma, beta, eps, rm, rv, scale, shift, mean, invstd);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, float* out, int accumulate,
+               cudaStream_t s) {
+  CHECK_C(C);
+  const int grid = reduce_grid(npix, C);
+  stats_kernel<<<grid, kThreads, reduce_smem(C, 2), s>>>(static_cast<const __nv_bfloat16*>(x), ld, npix, C, partial);
+  UNETK_CUDA(cudaGetLastError());
+  colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, grid, C, out, accumulate);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const float* shift, void* out, int64_t out_ld,
+                 void* pooled, int64_t pooled_ld, int N, int H, int W, int C, int relu, cudaStream_t s) {
+  CHECK_C(C);
+  if (pooled != nullptr) {
+    UNETK_CHECK(H % 2 == 0 && W % 2 == 0 && relu, -1, "fused pool needs even H,W and relu");
+    const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
+    bn_apply_pool_kernel<<<flat_grid(total), kThreads, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift, static_cast<__nv_bfloat16*>(out), out_ld,
+        static_cast<__nv_bfloat16*>(pooled), pooled_ld, N, H, W, C);
+  } else {
+    const int64_t npix = static_cast<int64_t>(N) * H * W;
+    bn_apply_kernel<<<flat_grid(npix * (C / 8)), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(raw), raw_ld,
+                                                                  scale, shift, static_cast<__nv_bfloat16*>(out),
+                                                                  out_ld, npix, C, relu);
+  }
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long long* idx, int N, int H, int W, int C,
+                    cudaStream_t s) {
+  CHECK_C(C);
+  const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
+  if (total == 0) return 0;
+  maxpool_fwd_kernel<<<flat_grid(total), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
+                                                          static_cast<__nv_bfloat16*>(y), y_ld, idx, N, H, W, C);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int N, int H,
+                    int W, int C, cudaStream_t s) {
+  CHECK_C(C);
+  UNETK_CHECK(H % 2 == 0 && W % 2 == 0, -1, "maxpool_bwd: odd spatial size %dx%d not supported", H, W);
+  const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
+  maxpool_bwd_kernel<<<flat_grid(total), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
+                                                          static_cast<const __nv_bfloat16*>(dy), dy_ld,
+                                                          static_cast<__nv_bfloat16*>(dx), dx_ld, N, H, W, C);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int bn_bwd_args(BnBwdArgs* A, const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp,
+                       int64_t gp_ld, const float* scale, const float* shift, const float* mean, const float* invstd,
+                       int N, int H, int W, int C, int relu) {
+  CHECK_C(C);
+  UNETK_CHECK(g1 != nullptr || gp != nullptr, -1, "bn_bwd: no incoming gradient");
+  if (gp != nullptr) UNETK_CHECK(H % 2 == 0 && W % 2 == 0, -1, "bn_bwd: pooled gradient needs even H,W");
+  *A = BnBwdArgs{static_cast<const __nv_bfloat16*>(raw), raw_ld, static_cast<const __nv_bfloat16*>(g1), g1_ld,
+                 static_cast<const __nv_bfloat16*>(gp), gp_ld, scale, shift, mean, invstd, N, H, W, C, relu};
+  return 0;
+}
+
+// sums (double [2][C]): sum of masked gradient, sum of masked gradient * xhat
+int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
+                      const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
+                      double* sums, int N, int H, int W, int C, int relu, cudaStream_t s) {
+  BnBwdArgs A;
+  if (int rc = bn_bwd_args(&A, raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, N, H, W, C, relu)) return rc;
+  const bool pool = gp != nullptr;
+  const int64_t units = pool ? static_cast<int64_t>(N) * (H / 2) * (W / 2) : static_cast<int64_t>(N) * H * W;
+  const int grid = reduce_grid(units, C);
+  const size_t smem = reduce_smem(C, 2);
+  if (pool) bn_bwd_reduce_kernel<true><<<grid, kThreads, smem, s>>>(A, partial);
+  else bn_bwd_reduce_kernel<false><<<grid, kThreads, smem, s>>>(A, partial);
+  UNETK_CUDA(cudaGetLastError());
+  return launch_sums(partial, grid, C, sums, s);
+}
+
+int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
+                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                     const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
+                     void* draw, int64_t draw_ld, int N, int H, int W, int C, int relu, cudaStream_t s) {
+  BnBwdArgs A;
+  if (int rc = bn_bwd_args(&A, raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, N, H, W, C, relu)) return rc;
+  const bool pool = gp != nullptr;
+  const int64_t units = pool ? static_cast<int64_t>(N) * (H / 2) * (W / 2) : static_cast<int64_t>(N) * H * W;
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, dgamma, dbeta, accumulate, coef);
+  UNETK_CUDA(cudaGetLastError());
+  const int fg = flat_grid(units * (C / 8));
+  if (pool) bn_bwd_apply_kernel<true><<<fg, kThreads, 0, s>>>(A, coef, static_cast<__nv_bfloat16*>(draw), draw_ld);
+  else bn_bwd_apply_kernel<false><<<fg, kThreads, 0, s>>>(A, coef, static_cast<__nv_bfloat16*>(draw), draw_ld);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace unetk

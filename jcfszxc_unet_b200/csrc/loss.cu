@@ -1,0 +1,221 @@
+// Segmentation head + loss, fused: OutConv (1x1, C -> 1, bias) + sigmoid + BCEWithLogits + dice sums in
+// ONE pass over the last activation (132 B/pixel at C = 64), and the matching backward that rebuilds
+// dL/dlogit from (logit, label, global sums) and emits the activation gradient plus dW/db partials.
+// Reference semantics replaced: OutConv.forward (UNetFamily/utils/unet_parts.py:73-79),
+// train.py:264-278 (sigmoid, BCEWithLogitsLoss, dice_loss, alpha = 0.5) and utils/dice_score.py:13-59.
+// The three dice sums are produced separately from the finalize step so that data-parallel ranks can
+// all-reduce them (the reference's dice is ONE ratio over the whole batch).
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace unetk {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kClampLo = 1e-7f, kClampHi = 1.0f - 1e-7f;  // dice_loss clamp, dice_score.py:56
+constexpr double kDiceEps = 1e-5;                            // dice_score.py:32
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+__device__ __forceinline__ float group_sum(float v, int lpp) {
+  for (int o = lpp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sums layout (double[4]): 0 = sum bce, 1 = sum p*y, 2 = sum p, 3 = sum y      (p clamped to [1e-7, 1-1e-7])
+__global__ void __launch_bounds__(kThreads)
+head_loss_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ w,
+                     const float* __restrict__ bias, const float* __restrict__ labels, float* __restrict__ logits,
+                     int64_t npix, int C, float* __restrict__ partial) {
+  const int lpp = C >> 3;                 // lanes per pixel (power of two <= 32)
+  const int gpb = kThreads / lpp;         // pixel groups per block
+  const int sub = threadIdx.x % lpp, grp = threadIdx.x / lpp;
+  float wv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wv[j] = __ldg(w + sub * 8 + j);
+  const float b = bias ? __ldg(bias) : 0.f;
+  float s_bce = 0.f, s_py = 0.f, s_p = 0.f, s_y = 0.f;
+  // uniform trip count per warp: all lanes of a pixel group iterate together
+  for (int64_t pix0 = static_cast<int64_t>(blockIdx.x) * gpb; pix0 < npix; pix0 += static_cast<int64_t>(gridDim.x) * gpb) {
+    const int64_t pix = pix0 + grp;
+    float dot = 0.f;
+    if (pix < npix) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * ld + sub * 8)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot = fmaf(f[j], wv[j], dot);
+    }
+    dot = group_sum(dot, lpp);
+    if (sub == 0 && pix < npix) {
+      const float z = dot + b;
+      logits[pix] = z;
+      if (labels != nullptr) {
+        const float y = __ldg(labels + pix);
+        s_bce += fmaxf(z, 0.f) - z * y + log1pf(__expf(-fabsf(z)));
+        float p = 1.f / (1.f + __expf(-z));
+        p = fminf(fmaxf(p, kClampLo), kClampHi);
+        s_py = fmaf(p, y, s_py);
+        s_p += p;
+        s_y += y;
+      }
+    }
+  }
+  __shared__ float red[4][kThreads / 32];
+  s_bce = warp_sum(s_bce); s_py = warp_sum(s_py); s_p = warp_sum(s_p); s_y = warp_sum(s_y);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = s_bce; red[1][warp] = s_py; red[2][warp] = s_p; red[3][warp] = s_y; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) s += red[threadIdx.x][i];
+    partial[static_cast<size_t>(blockIdx.x) * 4 + threadIdx.x] = s;
+  }
+}
+
+__global__ void loss_sums_kernel(const float* __restrict__ partial, int nblk, double* __restrict__ sums) {
+  const int k = threadIdx.x;
+  if (k >= 4) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[static_cast<size_t>(b) * 4 + k];
+  sums[k] = s;
+}
+
+// out[0]=loss out[1]=bce out[2]=dice out[3]=1/npix  out[4]=cA out[5]=cB  (d dice / d p_i = y_i*cA - cB)
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, double npix_total, float* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  const double bce = sums[0] / npix_total;
+  const double inter = 2.0 * sums[1];
+  double sets = sums[2] + sums[3];
+  double cA, cB;
+  if (sets < kDiceEps) {  // empty-mask branch (dice_score.py:35): sets_sum := inter -> dice == 1, zero gradient
+    sets = inter;
+    cA = 0.0; cB = 0.0;
+  } else {
+    cA = 2.0 / (sets + kDiceEps);
+    cB = (inter + kDiceEps) / ((sets + kDiceEps) * (sets + kDiceEps));
+  }
+  const double dice = (inter + kDiceEps) / (sets + kDiceEps);
+  out[0] = static_cast<float>(0.5 * bce + 0.5 * (1.0 - dice));
+  out[1] = static_cast<float>(bce);
+  out[2] = static_cast<float>(dice);
+  out[3] = static_cast<float>(1.0 / npix_total);
+  out[4] = static_cast<float>(cA);
+  out[5] = static_cast<float>(cB);
+}
+
+// dz = gscale * [ 0.5 * (sigmoid(z) - y) / Npix  -  0.5 * (y*cA - cB) * p(1-p) * 1[clamp inactive] ]
+// dx[pix][c] = dz * w[c];  partial[blk][c] = sum dz * x[pix][c];  partial[blk][C] = sum dz
+__global__ void __launch_bounds__(kThreads)
+head_loss_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ w,
+                     const float* __restrict__ labels, const float* __restrict__ logits,
+                     const float* __restrict__ fin, const float* __restrict__ dlogits, float gscale,
+                     __nv_bfloat16* __restrict__ dx, int64_t dx_ld, int64_t npix, int C,
+                     float* __restrict__ partial) {
+  const int lpp = C >> 3;
+  const int gpb = kThreads / lpp;
+  const int sub = threadIdx.x % lpp, grp = threadIdx.x / lpp;
+  float wv[8], acc[8] = {};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wv[j] = __ldg(w + sub * 8 + j);
+  float inv_n = 0.f, cA = 0.f, cB = 0.f;
+  if (dlogits == nullptr) { inv_n = __ldg(fin + 3); cA = __ldg(fin + 4); cB = __ldg(fin + 5); }
+  float s_dz = 0.f;
+  for (int64_t pix = static_cast<int64_t>(blockIdx.x) * gpb + grp; pix < npix; pix += static_cast<int64_t>(gridDim.x) * gpb) {
+    float dz;
+    if (dlogits != nullptr) {  // gradient handed in by autograd (loss computed outside the library)
+      dz = gscale * __ldg(dlogits + pix);
+    } else {
+      const float z = __ldg(logits + pix), y = __ldg(labels + pix);
+      const float p = 1.f / (1.f + __expf(-z));
+      const float inside = (p >= kClampLo && p <= kClampHi) ? 1.f : 0.f;
+      dz = gscale * (0.5f * inv_n * (p - y) - 0.5f * (y * cA - cB) * p * (1.f - p) * inside);
+    }
+    float f[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * ld + sub * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j] = fmaf(dz, f[j], acc[j]); o[j] = dz * wv[j]; }
+    uint4 u;
+    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+    u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(dx + pix * dx_ld + sub * 8) = u;
+    if (sub == 0) s_dz += dz;
+  }
+  extern __shared__ float red[];  // [gpb][C + 1]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[grp * (C + 1) + sub * 8 + j] = acc[j];
+  if (sub == 0) red[grp * (C + 1) + C] = s_dz;
+  __syncthreads();
+  for (int i = threadIdx.x; i <= C; i += kThreads) {
+    float s = 0.f;
+    for (int g = 0; g < gpb; ++g) s += red[g * (C + 1) + i];
+    partial[static_cast<size_t>(blockIdx.x) * (C + 1) + i] = s;
+  }
+}
+
+__global__ void head_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* dw, float* db,
+                                         int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > C) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[static_cast<size_t>(b) * (C + 1) + i];
+  float* o = (i < C) ? dw + i : db;
+  if (o) *o = accumulate ? *o + static_cast<float>(s) : static_cast<float>(s);
+}
+
+int head_grid(int64_t npix, int C) {
+  const int gpb = kThreads / (C / 8);
+  int64_t b = (npix + gpb * 8 - 1) / (gpb * 8);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 4;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+bool head_c_ok(int C) { return C == 8 || C == 16 || C == 32 || C == 64 || C == 128 || C == 256; }
+
+}  // namespace
+
+size_t head_partial_floats(int64_t npix, int C) { return static_cast<size_t>(head_grid(npix, C)) * (C + 1 > 4 ? C + 1 : 4); }
+
+int head_loss_fwd_run(const void* x, int64_t ld, const float* w, const float* bias, const float* labels, float* logits,
+                      int64_t npix, int C, float* partial, double* sums, cudaStream_t s) {
+  UNETK_CHECK(head_c_ok(C), -1, "head: C=%d must be a power of two in [8,256]", C);
+  const int grid = head_grid(npix, C);
+  head_loss_fwd_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, w, bias, labels, logits, npix,
+                                                C, partial);
+  UNETK_CUDA(cudaGetLastError());
+  if (labels != nullptr) {
+    UNETK_CHECK(sums != nullptr, -1, "head_loss_fwd: sums is null");
+    loss_sums_kernel<<<1, 32, 0, s>>>(partial, grid, sums);
+    UNETK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int loss_finalize_run(const double* sums, double npix_total, float* out, cudaStream_t s) {
+  loss_finalize_kernel<<<1, 32, 0, s>>>(sums, npix_total, out);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int head_loss_bwd_run(const void* x, int64_t ld, const float* w, const float* labels, const float* logits,
+                      const float* fin, const float* dlogits, float gscale, void* dx, int64_t dx_ld, float* dw,
+                      float* db, int accumulate, int64_t npix, int C, float* partial, cudaStream_t s) {
+  UNETK_CHECK(dlogits != nullptr || (labels && logits && fin), -1, "head_bwd: need dlogits or (labels, logits, fin)");
+  UNETK_CHECK(head_c_ok(C), -1, "head: C=%d must be a power of two in [8,256]", C);
+  const int grid = head_grid(npix, C);
+  const int gpb = kThreads / (C / 8);
+  const size_t smem = static_cast<size_t>(gpb) * (C + 1) * sizeof(float);
+  head_loss_bwd_kernel<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(x), ld, w, labels, logits, fin,
+                                                   dlogits, gscale, static_cast<__nv_bfloat16*>(dx), dx_ld, npix, C,
+                                                   partial);
+  UNETK_CUDA(cudaGetLastError());
+  head_bwd_finalize_kernel<<<(C + 1 + 127) / 128, 128, 0, s>>>(partial, grid, C, dw, db, accumulate);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace unetk

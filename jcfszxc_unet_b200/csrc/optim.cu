@@ -1,0 +1,104 @@
+// Optimizer tail over FLAT fp32 buffers (all parameters / gradients / RMSprop state are views into
+// four contiguous arrays): global-norm clip + RMSprop with momentum in two passes.
+// Reference semantics replaced: torch.nn.utils.clip_grad_norm_(params, 1.0) and optim.RMSprop.step
+// (train.py:107-112,299-300; alpha = 0.99, eps = 1e-8 are the torch defaults the reference relies on).
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace unetk {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) sqnorm_kernel(const float* __restrict__ g, int64_t n,
+                                                          float* __restrict__ partial) {
+  float s = 0.f;
+  const int64_t n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const float4 v = __ldg(g4 + i);
+    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[(n4 << 2) + threadIdx.x]; s = fmaf(v, v, s); }
+  __shared__ float red[kThreads / 32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) t += red[i];
+    partial[blockIdx.x] = t;
+  }
+}
+
+// out[0] = total L2 norm, out[1] = clip coefficient min(1, max_norm / (norm + 1e-6)); gscale pre-multiplies
+// the gradient (1/world_size after a sum all-reduce).
+__global__ void clip_finalize_kernel(const float* __restrict__ partial, int nblk, float gscale, float max_norm,
+                                     float* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[b];
+  const float norm = static_cast<float>(sqrt(s)) * gscale;
+  float coef = max_norm / (norm + 1e-6f);
+  if (coef > 1.f) coef = 1.f;
+  out[0] = norm;
+  out[1] = coef * gscale;
+}
+
+__global__ void __launch_bounds__(kThreads)
+rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq, float* __restrict__ buf,
+               int64_t n, float lr, float alpha, float eps, float wd, float momentum,
+               const float* __restrict__ clip) {
+  const float coef = clip ? __ldg(clip + 1) : 1.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    float pv = p[i];
+    const float gv = fmaf(wd, pv, g[i] * coef);
+    const float s = fmaf(1.f - alpha, gv * gv, alpha * sq[i]);
+    sq[i] = s;
+    const float avg = sqrtf(s) + eps;
+    float step = gv / avg;
+    if (momentum > 0.f) {
+      const float b = fmaf(momentum, buf[i], step);
+      buf[i] = b;
+      step = b;
+    }
+    p[i] = fmaf(-lr, step, pv);
+  }
+}
+
+}  // namespace
+
+int sqnorm_blocks(int64_t n) {
+  int64_t b = (n / 4 + kThreads * 4 - 1) / (kThreads * 4);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 4;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, float* partial, float* out,
+                       cudaStream_t s) {
+  UNETK_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, -1, "grad buffer must be 16-byte aligned");
+  const int nb = sqnorm_blocks(n);
+  sqnorm_kernel<<<nb, kThreads, 0, s>>>(g, n, partial);
+  UNETK_CUDA(cudaGetLastError());
+  clip_finalize_kernel<<<1, 32, 0, s>>>(partial, nb, gscale, max_norm, out);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, float lr, float alpha, float eps, float wd,
+                float momentum, const float* clip, cudaStream_t s) {
+  int64_t b = (n + kThreads * 4 - 1) / (kThreads * 4);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  rmsprop_kernel<<<static_cast<int>(b), kThreads, 0, s>>>(p, g, sq, buf, n, lr, alpha, eps, wd, momentum, clip);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace unetk

@@ -1,0 +1,193 @@
+// Stem convolution: the network-input conv (Cin <= 4, e.g. 3 -> 64) is flatly HBM-bound
+// (27 FLOP/B) and its K = 27 cannot feed a 128B TMA row, so it runs as a direct
+// CUDA-core kernel that reads the fp32 image in whatever strides the caller has (NCHW or channels_last),
+// applies the same bf16 rounding autocast would, and writes NHWC bf16.  Its weight gradient is the matching
+// direct reduction.  No input gradient is needed (the image is a leaf).
+// Reference semantics replaced: the first nn.Conv2d of DoubleConv `inc` (UNetFamily/UNet.py:21,
+// unet_parts.py:24) and its weight gradient.
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace unetk {
+
+namespace {
+
+constexpr int kTH = 4, kTW = 32;  // 128 pixels per tile
+
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+struct StemGeom {
+  const float* x; int64_t sn, sc, sh, sw;  // fp32 image, element strides
+  int N, H, W, Cin, Cout;
+};
+
+// stage the (kTH+2) x (kTW+2) x Cin halo of tile (n, h0, w0) into smem as bf16-rounded floats
+__device__ __forceinline__ void load_halo(const StemGeom& G, int n, int h0, int w0, float* sx) {
+  const int per = (kTH + 2) * (kTW + 2);
+  for (int i = threadIdx.x; i < per * G.Cin; i += blockDim.x) {
+    const int ci = i / per, r = (i % per) / (kTW + 2), c = i % (kTW + 2);
+    const int h = h0 + r - 1, w = w0 + c - 1;
+    float v = 0.f;
+    if (h >= 0 && h < G.H && w >= 0 && w < G.W) v = bf16r(__ldg(G.x + n * G.sn + ci * G.sc + h * G.sh + w * G.sw));
+    sx[(r * (kTW + 2) + c) * 4 + ci] = v;
+  }
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(128) stem_fwd_kernel(const StemGeom G, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                       int64_t y_ld, int tiles_h, int tiles_w) {
+  __shared__ float sx[(kTH + 2) * (kTW + 2) * 4];
+  __shared__ __align__(16) float sw[36 * COUT];  // [k = (ci*3+r)*3+s][co], bf16-rounded
+  for (int i = threadIdx.x; i < 9 * G.Cin * COUT; i += blockDim.x) {
+    const int k = i / COUT, co = i % COUT;  // k = ci*9 + r*3 + s
+    sw[i] = co < G.Cout ? bf16r(__ldg(w + static_cast<int64_t>(co) * G.Cin * 9 + k)) : 0.f;
+  }
+  const int num_tiles = G.N * tiles_h * tiles_w;
+  const int py = threadIdx.x / kTW, px = threadIdx.x % kTW;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int h0 = th * kTH, w0 = tw * kTW;
+    __syncthreads();
+    load_halo(G, n, h0, w0, sx);
+    __syncthreads();
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    for (int ci = 0; ci < G.Cin; ++ci) {
+#pragma unroll
+      for (int rs = 0; rs < 9; ++rs) {
+        const float xv = sx[((py + rs / 3) * (kTW + 2) + px + rs % 3) * 4 + ci];
+        const float4* wr = reinterpret_cast<const float4*>(sw + (ci * 9 + rs) * COUT);
+#pragma unroll
+        for (int c4 = 0; c4 < COUT / 4; ++c4) {
+          const float4 wv = wr[c4];
+          acc[c4 * 4 + 0] = fmaf(xv, wv.x, acc[c4 * 4 + 0]);
+          acc[c4 * 4 + 1] = fmaf(xv, wv.y, acc[c4 * 4 + 1]);
+          acc[c4 * 4 + 2] = fmaf(xv, wv.z, acc[c4 * 4 + 2]);
+          acc[c4 * 4 + 3] = fmaf(xv, wv.w, acc[c4 * 4 + 3]);
+        }
+      }
+    }
+    const int h = h0 + py, wq = w0 + px;
+    if (h < G.H && wq < G.W) {
+      __nv_bfloat16* o = y + ((static_cast<int64_t>(n) * G.H + h) * G.W + wq) * y_ld;
+#pragma unroll
+      for (int c8 = 0; c8 < COUT / 8; ++c8) {
+        if (c8 * 8 < G.Cout) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = acc[c8 * 8 + j] + (bias ? __ldg(bias + c8 * 8 + j) : 0.f);
+          uint4 u;
+          u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+          u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(o + c8 * 8) = u;
+        }
+      }
+    }
+  }
+}
+
+// partial[blk][co][k] = sum over the block's tiles of dy[p][co] * x[p + off(k)][ci(k)],  k = ci*9 + r*3 + s
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const StemGeom G, const __nv_bfloat16* __restrict__ dy,
+                                                         int64_t dy_ld, float* __restrict__ partial, int tiles_h,
+                                                         int tiles_w) {
+  __shared__ float sx[(kTH + 2) * (kTW + 2) * 4];
+  __shared__ float sg[kTH * kTW][64 + 1];
+  const int K = 9 * G.Cin;
+  const int co = threadIdx.x & 63, part = threadIdx.x >> 6;  // 4 parts share the K taps round-robin
+  float acc[9];                                                // ceil(36/4)
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+  const int num_tiles = G.N * tiles_h * tiles_w;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int h0 = th * kTH, w0 = tw * kTW;
+    __syncthreads();
+    load_halo(G, n, h0, w0, sx);
+    for (int i = threadIdx.x; i < kTH * kTW * 64; i += blockDim.x) {
+      const int p = i >> 6, c = i & 63;
+      const int h = h0 + p / kTW, w = w0 + p % kTW;
+      float v = 0.f;
+      if (c < G.Cout && h < G.H && w < G.W)
+        v = __bfloat162float(dy[((static_cast<int64_t>(n) * G.H + h) * G.W + w) * dy_ld + c]);
+      sg[p][c] = v;
+    }
+    __syncthreads();
+    for (int p = 0; p < kTH * kTW; ++p) {
+      const float gv = sg[p][co];
+      const int py = p / kTW, px = p % kTW;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int k = part + 4 * i;
+        if (k < K) {
+          const int ci = k / 9, rs = k % 9;
+          acc[i] = fmaf(gv, sx[((py + rs / 3) * (kTW + 2) + px + rs % 3) * 4 + ci], acc[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int k = part + 4 * i;
+    if (k < K) partial[(static_cast<size_t>(blockIdx.x) * 64 + co) * K + k] = acc[i];
+  }
+}
+
+__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int Cout, int K,
+                                         float* __restrict__ dw, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * K) return;
+  const int co = i / K, k = i % K;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[(static_cast<size_t>(b) * 64 + co) * K + k];
+  dw[i] = accumulate ? dw[i] + static_cast<float>(s) : static_cast<float>(s);
+}
+
+}  // namespace
+
+int stem_grid(int N, int H, int W) {
+  const int tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+  const int cap = 2 * num_sms();
+  return tiles < cap ? tiles : cap;
+}
+
+int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
+                 void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s) {
+  UNETK_CHECK(Cin >= 1 && Cin <= 4, -1, "stem: Cin=%d must be <= 4", Cin);
+  UNETK_CHECK(Cout % 8 == 0 && Cout <= 64, -1, "stem: Cout=%d must be a multiple of 8 and <= 64", Cout);
+  StemGeom G{x, sn, sc, sh, sw, N, H, W, Cin, Cout};
+  const int th = (H + kTH - 1) / kTH, tw = (W + kTW - 1) / kTW;
+  const int grid = N * th * tw < 8 * num_sms() ? N * th * tw : 8 * num_sms();
+  if (Cout > 32)
+    stem_fwd_kernel<64><<<grid, 128, 0, s>>>(G, w, bias, static_cast<__nv_bfloat16*>(y), y_ld, th, tw);
+  else
+    stem_fwd_kernel<32><<<grid, 128, 0, s>>>(G, w, bias, static_cast<__nv_bfloat16*>(y), y_ld, th, tw);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t stem_wgrad_workspace(int N, int H, int W, int Cin) {
+  return static_cast<size_t>(stem_grid(N, H, W)) * 64 * 9 * Cin * sizeof(float);
+}
+
+int stem_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy, int64_t dy_ld,
+                   float* dw, int accumulate, int N, int H, int W, int Cin, int Cout, void* ws, size_t ws_bytes,
+                   cudaStream_t s) {
+  UNETK_CHECK(Cin >= 1 && Cin <= 4, -1, "stem: Cin=%d must be <= 4", Cin);
+  UNETK_CHECK(Cout % 8 == 0 && Cout <= 64, -1, "stem: Cout=%d must be a multiple of 8 and <= 64", Cout);
+  UNETK_CHECK(ws != nullptr && ws_bytes >= stem_wgrad_workspace(N, H, W, Cin), -1, "stem_wgrad: workspace too small");
+  StemGeom G{x, sn, sc, sh, sw, N, H, W, Cin, Cout};
+  const int th = (H + kTH - 1) / kTH, tw = (W + kTW - 1) / kTW;
+  const int grid = stem_grid(N, H, W);
+  stem_wgrad_kernel<<<grid, 256, 0, s>>>(G, static_cast<const __nv_bfloat16*>(dy), dy_ld, static_cast<float*>(ws), th,
+                                         tw);
+  UNETK_CUDA(cudaGetLastError());
+  const int K = 9 * Cin;
+  stem_wgrad_reduce_kernel<<<(Cout * K + 127) / 128, 128, 0, s>>>(static_cast<const float*>(ws), grid, Cout, K, dw,
+                                                                accumulate);
+  UNETK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace unetk

@@ -131,3 +131,143 @@ def convT_wgrad(x, dy, dw, accumulate: bool = False):
     _lib.call("unetk_convT2x2_wgrad", xp, xld, dyp, dyld, dw.data_ptr(), int(accumulate), n, h, w, cin, cout,
               ws.data_ptr(), ws.numel(), _stream())
     return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# stem (network-input conv), BatchNorm/ReLU/MaxPool, head + loss, optimizer
+# ------------------------------------------------------------------------------------------------
+def _img(x: torch.Tensor):
+    """fp32 image [N,C,H,W] in any strides (NCHW or channels_last) -> (ptr, sn, sc, sh, sw)."""
+    if x.dim() != 4 or x.dtype != torch.float32 or not x.is_cuda:
+        raise ValueError(f"expected a CUDA fp32 [N,C,H,W] image, got {tuple(x.shape)} {x.dtype} {x.device}")
+    sn, sc, sh, sw = x.stride()
+    return x.data_ptr(), sn, sc, sh, sw
+
+
+def stem_fwd(x, w, bias, y):
+    n, cin, h, wd = x.shape
+    cout = y.shape[3]
+    xp, sn, sc, sh, sw = _img(x)
+    yp, yld = nhwc(y)
+    _lib.call("unetk_stem_conv3x3_fwd", xp, sn, sc, sh, sw, _f32(w.detach()), _f32(bias), yp, yld, n, h, wd, cin, cout,
+              _stream())
+    return y
+
+
+def stem_wgrad(x, dy, dw, accumulate=False):
+    n, cin, h, wd = x.shape
+    cout = dy.shape[3]
+    need = _lib.load().unetk_stem_wgrad_workspace(n, h, wd, cin)
+    ws = workspace(need, x.device)
+    xp, sn, sc, sh, sw = _img(x)
+    dyp, dyld = nhwc(dy)
+    _lib.call("unetk_stem_conv3x3_wgrad", xp, sn, sc, sh, sw, dyp, dyld, _f32(dw), int(accumulate), n, h, wd, cin, cout,
+              ws.data_ptr(), ws.numel(), _stream())
+    return dw
+
+
+def chan_partial_floats(units: int, c: int) -> int:
+    return _lib.load().unetk_chan_partial_floats(units, c)
+
+
+def bn_stats(x, partial, sums):
+    """sums (fp64 [2,C]) <- per-channel (sum, sum of squares) of x [N,H,W,C]."""
+    n, h, w, c = x.shape
+    xp, xld = nhwc(x)
+    _lib.call("unetk_bn_stats", xp, xld, n * h * w, c, partial.data_ptr(), sums.data_ptr(), _stream())
+
+
+def bn_finalize(sums, count, gamma, beta, eps, momentum, rm, rv, nbt, scale, shift, mean, invstd):
+    c = scale.numel()
+    _lib.call("unetk_bn_finalize", sums.data_ptr(), c, float(count), _f32(gamma), _f32(beta), eps, momentum,
+              _f32(rm), _f32(rv), nbt.data_ptr() if nbt is not None else None, _f32(scale), _f32(shift), _f32(mean),
+              _f32(invstd), _stream())
+
+
+def bn_eval_fold(gamma, beta, eps, rm, rv, scale, shift, mean, invstd):
+    _lib.call("unetk_bn_eval_fold", scale.numel(), _f32(gamma), _f32(beta), eps, _f32(rm), _f32(rv), _f32(scale),
+              _f32(shift), _f32(mean), _f32(invstd), _stream())
+
+
+def bn_apply(raw, scale, shift, out, pooled=None, relu=True):
+    n, h, w, c = raw.shape
+    rp, rld = nhwc(raw)
+    op, old = nhwc(out)
+    pp, pld = nhwc(pooled) if pooled is not None else (None, 0)
+    _lib.call("unetk_bn_apply", rp, rld, _f32(scale), _f32(shift), op, old, pp, pld, n, h, w, c, int(relu), _stream())
+
+
+def bn_bwd_reduce(raw, g1, gp, scale, shift, mean, invstd, partial, sums, relu=True):
+    n, h, w, c = raw.shape
+    rp, rld = nhwc(raw)
+    g1p, g1ld = nhwc(g1) if g1 is not None else (None, 0)
+    gpp, gpld = nhwc(gp) if gp is not None else (None, 0)
+    _lib.call("unetk_bn_bwd_reduce", rp, rld, g1p, g1ld, gpp, gpld, _f32(scale), _f32(shift), _f32(mean), _f32(invstd),
+              partial.data_ptr(), sums.data_ptr(), n, h, w, c, int(relu), _stream())
+
+
+def bn_bwd_apply(raw, g1, gp, scale, shift, mean, invstd, sums, count, dgamma, dbeta, coef, draw, relu=True,
+                 accumulate=False):
+    n, h, w, c = raw.shape
+    rp, rld = nhwc(raw)
+    g1p, g1ld = nhwc(g1) if g1 is not None else (None, 0)
+    gpp, gpld = nhwc(gp) if gp is not None else (None, 0)
+    dp, dld = nhwc(draw)
+    _lib.call("unetk_bn_bwd_apply", rp, rld, g1p, g1ld, gpp, gpld, _f32(scale), _f32(shift), _f32(mean), _f32(invstd),
+              sums.data_ptr(), float(count), _f32(dgamma), _f32(dbeta), int(accumulate), _f32(coef), dp, dld, n, h, w,
+              c, int(relu), _stream())
+
+
+def maxpool_fwd(x, y, idx=None):
+    n, h, w, c = x.shape
+    xp, xld = nhwc(x)
+    yp, yld = nhwc(y)
+    _lib.call("unetk_maxpool2x2_fwd", xp, xld, yp, yld, idx.data_ptr() if idx is not None else None, n, h, w, c,
+              _stream())
+
+
+def maxpool_bwd(x, dy, dx):
+    n, h, w, c = x.shape
+    xp, xld = nhwc(x)
+    dyp, dyld = nhwc(dy)
+    dxp, dxld = nhwc(dx)
+    _lib.call("unetk_maxpool2x2_bwd", xp, xld, dyp, dyld, dxp, dxld, n, h, w, c, _stream())
+
+
+def colsum(x, partial, out, accumulate=False):
+    n, h, w, c = x.shape
+    xp, xld = nhwc(x)
+    _lib.call("unetk_colsum", xp, xld, n * h * w, c, partial.data_ptr(), _f32(out), int(accumulate), _stream())
+
+
+def head_partial_floats(npix: int, c: int) -> int:
+    return _lib.load().unetk_head_partial_floats(npix, c)
+
+
+def head_fwd(x, w, bias, labels, logits, partial, sums):
+    n, h, wd, c = x.shape
+    xp, xld = nhwc(x)
+    _lib.call("unetk_head_fwd", xp, xld, _f32(w), _f32(bias), _f32(labels), _f32(logits), n * h * wd, c,
+              partial.data_ptr(), sums.data_ptr() if sums is not None else None, _stream())
+
+
+def loss_finalize(sums, npix_total, fin):
+    _lib.call("unetk_loss_finalize", sums.data_ptr(), float(npix_total), _f32(fin), _stream())
+
+
+def head_bwd(x, w, labels, logits, fin, dlogits, gscale, dx, dw, db, partial, accumulate=False):
+    n, h, wd, c = x.shape
+    xp, xld = nhwc(x)
+    dxp, dxld = nhwc(dx)
+    _lib.call("unetk_head_bwd", xp, xld, _f32(w), _f32(labels), _f32(logits), _f32(fin), _f32(dlogits), float(gscale),
+              dxp, dxld, _f32(dw), _f32(db), int(accumulate), n * h * wd, c, partial.data_ptr(), _stream())
+
+
+def grad_clip_coef(g, gscale, max_norm, partial, out):
+    _lib.call("unetk_grad_clip_coef", _f32(g), g.numel(), float(gscale), float(max_norm), partial.data_ptr(), _f32(out),
+              _stream())
+
+
+def rmsprop_step(p, g, sq, buf, lr, alpha, eps, wd, momentum, clip):
+    _lib.call("unetk_rmsprop_step", _f32(p), _f32(g), _f32(sq), _f32(buf), p.numel(), float(lr), float(alpha),
+              float(eps), float(wd), float(momentum), _f32(clip), _stream())

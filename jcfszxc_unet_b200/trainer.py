@@ -1,0 +1,159 @@
+"""Fused training step — the restatement of the reference's hot loop body (train.py:255-301):
+
+    forward -> 0.5*BCEWithLogits + 0.5*dice_loss -> backward -> clip_grad_norm_(1.0) -> RMSprop
+
+as three CUDA-graph segments with the two data-parallel collectives between them:
+
+    [pack weights, forward, head+loss sums]  --all-reduce(loss sums)-->
+    [loss finalize, backward]                --all-reduce(flat grads)-->
+    [global-norm clip coefficient, RMSprop]
+
+Parameters, gradients and RMSprop state live in four flat fp32 buffers (the model's nn.Parameters are
+re-homed as views, so state_dict()/checkpoints keep working).  No host synchronisation happens inside
+step(); the loss is returned as a device scalar.  bf16 needs no GradScaler (the reference's
+GradScaler/fp16 autocast is replaced by bf16 as BASELINE.json asks).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import engine, ops
+from .dp import DataParallel
+
+
+class Trainer:
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-6, weight_decay: float = 1e-8,
+                 momentum: float = 0.999, alpha: float = 0.99, eps: float = 1e-8, max_norm: float = 1.0,
+                 builder=None, use_cuda_graph: bool = True, dp: DataParallel | None = None):
+        self.model = model
+        self.lr, self.wd, self.momentum, self.alpha, self.eps, self.max_norm = lr, weight_decay, momentum, alpha, eps, max_norm
+        self.builder = builder or engine.build_unet_plan
+        self.dp = dp or DataParallel()
+        self.use_graph = use_cuda_graph and not self.dp.sync_bn  # SyncBN puts collectives between kernels
+        params = [p for p in model.parameters()]
+        if not params or not params[0].is_cuda:
+            raise RuntimeError("Trainer: move the model to a CUDA device first (no CPU fallback on this path)")
+        dev = params[0].device
+        self.device = dev
+        total = sum(p.numel() for p in params)
+        # 16-byte aligned slices so vector kernels can run on any per-tensor view
+        offs, off = [], 0
+        for p in params:
+            offs.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.sq = torch.zeros_like(self.flat_p)
+        self.buf = torch.zeros_like(self.flat_p)
+        self.grad_views = {}
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                v = self.flat_p[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                self.grad_views[id(p)] = self.flat_g[o:o + p.numel()].view(p.shape)
+        self.n_params = total
+        if self.dp.enabled:
+            self.dp.broadcast_(self.flat_p, 0)  # replicas start identical
+        self.clip = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.sq_partial = None
+        self.plan = None
+        self.graphs = None
+        self.images = self.labels = None
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def _build(self, n, c, h, w):
+        dev = self.device
+        self.plan = self.builder(self.model, n, h, w, dev, True, self.grad_views, True)
+        self.images = torch.zeros((n, c, h, w), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+        self.labels = torch.zeros((n, 1, h, w), dtype=torch.float32, device=dev)
+        head = self.plan.head
+        head.labels = self.labels
+        head.dlogits = None
+        head.auto_finalize = False
+        if self.dp.sync_bn:
+            self.plan.sync_sums = self.dp.reduce_bn_sums
+        from . import _lib
+        self.sq_partial = torch.empty(_lib.load().unetk_sqnorm_partial_floats(self.flat_g.numel()),
+                                      dtype=torch.float32, device=dev)
+        self._gscale = 1.0
+
+    # three segments ---------------------------------------------------------------------------------
+    def _seg_forward(self):
+        self.plan.forward(self.images)
+
+    def _seg_backward(self):
+        self.plan.head.finalize_loss(self._npix_total)
+        self.plan.backward()
+
+    def _seg_optim(self):
+        ops.grad_clip_coef(self.flat_g, self._gscale, self.max_norm, self.sq_partial, self.clip)
+        ops.rmsprop_step(self.flat_p, self.flat_g, self.sq, self.buf, self.lr, self.alpha, self.eps, self.wd,
+                         self.momentum, self.clip)
+
+    def _run_segments(self):
+        head = self.plan.head
+        if self.graphs is not None:
+            self.graphs[0].replay()
+        else:
+            self.plan.refresh_weights(force=True)
+            self._seg_forward()
+        if self.dp.sync_loss:
+            self.dp.reduce_loss_sums(head.loss_sums, head.npix)
+        if self.graphs is not None:
+            self.graphs[1].replay()
+        else:
+            self._seg_backward()
+        if self.dp.enabled:
+            self.dp.reduce_grads(self.flat_g)
+        if self.graphs is not None:
+            self.graphs[2].replay()
+        else:
+            self._seg_optim()
+
+    def _capture(self):
+        # constants baked into the graphs
+        graphs = []
+        pool = None
+        for seg in (self._seg_forward_packed, self._seg_backward, self._seg_optim):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                seg()
+            pool = g.pool()
+            graphs.append(g)
+        self.graphs = graphs
+
+    def _seg_forward_packed(self):
+        self.plan.refresh_weights(force=True)  # the optimizer updates weights behind torch's version counter
+        self._seg_forward()
+
+    # ------------------------------------------------------------------------------------------------
+    def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """One training iteration on this rank's shard.  images [N,C,H,W], labels [N,1,H,W] (host or device).
+        Returns the loss as a 0-dim device tensor (no sync)."""
+        n, c, h, w = images.shape
+        if self.plan is None:
+            self._build(n, c, h, w)
+            head = self.plan.head
+            self._npix_total = head.npix * (self.dp.world if self.dp.sync_loss else 1)
+            self._gscale = 1.0 if (self.dp.sync_loss or not self.dp.enabled) else 1.0 / self.dp.world
+        elif tuple(self.images.shape) != (n, c, h, w):
+            raise ValueError(f"Trainer was built for input {tuple(self.images.shape)}, got {(n, c, h, w)}")
+        self.images.copy_(images, non_blocking=True)
+        self.labels.copy_(labels.reshape(self.labels.shape), non_blocking=True)
+        if self.use_graph and self.graphs is None and self.steps_done >= 1:
+            # step 0 ran eagerly (lazy one-time initialisation inside the library); capture now
+            torch.cuda.synchronize()
+            self._capture()
+        self._run_segments()
+        self.steps_done += 1
+        return self.plan.head.fin[0]
+
+    def loss_terms(self):
+        """(loss, bce, dice) of the last step as device scalars."""
+        f = self.plan.head.fin
+        return f[0], f[1], f[2]
+
+    def grad_norm(self):
+        return self.clip[0]

@@ -1,0 +1,237 @@
+"""Pin the oracle (oracle/unet_oracle.py) against the UNMODIFIED reference, and write golden vectors.
+
+Runs only where /root/reference exists (this container, not the GPU box).  The reference is imported
+under its own package name `UNetFamily` from /root/reference with the 4-line timm shim of SURVEY.md
+Appendix A; this repository's own `UNetFamily` package is kept OFF sys.path in this process so the two
+cannot collide (the oracle is loaded by file path).
+
+    python oracle/pin_against_reference.py            # assert bit-equality, regenerate tests/golden/*.npz
+
+Checks (all on CPU, fp32, bit-exact unless noted):
+  1. UNet.forward (train + eval mode) and every running-stat update        == oracle.unet_forward
+  2. the restated train step (train.py:255-301, bf16 autocast and fp32): loss, gradients after
+     clip_grad_norm_, parameters after RMSprop.step                         == oracle.train_step
+  3. DoubleConv / Down / Up / OutConv blocks at small channel counts        == oracle block functions
+  4. utils/dice_score.py dice_coeff / dice_loss incl. the empty-mask branch == oracle + numpy restatement
+  5. F.max_pool2d(return_indices=True) incl. ties and NaNs                  == oracle numpy restatement
+Golden files hold the reference's OUTPUTS for fixed seeds; weights are regenerated from the seed by
+constructing the model (default torch init), so fixtures stay small.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _import_reference():
+    sys.dont_write_bytecode = True
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != ROOT]
+    _t, _l = types.ModuleType("timm"), types.ModuleType("timm.layers")
+    _l.trunc_normal_ = torch.nn.init.trunc_normal_
+    _t.layers = _l
+    sys.modules.setdefault("timm", _t)
+    sys.modules.setdefault("timm.layers", _l)
+    sys.path.insert(0, REF)
+    from UNetFamily import UNet as ref_unet  # noqa
+    from UNetFamily.utils import unet_parts as ref_parts  # noqa
+    from utils import dice_score as ref_dice  # noqa
+    return ref_unet, ref_parts, ref_dice
+
+
+def _load_oracle():
+    spec = importlib.util.spec_from_file_location("unet_oracle", os.path.join(HERE, "unet_oracle.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _inputs(seed, n, h, w, c=3):
+    g = torch.Generator().manual_seed(seed)
+    images = torch.rand(n, c, h, w, generator=g)
+    labels = (torch.rand(n, 1, h, w, generator=g) < 0.12).float()
+    return images, labels
+
+
+def _ref_train_step(model, opt, images, labels, bf16):
+    """Line-for-line restatement of train.py:255-301 around the UNMODIFIED reference modules
+    (train_model itself cannot be imported: h5py/matplotlib missing and train.py:114-122 breaks on torch 2.11)."""
+    import contextlib
+
+    ctx = torch.autocast("cpu", dtype=torch.bfloat16) if bf16 else contextlib.nullcontext()
+    criterion = torch.nn.BCEWithLogitsLoss()
+    with ctx:
+        masks_pred = model(images)
+        masks_pred_sigmoid = torch.sigmoid(masks_pred)
+        bce_loss = criterion(masks_pred, labels)
+        dice = REF_DICE.dice_loss(masks_pred_sigmoid.squeeze(1), labels.squeeze(1), multiclass=False)
+        alpha = 0.5
+        loss = alpha * bce_loss + (1 - alpha) * dice
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+    opt.step()
+    return loss.detach(), masks_pred.detach(), bce_loss.detach(), dice.detach(), grads
+
+
+def main():
+    global REF_DICE
+    ref_unet, ref_parts, REF_DICE = _import_reference()
+    O = _load_oracle()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.use_deterministic_algorithms(False)
+    os.makedirs(GOLDEN, exist_ok=True)
+    report = []
+
+    # ---- 1. forward, train and eval mode ---------------------------------------------------------
+    torch.manual_seed(42)
+    model = ref_unet.UNet(3, 1)
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    images, labels = _inputs(7, 2, 32, 32)
+    model.train()
+    with torch.no_grad():
+        y_ref = model(images)
+    sd = {k: v.clone() for k, v in sd0.items()}
+    with torch.no_grad():
+        y_or = O.unet_forward(images, sd, training=True)
+    assert torch.equal(y_ref, y_or), "train-mode forward differs"
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), f"running stat {k} differs"
+    model.eval()
+    with torch.no_grad():
+        y_ref_eval = model(images)
+        y_or_eval = O.unet_forward(images, sd, training=False)
+    assert torch.equal(y_ref_eval, y_or_eval), "eval-mode forward differs"
+    report.append("forward train/eval + running stats: bit-exact")
+    np.savez_compressed(os.path.join(GOLDEN, "unet_forward_seed42.npz"), images=images.numpy(), labels=labels.numpy(),
+                        logits_train=y_ref.numpy(), logits_eval_after_1_train_fwd=y_ref_eval.numpy(),
+                        running_mean_inc1=model.state_dict()["inc.double_conv.1.running_mean"].numpy(),
+                        running_var_up4_4=model.state_dict()["up4.conv.double_conv.4.running_var"].numpy(),
+                        num_batches_tracked=np.int64(model.state_dict()["inc.double_conv.1.num_batches_tracked"].item()))
+
+    # ---- 2. train step (fp32 and bf16 autocast) ---------------------------------------------------
+    for bf16 in (False, True):
+        torch.manual_seed(42)
+        model = ref_unet.UNet(3, 1).train()
+        lr = 1e-3  # larger than the reference default (1e-6) so that the parameter update is visible in fp32
+        opt = torch.optim.RMSprop(model.parameters(), lr=lr, weight_decay=1e-8, momentum=0.999)
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        opt_state = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in O.param_names(sd)}
+        gold = {}
+        for step in range(2):
+            images, labels = _inputs(100 + step, 2, 32, 32)
+            loss_r, logits_r, bce_r, dice_r, grads_r = _ref_train_step(model, opt, images, labels, bf16)
+            loss_o, logits_o, grads_o = O.train_step(sd, opt_state, images, labels, lr, bf16)
+            assert torch.equal(loss_r, loss_o), f"loss differs (bf16={bf16}, step {step}): {loss_r} vs {loss_o}"
+            assert torch.equal(logits_r.float(), logits_o.float())
+            for k in grads_r:
+                assert torch.equal(grads_r[k], grads_o[k]), f"clipped grad {k} differs"
+            for k, v in model.state_dict().items():
+                assert torch.equal(v, sd[k]), f"post-step tensor {k} differs (bf16={bf16}, step {step})"
+            gold[f"loss{step}"] = loss_r.float().numpy()
+            gold[f"bce{step}"] = bce_r.float().numpy()
+            gold[f"dice_loss{step}"] = dice_r.float().numpy()
+            gold[f"logits{step}"] = logits_r.float().numpy()
+            gold[f"gradnorm{step}"] = np.array([float(g.float().norm()) for g in grads_r.values()], dtype=np.float64)
+            for k in ("outc.conv.weight", "outc.conv.bias", "inc.double_conv.1.weight", "inc.double_conv.1.bias",
+                      "up4.conv.double_conv.4.weight", "down4.maxpool_conv.1.double_conv.4.bias", "up1.up.bias",
+                      "inc.double_conv.0.weight"):
+                gold[f"grad{step}:{k}"] = grads_r[k].float().numpy()
+                gold[f"param{step}:{k}"] = model.state_dict()[k].detach().float().clone().numpy()
+        gold["param_names"] = np.array(list(grads_r.keys()))
+        np.savez_compressed(os.path.join(GOLDEN, f"unet_trainstep_seed42_{'bf16' if bf16 else 'fp32'}.npz"), **gold)
+        report.append(f"train step x2 ({'bf16 autocast' if bf16 else 'fp32'}): loss, clipped grads, RMSprop update bit-exact")
+
+    # ---- 3. blocks -------------------------------------------------------------------------------
+    g = torch.Generator().manual_seed(5)
+    blocks = {}
+    torch.manual_seed(3)
+    dc = ref_parts.DoubleConv(8, 16).train()
+    x = torch.randn(2, 8, 12, 20, generator=g)
+    sd = {k: v.detach().clone() for k, v in dc.state_dict().items()}
+    with torch.no_grad():
+        assert torch.equal(dc(x), O.double_conv(x, sd, "", True))
+    blocks.update(dc_x=x.numpy(), dc_y=dc(x).detach().numpy())
+    torch.manual_seed(4)
+    dn = ref_parts.Down(8, 16).train()
+    sd = {k: v.detach().clone() for k, v in dn.state_dict().items()}
+    with torch.no_grad():
+        assert torch.equal(dn(x), O.down(x, sd, "", True))
+    blocks.update(down_y=dn(x).detach().numpy())
+    torch.manual_seed(5)
+    upm = ref_parts.Up(16, 8).train()
+    x1 = torch.randn(2, 16, 6, 10, generator=g)
+    x2 = torch.randn(2, 8, 12, 20, generator=g)
+    sd = {k: v.detach().clone() for k, v in upm.state_dict().items()}
+    with torch.no_grad():
+        assert torch.equal(upm(x1, x2), O.up(x1, x2, sd, "", True))
+    blocks.update(up_x1=x1.numpy(), up_x2=x2.numpy(), up_y=upm(x1, x2).detach().numpy())
+    # odd sizes exercise the F.pad branch (unet_parts.py:64-67) of the oracle
+    x2o = torch.randn(2, 8, 13, 21, generator=g)
+    with torch.no_grad():
+        assert torch.equal(upm(x1, x2o), O.up(x1, x2o, {k: v.detach().clone() for k, v in upm.state_dict().items()}, "", True))
+    torch.manual_seed(6)
+    oc = ref_parts.OutConv(8, 1)
+    sd = {k: v.detach().clone() for k, v in oc.state_dict().items()}
+    with torch.no_grad():
+        assert torch.equal(oc(x), O.out_conv(x, sd, ""))
+    blocks.update(outc_y=oc(x).detach().numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "blocks_seeds3to6.npz"), **blocks)
+    report.append("DoubleConv / Down / Up (+pad branch) / OutConv: bit-exact")
+
+    # ---- 4. dice ---------------------------------------------------------------------------------
+    p = torch.rand(3, 16, 16, generator=g)
+    t = (torch.rand(3, 16, 16, generator=g) < 0.2).float()
+    cases = {"rand": (p, t), "empty": (torch.zeros(3, 16, 16), torch.zeros(3, 16, 16)),
+             "full": (torch.ones(3, 16, 16), torch.ones(3, 16, 16)), "out_of_range": (p * 3 - 1, t)}
+    dice_gold = {}
+    for name, (pp, tt) in cases.items():
+        a = REF_DICE.dice_coeff(pp, tt, reduce_batch_first=True)
+        b = O.dice_coeff(pp, tt, reduce_batch_first=True)
+        assert torch.equal(a, b), name
+        assert abs(float(a) - O.dice_coeff_numpy(pp.numpy(), tt.numpy())) < 1e-6, name
+        assert torch.equal(REF_DICE.dice_loss(pp, tt), O.dice_loss(pp, tt)), name
+        a4 = REF_DICE.dice_coeff(pp[:, None], tt[:, None], reduce_batch_first=False)
+        assert torch.equal(a4, O.dice_coeff(pp[:, None], tt[:, None], reduce_batch_first=False)), name
+        assert torch.equal(REF_DICE.multiclass_dice_coeff(pp[:, None], tt[:, None]), O.multiclass_dice_coeff(pp[:, None], tt[:, None]))
+        dice_gold[f"{name}_p"] = pp.numpy()
+        dice_gold[f"{name}_t"] = tt.numpy()
+        dice_gold[f"{name}_coeff_batch"] = a.numpy()
+        dice_gold[f"{name}_coeff_per_item"] = a4.numpy()
+        dice_gold[f"{name}_loss"] = REF_DICE.dice_loss(pp, tt).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "dice_cases.npz"), **dice_gold)
+    report.append("dice_coeff / multiclass_dice_coeff / dice_loss incl. empty-mask branch: bit-exact (+numpy within 1e-6)")
+
+    # ---- 5. max-pool indices ----------------------------------------------------------------------
+    xm = torch.randn(2, 8, 8, 12, generator=g)
+    xm = torch.relu(xm)                       # many all-zero windows -> ties
+    xm[0, 0, 0, 0] = float("nan")
+    xm[0, 1, 2:4, 2:4] = float("nan")         # several NaNs in one window: the last one wins
+    xm[1, 2, 4, 5] = float("inf")
+    vals, idx = torch.nn.functional.max_pool2d(xm, 2, return_indices=True)
+    ov, oi = O.maxpool2x2_with_indices_numpy(xm.numpy())
+    assert np.array_equal(idx.numpy(), oi), "maxpool indices differ"
+    assert np.array_equal(np.nan_to_num(vals.numpy(), nan=-7.0), np.nan_to_num(ov, nan=-7.0))
+    vcl, icl = torch.nn.functional.max_pool2d(xm.contiguous(memory_format=torch.channels_last), 2, return_indices=True)
+    assert torch.equal(icl, idx)
+    np.savez_compressed(os.path.join(GOLDEN, "maxpool_indices.npz"), x=xm.numpy(), values=vals.numpy(), indices=idx.numpy())
+    report.append("max_pool2d indices with ties / NaN / inf: bit-exact (NCHW and channels_last)")
+
+    print("ORACLE PINNED against /root/reference:")
+    for r in report:
+        print("  -", r)
+    print("golden vectors written to", GOLDEN)
+
+
+if __name__ == "__main__":
+    main()

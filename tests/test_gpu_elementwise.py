@@ -1,0 +1,276 @@
+"""Parity of the HBM-bound kernels (BatchNorm stats/apply/backward, MaxPool2d(2) with indices, stem conv,
+head + loss, optimizer) through the C ABI against torch.nn.functional / the oracle on the same inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _exact_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _ops():
+    from jcfszxc_unet_b200 import ops
+
+    return ops
+
+
+DEV = "cuda:0"
+
+
+def _scratch(ops, units, c):
+    partial = torch.empty(max(ops.chan_partial_floats(units, c), 4096), device=DEV)
+    sums = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
+    return partial, sums
+
+
+@pytest.mark.parametrize("n,h,w,c,pad", [(2, 16, 16, 64, 0), (1, 32, 24, 128, 64), (3, 8, 8, 1024, 0), (1, 10, 14, 72, 8)])
+def test_bn_train_forward(n, h, w, c, pad):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(c + h)
+    buf = torch.zeros(n, h, w, c + pad, device=DEV, dtype=torch.bfloat16)
+    raw = buf[..., pad:]
+    raw.copy_(torch.randn(n, h, w, c, device=DEV, generator=g) * 2 + 0.5)
+    gamma = torch.rand(c, device=DEV, generator=g) + 0.5
+    beta = torch.randn(c, device=DEV, generator=g)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    partial, sums = _scratch(ops, n * h * w, c)
+    stat = torch.zeros(4, c, device=DEV)
+    ops.bn_stats(raw, partial, sums)
+    ops.bn_finalize(sums, n * h * w, gamma, beta, 1e-5, 0.1, rm, rv, nbt, stat[0], stat[1], stat[2], stat[3])
+    out = torch.empty(n, h, w, c, device=DEV, dtype=torch.bfloat16)
+    ops.bn_apply(raw, stat[0], stat[1], out, None, True)
+    # checker: nn.BatchNorm2d arithmetic in fp32 on the same bf16 input
+    x = raw.float().permute(0, 3, 1, 2)
+    rm_ref, rv_ref = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    ref = F.relu(F.batch_norm(x, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5)).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-3
+    assert torch.allclose(rm, rm_ref, rtol=1e-5, atol=1e-6) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-6)
+    assert int(nbt) == 1
+    assert torch.allclose(stat[2], x.mean(dim=(0, 2, 3)), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 64), (1, 8, 12, 256)])
+def test_bn_apply_fused_pool_equals_separate_and_matches_torch(n, h, w, c):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(1)
+    raw = (torch.randn(n, h, w, c, device=DEV, generator=g)).bfloat16()
+    scale = torch.rand(c, device=DEV, generator=g) + 0.5
+    shift = torch.randn(c, device=DEV, generator=g) * 0.5
+    out = torch.empty_like(raw)
+    pooled = torch.empty(n, h // 2, w // 2, c, device=DEV, dtype=torch.bfloat16)
+    ops.bn_apply(raw, scale, shift, out, pooled, True)
+    out2 = torch.empty_like(raw)
+    ops.bn_apply(raw, scale, shift, out2, None, True)
+    assert torch.equal(out, out2)
+    ref_pool = F.max_pool2d(out.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(pooled.float(), ref_pool)
+    pooled2 = torch.empty_like(pooled)
+    ops.maxpool_fwd(out, pooled2)
+    assert torch.equal(pooled, pooled2)
+
+
+def test_maxpool_indices_bit_exact_golden_and_live():
+    """Indices must equal F.max_pool2d(..., return_indices=True) bit for bit: ties (first max wins),
+    NaN (always taken, last wins), +inf.  Golden = reference torch output on CPU; live = torch on this GPU."""
+    ops = _ops()
+    gold = np.load(os.path.join(GOLDEN, "maxpool_indices.npz"))
+    x = torch.from_numpy(gold["x"]).to(DEV)                      # [2, 8, 8, 12] NCHW, all values bf16-exact? no:
+    xb = x.bfloat16()                                            # kernels are bf16; round first, compare on the rounded tensor
+    xn = xb.permute(0, 2, 3, 1).contiguous()
+    n, h, w, c = xn.shape
+    y = torch.empty(n, h // 2, w // 2, c, device=DEV, dtype=torch.bfloat16)
+    idx = torch.full((n, c, h // 2, w // 2), -1, dtype=torch.int64, device=DEV)
+    ops.maxpool_fwd(xn, y, idx)
+    ref_v, ref_i = F.max_pool2d(xb.float(), 2, return_indices=True)
+    assert torch.equal(idx, ref_i)
+    assert torch.equal(torch.nan_to_num(y.float().permute(0, 3, 1, 2), nan=-7.0), torch.nan_to_num(ref_v, nan=-7.0))
+    # ties and NaNs sit at bf16-exact positions, so the golden indices (from fp32) must agree wherever rounding
+    # did not reorder a window; the NaN / all-zero windows are the ones the rule is about:
+    gi = torch.from_numpy(gold["indices"]).to(DEV)
+    special = torch.isnan(ref_v) | (ref_v == 0)
+    assert torch.equal(idx[special], gi[special])
+    # larger random case with heavy ties (post-ReLU zeros)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    xr = torch.relu(torch.randn(4, 64, 32, 64, device=DEV, generator=g)).bfloat16()   # NCHW
+    xrn = xr.permute(0, 2, 3, 1).contiguous()
+    y = torch.empty(4, 16, 32, 64, device=DEV, dtype=torch.bfloat16)
+    idx = torch.empty(4, 64, 16, 32, dtype=torch.int64, device=DEV)
+    ops.maxpool_fwd(xrn, y, idx)
+    rv, ri = F.max_pool2d(xr.float(), 2, return_indices=True)
+    assert torch.equal(idx, ri) and torch.equal(y.float().permute(0, 3, 1, 2), rv)
+    # backward = scatter through the same argmax
+    dy = torch.randn(4, 16, 32, 64, device=DEV, generator=g).bfloat16()
+    dx = torch.empty_like(xrn)
+    ops.maxpool_bwd(xrn, dy, dx)
+    xr32 = xr.float().requires_grad_(True)
+    F.max_pool2d(xr32, 2).backward(dy.float().permute(0, 3, 1, 2))
+    assert torch.equal(dx.float().permute(0, 3, 1, 2), xr32.grad)
+
+
+@pytest.mark.parametrize("n,h,w,c,pool,skip", [(2, 16, 16, 64, False, True), (2, 16, 16, 64, True, True),
+                                               (1, 8, 8, 512, True, False), (1, 12, 20, 128, False, True)])
+def test_bn_relu_backward(n, h, w, c, pool, skip):
+    """dL/d(raw), dgamma, dbeta of out = relu(bn(raw)) [+ maxpool consumer] against autograd on the same graph."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(17)
+    raw = torch.randn(n, h, w, c, device=DEV, generator=g).bfloat16()
+    gamma = (torch.rand(c, device=DEV, generator=g) + 0.5)
+    beta = torch.randn(c, device=DEV, generator=g) * 0.3
+    partial, sums = _scratch(ops, n * h * w, c)
+    stat = torch.zeros(4, c, device=DEV)
+    ops.bn_stats(raw, partial, sums)
+    ops.bn_finalize(sums, n * h * w, gamma, beta, 1e-5, 0.1, None, None, None, stat[0], stat[1], stat[2], stat[3])
+    out = torch.empty_like(raw)
+    ops.bn_apply(raw, stat[0], stat[1], out, None, True)
+    g1 = torch.randn(n, h, w, c, device=DEV, generator=g).bfloat16() if skip else None
+    gp = torch.randn(n, h // 2, w // 2, c, device=DEV, generator=g).bfloat16() if pool else None
+    dgamma, dbeta = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    coef = torch.zeros(2 * c, device=DEV)
+    draw = torch.empty_like(raw)
+    ops.bn_bwd_reduce(raw, g1, gp, stat[0], stat[1], stat[2], stat[3], partial, sums, True)
+    ops.bn_bwd_apply(raw, g1, gp, stat[0], stat[1], stat[2], stat[3], sums, n * h * w, dgamma, dbeta, coef, draw, True)
+    # autograd reference; the bf16 rounding of the BN output is emulated with a straight-through cast so that the
+    # ReLU mask and the pool argmax are decided on the same values the kernel saw
+    x = raw.float().permute(0, 3, 1, 2).requires_grad_(True)
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = F.batch_norm(x, None, None, gm, bt, True, 0.1, 1e-5)
+    z = z + (z.detach().bfloat16().float() - z.detach())
+    a = F.relu(z)
+    loss = 0
+    if skip:
+        loss = loss + (a * g1.float().permute(0, 3, 1, 2)).sum()
+    if pool:
+        loss = loss + (F.max_pool2d(a, 2) * gp.float().permute(0, 3, 1, 2)).sum()
+    loss.backward()
+    ref = x.grad.permute(0, 2, 3, 1)
+    scale = ref.abs().max().item()
+    assert (draw.float() - ref).abs().max().item() <= 1.5e-2 * scale
+    assert torch.allclose(dgamma, gm.grad, rtol=2e-3, atol=2e-3 * gm.grad.abs().max().item())
+    assert torch.allclose(dbeta, bt.grad, rtol=2e-3, atol=2e-3 * bt.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+@pytest.mark.parametrize("cout,bias", [(64, False), (32, True)])
+def test_stem_conv(layout, cout, bias):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(2)
+    x = torch.rand(2, 3, 36, 40, device=DEV, generator=g)
+    if layout == "channels_last":
+        x = x.contiguous(memory_format=torch.channels_last)
+    w = torch.randn(cout, 3, 3, 3, device=DEV, generator=g) * 0.2
+    b = torch.randn(cout, device=DEV, generator=g) if bias else None
+    y = torch.empty(2, 36, 40, cout, device=DEV, dtype=torch.bfloat16)
+    ops.stem_fwd(x, w, b, y)
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, padding=1).permute(0, 2, 3, 1)
+    assert (y.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    dy = torch.randn(2, 36, 40, cout, device=DEV, generator=g).bfloat16()
+    dw = torch.empty(cout, 3, 3, 3, device=DEV)
+    ops.stem_wgrad(x, dy, dw)
+    refw = torch.nn.grad.conv2d_weight(x.bfloat16().float(), (cout, 3, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
+    assert (dw - refw).abs().max().item() <= 1e-3 * refw.abs().max().item()
+
+
+@pytest.mark.parametrize("c", [64, 32])
+def test_head_loss_forward_backward_vs_oracle(c):
+    from oracle import unet_oracle as O
+
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(4)
+    n, h, w = 2, 24, 40
+    x = torch.randn(n, h, w, c, device=DEV, generator=g).bfloat16()
+    wt = torch.randn(1, c, 1, 1, device=DEV, generator=g) * 0.3
+    b = torch.randn(1, device=DEV, generator=g)
+    labels = (torch.rand(n, 1, h, w, device=DEV, generator=g) < 0.12).float()
+    npix = n * h * w
+    partial = torch.empty(max(ops.head_partial_floats(npix, c), 4096), device=DEV)
+    sums = torch.zeros(4, dtype=torch.float64, device=DEV)
+    fin = torch.zeros(8, device=DEV)
+    logits = torch.empty(n, 1, h, w, device=DEV)
+    ops.head_fwd(x, wt.view(-1), b, labels, logits, partial, sums)
+    ops.loss_finalize(sums, npix, fin)
+    # oracle on the same values (train.py:264-278 + dice_score.py)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    z = F.conv2d(xr, wr, br)
+    loss, bce, dice_l = O.segmentation_loss(z, labels)
+    assert torch.allclose(logits, z.detach(), rtol=1e-4, atol=1e-4)
+    assert abs(float(fin[0]) - float(loss)) <= 1e-5 and abs(float(fin[1]) - float(bce)) <= 1e-5
+    assert abs(float(fin[2]) - (1 - float(dice_l))) <= 1e-5                       # Dice within 1e-3 (north_star): here 1e-5
+    loss.backward()
+    dx = torch.empty_like(x)
+    dw, db = torch.zeros(c, device=DEV), torch.zeros(1, device=DEV)
+    ops.head_bwd(x, wt.view(-1), labels, logits, fin, None, 1.0, dx, dw, db, partial)
+    ref = xr.grad.permute(0, 2, 3, 1)
+    assert (dx.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    assert torch.allclose(dw, wr.grad.view(-1), rtol=1e-3, atol=1e-3 * wr.grad.abs().max().item())
+    assert torch.allclose(db, br.grad, rtol=1e-3, atol=1e-6)
+    # explicit dlogits path (loss computed outside, e.g. by the reference's train.py)
+    dlog = torch.randn(n, 1, h, w, device=DEV, generator=g)
+    ops.head_bwd(x, wt.view(-1), None, None, None, dlog, 1.0, dx, dw, db, partial)
+    ref = (dlog.permute(0, 2, 3, 1) * wt.view(1, 1, 1, c))
+    assert (dx.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    # empty mask: dice == 1 branch
+    zero_labels = torch.zeros_like(labels)
+    xs = (x * 0 - 0).bfloat16()
+    ops.head_fwd(xs, wt.view(-1), torch.full((1,), -40.0, device=DEV), zero_labels, logits, partial, sums)
+    ops.loss_finalize(sums, npix, fin)
+    ref_loss, _, ref_dl = O.segmentation_loss(torch.full((n, 1, h, w), -40.0, device=DEV), zero_labels)
+    assert abs(float(fin[2]) - (1 - float(ref_dl))) <= 1e-4 and abs(float(fin[0]) - float(ref_loss)) <= 1e-4
+    # truly empty: 32 pixels * 1e-7 < eps -> sets_sum := inter branch of dice_score.py:35 (dice == 1, zero dice gradient)
+    xt = torch.zeros(1, 4, 8, c, device=DEV, dtype=torch.bfloat16)
+    lt = torch.zeros(1, 1, 4, 8, device=DEV)
+    zt = torch.empty(1, 1, 4, 8, device=DEV)
+    ops.head_fwd(xt, wt.view(-1), torch.full((1,), -40.0, device=DEV), lt, zt, partial, sums)
+    ops.loss_finalize(sums, 32, fin)
+    ref_loss, _, ref_dl = O.segmentation_loss(torch.full((1, 1, 4, 8), -40.0, device=DEV), lt)
+    assert float(ref_dl) == 0.0 and abs(float(fin[2]) - 1.0) <= 1e-6 and abs(float(fin[0]) - float(ref_loss)) <= 1e-6
+    assert float(fin[4]) == 0.0 and float(fin[5]) == 0.0
+
+
+def test_clip_and_rmsprop_vs_oracle():
+    from oracle import unet_oracle as O
+
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(6)
+    n = 1_000_003
+    p = torch.randn(n + 1, device=DEV, generator=g)[:n + 1]
+    grad = torch.randn(n + 1, device=DEV, generator=g) * 0.01
+    p, grad = p[:n + 1].clone(), grad[:n + 1].clone()
+    sq, buf = torch.zeros_like(p), torch.zeros_like(p)
+    from jcfszxc_unet_b200 import _lib
+
+    partial = torch.empty(_lib.load().unetk_sqnorm_partial_floats(p.numel()), device=DEV)
+    clip = torch.zeros(2, device=DEV)
+    pr, sqr, bufr = p.clone(), sq.clone(), buf.clone()
+    for it in range(3):
+        ops.grad_clip_coef(grad, 1.0, 1.0, partial, clip)
+        ops.rmsprop_step(p, grad, sq, buf, 1e-3, 0.99, 1e-8, 1e-8, 0.999, clip)
+        (gc,), total = O.clip_grad_norm([grad], 1.0)
+        O.rmsprop_step(pr, gc, sqr, bufr, 1e-3)
+        assert abs(float(clip[0]) - float(total)) <= 1e-4 * float(total)
+    assert torch.allclose(p, pr, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(sq, sqr, rtol=1e-4, atol=1e-12) and torch.allclose(buf, bufr, rtol=1e-4, atol=1e-6)
+
+
+def test_colsum():
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(8)
+    x = torch.randn(2, 20, 12, 128, device=DEV, generator=g).bfloat16()
+    partial = torch.empty(max(ops.chan_partial_floats(2 * 20 * 12, 128), 4096), device=DEV)
+    out = torch.zeros(128, device=DEV)
+    ops.colsum(x, partial, out)
+    ref = x.float().sum(dim=(0, 1, 2))
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3)
+    ops.colsum(x, partial, out, accumulate=True)
+    assert torch.allclose(out, 2 * ref, rtol=1e-4, atol=2e-3)
