@@ -30,6 +30,8 @@ extern "C" {
 
 int unetk_abi_version(void);
 const char* unetk_last_error(void);
+/* Number of CUDA kernels this library has launched (or recorded into a CUDA graph) in this process. */
+int64_t unetk_launch_count(void);
 
 /* ---- weight cache -------------------------------------------------------------------------------
  * fp32 master weights stay in PyTorch layout (state_dict compatible); the kernels read bf16 packs.

@@ -22,6 +22,7 @@ _vp, _i, _i64, _sz, _fp, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_vo
 SIGNATURES = {
     "unetk_abi_version": (_i, []),
     "unetk_last_error": (C.c_char_p, []),
+    "unetk_launch_count": (_i64, []),
     "unetk_pack_weight": (_i, [_fp, _vp, _vp, _i, _i, _i, _vp]),
     "unetk_conv3x3_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv3x3_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
@@ -95,6 +96,42 @@ def check(rc: int, what: str) -> None:
         raise UnetkError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
 
 
+_profile: list | None = None  # when a list: (name, args, start_event, end_event) per C-ABI call
+
+
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point and raise on error."""
+    if _profile is None:
+        check(getattr(load(), name)(*args), name)
+        return
+    import torch
+
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
     check(getattr(load(), name)(*args), name)
+    end.record()
+    _profile.append((name, args, start, end))
+
+
+class profile_calls:
+    """Context manager: time every C-ABI call with CUDA events on the launching (current) stream."""
+
+    def __enter__(self):
+        global _profile
+        self.records = []
+        _profile = self.records
+        return self
+
+    def __exit__(self, *exc):
+        global _profile
+        _profile = None
+        return False
+
+    def summary(self):
+        """name -> (calls, total_ms); call after torch.cuda.synchronize()."""
+        out: dict[str, list] = {}
+        for name, _args, s, e in self.records:
+            slot = out.setdefault(name, [0, 0.0])
+            slot[0] += 1
+            slot[1] += s.elapsed_time(e)
+        return out

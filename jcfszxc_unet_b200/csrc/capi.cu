@@ -63,6 +63,7 @@ extern "C" {
 
 int unetk_abi_version(void) { return UNETK_ABI_VERSION; }
 const char* unetk_last_error(void) { return unetk::last_error(); }
+int64_t unetk_launch_count(void) { return static_cast<int64_t>(unetk::launch_count()); }
 
 int unetk_pack_weight(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, void* stream) {
   UNETK_CHECK(src != nullptr && A > 0 && B > 0 && T > 0, -1, "pack_weight: bad arguments");

@@ -215,7 +215,7 @@ int launch(const ConvGemmParams& p, cudaStream_t stream) {
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   conv_gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 

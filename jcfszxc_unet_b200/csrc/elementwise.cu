@@ -473,7 +473,7 @@ size_t chan_partial_floats(int64_t units, int C) { return static_cast<size_t>(re
 
 static int launch_sums(const float* partial, int nblk, int C, double* sums, cudaStream_t s) {
   chan_sums_kernel<<<(2 * C + 127) / 128, 128, 0, s>>>(partial, nblk, C, sums);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
@@ -482,7 +482,7 @@ int bn_stats_run(const void* x, int64_t ld, int64_t npix, int C, float* partial,
   CHECK_C(C);
   const int grid = reduce_grid(npix, C);
   stats_kernel<<<grid, kThreads, reduce_smem(C, 2), s>>>(static_cast<const __nv_bfloat16*>(x), ld, npix, C, partial);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return launch_sums(partial, grid, C, sums, s);
 }
 
@@ -491,14 +491,14 @@ int bn_finalize_run(const double* sums, int C, double count, const float* gamma,
                     float* invstd, cudaStream_t s) {
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, gamma, beta, eps, momentum, rm, rv, nbt, scale,
                                                     shift, mean, invstd);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
 int bn_eval_fold_run(int C, const float* gamma, const float* beta, float eps, const float* rm, const float* rv,
                      float* scale, float* shift, float* mean, float* invstd, cudaStream_t s) {
   bn_eval_fold_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, gamma, beta, eps, rm, rv, scale, shift, mean, invstd);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
@@ -507,9 +507,9 @@ int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, f
   CHECK_C(C);
   const int grid = reduce_grid(npix, C);
   stats_kernel<<<grid, kThreads, reduce_smem(C, 2), s>>>(static_cast<const __nv_bfloat16*>(x), ld, npix, C, partial);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, grid, C, out, accumulate);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
@@ -528,7 +528,7 @@ int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const floa
                                                                   scale, shift, static_cast<__nv_bfloat16*>(out),
                                                                   out_ld, npix, C, relu);
   }
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
@@ -539,7 +539,7 @@ int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long lon
   if (total == 0) return 0;
   maxpool_fwd_kernel<<<flat_grid(total), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
                                                           static_cast<__nv_bfloat16*>(y), y_ld, idx, N, H, W, C);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
@@ -551,7 +551,7 @@ int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, 
   maxpool_bwd_kernel<<<flat_grid(total), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
                                                           static_cast<const __nv_bfloat16*>(dy), dy_ld,
                                                           static_cast<__nv_bfloat16*>(dx), dx_ld, N, H, W, C);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
@@ -578,7 +578,7 @@ int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g
   const size_t smem = reduce_smem(C, 2);
   if (pool) bn_bwd_reduce_kernel<true><<<grid, kThreads, smem, s>>>(A, partial);
   else bn_bwd_reduce_kernel<false><<<grid, kThreads, smem, s>>>(A, partial);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return launch_sums(partial, grid, C, sums, s);
 }
 
@@ -591,11 +591,11 @@ int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1
   const bool pool = gp != nullptr;
   const int64_t units = pool ? static_cast<int64_t>(N) * (H / 2) * (W / 2) : static_cast<int64_t>(N) * H * W;
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, dgamma, dbeta, accumulate, coef);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   const int fg = flat_grid(units * (C / 8));
   if (pool) bn_bwd_apply_kernel<true><<<fg, kThreads, 0, s>>>(A, coef, static_cast<__nv_bfloat16*>(draw), draw_ld);
   else bn_bwd_apply_kernel<false><<<fg, kThreads, 0, s>>>(A, coef, static_cast<__nv_bfloat16*>(draw), draw_ld);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 

@@ -1,5 +1,6 @@
 #include "host_common.cuh"
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -19,6 +20,10 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
   static int cached = 0;

@@ -30,6 +30,15 @@ void set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
+// Every kernel launch site ends with this: counts the launch (unetk_launch_count) and checks for errors.
+void count_launch();
+#define UNETK_LAUNCHED()              \
+  do {                                \
+    ::unetk::count_launch();          \
+    UNETK_CUDA(cudaGetLastError());   \
+  } while (0)
+
+long long launch_count();
 int num_sms();
 const char* last_error();
 

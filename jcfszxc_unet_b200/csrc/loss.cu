@@ -186,18 +186,18 @@ int head_loss_fwd_run(const void* x, int64_t ld, const float* w, const float* bi
   const int grid = head_grid(npix, C);
   head_loss_fwd_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, w, bias, labels, logits, npix,
                                                 C, partial);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   if (labels != nullptr) {
     UNETK_CHECK(sums != nullptr, -1, "head_loss_fwd: sums is null");
     loss_sums_kernel<<<1, 32, 0, s>>>(partial, grid, sums);
-    UNETK_CUDA(cudaGetLastError());
+    UNETK_LAUNCHED();
   }
   return 0;
 }
 
 int loss_finalize_run(const double* sums, double npix_total, float* out, cudaStream_t s) {
   loss_finalize_kernel<<<1, 32, 0, s>>>(sums, npix_total, out);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
@@ -212,9 +212,9 @@ int head_loss_bwd_run(const void* x, int64_t ld, const float* w, const float* la
   head_loss_bwd_kernel<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(x), ld, w, labels, logits, fin,
                                                    dlogits, gscale, static_cast<__nv_bfloat16*>(dx), dx_ld, npix, C,
                                                    partial);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   head_bwd_finalize_kernel<<<(C + 1 + 127) / 128, 128, 0, s>>>(partial, grid, C, dw, db, accumulate);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 

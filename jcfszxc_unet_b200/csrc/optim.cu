@@ -84,9 +84,9 @@ int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, 
   UNETK_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, -1, "grad buffer must be 16-byte aligned");
   const int nb = sqnorm_blocks(n);
   sqnorm_kernel<<<nb, kThreads, 0, s>>>(g, n, partial);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   clip_finalize_kernel<<<1, 32, 0, s>>>(partial, nb, gscale, max_norm, out);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
@@ -97,7 +97,7 @@ int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, floa
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   rmsprop_kernel<<<static_cast<int>(b), kThreads, 0, s>>>(p, g, sq, buf, n, lr, alpha, eps, wd, momentum, clip);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 

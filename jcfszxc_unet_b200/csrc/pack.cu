@@ -28,7 +28,7 @@ int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, 
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   pack_weight_kernel<<<blocks, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst_ab),
                                                  static_cast<__nv_bfloat16*>(dst_ba), A, B, T);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 

@@ -128,7 +128,7 @@ int probe_run(const void* a, const void* b, float* d, int mode, int shift, int b
   const int smem = 40960 + 8192 + 64 + 1024;
   UNETK_CUDA(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   probe_kernel<<<1, 128, smem, stream>>>(p);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 

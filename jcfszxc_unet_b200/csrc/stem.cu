@@ -163,7 +163,7 @@ int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
     stem_fwd_kernel<64><<<grid, 128, 0, s>>>(G, w, bias, static_cast<__nv_bfloat16*>(y), y_ld, th, tw);
   else
     stem_fwd_kernel<32><<<grid, 128, 0, s>>>(G, w, bias, static_cast<__nv_bfloat16*>(y), y_ld, th, tw);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
@@ -182,11 +182,11 @@ int stem_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t s
   const int grid = stem_grid(N, H, W);
   stem_wgrad_kernel<<<grid, 256, 0, s>>>(G, static_cast<const __nv_bfloat16*>(dy), dy_ld, static_cast<float*>(ws), th,
                                          tw);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   const int K = 9 * Cin;
   stem_wgrad_reduce_kernel<<<(Cout * K + 127) / 128, 128, 0, s>>>(static_cast<const float*>(ws), grid, Cout, K, dw,
                                                                 accumulate);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 

@@ -206,7 +206,7 @@ int launch(const WgradParams& p, cudaStream_t stream) {
   const int items = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = items < num_sms() ? items : num_sms();
   wgrad_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 
@@ -282,7 +282,7 @@ int wgrad_run(const WgradDesc& d, void* workspace, size_t ws_bytes, cudaStream_t
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
   wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, d.dw, p.ksplit, d.taps, d.M, d.Nn, d.dw_sm,
                                                   d.dw_sn, d.dw_st, d.accumulate);
-  UNETK_CUDA(cudaGetLastError());
+  UNETK_LAUNCHED();
   return 0;
 }
 

@@ -113,7 +113,17 @@ def main():
         y_or_eval = O.unet_forward(images, sd, training=False)
     assert torch.equal(y_ref_eval, y_or_eval), "eval-mode forward differs"
     report.append("forward train/eval + running stats: bit-exact")
+    # the reference's own bf16-autocast forward on the same weights/inputs: the yardstick for "how far from
+    # fp32 does stock bf16 land" that the GPU tests compare our deviation with
+    torch.manual_seed(42)
+    model_bf = ref_unet.UNet(3, 1).train()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        y_ref_bf16 = model_bf(images).float()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        y_or_bf16 = O.unet_forward(images, {k: v.clone() for k, v in sd0.items()}, training=True).float()
+    assert torch.equal(y_ref_bf16, y_or_bf16), "bf16-autocast forward differs"
     np.savez_compressed(os.path.join(GOLDEN, "unet_forward_seed42.npz"), images=images.numpy(), labels=labels.numpy(),
+                        logits_train_bf16_autocast=y_ref_bf16.numpy(),
                         logits_train=y_ref.numpy(), logits_eval_after_1_train_fwd=y_ref_eval.numpy(),
                         running_mean_inc1=model.state_dict()["inc.double_conv.1.running_mean"].numpy(),
                         running_var_up4_4=model.state_dict()["up4.conv.double_conv.4.running_var"].numpy(),
