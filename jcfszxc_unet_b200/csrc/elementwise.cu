@@ -318,126 +318,185 @@ struct BnBwdArgs {
 };
 
 // Loads one unit; returns masked gradients gm[q][8] and xhat[q][8] for nq pixels.
+// One unit = one pixel (POOL = false) or one 2x2 window (POOL = true) x 8 channels.  All global loads of
+// the unit are issued up front; per-pixel results are streamed to `emit(pix, gm[8], r[8])` (masked incoming
+// gradient and raw conv output) so that nothing but the packed input vectors stays live.
+// Register diet: only scale/shift (for the ReLU mask / pool argmax) are needed here; the mean/invstd algebra is
+// folded into per-channel coefficients by bn_bwd_finalize_kernel.
 template <bool POOL>
-__device__ __forceinline__ void bn_bwd_unit(const BnBwdArgs& A, int n, int hu, int wu, int g, float (&gm)[POOL ? 4 : 1][8],
-                                            float (&xh)[POOL ? 4 : 1][8], int64_t (&pixs)[POOL ? 4 : 1]) {
-  constexpr int NQ = POOL ? 4 : 1;
-  float sc[8], sh[8], mu[8], is[8];
+struct BnBwdUnit {
+  static constexpr int NQ = POOL ? 4 : 1;
+  uint4 ur[NQ], ug[NQ], ugp;
+  int64_t pix[NQ];
+
+  __device__ __forceinline__ void load(const BnBwdArgs& A, int64_t u, int g) {
+    const int Hu = POOL ? A.H >> 1 : A.H, Wu = POOL ? A.W >> 1 : A.W;
+    const int wu = static_cast<int>(u % Wu);
+    const int hu = static_cast<int>((u / Wu) % Hu);
+    const int n = static_cast<int>(u / (static_cast<int64_t>(Wu) * Hu));
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = __ldg(A.scale + g * 8 + j); sh[j] = __ldg(A.shift + g * 8 + j);
-    mu[j] = __ldg(A.mean + g * 8 + j); is[j] = __ldg(A.invstd + g * 8 + j);
+    for (int q = 0; q < NQ; ++q) {
+      const int h = POOL ? 2 * hu + (q >> 1) : hu, w = POOL ? 2 * wu + (q & 1) : wu;
+      pix[q] = (static_cast<int64_t>(n) * A.H + h) * A.W + w;
+      ur[q] = ldg16(A.raw + pix[q] * A.raw_ld + g * 8);
+      ug[q] = A.g1 ? ldg16(A.g1 + pix[q] * A.g1_ld + g * 8) : make_uint4(0, 0, 0, 0);
+    }
+    if constexpr (POOL) ugp = ldg16(A.gp + u * A.gp_ld + g * 8);
   }
-  uint4 ur[NQ], ug[NQ];
+
+  template <class Emit>
+  __device__ __forceinline__ void visit(const BnBwdArgs& A, const float (&sc)[8], const float (&sh)[8],
+                                        Emit&& emit) const {
+    int arg[8];
+    float gy[8];
+    if constexpr (POOL) {
+      // recompute the forward's pooled argmax on the same bf16-rounded activations (first max wins, NaN taken)
+      float best[8], f[8];
+      unpack8(ur[0], f);
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const int h = POOL ? 2 * hu + (q >> 1) : hu, w = POOL ? 2 * wu + (q & 1) : wu;
-    pixs[q] = (static_cast<int64_t>(n) * A.H + h) * A.W + w;
-    ur[q] = ldg16(A.raw + pixs[q] * A.raw_ld + g * 8);
-    ug[q] = A.g1 ? ldg16(A.g1 + pixs[q] * A.g1_ld + g * 8) : make_uint4(0, 0, 0, 0);
-  }
-  float r[NQ][8], a[NQ][8];
+      for (int j = 0; j < 8; ++j) {
+        const float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
+        best[j] = A.relu ? fmaxf(z, 0.f) : z;
+        arg[j] = 0;
+      }
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    unpack8(ur[q], r[q]);
-    unpack8(ug[q], gm[q]);
+      for (int q = 1; q < 4; ++q) {
+        unpack8(ur[q], f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float z = bf16_round(fmaf(r[q][j], sc[j], sh[j]));
-      a[q][j] = A.relu ? fmaxf(z, 0.f) : z;
-      xh[q][j] = (r[q][j] - mu[j]) * is[j];
+        for (int j = 0; j < 8; ++j) {
+          const float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
+          const float v = A.relu ? fmaxf(z, 0.f) : z;
+          if (v > best[j] || v != v) { best[j] = v; arg[j] = q; }
+        }
+      }
+      unpack8(ugp, gy);
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float r[8], gm[8];
+      unpack8(ur[q], r);
+      unpack8(ug[q], gm);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if constexpr (POOL) gm[j] += (arg[j] == q) ? gy[j] : 0.f;
+        if (A.relu) {
+          const float z = bf16_round(fmaf(r[j], sc[j], sh[j]));
+          if (!(z > 0.f)) gm[j] = 0.f;
+        }
+      }
+      emit(pix[q], gm, r);
     }
   }
-  if constexpr (POOL) {
-    float best[8], gy[8];
-    int arg[8];
-    argmax4(a, best, arg);
-    const int64_t opix = (static_cast<int64_t>(n) * (A.H >> 1) + hu) * (A.W >> 1) + wu;
-    unpack8(ldg16(A.gp + opix * A.gp_ld + g * 8), gy);
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (arg[j] == q) gm[q][j] += gy[j];
-  }
-  if (A.relu) {
-#pragma unroll
-    for (int q = 0; q < NQ; ++q)
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (!(a[q][j] > 0.f)) gm[q][j] = 0.f;
-  }
-}
+};
 
+// partial[blk][0][c] = sum gm, partial[blk][1][c] = sum gm * (raw - mean)
 template <bool POOL>
-__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BnBwdArgs A, float* __restrict__ partial) {
+__global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_kernel(const BnBwdArgs A, float* __restrict__ partial) {
   Lanes L(A.C);
-  const int Hu = POOL ? A.H >> 1 : A.H, Wu = POOL ? A.W >> 1 : A.W;
-  const int64_t units = static_cast<int64_t>(A.N) * Hu * Wu;
+  const int64_t units = static_cast<int64_t>(A.N) * (POOL ? (A.H >> 1) * (A.W >> 1) : A.H * A.W);
   float acc[2][8] = {};
   if (L.active) {
-    for (int64_t u = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl; u < units;
-         u += static_cast<int64_t>(gridDim.x) * L.ppb) {
-      const int wu = static_cast<int>(u % Wu);
-      const int hu = static_cast<int>((u / Wu) % Hu);
-      const int n = static_cast<int>(u / (static_cast<int64_t>(Wu) * Hu));
-      float gm[POOL ? 4 : 1][8], xh[POOL ? 4 : 1][8];
-      int64_t pixs[POOL ? 4 : 1];
-      bn_bwd_unit<POOL>(A, n, hu, wu, L.g, gm, xh, pixs);
+    float sc[8], sh[8], mu[8];
 #pragma unroll
-      for (int q = 0; q < (POOL ? 4 : 1); ++q)
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(A.scale + L.g * 8 + j); sh[j] = __ldg(A.shift + L.g * 8 + j); mu[j] = __ldg(A.mean + L.g * 8 + j);
+    }
+    auto emit = [&](int64_t, const float* gm, const float* r) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[0][j] += gm[q][j]; acc[1][j] = fmaf(gm[q][j], xh[q][j], acc[1][j]); }
+      for (int j = 0; j < 8; ++j) { acc[0][j] += gm[j]; acc[1][j] = fmaf(gm[j], r[j] - mu[j], acc[1][j]); }
+    };
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+    int64_t u = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
+    if constexpr (!POOL) {
+      for (; u + stride < units; u += 2 * stride) {   // two pixels in flight per thread
+        BnBwdUnit<false> a, b;
+        a.load(A, u, L.g);
+        b.load(A, u + stride, L.g);
+        a.visit(A, sc, sh, emit);
+        b.visit(A, sc, sh, emit);
+      }
+    }
+    for (; u < units; u += stride) {
+      BnBwdUnit<POOL> a;
+      a.load(A, u, L.g);
+      a.visit(A, sc, sh, emit);
     }
   }
   block_reduce_store<2>(acc, L, A.C, partial);
 }
 
-// dbeta = sum gm, dgamma = sum gm*xhat; coef[0][c] = dbeta/M, coef[1][c] = dgamma/M (used by the apply pass).
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int C, double count, float* dgamma,
-                                       float* dbeta, int accumulate, float* __restrict__ coef) {
+// sums[0][c] = S0 = sum gm, sums[1][c] = S1 = sum gm*(raw-mean).   dbeta = S0, dgamma = invstd * S1.
+// The apply pass computes  draw = scale*(gm - dbeta/M - xhat*dgamma/M)  as  scale*gm + K1*raw + K0  with
+//   K1 = -scale * invstd^2 * S1 / M,   K0 = -scale * S0 / M - K1 * mean          (coef[0][c] = K0, coef[1][c] = K1)
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int C, double count,
+                                       const float* __restrict__ scale, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, float* dgamma, float* dbeta, int accumulate,
+                                       float* __restrict__ coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double s = sums[c], sx = sums[C + c];
-  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(s) : static_cast<float>(s);
-  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(sx) : static_cast<float>(sx);
-  coef[c] = static_cast<float>(s / count);
-  coef[C + c] = static_cast<float>(sx / count);
+  const double s0 = sums[c], s1 = sums[C + c];
+  const double is = invstd[c], sc = scale[c], mu = mean[c];
+  const float db = static_cast<float>(s0), dg = static_cast<float>(is * s1);
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+  const double k1 = -sc * is * is * s1 / count;
+  coef[c] = static_cast<float>(-sc * s0 / count - k1 * mu);
+  coef[C + c] = static_cast<float>(k1);
 }
 
-// draw = scale * (gm - dbeta/M - xhat * dgamma/M)      (scale = gamma * invstd)
 template <bool POOL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(const BnBwdArgs A, const float* __restrict__ coef, __nv_bfloat16* __restrict__ draw,
                     int64_t draw_ld) {
   const int cg = A.C >> 3;
-  const int Hu = POOL ? A.H >> 1 : A.H, Wu = POOL ? A.W >> 1 : A.W;
-  const int64_t total = static_cast<int64_t>(A.N) * Hu * Wu * cg;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * kThreads) {
-    const int g = static_cast<int>(i % cg);
-    int64_t u = i / cg;
-    const int wu = static_cast<int>(u % Wu);
-    const int hu = static_cast<int>((u / Wu) % Hu);
-    const int n = static_cast<int>(u / (static_cast<int64_t>(Wu) * Hu));
-    float gm[POOL ? 4 : 1][8], xh[POOL ? 4 : 1][8];
-    int64_t pixs[POOL ? 4 : 1];
-    bn_bwd_unit<POOL>(A, n, hu, wu, g, gm, xh, pixs);
-    float sc[8], cb[8], cgm[8];
+  const int64_t units = static_cast<int64_t>(A.N) * (POOL ? (A.H >> 1) * (A.W >> 1) : A.H * A.W);
+  const int64_t total = units * cg;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x;
+  // consecutive threads walk consecutive channel groups of one unit; a thread's next item is `stride` ahead,
+  // which keeps its channel group fixed because stride % cg == 0 (flat_grid_cg)
+  if (i >= total) return;
+  const int g = static_cast<int>(i % cg);
+  float sc[8], sh[8], k0[8], k1[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = __ldg(A.scale + g * 8 + j);
-      cb[j] = __ldg(coef + g * 8 + j);
-      cgm[j] = __ldg(coef + A.C + g * 8 + j);
-    }
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(A.scale + g * 8 + j); sh[j] = __ldg(A.shift + g * 8 + j);
+    k0[j] = __ldg(coef + g * 8 + j); k1[j] = __ldg(coef + A.C + g * 8 + j);
+  }
+  auto emit = [&](int64_t pix, const float* gm, const float* r) {
+    float o[8];
 #pragma unroll
-    for (int q = 0; q < (POOL ? 4 : 1); ++q) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = sc[j] * (gm[q][j] - cb[j] - xh[q][j] * cgm[j]);
-      stg16(draw + pixs[q] * draw_ld + g * 8, pack8(o));
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], gm[j], fmaf(k1[j], r[j], k0[j]));
+    stg16(draw + pix * draw_ld + g * 8, pack8(o));
+  };
+  if constexpr (!POOL) {
+    for (; i + stride < total; i += 2 * stride) {
+      BnBwdUnit<false> a, b;
+      a.load(A, i / cg, g);
+      b.load(A, (i + stride) / cg, g);
+      a.visit(A, sc, sh, emit);
+      b.visit(A, sc, sh, emit);
     }
   }
+  for (; i < total; i += stride) {
+    BnBwdUnit<POOL> a;
+    a.load(A, i / cg, g);
+    a.visit(A, sc, sh, emit);
+  }
+}
+
+// grid for the flat (unit x channel-group) kernels whose threads keep their channel group: blocks*kThreads % cg == 0
+int flat_grid_cg(int64_t total, int cg) {
+  int64_t b = (total + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  // kThreads = 256 = 2^8; make b*256 a multiple of cg by rounding b up to a multiple of cg / gcd(cg, 256)
+  int g = cg, a = kThreads;
+  while (a) { int t = g % a; g = a; a = t; }
+  const int m = cg / g;
+  b = (b + m - 1) / m * m;
+  return static_cast<int>(b);
 }
 
 int reduce_grid(int64_t units, int C) {
@@ -590,9 +649,9 @@ int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1
   if (int rc = bn_bwd_args(&A, raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, N, H, W, C, relu)) return rc;
   const bool pool = gp != nullptr;
   const int64_t units = pool ? static_cast<int64_t>(N) * (H / 2) * (W / 2) : static_cast<int64_t>(N) * H * W;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, dgamma, dbeta, accumulate, coef);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef);
   UNETK_LAUNCHED();
-  const int fg = flat_grid(units * (C / 8));
+  const int fg = flat_grid_cg(units * (C / 8), C / 8);
   if (pool) bn_bwd_apply_kernel<true><<<fg, kThreads, 0, s>>>(A, coef, static_cast<__nv_bfloat16*>(draw), draw_ld);
   else bn_bwd_apply_kernel<false><<<fg, kThreads, 0, s>>>(A, coef, static_cast<__nv_bfloat16*>(draw), draw_ld);
   UNETK_LAUNCHED();

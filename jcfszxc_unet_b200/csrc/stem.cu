@@ -89,49 +89,67 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const StemGeom G, const f
 }
 
 // partial[blk][co][k] = sum over the block's tiles of dy[p][co] * x[p + off(k)][ci(k)],  k = ci*9 + r*3 + s
+// One warp per pixel sub-lane: lane = (ci 0..3) x (8 groups of 8 output channels); every thread keeps an
+// 8 (co) x 9 (tap) register tile, so a pixel costs 1 LDS.128 + 9 broadcast LDS for 72 FMAs.
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const StemGeom G, const __nv_bfloat16* __restrict__ dy,
                                                          int64_t dy_ld, float* __restrict__ partial, int tiles_h,
                                                          int tiles_w) {
   __shared__ float sx[(kTH + 2) * (kTW + 2) * 4];
-  __shared__ float sg[kTH * kTW][64 + 1];
+  __shared__ __align__(16) __nv_bfloat16 sg[kTH * kTW][64];
+  __shared__ float sacc[64 * 36];
   const int K = 9 * G.Cin;
-  const int co = threadIdx.x & 63, part = threadIdx.x >> 6;  // 4 parts share the K taps round-robin
-  float acc[9];                                                // ceil(36/4)
+  const int warp = threadIdx.x >> 5, lid = threadIdx.x & 31;
+  const int cog = lid & 7, ci = lid >> 3;
+  const bool live = ci < G.Cin;
+  float acc[8][9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[c][i] = 0.f;
   const int num_tiles = G.N * tiles_h * tiles_w;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
     const int h0 = th * kTH, w0 = tw * kTW;
     __syncthreads();
     load_halo(G, n, h0, w0, sx);
-    for (int i = threadIdx.x; i < kTH * kTW * 64; i += blockDim.x) {
-      const int p = i >> 6, c = i & 63;
+    for (int i = threadIdx.x; i < kTH * kTW * 8; i += blockDim.x) {
+      const int p = i >> 3, c8 = i & 7;
       const int h = h0 + p / kTW, w = w0 + p % kTW;
-      float v = 0.f;
-      if (c < G.Cout && h < G.H && w < G.W)
-        v = __bfloat162float(dy[((static_cast<int64_t>(n) * G.H + h) * G.W + w) * dy_ld + c]);
-      sg[p][c] = v;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (c8 * 8 < G.Cout && h < G.H && w < G.W)
+        v = __ldg(reinterpret_cast<const uint4*>(dy + ((static_cast<int64_t>(n) * G.H + h) * G.W + w) * dy_ld + c8 * 8));
+      *reinterpret_cast<uint4*>(&sg[p][c8 * 8]) = v;
     }
     __syncthreads();
-    for (int p = 0; p < kTH * kTW; ++p) {
-      const float gv = sg[p][co];
-      const int py = p / kTW, px = p % kTW;
+    if (live) {
+#pragma unroll 2
+      for (int p = warp; p < kTH * kTW; p += 8) {
+        const uint4 gu = *reinterpret_cast<const uint4*>(&sg[p][cog * 8]);
+        const float g[8] = {bf16_lo(gu.x), bf16_hi(gu.x), bf16_lo(gu.y), bf16_hi(gu.y),
+                            bf16_lo(gu.z), bf16_hi(gu.z), bf16_lo(gu.w), bf16_hi(gu.w)};
+        const float* xr = sx + ((p / kTW) * (kTW + 2) + (p % kTW)) * 4 + ci;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const int k = part + 4 * i;
-        if (k < K) {
-          const int ci = k / 9, rs = k % 9;
-          acc[i] = fmaf(gv, sx[((py + rs / 3) * (kTW + 2) + px + rs % 3) * 4 + ci], acc[i]);
+        for (int rs = 0; rs < 9; ++rs) {
+          const float xv = xr[((rs / 3) * (kTW + 2) + rs % 3) * 4];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c][rs] = fmaf(g[c], xv, acc[c][rs]);
         }
       }
     }
   }
+  // ordered (deterministic) reduction over the 8 warps of the block
+  for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w && live) {
 #pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    const int k = part + 4 * i;
-    if (k < K) partial[(static_cast<size_t>(blockIdx.x) * 64 + co) * K + k] = acc[i];
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int rs = 0; rs < 9; ++rs) sacc[(cog * 8 + c) * K + ci * 9 + rs] += acc[c][rs];
+    }
+    __syncthreads();
   }
+  for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) partial[static_cast<size_t>(blockIdx.x) * 64 * K + i] = sacc[i];
 }
 
 __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int Cout, int K,
