@@ -49,6 +49,13 @@ int unetk_pack_weight(const float* src, void* dst_ab, void* dst_ba, int A, int B
  * Cin, Cout multiples of 8 (the 3-channel stem has its own entry point below). */
 int unetk_conv3x3_fwd(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y,
                       int64_t y_ld, int N, int H, int W, int Cin, int Cout, void* stream);
+/* fwd fused with the BatchNorm statistics pass that follows it in DoubleConv (unet_parts.py:24-25): also
+ * writes sums = double[2][Cout] (per-channel sum and sum of squares of the bf16 output y), exactly what
+ * unetk_bn_stats(y) would produce; partial >= unetk_conv_stats_partial_floats(Cout) floats of scratch. */
+size_t unetk_conv_stats_partial_floats(int Cout);
+int unetk_conv3x3_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y,
+                              int64_t y_ld, float* partial, double* sums, int N, int H, int W, int Cin,
+                              int Cout, void* stream);
 int unetk_conv3x3_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
                         int N, int H, int W, int Cin, int Cout, void* stream);
 size_t unetk_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int taps);

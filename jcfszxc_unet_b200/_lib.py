@@ -25,6 +25,8 @@ SIGNATURES = {
     "unetk_launch_count": (_i64, []),
     "unetk_pack_weight": (_i, [_fp, _vp, _vp, _i, _i, _i, _vp]),
     "unetk_conv3x3_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv_stats_partial_floats": (_sz, [_i]),
+    "unetk_conv3x3_fwd_bnstats": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv3x3_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv_wgrad_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
     "unetk_conv3x3_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),

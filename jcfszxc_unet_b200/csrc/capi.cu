@@ -71,10 +71,12 @@ int unetk_pack_weight(const float* src, void* dst_ab, void* dst_ba, int A, int B
 }
 
 static int conv_fwd_like(const void* x, int64_t x_ld, const void* w, const float* bias, void* y, int64_t y_ld,
-                         int N, int H, int W, int K, int ncols, int ksize, bool dgrad, void* stream) {
+                         int N, int H, int W, int K, int ncols, int ksize, bool dgrad, void* stream,
+                         float* stats_partial = nullptr, double* stats_sums = nullptr) {
   UNETK_CHECK(x && w && y && N > 0 && H > 0 && W > 0 && K > 0 && ncols > 0, -1, "conv: bad arguments");
   ConvGemmDesc d{};
   d.a = x; d.a_ld = x_ld; d.b = w; d.out = y; d.out_ld = y_ld; d.bias = bias;
+  d.stats_partial = stats_partial; d.stats_sums = stats_sums;
   d.N = N; d.H = H; d.W = W; d.K = K; d.ncols = ncols; d.q_groups = 1;
   d.a_step = 1; d.out_step = 1;
   d.taps = ksize * ksize; d.b_taps = d.taps;
@@ -91,6 +93,16 @@ static int conv_fwd_like(const void* x, int64_t x_ld, const void* w, const float
 int unetk_conv3x3_fwd(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y, int64_t y_ld,
                       int N, int H, int W, int Cin, int Cout, void* stream) {
   return conv_fwd_like(x, x_ld, w_pack, bias, y, y_ld, N, H, W, Cin, Cout, 3, false, stream);
+}
+size_t unetk_conv_stats_partial_floats(int Cout) {
+  if (Cout < 8 || Cout % 8) return 0;
+  return conv_gemm_stats_partial_floats(Cout);
+}
+int unetk_conv3x3_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y,
+                              int64_t y_ld, float* partial, double* sums, int N, int H, int W, int Cin, int Cout,
+                              void* stream) {
+  UNETK_CHECK(partial && sums, -1, "conv3x3_fwd_bnstats: null statistics buffers");
+  return conv_fwd_like(x, x_ld, w_pack, bias, y, y_ld, N, H, W, Cin, Cout, 3, false, stream, partial, sums);
 }
 int unetk_conv3x3_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld, int N, int H,
                         int W, int Cin, int Cout, void* stream) {

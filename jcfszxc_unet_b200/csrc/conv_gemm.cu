@@ -8,13 +8,20 @@
 //   so there is no im2col buffer and no halo logic.  128B swizzle -> canonical K-major UMMA layout.
 // * B tiles (BN x 64) come from the packed weight [tap][n][k] (K-major) the same way.
 // * Warp-specialised persistent CTA: warp0 = TMA producer, warp1 = MMA issuer (one thread) + TMEM
-//   owner, warps2-5 = epilogue (TMEM -> registers -> bf16 -> global).  Double-buffered accumulator so
-//   the epilogue of tile i overlaps the MMAs of tile i+1.
+//   owner, warps2-5 = epilogue.  Double-buffered accumulator: the epilogue of tile i overlaps the MMAs
+//   of tile i+1.
+// * Epilogue: TMEM -> registers -> (+bias) -> bf16 -> 128B-swizzled smem staging -> TMA store.  The TMA
+//   writes full 128-byte rows per pixel (the first version stored 16 B per thread straight to global and
+//   was LSU-bound on the thin layers: 64->64 @512^2 ran at 475 TFLOP/s, profiles/r01_*), clips ragged
+//   tiles, and handles the ConvTranspose pixel shuffle through per-phase tensor maps.
+// * Optional fused BatchNorm statistics: per-channel sum / sum-of-squares of the bf16 tile are taken
+//   from the staging buffer while the TMA store drains it (deterministic: per-CTA partials, ordered
+//   second stage), which removes one full read of every conv output.
 // Reference semantics replaced: nn.Conv2d(k=3,p=1)/nn.Conv2d(k=1)/nn.ConvTranspose2d(k=2,s=2) as
 // used by UNetFamily/utils/unet_parts.py:24-31,56-58,77 (reference), forward and input-gradient.
+#include "conv_gemm.cuh"
 #include "host_common.cuh"
 #include "ptx.cuh"
-#include "conv_gemm.cuh"
 
 namespace unetk {
 
@@ -24,15 +31,18 @@ constexpr int kTileM = 128;   // output pixels per tile (UMMA M)
 constexpr int kTileK = 64;    // channels per k-block: 64 bf16 = one 128B swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
 constexpr uint32_t kABytes = kTileM * kTileK * 2;
+constexpr uint32_t kStagingBytes = kTileM * 64 * 2;  // one 128 x 64 bf16 chunk
 
 template <int BN>
 struct Cfg {
   static constexpr uint32_t kBBytes = BN * kTileK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 7);
   static constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: all powers of two >= 32
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kPipeBytes = kStages * kStageBytes;
+  static constexpr uint32_t kSmemBytes = kPipeBytes + 2 * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -43,7 +53,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   // SWIZZLE_128B tiles need 1024B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* staging = smem + C::kPipeBytes;  // 2 x 16 KB, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
   uint64_t* full_bar = bars;                     // [kStages]
   uint64_t* empty_bar = bars + C::kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * C::kStages;   // [2]
@@ -56,6 +67,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmOut[0]);
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -136,9 +148,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       }
     }
   } else {
-    // -------------------------------------------------------------- epilogue (warps 2..5)
+    // -------------------------------------------------------------- epilogue (warps 2..5, 128 threads)
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;     // tile row == TMEM lane
+    const int et = threadIdx.x - 64;         // 0..127
+    const bool leader = (et == 0);
+    const int st_ch = et & 63, st_half = et >> 6;  // statistics: this thread owns channel st_ch of every 64-chunk
+    float ssum[BN / 64], ssq[BN / 64];
+#pragma unroll
+    for (int c = 0; c < BN / 64; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+    uint32_t chunk_ctr = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -148,50 +167,106 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int img = mt / (p.tiles_w * p.tiles_h);
-      const int hh = th * p.TH + row / p.TW;
-      const int ww = tw * p.TW + row % p.TW;
+      const int h0 = th * p.TH, w0 = tw * p.TW;
       const int q = nt / p.tiles_per_q;
       const int co0 = (nt % p.tiles_per_q) * BN;
-      const bool valid = (hh < p.H) && (ww < p.W);
-      const int oh = p.out_step * hh + (q >> 1);
-      const int ow = p.out_step * ww + (q & 1);
-      __nv_bfloat16* optr =
-          p.out + (static_cast<size_t>(img) * p.Hout * p.Wout + static_cast<size_t>(oh) * p.Wout + ow) *
-                      p.out_ld + co0;
+      const bool ragged = (h0 + p.TH > p.H) || (w0 + p.TW > p.W);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (valid) {
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const int col = co0 + c * 32 + v * 8;
-            if (col < p.ncols) {
-              float f[8];
+      for (int c = 0; c < BN / 64; ++c) {
+        const int colbase = co0 + c * 64;
+        const bool live = colbase < p.ncols;  // false: whole chunk beyond the real channels (ragged N tile)
+        uint8_t* buf = staging + (chunk_ctr & 1u) * kStagingBytes;
+        if (live) {
+          // the buffer is free once the TMA store issued two chunks ago has read it (and everybody has passed
+          // the statistics pass over it, which the barrier below also guarantees)
+          if (leader) bulk_wait_read<1>();
+          named_bar_sync(1, kEpiThreads);
+        }
+        uint32_t r0[32], r1[32];
+        if (live) {
+          tmem_ld32(taddr + c * 64, r0);
+          tmem_ld32(taddr + c * 64 + 32, r1);
+          tmem_ld_wait();
+        }
+        if (c == BN / 64 - 1) {  // accumulator fully drained into registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (!live) continue;
+        ++chunk_ctr;
+        uint8_t* rowp = buf + row * 128;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]);
-              if (p.bias != nullptr) {
+        for (int v = 0; v < 8; ++v) {
+          const uint32_t* src = (v < 4) ? &r0[v * 8] : &r1[(v - 4) * 8];
+          float f[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += __ldg(p.bias + col + j);
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(optr + c * 32 + v * 8) = o;
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(src[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int col = colbase + v * 8 + j;
+              f[j] += (col < p.ncols) ? __ldg(p.bias + col) : 0.f;
             }
           }
+          uint4 o;
+          o.x = pack_bf16x2(f[0], f[1]);
+          o.y = pack_bf16x2(f[2], f[3]);
+          o.z = pack_bf16x2(f[4], f[5]);
+          o.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(rowp + ((v ^ (row & 7)) << 4)) = o;  // 128B swizzle, conflict-free
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, kEpiThreads);
+        if (leader) {
+          tma_store_4d(&p.tmOut[q], buf, colbase, w0, h0, img);
+          bulk_commit();
+        }
+        if (p.stats_partial != nullptr && colbase + st_ch < p.ncols) {
+          // per-channel sum / sum of squares of the bf16 values just staged (rows outside the image excluded)
+          float s = 0.f, ss = 0.f;
+          const int chunk16 = st_ch >> 3, within = (st_ch & 7) * 2;
+          const int r_begin = st_half * 64;
+          if (!ragged) {
+#pragma unroll 8
+            for (int r = r_begin; r < r_begin + 64; ++r) {
+              const uint16_t raw = *reinterpret_cast<const uint16_t*>(buf + r * 128 + ((chunk16 ^ (r & 7)) << 4) + within);
+              const float v = __uint_as_float(static_cast<uint32_t>(raw) << 16);
+              s += v;
+              ss = fmaf(v, v, ss);
+            }
+          } else {
+            for (int r = r_begin; r < r_begin + 64; ++r) {
+              const bool ok = (h0 + (r >> p.tw_shift) < p.H) && (w0 + (r & (p.TW - 1)) < p.W);
+              const uint16_t raw = *reinterpret_cast<const uint16_t*>(buf + r * 128 + ((chunk16 ^ (r & 7)) << 4) + within);
+              const float v = ok ? __uint_as_float(static_cast<uint32_t>(raw) << 16) : 0.f;
+              s += v;
+              ss = fmaf(v, v, ss);
+            }
+          }
+          ssum[c] += s;
+          ssq[c] += ss;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+    // all bulk stores of this thread must be complete before the CTA exits
+    if (leader) bulk_wait<0>();
+    if (p.stats_partial != nullptr) {
+      // combine the two row-halves through the (now idle) staging buffer, then one partial row per CTA
+      named_bar_sync(1, kEpiThreads);
+      float* red = reinterpret_cast<float*>(staging);  // [2 halves][2][BN]
+#pragma unroll
+      for (int c = 0; c < BN / 64; ++c) {
+        red[(st_half * 2 + 0) * BN + c * 64 + st_ch] = ssum[c];
+        red[(st_half * 2 + 1) * BN + c * 64 + st_ch] = ssq[c];
+      }
+      named_bar_sync(1, kEpiThreads);
+      for (int i = et; i < 2 * BN; i += kEpiThreads)
+        p.stats_partial[static_cast<size_t>(blockIdx.x) * 2 * BN + i] = red[i] + red[2 * BN + i];
     }
   }
 
@@ -203,8 +278,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
 }
 
+// sums[k][c] = sum over the CTAs that own channel c's N tile (CTA b owns tile b % num_n_tiles), fixed order
+__global__ void conv_stats_sums_kernel(const float* __restrict__ partial, int grid, int num_n_tiles, int BN, int C,
+                                       double* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * C) return;
+  const int k = i / C, c = i % C;
+  const int nt = c / BN, cc = c % BN;
+  double s = 0.0;
+  for (int b = nt; b < grid; b += num_n_tiles) s += partial[(static_cast<size_t>(b) * 2 + k) * BN + cc];
+  sums[i] = s;
+}
+
 template <int BN>
-int launch(const ConvGemmParams& p, cudaStream_t stream) {
+int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -212,14 +299,25 @@ int launch(const ConvGemmParams& p, cudaStream_t stream) {
                                     C::kSmemBytes));
     configured = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
   conv_gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
   UNETK_LAUNCHED();
   return 0;
 }
 
+int pick_bn(int ncols, int q_groups) {
+  if (q_groups > 1) {
+    // ConvTranspose fwd: an N tile must not straddle two output phases q (a ragged last tile reads the next
+    // phase's weight rows; those columns are never stored)
+    return (ncols % 256 == 0) ? 256 : (ncols % 128 == 0 ? 128 : 64);
+  }
+  return ncols >= 256 ? 256 : (ncols > 64 ? 128 : 64);
+}
+
 }  // namespace
+
+size_t conv_gemm_stats_partial_floats(int ncols) {
+  return static_cast<size_t>(num_sms()) * 2 * pick_bn(ncols, 1);
+}
 
 int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   UNETK_CHECK(d.K % 8 == 0 && d.K >= 8, -1, "conv_gemm: K=%d must be a multiple of 8", d.K);
@@ -229,28 +327,22 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
                   (reinterpret_cast<uintptr_t>(d.b) & 15) == 0,
               -1, "conv_gemm: pointers must be 16-byte aligned");
   UNETK_CHECK(d.taps >= 1 && d.taps <= 9, -1, "conv_gemm: taps=%d", d.taps);
+  UNETK_CHECK(d.stats_sums == nullptr || (d.q_groups == 1 && d.stats_partial != nullptr), -1,
+              "conv_gemm: fused statistics need q_groups == 1 and a partial buffer");
 
   ConvGemmParams p{};
-  // ---- N tiling
-  int BN;
-  if (d.q_groups > 1) {
-    // ConvTranspose fwd: an N tile must not straddle two output phases q.
-    // (a ragged last tile reads the next phase's weight rows; those columns are masked in the epilogue)
-    BN = (d.ncols % 256 == 0) ? 256 : (d.ncols % 128 == 0 ? 128 : 64);
-  } else {
-    BN = d.ncols >= 256 ? 256 : (d.ncols > 64 ? 128 : 64);
-  }
+  const int BN = pick_bn(d.ncols, d.q_groups);
   p.tiles_per_q = (d.ncols + BN - 1) / BN;
   p.rows_per_q = d.ncols;
   p.num_n_tiles = p.tiles_per_q * d.q_groups;
   p.ncols = d.ncols;
 
   // ---- M tiling: TH x TW = 128 output positions, TW a power of two
-  int TW = 128;
-  while (TW > d.W) TW >>= 1;
-  if (TW < 1) TW = 1;
+  int TW = 128, shift = 7;
+  while (TW > d.W) { TW >>= 1; --shift; }
+  if (TW < 1) { TW = 1; shift = 0; }
   const int TH = kTileM / TW;
-  p.TH = TH; p.TW = TW;
+  p.TH = TH; p.TW = TW; p.tw_shift = shift;
   p.H = d.H; p.W = d.W;
   p.tiles_h = (d.H + TH - 1) / TH;
   p.tiles_w = (d.W + TW - 1) / TW;
@@ -259,13 +351,15 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.kchunks = (d.K + kTileK - 1) / kTileK;
   p.a_step = d.a_step;
   for (int t = 0; t < d.taps; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
-  p.out = reinterpret_cast<__nv_bfloat16*>(d.out);
-  p.out_ld = d.out_ld;
-  p.out_step = d.out_step;
-  p.Hout = d.H * d.out_step;
-  p.Wout = d.W * d.out_step;
   p.bias = d.bias;
+  p.stats_partial = d.stats_sums ? d.stats_partial : nullptr;
   UNETK_CHECK(TW * d.a_step <= 256 && TH * d.a_step <= 256, -1, "conv_gemm: TMA box too large");
+
+  // persistent grid; a multiple of num_n_tiles so that every CTA keeps one N tile (fused statistics rely on it)
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  grid = grid / p.num_n_tiles * p.num_n_tiles;
+  if (grid < p.num_n_tiles) grid = p.num_n_tiles;
 
   // ---- tensor maps
   {
@@ -276,8 +370,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
                            static_cast<uint64_t>(d.a_ld) * 2 * AW * AH};
     uint32_t box[4] = {kTileK, static_cast<uint32_t>(TW * d.a_step), static_cast<uint32_t>(TH * d.a_step), 1};
     uint32_t es[4] = {1, static_cast<uint32_t>(d.a_step), static_cast<uint32_t>(d.a_step), 1};
-    int rc = make_tmap_bf16(&p.tmA, d.a, 4, dims, strides, box, es, true);
-    if (rc) return rc;
+    if (int rc = make_tmap_bf16(&p.tmA, d.a, 4, dims, strides, box, es, true)) return rc;
   }
   {
     const uint64_t rows = static_cast<uint64_t>(d.ncols) * d.q_groups;
@@ -285,14 +378,36 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
     uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * rows};
     uint32_t box[3] = {kTileK, static_cast<uint32_t>(BN), 1};
     uint32_t es[3] = {1, 1, 1};
-    int rc = make_tmap_bf16(&p.tmB, d.b, 3, dims, strides, box, es, true);
-    if (rc) return rc;
+    if (int rc = make_tmap_bf16(&p.tmB, d.b, 3, dims, strides, box, es, true)) return rc;
   }
+  {
+    // Output seen on the grid of GEMM rows: pixel (h, w) of phase q lives at out[(s*h + qy) * Wout + s*w + qx].
+    const int s = d.out_step;
+    const int64_t Wout = static_cast<int64_t>(d.W) * s, Hout = static_cast<int64_t>(d.H) * s;
+    uint64_t dims[4] = {static_cast<uint64_t>(d.ncols), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
+                        static_cast<uint64_t>(d.N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(d.out_ld) * 2 * s, static_cast<uint64_t>(d.out_ld) * 2 * Wout * s,
+                           static_cast<uint64_t>(d.out_ld) * 2 * Wout * Hout};
+    uint32_t box[4] = {64, static_cast<uint32_t>(TW), static_cast<uint32_t>(TH), 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    for (int q = 0; q < d.q_groups; ++q) {
+      const uint8_t* base = static_cast<const uint8_t*>(d.out) + (static_cast<int64_t>(q >> 1) * Wout + (q & 1)) * d.out_ld * 2;
+      if (int rc = make_tmap_bf16(&p.tmOut[q], base, 4, dims, strides, box, es, true)) return rc;
+    }
+  }
+  int rc;
   switch (BN) {
-    case 256: return launch<256>(p, stream);
-    case 128: return launch<128>(p, stream);
-    default: return launch<64>(p, stream);
+    case 256: rc = launch<256>(p, grid, stream); break;
+    case 128: rc = launch<128>(p, grid, stream); break;
+    default: rc = launch<64>(p, grid, stream); break;
   }
+  if (rc) return rc;
+  if (d.stats_sums != nullptr) {
+    conv_stats_sums_kernel<<<(2 * d.ncols + 127) / 128, 128, 0, stream>>>(d.stats_partial, grid, p.num_n_tiles, BN,
+                                                                        d.ncols, d.stats_sums);
+    UNETK_LAUNCHED();
+  }
+  return 0;
 }
 
 }  // namespace unetk

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdint>
 
 namespace unetk {
@@ -25,22 +26,26 @@ struct ConvGemmDesc {
   int a_step;         // A coordinate = a_step*pos + offset (2 for ConvTranspose dgrad)
   int out_step;       // out coordinate = out_step*pos + phase (2 for ConvTranspose fwd)
   int8_t dh[9], dw[9], btap[9];
+  // Optional fused BatchNorm statistics of the bf16 output (q_groups == 1 only):
+  float* stats_partial;   // scratch, >= conv_gemm_stats_partial_floats(ncols) floats
+  double* stats_sums;     // out: double [2][ncols] = per-channel (sum, sum of squares)
 };
 
 // Kernel parameter block (passed by value, holds the TMA descriptors).
 struct ConvGemmParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
-  __nv_bfloat16* out;
+  CUtensorMap tmOut[4];  // one per output phase q (only [0] unless ConvTranspose fwd)
   const float* bias;
-  int64_t out_ld;
-  int H, W, Hout, Wout;
-  int TH, TW, tiles_h, tiles_w;
+  float* stats_partial;  // [gridDim][2][BN] or null
+  int H, W;
+  int TH, TW, tw_shift, tiles_h, tiles_w;
   int num_m_tiles, num_n_tiles, tiles_per_q, rows_per_q, ncols;
-  int taps, kchunks, a_step, out_step;
+  int taps, kchunks, a_step;
   int8_t dh[9], dw[9], btap[9];
 };
 
+size_t conv_gemm_stats_partial_floats(int ncols);
 int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream);
 
 }  // namespace unetk

@@ -140,7 +140,8 @@ class ConvBNReLU:
         N, H, W = out.N, out.H, out.W
         lib = _lib.load()
         units = N * H * W
-        plan.need(lib.unetk_chan_partial_floats(units, self.cout), 0, self.cout)
+        plan.need(max(lib.unetk_chan_partial_floats(units, self.cout), lib.unetk_conv_stats_partial_floats(self.cout)),
+                  0, self.cout)
         if plan.with_grad:
             if self.stem:
                 plan.need(0, lib.unetk_stem_wgrad_workspace(N, H, W, self.cin))
@@ -173,15 +174,25 @@ class ConvBNReLU:
     def fwd(self):
         P, bn = self.plan, self.bn
         bias = self.conv.bias
+        batch_stats = P.training or not bn.track_running_stats
+        fused_stats = batch_stats and not self.stem
         if self.stem:
             ops.stem_fwd(P.image.x, self.conv.weight, bias.detach() if bias is not None else None, self.raw.t)
+        elif fused_stats:
+            # conv epilogue also produces the per-channel (sum, sum of squares) of its bf16 output
+            xp, xld = ops.nhwc(self.x.t)
+            yp, yld = ops.nhwc(self.raw.t)
+            _lib.call("unetk_conv3x3_fwd_bnstats", xp, xld, self.wpack.data_ptr(),
+                      bias.detach().data_ptr() if bias is not None else None, yp, yld, P.partial.data_ptr(),
+                      P.sums.data_ptr(), self.raw.N, self.raw.H, self.raw.W, self.cin, self.cout, _s())
         else:
             ops.conv_fwd(self.x.t, self.wpack, bias.detach() if bias is not None else None, self.raw.t, 3)
         sc, sh, mu, iv = self.stat[0], self.stat[1], self.stat[2], self.stat[3]
         gamma = bn.weight.detach() if bn.weight is not None else None
         beta = bn.bias.detach() if bn.bias is not None else None
-        if P.training or not bn.track_running_stats:
-            ops.bn_stats(self.raw.t, P.partial, P.sums)
+        if batch_stats:
+            if not fused_stats:
+                ops.bn_stats(self.raw.t, P.partial, P.sums)
             count = self.raw.N * self.raw.H * self.raw.W
             if P.sync_sums is not None:
                 count = P.sync_sums(P.sums[: 2 * self.cout], count)

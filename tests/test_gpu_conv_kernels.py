@@ -75,6 +75,40 @@ def test_conv3x3_fwd(n, h, w, cin, cout, xpad, ypad):
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout,xpad,ypad", CONV_SHAPES)
+def test_conv3x3_fwd_fused_bn_statistics(n, h, w, cin, cout, xpad, ypad):
+    """The conv epilogue's per-channel (sum, sum of squares) must equal what unetk_bn_stats computes from the
+    stored bf16 output (same values, different summation order), including ragged tiles and channel tails."""
+    from jcfszxc_unet_b200 import _lib
+
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    g = torch.Generator(device=dev).manual_seed(4321 + cin + cout)
+    _, x = _nhwc_slice(n, h, w, cin, dev, *xpad)
+    x.copy_(torch.randn(n, h, w, cin, device=dev, generator=g))
+    wt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * (1.0 / (3 * cin ** 0.5))
+    bias = torch.randn(cout, device=dev, generator=g)
+    _, y = _nhwc_slice(n, h, w, cout, dev, *ypad)
+    w_pack, _ = ops.pack_weight(wt, True, False)
+    partial = torch.empty(max(lib.unetk_conv_stats_partial_floats(cout), lib.unetk_chan_partial_floats(n * h * w, cout), 4096), device=dev)
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+    xp, xld = ops.nhwc(x)
+    yp, yld = ops.nhwc(y)
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.call("unetk_conv3x3_fwd_bnstats", xp, xld, w_pack.data_ptr(), bias.data_ptr(), yp, yld, partial.data_ptr(),
+              sums.data_ptr(), n, h, w, cin, cout, stream)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float(), bias, padding=1).permute(0, 2, 3, 1)
+    _close(y, ref, "conv3x3_fwd_bnstats output")
+    yf = y.float().double()
+    s_ref = torch.cat([yf.sum(dim=(0, 1, 2)), (yf * yf).sum(dim=(0, 1, 2))])
+    assert torch.allclose(sums, s_ref, rtol=1e-4, atol=1e-3 * float(s_ref.abs().max())), (sums - s_ref).abs().max()
+    sums2 = torch.zeros_like(sums)
+    ops.bn_stats(y, partial, sums2)
+    assert torch.allclose(sums, sums2, rtol=1e-4, atol=1e-3 * float(s_ref.abs().max()))
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,xpad,ypad", CONV_SHAPES)
 def test_conv3x3_dgrad(n, h, w, cin, cout, xpad, ypad):
     ops = _ops()
     dev = torch.device("cuda:0")
