@@ -9,6 +9,10 @@ namespace unetk {
 const char* last_error();
 int probe_run(const void* a, const void* b, float* d, int mode, int shift, int bo, cudaStream_t stream);
 int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, cudaStream_t stream);
+// wgrad3x3.cu
+size_t wgrad3x3_workspace_bytes(int N, int H, int W, int M, int Nn);
+int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, float* dw, int accumulate, int N, int H,
+                 int W, int M, int Nn, void* workspace, size_t ws_bytes, cudaStream_t stream);
 // stem.cu
 int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
                  void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
@@ -148,12 +152,20 @@ size_t unetk_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ta
   }
   const int ksize = taps == 9 ? 3 : 1;
   WgradDesc d = conv_wgrad_desc(nullptr, 0, nullptr, 0, nullptr, 0, N, H, W, Cin, Cout, ksize);
-  return wgrad_workspace_bytes(d);
+  size_t need = wgrad_workspace_bytes(d);
+  if (taps == 9) {
+    const size_t need3 = wgrad3x3_workspace_bytes(N, H, W, Cout, Cin);
+    if (need3 > need) need = need3;
+  }
+  return need;
 }
 
 int unetk_conv3x3_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw, int accumulate,
                         int N, int H, int W, int Cin, int Cout, void* workspace, size_t ws_bytes, void* stream) {
   UNETK_CHECK(x && dy && dw, -1, "conv3x3_wgrad: null pointer");
+  // halo-reuse kernel (one activation load per filter row); shapes it does not cover use the per-tap kernel
+  const int rc3 = wgrad3x3_run(dy, dy_ld, x, x_ld, dw, accumulate, N, H, W, Cout, Cin, workspace, ws_bytes, S(stream));
+  if (rc3 <= 0) return rc3;
   WgradDesc d = conv_wgrad_desc(x, x_ld, dy, dy_ld, dw, accumulate, N, H, W, Cin, Cout, 3);
   return wgrad_run(d, workspace, ws_bytes, S(stream));
 }

@@ -230,6 +230,16 @@ void plan(const WgradDesc& d, int* BN, int* ksplit, int* TH, int* TW, int* pix_t
 
 }  // namespace
 
+int wgrad_reduce_launch(const float* partial, float* dw, int ksplit, int taps, int M, int Nn, int64_t sm, int64_t sn,
+                        int64_t st, int accumulate, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(taps) * M * Nn;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
 size_t wgrad_workspace_bytes(const WgradDesc& d) {
   int BN, ks, TH, TW, pt;
   plan(d, &BN, &ks, &TH, &TW, &pt);

@@ -1,0 +1,298 @@
+// 3x3 weight gradient, second generation: ONE halo load of the activations feeds the three taps of a
+// filter row.
+//
+//   dW[co][ci][r][s] = sum_{n,h,w} dY[n,h,w,co] * X[n,h+r-1,w+s-1,ci]
+//
+// Work item = (pixel range, filter row r, 128 output channels, NT input channels).  Per 64-pixel k-block
+// (TH x TW pixels, TW in {16,32,64}) the CTA loads
+//   P: dY tile            box (64ch, TW,   TH)  -> [64 px][64 ch]   x 2 (M = 128)
+//   Q: X halo of row r    box (64ch, TW+2, TH)  -> [TH*(TW+2) px][64 ch] per 64 input channels
+// and issues, for every tap s = 0,1,2, MMAs whose B descriptor simply STARTS s pixel-rows (s*128 B)
+// further into the same halo tile: tcgen05 applies the 128B-swizzle XOR on absolute smem address bits
+// (probe: profiles/r01_umma_descriptor_probe.txt), so a row-shifted start is exact.  For Cin tiles of 64
+// the three taps are even fused into ONE MMA of N = 192 by giving the descriptor a leading-dimension
+// stride of 128 B (three overlapping 64-wide atoms).
+// Versus the first kernel (one tap per work item, wgrad.cu) this cuts the operand traffic per FLOP by ~3x:
+// that kernel re-read dY and X nine times and was HBM-bound on the 512^2 layers (138 TFLOP/s, 64->64).
+// Accumulators: 3 taps x NT fp32 columns in TMEM; fp32 partials + ordered reduce (deterministic).
+#include "host_common.cuh"
+#include "ptx.cuh"
+#include "wgrad.cuh"
+
+namespace unetk {
+
+int wgrad_reduce_launch(const float* partial, float* dw, int ksplit, int taps, int M, int Nn, int64_t sm, int64_t sn,
+                        int64_t st, int accumulate, cudaStream_t stream);
+
+namespace {
+
+constexpr int kPix = 64;
+constexpr int kThreads = 192;
+constexpr uint32_t kPBoxBytes = kPix * 128;  // [64 px][64 ch] bf16
+
+struct W3Params {
+  CUtensorMap tmP;  // dY: dims (M, W, H, N), box (64, TW, TH, 1)
+  CUtensorMap tmQ;  // X : dims (Nn, W, H, N), box (64, TW+2, TH, 1)
+  float* partial;   // [ksplit][9][M][Nn]
+  int TH, TW, tiles_h, tiles_w, pix_tiles;
+  int m_tiles, n_tiles, ksplit;
+  int M, Nn;
+  uint32_t q_box_bytes;  // TH*(TW+2)*128 rounded up to 1024
+  uint32_t q_tx_bytes;   // TH*(TW+2)*128 (what the TMA really writes)
+};
+
+template <int NT>
+struct W3Cfg {
+  static constexpr int kQBoxes = NT / 64;
+  static constexpr int kStages = (NT == 128) ? 5 : 7;
+  static constexpr uint32_t kTmemCols = (3 * NT > 256) ? 512 : 256;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_constant__ W3Params p) {
+  using C = W3Cfg<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const uint32_t stage_bytes = 2 * kPBoxBytes + C::kQBoxes * p.q_box_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tfull_bar = bars + 2 * C::kStages;   // [1]
+  uint64_t* tempty_bar = tfull_bar + 1;          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmP);
+    tma_prefetch_desc(&p.tmQ);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int items_per_split = 3 * p.m_tiles * p.n_tiles;
+  const int num_items = items_per_split * p.ksplit;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = 2 * kPBoxBytes + C::kQBoxes * p.q_tx_bytes;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int nt = item % p.n_tiles;
+        const int mt = (item / p.n_tiles) % p.m_tiles;
+        const int r = (item / (p.n_tiles * p.m_tiles)) % 3;
+        const int ks = item / items_per_split;
+        const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
+        const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
+        for (int kt = kt0; kt < kt1; ++kt) {
+          const int tw = kt % p.tiles_w;
+          const int th = (kt / p.tiles_w) % p.tiles_h;
+          const int img = kt / (p.tiles_w * p.tiles_h);
+          const int h0 = th * p.TH, w0 = tw * p.TW;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sp = smem + stage * stage_bytes;
+          uint8_t* sq = sp + 2 * kPBoxBytes;
+          mbar_expect_tx(&full_bar[stage], tx);
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            tma_load_4d(sp + b * kPBoxBytes, &p.tmP, &full_bar[stage], mt * 128 + b * 64, w0, h0, img);
+#pragma unroll
+          for (int b = 0; b < C::kQBoxes; ++b)
+            tma_load_4d(sq + b * p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT + b * 64, w0 - 1, h0 + r - 1, img);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const int row_pitch = p.TW + 2;                 // halo pixels per image row in the Q tile
+      const int steps_per_row = p.TW >> 4;            // 16-pixel k-steps per image row
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int ks = item / items_per_split;
+        const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
+        const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
+        mbar_wait(tempty_bar, (it & 1) ^ 1u);
+        tc_fence_after();
+        for (int kt = kt0; kt < kt1; ++kt) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t p_base = smem_u32(smem + stage * stage_bytes);
+          const uint32_t q_base = p_base + 2 * kPBoxBytes;
+          const uint32_t accum = (kt > kt0) ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < kPix / 16; ++k) {
+            // 16 consecutive pixels of one image row: P rows k*16.., Q rows i*(TW+2) + j0 (+ s per tap)
+            const int i = k / steps_per_row, j0 = (k % steps_per_row) * 16;
+            const uint64_t da = make_smem_desc(p_base + k * 2048, kPBoxBytes, 1024, kLayoutSW128);
+            const uint32_t q_row = q_base + static_cast<uint32_t>(i * row_pitch + j0) * 128;
+            if constexpr (NT == 64) {
+              // taps s = 0,1,2 as three overlapping 64-wide N atoms, 128 B (one pixel row) apart
+              constexpr uint32_t idesc = make_idesc_bf16(128, 192, true, true);
+              const uint64_t db = make_smem_desc(q_row, 128, 1024, kLayoutSW128);
+              umma_bf16(tmem_base, da, db, idesc, accum | (k != 0));
+            } else {
+              constexpr uint32_t idesc = make_idesc_bf16(128, NT, true, true);
+#pragma unroll
+              for (int s = 0; s < 3; ++s) {
+                const uint64_t db = make_smem_desc(q_row + s * 128, p.q_box_bytes, 1024, kLayoutSW128);
+                umma_bf16(tmem_base + s * NT, da, db, idesc, accum | (k != 0));
+              }
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int nt = item % p.n_tiles;
+      const int mt = (item / p.n_tiles) % p.m_tiles;
+      const int r = (item / (p.n_tiles * p.m_tiles)) % 3;
+      const int ks = item / items_per_split;
+      const int m = mt * 128 + row;
+      mbar_wait(tfull_bar, it & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+        float* dst = p.partial + ((static_cast<size_t>(ks) * 9 + r * 3 + s) * p.M + m) * p.Nn + nt * NT;
+#pragma unroll 1
+        for (int c = 0; c < NT / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + s * NT + c * 32, v);
+          tmem_ld_wait();
+          if (m < p.M) {
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+              const int col = nt * NT + c * 32 + x * 4;
+              if (col < p.Nn) {
+                float4 o = make_float4(__uint_as_float(v[x * 4]), __uint_as_float(v[x * 4 + 1]),
+                                       __uint_as_float(v[x * 4 + 2]), __uint_as_float(v[x * 4 + 3]));
+                *reinterpret_cast<float4*>(dst + c * 32 + x * 4) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+struct W3Plan {
+  int NT, TH, TW, tiles_h, tiles_w, pix_tiles, m_tiles, n_tiles, ksplit;
+  uint32_t q_box_bytes, q_tx_bytes, smem_bytes;
+};
+
+bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
+  if (W < 16 || M % 8 || Nn % 8) return false;
+  int tw = 64;
+  while (tw > W) tw >>= 1;
+  pl->TW = tw;
+  pl->TH = kPix / tw;
+  pl->NT = Nn > 64 ? 128 : 64;
+  pl->tiles_h = (H + pl->TH - 1) / pl->TH;
+  pl->tiles_w = (W + tw - 1) / tw;
+  pl->pix_tiles = N * pl->tiles_h * pl->tiles_w;
+  pl->m_tiles = (M + 127) / 128;
+  pl->n_tiles = (Nn + pl->NT - 1) / pl->NT;
+  pl->q_tx_bytes = static_cast<uint32_t>(pl->TH * (tw + 2) * 128);
+  pl->q_box_bytes = (pl->q_tx_bytes + 1023u) & ~1023u;
+  const int stages = pl->NT == 128 ? 5 : 7;
+  const uint32_t stage = 2 * kPBoxBytes + (pl->NT / 64) * pl->q_box_bytes;
+  pl->smem_bytes = stages * stage + 1024 + 256;
+  if (pl->smem_bytes > 227 * 1024) return false;
+  // items = 3 * m_tiles * n_tiles * ksplit: aim at ~2 items per SM, at least 8 k-blocks each
+  const int base = 3 * pl->m_tiles * pl->n_tiles;
+  int ks = (2 * num_sms()) / base;
+  const int cap = pl->pix_tiles / 8 > 0 ? pl->pix_tiles / 8 : 1;
+  if (ks > cap) ks = cap;
+  if (ks < 1) ks = 1;
+  pl->ksplit = ks;
+  return true;
+}
+
+template <int NT>
+int launch(const W3Params& p, const W3Plan& pl, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    UNETK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int items = 3 * pl.m_tiles * pl.n_tiles * pl.ksplit;
+  const int grid = items < num_sms() ? items : num_sms();
+  wgrad3x3_kernel<NT><<<grid, kThreads, pl.smem_bytes, stream>>>(p);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+// 0 when this kernel does not apply to the shape (caller falls back to the per-tap kernel)
+size_t wgrad3x3_workspace_bytes(int N, int H, int W, int M, int Nn) {
+  W3Plan pl;
+  if (!make_plan(N, H, W, M, Nn, &pl)) return 0;
+  return static_cast<size_t>(pl.ksplit) * 9 * M * Nn * sizeof(float);
+}
+
+// dw[co][ci][3][3] (+)= dY (M = Cout channels) x X (Nn = Cin channels); returns 1 if the shape is not eligible
+int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, float* dw, int accumulate, int N, int H,
+                 int W, int M, int Nn, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  W3Plan pl;
+  if (!make_plan(N, H, W, M, Nn, &pl)) return 1;
+  UNETK_CHECK(dy_ld % 8 == 0 && x_ld % 8 == 0, -1, "wgrad3x3: pixel strides must be multiples of 8");
+  const size_t need = static_cast<size_t>(pl.ksplit) * 9 * M * Nn * sizeof(float);
+  UNETK_CHECK(workspace != nullptr && ws_bytes >= need, -1, "wgrad3x3: workspace too small (%zu < %zu)", ws_bytes, need);
+  W3Params p{};
+  p.partial = static_cast<float*>(workspace);
+  p.TH = pl.TH; p.TW = pl.TW; p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w; p.pix_tiles = pl.pix_tiles;
+  p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.ksplit = pl.ksplit;
+  p.M = M; p.Nn = Nn;
+  p.q_box_bytes = pl.q_box_bytes; p.q_tx_bytes = pl.q_tx_bytes;
+  auto mk = [&](CUtensorMap* tm, const void* base, int64_t ld, int C, int halo) -> int {
+    uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * W,
+                           static_cast<uint64_t>(ld) * 2 * W * H};
+    uint32_t box[4] = {64, static_cast<uint32_t>(pl.TW + halo), static_cast<uint32_t>(pl.TH), 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    return make_tmap_bf16(tm, base, 4, dims, strides, box, es, true);
+  };
+  if (int rc = mk(&p.tmP, dy, dy_ld, M, 0)) return rc;
+  if (int rc = mk(&p.tmQ, x, x_ld, Nn, 2)) return rc;
+  int rc = (pl.NT == 128) ? launch<128>(p, pl, stream) : launch<64>(p, pl, stream);
+  if (rc) return rc;
+  return wgrad_reduce_launch(p.partial, dw, pl.ksplit, 9, M, Nn, static_cast<int64_t>(Nn) * 9, 9, 1, accumulate, stream);
+}
+
+}  // namespace unetk
