@@ -162,6 +162,9 @@ __device__ __forceinline__ void bn_relu8(const uint4& raw, const float* sc, cons
   }
 }
 
+// Threads keep ONE channel group for the whole kernel (grid stride is a multiple of cg, see flat_grid_cg), so the
+// per-channel constants are loaded once; four 16-byte loads per thread are in flight per iteration (>= 64 KB
+// per SM, what it takes to cover HBM latency at full bandwidth).
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld,
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
@@ -169,14 +172,30 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16*
                                                             int64_t npix, int C, int relu) {
   const int cg = C >> 3;
   const int64_t total = npix * cg;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * kThreads) {
-    const int g = static_cast<int>(i % cg);
-    const int64_t pix = i / cg;
-    float sc[8], sh[8], a[8];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % cg);
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
-    bn_relu8(ldg16(raw + pix * raw_ld + g * 8), sc, sh, a, relu != 0);
+  for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
+  const bool r = relu != 0;
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    uint4 u[4];
+    int64_t pix[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { pix[k] = (i + k * stride) / cg; u[k] = ldg16(raw + pix[k] * raw_ld + g * 8); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a[8];
+      bn_relu8(u[k], sc, sh, a, r);
+      stg16(out + pix[k] * out_ld + g * 8, pack8(a));
+    }
+  }
+  for (; i < total; i += stride) {
+    const int64_t pix = i / cg;
+    float a[8];
+    bn_relu8(ldg16(raw + pix * raw_ld + g * 8), sc, sh, a, r);
     stg16(out + pix * out_ld + g * 8, pack8(a));
   }
 }
@@ -203,32 +222,34 @@ bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld, cons
                      __nv_bfloat16* __restrict__ pooled, int64_t pooled_ld, int N, int H, int W, int C) {
   const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cg;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * kThreads) {
-    const int g = static_cast<int>(i % cg);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;  // multiple of cg
+  int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % cg);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
+  for (; i < total; i += stride) {
     int64_t t = i / cg;
     const int wo = static_cast<int>(t % Wo); t /= Wo;
     const int ho = static_cast<int>(t % Ho);
     const int n = static_cast<int>(t / Ho);
-    float sc[8], sh[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
-    float a[4][8];
+    const int64_t pix0 = (static_cast<int64_t>(n) * H + 2 * ho) * W + 2 * wo;
     uint4 u[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int64_t pix = (static_cast<int64_t>(n) * H + 2 * ho + (q >> 1)) * W + 2 * wo + (q & 1);
-      u[q] = ldg16(raw + pix * raw_ld + g * 8);
-    }
+    for (int q = 0; q < 4; ++q) u[q] = ldg16(raw + (pix0 + (q >> 1) * W + (q & 1)) * raw_ld + g * 8);
+    float best[8];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int64_t pix = (static_cast<int64_t>(n) * H + 2 * ho + (q >> 1)) * W + 2 * wo + (q & 1);
-      bn_relu8(u[q], sc, sh, a[q], true);
-      stg16(out + pix * out_ld + g * 8, pack8(a[q]));
+      float a[8];
+      bn_relu8(u[q], sc, sh, a, true);
+      stg16(out + (pix0 + (q >> 1) * W + (q & 1)) * out_ld + g * 8, pack8(a));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (q == 0) best[j] = a[j];
+        else if (a[j] > best[j] || a[j] != a[j]) best[j] = a[j];
+      }
     }
-    float best[8];
-    int arg[8];
-    argmax4(a, best, arg);
     const int64_t opix = (static_cast<int64_t>(n) * Ho + ho) * Wo + wo;
     stg16(pooled + opix * pooled_ld + g * 8, pack8(best));
   }
@@ -408,12 +429,16 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_kernel(const BnBwdA
     const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
     int64_t u = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
     if constexpr (!POOL) {
-      for (; u + stride < units; u += 2 * stride) {   // two pixels in flight per thread
-        BnBwdUnit<false> a, b;
+      for (; u + 3 * stride < units; u += 4 * stride) {   // four pixels (8 x 16 B) in flight per thread
+        BnBwdUnit<false> a, b, c, d;
         a.load(A, u, L.g);
         b.load(A, u + stride, L.g);
+        c.load(A, u + 2 * stride, L.g);
+        d.load(A, u + 3 * stride, L.g);
         a.visit(A, sc, sh, emit);
         b.visit(A, sc, sh, emit);
+        c.visit(A, sc, sh, emit);
+        d.visit(A, sc, sh, emit);
       }
     }
     for (; u < units; u += stride) {
@@ -470,12 +495,16 @@ bn_bwd_apply_kernel(const BnBwdArgs A, const float* __restrict__ coef, __nv_bflo
     stg16(draw + pix * draw_ld + g * 8, pack8(o));
   };
   if constexpr (!POOL) {
-    for (; i + stride < total; i += 2 * stride) {
-      BnBwdUnit<false> a, b;
+    for (; i + 3 * stride < total; i += 4 * stride) {
+      BnBwdUnit<false> a, b, c, d;
       a.load(A, i / cg, g);
       b.load(A, (i + stride) / cg, g);
+      c.load(A, (i + 2 * stride) / cg, g);
+      d.load(A, (i + 3 * stride) / cg, g);
       a.visit(A, sc, sh, emit);
       b.visit(A, sc, sh, emit);
+      c.visit(A, sc, sh, emit);
+      d.visit(A, sc, sh, emit);
     }
   }
   for (; i < total; i += stride) {
@@ -578,12 +607,12 @@ int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const floa
   if (pooled != nullptr) {
     UNETK_CHECK(H % 2 == 0 && W % 2 == 0 && relu, -1, "fused pool needs even H,W and relu");
     const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
-    bn_apply_pool_kernel<<<flat_grid(total), kThreads, 0, s>>>(
+    bn_apply_pool_kernel<<<flat_grid_cg(total, C / 8), kThreads, 0, s>>>(
         static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift, static_cast<__nv_bfloat16*>(out), out_ld,
         static_cast<__nv_bfloat16*>(pooled), pooled_ld, N, H, W, C);
   } else {
     const int64_t npix = static_cast<int64_t>(N) * H * W;
-    bn_apply_kernel<<<flat_grid(npix * (C / 8)), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(raw), raw_ld,
+    bn_apply_kernel<<<flat_grid_cg(npix * (C / 8), C / 8), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(raw), raw_ld,
                                                                   scale, shift, static_cast<__nv_bfloat16*>(out),
                                                                   out_ld, npix, C, relu);
   }
