@@ -1,0 +1,351 @@
+// conv3x3 (fwd / dgrad) for the wide-image, thin-channel layers: W >= 128 and at most 128 output channels.
+//
+// Why a second kernel.  The tap-GEMM in conv_gemm.cu loads a fresh 16 KB A tile for every (tap, 64-channel
+// chunk); with N = 64 that is 24 KB of TMA traffic per 128-192 MMA cycles, and every counter in
+// profiles/r01_ncu_conv_thin_layers.txt sits at ~30% (tensor 22%, L2 31%, DRAM 20%): the TMA/L2 path
+// delivers ~40 B/clk/SM and the layer is bound by bytes per FLOP.  Here one CTA tile is TWO output rows x
+// 128 columns and the four input rows it touches (with a one-pixel halo left and right) are loaded ONCE per
+// 64-channel chunk; all nine taps of both rows read that halo through row-shifted UMMA descriptors
+// (tcgen05 swizzles on absolute smem address bits, profiles/r01_umma_descriptor_probe.txt).  A-operand
+// traffic drops 4.3x (66.5 KB instead of 18 x 16 KB) and each weight tile feeds two accumulators.
+//
+// Pipeline: warp0 = TMA producer (A halo ring of 2, B ring per tap), warp1 = MMA issuer, warps2-5 =
+// epilogue (TMEM -> bf16 -> swizzled smem -> TMA store, optional fused BatchNorm statistics), accumulators
+// double-buffered in TMEM (2 tiles x 2 rows x BN columns).
+#include "conv_gemm.cuh"
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+#include <cstdlib>
+
+namespace unetk {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kTW = 128;                              // output columns per tile
+constexpr int kHaloW = kTW + 2;                       // 130 pixels per halo row
+constexpr uint32_t kHaloBytes = 4 * kHaloW * 128;     // 66,560 B written by the TMA
+constexpr uint32_t kHaloSlot = (kHaloBytes + 1023u) & ~1023u;  // 67,584 B per ring slot
+constexpr uint32_t kStagingBytes = 128 * 64 * 2;
+
+template <int BN>
+struct HCfg {
+  static constexpr uint32_t kBBytes = BN * 128;                // one (tap, chunk) weight tile
+  static constexpr int kBStages = (BN == 64) ? 6 : 4;
+  static constexpr int kStaging = (BN == 64) ? 2 : 1;          // staging buffers for the epilogue
+  static constexpr uint32_t kTmemCols = 4 * BN;                // 2 tiles x 2 rows x BN
+  static constexpr uint32_t kSmemBytes = 2 * kHaloSlot + kBStages * kBBytes + kStaging * kStagingBytes + 1024 + 256;
+};
+
+struct HaloParams {
+  CUtensorMap tmA;    // dims (K, W, H, N), box (64, 130, 4, 1)
+  CUtensorMap tmB;    // dims (K, ncols, 9), box (64, BN, 1)
+  CUtensorMap tmOut;  // dims (ncols, W, H, N), box (64, 128, 1, 1)
+  const float* bias;
+  float* stats_partial;
+  int H, W, tiles_h, tiles_w, num_m_tiles, num_n_tiles, ncols, kchunks;
+  int8_t dh[9], dw[9], btap[9];
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_constant__ HaloParams p) {
+  using C = HCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;                                   // [2][kHaloSlot]
+  uint8_t* sB = sA + 2 * kHaloSlot;                     // [kBStages][kBBytes]
+  uint8_t* staging = sB + C::kBStages * C::kBBytes;     // [kStaging][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::kStaging * kStagingBytes);
+  uint64_t* a_full = bars;                  // [2]
+  uint64_t* a_empty = bars + 2;             // [2]
+  uint64_t* b_full = bars + 4;              // [kBStages]
+  uint64_t* b_empty = b_full + C::kBStages; // [kBStages]
+  uint64_t* tfull = b_empty + C::kBStages;  // [2]
+  uint64_t* tempty = tfull + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmOut);
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.num_n_tiles;
+        const int mt = tile / p.num_n_tiles;
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int img = mt / (p.tiles_w * p.tiles_h);
+        const int h0 = th * 2, w0 = tw * kTW;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&a_empty[as], aph ^ 1u);
+          mbar_expect_tx(&a_full[as], kHaloBytes);
+          tma_load_4d(sA + as * kHaloSlot, &p.tmA, &a_full[as], kc * 64, w0 - 1, h0 - 1, img);
+          if (++as == 2) { as = 0; aph ^= 1u; }
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&b_empty[bs], bph ^ 1u);
+            mbar_expect_tx(&b_full[bs], C::kBBytes);
+            tma_load_3d(sB + bs * C::kBBytes, &p.tmB, &b_full[bs], kc * 64, nt * BN, p.btap[t]);
+            if (++bs == C::kBStages) { bs = 0; bph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 2 * BN;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + as * kHaloSlot);
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(sB + bs * C::kBBytes);
+            // halo row of output row u and tap t: (u + dh + 1); halo column of output column 0: (dw + 1)
+            const uint32_t a_tap = a_base + static_cast<uint32_t>(((p.dh[t] + 1) * kHaloW + p.dw[t] + 1) * 128);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = make_smem_desc(a_tap + u * kHaloW * 128 + k * 32, 16, 1024, kLayoutSW128);
+                const uint64_t db = make_smem_desc(b_base + k * 32, 16, 1024, kLayoutSW128);
+                umma_bf16(d_tmem + u * BN, da, db, idesc, (kc | t | k) != 0);
+              }
+            }
+            umma_commit(&b_empty[bs]);
+            if (++bs == C::kBStages) { bs = 0; bph ^= 1u; }
+          }
+          umma_commit(&a_empty[as]);  // all nine taps of this chunk have been issued
+          if (++as == 2) { as = 0; aph ^= 1u; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (warps 2..5)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;     // output column within the tile == TMEM lane
+    const int et = threadIdx.x - 64;
+    const bool leader = (et == 0);
+    const int st_ch = et & 63, st_half = et >> 6;
+    float ssum[BN / 64], ssq[BN / 64];
+#pragma unroll
+    for (int c = 0; c < BN / 64; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+    uint32_t chunk_ctr = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int nt = tile % p.num_n_tiles;
+      const int mt = tile / p.num_n_tiles;
+      const int tw = mt % p.tiles_w;
+      const int th = (mt / p.tiles_w) % p.tiles_h;
+      const int img = mt / (p.tiles_w * p.tiles_h);
+      const int h0 = th * 2, w0 = tw * kTW;
+      const int co0 = nt * BN;
+      const int valid_w = (p.W - w0 < kTW) ? (p.W - w0) : kTW;   // columns of this tile inside the image
+
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 2 * BN;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const bool row_ok = (h0 + u) < p.H;
+#pragma unroll
+        for (int c = 0; c < BN / 64; ++c) {
+          const int colbase = co0 + c * 64;
+          const bool live = row_ok && colbase < p.ncols;
+          const bool last = (u == 1) && (c == BN / 64 - 1);
+          uint8_t* buf = staging + (C::kStaging == 2 ? (chunk_ctr & 1u) : 0u) * kStagingBytes;
+          if (live) {
+            if (leader) { if (C::kStaging == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+            named_bar_sync(1, kEpiThreads);
+          }
+          uint32_t r0[32], r1[32];
+          if (live) {
+            tmem_ld32(taddr + u * BN + c * 64, r0);
+            tmem_ld32(taddr + u * BN + c * 64 + 32, r1);
+            tmem_ld_wait();
+          }
+          if (last) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          if (!live) continue;
+          ++chunk_ctr;
+          uint8_t* rowp = buf + row * 128;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const uint32_t* src = (v < 4) ? &r0[v * 8] : &r1[(v - 4) * 8];
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(src[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int col = colbase + v * 8 + j;
+                f[j] += (col < p.ncols) ? __ldg(p.bias + col) : 0.f;
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(rowp + ((v ^ (row & 7)) << 4)) = o;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, kEpiThreads);
+          if (leader) {
+            tma_store_4d(&p.tmOut, buf, colbase, w0, h0 + u, img);
+            bulk_commit();
+          }
+          if (p.stats_partial != nullptr && colbase + st_ch < p.ncols) {
+            float s = 0.f, ss = 0.f;
+            const int chunk16 = st_ch >> 3, within = (st_ch & 7) * 2;
+            const int r_begin = st_half * 64;
+            int r_end = r_begin + 64;
+            if (r_end > valid_w) r_end = valid_w;
+#pragma unroll 8
+            for (int r = r_begin; r < r_end; ++r) {
+              const uint16_t raw = *reinterpret_cast<const uint16_t*>(buf + r * 128 + ((chunk16 ^ (r & 7)) << 4) + within);
+              const float v = __uint_as_float(static_cast<uint32_t>(raw) << 16);
+              s += v;
+              ss = fmaf(v, v, ss);
+            }
+            ssum[c] += s;
+            ssq[c] += ss;
+          }
+        }
+      }
+    }
+    if (leader) bulk_wait<0>();
+    if (p.stats_partial != nullptr) {
+      named_bar_sync(1, kEpiThreads);
+      float* red = reinterpret_cast<float*>(staging);  // [2 halves][2][BN] floats <= 4 KB
+#pragma unroll
+      for (int c = 0; c < BN / 64; ++c) {
+        red[(st_half * 2 + 0) * BN + c * 64 + st_ch] = ssum[c];
+        red[(st_half * 2 + 1) * BN + c * 64 + st_ch] = ssq[c];
+      }
+      named_bar_sync(1, kEpiThreads);
+      for (int i = et; i < 2 * BN; i += kEpiThreads)
+        p.stats_partial[static_cast<size_t>(blockIdx.x) * 2 * BN + i] = red[i] + red[2 * BN + i];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+int launch(const HaloParams& p, int grid, cudaStream_t stream) {
+  using C = HCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    UNETK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  conv3x3_halo_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+int conv_stats_sums_launch(const float* partial, int grid, int num_n_tiles, int BN, int C, double* sums,
+                           cudaStream_t stream);
+
+bool conv3x3_halo_eligible(const ConvGemmDesc& d) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("UNETK_HALO_CONV"); enabled = e ? atoi(e) : 1; }
+  return enabled && d.taps == 9 && d.a_step == 1 && d.out_step == 1 && d.q_groups == 1 && d.W >= 128 && d.H >= 2 &&
+         d.ncols <= 128 && d.K >= 8;
+}
+
+// Same contract as conv_gemm_run for the shapes conv3x3_halo_eligible() accepts.
+int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream) {
+  HaloParams p{};
+  const int BN = d.ncols > 64 ? 128 : 64;
+  p.H = d.H; p.W = d.W;
+  p.tiles_h = (d.H + 1) / 2;
+  p.tiles_w = (d.W + kTW - 1) / kTW;
+  p.num_m_tiles = d.N * p.tiles_h * p.tiles_w;
+  p.num_n_tiles = (d.ncols + BN - 1) / BN;
+  p.ncols = d.ncols;
+  p.kchunks = (d.K + 63) / 64;
+  for (int t = 0; t < 9; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
+  p.bias = d.bias;
+  p.stats_partial = d.stats_sums ? d.stats_partial : nullptr;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  grid = grid / p.num_n_tiles * p.num_n_tiles;
+  if (grid < p.num_n_tiles) grid = p.num_n_tiles;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
+                        static_cast<uint64_t>(d.N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(d.a_ld) * 2, static_cast<uint64_t>(d.a_ld) * 2 * d.W,
+                           static_cast<uint64_t>(d.a_ld) * 2 * d.W * d.H};
+    uint32_t box[4] = {64, kHaloW, 4, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (int rc = make_tmap_bf16(&p.tmA, d.a, 4, dims, strides, box, es, true)) return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.ncols), static_cast<uint64_t>(d.b_taps)};
+    uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * d.ncols};
+    uint32_t box[3] = {64, static_cast<uint32_t>(BN), 1};
+    uint32_t es[3] = {1, 1, 1};
+    if (int rc = make_tmap_bf16(&p.tmB, d.b, 3, dims, strides, box, es, true)) return rc;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(d.ncols), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
+                        static_cast<uint64_t>(d.N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(d.out_ld) * 2, static_cast<uint64_t>(d.out_ld) * 2 * d.W,
+                           static_cast<uint64_t>(d.out_ld) * 2 * d.W * d.H};
+    uint32_t box[4] = {64, kTW, 1, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (int rc = make_tmap_bf16(&p.tmOut, d.out, 4, dims, strides, box, es, true)) return rc;
+  }
+  const int rc = (BN == 128) ? launch<128>(p, grid, stream) : launch<64>(p, grid, stream);
+  if (rc) return rc;
+  if (d.stats_sums != nullptr) return conv_stats_sums_launch(d.stats_partial, grid, p.num_n_tiles, BN, d.ncols, d.stats_sums, stream);
+  return 0;
+}
+
+}  // namespace unetk

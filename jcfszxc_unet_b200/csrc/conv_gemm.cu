@@ -23,6 +23,8 @@
 #include "host_common.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace unetk {
 
 namespace {
@@ -101,6 +103,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int h0 = th * p.TH, w0 = tw * p.TW;
         const int q = nt / p.tiles_per_q;
         const int brow = q * p.rows_per_q + (nt % p.tiles_per_q) * BN;
+        if (p.l2_prefetch > 0) {
+          // Streaming layers are latency-bound (the smem ring cannot hold enough bytes in flight to cover an HBM
+          // miss): pull the A box of a tile this CTA will reach `l2_prefetch` rounds from now into L2.
+          const int ftile = tile + p.l2_prefetch * gridDim.x;
+          if (ftile < num_tiles && (ftile % p.num_n_tiles) == 0) {
+            const int fmt = ftile / p.num_n_tiles;
+            const int fw0 = (fmt % p.tiles_w) * p.TW, fh0 = ((fmt / p.tiles_w) % p.tiles_h) * p.TH;
+            const int fimg = fmt / (p.tiles_w * p.tiles_h);
+            for (int kc = 0; kc < p.kchunks; ++kc)
+              tma_prefetch_l2_4d(&p.tmA, kc * kTileK, p.a_step * fw0, p.a_step * fh0, fimg);
+          }
+        }
         for (int t = 0; t < p.taps; ++t) {
           const int ah = p.a_step * h0 + p.dh[t];
           const int aw = p.a_step * w0 + p.dw[t];
@@ -315,6 +329,16 @@ int pick_bn(int ncols, int q_groups) {
 
 }  // namespace
 
+int conv_stats_sums_launch(const float* partial, int grid, int num_n_tiles, int BN, int C, double* sums,
+                           cudaStream_t stream) {
+  conv_stats_sums_kernel<<<(2 * C + 127) / 128, 128, 0, stream>>>(partial, grid, num_n_tiles, BN, C, sums);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+bool conv3x3_halo_eligible(const ConvGemmDesc& d);
+int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream);
+
 size_t conv_gemm_stats_partial_floats(int ncols) {
   return static_cast<size_t>(num_sms()) * 2 * pick_bn(ncols, 1);
 }
@@ -329,6 +353,8 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   UNETK_CHECK(d.taps >= 1 && d.taps <= 9, -1, "conv_gemm: taps=%d", d.taps);
   UNETK_CHECK(d.stats_sums == nullptr || (d.q_groups == 1 && d.stats_partial != nullptr), -1,
               "conv_gemm: fused statistics need q_groups == 1 and a partial buffer");
+
+  if (conv3x3_halo_eligible(d)) return conv3x3_halo_run(d, stream);  // wide images, <= 128 output channels
 
   ConvGemmParams p{};
   const int BN = pick_bn(d.ncols, d.q_groups);
@@ -353,6 +379,14 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   for (int t = 0; t < d.taps; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
   p.bias = d.bias;
   p.stats_partial = d.stats_sums ? d.stats_partial : nullptr;
+  {
+    // L2 prefetch only pays when A streams from HBM (tensor much larger than what L2 keeps between taps)
+    static int env = -1;
+    // measured on B200: no gain (0.640 -> 0.667 ms on 64->64 @512^2, profiles/r01_notes.md) => off by default
+    if (env < 0) { const char* e = getenv("UNETK_L2_PREFETCH"); env = e ? atoi(e) : 0; }
+    const double a_bytes = 2.0 * d.N * d.H * d.W * d.a_step * d.a_step * d.K;
+    p.l2_prefetch = (a_bytes > 48e6) ? env : 0;
+  }
   UNETK_CHECK(TW * d.a_step <= 256 && TH * d.a_step <= 256, -1, "conv_gemm: TMA box too large");
 
   // persistent grid; a multiple of num_n_tiles so that every CTA keeps one N tile (fused statistics rely on it)

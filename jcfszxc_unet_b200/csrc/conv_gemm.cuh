@@ -42,6 +42,7 @@ struct ConvGemmParams {
   int TH, TW, tw_shift, tiles_h, tiles_w;
   int num_m_tiles, num_n_tiles, tiles_per_q, rows_per_q, ncols;
   int taps, kchunks, a_step;
+  int l2_prefetch;  // > 0: prefetch the A box of the tile `l2_prefetch` rounds ahead into L2
   int8_t dh[9], dw[9], btap[9];
 };
 
