@@ -22,7 +22,7 @@ namespace unetk {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;  // warp0 A producer, warp1 MMA, warps2-5 epilogue, warp6 B producer
 constexpr int kEpiThreads = 128;
 constexpr int kTW = 128;                              // output columns per tile
 constexpr int kHaloW = kTW + 2;                       // 130 pixels per halo row
@@ -46,6 +46,7 @@ struct HaloParams {
   const float* bias;
   float* stats_partial;
   int H, W, tiles_h, tiles_w, num_m_tiles, num_n_tiles, ncols, kchunks;
+  int resident;  // 1: all 9*kchunks weight tiles stay in smem for the whole kernel (they fit), no B ring
   int8_t dh[9], dw[9], btap[9];
 };
 
@@ -57,15 +58,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;                                   // [2][kHaloSlot]
   uint8_t* sB = sA + 2 * kHaloSlot;                     // [kBStages][kBBytes]
-  uint8_t* staging = sB + C::kBStages * C::kBBytes;     // [kStaging][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::kStaging * kStagingBytes);
+  const uint32_t b_region = p.resident ? static_cast<uint32_t>(9 * p.kchunks) * C::kBBytes : C::kBStages * C::kBBytes;
+  const int n_staging = p.resident ? 1 : C::kStaging;
+  uint8_t* staging = sB + b_region;                     // [n_staging][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + n_staging * kStagingBytes);
   uint64_t* a_full = bars;                  // [2]
   uint64_t* a_empty = bars + 2;             // [2]
   uint64_t* b_full = bars + 4;              // [kBStages]
   uint64_t* b_empty = b_full + C::kBStages; // [kBStages]
   uint64_t* tfull = b_empty + C::kBStages;  // [2]
   uint64_t* tempty = tfull + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* w_full = tempty + 2;            // [1] resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(w_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -90,10 +95,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+      int as = 0;
+      uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.num_n_tiles;
         const int mt = tile / p.num_n_tiles;
         const int tw = mt % p.tiles_w;
         const int th = (mt / p.tiles_w) % p.tiles_h;
@@ -104,11 +108,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
           mbar_expect_tx(&a_full[as], kHaloBytes);
           tma_load_4d(sA + as * kHaloSlot, &p.tmA, &a_full[as], kc * 64, w0 - 1, h0 - 1, img);
           if (++as == 2) { as = 0; aph ^= 1u; }
-          for (int t = 0; t < 9; ++t) {
-            mbar_wait(&b_empty[bs], bph ^ 1u);
-            mbar_expect_tx(&b_full[bs], C::kBBytes);
-            tma_load_3d(sB + bs * C::kBBytes, &p.tmB, &b_full[bs], kc * 64, nt * BN, p.btap[t]);
-            if (++bs == C::kBStages) { bs = 0; bph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ weight producer (own warp: a full B ring must
+      // never delay the next tile's halo load, and vice versa)
+      if (p.resident) {
+        // grid is a multiple of num_n_tiles => this CTA always works on N tile blockIdx % num_n_tiles
+        const int nt = blockIdx.x % p.num_n_tiles;
+        mbar_expect_tx(w_full, static_cast<uint32_t>(9 * p.kchunks) * C::kBBytes);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int t = 0; t < 9; ++t)
+            tma_load_3d(sB + (kc * 9 + t) * C::kBBytes, &p.tmB, w_full, kc * 64, nt * BN, p.btap[t]);
+      } else {
+        int bs = 0;
+        uint32_t bph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int nt = tile % p.num_n_tiles;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(&b_empty[bs], bph ^ 1u);
+              mbar_expect_tx(&b_full[bs], C::kBBytes);
+              tma_load_3d(sB + bs * C::kBBytes, &p.tmB, &b_full[bs], kc * 64, nt * BN, p.btap[t]);
+              if (++bs == C::kBStages) { bs = 0; bph ^= 1u; }
+            }
           }
         }
       }
@@ -120,6 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
+      if (p.resident) { mbar_wait(w_full, 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1u);
@@ -130,9 +156,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + as * kHaloSlot);
           for (int t = 0; t < 9; ++t) {
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(sB + bs * C::kBBytes);
+            uint32_t b_base;
+            if (p.resident) {
+              b_base = smem_u32(sB + (kc * 9 + t) * C::kBBytes);
+            } else {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              b_base = smem_u32(sB + bs * C::kBBytes);
+            }
             // halo row of output row u and tap t: (u + dh + 1); halo column of output column 0: (dw + 1)
             const uint32_t a_tap = a_base + static_cast<uint32_t>(((p.dh[t] + 1) * kHaloW + p.dw[t] + 1) * 128);
 #pragma unroll
@@ -144,8 +175,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
                 umma_bf16(d_tmem + u * BN, da, db, idesc, (kc | t | k) != 0);
               }
             }
-            umma_commit(&b_empty[bs]);
-            if (++bs == C::kBStages) { bs = 0; bph ^= 1u; }
+            if (!p.resident) {
+              umma_commit(&b_empty[bs]);
+              if (++bs == C::kBStages) { bs = 0; bph ^= 1u; }
+            }
           }
           umma_commit(&a_empty[as]);  // all nine taps of this chunk have been issued
           if (++as == 2) { as = 0; aph ^= 1u; }
@@ -153,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         umma_commit(&tfull[acc]);
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // -------------------------------------------------------------- epilogue (warps 2..5)
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;     // output column within the tile == TMEM lane
@@ -187,9 +220,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
           const int colbase = co0 + c * 64;
           const bool live = row_ok && colbase < p.ncols;
           const bool last = (u == 1) && (c == BN / 64 - 1);
-          uint8_t* buf = staging + (C::kStaging == 2 ? (chunk_ctr & 1u) : 0u) * kStagingBytes;
+          uint8_t* buf = staging + (n_staging == 2 ? (chunk_ctr & 1u) : 0u) * kStagingBytes;
           if (live) {
-            if (leader) { if (C::kStaging == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+            if (leader) { if (n_staging == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
             named_bar_sync(1, kEpiThreads);
           }
           uint32_t r0[32], r1[32];
@@ -275,14 +308,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
 }
 
 template <int BN>
-int launch(const HaloParams& p, int grid, cudaStream_t stream) {
+int launch(HaloParams& p, int grid, cudaStream_t stream) {
   using C = HCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    UNETK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    UNETK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  conv3x3_halo_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  // weights resident when all 9*kchunks tiles fit next to the two halo slots and one staging buffer
+  const uint32_t w_bytes = static_cast<uint32_t>(9 * p.kchunks) * C::kBBytes;
+  const uint32_t resident_smem = 2 * kHaloSlot + w_bytes + kStagingBytes + 1024 + 256;
+  p.resident = (resident_smem <= 227 * 1024) ? 1 : 0;
+  const uint32_t smem_bytes = p.resident ? resident_smem : C::kSmemBytes;
+  conv3x3_halo_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(p);
   UNETK_LAUNCHED();
   return 0;
 }

@@ -49,6 +49,11 @@ CONV_SHAPES = [
     (1, 20, 24, 72, 72, (0, 0), (0, 0)),       # ragged: H,W not tile multiples; C not a multiple of 64
     (3, 5, 7, 8, 8, (0, 0), (0, 0)),           # tiny
     (1, 32, 32, 512, 320, (0, 0), (0, 0)),     # BN=256 with a masked N tail (320 = 256 + 64)
+    # W >= 128 and <= 128 output channels -> the halo kernel (conv3x3_halo.cu): two rows per tile, shifted descriptors
+    (1, 5, 200, 64, 64, (0, 0), (0, 0)),       # odd H (last tile has one live row), ragged W, resident weights
+    (2, 6, 128, 136, 72, (8, 0), (0, 56)),     # K tail chunk (136 = 2*64 + 8), 72 output channels, sliced in/out
+    (1, 4, 384, 128, 128, (0, 0), (128, 0)),   # BN=128, three column tiles, weight ring (not resident)
+    (1, 3, 256, 64, 128, (64, 0), (0, 0)),     # 64 -> 128 (dgrad of it is 128 -> 64)
 ]
 
 
