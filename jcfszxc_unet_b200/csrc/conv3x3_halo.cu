@@ -154,26 +154,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + as * kHaloSlot);
+          // Descriptors are built once per chunk and only ADVANCED per MMA (one 64-bit add each): with N = 64 an
+          // MMA lasts ~32-48 clocks, so the single issuing thread must spend only a few instructions per MMA.
+          const uint64_t a_desc0 = make_smem_desc(smem_u32(sA + as * kHaloSlot), 16, 1024, kLayoutSW128);
+          const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 16, 1024, kLayoutSW128);
           for (int t = 0; t < 9; ++t) {
-            uint32_t b_base;
+            uint64_t db0;
             if (p.resident) {
-              b_base = smem_u32(sB + (kc * 9 + t) * C::kBBytes);
+              db0 = desc_advance(b_desc0, static_cast<uint32_t>(kc * 9 + t) * C::kBBytes);
             } else {
               mbar_wait(&b_full[bs], bph);
               tc_fence_after();
-              b_base = smem_u32(sB + bs * C::kBBytes);
+              db0 = desc_advance(b_desc0, static_cast<uint32_t>(bs) * C::kBBytes);
             }
             // halo row of output row u and tap t: (u + dh + 1); halo column of output column 0: (dw + 1)
-            const uint32_t a_tap = a_base + static_cast<uint32_t>(((p.dh[t] + 1) * kHaloW + p.dw[t] + 1) * 128);
+            const uint64_t da0 = desc_advance(a_desc0, static_cast<uint32_t>(((p.dh[t] + 1) * kHaloW + p.dw[t] + 1) * 128));
+            if ((kc | t) == 0) {
+              umma_bf16(d_tmem, da0, db0, idesc, 0u);
+              umma_bf16(d_tmem + BN, desc_advance(da0, kHaloW * 128), db0, idesc, 0u);
+            } else {
+              umma_bf16_acc(d_tmem, da0, db0, idesc);
+              umma_bf16_acc(d_tmem + BN, desc_advance(da0, kHaloW * 128), db0, idesc);
+            }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = make_smem_desc(a_tap + u * kHaloW * 128 + k * 32, 16, 1024, kLayoutSW128);
-                const uint64_t db = make_smem_desc(b_base + k * 32, 16, 1024, kLayoutSW128);
-                umma_bf16(d_tmem + u * BN, da, db, idesc, (kc | t | k) != 0);
-              }
+            for (int k = 1; k < 4; ++k) {
+              const uint64_t db = desc_advance(db0, k * 32);
+              umma_bf16_acc(d_tmem, desc_advance(da0, k * 32), db, idesc);
+              umma_bf16_acc(d_tmem + BN, desc_advance(da0, kHaloW * 128 + k * 32), db, idesc);
             }
             if (!p.resident) {
               umma_commit(&b_empty[bs]);

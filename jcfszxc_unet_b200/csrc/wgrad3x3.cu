@@ -123,6 +123,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       int it = 0;
       const int row_pitch = p.TW + 2;                 // halo pixels per image row in the Q tile
       const int steps_per_row = p.TW >> 4;            // 16-pixel k-steps per image row
+      // stage-0 descriptors: P = two 64-channel boxes kPBoxBytes apart; Q = 64-channel halo boxes q_box_bytes apart,
+      // or (NT == 64) three overlapping tap atoms one pixel row (128 B) apart
+      uint32_t q_off[kPix / 16];
+#pragma unroll
+      for (int k = 0; k < kPix / 16; ++k)
+        q_off[k] = static_cast<uint32_t>((k / steps_per_row) * row_pitch + (k % steps_per_row) * 16) * 128;
+      const uint64_t p_desc0 = make_smem_desc(smem_u32(smem), kPBoxBytes, 1024, kLayoutSW128);
+      const uint64_t q_desc0 = make_smem_desc(smem_u32(smem) + 2 * kPBoxBytes, (NT == 64) ? 128u : p.q_box_bytes, 1024,
+                                              kLayoutSW128);
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int ks = item / items_per_split;
         const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
@@ -132,26 +141,26 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
         for (int kt = kt0; kt < kt1; ++kt) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t p_base = smem_u32(smem + stage * stage_bytes);
-          const uint32_t q_base = p_base + 2 * kPBoxBytes;
-          const uint32_t accum = (kt > kt0) ? 1u : 0u;
+          // descriptors are advanced from per-kernel bases (few instructions per MMA on the issuing thread)
+          const uint64_t dp0 = desc_advance(p_desc0, static_cast<uint32_t>(stage) * stage_bytes);
+          const uint64_t dq0 = desc_advance(q_desc0, static_cast<uint32_t>(stage) * stage_bytes);
+          const bool first = (kt == kt0);
 #pragma unroll
           for (int k = 0; k < kPix / 16; ++k) {
             // 16 consecutive pixels of one image row: P rows k*16.., Q rows i*(TW+2) + j0 (+ s per tap)
-            const int i = k / steps_per_row, j0 = (k % steps_per_row) * 16;
-            const uint64_t da = make_smem_desc(p_base + k * 2048, kPBoxBytes, 1024, kLayoutSW128);
-            const uint32_t q_row = q_base + static_cast<uint32_t>(i * row_pitch + j0) * 128;
+            const uint64_t da = desc_advance(dp0, k * 2048);
+            const uint64_t dq = desc_advance(dq0, q_off[k]);
             if constexpr (NT == 64) {
-              // taps s = 0,1,2 as three overlapping 64-wide N atoms, 128 B (one pixel row) apart
+              // taps s = 0,1,2 as three overlapping 64-wide N atoms, 128 B (one pixel row) apart (LBO = 128 B)
               constexpr uint32_t idesc = make_idesc_bf16(128, 192, true, true);
-              const uint64_t db = make_smem_desc(q_row, 128, 1024, kLayoutSW128);
-              umma_bf16(tmem_base, da, db, idesc, accum | (k != 0));
+              if (first && k == 0) umma_bf16(tmem_base, da, dq, idesc, 0u);
+              else umma_bf16_acc(tmem_base, da, dq, idesc);
             } else {
               constexpr uint32_t idesc = make_idesc_bf16(128, NT, true, true);
 #pragma unroll
               for (int s = 0; s < 3; ++s) {
-                const uint64_t db = make_smem_desc(q_row + s * 128, p.q_box_bytes, 1024, kLayoutSW128);
-                umma_bf16(tmem_base + s * NT, da, db, idesc, accum | (k != 0));
+                if (first && k == 0) umma_bf16(tmem_base + s * NT, da, desc_advance(dq, s * 128), idesc, 0u);
+                else umma_bf16_acc(tmem_base + s * NT, da, desc_advance(dq, s * 128), idesc);
               }
             }
           }
