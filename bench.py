@@ -170,10 +170,13 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------------
 CONV_FLOPS = {
     # name -> (index of N in args, taps, family)
-    "unetk_conv3x3_fwd": (6, 9, "tap_gemm"), "unetk_conv3x3_dgrad": (5, 9, "tap_gemm"),
-    "unetk_conv1x1_fwd": (6, 1, "tap_gemm"), "unetk_conv1x1_dgrad": (5, 1, "tap_gemm"),
-    "unetk_convT2x2_fwd": (6, 4, "tap_gemm"), "unetk_convT2x2_dgrad": (5, 4, "tap_gemm"),
+    "unetk_conv3x3_fwd": (6, 9, "tap_gemm"), "unetk_conv3x3_dgrad": (6, 9, "tap_gemm"),
+    "unetk_conv3x3_fwd_bnstats": (8, 9, "tap_gemm"), "unetk_conv1x1_fwd_bnstats": (8, 1, "tap_gemm"),
+    "unetk_conv3x3s2_fwd": (8, 9, "tap_gemm"), "unetk_conv3x3s2_dgrad": (6, 9, "tap_gemm"),
+    "unetk_conv1x1_fwd": (6, 1, "tap_gemm"), "unetk_conv1x1_dgrad": (6, 1, "tap_gemm"),
+    "unetk_convT2x2_fwd": (6, 4, "tap_gemm"), "unetk_convT2x2_dgrad": (6, 4, "tap_gemm"),
     "unetk_conv3x3_wgrad": (6, 9, "wgrad"), "unetk_conv1x1_wgrad": (6, 1, "wgrad"), "unetk_convT2x2_wgrad": (6, 4, "wgrad"),
+    "unetk_conv3x3s2_wgrad": (6, 9, "wgrad"),
 }
 
 

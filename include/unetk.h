@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define UNETK_ABI_VERSION 1
+#define UNETK_ABI_VERSION 2
 
 int unetk_abi_version(void);
 const char* unetk_last_error(void);
@@ -43,7 +43,8 @@ int unetk_pack_weight(const float* src, void* dst_ab, void* dst_ba, int A, int B
  * fwd:   y[n,h,w,co] = bias[co] + sum_{r,s,ci} x[n,h+r-1,w+s-1,ci] * w[co,ci,r,s]
  *        w_pack = bf16 [9][Cout][Cin] (dst_ab of unetk_pack_weight), bias fp32 [Cout] or NULL.
  * dgrad: dx[n,h,w,ci] = sum_{r,s,co} dy[n,h-r+1,w-s+1,co] * w[co,ci,r,s]
- *        w_pack_t = bf16 [9][Cin][Cout] (dst_ba).
+ *        w_pack_t = bf16 [9][Cin][Cout] (dst_ba).  accumulate != 0: dx += result (bf16 add in the TMA store;
+ *        for tensors with several consumers: recurrent / residual / dense-skip variants).
  * wgrad: dw[co,ci,r,s] (fp32, PyTorch layout) = sum_{n,h,w} dy[n,h,w,co] * x[n,h+r-1,w+s-1,ci]
  *        workspace >= unetk_conv_wgrad_workspace(...) bytes; accumulate!=0 adds into dw.
  * Cin, Cout multiples of 8 (the 3-channel stem has its own entry point below). */
@@ -57,18 +58,33 @@ int unetk_conv3x3_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, c
                               int64_t y_ld, float* partial, double* sums, int N, int H, int W, int Cin,
                               int Cout, void* stream);
 int unetk_conv3x3_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
-                        int N, int H, int W, int Cin, int Cout, void* stream);
+                        int accumulate, int N, int H, int W, int Cin, int Cout, void* stream);
 size_t unetk_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int taps);
 int unetk_conv3x3_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw,
                         int accumulate, int N, int H, int W, int Cin, int Cout, void* workspace,
                         size_t ws_bytes, void* stream);
 
+/* ---- 3x3 convolution, padding 1, STRIDE 2 (ResidualConv, unet_parts.py:460-462,469; ResUNet.py:32-35) ----
+ * x is [N,2Ho,2Wo,Cin], y / dy are [N,Ho,Wo,Cout]:  y[n,h,w,co] = bias[co] + sum x[n,2h+r-1,2w+s-1,ci]*w[co,ci,r,s].
+ * Same weight packs, workspace rule and accumulate flags as the stride-1 entry points; the dgrad runs as four
+ * sub-pixel classes (1, 2, 2 and 4 taps) that store into the parity views of dx. */
+int unetk_conv3x3s2_fwd(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y, int64_t y_ld,
+                        float* partial, double* sums, int N, int Ho, int Wo, int Cin, int Cout, void* stream);
+int unetk_conv3x3s2_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
+                          int accumulate, int N, int Ho, int Wo, int Cin, int Cout, void* stream);
+int unetk_conv3x3s2_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw, int accumulate,
+                          int N, int Ho, int Wo, int Cin, int Cout, void* workspace, size_t ws_bytes,
+                          void* stream);
+
 /* ---- 1x1 convolution (nn.Conv2d k=1: unet_parts.py:77,143,153,158) on the tensor-core path ------
  * Same contracts with a single tap; w_pack = bf16 [Cout][Cin], w_pack_t = bf16 [Cin][Cout]. */
 int unetk_conv1x1_fwd(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y,
                       int64_t y_ld, int N, int H, int W, int Cin, int Cout, void* stream);
+int unetk_conv1x1_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y,
+                              int64_t y_ld, float* partial, double* sums, int N, int H, int W, int Cin,
+                              int Cout, void* stream);
 int unetk_conv1x1_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
-                        int N, int H, int W, int Cin, int Cout, void* stream);
+                        int accumulate, int N, int H, int W, int Cin, int Cout, void* stream);
 int unetk_conv1x1_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw,
                         int accumulate, int N, int H, int W, int Cin, int Cout, void* workspace,
                         size_t ws_bytes, void* stream);
@@ -82,7 +98,7 @@ int unetk_conv1x1_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_
 int unetk_convT2x2_fwd(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y,
                        int64_t y_ld, int N, int H, int W, int Cin, int Cout, void* stream);
 int unetk_convT2x2_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
-                         int N, int H, int W, int Cin, int Cout, void* stream);
+                         int accumulate, int N, int H, int W, int Cin, int Cout, void* stream);
 int unetk_convT2x2_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw,
                          int accumulate, int N, int H, int W, int Cin, int Cout, void* workspace,
                          size_t ws_bytes, void* stream);
@@ -107,7 +123,9 @@ int unetk_stem_conv3x3_wgrad(const float* x, int64_t sn, int64_t sc, int64_t sh,
  *                       mean, invstd and updates running_mean/var (momentum, unbiased var) and
  *                       num_batches_tracked (+1) when those pointers are non-NULL.
  *   unetk_bn_eval_fold: eval mode, scale/shift from the running statistics.
- *   unetk_bn_apply    : out = relu?(bf16(raw*scale+shift)); if pooled != NULL also writes the 2x2 max-pool.
+ *   unetk_bn_apply    : out = relu?(bf16(raw*scale+shift)) [+ res]; if pooled != NULL also writes the 2x2 max-pool.
+ *                       res (optional, bf16 NHWC) is the residual of Recurrent_block / RRCNN_block / ResidualConv
+ *                       (unet_parts.py:128,146,475); res and pooled are mutually exclusive.
  * partial: fp32 scratch of >= unetk_chan_partial_floats(units, C) floats (units = pixels). */
 size_t unetk_chan_partial_floats(int64_t units, int C);
 int unetk_bn_stats(const void* x, int64_t x_ld, int64_t npix, int C, float* partial, double* sums, void* stream);
@@ -117,14 +135,15 @@ int unetk_bn_finalize(const double* sums, int C, double count, const float* gamm
 int unetk_bn_eval_fold(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
                        const float* running_var, float* scale, float* shift, float* mean, float* invstd,
                        void* stream);
-int unetk_bn_apply(const void* raw, int64_t raw_ld, const float* scale, const float* shift, void* out,
-                   int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W, int C, int relu,
-                   void* stream);
+int unetk_bn_apply(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const void* res,
+                   int64_t res_ld, void* out, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W,
+                   int C, int relu, void* stream);
 /* Backward of out = relu?(bn(raw)).  Incoming gradient = g1 (same resolution; may be NULL) + the scatter of
  * gp (gradient of the 2x2 max-pool of `out`; may be NULL) through the recomputed argmax (first max wins).
  *   unetk_bn_bwd_reduce: sums = double[2][C] (sum g, sum g*xhat)      (SyncBN: all-reduce here)
  *   unetk_bn_bwd_apply : dgamma/dbeta (fp32, optional, accumulate!=0 adds), coef = fp32 scratch [2][C],
- *                        draw = gradient w.r.t. the raw conv output (bf16 NHWC). count = pixels behind sums. */
+ *                        draw = gradient w.r.t. the raw conv output (bf16 NHWC). count = pixels behind sums.
+ *                        draw_accumulate != 0: draw += (pre-activation BN whose input has other consumers). */
 int unetk_bn_bwd_reduce(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp,
                         int64_t gp_ld, const float* scale, const float* shift, const float* mean,
                         const float* invstd, float* partial, double* sums, int N, int H, int W, int C, int relu,
@@ -132,8 +151,12 @@ int unetk_bn_bwd_reduce(const void* raw, int64_t raw_ld, const void* g1, int64_t
 int unetk_bn_bwd_apply(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp,
                        int64_t gp_ld, const float* scale, const float* shift, const float* mean,
                        const float* invstd, const double* sums, double count, float* dgamma, float* dbeta,
-                       int accumulate, float* coef, void* draw, int64_t draw_ld, int N, int H, int W, int C,
-                       int relu, void* stream);
+                       int accumulate, float* coef, void* draw, int64_t draw_ld, int draw_accumulate, int N, int H,
+                       int W, int C, int relu, void* stream);
+/* The per-channel part of unetk_bn_bwd_apply alone: dgamma/dbeta and coef = [K0[C] | K1[C]] with
+ * d(raw) = scale*g + K1*raw + K0 (used by the attention gate's fused backward; C >= 1). */
+int unetk_bn_bwd_coef(const double* sums, int C, double count, const float* scale, const float* mean,
+                      const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, void* stream);
 
 /* ---- MaxPool2d(2) standalone (unet_parts.py:43; indices as F.max_pool2d(return_indices=True)) ----
  * idx (optional) is int64 [N][C][H/2][W/2] holding h*W+w of the selected input element:
@@ -141,7 +164,7 @@ int unetk_bn_bwd_apply(const void* raw, int64_t raw_ld, const void* g1, int64_t 
 int unetk_maxpool2x2_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t* idx, int N, int H, int W,
                          int C, void* stream);
 int unetk_maxpool2x2_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
-                         int N, int H, int W, int C, void* stream);
+                         int accumulate, int N, int H, int W, int C, void* stream);
 
 /* ---- per-channel column sum (bias gradients of ConvTranspose2d / biased convs) -------------------- */
 int unetk_colsum(const void* x, int64_t x_ld, int64_t npix, int C, float* partial, float* out, int accumulate,
@@ -154,14 +177,17 @@ int unetk_colsum(const void* x, int64_t x_ld, int64_t npix, int C, float* partia
  * loss_finalize: fin = fp32[8] {loss, bce, dice, 1/npix, cA, cB, -, -}; loss = 0.5*bce + 0.5*(1-dice).
  * head_bwd : dz from (logits, labels, fin) — or from dlogits when the loss was computed outside —
  *            dx[pix][c] = dz*w[c] (bf16), dw[c] = sum dz*x[pix][c], db = sum dz.  gscale multiplies dz.
+ * post_sigmoid != 0: the model ends in nn.Sigmoid (ResUNet.py:47-50, UNetPP.py:105-106): logits[] receives
+ *            sigmoid(conv) and the loss / backward treat that value as the logit, as train.py:264-278 does.
  * C power of two in [8,256]; partial >= unetk_head_partial_floats(npix, C) floats. */
 size_t unetk_head_partial_floats(int64_t npix, int C);
 int unetk_head_fwd(const void* x, int64_t x_ld, const float* w, const float* bias, const float* labels,
-                   float* logits, int64_t npix, int C, float* partial, double* sums, void* stream);
+                   float* logits, int post_sigmoid, int64_t npix, int C, float* partial, double* sums,
+                   void* stream);
 int unetk_loss_finalize(const double* sums, double npix_total, float* fin, void* stream);
 int unetk_head_bwd(const void* x, int64_t x_ld, const float* w, const float* labels, const float* logits,
-                   const float* fin, const float* dlogits, float gscale, void* dx, int64_t dx_ld, float* dw,
-                   float* db, int accumulate, int64_t npix, int C, float* partial, void* stream);
+                   const float* fin, const float* dlogits, float gscale, int post_sigmoid, void* dx, int64_t dx_ld,
+                   float* dw, float* db, int accumulate, int64_t npix, int C, float* partial, void* stream);
 
 /* ---- optimizer tail on flat fp32 buffers (train.py:107-112,299-300) -------------------------------
  * grad_clip_coef: out[0] = gscale*||g||_2, out[1] = gscale*min(1, max_norm/(out[0]+1e-6)); partial >=
@@ -174,6 +200,61 @@ int unetk_grad_clip_coef(const float* g, int64_t n, float gscale, float max_norm
 int unetk_rmsprop_step(float* p, const float* g, float* square_avg, float* momentum_buf, int64_t n, float lr,
                        float alpha, float eps, float weight_decay, float momentum, const float* clip,
                        void* stream);
+
+/* ---- glue of the U-Net variants (bf16 NHWC views, C multiple of 8) ---------------------------------
+ * add_n: dst = [dst +] a [+ b [+ c [+ d]]] with every partial sum rounded to bf16 (a chain of bf16 tensor adds:
+ *        x + x1 of Recurrent_block / RRCNN_block / ResidualConv, unet_parts.py:128,146,475; ResUNet.py:54).  With
+ *        one source it is the slice copy behind NestedUNet's dense torch.cat (UNetPP.py:75-99), and with
+ *        accumulate its backward.  Unused sources are NULL.
+ * upsample_nearest2x (nn.Upsample(scale_factor=2), unet_parts.py:103): fwd x [N,H,W,C] -> y [N,2H,2W,C];
+ *        bwd dx (+)= sum of the 2x2 block of dy.
+ * upsample_bilinear2x (mode="bilinear", align_corners=True, UNetPP.py:44): same shapes, ATen's index rule. */
+int unetk_add_n(void* dst, int64_t dst_ld, int accumulate, const void* a, int64_t a_ld, const void* b, int64_t b_ld,
+                const void* c, int64_t c_ld, const void* d, int64_t d_ld, int64_t npix, int C, void* stream);
+int unetk_upsample_nearest2x_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int N, int H, int W, int C,
+                                 void* stream);
+int unetk_upsample_nearest2x_bwd(const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int accumulate, int N, int H,
+                                 int W, int C, void* stream);
+int unetk_upsample_bilinear2x_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int N, int H, int W, int C,
+                                  void* stream);
+int unetk_upsample_bilinear2x_bwd(const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int accumulate, int N, int H,
+                                  int W, int C, void* stream);
+/* dst[i*dst_stride] (+)= src[i*src_stride], fp32, i < n: derived weight caches (a 1x1 stem kernel embedded in the
+ * centre tap of the 3x3 stem kernel, RRCNN_block.Conv_1x1 on the image, unet_parts.py:143) and their gradients. */
+int unetk_copy_f32_strided(float* dst, int64_t dst_stride, const float* src, int64_t src_stride, int64_t n,
+                           int accumulate, void* stream);
+
+/* ---- attention gate (Attention_block, unet_parts.py:149-176) -------------------------------------------
+ * raw_g / raw_x: outputs of the two 1x1 GEMMs (bf16, F_int channels); (scale, shift, mean) of BN_g / BN_x from
+ * unetk_bn_finalize; w_psi fp32 [F_int], b_psi fp32 [1]; BN_1 = the single-channel BatchNorm of psi.
+ *   gate_fwd        s[pix] = b_psi + sum_c w_psi[c]*relu(bn_g(raw_g) + bn_x(raw_x))   (fp32 holding bf16 values)
+ *                   sums = double[2] (sum s, sum s^2) for BN_1
+ *   gate_apply      out = x * sigmoid(s*sc1 + sh1)                                     (F_l channels)
+ *   gate_bwd_psi    dx (+)= dout*psi; dz[pix] = (sum_c dout*x) * psi*(1-psi); sums = double[2] (sum dz, sum dz*(s-mean1))
+ *   gate_bwd_reduce ds = sc1*dz + K1*s + K0 (coef1 = {K0,K1} from unetk_bn_bwd_coef with C = 1);
+ *                   da = ds*w_psi*[a>0]; sums_g / sums_x = double[2][F_int] for unetk_bn_bwd_coef of BN_g / BN_x;
+ *                   dw_psi[c] (+)= sum ds*a_c, db_psi (+)= sum ds
+ *   gate_bwd_apply  draw_g = sc_g*da + K1g*raw_g + K0g, draw_x likewise (coef_g / coef_x = [K0 | K1])
+ * F_int power of two in [8,256]; partial >= unetk_gate_partial_floats(npix, F_int) floats. */
+size_t unetk_gate_partial_floats(int64_t npix, int F_int);
+int unetk_gate_fwd(const void* raw_g, int64_t raw_g_ld, const void* raw_x, int64_t raw_x_ld, const float* sc_g,
+                   const float* sh_g, const float* sc_x, const float* sh_x, const float* w_psi, const float* b_psi,
+                   float* s, float* partial, double* sums, int64_t npix, int F_int, void* stream);
+int unetk_gate_apply(const void* x, int64_t x_ld, const float* s, const float* sc1, const float* sh1, void* out,
+                     int64_t out_ld, int64_t npix, int F_l, void* stream);
+int unetk_gate_bwd_psi(const void* dout, int64_t dout_ld, const void* x, int64_t x_ld, const float* s,
+                       const float* sc1, const float* sh1, const float* mean1, void* dx, int64_t dx_ld,
+                       int dx_accumulate, float* dz, float* partial, double* sums, int64_t npix, int F_l, void* stream);
+int unetk_gate_bwd_reduce(const void* raw_g, int64_t raw_g_ld, const void* raw_x, int64_t raw_x_ld, const float* sc_g,
+                          const float* sh_g, const float* mean_g, const float* sc_x, const float* sh_x,
+                          const float* mean_x, const float* w_psi, const float* s, const float* dz, const float* sc1,
+                          const float* coef1, float* partial, double* sums_g, double* sums_x, float* dw_psi,
+                          float* db_psi, int accumulate, int64_t npix, int F_int, void* stream);
+int unetk_gate_bwd_apply(const void* raw_g, int64_t raw_g_ld, const void* raw_x, int64_t raw_x_ld, const float* sc_g,
+                         const float* sh_g, const float* sc_x, const float* sh_x, const float* w_psi, const float* s,
+                         const float* dz, const float* sc1, const float* coef1, const float* coef_g,
+                         const float* coef_x, void* draw_g, int64_t draw_g_ld, void* draw_x, int64_t draw_x_ld,
+                         int64_t npix, int F_int, void* stream);
 
 /* ---- test infrastructure: tcgen05 descriptor-semantics probe (not on the product path) ---------- */
 int unetk_probe_umma(const void* a, const void* b, float* d, int mode, int shift, int base_offset,

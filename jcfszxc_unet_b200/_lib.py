@@ -27,14 +27,18 @@ SIGNATURES = {
     "unetk_conv3x3_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv_stats_partial_floats": (_sz, [_i]),
     "unetk_conv3x3_fwd_bnstats": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "unetk_conv3x3_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv3x3_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv3x3s2_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv3x3s2_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv3x3s2_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "unetk_conv_wgrad_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
     "unetk_conv3x3_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "unetk_conv1x1_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
-    "unetk_conv1x1_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv1x1_fwd_bnstats": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv1x1_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv1x1_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "unetk_convT2x2_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
-    "unetk_convT2x2_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_convT2x2_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "unetk_convT2x2_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "unetk_stem_conv3x3_fwd": (_i, [_fp, _i64, _i64, _i64, _i64, _fp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_stem_wgrad_workspace": (_sz, [_i, _i, _i, _i]),
@@ -43,20 +47,35 @@ SIGNATURES = {
     "unetk_bn_stats": (_i, [_vp, _i64, _i64, _i, _fp, _vp, _vp]),
     "unetk_bn_finalize": (_i, [_vp, _i, C.c_double, _fp, _fp, _f, _f, _fp, _fp, _vp, _fp, _fp, _fp, _fp, _vp]),
     "unetk_bn_eval_fold": (_i, [_i, _fp, _fp, _f, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
-    "unetk_bn_apply": (_i, [_vp, _i64, _fp, _fp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_bn_apply": (_i, [_vp, _i64, _fp, _fp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_bn_bwd_reduce": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "unetk_bn_bwd_apply": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _vp, C.c_double, _fp, _fp, _i,
-                                _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+                                _fp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "unetk_bn_bwd_coef": (_i, [_vp, _i, C.c_double, _fp, _fp, _fp, _fp, _fp, _i, _fp, _vp]),
     "unetk_maxpool2x2_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
-    "unetk_maxpool2x2_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "unetk_maxpool2x2_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_colsum": (_i, [_vp, _i64, _i64, _i, _fp, _fp, _i, _vp]),
     "unetk_head_partial_floats": (_sz, [_i64, _i]),
-    "unetk_head_fwd": (_i, [_vp, _i64, _fp, _fp, _fp, _fp, _i64, _i, _fp, _vp, _vp]),
+    "unetk_head_fwd": (_i, [_vp, _i64, _fp, _fp, _fp, _fp, _i, _i64, _i, _fp, _vp, _vp]),
     "unetk_loss_finalize": (_i, [_vp, C.c_double, _fp, _vp]),
-    "unetk_head_bwd": (_i, [_vp, _i64, _fp, _fp, _fp, _fp, _fp, _f, _vp, _i64, _fp, _fp, _i, _i64, _i, _fp, _vp]),
+    "unetk_head_bwd": (_i, [_vp, _i64, _fp, _fp, _fp, _fp, _fp, _f, _i, _vp, _i64, _fp, _fp, _i, _i64, _i, _fp, _vp]),
     "unetk_sqnorm_partial_floats": (_sz, [_i64]),
     "unetk_grad_clip_coef": (_i, [_fp, _i64, _f, _f, _fp, _fp, _vp]),
     "unetk_rmsprop_step": (_i, [_fp, _fp, _fp, _fp, _i64, _f, _f, _f, _f, _f, _fp, _vp]),
+    "unetk_add_n": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp]),
+    "unetk_upsample_nearest2x_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "unetk_upsample_nearest2x_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_upsample_bilinear2x_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "unetk_upsample_bilinear2x_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_copy_f32_strided": (_i, [_fp, _i64, _fp, _i64, _i64, _i, _vp]),
+    "unetk_gate_partial_floats": (_sz, [_i64, _i]),
+    "unetk_gate_fwd": (_i, [_vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _i64, _i, _vp]),
+    "unetk_gate_apply": (_i, [_vp, _i64, _fp, _fp, _fp, _vp, _i64, _i64, _i, _vp]),
+    "unetk_gate_bwd_psi": (_i, [_vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _vp, _i64, _i, _fp, _fp, _vp, _i64, _i, _vp]),
+    "unetk_gate_bwd_reduce": (_i, [_vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                   _vp, _vp, _fp, _fp, _i, _i64, _i, _vp]),
+    "unetk_gate_bwd_apply": (_i, [_vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp,
+                                  _i64, _vp, _i64, _i64, _i, _vp]),
     "unetk_probe_umma": (_i, [_vp, _vp, _fp, _i, _i, _i, _vp]),
 }
 
@@ -82,8 +101,8 @@ def load() -> C.CDLL:
         fn.restype = res
         fn.argtypes = args
     got = lib.unetk_abi_version()
-    if got != 1:
-        raise RuntimeError(f"libunetk.so ABI version {got}, expected 1")
+    if got != 2:
+        raise RuntimeError(f"libunetk.so ABI version {got}, expected 2")
     _lib = lib
     return lib
 

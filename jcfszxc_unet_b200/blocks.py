@@ -160,3 +160,22 @@ def run_out_conv(mod, x):
         return _BlockPlan(P.finalize(), [xin], head, False)
 
     return _run(mod, "outc", build, [x])
+
+
+def run_emit(mod, key, xs, emit):
+    """Generic stand-alone execution of a block of the variants: `emit(P, acts)` wires the block into plan P from
+    the input activations (the plan's Image when the first input has <= 4 channels) and returns the output Act."""
+    n = xs[0].shape[0]
+    h, w = xs[0].shape[2], xs[0].shape[3]
+    image = xs[0].shape[1] <= 4
+    if not image:
+        for x in xs:
+            _check_c(x.shape[1], type(mod).__name__)
+
+    def build(training, need_grad):
+        P = Plan(xs[0].device, n, h, w, training, need_grad)
+        acts = [P.image] if image else [P.act(x.shape[2], x.shape[3], x.shape[1]) for x in xs]
+        out = emit(P, acts)
+        return _BlockPlan(P.finalize(), [] if image else acts, out, image)
+
+    return _run(mod, key, build, list(xs))

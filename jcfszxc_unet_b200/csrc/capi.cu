@@ -3,61 +3,8 @@
 
 #include "conv_gemm.cuh"
 #include "host_common.cuh"
+#include "kernels.cuh"
 #include "wgrad.cuh"
-
-namespace unetk {
-const char* last_error();
-int probe_run(const void* a, const void* b, float* d, int mode, int shift, int bo, cudaStream_t stream);
-int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, cudaStream_t stream);
-// wgrad3x3.cu
-size_t wgrad3x3_workspace_bytes(int N, int H, int W, int M, int Nn);
-int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, float* dw, int accumulate, int N, int H,
-                 int W, int M, int Nn, void* workspace, size_t ws_bytes, cudaStream_t stream);
-// stem.cu
-int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
-                 void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
-size_t stem_wgrad_workspace(int N, int H, int W, int Cin);
-int stem_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy, int64_t dy_ld,
-                   float* dw, int accumulate, int N, int H, int W, int Cin, int Cout, void* ws, size_t ws_bytes,
-                   cudaStream_t s);
-// elementwise.cu
-size_t chan_partial_floats(int64_t units, int C);
-int bn_stats_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, double* sums, cudaStream_t s);
-int bn_finalize_run(const double* sums, int C, double count, const float* gamma, const float* beta, float eps,
-                    float momentum, float* rm, float* rv, long long* nbt, float* scale, float* shift, float* mean,
-                    float* invstd, cudaStream_t s);
-int bn_eval_fold_run(int C, const float* gamma, const float* beta, float eps, const float* rm, const float* rv,
-                     float* scale, float* shift, float* mean, float* invstd, cudaStream_t s);
-int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, float* out, int accumulate,
-               cudaStream_t s);
-int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const float* shift, void* out, int64_t out_ld,
-                 void* pooled, int64_t pooled_ld, int N, int H, int W, int C, int relu, cudaStream_t s);
-int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long long* idx, int N, int H, int W, int C,
-                    cudaStream_t s);
-int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int N, int H,
-                    int W, int C, cudaStream_t s);
-int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
-                      const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
-                      double* sums, int N, int H, int W, int C, int relu, cudaStream_t s);
-int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
-                     const float* scale, const float* shift, const float* mean, const float* invstd,
-                     const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
-                     void* draw, int64_t draw_ld, int N, int H, int W, int C, int relu, cudaStream_t s);
-// loss.cu
-size_t head_partial_floats(int64_t npix, int C);
-int head_loss_fwd_run(const void* x, int64_t ld, const float* w, const float* bias, const float* labels, float* logits,
-                      int64_t npix, int C, float* partial, double* sums, cudaStream_t s);
-int loss_finalize_run(const double* sums, double npix_total, float* out, cudaStream_t s);
-int head_loss_bwd_run(const void* x, int64_t ld, const float* w, const float* labels, const float* logits,
-                      const float* fin, const float* dlogits, float gscale, void* dx, int64_t dx_ld, float* dw,
-                      float* db, int accumulate, int64_t npix, int C, float* partial, cudaStream_t s);
-// optim.cu
-int sqnorm_blocks(int64_t n);
-int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, float* partial, float* out,
-                       cudaStream_t s);
-int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, float lr, float alpha, float eps, float wd,
-                float momentum, const float* clip, cudaStream_t s);
-}  // namespace unetk
 
 using namespace unetk;
 
@@ -74,15 +21,19 @@ int unetk_pack_weight(const float* src, void* dst_ab, void* dst_ba, int A, int B
   return pack_weight_run(src, dst_ab, dst_ba, A, B, T, S(stream));
 }
 
+static WgradDesc conv_wgrad_desc(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw,
+                                 int accumulate, int N, int H, int W, int Cin, int Cout, int ksize);
+
 static int conv_fwd_like(const void* x, int64_t x_ld, const void* w, const float* bias, void* y, int64_t y_ld,
                          int N, int H, int W, int K, int ncols, int ksize, bool dgrad, void* stream,
-                         float* stats_partial = nullptr, double* stats_sums = nullptr) {
+                         float* stats_partial = nullptr, double* stats_sums = nullptr, int accumulate = 0,
+                         int a_step = 1) {
   UNETK_CHECK(x && w && y && N > 0 && H > 0 && W > 0 && K > 0 && ncols > 0, -1, "conv: bad arguments");
   ConvGemmDesc d{};
   d.a = x; d.a_ld = x_ld; d.b = w; d.out = y; d.out_ld = y_ld; d.bias = bias;
   d.stats_partial = stats_partial; d.stats_sums = stats_sums;
   d.N = N; d.H = H; d.W = W; d.K = K; d.ncols = ncols; d.q_groups = 1;
-  d.a_step = 1; d.out_step = 1;
+  d.a_step = a_step; d.out_step = 1; d.accumulate = accumulate;
   d.taps = ksize * ksize; d.b_taps = d.taps;
   const int half = ksize / 2;
   for (int t = 0; t < d.taps; ++t) {
@@ -108,17 +59,70 @@ int unetk_conv3x3_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, c
   UNETK_CHECK(partial && sums, -1, "conv3x3_fwd_bnstats: null statistics buffers");
   return conv_fwd_like(x, x_ld, w_pack, bias, y, y_ld, N, H, W, Cin, Cout, 3, false, stream, partial, sums);
 }
-int unetk_conv3x3_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld, int N, int H,
-                        int W, int Cin, int Cout, void* stream) {
-  return conv_fwd_like(dy, dy_ld, w_pack_t, nullptr, dx, dx_ld, N, H, W, Cout, Cin, 3, true, stream);
+int unetk_conv3x3_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld, int accumulate,
+                        int N, int H, int W, int Cin, int Cout, void* stream) {
+  return conv_fwd_like(dy, dy_ld, w_pack_t, nullptr, dx, dx_ld, N, H, W, Cout, Cin, 3, true, stream, nullptr, nullptr,
+                       accumulate);
+}
+
+// ---- stride 2: forward = the same tap-GEMM with A coordinates 2*pos + (r-1, s-1) (TMA element stride 2)
+int unetk_conv3x3s2_fwd(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y, int64_t y_ld,
+                        float* partial, double* sums, int N, int Ho, int Wo, int Cin, int Cout, void* stream) {
+  UNETK_CHECK((partial == nullptr) == (sums == nullptr), -1, "conv3x3s2_fwd: partial and sums go together");
+  return conv_fwd_like(x, x_ld, w_pack, bias, y, y_ld, N, Ho, Wo, Cin, Cout, 3, false, stream, partial, sums, 0, 2);
+}
+// dgrad: dx[2i+ph, 2j+pw] = sum over the taps (r, s) with r = ph+1 (mod 2), s = pw+1 (mod 2) of
+//        dy[i + (ph+1-r)/2, j + (pw+1-s)/2] * w[:, :, r, s]  -> one tap-GEMM per sub-pixel class (ph, pw),
+//        storing into the parity view of dx (out_step = 2, base offset (ph, pw)).
+int unetk_conv3x3s2_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
+                          int accumulate, int N, int Ho, int Wo, int Cin, int Cout, void* stream) {
+  UNETK_CHECK(dy && w_pack_t && dx && N > 0 && Ho > 0 && Wo > 0, -1, "conv3x3s2_dgrad: bad arguments");
+  for (int ph = 0; ph < 2; ++ph) {
+    for (int pw = 0; pw < 2; ++pw) {
+      ConvGemmDesc d{};
+      d.a = dy; d.a_ld = dy_ld; d.b = w_pack_t; d.b_taps = 9; d.bias = nullptr;
+      d.out = static_cast<uint8_t*>(dx) + (static_cast<int64_t>(ph) * (2 * Wo) + pw) * dx_ld * 2;
+      d.out_ld = dx_ld;
+      d.N = N; d.H = Ho; d.W = Wo; d.K = Cout; d.ncols = Cin; d.q_groups = 1;
+      d.a_step = 1; d.out_step = 2; d.accumulate = accumulate;
+      int t = 0;
+      for (int r = 0; r < 3; ++r) {
+        if (((ph + 1 - r) & 1) != 0) continue;
+        for (int s = 0; s < 3; ++s) {
+          if (((pw + 1 - s) & 1) != 0) continue;
+          d.dh[t] = static_cast<int8_t>((ph + 1 - r) / 2);
+          d.dw[t] = static_cast<int8_t>((pw + 1 - s) / 2);
+          d.btap[t] = static_cast<int8_t>(r * 3 + s);
+          ++t;
+        }
+      }
+      d.taps = t;
+      if (int rc = conv_gemm_run(d, S(stream))) return rc;
+    }
+  }
+  return 0;
+}
+int unetk_conv3x3s2_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw, int accumulate,
+                          int N, int Ho, int Wo, int Cin, int Cout, void* workspace, size_t ws_bytes, void* stream) {
+  UNETK_CHECK(x && dy && dw, -1, "conv3x3s2_wgrad: null pointer");
+  WgradDesc d = conv_wgrad_desc(x, x_ld, dy, dy_ld, dw, accumulate, N, Ho, Wo, Cin, Cout, 3);
+  if (d.p == x) d.p_step = 2; else d.q_step = 2;   // the activation operand is read at 2*pos + (r-1, s-1)
+  return wgrad_run(d, workspace, ws_bytes, S(stream));
 }
 int unetk_conv1x1_fwd(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y, int64_t y_ld,
                       int N, int H, int W, int Cin, int Cout, void* stream) {
   return conv_fwd_like(x, x_ld, w_pack, bias, y, y_ld, N, H, W, Cin, Cout, 1, false, stream);
 }
-int unetk_conv1x1_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld, int N, int H,
-                        int W, int Cin, int Cout, void* stream) {
-  return conv_fwd_like(dy, dy_ld, w_pack_t, nullptr, dx, dx_ld, N, H, W, Cout, Cin, 1, true, stream);
+int unetk_conv1x1_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y,
+                              int64_t y_ld, float* partial, double* sums, int N, int H, int W, int Cin, int Cout,
+                              void* stream) {
+  UNETK_CHECK(partial && sums, -1, "conv1x1_fwd_bnstats: null statistics buffers");
+  return conv_fwd_like(x, x_ld, w_pack, bias, y, y_ld, N, H, W, Cin, Cout, 1, false, stream, partial, sums);
+}
+int unetk_conv1x1_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld, int accumulate,
+                        int N, int H, int W, int Cin, int Cout, void* stream) {
+  return conv_fwd_like(dy, dy_ld, w_pack_t, nullptr, dx, dx_ld, N, H, W, Cout, Cin, 1, true, stream, nullptr, nullptr,
+                       accumulate);
 }
 
 // Orientation of the conv weight-gradient GEMM: rows of D come from the operand with >= 128 channels
@@ -186,13 +190,13 @@ int unetk_convT2x2_fwd(const void* x, int64_t x_ld, const void* w_pack, const fl
   d.dh[0] = 0; d.dw[0] = 0; d.btap[0] = 0;
   return conv_gemm_run(d, S(stream));
 }
-int unetk_convT2x2_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld, int N, int H,
-                         int W, int Cin, int Cout, void* stream) {
+int unetk_convT2x2_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld, int accumulate,
+                         int N, int H, int W, int Cin, int Cout, void* stream) {
   UNETK_CHECK(dy && w_pack_t && dx, -1, "convT2x2_dgrad: null pointer");
   ConvGemmDesc d{};
   d.a = dy; d.a_ld = dy_ld; d.b = w_pack_t; d.b_taps = 4; d.out = dx; d.out_ld = dx_ld; d.bias = nullptr;
   d.N = N; d.H = H; d.W = W; d.K = Cout; d.ncols = Cin; d.q_groups = 1;
-  d.taps = 4; d.a_step = 2; d.out_step = 1;
+  d.taps = 4; d.a_step = 2; d.out_step = 1; d.accumulate = accumulate;
   for (int t = 0; t < 4; ++t) { d.dh[t] = static_cast<int8_t>(t >> 1); d.dw[t] = static_cast<int8_t>(t & 1); d.btap[t] = static_cast<int8_t>(t); }
   return conv_gemm_run(d, S(stream));
 }
@@ -246,10 +250,12 @@ int unetk_bn_eval_fold(int C, const float* gamma, const float* beta, float eps, 
   UNETK_CHECK(running_mean && running_var && scale && shift && mean && invstd, -1, "bn_eval_fold: null pointer");
   return bn_eval_fold_run(C, gamma, beta, eps, running_mean, running_var, scale, shift, mean, invstd, S(stream));
 }
-int unetk_bn_apply(const void* raw, int64_t raw_ld, const float* scale, const float* shift, void* out, int64_t out_ld,
-                   void* pooled, int64_t pooled_ld, int N, int H, int W, int C, int relu, void* stream) {
+int unetk_bn_apply(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const void* res,
+                   int64_t res_ld, void* out, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W, int C,
+                   int relu, void* stream) {
   UNETK_CHECK(raw && scale && shift && out, -1, "bn_apply: null pointer");
-  return bn_apply_run(raw, raw_ld, scale, shift, out, out_ld, pooled, pooled_ld, N, H, W, C, relu, S(stream));
+  return bn_apply_run(raw, raw_ld, scale, shift, res, res_ld, out, out_ld, pooled, pooled_ld, N, H, W, C, relu,
+                      S(stream));
 }
 int unetk_bn_bwd_reduce(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
                         const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
@@ -261,21 +267,27 @@ int unetk_bn_bwd_reduce(const void* raw, int64_t raw_ld, const void* g1, int64_t
 int unetk_bn_bwd_apply(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
                        const float* scale, const float* shift, const float* mean, const float* invstd,
                        const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
-                       void* draw, int64_t draw_ld, int N, int H, int W, int C, int relu, void* stream) {
+                       void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C, int relu,
+                       void* stream) {
   UNETK_CHECK(raw && scale && shift && mean && invstd && sums && coef && draw && count > 0, -1,
               "bn_bwd_apply: bad arguments");
   return bn_bwd_apply_run(raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, sums, count, dgamma, dbeta,
-                          accumulate, coef, draw, draw_ld, N, H, W, C, relu, S(stream));
+                          accumulate, coef, draw, draw_ld, draw_accumulate, N, H, W, C, relu, S(stream));
+}
+int unetk_bn_bwd_coef(const double* sums, int C, double count, const float* scale, const float* mean,
+                      const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, void* stream) {
+  UNETK_CHECK(sums && scale && mean && invstd && coef && count > 0, -1, "bn_bwd_coef: bad arguments");
+  return bn_bwd_coef_run(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef, S(stream));
 }
 int unetk_maxpool2x2_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t* idx, int N, int H, int W, int C,
                          void* stream) {
   UNETK_CHECK(x && y, -1, "maxpool_fwd: null pointer");
   return maxpool_fwd_run(x, x_ld, y, y_ld, reinterpret_cast<long long*>(idx), N, H, W, C, S(stream));
 }
-int unetk_maxpool2x2_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int N,
-                         int H, int W, int C, void* stream) {
+int unetk_maxpool2x2_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
+                         int accumulate, int N, int H, int W, int C, void* stream) {
   UNETK_CHECK(x && dy && dx, -1, "maxpool_bwd: null pointer");
-  return maxpool_bwd_run(x, x_ld, dy, dy_ld, dx, dx_ld, N, H, W, C, S(stream));
+  return maxpool_bwd_run(x, x_ld, dy, dy_ld, dx, dx_ld, accumulate, N, H, W, C, S(stream));
 }
 int unetk_colsum(const void* x, int64_t x_ld, int64_t npix, int C, float* partial, float* out, int accumulate,
                  void* stream) {
@@ -289,20 +301,20 @@ size_t unetk_head_partial_floats(int64_t npix, int C) {
   return head_partial_floats(npix, C);
 }
 int unetk_head_fwd(const void* x, int64_t x_ld, const float* w, const float* bias, const float* labels, float* logits,
-                   int64_t npix, int C, float* partial, double* sums, void* stream) {
+                   int post_sigmoid, int64_t npix, int C, float* partial, double* sums, void* stream) {
   UNETK_CHECK(x && w && logits && partial && npix > 0, -1, "head_fwd: bad arguments");
-  return head_loss_fwd_run(x, x_ld, w, bias, labels, logits, npix, C, partial, sums, S(stream));
+  return head_loss_fwd_run(x, x_ld, w, bias, labels, logits, post_sigmoid, npix, C, partial, sums, S(stream));
 }
 int unetk_loss_finalize(const double* sums, double npix_total, float* fin, void* stream) {
   UNETK_CHECK(sums && fin && npix_total > 0, -1, "loss_finalize: bad arguments");
   return loss_finalize_run(sums, npix_total, fin, S(stream));
 }
 int unetk_head_bwd(const void* x, int64_t x_ld, const float* w, const float* labels, const float* logits,
-                   const float* fin, const float* dlogits, float gscale, void* dx, int64_t dx_ld, float* dw, float* db,
-                   int accumulate, int64_t npix, int C, float* partial, void* stream) {
+                   const float* fin, const float* dlogits, float gscale, int post_sigmoid, void* dx, int64_t dx_ld,
+                   float* dw, float* db, int accumulate, int64_t npix, int C, float* partial, void* stream) {
   UNETK_CHECK(x && w && dx && partial && npix > 0, -1, "head_bwd: bad arguments");
-  return head_loss_bwd_run(x, x_ld, w, labels, logits, fin, dlogits, gscale, dx, dx_ld, dw, db, accumulate, npix, C,
-                           partial, S(stream));
+  return head_loss_bwd_run(x, x_ld, w, labels, logits, fin, dlogits, gscale, post_sigmoid, dx, dx_ld, dw, db,
+                           accumulate, npix, C, partial, S(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ optimizer
@@ -316,6 +328,88 @@ int unetk_rmsprop_step(float* p, const float* g, float* square_avg, float* momen
                        float alpha, float eps, float weight_decay, float momentum, const float* clip, void* stream) {
   UNETK_CHECK(p && g && square_avg && n > 0 && (momentum <= 0.f || momentum_buf), -1, "rmsprop_step: bad arguments");
   return rmsprop_run(p, g, square_avg, momentum_buf, n, lr, alpha, eps, weight_decay, momentum, clip, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ variants glue
+int unetk_add_n(void* dst, int64_t dst_ld, int accumulate, const void* a, int64_t a_ld, const void* b, int64_t b_ld,
+                const void* c, int64_t c_ld, const void* d, int64_t d_ld, int64_t npix, int C, void* stream) {
+  UNETK_CHECK(dst && a, -1, "add_n: null pointer");
+  const void* src[4] = {a, b, c, d};
+  const int64_t ld[4] = {a_ld, b_ld, c_ld, d_ld};
+  int n = 1;
+  while (n < 4 && src[n] != nullptr) ++n;
+  for (int k = n; k < 4; ++k) UNETK_CHECK(src[k] == nullptr, -1, "add_n: sources must be packed (NULL only at the end)");
+  return add_n_run(dst, dst_ld, accumulate, src, ld, n, npix, C, S(stream));
+}
+int unetk_upsample_nearest2x_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int N, int H, int W, int C,
+                                 void* stream) {
+  UNETK_CHECK(x && y, -1, "upsample_nearest2x_fwd: null pointer");
+  return upsample_nearest2x_run(x, x_ld, y, y_ld, 0, 0, N, H, W, C, S(stream));
+}
+int unetk_upsample_nearest2x_bwd(const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int accumulate, int N, int H,
+                                 int W, int C, void* stream) {
+  UNETK_CHECK(dy && dx, -1, "upsample_nearest2x_bwd: null pointer");
+  return upsample_nearest2x_run(dy, dy_ld, dx, dx_ld, 1, accumulate, N, H, W, C, S(stream));
+}
+int unetk_upsample_bilinear2x_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int N, int H, int W, int C,
+                                  void* stream) {
+  UNETK_CHECK(x && y, -1, "upsample_bilinear2x_fwd: null pointer");
+  return upsample_bilinear2x_run(x, x_ld, y, y_ld, 0, 0, N, H, W, C, S(stream));
+}
+int unetk_upsample_bilinear2x_bwd(const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int accumulate, int N, int H,
+                                  int W, int C, void* stream) {
+  UNETK_CHECK(dy && dx, -1, "upsample_bilinear2x_bwd: null pointer");
+  return upsample_bilinear2x_run(dy, dy_ld, dx, dx_ld, 1, accumulate, N, H, W, C, S(stream));
+}
+int unetk_copy_f32_strided(float* dst, int64_t dst_stride, const float* src, int64_t src_stride, int64_t n,
+                           int accumulate, void* stream) {
+  return copy_f32_strided_run(dst, dst_stride, src, src_stride, n, accumulate, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ attention gate
+size_t unetk_gate_partial_floats(int64_t npix, int F_int) { return gate_partial_floats(npix, F_int); }
+int unetk_gate_fwd(const void* raw_g, int64_t raw_g_ld, const void* raw_x, int64_t raw_x_ld, const float* sc_g,
+                   const float* sh_g, const float* sc_x, const float* sh_x, const float* w_psi, const float* b_psi,
+                   float* s, float* partial, double* sums, int64_t npix, int F_int, void* stream) {
+  UNETK_CHECK(raw_g && raw_x && sc_g && sh_g && sc_x && sh_x && w_psi && s && partial && sums && npix > 0, -1,
+              "gate_fwd: bad arguments");
+  return gate_fwd_run(raw_g, raw_g_ld, raw_x, raw_x_ld, sc_g, sh_g, sc_x, sh_x, w_psi, b_psi, s, partial, sums, npix,
+                      F_int, S(stream));
+}
+int unetk_gate_apply(const void* x, int64_t x_ld, const float* s, const float* sc1, const float* sh1, void* out,
+                     int64_t out_ld, int64_t npix, int F_l, void* stream) {
+  UNETK_CHECK(x && s && sc1 && sh1 && out && npix > 0, -1, "gate_apply: bad arguments");
+  return gate_apply_run(x, x_ld, s, sc1, sh1, out, out_ld, npix, F_l, S(stream));
+}
+int unetk_gate_bwd_psi(const void* dout, int64_t dout_ld, const void* x, int64_t x_ld, const float* s,
+                       const float* sc1, const float* sh1, const float* mean1, void* dx, int64_t dx_ld,
+                       int dx_accumulate, float* dz, float* partial, double* sums, int64_t npix, int F_l, void* stream) {
+  UNETK_CHECK(dout && x && s && sc1 && sh1 && mean1 && dx && dz && partial && sums && npix > 0, -1,
+              "gate_bwd_psi: bad arguments");
+  return gate_bwd_psi_run(dout, dout_ld, x, x_ld, s, sc1, sh1, mean1, dx, dx_ld, dx_accumulate, dz, partial, sums, npix,
+                          F_l, S(stream));
+}
+int unetk_gate_bwd_reduce(const void* raw_g, int64_t raw_g_ld, const void* raw_x, int64_t raw_x_ld, const float* sc_g,
+                          const float* sh_g, const float* mean_g, const float* sc_x, const float* sh_x,
+                          const float* mean_x, const float* w_psi, const float* s, const float* dz, const float* sc1,
+                          const float* coef1, float* partial, double* sums_g, double* sums_x, float* dw_psi,
+                          float* db_psi, int accumulate, int64_t npix, int F_int, void* stream) {
+  UNETK_CHECK(raw_g && raw_x && sc_g && sh_g && mean_g && sc_x && sh_x && mean_x && w_psi && s && dz && sc1 && coef1 &&
+                  partial && sums_g && sums_x && npix > 0,
+              -1, "gate_bwd_reduce: bad arguments");
+  return gate_bwd_reduce_run(raw_g, raw_g_ld, raw_x, raw_x_ld, sc_g, sh_g, mean_g, sc_x, sh_x, mean_x, w_psi, s, dz, sc1,
+                             coef1, partial, sums_g, sums_x, dw_psi, db_psi, accumulate, npix, F_int, S(stream));
+}
+int unetk_gate_bwd_apply(const void* raw_g, int64_t raw_g_ld, const void* raw_x, int64_t raw_x_ld, const float* sc_g,
+                         const float* sh_g, const float* sc_x, const float* sh_x, const float* w_psi, const float* s,
+                         const float* dz, const float* sc1, const float* coef1, const float* coef_g,
+                         const float* coef_x, void* draw_g, int64_t draw_g_ld, void* draw_x, int64_t draw_x_ld,
+                         int64_t npix, int F_int, void* stream) {
+  UNETK_CHECK(raw_g && raw_x && sc_g && sh_g && sc_x && sh_x && w_psi && s && dz && sc1 && coef1 && coef_g && coef_x &&
+                  draw_g && draw_x && npix > 0,
+              -1, "gate_bwd_apply: bad arguments");
+  return gate_bwd_apply_run(raw_g, raw_g_ld, raw_x, raw_x_ld, sc_g, sh_g, sc_x, sh_x, w_psi, s, dz, sc1, coef1, coef_g,
+                            coef_x, draw_g, draw_g_ld, draw_x, draw_x_ld, npix, F_int, S(stream));
 }
 
 int unetk_probe_umma(const void* a, const void* b, float* d, int mode, int shift, int base_offset, void* stream) {

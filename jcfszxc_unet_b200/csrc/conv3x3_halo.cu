@@ -45,6 +45,7 @@ struct HaloParams {
   CUtensorMap tmOut;  // dims (ncols, W, H, N), box (64, 128, 1, 1)
   const float* bias;
   float* stats_partial;
+  int accumulate;  // != 0: out += tile (TMA reduce-add)
   int H, W, tiles_h, tiles_w, num_m_tiles, num_n_tiles, ncols, kchunks;
   int resident;  // 1: all 9*kchunks weight tiles stay in smem for the whole kernel (they fit), no B ring
   int8_t dh[9], dw[9], btap[9];
@@ -269,7 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
           fence_proxy_async_smem();
           named_bar_sync(1, kEpiThreads);
           if (leader) {
-            tma_store_4d(&p.tmOut, buf, colbase, w0, h0 + u, img);
+            if (p.accumulate) tma_reduce_add_4d(&p.tmOut, buf, colbase, w0, h0 + u, img);
+            else tma_store_4d(&p.tmOut, buf, colbase, w0, h0 + u, img);
             bulk_commit();
           }
           if (p.stats_partial != nullptr && colbase + st_ch < p.ncols) {
@@ -357,6 +359,7 @@ int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.kchunks = (d.K + 63) / 64;
   for (int t = 0; t < 9; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
   p.bias = d.bias;
+  p.accumulate = d.accumulate;
   p.stats_partial = d.stats_sums ? d.stats_partial : nullptr;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();

@@ -238,7 +238,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         fence_proxy_async_smem();
         named_bar_sync(1, kEpiThreads);
         if (leader) {
-          tma_store_4d(&p.tmOut[q], buf, colbase, w0, h0, img);
+          if (p.accumulate) tma_reduce_add_4d(&p.tmOut[q], buf, colbase, w0, h0, img);
+          else tma_store_4d(&p.tmOut[q], buf, colbase, w0, h0, img);
           bulk_commit();
         }
         if (p.stats_partial != nullptr && colbase + st_ch < p.ncols) {
@@ -379,6 +380,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.a_step = d.a_step;
   for (int t = 0; t < d.taps; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
   p.bias = d.bias;
+  p.accumulate = d.accumulate;
   p.stats_partial = d.stats_sums ? d.stats_partial : nullptr;
   {
     // L2 prefetch only pays when A streams from HBM (tensor much larger than what L2 keeps between taps)

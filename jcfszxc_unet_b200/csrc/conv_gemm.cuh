@@ -29,6 +29,7 @@ struct ConvGemmDesc {
   // Optional fused BatchNorm statistics of the bf16 output (q_groups == 1 only):
   float* stats_partial;   // scratch, >= conv_gemm_stats_partial_floats(ncols) floats
   double* stats_sums;     // out: double [2][ncols] = per-channel (sum, sum of squares)
+  int accumulate;         // != 0: out += result (TMA reduce-add, bf16) instead of out = result
 };
 
 // Kernel parameter block (passed by value, holds the TMA descriptors).
@@ -42,6 +43,7 @@ struct ConvGemmParams {
   int TH, TW, tw_shift, tiles_h, tiles_w;
   int num_m_tiles, num_n_tiles, tiles_per_q, rows_per_q, ncols;
   int taps, kchunks, a_step;
+  int accumulate;   // != 0: epilogue uses cp.reduce.async.bulk.tensor (.add) instead of a plain store
   int l2_prefetch;  // > 0: prefetch the A box of the tile `l2_prefetch` rounds ahead into L2
   int8_t dh[9], dw[9], btap[9];
 };

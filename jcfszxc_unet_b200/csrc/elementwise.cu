@@ -6,6 +6,7 @@
 // Reference semantics replaced: nn.BatchNorm2d + nn.ReLU(inplace) + nn.MaxPool2d(2) inside
 // DoubleConv/Down (UNetFamily/utils/unet_parts.py:24-31,42-44) and their autograd backward.
 #include "host_common.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace unetk {
@@ -162,41 +163,59 @@ __device__ __forceinline__ void bn_relu8(const uint4& raw, const float* sc, cons
   }
 }
 
-// Threads keep ONE channel group for the whole kernel (grid stride is a multiple of cg, see flat_grid_cg), so the
-// per-channel constants are loaded once; four 16-byte loads per thread are in flight per iteration (>= 64 KB
-// per SM, what it takes to cover HBM latency at full bandwidth).
+// Threads keep ONE channel group for the whole kernel and walk pixels with a constant pointer step (no division
+// in the loop); four 16-byte loads per tensor per thread are in flight per iteration.
+// RES: out = act(bn(raw)) + res  (the `x + x1` of Recurrent_block / RRCNN_block / ResidualConv,
+// unet_parts.py:128,146,475: a bf16 add of two bf16 tensors under autocast).
+template <bool RES>
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld,
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
+                                                            const __nv_bfloat16* __restrict__ res, int64_t res_ld,
                                                             __nv_bfloat16* __restrict__ out, int64_t out_ld,
                                                             int64_t npix, int C, int relu) {
-  const int cg = C >> 3;
-  const int64_t total = npix * cg;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
-  int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x;
-  if (i >= total) return;
-  const int g = static_cast<int>(i % cg);
+  Lanes L(C);
+  if (!L.active) return;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
+  if (first >= npix) return;
+  const int g = L.g;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
   const bool r = relu != 0;
-  for (; i + 3 * stride < total; i += 4 * stride) {
-    uint4 u[4];
-    int64_t pix[4];
+  int64_t left = (npix - first + stride - 1) / stride;
+  const __nv_bfloat16* pr = raw + first * raw_ld + g * 8;
+  const __nv_bfloat16* ps = RES ? res + first * res_ld + g * 8 : nullptr;
+  __nv_bfloat16* po = out + first * out_ld + g * 8;
+  const int64_t sr = stride * raw_ld, ss = stride * res_ld, so = stride * out_ld;
+  auto one = [&](const uint4& u, const uint4& v, __nv_bfloat16* dst) {
+    float a[8];
+    bn_relu8(u, sc, sh, a, r);
+    if constexpr (RES) {
+      float f[8];
+      unpack8(v, f);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { pix[k] = (i + k * stride) / cg; u[k] = ldg16(raw + pix[k] * raw_ld + g * 8); }
+      for (int j = 0; j < 8; ++j) a[j] += f[j];
+    }
+    stg16(dst, pack8(a));
+  };
+  for (; left >= 4; left -= 4) {
+    uint4 u[4], v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float a[8];
-      bn_relu8(u[k], sc, sh, a, r);
-      stg16(out + pix[k] * out_ld + g * 8, pack8(a));
+      u[k] = ldg16(pr + k * sr);
+      v[k] = RES ? ldg16(ps + k * ss) : make_uint4(0, 0, 0, 0);
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) one(u[k], v[k], po + k * so);
+    pr += 4 * sr; po += 4 * so;
+    if constexpr (RES) ps += 4 * ss;
   }
-  for (; i < total; i += stride) {
-    const int64_t pix = i / cg;
-    float a[8];
-    bn_relu8(ldg16(raw + pix * raw_ld + g * 8), sc, sh, a, r);
-    stg16(out + pix * out_ld + g * 8, pack8(a));
+  for (; left > 0; --left) {
+    one(ldg16(pr), RES ? ldg16(ps) : make_uint4(0, 0, 0, 0), po);
+    pr += sr; po += so;
+    if constexpr (RES) ps += ss;
   }
 }
 
@@ -292,6 +311,7 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, __nv_bfloa
 }
 
 // dx[window pos] = (pos == argmax) ? dy : 0, argmax recomputed from x with the forward rule.
+template <bool ACC>
 __global__ void __launch_bounds__(kThreads)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, const __nv_bfloat16* __restrict__ dy,
                    int64_t dy_ld, __nv_bfloat16* __restrict__ dx, int64_t dx_ld, int N, int H, int W, int C) {
@@ -321,6 +341,12 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, const __nv
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (arg[j] == q) ? gy[j] : 0.f;
+      if constexpr (ACC) {
+        float old[8];
+        unpack8(*reinterpret_cast<const uint4*>(dx + pix * dx_ld + g * 8), old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += old[j];
+      }
       stg16(dx + pix * dx_ld + g * 8, pack8(o));
     }
   }
@@ -330,6 +356,9 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, const __nv
 // Incoming gradient of the activation a = relu(bn(raw)):   g = g1 (same resolution, optional)
 //                                                            + scatter(gp) through the 2x2 max-pool (optional).
 // Unit of work: one 2x2 window x 8 channels when gp is given, else one pixel x 8 channels.
+// Thread layout (Lanes): a thread keeps ONE channel group for the whole kernel and walks pixels with a fixed
+// pointer step, so the loop body has no integer division (the first version spent ~10 of its ~25 instructions
+// per element on 64-bit div/mod and was issue-bound at 39 % of HBM bandwidth, profiles/r01_ncu_bn_bwd_v1.txt).
 struct BnBwdArgs {
   const __nv_bfloat16* raw; int64_t raw_ld;
   const __nv_bfloat16* g1; int64_t g1_ld;   // may be null
@@ -338,83 +367,128 @@ struct BnBwdArgs {
   int N, H, W, C, relu;
 };
 
-// Loads one unit; returns masked gradients gm[q][8] and xhat[q][8] for nq pixels.
-// One unit = one pixel (POOL = false) or one 2x2 window (POOL = true) x 8 channels.  All global loads of
-// the unit are issued up front; per-pixel results are streamed to `emit(pix, gm[8], r[8])` (masked incoming
-// gradient and raw conv output) so that nothing but the packed input vectors stays live.
-// Register diet: only scale/shift (for the ReLU mask / pool argmax) are needed here; the mean/invstd algebra is
-// folded into per-channel coefficients by bn_bwd_finalize_kernel.
-template <bool POOL>
-struct BnBwdUnit {
-  static constexpr int NQ = POOL ? 4 : 1;
-  uint4 ur[NQ], ug[NQ], ugp;
-  int64_t pix[NQ];
-
-  __device__ __forceinline__ void load(const BnBwdArgs& A, int64_t u, int g) {
-    const int Hu = POOL ? A.H >> 1 : A.H, Wu = POOL ? A.W >> 1 : A.W;
-    const int wu = static_cast<int>(u % Wu);
-    const int hu = static_cast<int>((u / Wu) % Hu);
-    const int n = static_cast<int>(u / (static_cast<int64_t>(Wu) * Hu));
+// masked gradient of one pixel x 8 channels: gm = (relu && !(bf16(raw*sc+sh) > 0)) ? 0 : g
+__device__ __forceinline__ void masked8(const uint4& ur, const uint4& ug, const float (&sc)[8], const float (&sh)[8],
+                                        bool relu, float* r, float* gm) {
+  unpack8(ur, r);
+  unpack8(ug, gm);
+  if (relu) {
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int h = POOL ? 2 * hu + (q >> 1) : hu, w = POOL ? 2 * wu + (q & 1) : wu;
-      pix[q] = (static_cast<int64_t>(n) * A.H + h) * A.W + w;
-      ur[q] = ldg16(A.raw + pix[q] * A.raw_ld + g * 8);
-      ug[q] = A.g1 ? ldg16(A.g1 + pix[q] * A.g1_ld + g * 8) : make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < 8; ++j) {
+      const float z = bf16_round(fmaf(r[j], sc[j], sh[j]));
+      gm[j] = (z > 0.f) ? gm[j] : 0.f;
     }
-    if constexpr (POOL) ugp = ldg16(A.gp + u * A.gp_ld + g * 8);
   }
+}
 
+// One 2x2 window x 8 channels: loads issued up front, argmax of the forward's pooled activation recomputed on the
+// same bf16-rounded values (first max wins, NaN taken), per-pixel results streamed to emit(q, gm, r).
+struct PoolWindow {
+  uint4 ur[4], ug[4], ugp;
+  __device__ __forceinline__ void load(const BnBwdArgs& A, int64_t pix0, int64_t opix, int g) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t pix = pix0 + (q >> 1) * A.W + (q & 1);
+      ur[q] = ldg16(A.raw + pix * A.raw_ld + g * 8);
+      ug[q] = A.g1 ? ldg16(A.g1 + pix * A.g1_ld + g * 8) : make_uint4(0, 0, 0, 0);
+    }
+    ugp = ldg16(A.gp + opix * A.gp_ld + g * 8);
+  }
   template <class Emit>
   __device__ __forceinline__ void visit(const BnBwdArgs& A, const float (&sc)[8], const float (&sh)[8],
                                         Emit&& emit) const {
     int arg[8];
-    float gy[8];
-    if constexpr (POOL) {
-      // recompute the forward's pooled argmax on the same bf16-rounded activations (first max wins, NaN taken)
-      float best[8], f[8];
-      unpack8(ur[0], f);
+    float gy[8], best[8], f[8];
+    unpack8(ur[0], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
+      best[j] = A.relu ? fmaxf(z, 0.f) : z;
+      arg[j] = 0;
+    }
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      unpack8(ur[q], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
-        best[j] = A.relu ? fmaxf(z, 0.f) : z;
-        arg[j] = 0;
+        const float v = A.relu ? fmaxf(z, 0.f) : z;
+        if (v > best[j] || v != v) { best[j] = v; arg[j] = q; }
       }
-#pragma unroll
-      for (int q = 1; q < 4; ++q) {
-        unpack8(ur[q], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
-          const float v = A.relu ? fmaxf(z, 0.f) : z;
-          if (v > best[j] || v != v) { best[j] = v; arg[j] = q; }
-        }
-      }
-      unpack8(ugp, gy);
     }
+    unpack8(ugp, gy);
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
+    for (int q = 0; q < 4; ++q) {
       float r[8], gm[8];
       unpack8(ur[q], r);
       unpack8(ug[q], gm);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if constexpr (POOL) gm[j] += (arg[j] == q) ? gy[j] : 0.f;
+        gm[j] += (arg[j] == q) ? gy[j] : 0.f;
         if (A.relu) {
           const float z = bf16_round(fmaf(r[j], sc[j], sh[j]));
-          if (!(z > 0.f)) gm[j] = 0.f;
+          gm[j] = (z > 0.f) ? gm[j] : 0.f;
         }
       }
-      emit(pix[q], gm, r);
+      emit(q, gm, r);
     }
   }
 };
+
+// Walks this thread's share of the tensor: pixels (POOL = false, kUnroll in flight) or 2x2 windows (POOL = true)
+// of channel group L.g, calling emit(pixel index, gm[8], raw[8]).
+template <bool POOL, class Emit>
+__device__ __forceinline__ void bn_bwd_walk(const BnBwdArgs& A, const Lanes& L, const float (&sc)[8],
+                                            const float (&sh)[8], Emit&& emit) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
+  const bool relu = A.relu != 0;
+  if constexpr (!POOL) {
+    const int64_t npix = static_cast<int64_t>(A.N) * A.H * A.W;
+    if (first >= npix) return;
+    int64_t left = (npix - first + stride - 1) / stride;   // pixels this thread visits (one division per thread)
+    const __nv_bfloat16* pr = A.raw + first * A.raw_ld + L.g * 8;
+    const __nv_bfloat16* pg = A.g1 + first * A.g1_ld + L.g * 8;
+    const int64_t sr = stride * A.raw_ld, sg = stride * A.g1_ld;
+    int64_t pix = first;
+    constexpr int kUnroll = 4;
+    for (; left >= kUnroll; left -= kUnroll) {
+      uint4 ur[kUnroll], ug[kUnroll];
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) { ur[k] = ldg16(pr + k * sr); ug[k] = ldg16(pg + k * sg); }
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        float r[8], gm[8];
+        masked8(ur[k], ug[k], sc, sh, relu, r, gm);
+        emit(pix + k * stride, gm, r);
+      }
+      pr += kUnroll * sr; pg += kUnroll * sg; pix += kUnroll * stride;
+    }
+    for (; left > 0; --left) {
+      float r[8], gm[8];
+      masked8(ldg16(pr), ldg16(pg), sc, sh, relu, r, gm);
+      emit(pix, gm, r);
+      pr += sr; pg += sg; pix += stride;
+    }
+  } else {
+    const uint32_t Wu = static_cast<uint32_t>(A.W >> 1), Hu = static_cast<uint32_t>(A.H >> 1);
+    const int64_t units = static_cast<int64_t>(A.N) * Hu * Wu;   // < 2^31 (checked on the host)
+    for (int64_t u = first; u < units; u += stride) {
+      const uint32_t uu = static_cast<uint32_t>(u);
+      const uint32_t wu = uu % Wu, t = uu / Wu;
+      const uint32_t hu = t % Hu, n = t / Hu;
+      const int64_t pix0 = (static_cast<int64_t>(n) * A.H + 2 * hu) * A.W + 2 * wu;
+      PoolWindow w;
+      w.load(A, pix0, u, L.g);
+      w.visit(A, sc, sh, [&](int q, const float* gm, const float* r) { emit(pix0 + (q >> 1) * A.W + (q & 1), gm, r); });
+    }
+  }
+}
 
 // partial[blk][0][c] = sum gm, partial[blk][1][c] = sum gm * (raw - mean)
 template <bool POOL>
 __global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_kernel(const BnBwdArgs A, float* __restrict__ partial) {
   Lanes L(A.C);
-  const int64_t units = static_cast<int64_t>(A.N) * (POOL ? (A.H >> 1) * (A.W >> 1) : A.H * A.W);
   float acc[2][8] = {};
   if (L.active) {
     float sc[8], sh[8], mu[8];
@@ -422,30 +496,10 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_kernel(const BnBwdA
     for (int j = 0; j < 8; ++j) {
       sc[j] = __ldg(A.scale + L.g * 8 + j); sh[j] = __ldg(A.shift + L.g * 8 + j); mu[j] = __ldg(A.mean + L.g * 8 + j);
     }
-    auto emit = [&](int64_t, const float* gm, const float* r) {
+    bn_bwd_walk<POOL>(A, L, sc, sh, [&](int64_t, const float* gm, const float* r) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { acc[0][j] += gm[j]; acc[1][j] = fmaf(gm[j], r[j] - mu[j], acc[1][j]); }
-    };
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
-    int64_t u = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
-    if constexpr (!POOL) {
-      for (; u + 3 * stride < units; u += 4 * stride) {   // four pixels (8 x 16 B) in flight per thread
-        BnBwdUnit<false> a, b, c, d;
-        a.load(A, u, L.g);
-        b.load(A, u + stride, L.g);
-        c.load(A, u + 2 * stride, L.g);
-        d.load(A, u + 3 * stride, L.g);
-        a.visit(A, sc, sh, emit);
-        b.visit(A, sc, sh, emit);
-        c.visit(A, sc, sh, emit);
-        d.visit(A, sc, sh, emit);
-      }
-    }
-    for (; u < units; u += stride) {
-      BnBwdUnit<POOL> a;
-      a.load(A, u, L.g);
-      a.visit(A, sc, sh, emit);
-    }
+    });
   }
   block_reduce_store<2>(acc, L, A.C, partial);
 }
@@ -469,49 +523,34 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int C, d
   coef[C + c] = static_cast<float>(k1);
 }
 
-template <bool POOL>
+// ACC: draw += (bf16 read-modify-write) instead of draw = ; used when `draw` is the gradient of a tensor that has
+// other consumers (pre-activation BatchNorm of ResidualConv, unet_parts.py:458-459).
+template <bool POOL, bool ACC>
 __global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(const BnBwdArgs A, const float* __restrict__ coef, __nv_bfloat16* __restrict__ draw,
                     int64_t draw_ld) {
-  const int cg = A.C >> 3;
-  const int64_t units = static_cast<int64_t>(A.N) * (POOL ? (A.H >> 1) * (A.W >> 1) : A.H * A.W);
-  const int64_t total = units * cg;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
-  int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x;
-  // consecutive threads walk consecutive channel groups of one unit; a thread's next item is `stride` ahead,
-  // which keeps its channel group fixed because stride % cg == 0 (flat_grid_cg)
-  if (i >= total) return;
-  const int g = static_cast<int>(i % cg);
+  Lanes L(A.C);
+  if (!L.active) return;
+  const int g = L.g;
   float sc[8], sh[8], k0[8], k1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sc[j] = __ldg(A.scale + g * 8 + j); sh[j] = __ldg(A.shift + g * 8 + j);
     k0[j] = __ldg(coef + g * 8 + j); k1[j] = __ldg(coef + A.C + g * 8 + j);
   }
-  auto emit = [&](int64_t pix, const float* gm, const float* r) {
+  bn_bwd_walk<POOL>(A, L, sc, sh, [&](int64_t pix, const float* gm, const float* r) {
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], gm[j], fmaf(k1[j], r[j], k0[j]));
-    stg16(draw + pix * draw_ld + g * 8, pack8(o));
-  };
-  if constexpr (!POOL) {
-    for (; i + 3 * stride < total; i += 4 * stride) {
-      BnBwdUnit<false> a, b, c, d;
-      a.load(A, i / cg, g);
-      b.load(A, (i + stride) / cg, g);
-      c.load(A, (i + 2 * stride) / cg, g);
-      d.load(A, (i + 3 * stride) / cg, g);
-      a.visit(A, sc, sh, emit);
-      b.visit(A, sc, sh, emit);
-      c.visit(A, sc, sh, emit);
-      d.visit(A, sc, sh, emit);
+    __nv_bfloat16* dst = draw + pix * draw_ld + g * 8;
+    if constexpr (ACC) {
+      float old[8];
+      unpack8(*reinterpret_cast<const uint4*>(dst), old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = old[j] + bf16_round(o[j]);
     }
-  }
-  for (; i < total; i += stride) {
-    BnBwdUnit<POOL> a;
-    a.load(A, i / cg, g);
-    a.visit(A, sc, sh, emit);
-  }
+    stg16(dst, pack8(o));
+  });
 }
 
 // grid for the flat (unit x channel-group) kernels whose threads keep their channel group: blocks*kThreads % cg == 0
@@ -537,6 +576,11 @@ int reduce_grid(int64_t units, int C) {
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return static_cast<int>(want);
+}
+// BN backward kernels: 2 resident blocks per SM (register budget), exactly one wave
+int bwd_grid(int64_t units, int C) {
+  const int g = reduce_grid(units, C), cap = num_sms() * 2;
+  return g < cap ? g : cap;
 }
 size_t reduce_smem(int C, int K) {
   const int cg = C / 8;
@@ -601,20 +645,39 @@ int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, f
   return 0;
 }
 
-int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const float* shift, void* out, int64_t out_ld,
-                 void* pooled, int64_t pooled_ld, int N, int H, int W, int C, int relu, cudaStream_t s) {
+// grid for the Lanes-layout streaming kernels: one resident wave, >= 4 units per lane
+static int lanes_grid(int64_t units, int C, int blocks_per_sm) {
+  int ppb = kThreads / (C / 8);
+  if (ppb < 1) ppb = 1;
+  int64_t want = (units + ppb * 4 - 1) / (ppb * 4);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * blocks_per_sm;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+
+int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const void* res,
+                 int64_t res_ld, void* out, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W, int C,
+                 int relu, cudaStream_t s) {
   CHECK_C(C);
   if (pooled != nullptr) {
     UNETK_CHECK(H % 2 == 0 && W % 2 == 0 && relu, -1, "fused pool needs even H,W and relu");
+    UNETK_CHECK(res == nullptr, -1, "bn_apply: fused pool and residual add cannot be combined");
     const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
     bn_apply_pool_kernel<<<flat_grid_cg(total, C / 8), kThreads, 0, s>>>(
         static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift, static_cast<__nv_bfloat16*>(out), out_ld,
         static_cast<__nv_bfloat16*>(pooled), pooled_ld, N, H, W, C);
   } else {
     const int64_t npix = static_cast<int64_t>(N) * H * W;
-    bn_apply_kernel<<<flat_grid_cg(npix * (C / 8), C / 8), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(raw), raw_ld,
-                                                                  scale, shift, static_cast<__nv_bfloat16*>(out),
-                                                                  out_ld, npix, C, relu);
+    const int grid = lanes_grid(npix, C, 8);
+    if (res != nullptr)
+      bn_apply_kernel<true><<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift,
+                                                      static_cast<const __nv_bfloat16*>(res), res_ld,
+                                                      static_cast<__nv_bfloat16*>(out), out_ld, npix, C, relu);
+    else
+      bn_apply_kernel<false><<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift,
+                                                       nullptr, 0, static_cast<__nv_bfloat16*>(out), out_ld, npix, C,
+                                                       relu);
   }
   UNETK_LAUNCHED();
   return 0;
@@ -631,14 +694,19 @@ int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long lon
   return 0;
 }
 
-int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int N, int H,
-                    int W, int C, cudaStream_t s) {
+int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
+                    int accumulate, int N, int H, int W, int C, cudaStream_t s) {
   CHECK_C(C);
   UNETK_CHECK(H % 2 == 0 && W % 2 == 0, -1, "maxpool_bwd: odd spatial size %dx%d not supported", H, W);
   const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
-  maxpool_bwd_kernel<<<flat_grid(total), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
-                                                          static_cast<const __nv_bfloat16*>(dy), dy_ld,
-                                                          static_cast<__nv_bfloat16*>(dx), dx_ld, N, H, W, C);
+  if (accumulate)
+    maxpool_bwd_kernel<true><<<flat_grid(total), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
+                                                                  static_cast<const __nv_bfloat16*>(dy), dy_ld,
+                                                                  static_cast<__nv_bfloat16*>(dx), dx_ld, N, H, W, C);
+  else
+    maxpool_bwd_kernel<false><<<flat_grid(total), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
+                                                                   static_cast<const __nv_bfloat16*>(dy), dy_ld,
+                                                                   static_cast<__nv_bfloat16*>(dx), dx_ld, N, H, W, C);
   UNETK_LAUNCHED();
   return 0;
 }
@@ -648,7 +716,10 @@ static int bn_bwd_args(BnBwdArgs* A, const void* raw, int64_t raw_ld, const void
                        int N, int H, int W, int C, int relu) {
   CHECK_C(C);
   UNETK_CHECK(g1 != nullptr || gp != nullptr, -1, "bn_bwd: no incoming gradient");
-  if (gp != nullptr) UNETK_CHECK(H % 2 == 0 && W % 2 == 0, -1, "bn_bwd: pooled gradient needs even H,W");
+  if (gp != nullptr) {
+    UNETK_CHECK(H % 2 == 0 && W % 2 == 0, -1, "bn_bwd: pooled gradient needs even H,W");
+    UNETK_CHECK(static_cast<int64_t>(N) * (H / 2) * (W / 2) < (1ll << 31), -1, "bn_bwd: too many pooling windows");
+  }
   *A = BnBwdArgs{static_cast<const __nv_bfloat16*>(raw), raw_ld, static_cast<const __nv_bfloat16*>(g1), g1_ld,
                  static_cast<const __nv_bfloat16*>(gp), gp_ld, scale, shift, mean, invstd, N, H, W, C, relu};
   return 0;
@@ -662,7 +733,7 @@ int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g
   if (int rc = bn_bwd_args(&A, raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, N, H, W, C, relu)) return rc;
   const bool pool = gp != nullptr;
   const int64_t units = pool ? static_cast<int64_t>(N) * (H / 2) * (W / 2) : static_cast<int64_t>(N) * H * W;
-  const int grid = reduce_grid(units, C);
+  const int grid = bwd_grid(units, C);
   const size_t smem = reduce_smem(C, 2);
   if (pool) bn_bwd_reduce_kernel<true><<<grid, kThreads, smem, s>>>(A, partial);
   else bn_bwd_reduce_kernel<false><<<grid, kThreads, smem, s>>>(A, partial);
@@ -670,19 +741,34 @@ int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g
   return launch_sums(partial, grid, C, sums, s);
 }
 
+int bn_bwd_coef_run(const double* sums, int C, double count, const float* scale, const float* mean,
+                    const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, cudaStream_t s) {
+  UNETK_CHECK(C >= 1, -1, "bn_bwd_coef: C=%d", C);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
 int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
                      const float* scale, const float* shift, const float* mean, const float* invstd,
                      const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
-                     void* draw, int64_t draw_ld, int N, int H, int W, int C, int relu, cudaStream_t s) {
+                     void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C, int relu,
+                     cudaStream_t s) {
   BnBwdArgs A;
   if (int rc = bn_bwd_args(&A, raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, N, H, W, C, relu)) return rc;
   const bool pool = gp != nullptr;
   const int64_t units = pool ? static_cast<int64_t>(N) * (H / 2) * (W / 2) : static_cast<int64_t>(N) * H * W;
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef);
   UNETK_LAUNCHED();
-  const int fg = flat_grid_cg(units * (C / 8), C / 8);
-  if (pool) bn_bwd_apply_kernel<true><<<fg, kThreads, 0, s>>>(A, coef, static_cast<__nv_bfloat16*>(draw), draw_ld);
-  else bn_bwd_apply_kernel<false><<<fg, kThreads, 0, s>>>(A, coef, static_cast<__nv_bfloat16*>(draw), draw_ld);
+  const int grid = bwd_grid(units, C);
+  __nv_bfloat16* d = static_cast<__nv_bfloat16*>(draw);
+  if (pool) {
+    if (draw_accumulate) bn_bwd_apply_kernel<true, true><<<grid, kThreads, 0, s>>>(A, coef, d, draw_ld);
+    else bn_bwd_apply_kernel<true, false><<<grid, kThreads, 0, s>>>(A, coef, d, draw_ld);
+  } else {
+    if (draw_accumulate) bn_bwd_apply_kernel<false, true><<<grid, kThreads, 0, s>>>(A, coef, d, draw_ld);
+    else bn_bwd_apply_kernel<false, false><<<grid, kThreads, 0, s>>>(A, coef, d, draw_ld);
+  }
   UNETK_LAUNCHED();
   return 0;
 }

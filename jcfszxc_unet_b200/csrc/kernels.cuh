@@ -1,0 +1,94 @@
+// Internal entry points of the kernel translation units (one *_run per C-ABI function family).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace unetk {
+const char* last_error();
+int probe_run(const void* a, const void* b, float* d, int mode, int shift, int bo, cudaStream_t stream);
+int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, cudaStream_t stream);
+// wgrad3x3.cu
+size_t wgrad3x3_workspace_bytes(int N, int H, int W, int M, int Nn);
+int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, float* dw, int accumulate, int N, int H,
+                 int W, int M, int Nn, void* workspace, size_t ws_bytes, cudaStream_t stream);
+// stem.cu
+int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
+                 void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
+size_t stem_wgrad_workspace(int N, int H, int W, int Cin);
+int stem_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy, int64_t dy_ld,
+                   float* dw, int accumulate, int N, int H, int W, int Cin, int Cout, void* ws, size_t ws_bytes,
+                   cudaStream_t s);
+// elementwise.cu
+size_t chan_partial_floats(int64_t units, int C);
+int bn_stats_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, double* sums, cudaStream_t s);
+int bn_finalize_run(const double* sums, int C, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* rm, float* rv, long long* nbt, float* scale, float* shift, float* mean,
+                    float* invstd, cudaStream_t s);
+int bn_eval_fold_run(int C, const float* gamma, const float* beta, float eps, const float* rm, const float* rv,
+                     float* scale, float* shift, float* mean, float* invstd, cudaStream_t s);
+int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, float* out, int accumulate,
+               cudaStream_t s);
+int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const void* res,
+                 int64_t res_ld, void* out, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W, int C,
+                 int relu, cudaStream_t s);
+int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long long* idx, int N, int H, int W, int C,
+                    cudaStream_t s);
+int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
+                    int accumulate, int N, int H, int W, int C, cudaStream_t s);
+int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
+                      const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
+                      double* sums, int N, int H, int W, int C, int relu, cudaStream_t s);
+int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
+                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                     const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
+                     void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C, int relu,
+                     cudaStream_t s);
+// loss.cu
+size_t head_partial_floats(int64_t npix, int C);
+int head_loss_fwd_run(const void* x, int64_t ld, const float* w, const float* bias, const float* labels, float* logits,
+                      int post_sigmoid, int64_t npix, int C, float* partial, double* sums, cudaStream_t s);
+int loss_finalize_run(const double* sums, double npix_total, float* out, cudaStream_t s);
+int head_loss_bwd_run(const void* x, int64_t ld, const float* w, const float* labels, const float* logits,
+                      const float* fin, const float* dlogits, float gscale, int post_sigmoid, void* dx, int64_t dx_ld,
+                      float* dw, float* db, int accumulate, int64_t npix, int C, float* partial, cudaStream_t s);
+// optim.cu
+int sqnorm_blocks(int64_t n);
+int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, float* partial, float* out,
+                       cudaStream_t s);
+int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, float lr, float alpha, float eps, float wd,
+                float momentum, const float* clip, cudaStream_t s);
+// resample.cu
+int add_n_run(void* dst, int64_t dst_ld, int accumulate, const void* const* src, const int64_t* src_ld, int nsrc,
+              int64_t npix, int C, cudaStream_t s);
+int upsample_nearest2x_run(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int backward, int accumulate,
+                           int N, int H, int W, int C, cudaStream_t s);
+int upsample_bilinear2x_run(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int backward, int accumulate,
+                            int N, int H, int W, int C, cudaStream_t s);
+int copy_f32_strided_run(float* dst, int64_t ds, const float* src, int64_t ss, int64_t n, int accumulate,
+                         cudaStream_t s);
+// elementwise.cu
+int bn_bwd_coef_run(const double* sums, int C, double count, const float* scale, const float* mean,
+                    const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, cudaStream_t s);
+// gate.cu
+size_t gate_partial_floats(int64_t npix, int F);
+int gate_fwd_run(const void* rawg, int64_t rawg_ld, const void* rawx, int64_t rawx_ld, const float* scg,
+                 const float* shg, const float* scx, const float* shx, const float* wpsi, const float* bpsi, float* s,
+                 float* partial, double* sums, int64_t npix, int F, cudaStream_t st);
+int gate_apply_run(const void* x, int64_t x_ld, const float* s, const float* sc1, const float* sh1, void* out,
+                   int64_t out_ld, int64_t npix, int F, cudaStream_t st);
+int gate_bwd_psi_run(const void* dout, int64_t dout_ld, const void* x, int64_t x_ld, const float* s, const float* sc1,
+                     const float* sh1, const float* mean1, void* dx, int64_t dx_ld, int dx_accumulate, float* dz,
+                     float* partial, double* sums, int64_t npix, int F, cudaStream_t st);
+int gate_bwd_reduce_run(const void* rawg, int64_t rawg_ld, const void* rawx, int64_t rawx_ld, const float* scg,
+                        const float* shg, const float* mug, const float* scx, const float* shx, const float* mux,
+                        const float* wpsi, const float* s, const float* dz, const float* sc1, const float* coef1,
+                        float* partial, double* sums_g, double* sums_x, float* dwpsi, float* dbpsi, int accumulate,
+                        int64_t npix, int F, cudaStream_t st);
+int gate_bwd_apply_run(const void* rawg, int64_t rawg_ld, const void* rawx, int64_t rawx_ld, const float* scg,
+                       const float* shg, const float* scx, const float* shx, const float* wpsi, const float* s,
+                       const float* dz, const float* sc1, const float* coef1, const float* coefg, const float* coefx,
+                       void* drawg, int64_t drawg_ld, void* drawx, int64_t drawx_ld, int64_t npix, int F,
+                       cudaStream_t st);
+}  // namespace unetk

@@ -6,6 +6,7 @@
 // The three dice sums are produced separately from the finalize step so that data-parallel ranks can
 // all-reduce them (the reference's dice is ONE ratio over the whole batch).
 #include "host_common.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace unetk {
@@ -30,7 +31,7 @@ __device__ __forceinline__ float group_sum(float v, int lpp) {
 __global__ void __launch_bounds__(kThreads)
 head_loss_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ w,
                      const float* __restrict__ bias, const float* __restrict__ labels, float* __restrict__ logits,
-                     int64_t npix, int C, float* __restrict__ partial) {
+                     int post_sigmoid, int64_t npix, int C, float* __restrict__ partial) {
   const int lpp = C >> 3;                 // lanes per pixel (power of two <= 32)
   const int gpb = kThreads / lpp;         // pixel groups per block
   const int sub = threadIdx.x % lpp, grp = threadIdx.x / lpp;
@@ -51,7 +52,9 @@ head_loss_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const floa
     }
     dot = group_sum(dot, lpp);
     if (sub == 0 && pix < npix) {
-      const float z = dot + b;
+      // post_sigmoid: the model itself ends in nn.Sigmoid (ResUNet.py:47-50, UNetPP.py:105-106) and train.py
+      // still feeds that output to BCEWithLogits / sigmoid+dice, so the loss sees sigmoid(z) as its "logit"
+      const float z = post_sigmoid ? 1.f / (1.f + __expf(-(dot + b))) : dot + b;
       logits[pix] = z;
       if (labels != nullptr) {
         const float y = __ldg(labels + pix);
@@ -112,7 +115,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ sums, double npi
 __global__ void __launch_bounds__(kThreads)
 head_loss_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ w,
                      const float* __restrict__ labels, const float* __restrict__ logits,
-                     const float* __restrict__ fin, const float* __restrict__ dlogits, float gscale,
+                     const float* __restrict__ fin, const float* __restrict__ dlogits, float gscale, int post_sigmoid,
                      __nv_bfloat16* __restrict__ dx, int64_t dx_ld, int64_t npix, int C,
                      float* __restrict__ partial) {
   const int lpp = C >> 3;
@@ -133,6 +136,10 @@ head_loss_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const floa
       const float p = 1.f / (1.f + __expf(-z));
       const float inside = (p >= kClampLo && p <= kClampHi) ? 1.f : 0.f;
       dz = gscale * (0.5f * inv_n * (p - y) - 0.5f * (y * cA - cB) * p * (1.f - p) * inside);
+    }
+    if (post_sigmoid) {  // chain through the model's own output sigmoid: logits[] holds its value
+      const float o = __ldg(logits + pix);
+      dz *= o * (1.f - o);
     }
     float f[8], o[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * ld + sub * 8)), f);
@@ -181,11 +188,11 @@ bool head_c_ok(int C) { return C == 8 || C == 16 || C == 32 || C == 64 || C == 1
 size_t head_partial_floats(int64_t npix, int C) { return static_cast<size_t>(head_grid(npix, C)) * (C + 1 > 4 ? C + 1 : 4); }
 
 int head_loss_fwd_run(const void* x, int64_t ld, const float* w, const float* bias, const float* labels, float* logits,
-                      int64_t npix, int C, float* partial, double* sums, cudaStream_t s) {
+                      int post_sigmoid, int64_t npix, int C, float* partial, double* sums, cudaStream_t s) {
   UNETK_CHECK(head_c_ok(C), -1, "head: C=%d must be a power of two in [8,256]", C);
   const int grid = head_grid(npix, C);
-  head_loss_fwd_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, w, bias, labels, logits, npix,
-                                                C, partial);
+  head_loss_fwd_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, w, bias, labels, logits,
+                                                post_sigmoid, npix, C, partial);
   UNETK_LAUNCHED();
   if (labels != nullptr) {
     UNETK_CHECK(sums != nullptr, -1, "head_loss_fwd: sums is null");
@@ -202,16 +209,17 @@ int loss_finalize_run(const double* sums, double npix_total, float* out, cudaStr
 }
 
 int head_loss_bwd_run(const void* x, int64_t ld, const float* w, const float* labels, const float* logits,
-                      const float* fin, const float* dlogits, float gscale, void* dx, int64_t dx_ld, float* dw,
-                      float* db, int accumulate, int64_t npix, int C, float* partial, cudaStream_t s) {
+                      const float* fin, const float* dlogits, float gscale, int post_sigmoid, void* dx, int64_t dx_ld,
+                      float* dw, float* db, int accumulate, int64_t npix, int C, float* partial, cudaStream_t s) {
   UNETK_CHECK(dlogits != nullptr || (labels && logits && fin), -1, "head_bwd: need dlogits or (labels, logits, fin)");
+  UNETK_CHECK(!post_sigmoid || logits != nullptr, -1, "head_bwd: post_sigmoid needs the forward's output");
   UNETK_CHECK(head_c_ok(C), -1, "head: C=%d must be a power of two in [8,256]", C);
   const int grid = head_grid(npix, C);
   const int gpb = kThreads / (C / 8);
   const size_t smem = static_cast<size_t>(gpb) * (C + 1) * sizeof(float);
   head_loss_bwd_kernel<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(x), ld, w, labels, logits, fin,
-                                                   dlogits, gscale, static_cast<__nv_bfloat16*>(dx), dx_ld, npix, C,
-                                                   partial);
+                                                   dlogits, gscale, post_sigmoid, static_cast<__nv_bfloat16*>(dx), dx_ld,
+                                                   npix, C, partial);
   UNETK_LAUNCHED();
   head_bwd_finalize_kernel<<<(C + 1 + 127) / 128, 128, 0, s>>>(partial, grid, C, dw, db, accumulate);
   UNETK_LAUNCHED();

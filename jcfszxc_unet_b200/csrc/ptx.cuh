@@ -121,6 +121,16 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_
       "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// same, but global += smem tile (element-wise add in the tensor map's data type: bf16 += bf16, one rounding).
+// Used when the destination is the gradient of a tensor with several consumers.
+__device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, const void* smem_src, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(tmap)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N bulk groups of this thread still READ their smem source
 template <int N>

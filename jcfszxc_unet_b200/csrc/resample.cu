@@ -1,0 +1,358 @@
+// HBM-bound glue of the U-Net variants: n-ary residual adds / slice copies, nearest and bilinear 2x
+// up-sampling with their backward passes, and a strided fp32 copy for derived weight caches.
+// NHWC bf16, 16-byte vectors (8 channels per thread); a thread keeps one channel group and walks pixels
+// with a constant pointer step (Lanes layout of elementwise.cu), so loops carry no integer division.
+// Reference semantics replaced:
+//   x + x1            Recurrent_block / RRCNN_block / ResidualConv / ResUNet   unet_parts.py:128,146,475, ResUNet.py:54
+//   torch.cat copies  NestedUNet dense skips                                    UNetPP.py:75-99
+//   nn.Upsample(scale_factor=2)  (nearest)  up_conv                             unet_parts.py:103
+//   nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)            UNetPP.py:44
+#include "host_common.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace unetk {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stg16(__nv_bfloat16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+struct Lanes {
+  int cg, ppb, g, pl;
+  bool active;
+  __device__ Lanes(int C) {
+    cg = C >> 3;
+    ppb = kThreads / cg;
+    if (ppb < 1) ppb = 1;
+    g = threadIdx.x % cg;
+    pl = threadIdx.x / cg;
+    active = pl < ppb;
+  }
+};
+
+int lanes_grid(int64_t units, int C, int per_lane = 4, int blocks_per_sm = 8) {
+  int ppb = kThreads / (C / 8);
+  if (ppb < 1) ppb = 1;
+  int64_t want = (units + static_cast<int64_t>(ppb) * per_lane - 1) / (static_cast<int64_t>(ppb) * per_lane);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * blocks_per_sm;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+
+// ------------------------------------------------------------------ dst = [dst +] a [+ b [+ c [+ d]]]
+struct AddArgs {
+  __nv_bfloat16* dst; int64_t dst_ld;
+  const __nv_bfloat16* src[4]; int64_t src_ld[4];
+  int nsrc, accumulate;
+  int64_t npix; int C;
+};
+
+// Every partial sum is rounded to bf16, like the chain of bf16 tensor adds it replaces.
+template <int NSRC, bool ACC>
+__global__ void __launch_bounds__(kThreads) add_n_kernel(const AddArgs A) {
+  Lanes L(A.C);
+  if (!L.active) return;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
+  if (first >= A.npix) return;
+  int64_t left = (A.npix - first + stride - 1) / stride;
+  const __nv_bfloat16* ps[NSRC];
+  int64_t ss[NSRC];
+#pragma unroll
+  for (int k = 0; k < NSRC; ++k) { ps[k] = A.src[k] + first * A.src_ld[k] + L.g * 8; ss[k] = stride * A.src_ld[k]; }
+  __nv_bfloat16* pd = A.dst + first * A.dst_ld + L.g * 8;
+  const int64_t sd = stride * A.dst_ld;
+  constexpr int U = (NSRC + (ACC ? 1 : 0)) <= 2 ? 4 : 2;
+  auto combine = [&](const uint4 (&v)[NSRC], const uint4& old, __nv_bfloat16* dst) {
+    float acc[8], f[8];
+    if constexpr (ACC) {
+      unpack8(old, acc);
+      unpack8(v[0], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = bf16_round(acc[j] + f[j]);
+    } else {
+      unpack8(v[0], acc);
+    }
+#pragma unroll
+    for (int k = 1; k < NSRC; ++k) {
+      unpack8(v[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = bf16_round(acc[j] + f[j]);
+    }
+    stg16(dst, pack8(acc));
+  };
+  for (; left >= U; left -= U) {
+    uint4 v[U][NSRC], old[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int k = 0; k < NSRC; ++k) v[u][k] = ldg16(ps[k] + u * ss[k]);
+      old[u] = ACC ? *reinterpret_cast<const uint4*>(pd + u * sd) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) combine(v[u], old[u], pd + u * sd);
+#pragma unroll
+    for (int k = 0; k < NSRC; ++k) ps[k] += U * ss[k];
+    pd += U * sd;
+  }
+  for (; left > 0; --left) {
+    uint4 v[NSRC];
+#pragma unroll
+    for (int k = 0; k < NSRC; ++k) v[k] = ldg16(ps[k]);
+    const uint4 old = ACC ? *reinterpret_cast<const uint4*>(pd) : make_uint4(0, 0, 0, 0);
+    combine(v, old, pd);
+#pragma unroll
+    for (int k = 0; k < NSRC; ++k) ps[k] += ss[k];
+    pd += sd;
+  }
+}
+
+template <int NSRC>
+void launch_add(const AddArgs& A, int grid, cudaStream_t s) {
+  if (A.accumulate) add_n_kernel<NSRC, true><<<grid, kThreads, 0, s>>>(A);
+  else add_n_kernel<NSRC, false><<<grid, kThreads, 0, s>>>(A);
+}
+
+// ------------------------------------------------------------------ nearest 2x
+// One unit = one INPUT pixel x 8 channels: fwd replicates it to the 2x2 output block; bwd sums the 2x2 block of
+// dy in fp32 and rounds once (ATen's upsample_nearest2d_backward accumulates in float as well).
+template <bool BWD, bool ACC>
+__global__ void __launch_bounds__(kThreads)
+nearest2x_kernel(const __nv_bfloat16* __restrict__ src, int64_t src_ld, __nv_bfloat16* __restrict__ dst,
+                 int64_t dst_ld, int N, int H, int W, int C) {
+  // H, W: low-resolution size.  fwd: src low -> dst high.  bwd: src high (dy) -> dst low (dx).
+  Lanes L(C);
+  if (!L.active) return;
+  const int64_t units = static_cast<int64_t>(N) * H * W;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+  const uint32_t Wu = static_cast<uint32_t>(W), Hu = static_cast<uint32_t>(H);
+  for (int64_t u = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl; u < units; u += stride) {
+    const uint32_t uu = static_cast<uint32_t>(u);
+    const uint32_t w = uu % Wu, t = uu / Wu;
+    const uint32_t h = t % Hu, n = t / Hu;
+    const int64_t hi0 = (static_cast<int64_t>(n) * 2 * H + 2 * h) * (2 * W) + 2 * w;
+    if constexpr (!BWD) {
+      const uint4 v = ldg16(src + u * src_ld + L.g * 8);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) stg16(dst + (hi0 + (q >> 1) * 2 * W + (q & 1)) * dst_ld + L.g * 8, v);
+    } else {
+      uint4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = ldg16(src + (hi0 + (q >> 1) * 2 * W + (q & 1)) * src_ld + L.g * 8);
+      float acc[8] = {}, f[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        unpack8(v[q], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+      __nv_bfloat16* d = dst + u * dst_ld + L.g * 8;
+      if constexpr (ACC) {
+        unpack8(*reinterpret_cast<const uint4*>(d), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = f[j] + bf16_round(acc[j]);
+      }
+      stg16(d, pack8(acc));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ bilinear 2x, align_corners=True
+// ATen upsample_bilinear2d (CUDA): scale = (in-1)/(out-1); src = scale*dst; i0 = (int)src; i1 = i0 + (i0 < in-1);
+// l1 = src - i0; l0 = 1 - l1;  out = l0h*(l0w*v00 + l1w*v01) + l1h*(l0w*v10 + l1w*v11) in fp32, rounded once.
+__device__ __forceinline__ void src_index(float scale, int o, int in, int* i0, int* i1, float* l0, float* l1) {
+  const float s = scale * o;
+  const int a = static_cast<int>(s);
+  *i0 = a;
+  *i1 = a + ((a < in - 1) ? 1 : 0);
+  *l1 = s - a;
+  *l0 = 1.f - *l1;
+}
+
+__global__ void __launch_bounds__(kThreads)
+bilinear2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, __nv_bfloat16* __restrict__ y, int64_t y_ld,
+                      int N, int H, int W, int C, float sh, float sw) {
+  Lanes L(C);
+  if (!L.active) return;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int64_t units = static_cast<int64_t>(N) * Ho * Wo;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+  for (int64_t u = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl; u < units; u += stride) {
+    const uint32_t uu = static_cast<uint32_t>(u);
+    const uint32_t wo = uu % Wo, t = uu / Wo;
+    const uint32_t ho = t % Ho, n = t / Ho;
+    int h0, h1, w0, w1;
+    float lh0, lh1, lw0, lw1;
+    src_index(sh, ho, H, &h0, &h1, &lh0, &lh1);
+    src_index(sw, wo, W, &w0, &w1, &lw0, &lw1);
+    const int64_t base = static_cast<int64_t>(n) * H * W;
+    float a[8], b[8], c[8], d[8], o[8];
+    unpack8(ldg16(x + (base + static_cast<int64_t>(h0) * W + w0) * x_ld + L.g * 8), a);
+    unpack8(ldg16(x + (base + static_cast<int64_t>(h0) * W + w1) * x_ld + L.g * 8), b);
+    unpack8(ldg16(x + (base + static_cast<int64_t>(h1) * W + w0) * x_ld + L.g * 8), c);
+    unpack8(ldg16(x + (base + static_cast<int64_t>(h1) * W + w1) * x_ld + L.g * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = lh0 * (lw0 * a[j] + lw1 * b[j]) + lh1 * (lw0 * c[j] + lw1 * d[j]);
+    stg16(y + u * y_ld + L.g * 8, pack8(o));
+  }
+}
+
+// Gather form of the backward: input pixel i receives from every output o whose (i0, i1) pair contains i.
+// With scale = (in-1)/(2in-1) < 1/2 those outputs lie in [ceil((i-1)/scale), floor((i+1)/scale)] (at most 5).
+__device__ __forceinline__ void contributors(float scale, int i, int in, int out, int* lo, int* hi) {
+  // conservative integer window; exact membership is re-tested with src_index
+  if (!(scale > 0.f)) { *lo = 0; *hi = out - 1; return; }   // in == 1: every output reads input 0
+  int a = static_cast<int>(floorf((i - 1) / scale)) - 1;
+  int b = static_cast<int>(ceilf((i + 1) / scale)) + 1;
+  if (a < 0) a = 0;
+  if (b > out - 1) b = out - 1;
+  *lo = a; *hi = b;
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(kThreads)
+bilinear2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_ld, __nv_bfloat16* __restrict__ dx,
+                      int64_t dx_ld, int N, int H, int W, int C, float sh, float sw) {
+  Lanes L(C);
+  if (!L.active) return;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int64_t units = static_cast<int64_t>(N) * H * W;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+  for (int64_t u = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl; u < units; u += stride) {
+    const uint32_t uu = static_cast<uint32_t>(u);
+    const int w = static_cast<int>(uu % W);
+    const uint32_t t = uu / W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    int hlo, hhi, wlo, whi;
+    contributors(sh, h, H, Ho, &hlo, &hhi);
+    contributors(sw, w, W, Wo, &wlo, &whi);
+    float acc[8] = {};
+    for (int ho = hlo; ho <= hhi; ++ho) {
+      int h0, h1;
+      float lh0, lh1;
+      src_index(sh, ho, H, &h0, &h1, &lh0, &lh1);
+      float wh = 0.f;
+      if (h0 == h) wh += lh0;
+      if (h1 == h) wh += lh1;
+      if (wh == 0.f) continue;
+      for (int wo = wlo; wo <= whi; ++wo) {
+        int w0, w1;
+        float lw0, lw1;
+        src_index(sw, wo, W, &w0, &w1, &lw0, &lw1);
+        float ww = 0.f;
+        if (w0 == w) ww += lw0;
+        if (w1 == w) ww += lw1;
+        if (ww == 0.f) continue;
+        float f[8];
+        unpack8(ldg16(dy + ((static_cast<int64_t>(n) * Ho + ho) * Wo + wo) * dy_ld + L.g * 8), f);
+        const float k = wh * ww;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(k, f[j], acc[j]);
+      }
+    }
+    __nv_bfloat16* d = dx + u * dx_ld + L.g * 8;
+    if constexpr (ACC) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(d), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = f[j] + bf16_round(acc[j]);
+    }
+    stg16(d, pack8(acc));
+  }
+}
+
+__global__ void copy_f32_strided_kernel(float* __restrict__ dst, int64_t ds, const float* __restrict__ src, int64_t ss,
+                                        int64_t n, int accumulate) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = src[i * ss];
+    dst[i * ds] = accumulate ? dst[i * ds] + v : v;
+  }
+}
+
+}  // namespace
+
+#define CHECK_C(C) UNETK_CHECK((C) % 8 == 0 && (C) >= 8 && (C) <= 2048, -1, "channel count %d must be a multiple of 8 in [8,2048]", (C))
+
+int add_n_run(void* dst, int64_t dst_ld, int accumulate, const void* const* src, const int64_t* src_ld, int nsrc,
+              int64_t npix, int C, cudaStream_t s) {
+  CHECK_C(C);
+  UNETK_CHECK(nsrc >= 1 && nsrc <= 4 && npix > 0, -1, "add_n: 1..4 sources");
+  AddArgs A{};
+  A.dst = static_cast<__nv_bfloat16*>(dst); A.dst_ld = dst_ld; A.nsrc = nsrc; A.accumulate = accumulate;
+  A.npix = npix; A.C = C;
+  for (int k = 0; k < nsrc; ++k) {
+    UNETK_CHECK(src[k] != nullptr, -1, "add_n: null source %d", k);
+    A.src[k] = static_cast<const __nv_bfloat16*>(src[k]); A.src_ld[k] = src_ld[k];
+  }
+  const int grid = lanes_grid(npix, C);
+  switch (nsrc) {
+    case 1: launch_add<1>(A, grid, s); break;
+    case 2: launch_add<2>(A, grid, s); break;
+    case 3: launch_add<3>(A, grid, s); break;
+    default: launch_add<4>(A, grid, s); break;
+  }
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+int upsample_nearest2x_run(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int backward, int accumulate,
+                           int N, int H, int W, int C, cudaStream_t s) {
+  CHECK_C(C);
+  const int64_t units = static_cast<int64_t>(N) * H * W;
+  UNETK_CHECK(units > 0 && units < (1ll << 31), -1, "upsample_nearest2x: bad size");
+  const int grid = lanes_grid(units, C, 2);
+  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(src);
+  __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
+  if (!backward) nearest2x_kernel<false, false><<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C);
+  else if (accumulate) nearest2x_kernel<true, true><<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C);
+  else nearest2x_kernel<true, false><<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+int upsample_bilinear2x_run(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int backward, int accumulate,
+                            int N, int H, int W, int C, cudaStream_t s) {
+  CHECK_C(C);
+  const int64_t units = static_cast<int64_t>(N) * H * W * (backward ? 1 : 4);
+  UNETK_CHECK(units > 0 && units < (1ll << 31) && H >= 1 && W >= 1, -1, "upsample_bilinear2x: bad size");
+  // area_pixel_compute_scale(align_corners=True): (in - 1) / (out - 1), 0 when out == 1 (cannot happen for 2x)
+  const float sh = static_cast<float>(H - 1) / static_cast<float>(2 * H - 1);
+  const float sw = static_cast<float>(W - 1) / static_cast<float>(2 * W - 1);
+  const int grid = lanes_grid(units, C, 2);
+  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(src);
+  __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
+  if (!backward) bilinear2x_fwd_kernel<<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C, sh, sw);
+  else if (accumulate) bilinear2x_bwd_kernel<true><<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C, sh, sw);
+  else bilinear2x_bwd_kernel<false><<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C, sh, sw);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+int copy_f32_strided_run(float* dst, int64_t ds, const float* src, int64_t ss, int64_t n, int accumulate,
+                         cudaStream_t s) {
+  UNETK_CHECK(dst && src && n > 0 && ds > 0 && ss > 0, -1, "copy_f32_strided: bad arguments");
+  int64_t b = (n + 255) / 256;
+  if (b > 1024) b = 1024;
+  copy_f32_strided_kernel<<<static_cast<int>(b), 256, 0, s>>>(dst, ds, src, ss, n, accumulate);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+}  // namespace unetk

@@ -57,6 +57,9 @@ class Plan:
         self.grad_of = {}          # id(param) -> fp32 gradient tensor (same shape as the parameter)
         self.params = []           # parameters in registration order
         self.sync_sums = None      # optional hook(sums_view) -> None: all-reduce BN statistics (SyncBN)
+        self.packs = {}            # id(weight) -> WeightPack shared by every op that applies that weight
+        self._g_init = {}          # gradient buffer -> set of channels already written during backward
+        self._p_init = set()       # parameters whose gradient was already written during backward
 
     # ---- allocation -----------------------------------------------------------------------------
     def act(self, H, W, C, grad=None) -> Act:
@@ -93,10 +96,51 @@ class Plan:
                     self.grad_of[id(p)] = torch.zeros_like(p, memory_format=torch.contiguous_format)
         for op in self.ops:
             op.bind(self)
+        # Static backward schedule: walking the ops in backward order, the first op that produces (part of) a
+        # gradient buffer writes it, every later one accumulates.  Tensors with several consumers (recurrent /
+        # residual / dense-skip / gated variants) and shared weights (Recurrent_block) need no zero-fill pass.
+        self._g_init.clear()
+        self._p_init.clear()
+        for op in reversed(self.ops):
+            op.plan_bwd(self)
         return self
+
+    def grad_acc(self, a: "Act") -> bool:
+        """True if `a.g` already holds a gradient when the calling op's backward runs (=> accumulate)."""
+        if a is None or a.g is None:
+            return False
+        st = a.g.untyped_storage().data_ptr()
+        ld = a.g.stride(2)
+        c0 = a.g.storage_offset() % ld
+        chans = set(range(c0, c0 + a.C))
+        seen = self._g_init.setdefault((st, ld), set())
+        hit = chans & seen
+        if hit and hit != chans:
+            raise RuntimeError("gradient buffer partially initialised: a builder wired overlapping channel slices")
+        seen |= chans
+        return bool(hit)
+
+    def grad_written(self, a: "Act"):
+        """Declare that `a.g` is filled from outside the plan (the loss gradient of a block-level plan)."""
+        self.grad_acc(a)
+
+    def param_acc(self, p) -> bool:
+        if p is None:
+            return False
+        hit = id(p) in self._p_init
+        self._p_init.add(id(p))
+        return hit
+
+    def pack_of(self, weight, taps: int, transposed_conv: bool = False) -> "WeightPack":
+        wp = self.packs.get(id(weight))
+        if wp is None:
+            wp = self.packs[id(weight)] = WeightPack(weight, taps)
+        return wp
 
     # ---- execution ------------------------------------------------------------------------------
     def refresh_weights(self, force=False):
+        for wp in self.packs.values():
+            wp.refresh(force)
         for op in self.ops:
             op.refresh(force)
 
@@ -122,22 +166,62 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
-class ConvBNReLU:
-    """conv3x3 (tcgen05 tap-GEMM, or the direct stem kernel when the input is the image) -> BatchNorm
-    (batch statistics in training, running statistics in eval) -> ReLU, optionally fused with the 2x2
-    max-pool that follows it in `Down`.  Reference: unet_parts.py:24-26 / 27-29 (+ :43)."""
+class WeightPack:
+    """bf16 kernel-layout copies of one fp32 master weight [A,B,kh,kw]: ab = [T][A][B], ba = [T][B][A].
+    A derived cache: re-packed when the master changes, shared by all ops using the weight."""
 
-    def __init__(self, plan: Plan, x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, out: Act,
-                 pooled: Act | None = None, relu: bool = True):
-        assert conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1)
-        self.plan, self.x, self.conv, self.bn, self.out, self.pooled, self.relu = plan, x, conv, bn, out, pooled, relu
+    def __init__(self, weight, taps):
+        a, b = weight.shape[0], weight.shape[1]
+        assert weight.numel() == a * b * taps
+        self.w, self.a, self.b, self.taps = weight, a, b, taps
+        self.ab = torch.empty((taps, a, b), dtype=BF16, device=weight.device)
+        self.ba = torch.empty((taps, b, a), dtype=BF16, device=weight.device)
+        self._ver = -1
+
+    def refresh(self, force=False):
+        if force or self.w._version != self._ver:
+            _lib.call("unetk_pack_weight", self.w.data_ptr(), self.ab.data_ptr(), self.ba.data_ptr(), self.a, self.b,
+                      self.taps, _s())
+            self._ver = self.w._version
+
+
+class ConvBNReLU:
+    """conv -> [BatchNorm -> ReLU?] [+ residual] [+ fused 2x2 max-pool]: the unit every U-Net variant is made of.
+
+    conv: 3x3 pad 1 (stride 1 or 2) or 1x1, on the tcgen05 tap-GEMM — or the direct stem kernel when the input is
+    the image (a 1x1 stem conv runs as the 3x3 stem kernel with the weight embedded in the centre tap).
+    bn=None: the conv output (with bias) IS `out`.  BatchNorm uses batch statistics in training plans and the
+    running statistics in eval plans.  res: out = act(bn(conv(x))) + res.
+    Reference: DoubleConv unet_parts.py:24-29 (+ :43 pool), conv_block :85-90, up_conv :104-106,
+    Recurrent_block :119-128, RRCNN_block :143-146, ResidualConv :458-475, NestedUNet DoubleConv UNetPP.py:18-25."""
+
+    def __init__(self, plan: Plan, x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d | None, out: Act,
+                 pooled: Act | None = None, relu: bool = True, res: Act | None = None):
+        k, stride = conv.kernel_size[0], conv.stride[0]
+        assert conv.kernel_size in ((3, 3), (1, 1)) and conv.padding == (k // 2, k // 2) and conv.stride == (stride, stride)
+        assert stride == 1 or (stride == 2 and k == 3)
+        assert conv.dilation == (1, 1) and conv.groups == 1
+        self.plan, self.x, self.conv, self.bn, self.out, self.pooled, self.relu, self.res = plan, x, conv, bn, out, pooled, relu, res
+        self.k, self.stride = k, stride
         self.stem = isinstance(x, Image)
+        assert not (self.stem and stride != 1)
+        if bn is None:
+            assert pooled is None and res is None and not relu, "a conv without BatchNorm writes its output as is"
         self.cin, self.cout = conv.in_channels, conv.out_channels
-        self.raw = plan.act(out.H, out.W, self.cout)
-        self.stat = plan.vec(self.cout, 4)  # scale, shift, mean, invstd
-        self.wpack = self.wpack_t = None
-        self._wver = -1
         N, H, W = out.N, out.H, out.W
+        if not self.stem:
+            assert (x.H, x.W) == (stride * H, stride * W) and x.C == self.cin, "conv input does not match its output"
+            if self.cin % 8 or self.cout % 8:
+                raise ValueError(f"conv {self.cin}->{self.cout}: channel counts must be multiples of 8 on the tensor-core path")
+        assert out.C == self.cout
+        self.raw = plan.act(H, W, self.cout) if bn is not None else out
+        self.stat = plan.vec(self.cout, 4) if bn is not None else None  # scale, shift, mean, invstd
+        self.pack = None if self.stem else plan.pack_of(conv.weight, k * k)
+        self.w3 = self.dw3 = None
+        if self.stem and k == 1:
+            self.w3 = torch.zeros((self.cout, self.cin, 3, 3), dtype=torch.float32, device=plan.device)
+            self.dw3 = torch.zeros_like(self.w3) if plan.with_grad else None
+        self._wver = -1
         lib = _lib.load()
         units = N * H * W
         plan.need(max(lib.unetk_chan_partial_floats(units, self.cout), lib.unetk_conv_stats_partial_floats(self.cout)),
@@ -146,53 +230,67 @@ class ConvBNReLU:
             if self.stem:
                 plan.need(0, lib.unetk_stem_wgrad_workspace(N, H, W, self.cin))
             else:
-                plan.need(0, lib.unetk_conv_wgrad_workspace(N, H, W, self.cin, self.cout, 9))
-        for p in (conv.weight, conv.bias, bn.weight, bn.bias):
+                plan.need(0, lib.unetk_conv_wgrad_workspace(N, H, W, self.cin, self.cout, k * k))
+        for p in (conv.weight, conv.bias) + ((bn.weight, bn.bias) if bn is not None else ()):
             if p is not None:
                 plan.register_param(p)
+        self.acc_w = self.acc_b = self.acc_bn = self.acc_x = self.acc_res = False
         plan.ops.append(self)
 
     def bind(self, plan):
         g = plan.grad_of
         self.dw = g.get(id(self.conv.weight))
         self.dbias = g.get(id(self.conv.bias)) if self.conv.bias is not None else None
-        self.dgamma = g.get(id(self.bn.weight)) if self.bn.weight is not None else None
-        self.dbeta = g.get(id(self.bn.bias)) if self.bn.bias is not None else None
+        bn = self.bn
+        self.dgamma = g.get(id(bn.weight)) if bn is not None and bn.weight is not None else None
+        self.dbeta = g.get(id(bn.bias)) if bn is not None and bn.bias is not None else None
+
+    def _res_aliases_out(self):
+        r = self.res
+        return r is None or r.g is None or r.g.data_ptr() == self.out.g.data_ptr()
+
+    def plan_bwd(self, plan):
+        if not plan.with_grad:
+            return
+        if self.bn is not None:
+            a, b = plan.param_acc(self.bn.weight), plan.param_acc(self.bn.bias)
+            self.acc_bn = a or b
+            if not self._res_aliases_out():
+                self.acc_res = plan.grad_acc(self.res)
+        self.acc_w = plan.param_acc(self.conv.weight)
+        self.acc_b = plan.param_acc(self.conv.bias)
+        if not self.stem and self.x.g is not None:
+            self.acc_x = plan.grad_acc(self.x)
 
     def refresh(self, force=False):
-        if self.stem:
-            return
-        w = self.conv.weight
-        if force or w._version != self._wver or self.wpack is None:
-            if self.wpack is None:
-                self.wpack = torch.empty((9, self.cout, self.cin), dtype=BF16, device=w.device)
-                self.wpack_t = torch.empty((9, self.cin, self.cout), dtype=BF16, device=w.device)
-            _lib.call("unetk_pack_weight", w.data_ptr(), self.wpack.data_ptr(), self.wpack_t.data_ptr(), self.cout,
-                      self.cin, 9, _s())
-            self._wver = w._version
+        if self.w3 is not None:
+            w = self.conv.weight
+            if force or w._version != self._wver:
+                # 1x1 kernel -> centre tap (index 4 of 9) of the zero-padded 3x3 stem kernel
+                ops.copy_f32_strided(self.w3, 9, w.detach(), 1, self.cout * self.cin, dst_offset=4)
+                self._wver = w._version
 
     def fwd(self):
         P, bn = self.plan, self.bn
-        bias = self.conv.bias
-        batch_stats = P.training or not bn.track_running_stats
-        fused_stats = batch_stats and not self.stem
+        bias = self.conv.bias.detach() if self.conv.bias is not None else None
+        batch_stats = bn is not None and (P.training or not bn.track_running_stats)
         if self.stem:
-            ops.stem_fwd(P.image.x, self.conv.weight, bias.detach() if bias is not None else None, self.raw.t)
-        elif fused_stats:
+            ops.stem_fwd(P.image.x, self.w3 if self.w3 is not None else self.conv.weight, bias, self.raw.t)
+            if batch_stats:
+                ops.bn_stats(self.raw.t, P.partial, P.sums)
+        elif batch_stats:
             # conv epilogue also produces the per-channel (sum, sum of squares) of its bf16 output
-            xp, xld = ops.nhwc(self.x.t)
-            yp, yld = ops.nhwc(self.raw.t)
-            _lib.call("unetk_conv3x3_fwd_bnstats", xp, xld, self.wpack.data_ptr(),
-                      bias.detach().data_ptr() if bias is not None else None, yp, yld, P.partial.data_ptr(),
-                      P.sums.data_ptr(), self.raw.N, self.raw.H, self.raw.W, self.cin, self.cout, _s())
+            ops.conv_fwd_stats(self.x.t, self.pack.ab, bias, self.raw.t, P.partial, P.sums, self.k, self.stride)
+        elif self.stride == 2:
+            ops.conv_fwd_stats(self.x.t, self.pack.ab, bias, self.raw.t, None, None, self.k, 2)
         else:
-            ops.conv_fwd(self.x.t, self.wpack, bias.detach() if bias is not None else None, self.raw.t, 3)
+            ops.conv_fwd(self.x.t, self.pack.ab, bias, self.raw.t, self.k)
+        if bn is None:
+            return
         sc, sh, mu, iv = self.stat[0], self.stat[1], self.stat[2], self.stat[3]
         gamma = bn.weight.detach() if bn.weight is not None else None
         beta = bn.bias.detach() if bn.bias is not None else None
         if batch_stats:
-            if not fused_stats:
-                ops.bn_stats(self.raw.t, P.partial, P.sums)
             count = self.raw.N * self.raw.H * self.raw.W
             if P.sync_sums is not None:
                 count = P.sync_sums(P.sums[: 2 * self.cout], count)
@@ -202,47 +300,52 @@ class ConvBNReLU:
                             bn.num_batches_tracked if track else None, sc, sh, mu, iv)
         else:
             ops.bn_eval_fold(gamma, beta, bn.eps, bn.running_mean, bn.running_var, sc, sh, mu, iv)
-        ops.bn_apply(self.raw.t, sc, sh, self.out.t, self.pooled.t if self.pooled is not None else None, self.relu)
+        ops.bn_apply(self.raw.t, sc, sh, self.out.t, self.pooled.t if self.pooled is not None else None, self.relu,
+                     self.res.t if self.res is not None else None)
 
     def bwd(self):
         P = self.plan
-        sc, sh, mu, iv = self.stat[0], self.stat[1], self.stat[2], self.stat[3]
-        g1 = self.out.g
-        gp = self.pooled.g if self.pooled is not None else None
-        ops.bn_bwd_reduce(self.raw.t, g1, gp, sc, sh, mu, iv, P.partial, P.sums, self.relu)
-        count = self.raw.N * self.raw.H * self.raw.W
-        if P.sync_sums is not None:
-            count = P.sync_sums(P.sums[: 2 * self.cout], count)
-        ops.bn_bwd_apply(self.raw.t, g1, gp, sc, sh, mu, iv, P.sums, count, self.dgamma, self.dbeta, P.coef,
-                         self.raw.g, self.relu)
+        if self.bn is not None:
+            sc, sh, mu, iv = self.stat[0], self.stat[1], self.stat[2], self.stat[3]
+            g1 = self.out.g
+            gp = self.pooled.g if self.pooled is not None else None
+            ops.bn_bwd_reduce(self.raw.t, g1, gp, sc, sh, mu, iv, P.partial, P.sums, self.relu)
+            count = self.raw.N * self.raw.H * self.raw.W
+            if P.sync_sums is not None:
+                count = P.sync_sums(P.sums[: 2 * self.cout], count)
+            ops.bn_bwd_apply(self.raw.t, g1, gp, sc, sh, mu, iv, P.sums, count, self.dgamma, self.dbeta, P.coef,
+                             self.raw.g, self.relu, accumulate=self.acc_bn)
+            if not self._res_aliases_out():
+                ops.add_n(self.res.g, [g1], accumulate=self.acc_res)
+        dy = self.raw.g
         if self.stem:
             n, cin, h, w = P.image.x.shape
             xp, sn, sc_, sh_, sw = ops._img(P.image.x)
-            dyp, dyld = ops.nhwc(self.raw.g)
-            _lib.call("unetk_stem_conv3x3_wgrad", xp, sn, sc_, sh_, sw, dyp, dyld, self.dw.data_ptr(), 0, n, h, w,
-                      cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
+            dyp, dyld = ops.nhwc(dy)
+            three = self.w3 is None
+            dw = self.dw if three else self.dw3
+            _lib.call("unetk_stem_conv3x3_wgrad", xp, sn, sc_, sh_, sw, dyp, dyld, dw.data_ptr(),
+                      int(self.acc_w and three), n, h, w, cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
+            if not three:
+                ops.copy_f32_strided(self.dw, 1, self.dw3, 9, self.cout * self.cin, accumulate=self.acc_w, src_offset=4)
         else:
-            xp, xld = ops.nhwc(self.x.t)
-            dyp, dyld = ops.nhwc(self.raw.g)
-            _lib.call("unetk_conv3x3_wgrad", xp, xld, dyp, dyld, self.dw.data_ptr(), 0, self.raw.N, self.raw.H,
-                      self.raw.W, self.cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
+            ops.conv_wgrad(self.x.t, dy, self.dw, self.k, self.acc_w, self.stride, ws=P.ws)
         if self.dbias is not None:
-            ops.colsum(self.raw.g, P.partial, self.dbias)
+            ops.colsum(dy, P.partial, self.dbias, self.acc_b)
         if not self.stem and self.x.g is not None:
-            ops.conv_dgrad(self.raw.g, self.wpack_t, self.x.g, 3)
+            ops.conv_dgrad(dy, self.pack.ba, self.x.g, self.k, self.acc_x, self.stride)
 
 
 class ConvT2x2:
-    """ConvTranspose2d(k=2, s=2) writing straight into the upper channel half of the concat buffer.
-    Reference: Up.up, unet_parts.py:56-58,62."""
+    """ConvTranspose2d(k=2, s=2) writing straight into a channel slice of the concat buffer.
+    Reference: Up.up, unet_parts.py:56-58,62; Upsample :478-487."""
 
     def __init__(self, plan: Plan, x: Act, mod: torch.nn.ConvTranspose2d, out: Act):
         assert mod.kernel_size == (2, 2) and mod.stride == (2, 2) and mod.padding == (0, 0)
         self.plan, self.x, self.mod, self.out = plan, x, mod, out
         self.cin, self.cout = mod.in_channels, mod.out_channels
         assert out.H == 2 * x.H and out.W == 2 * x.W and out.C == self.cout
-        self.w_fwd = self.w_dgrad = None
-        self._wver = -1
+        self.pack = plan.pack_of(mod.weight, 4)   # ab = [4][Cin][Cout] (dgrad), ba = [4][Cout][Cin] (fwd)
         lib = _lib.load()
         if plan.with_grad:
             plan.need(lib.unetk_chan_partial_floats(out.N * out.H * out.W, self.cout),
@@ -250,37 +353,39 @@ class ConvT2x2:
         plan.register_param(mod.weight)
         if mod.bias is not None:
             plan.register_param(mod.bias)
+        self.acc_w = self.acc_b = self.acc_x = False
         plan.ops.append(self)
 
     def bind(self, plan):
         self.dw = plan.grad_of.get(id(self.mod.weight))
         self.db = plan.grad_of.get(id(self.mod.bias)) if self.mod.bias is not None else None
 
+    def plan_bwd(self, plan):
+        if not plan.with_grad:
+            return
+        self.acc_w = plan.param_acc(self.mod.weight)
+        self.acc_b = plan.param_acc(self.mod.bias)
+        if self.x.g is not None:
+            self.acc_x = plan.grad_acc(self.x)
+
     def refresh(self, force=False):
-        w = self.mod.weight
-        if force or w._version != self._wver or self.w_fwd is None:
-            if self.w_fwd is None:
-                self.w_dgrad = torch.empty((4, self.cin, self.cout), dtype=BF16, device=w.device)
-                self.w_fwd = torch.empty((4, self.cout, self.cin), dtype=BF16, device=w.device)
-            _lib.call("unetk_pack_weight", w.data_ptr(), self.w_dgrad.data_ptr(), self.w_fwd.data_ptr(), self.cin,
-                      self.cout, 4, _s())
-            self._wver = w._version
+        pass
 
     def fwd(self):
         b = self.mod.bias
-        ops.convT_fwd(self.x.t, self.w_fwd, b.detach() if b is not None else None, self.out.t)
+        ops.convT_fwd(self.x.t, self.pack.ba, b.detach() if b is not None else None, self.out.t)
 
     def bwd(self):
         P = self.plan
         dy = self.out.g
         xp, xld = ops.nhwc(self.x.t)
         dyp, dyld = ops.nhwc(dy)
-        _lib.call("unetk_convT2x2_wgrad", xp, xld, dyp, dyld, self.dw.data_ptr(), 0, self.x.N, self.x.H, self.x.W,
-                  self.cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
+        _lib.call("unetk_convT2x2_wgrad", xp, xld, dyp, dyld, self.dw.data_ptr(), int(self.acc_w), self.x.N, self.x.H,
+                  self.x.W, self.cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
         if self.db is not None:
-            ops.colsum(dy, P.partial, self.db)
+            ops.colsum(dy, P.partial, self.db, self.acc_b)
         if self.x.g is not None:
-            ops.convT_dgrad(dy, self.w_dgrad, self.x.g)
+            ops.convT_dgrad(dy, self.pack.ab, self.x.g, self.acc_x)
 
 
 class MaxPool2x2:
@@ -289,10 +394,14 @@ class MaxPool2x2:
     def __init__(self, plan: Plan, x: Act, out: Act):
         assert out.H == x.H // 2 and out.W == x.W // 2 and out.C == x.C
         self.plan, self.x, self.out = plan, x, out
+        self.acc_x = False
         plan.ops.append(self)
 
     def bind(self, plan):
         pass
+
+    def plan_bwd(self, plan):
+        self.acc_x = plan.with_grad and self.x.g is not None and plan.grad_acc(self.x)
 
     def refresh(self, force=False):
         pass
@@ -302,18 +411,20 @@ class MaxPool2x2:
 
     def bwd(self):
         if self.x.g is not None:
-            ops.maxpool_bwd(self.x.t, self.out.g, self.x.g)
+            ops.maxpool_bwd(self.x.t, self.out.g, self.x.g, self.acc_x)
 
 
 class Head:
     """OutConv (1x1, C -> 1) fused with sigmoid + BCE-with-logits + dice sums when labels are attached.
     Reference: unet_parts.py:73-79; train.py:264-278; utils/dice_score.py:13-59."""
 
-    def __init__(self, plan: Plan, x: Act, conv: torch.nn.Conv2d):
+    def __init__(self, plan: Plan, x: Act, conv: torch.nn.Conv2d, post_sigmoid: bool = False):
+        """post_sigmoid: the model ends in nn.Sigmoid (ResUNet.py:47-50, UNetPP.py:105-106); `logits` then holds
+        sigmoid(conv) — the model output — which train.py:264-278 feeds to the loss as if it were a logit."""
         assert conv.kernel_size == (1, 1)
         if conv.out_channels != 1:
             raise NotImplementedError("the fused head supports n_classes == 1 (every BASELINE.json config)")
-        self.plan, self.x, self.conv = plan, x, conv
+        self.plan, self.x, self.conv, self.post_sigmoid = plan, x, conv, post_sigmoid
         self.C = conv.in_channels
         self.npix = x.N * x.H * x.W
         dev = plan.device
@@ -325,6 +436,7 @@ class Head:
         self.sync_loss = None                       # optional hook(sums, npix) -> global pixel count (data parallel)
         self.auto_finalize = True                   # trainer.py finalizes itself (collective between graph segments)
         self.gscale = 1.0
+        self.acc_w = False
         plan.need(_lib.load().unetk_head_partial_floats(self.npix, self.C), 0, self.C)
         plan.register_param(conv.weight)
         if conv.bias is not None:
@@ -335,6 +447,12 @@ class Head:
         self.dw = plan.grad_of.get(id(self.conv.weight))
         self.db = plan.grad_of.get(id(self.conv.bias)) if self.conv.bias is not None else None
 
+    def plan_bwd(self, plan):
+        if plan.with_grad:
+            self.acc_w = plan.param_acc(self.conv.weight) | plan.param_acc(self.conv.bias)
+            if self.x.g is not None and plan.grad_acc(self.x):
+                raise RuntimeError("Head: the input of the output conv must not have other consumers")
+
     def refresh(self, force=False):
         pass
 
@@ -342,7 +460,8 @@ class Head:
         P = self.plan
         w = self.conv.weight.detach().view(-1)
         b = self.conv.bias.detach() if self.conv.bias is not None else None
-        ops.head_fwd(self.x.t, w, b, self.labels, self.logits, P.partial, self.loss_sums if self.labels is not None else None)
+        ops.head_fwd(self.x.t, w, b, self.labels, self.logits, P.partial,
+                     self.loss_sums if self.labels is not None else None, self.post_sigmoid)
         if self.labels is not None and self.auto_finalize:
             npix = self.npix
             if self.sync_loss is not None:
@@ -357,7 +476,262 @@ class Head:
         P = self.plan
         w = self.conv.weight.detach().view(-1)
         ops.head_bwd(self.x.t, w, self.labels, self.logits, self.fin, self.dlogits, self.gscale, self.x.g,
-                     self.dw.view(-1) if self.dw is not None else None, self.db, P.partial)
+                     self.dw.view(-1) if self.dw is not None else None, self.db, P.partial, self.acc_w,
+                     self.post_sigmoid)
+
+
+class _Op:
+    """Default no-op hooks of a plan op."""
+
+    def bind(self, plan):
+        pass
+
+    def plan_bwd(self, plan):
+        pass
+
+    def refresh(self, force=False):
+        pass
+
+
+class AddN(_Op):
+    """out = sum(inputs) as a chain of bf16 adds (x + x1 of RRCNN_block / ResUNet input, unet_parts.py:146,
+    ResUNet.py:54); with ONE input it is the slice copy behind a torch.cat of NestedUNet (UNetPP.py:75-99).
+    Backward: every input's gradient (+)= out.g; an input whose .g aliases out.g needs no kernel."""
+
+    def __init__(self, plan: Plan, inputs: list, out: Act):
+        assert 1 <= len(inputs) <= 4 and all((a.N, a.H, a.W, a.C) == (out.N, out.H, out.W, out.C) for a in inputs)
+        self.plan, self.inputs, self.out = plan, inputs, out
+        self.acc = [False] * len(inputs)
+        plan.ops.append(self)
+
+    def _alias(self, a):
+        return a.g is None or a.g.data_ptr() == self.out.g.data_ptr()
+
+    def plan_bwd(self, plan):
+        if plan.with_grad:
+            self.acc = [False if self._alias(a) else plan.grad_acc(a) for a in self.inputs]
+
+    def fwd(self):
+        ops.add_n(self.out.t, [a.t for a in self.inputs])
+
+    def bwd(self):
+        for a, acc in zip(self.inputs, self.acc):
+            if not self._alias(a):
+                ops.add_n(a.g, [self.out.g], accumulate=acc)
+
+
+class Upsample2x(_Op):
+    """nn.Upsample(scale_factor=2): mode "nearest" (up_conv, unet_parts.py:103) or "bilinear" with
+    align_corners=True (NestedUNet.up, UNetPP.py:44), written straight into a concat slice."""
+
+    def __init__(self, plan: Plan, x: Act, out: Act, mode: str = "nearest"):
+        assert mode in ("nearest", "bilinear")
+        assert (out.H, out.W, out.C) == (2 * x.H, 2 * x.W, x.C)
+        self.plan, self.x, self.out, self.mode = plan, x, out, mode
+        self.acc_x = False
+        plan.ops.append(self)
+
+    def plan_bwd(self, plan):
+        self.acc_x = plan.with_grad and self.x.g is not None and plan.grad_acc(self.x)
+
+    def fwd(self):
+        ops.upsample2x(self.x.t, self.out.t, self.mode)
+
+    def bwd(self):
+        if self.x.g is not None:
+            ops.upsample2x_bwd(self.out.g, self.x.g, self.mode, self.acc_x)
+
+
+class BNAct(_Op):
+    """Stand-alone BatchNorm2d (+ReLU) on an existing activation: the pre-activation of ResidualConv
+    (unet_parts.py:458-459).  Statistics pass + apply in forward; reduce + apply in backward, accumulating
+    into x.g when x has other consumers (ResidualConv.conv_skip reads the same x, :467-470)."""
+
+    def __init__(self, plan: Plan, x: Act, bn: torch.nn.BatchNorm2d, out: Act, relu: bool = True):
+        assert (x.N, x.H, x.W, x.C) == (out.N, out.H, out.W, out.C) and bn.num_features == x.C
+        self.plan, self.x, self.bn, self.out, self.relu = plan, x, bn, out, relu
+        self.stat = plan.vec(x.C, 4)
+        plan.need(_lib.load().unetk_chan_partial_floats(x.N * x.H * x.W, x.C), 0, x.C)
+        for p in (bn.weight, bn.bias):
+            if p is not None:
+                plan.register_param(p)
+        self.acc_bn = self.acc_x = False
+        plan.ops.append(self)
+
+    def bind(self, plan):
+        bn = self.bn
+        self.dgamma = plan.grad_of.get(id(bn.weight)) if bn.weight is not None else None
+        self.dbeta = plan.grad_of.get(id(bn.bias)) if bn.bias is not None else None
+
+    def plan_bwd(self, plan):
+        if plan.with_grad:
+            a, b = plan.param_acc(self.bn.weight), plan.param_acc(self.bn.bias)
+            self.acc_bn = a or b
+            if self.x.g is not None:
+                self.acc_x = plan.grad_acc(self.x)
+
+    def fwd(self):
+        P, bn = self.plan, self.bn
+        sc, sh, mu, iv = self.stat[0], self.stat[1], self.stat[2], self.stat[3]
+        gamma = bn.weight.detach() if bn.weight is not None else None
+        beta = bn.bias.detach() if bn.bias is not None else None
+        if P.training or not bn.track_running_stats:
+            ops.bn_stats(self.x.t, P.partial, P.sums)
+            count = self.x.N * self.x.H * self.x.W
+            if P.sync_sums is not None:
+                count = P.sync_sums(P.sums[: 2 * self.x.C], count)
+            track = bn.track_running_stats and P.training
+            ops.bn_finalize(P.sums, count, gamma, beta, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                            bn.running_mean if track else None, bn.running_var if track else None,
+                            bn.num_batches_tracked if track else None, sc, sh, mu, iv)
+        else:
+            ops.bn_eval_fold(gamma, beta, bn.eps, bn.running_mean, bn.running_var, sc, sh, mu, iv)
+        ops.bn_apply(self.x.t, sc, sh, self.out.t, None, self.relu)
+
+    def bwd(self):
+        if self.x.g is None:
+            raise RuntimeError("BNAct: the input carries no gradient buffer")
+        P = self.plan
+        sc, sh, mu, iv = self.stat[0], self.stat[1], self.stat[2], self.stat[3]
+        ops.bn_bwd_reduce(self.x.t, self.out.g, None, sc, sh, mu, iv, P.partial, P.sums, self.relu)
+        count = self.x.N * self.x.H * self.x.W
+        if P.sync_sums is not None:
+            count = P.sync_sums(P.sums[: 2 * self.x.C], count)
+        ops.bn_bwd_apply(self.x.t, self.out.g, None, sc, sh, mu, iv, P.sums, count, self.dgamma, self.dbeta, P.coef,
+                         self.x.g, self.relu, accumulate=self.acc_bn, draw_accumulate=self.acc_x)
+
+
+class AttentionGate(_Op):
+    """Attention_block.forward (unet_parts.py:170-176): out = x * sigmoid(BN1(psi(relu(BN(W_g g) + BN(W_x x))))).
+    Two 1x1 tensor-core GEMMs with the BatchNorm statistics in their epilogue, then the fused gate kernels of
+    csrc/gate.cu; `out` is the skip half of the decoder's concat buffer (AttentionUNet.py:65-66)."""
+
+    def __init__(self, plan: Plan, g: Act, x: Act, mod, out: Act):
+        self.plan, self.g, self.x, self.mod, self.out = plan, g, x, mod, out
+        self.cg, self.bng = mod.W_g[0], mod.W_g[1]
+        self.cx, self.bnx = mod.W_x[0], mod.W_x[1]
+        self.cp, self.bn1 = mod.psi[0], mod.psi[1]
+        self.F = self.cg.out_channels
+        assert (g.N, g.H, g.W) == (x.N, x.H, x.W) == (out.N, out.H, out.W) and out.C == x.C
+        assert g.C == self.cg.in_channels and x.C == self.cx.in_channels and self.cp.out_channels == 1
+        N, H, W = x.N, x.H, x.W
+        self.npix = N * H * W
+        dev = plan.device
+        self.rawg, self.rawx = plan.act(H, W, self.F), plan.act(H, W, self.F)
+        self.statg, self.statx, self.stat1 = plan.vec(self.F, 4), plan.vec(self.F, 4), plan.vec(1, 4)
+        self.s = torch.empty(self.npix, dtype=torch.float32, device=dev)
+        self.dz = torch.empty(self.npix, dtype=torch.float32, device=dev) if plan.with_grad else None
+        self.sums2 = torch.zeros(4 * self.F + 4, dtype=torch.float64, device=dev)
+        self.coef1 = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.coefg = torch.zeros(2 * self.F, dtype=torch.float32, device=dev)
+        self.coefx = torch.zeros(2 * self.F, dtype=torch.float32, device=dev)
+        self.packg, self.packx = plan.pack_of(self.cg.weight, 1), plan.pack_of(self.cx.weight, 1)
+        lib = _lib.load()
+        plan.need(max(lib.unetk_gate_partial_floats(self.npix, self.F), lib.unetk_chan_partial_floats(self.npix, self.F),
+                      lib.unetk_conv_stats_partial_floats(self.F)), 0, self.F)
+        if plan.with_grad:
+            plan.need(0, max(lib.unetk_conv_wgrad_workspace(N, H, W, g.C, self.F, 1),
+                             lib.unetk_conv_wgrad_workspace(N, H, W, x.C, self.F, 1)))
+        self.param_list = [self.cg.weight, self.cg.bias, self.bng.weight, self.bng.bias, self.cx.weight, self.cx.bias,
+                           self.bnx.weight, self.bnx.bias, self.cp.weight, self.cp.bias, self.bn1.weight, self.bn1.bias]
+        for p in self.param_list:
+            if p is not None:
+                plan.register_param(p)
+        self.acc_p = False
+        self.acc_x = self.acc_g = self.acc_xw = False
+        plan.ops.append(self)
+
+    def bind(self, plan):
+        self.grads = [plan.grad_of.get(id(p)) if p is not None else None for p in self.param_list]
+
+    def plan_bwd(self, plan):
+        if not plan.with_grad:
+            return
+        hits = [plan.param_acc(p) for p in self.param_list if p is not None]
+        if any(hits) and not all(hits):
+            raise RuntimeError("AttentionGate: parameters partially shared with other ops")
+        self.acc_p = any(hits)
+        # order of the gradient writes in bwd(): x (gate multiply), then W_g dgrad -> g, then W_x dgrad -> x
+        self.acc_x = plan.grad_acc(self.x)
+        self.acc_g = plan.grad_acc(self.g)
+        self.acc_xw = True
+
+    def _bn(self, bn, stat, sums, count):
+        P = self.plan
+        sc, sh, mu, iv = stat[0], stat[1], stat[2], stat[3]
+        gamma = bn.weight.detach() if bn.weight is not None else None
+        beta = bn.bias.detach() if bn.bias is not None else None
+        if P.training or not bn.track_running_stats:
+            if P.sync_sums is not None:
+                count = P.sync_sums(sums, count)
+            track = bn.track_running_stats and P.training
+            ops.bn_finalize(sums, count, gamma, beta, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                            bn.running_mean if track else None, bn.running_var if track else None,
+                            bn.num_batches_tracked if track else None, sc, sh, mu, iv)
+        else:
+            ops.bn_eval_fold(gamma, beta, bn.eps, bn.running_mean, bn.running_var, sc, sh, mu, iv)
+
+    def fwd(self):
+        P, F = self.plan, self.F
+        for conv, bn, pack, src, raw, stat in ((self.cg, self.bng, self.packg, self.g, self.rawg, self.statg),
+                                               (self.cx, self.bnx, self.packx, self.x, self.rawx, self.statx)):
+            bias = conv.bias.detach() if conv.bias is not None else None
+            ops.conv_fwd_stats(src.t, pack.ab, bias, raw.t, P.partial, P.sums, 1, 1)
+            self._bn(bn, stat, P.sums[: 2 * F], self.npix)
+        gp, gld = ops.nhwc(self.rawg.t)
+        xp, xld = ops.nhwc(self.rawx.t)
+        f = ops._f32
+        wpsi = self.cp.weight.detach().view(-1)
+        bpsi = self.cp.bias.detach() if self.cp.bias is not None else None
+        _lib.call("unetk_gate_fwd", gp, gld, xp, xld, f(self.statg[0]), f(self.statg[1]), f(self.statx[0]),
+                  f(self.statx[1]), f(wpsi), f(bpsi), f(self.s), P.partial.data_ptr(), self.sums2.data_ptr(), self.npix,
+                  F, _s())
+        self._bn(self.bn1, self.stat1, self.sums2[:2], self.npix)
+        ip, ild = ops.nhwc(self.x.t)
+        op, old = ops.nhwc(self.out.t)
+        _lib.call("unetk_gate_apply", ip, ild, f(self.s), f(self.stat1[0]), f(self.stat1[1]), op, old, self.npix,
+                  self.x.C, _s())
+
+    def bwd(self):
+        P, F, f = self.plan, self.F, ops._f32
+        (dwg, dbg, dgam_g, dbet_g, dwx, dbx, dgam_x, dbet_x, dwp, dbp, dgam_1, dbet_1) = self.grads
+        acc = self.acc_p
+        st1 = self.stat1
+        dop, dold = ops.nhwc(self.out.g)
+        ip, ild = ops.nhwc(self.x.t)
+        dxp, dxld = ops.nhwc(self.x.g)
+        s1 = self.sums2[:2]
+        _lib.call("unetk_gate_bwd_psi", dop, dold, ip, ild, f(self.s), f(st1[0]), f(st1[1]), f(st1[2]), dxp, dxld,
+                  int(self.acc_x), f(self.dz), P.partial.data_ptr(), s1.data_ptr(), self.npix, self.x.C, _s())
+        count = self.npix
+        if P.sync_sums is not None:
+            count = P.sync_sums(s1, count)
+        ops.bn_bwd_coef(s1, count, st1[0], st1[2], st1[3], dgam_1, dbet_1, self.coef1, acc)
+        gp, gld = ops.nhwc(self.rawg.t)
+        xp, xld = ops.nhwc(self.rawx.t)
+        sg, sx = self.statg, self.statx
+        wpsi = self.cp.weight.detach().view(-1)
+        sums_g, sums_x = self.sums2[4:4 + 2 * F], self.sums2[4 + 2 * F:4 + 4 * F]
+        _lib.call("unetk_gate_bwd_reduce", gp, gld, xp, xld, f(sg[0]), f(sg[1]), f(sg[2]), f(sx[0]), f(sx[1]), f(sx[2]),
+                  f(wpsi), f(self.s), f(self.dz), f(st1[0]), f(self.coef1), P.partial.data_ptr(), sums_g.data_ptr(),
+                  sums_x.data_ptr(), f(dwp.view(-1)) if dwp is not None else None, f(dbp), int(acc), self.npix, F, _s())
+        cg_count = cx_count = self.npix
+        if P.sync_sums is not None:
+            cg_count = P.sync_sums(sums_g, self.npix)
+            cx_count = P.sync_sums(sums_x, self.npix)
+        ops.bn_bwd_coef(sums_g, cg_count, sg[0], sg[2], sg[3], dgam_g, dbet_g, self.coefg, acc)
+        ops.bn_bwd_coef(sums_x, cx_count, sx[0], sx[2], sx[3], dgam_x, dbet_x, self.coefx, acc)
+        dgp, dgld = ops.nhwc(self.rawg.g)
+        dxrp, dxrld = ops.nhwc(self.rawx.g)
+        _lib.call("unetk_gate_bwd_apply", gp, gld, xp, xld, f(sg[0]), f(sg[1]), f(sx[0]), f(sx[1]), f(wpsi), f(self.s),
+                  f(self.dz), f(st1[0]), f(self.coef1), f(self.coefg), f(self.coefx), dgp, dgld, dxrp, dxrld, self.npix,
+                  F, _s())
+        for src, raw, pack, dw, db, a_in in ((self.g, self.rawg, self.packg, dwg, dbg, self.acc_g),
+                                             (self.x, self.rawx, self.packx, dwx, dbx, self.acc_xw)):
+            ops.conv_wgrad(src.t, raw.g, dw, 1, acc, 1, ws=P.ws)
+            if db is not None:
+                ops.colsum(raw.g, P.partial, db, acc)
+            ops.conv_dgrad(raw.g, pack.ba, src.g, 1, a_in, 1)
 
 
 def _require(cond, msg):

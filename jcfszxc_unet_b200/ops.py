@@ -70,28 +70,59 @@ def conv_fwd(x, w_pack, bias, y, ksize: int = 3):
     return y
 
 
-def conv_dgrad(dy, w_pack_t, dx, ksize: int = 3):
-    """dx <- conv^T(dy): dy [N,H,W,Cout], w_pack_t bf16 [k*k,Cin,Cout], dx [N,H,W,Cin]."""
+def conv_dgrad(dy, w_pack_t, dx, ksize: int = 3, accumulate: bool = False, stride: int = 1):
+    """dx (+)<- conv^T(dy): dy [N,H,W,Cout], w_pack_t bf16 [k*k,Cin,Cout], dx [N,stride*H,stride*W,Cin]."""
     n, h, w, cout = dy.shape
     cin = dx.shape[3]
     assert w_pack_t.shape == (ksize * ksize, cin, cout)
+    assert dx.shape[1] == stride * h and dx.shape[2] == stride * w
     dyp, dyld = nhwc(dy)
     dxp, dxld = nhwc(dx)
-    name = "unetk_conv3x3_dgrad" if ksize == 3 else "unetk_conv1x1_dgrad"
-    _lib.call(name, dyp, dyld, w_pack_t.data_ptr(), dxp, dxld, n, h, w, cin, cout, _stream())
+    if stride == 2:
+        assert ksize == 3
+        name = "unetk_conv3x3s2_dgrad"
+    else:
+        name = "unetk_conv3x3_dgrad" if ksize == 3 else "unetk_conv1x1_dgrad"
+    _lib.call(name, dyp, dyld, w_pack_t.data_ptr(), dxp, dxld, int(accumulate), n, h, w, cin, cout, _stream())
     return dx
 
 
-def conv_wgrad(x, dy, dw, ksize: int = 3, accumulate: bool = False):
-    """dw (fp32 [Cout,Cin,k,k]) <- sum_pixels dy (x) x."""
-    n, h, w, cin = x.shape
-    cout = dy.shape[3]
+def conv_fwd_stats(x, w_pack, bias, y, partial, sums, ksize: int = 3, stride: int = 1):
+    """y <- conv(x) and sums (fp64 [2,Cout]) <- per-channel (sum, sum sq) of y; stride 2 only for 3x3.
+    partial/sums None (stride 2 only) skips the statistics."""
+    n, h, w, cout = y.shape
+    cin = x.shape[3]
+    assert w_pack.shape == (ksize * ksize, cout, cin)
+    assert x.shape[1] == stride * h and x.shape[2] == stride * w
+    xp, xld = nhwc(x)
+    yp, yld = nhwc(y)
+    pp = partial.data_ptr() if partial is not None else None
+    sp = sums.data_ptr() if sums is not None else None
+    if stride == 2:
+        assert ksize == 3
+        name = "unetk_conv3x3s2_fwd"
+    else:
+        name = "unetk_conv3x3_fwd_bnstats" if ksize == 3 else "unetk_conv1x1_fwd_bnstats"
+    _lib.call(name, xp, xld, w_pack.data_ptr(), _f32(bias), yp, yld, pp, sp, n, h, w, cin, cout, _stream())
+    return y
+
+
+def conv_wgrad(x, dy, dw, ksize: int = 3, accumulate: bool = False, stride: int = 1, ws=None):
+    """dw (fp32 [Cout,Cin,k,k]) (+)<- sum_pixels dy (x) x; the reduction grid is dy's (stride 2: x is 2x larger)."""
+    n, h, w, cout = dy.shape
+    cin = x.shape[3]
     assert dw.shape == (cout, cin, ksize, ksize) and dw.dtype == torch.float32 and dw.is_contiguous()
-    need = _lib.load().unetk_conv_wgrad_workspace(n, h, w, cin, cout, ksize * ksize)
-    ws = workspace(need, x.device)
+    assert x.shape[1] == stride * h and x.shape[2] == stride * w
+    if ws is None:
+        need = _lib.load().unetk_conv_wgrad_workspace(n, h, w, cin, cout, ksize * ksize)
+        ws = workspace(need, x.device)
     xp, xld = nhwc(x)
     dyp, dyld = nhwc(dy)
-    name = "unetk_conv3x3_wgrad" if ksize == 3 else "unetk_conv1x1_wgrad"
+    if stride == 2:
+        assert ksize == 3
+        name = "unetk_conv3x3s2_wgrad"
+    else:
+        name = "unetk_conv3x3_wgrad" if ksize == 3 else "unetk_conv1x1_wgrad"
     _lib.call(name, xp, xld, dyp, dyld, dw.data_ptr(), int(accumulate), n, h, w, cin, cout, ws.data_ptr(),
               ws.numel(), _stream())
     return dw
@@ -108,14 +139,15 @@ def convT_fwd(x, w_pack, bias, y):
     return y
 
 
-def convT_dgrad(dy, w_pack_t, dx):
-    """dx [N,H,W,Cin] <- dy [N,2H,2W,Cout]; w_pack_t bf16 [4,Cin,Cout]."""
+def convT_dgrad(dy, w_pack_t, dx, accumulate: bool = False):
+    """dx [N,H,W,Cin] (+)<- dy [N,2H,2W,Cout]; w_pack_t bf16 [4,Cin,Cout]."""
     n, h, w, cin = dx.shape
     cout = dy.shape[3]
     assert w_pack_t.shape == (4, cin, cout) and dy.shape[1] == 2 * h and dy.shape[2] == 2 * w
     dyp, dyld = nhwc(dy)
     dxp, dxld = nhwc(dx)
-    _lib.call("unetk_convT2x2_dgrad", dyp, dyld, w_pack_t.data_ptr(), dxp, dxld, n, h, w, cin, cout, _stream())
+    _lib.call("unetk_convT2x2_dgrad", dyp, dyld, w_pack_t.data_ptr(), dxp, dxld, int(accumulate), n, h, w, cin, cout,
+              _stream())
     return dx
 
 
@@ -189,12 +221,15 @@ def bn_eval_fold(gamma, beta, eps, rm, rv, scale, shift, mean, invstd):
               _f32(shift), _f32(mean), _f32(invstd), _stream())
 
 
-def bn_apply(raw, scale, shift, out, pooled=None, relu=True):
+def bn_apply(raw, scale, shift, out, pooled=None, relu=True, res=None):
+    """out <- relu?(bn(raw)) [+ res]; pooled (optional) <- 2x2 max-pool of out."""
     n, h, w, c = raw.shape
     rp, rld = nhwc(raw)
     op, old = nhwc(out)
     pp, pld = nhwc(pooled) if pooled is not None else (None, 0)
-    _lib.call("unetk_bn_apply", rp, rld, _f32(scale), _f32(shift), op, old, pp, pld, n, h, w, c, int(relu), _stream())
+    sp, sld = nhwc(res) if res is not None else (None, 0)
+    _lib.call("unetk_bn_apply", rp, rld, _f32(scale), _f32(shift), sp, sld, op, old, pp, pld, n, h, w, c, int(relu),
+              _stream())
 
 
 def bn_bwd_reduce(raw, g1, gp, scale, shift, mean, invstd, partial, sums, relu=True):
@@ -207,15 +242,21 @@ def bn_bwd_reduce(raw, g1, gp, scale, shift, mean, invstd, partial, sums, relu=T
 
 
 def bn_bwd_apply(raw, g1, gp, scale, shift, mean, invstd, sums, count, dgamma, dbeta, coef, draw, relu=True,
-                 accumulate=False):
+                 accumulate=False, draw_accumulate=False):
     n, h, w, c = raw.shape
     rp, rld = nhwc(raw)
     g1p, g1ld = nhwc(g1) if g1 is not None else (None, 0)
     gpp, gpld = nhwc(gp) if gp is not None else (None, 0)
     dp, dld = nhwc(draw)
     _lib.call("unetk_bn_bwd_apply", rp, rld, g1p, g1ld, gpp, gpld, _f32(scale), _f32(shift), _f32(mean), _f32(invstd),
-              sums.data_ptr(), float(count), _f32(dgamma), _f32(dbeta), int(accumulate), _f32(coef), dp, dld, n, h, w,
-              c, int(relu), _stream())
+              sums.data_ptr(), float(count), _f32(dgamma), _f32(dbeta), int(accumulate), _f32(coef), dp, dld,
+              int(draw_accumulate), n, h, w, c, int(relu), _stream())
+
+
+def bn_bwd_coef(sums, count, scale, mean, invstd, dgamma, dbeta, coef, accumulate=False):
+    c = scale.numel()
+    _lib.call("unetk_bn_bwd_coef", sums.data_ptr(), c, float(count), _f32(scale), _f32(mean), _f32(invstd),
+              _f32(dgamma), _f32(dbeta), int(accumulate), _f32(coef), _stream())
 
 
 def maxpool_fwd(x, y, idx=None):
@@ -226,12 +267,12 @@ def maxpool_fwd(x, y, idx=None):
               _stream())
 
 
-def maxpool_bwd(x, dy, dx):
+def maxpool_bwd(x, dy, dx, accumulate=False):
     n, h, w, c = x.shape
     xp, xld = nhwc(x)
     dyp, dyld = nhwc(dy)
     dxp, dxld = nhwc(dx)
-    _lib.call("unetk_maxpool2x2_bwd", xp, xld, dyp, dyld, dxp, dxld, n, h, w, c, _stream())
+    _lib.call("unetk_maxpool2x2_bwd", xp, xld, dyp, dyld, dxp, dxld, int(accumulate), n, h, w, c, _stream())
 
 
 def colsum(x, partial, out, accumulate=False):
@@ -244,10 +285,10 @@ def head_partial_floats(npix: int, c: int) -> int:
     return _lib.load().unetk_head_partial_floats(npix, c)
 
 
-def head_fwd(x, w, bias, labels, logits, partial, sums):
+def head_fwd(x, w, bias, labels, logits, partial, sums, post_sigmoid=False):
     n, h, wd, c = x.shape
     xp, xld = nhwc(x)
-    _lib.call("unetk_head_fwd", xp, xld, _f32(w), _f32(bias), _f32(labels), _f32(logits), n * h * wd, c,
+    _lib.call("unetk_head_fwd", xp, xld, _f32(w), _f32(bias), _f32(labels), _f32(logits), int(post_sigmoid), n * h * wd, c,
               partial.data_ptr(), sums.data_ptr() if sums is not None else None, _stream())
 
 
@@ -255,12 +296,12 @@ def loss_finalize(sums, npix_total, fin):
     _lib.call("unetk_loss_finalize", sums.data_ptr(), float(npix_total), _f32(fin), _stream())
 
 
-def head_bwd(x, w, labels, logits, fin, dlogits, gscale, dx, dw, db, partial, accumulate=False):
+def head_bwd(x, w, labels, logits, fin, dlogits, gscale, dx, dw, db, partial, accumulate=False, post_sigmoid=False):
     n, h, wd, c = x.shape
     xp, xld = nhwc(x)
     dxp, dxld = nhwc(dx)
     _lib.call("unetk_head_bwd", xp, xld, _f32(w), _f32(labels), _f32(logits), _f32(fin), _f32(dlogits), float(gscale),
-              dxp, dxld, _f32(dw), _f32(db), int(accumulate), n * h * wd, c, partial.data_ptr(), _stream())
+              int(post_sigmoid), dxp, dxld, _f32(dw), _f32(db), int(accumulate), n * h * wd, c, partial.data_ptr(), _stream())
 
 
 def grad_clip_coef(g, gscale, max_norm, partial, out):
@@ -271,3 +312,44 @@ def grad_clip_coef(g, gscale, max_norm, partial, out):
 def rmsprop_step(p, g, sq, buf, lr, alpha, eps, wd, momentum, clip):
     _lib.call("unetk_rmsprop_step", _f32(p), _f32(g), _f32(sq), _f32(buf), p.numel(), float(lr), float(alpha),
               float(eps), float(wd), float(momentum), _f32(clip), _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# glue of the U-Net variants: residual adds / slice copies, 2x up-sampling, attention gate
+# ------------------------------------------------------------------------------------------------
+def add_n(dst, srcs, accumulate=False):
+    """dst (+)<- sum(srcs) (1..4 bf16 NHWC views of the same shape; bf16 rounding after every add)."""
+    n, h, w, c = dst.shape
+    assert 1 <= len(srcs) <= 4 and all(t.shape == dst.shape for t in srcs)
+    dp, dld = nhwc(dst)
+    args = []
+    for i in range(4):
+        if i < len(srcs):
+            args += list(nhwc(srcs[i]))
+        else:
+            args += [None, 0]
+    _lib.call("unetk_add_n", dp, dld, int(accumulate), *args, n * h * w, c, _stream())
+
+
+def upsample2x(x, y, mode="nearest"):
+    """y [N,2H,2W,C] <- nn.Upsample(scale_factor=2, mode)(x); bilinear uses align_corners=True."""
+    n, h, w, c = x.shape
+    assert y.shape == (n, 2 * h, 2 * w, c)
+    xp, xld = nhwc(x)
+    yp, yld = nhwc(y)
+    _lib.call(f"unetk_upsample_{mode}2x_fwd", xp, xld, yp, yld, n, h, w, c, _stream())
+
+
+def upsample2x_bwd(dy, dx, mode="nearest", accumulate=False):
+    n, h, w, c = dx.shape
+    assert dy.shape == (n, 2 * h, 2 * w, c)
+    dyp, dyld = nhwc(dy)
+    dxp, dxld = nhwc(dx)
+    _lib.call(f"unetk_upsample_{mode}2x_bwd", dyp, dyld, dxp, dxld, int(accumulate), n, h, w, c, _stream())
+
+
+def copy_f32_strided(dst, dst_stride, src, src_stride, n, accumulate=False, dst_offset=0, src_offset=0):
+    """dst.flat[dst_offset + i*dst_stride] (+)<- src.flat[src_offset + i*src_stride], i < n (fp32)."""
+    assert dst.dtype == torch.float32 and src.dtype == torch.float32 and dst.is_cuda and src.is_cuda
+    _lib.call("unetk_copy_f32_strided", dst.data_ptr() + 4 * dst_offset, dst_stride, src.data_ptr() + 4 * src_offset,
+              src_stride, n, int(accumulate), _stream())

@@ -14,6 +14,10 @@ Checks (all on CPU, fp32, bit-exact unless noted):
   3. DoubleConv / Down / Up / OutConv blocks at small channel counts        == oracle block functions
   4. utils/dice_score.py dice_coeff / dice_loss incl. the empty-mask branch == oracle + numpy restatement
   5. F.max_pool2d(return_indices=True) incl. ties and NaNs                  == oracle numpy restatement
+  6. AttentionUNet / R2UNet / R2AttentionUNet / ResUNet / NestedUNet: train+eval forward, running stats,
+     bf16-autocast forward and one restated train step (loss, clipped grads, RMSprop update)
+                                                                            == oracle.FORWARDS / train_step
+     and their blocks conv_block / up_conv / Recurrent_block / RRCNN_block / Attention_block / ResidualConv
 Golden files hold the reference's OUTPUTS for fixed seeds; weights are regenerated from the seed by
 constructing the model (default torch init), so fixtures stay small.
 """
@@ -236,6 +240,110 @@ def main():
     assert torch.equal(icl, idx)
     np.savez_compressed(os.path.join(GOLDEN, "maxpool_indices.npz"), x=xm.numpy(), values=vals.numpy(), indices=idx.numpy())
     report.append("max_pool2d indices with ties / NaN / inf: bit-exact (NCHW and channels_last)")
+
+    # ---- 6. the variants ---------------------------------------------------------------------------
+    import importlib
+
+    variants = {"AttentionUNet": ("AttentionUNet", "AttentionUNet"), "R2UNet": ("R2UNet", "R2UNet"),
+                "R2AttentionUNet": ("R2AttentionUNet", "R2AttentionUNet"), "ResUNet": ("ResUNet", "ResUNet"),
+                "NestedUNet": ("UNetPP", "NestedUNet")}
+    for name, (modname, clsname) in variants.items():
+        cls = getattr(importlib.import_module(f"UNetFamily.{modname}"), clsname)
+        torch.manual_seed(42)
+        model = cls().train()
+        sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        images, labels = _inputs(21, 2, 32, 32)
+        fwd = O.FORWARDS[name]
+        with torch.no_grad():
+            y_ref = model(images)
+        sd = {k: v.clone() for k, v in sd0.items()}
+        with torch.no_grad():
+            y_or = fwd(images, sd, training=True)
+        assert torch.equal(y_ref, y_or), f"{name}: train-mode forward differs"
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, sd[k]), f"{name}: running stat {k} differs"
+        model.eval()
+        with torch.no_grad():
+            y_ref_eval = model(images)
+            y_or_eval = fwd(images, sd, training=False)
+        assert torch.equal(y_ref_eval, y_or_eval), f"{name}: eval-mode forward differs"
+        torch.manual_seed(42)
+        model_bf = cls().train()
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            y_ref_bf16 = model_bf(images).float()
+            y_or_bf16 = fwd(images, {k: v.clone() for k, v in sd0.items()}, training=True).float()
+        assert torch.equal(y_ref_bf16, y_or_bf16), f"{name}: bf16-autocast forward differs"
+        gold = dict(images=images.numpy(), labels=labels.numpy(), logits_train=y_ref.numpy(),
+                    logits_eval_after_1_train_fwd=y_ref_eval.numpy(), logits_train_bf16_autocast=y_ref_bf16.numpy(),
+                    state_dict_keys=np.array(list(sd0.keys())),
+                    init_abs_sum=np.array([float(v.double().abs().sum()) for v in sd0.values()], dtype=np.float64))
+        # one restated train step, fp32 (train.py:255-301 is model-agnostic)
+        torch.manual_seed(42)
+        model = cls().train()
+        lr = 1e-3
+        opt = torch.optim.RMSprop(model.parameters(), lr=lr, weight_decay=1e-8, momentum=0.999)
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        opt_state = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in O.param_names(sd)}
+        images, labels = _inputs(200, 2, 32, 32)
+        loss_r, logits_r, bce_r, dice_r, grads_r = _ref_train_step(model, opt, images, labels, False)
+        loss_o, logits_o, grads_o = O.train_step(sd, opt_state, images, labels, lr, False, model=name)
+        assert torch.equal(loss_r, loss_o), f"{name}: loss differs {loss_r} vs {loss_o}"
+        assert torch.equal(logits_r, logits_o)
+        for k in grads_r:
+            assert torch.equal(grads_r[k], grads_o[k]), f"{name}: clipped grad {k} differs"
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, sd[k]), f"{name}: post-step tensor {k} differs"
+        gold.update(step_images=images.numpy(), step_labels=labels.numpy(), step_loss=loss_r.numpy(),
+                    step_bce=bce_r.numpy(), step_dice_loss=dice_r.numpy(), step_logits=logits_r.numpy(),
+                    step_param_names=np.array(list(grads_r.keys())),
+                    step_gradnorm=np.array([float(g.norm()) for g in grads_r.values()], dtype=np.float64))
+        np.savez_compressed(os.path.join(GOLDEN, f"{name.lower()}_seed42.npz"), **gold)
+        report.append(f"{name}: forward train/eval, running stats, bf16-autocast forward, fp32 train step: bit-exact")
+
+    # blocks of the variants (small channel counts), forward bit-exact
+    g = torch.Generator().manual_seed(9)
+    vb = {}
+    x16 = torch.randn(2, 16, 12, 20, generator=g)
+    torch.manual_seed(11)
+    m = ref_parts.conv_block(16, 24).train()
+    with torch.no_grad():
+        y = m(x16)
+        assert torch.equal(y, O.conv_block(x16, {k: v.detach().clone() for k, v in m.state_dict().items()}, "", True))
+    vb.update(x16=x16.numpy(), conv_block_y=y.numpy())
+    torch.manual_seed(12)
+    m = ref_parts.up_conv(16, 8).train()
+    with torch.no_grad():
+        y = m(x16)
+        assert torch.equal(y, O.up_conv(x16, {k: v.detach().clone() for k, v in m.state_dict().items()}, "", True))
+    vb.update(up_conv_y=y.numpy())
+    torch.manual_seed(13)
+    m = ref_parts.Recurrent_block(16, t=2).train()
+    with torch.no_grad():
+        y = m(x16)
+        assert torch.equal(y, O.recurrent_block(x16, {k: v.detach().clone() for k, v in m.state_dict().items()}, "", True, 2))
+    vb.update(recurrent_y=y.numpy())
+    torch.manual_seed(14)
+    m = ref_parts.RRCNN_block(16, 24, t=2).train()
+    with torch.no_grad():
+        y = m(x16)
+        assert torch.equal(y, O.rrcnn_block(x16, {k: v.detach().clone() for k, v in m.state_dict().items()}, "", True, 2))
+    vb.update(rrcnn_y=y.numpy())
+    torch.manual_seed(15)
+    m = ref_parts.Attention_block(16, 16, 8).train()
+    gsig = torch.randn(2, 16, 12, 20, generator=g)
+    with torch.no_grad():
+        y = m(gsig, x16)
+        assert torch.equal(y, O.attention_block(gsig, x16, {k: v.detach().clone() for k, v in m.state_dict().items()}, "", True))
+    vb.update(att_g=gsig.numpy(), attention_y=y.numpy())
+    for stride, seed in ((1, 16), (2, 17)):
+        torch.manual_seed(seed)
+        m = ref_parts.ResidualConv(16, 24, stride, 1).train()
+        with torch.no_grad():
+            y = m(x16)
+            assert torch.equal(y, O.residual_conv(x16, {k: v.detach().clone() for k, v in m.state_dict().items()}, "", True, stride))
+        vb[f"residual_conv_s{stride}_y"] = y.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "variant_blocks_seeds11to17.npz"), **vb)
+    report.append("conv_block / up_conv / Recurrent_block / RRCNN_block / Attention_block / ResidualConv(s1,s2): bit-exact")
 
     print("ORACLE PINNED against /root/reference:")
     for r in report:

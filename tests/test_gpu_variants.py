@@ -1,0 +1,441 @@
+"""GPU parity of the U-Net variants (AttentionUNet, R2UNet, R2AttentionUNet, ResUNet, NestedUNet) and of the
+kernels only they use, against the oracle (oracle/unet_oracle.py, pinned bit-exact to the reference) on identical
+seeded inputs and weights, and against the committed golden vectors produced by the reference itself.
+
+Tolerances are BASELINE.json's: bf16 storage / fp32 accumulate -> outputs within 2e-2 relative (or as close to the
+fp32 oracle as the reference's own bf16-autocast path is, see _assert_as_close_as_stock_bf16), Dice within 1e-3.
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+BF = torch.bfloat16
+
+VARIANTS = {
+    "AttentionUNet": ("UNetFamily.AttentionUNet", "AttentionUNet"),
+    "R2UNet": ("UNetFamily.R2UNet", "R2UNet"),
+    "R2AttentionUNet": ("UNetFamily.R2AttentionUNet", "R2AttentionUNet"),
+    "ResUNet": ("UNetFamily.ResUNet", "ResUNet"),
+    "NestedUNet": ("UNetFamily.UNetPP", "NestedUNet"),
+}
+BUILDERS = {"AttentionUNet": "build_attention_unet_plan", "R2UNet": "build_r2unet_plan",
+            "R2AttentionUNet": "build_r2attention_unet_plan", "ResUNet": "build_resunet_plan",
+            "NestedUNet": "build_nested_unet_plan"}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _exact_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _make(name, seed=42):
+    mod, cls = VARIANTS[name]
+    torch.manual_seed(seed)
+    return getattr(importlib.import_module(mod), cls)()
+
+
+def _inputs(seed, n, h, w):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n, 3, h, w, generator=g), (torch.rand(n, 1, h, w, generator=g) < 0.12).float()
+
+
+def _rel(a, b):
+    return (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-12)
+
+
+def _l2rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
+
+
+def _assert_as_close_as_stock_bf16(ours, ref32, ref16, what, floor, slack):
+    """Within `floor` of the fp32 oracle (tensor-level and worst-element relative error), or — where bf16 storage
+    itself cannot do better — within `slack` x the deviation of the reference's own bf16-autocast path."""
+    l2, mx = _l2rel(ours, ref32), _rel(ours, ref32)
+    l2_ref, mx_ref = _l2rel(ref16, ref32), _rel(ref16, ref32)
+    msg = f"{what}: ours l2 {l2:.4g} max {mx:.4g} | reference bf16-autocast l2 {l2_ref:.4g} max {mx_ref:.4g}"
+    print(msg)
+    assert l2 <= max(floor, slack * l2_ref), msg
+    assert mx <= max(floor, slack * mx_ref), msg
+
+
+def _nhwc(t):
+    """NCHW fp32 -> NHWC bf16 contiguous."""
+    return t.permute(0, 2, 3, 1).contiguous().to(BF)
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).float()
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("nsrc,acc", [(1, False), (1, True), (2, False), (3, True), (4, False), (4, True)])
+def test_add_n(nsrc, acc):
+    from jcfszxc_unet_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(nsrc)
+    wide = torch.randn(2, 9, 13, 96, device=DEV, generator=g).to(BF)
+    srcs = [torch.randn(2, 9, 13, 40, device=DEV, generator=g).to(BF) for _ in range(nsrc - 1)] + [wide[..., 16:56]]
+    dst_buf = torch.randn(2, 9, 13, 64, device=DEV, generator=g).to(BF)
+    dst = dst_buf[..., 8:48]
+    ref = dst.clone() if acc else None
+    for s in srcs:
+        ref = s.clone() if ref is None else (ref + s)          # bf16 tensor adds, one rounding each
+    keep = dst_buf.clone()
+    ops.add_n(dst, srcs, accumulate=acc)
+    assert torch.equal(dst, ref)
+    assert torch.equal(dst_buf[..., :8], keep[..., :8]) and torch.equal(dst_buf[..., 48:], keep[..., 48:])
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+@pytest.mark.parametrize("n,h,w,c", [(2, 5, 7, 24), (1, 16, 16, 64), (1, 1, 3, 8)])
+def test_upsample2x(mode, n, h, w, c):
+    from jcfszxc_unet_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(n, c, h, w, device=DEV, generator=g).to(BF).float().requires_grad_(True)
+    kw = dict(mode="nearest") if mode == "nearest" else dict(mode="bilinear", align_corners=True)
+    y_ref = F.interpolate(x, scale_factor=2.0, **kw)
+    gy = torch.randn_like(y_ref).to(BF).float()
+    (y_ref * gy).sum().backward()
+    xin = _nhwc(x.detach())
+    cat = torch.zeros(n, 2 * h, 2 * w, c + 16, device=DEV, dtype=BF)
+    y = cat[..., 8:8 + c]
+    ops.upsample2x(xin, y, mode)
+    if mode == "nearest":
+        assert torch.equal(_nchw(y), y_ref.detach())
+    else:
+        assert (_nchw(y) - y_ref.detach()).abs().max() <= 2 ** -7 * y_ref.detach().abs().max()   # one bf16 rounding
+    assert float(cat[..., :8].abs().max()) == 0 and float(cat[..., 8 + c:].abs().max()) == 0
+    dx = torch.empty_like(xin)
+    ops.upsample2x_bwd(_nhwc(gy), dx, mode)
+    tol = 2 ** -7 * x.grad.abs().max()
+    assert (_nchw(dx) - x.grad).abs().max() <= tol
+    base = torch.randn_like(dx)
+    dx2 = base.clone()
+    ops.upsample2x_bwd(_nhwc(gy), dx2, mode, accumulate=True)
+    assert (dx2.float() - (base.float() + dx.float())).abs().max() <= 2 ** -6 * (base.float().abs().max() + x.grad.abs().max())
+
+
+@pytest.mark.parametrize("n,ho,wo,cin,cout", [(2, 8, 8, 64, 128), (1, 6, 10, 24, 40), (1, 64, 64, 64, 128), (2, 4, 4, 256, 512)])
+def test_conv3x3_stride2(n, ho, wo, cin, cout):
+    """ResidualConv's stride-2 convolutions: forward (+fused BN statistics), dgrad (sub-pixel classes, with and
+    without accumulation) and wgrad against torch's fp32 convolution on the same bf16-rounded operands."""
+    from jcfszxc_unet_b200 import _lib, ops
+
+    g = torch.Generator(device=DEV).manual_seed(cin + cout)
+    x = torch.randn(n, cin, 2 * ho, 2 * wo, device=DEV, generator=g).to(BF).float().requires_grad_(True)
+    w = (torch.randn(cout, cin, 3, 3, device=DEV, generator=g) / (3 * cin ** 0.5)).to(BF).float().requires_grad_(True)
+    b = torch.randn(cout, device=DEV, generator=g)
+    y_ref = F.conv2d(x, w, b, stride=2, padding=1)
+    gy = torch.randn(n, cout, ho, wo, device=DEV, generator=g).to(BF).float()
+    (y_ref * gy).sum().backward()
+    ab, ba = ops.pack_weight(w.detach())
+    xin = _nhwc(x.detach())
+    y = torch.empty(n, ho, wo, cout, device=DEV, dtype=BF)
+    lib = _lib.load()
+    partial = torch.empty(max(lib.unetk_conv_stats_partial_floats(cout), 4096), device=DEV)
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    ops.conv_fwd_stats(xin, ab, b, y, partial, sums, 3, 2)
+    assert _rel(_nchw(y), y_ref.detach()) <= 1e-2
+    yf = y.float().view(-1, cout).double()
+    assert torch.allclose(sums[:cout], yf.sum(0), rtol=1e-6, atol=1e-4)
+    assert torch.allclose(sums[cout:], (yf * yf).sum(0), rtol=1e-6, atol=1e-4)
+    y2 = torch.empty_like(y)
+    ops.conv_fwd_stats(xin, ab, b, y2, None, None, 3, 2)
+    assert torch.equal(y, y2)
+    dy = _nhwc(gy)
+    dx = torch.empty_like(xin)
+    ops.conv_dgrad(dy, ba, dx, 3, False, 2)
+    assert _rel(_nchw(dx), x.grad) <= 1e-2
+    base = torch.randn_like(dx)
+    dx2 = base.clone()
+    ops.conv_dgrad(dy, ba, dx2, 3, True, 2)
+    assert (dx2.float() - (base.float() + dx.float())).abs().max() <= 2 ** -6 * (base.float().abs().max() + dx.float().abs().max())
+    dw = torch.zeros_like(w.detach())
+    ops.conv_wgrad(xin, dy, dw, 3, False, 2)
+    assert _rel(dw, w.grad) <= 1e-2
+    ops.conv_wgrad(xin, dy, dw, 3, True, 2)
+    assert _rel(dw, 2 * w.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("kind,n,h,w,cin,cout", [("3x3", 1, 16, 16, 64, 64), ("3x3", 1, 8, 256, 64, 64), ("3x3", 1, 4, 128, 128, 64),
+                                                ("1x1", 2, 12, 12, 64, 32), ("convT", 1, 8, 8, 128, 64)])
+def test_dgrad_accumulate(kind, n, h, w, cin, cout):
+    """dx += conv^T(dy) through the TMA reduce-add epilogue (tap-GEMM and halo kernels) == separate add in bf16."""
+    from jcfszxc_unet_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(h * w)
+    taps = {"3x3": 9, "1x1": 1, "convT": 4}[kind]
+    if kind == "convT":
+        wt = (torch.randn(cin, cout, 2, 2, device=DEV, generator=g) / cout ** 0.5)
+        ab, _ = ops.pack_weight(wt)          # [4][Cin][Cout]
+        dy = torch.randn(n, 2 * h, 2 * w, cout, device=DEV, generator=g).to(BF)
+        run = lambda dx, acc: ops.convT_dgrad(dy, ab, dx, acc)
+    else:
+        k = 3 if kind == "3x3" else 1
+        wt = (torch.randn(cout, cin, k, k, device=DEV, generator=g) / (k * cout ** 0.5))
+        _, ba = ops.pack_weight(wt)
+        dy = torch.randn(n, h, w, cout, device=DEV, generator=g).to(BF)
+        run = lambda dx, acc: ops.conv_dgrad(dy, ba, dx, k, acc)
+    assert taps
+    dx = torch.empty(n, h, w, cin, device=DEV, dtype=BF)
+    run(dx, False)
+    base = torch.randn(n, h, w, cin, device=DEV, generator=g).to(BF)
+    dx2 = base.clone()
+    run(dx2, True)
+    assert torch.equal(dx2, base + dx)       # bf16 + bf16 with one rounding, exactly like a tensor add
+
+
+def test_bn_apply_residual_and_bwd_accumulate():
+    from jcfszxc_unet_b200 import _lib, ops
+
+    g = torch.Generator(device=DEV).manual_seed(8)
+    n, h, w, c = 2, 9, 11, 48
+    raw = torch.randn(n, h, w, c, device=DEV, generator=g).to(BF)
+    res = torch.randn(n, h, w, c, device=DEV, generator=g).to(BF)
+    sc = torch.rand(c, device=DEV, generator=g) + 0.5
+    sh = torch.randn(c, device=DEV, generator=g)
+    out = torch.empty_like(raw)
+    ops.bn_apply(raw, sc, sh, out, None, True, res)
+    ref = torch.relu((raw.float() * sc + sh).to(BF)) + res
+    assert torch.equal(out, ref)
+    ops.bn_apply(raw, sc, sh, out, None, False, res)
+    assert torch.equal(out, (raw.float() * sc + sh).to(BF) + res)
+    # backward: draw_accumulate adds the BN input-gradient onto an existing gradient
+    lib = _lib.load()
+    npix = n * h * w
+    partial = torch.empty(max(lib.unetk_chan_partial_floats(npix, c), 4096), device=DEV)
+    sums = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
+    stat = torch.zeros(4, c, device=DEV)
+    ops.bn_stats(raw, partial, sums)
+    ops.bn_finalize(sums, npix, sc, sh, 1e-5, 0.1, None, None, None, stat[0], stat[1], stat[2], stat[3])
+    gout = torch.randn(n, h, w, c, device=DEV, generator=g).to(BF)
+    coef = torch.zeros(2 * c, device=DEV)
+    d1 = torch.empty_like(raw)
+    for acc, dst in ((False, d1),):
+        ops.bn_bwd_reduce(raw, gout, None, stat[0], stat[1], stat[2], stat[3], partial, sums, True)
+        ops.bn_bwd_apply(raw, gout, None, stat[0], stat[1], stat[2], stat[3], sums, npix, None, None, coef, dst, True)
+    base = torch.randn(n, h, w, c, device=DEV, generator=g).to(BF)
+    d2 = base.clone()
+    ops.bn_bwd_apply(raw, gout, None, stat[0], stat[1], stat[2], stat[3], sums, npix, None, None, coef, d2, True,
+                     draw_accumulate=True)
+    assert torch.equal(d2, base + d1)
+    # and the gradient itself against autograd through F.batch_norm + relu (fp32 on the same bf16 raw)
+    x = raw.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    y = torch.relu(F.batch_norm(x, None, None, sc, sh, True, 0.1, 1e-5).to(BF).float())
+    y.backward(gout.float().permute(0, 3, 1, 2))
+    assert _rel(_nchw(d1), x.grad) <= 1e-2
+
+
+def test_maxpool_bwd_accumulate():
+    from jcfszxc_unet_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(2)
+    x = torch.randn(2, 8, 12, 24, device=DEV, generator=g).to(BF)
+    dy = torch.randn(2, 4, 6, 24, device=DEV, generator=g).to(BF)
+    dx = torch.empty_like(x)
+    ops.maxpool_bwd(x, dy, dx)
+    base = torch.randn_like(x)
+    dx2 = base.clone()
+    ops.maxpool_bwd(x, dy, dx2, accumulate=True)
+    assert torch.equal(dx2, base + dx)
+
+
+def test_head_post_sigmoid():
+    """Head of ResUNet / NestedUNet: output = sigmoid(conv1x1); the loss treats that output as the logit."""
+    from jcfszxc_unet_b200 import _lib, ops
+    from oracle import unet_oracle as O
+
+    g = torch.Generator(device=DEV).manual_seed(4)
+    n, h, w, c = 2, 16, 24, 32
+    x = torch.randn(n, h, w, c, device=DEV, generator=g).to(BF)
+    wt = (torch.randn(1, c, 1, 1, device=DEV, generator=g) / c ** 0.5).requires_grad_(True)
+    b = torch.randn(1, device=DEV, generator=g).requires_grad_(True)
+    labels = (torch.rand(n, 1, h, w, device=DEV, generator=g) < 0.2).float()
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    out_ref = torch.sigmoid(F.conv2d(xr, wt, b))
+    loss_ref, _, dice_ref = O.segmentation_loss(out_ref, labels)
+    loss_ref.backward()
+    npix = n * h * w
+    partial = torch.empty(max(_lib.load().unetk_head_partial_floats(npix, c), 4096), device=DEV)
+    sums = torch.zeros(4, dtype=torch.float64, device=DEV)
+    out = torch.empty(n, 1, h, w, device=DEV)
+    ops.head_fwd(x, wt.detach().view(-1), b.detach(), labels, out, partial, sums, post_sigmoid=True)
+    assert torch.allclose(out, out_ref.detach(), atol=2e-6)
+    fin = torch.zeros(8, device=DEV)
+    ops.loss_finalize(sums, npix, fin)
+    assert abs(float(fin[0]) - float(loss_ref)) <= 1e-5 and abs((1 - float(fin[2])) - float(dice_ref)) <= 1e-5
+    dx = torch.empty_like(x)
+    dw, db = torch.zeros(c, device=DEV), torch.zeros(1, device=DEV)
+    ops.head_bwd(x, wt.detach().view(-1), labels, out, fin, None, 1.0, dx, dw, db, partial, post_sigmoid=True)
+    assert _rel(_nchw(dx), xr.grad) <= 1e-2
+    assert _rel(dw, wt.grad.view(-1)) <= 1e-3 and _rel(db, b.grad) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ blocks
+def _block_case(name):
+    from oracle import unet_oracle as O
+    from UNetFamily.utils import unet_parts as P
+
+    return {
+        "conv_block": (lambda: P.conv_block(64, 32), [(2, 64, 16, 16)], lambda xs, sd: O.conv_block(xs[0], sd, "", True)),
+        "up_conv": (lambda: P.up_conv(64, 32), [(2, 64, 8, 8)], lambda xs, sd: O.up_conv(xs[0], sd, "", True)),
+        "recurrent": (lambda: P.Recurrent_block(32, t=2), [(2, 32, 16, 16)], lambda xs, sd: O.recurrent_block(xs[0], sd, "", True, 2)),
+        "rrcnn": (lambda: P.RRCNN_block(64, 32, t=2), [(2, 64, 16, 16)], lambda xs, sd: O.rrcnn_block(xs[0], sd, "", True, 2)),
+        "attention": (lambda: P.Attention_block(64, 64, 32), [(2, 64, 16, 16), (2, 64, 16, 16)],
+                      lambda xs, sd: O.attention_block(xs[0], xs[1], sd, "", True)),
+        "attention_wide": (lambda: P.Attention_block(512, 512, 256), [(1, 512, 8, 8), (1, 512, 8, 8)],
+                           lambda xs, sd: O.attention_block(xs[0], xs[1], sd, "", True)),
+        "residual_s1": (lambda: P.ResidualConv(96, 32, 1, 1), [(2, 96, 16, 16)], lambda xs, sd: O.residual_conv(xs[0], sd, "", True, 1)),
+        "residual_s2": (lambda: P.ResidualConv(64, 128, 2, 1), [(2, 64, 16, 16)], lambda xs, sd: O.residual_conv(xs[0], sd, "", True, 2)),
+    }[name]
+
+
+@pytest.mark.parametrize("name", ["conv_block", "up_conv", "recurrent", "rrcnn", "attention", "attention_wide",
+                                  "residual_s1", "residual_s2"])
+def test_variant_block_forward_backward_vs_oracle(name):
+    from oracle import unet_oracle as O
+
+    make, shapes, oracle_fn = _block_case(name)
+    torch.manual_seed(31)
+    mod = make().to(DEV).train()
+    sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    g = torch.Generator(device=DEV).manual_seed(5)
+    xs = [torch.randn(*s, device=DEV, generator=g).to(BF).float().requires_grad_(True) for s in shapes]
+    y = mod(*xs)
+    gy = torch.randn(y.shape, device=DEV, generator=g)
+    (y.float() * gy).sum().backward()
+
+    def oracle(bf16):
+        s = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+        ins = [x.detach().clone().requires_grad_(True) for x in xs]
+        with O.autocast_ctx("cuda", bf16):
+            yo = oracle_fn(ins, s)
+        (yo.float() * gy).sum().backward()
+        return yo.detach().float(), [i.grad for i in ins], {k: v.grad for k, v in s.items() if v.requires_grad}, s
+
+    y32, i32, p32, s32 = oracle(False)
+    y16, i16, p16, _ = oracle(True)
+    _assert_as_close_as_stock_bf16(y.detach(), y32, y16, f"{name} output", floor=2e-2, slack=1.5)
+    for k, (x, a, b) in enumerate(zip(xs, i32, i16)):
+        _assert_as_close_as_stock_bf16(x.grad, a, b, f"{name} d input{k}", floor=5e-2, slack=2.0)
+    for k, p in mod.named_parameters():
+        if p32[k].abs().max() < 1e-3 * max(v.abs().max() for v in p32.values()):
+            continue   # conv biases in front of a train-mode BatchNorm: mathematically zero gradient, pure rounding noise
+        _assert_as_close_as_stock_bf16(p.grad, p32[k], p16[k], f"{name} d {k}", floor=5e-2, slack=2.0)
+    for k, v in mod.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert torch.allclose(v, s32[k], rtol=3e-2, atol=3e-3), k
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(s32[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ models
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_variant_forward_matches_reference_golden(name):
+    g = np.load(os.path.join(GOLDEN, f"{name.lower()}_seed42.npz"))
+    m = _make(name).to(DEV).train()
+    x = torch.from_numpy(g["images"]).to(DEV)
+    with torch.no_grad():
+        y = m(x)
+    ref = torch.from_numpy(g["logits_train"]).to(DEV)
+    ref_bf = torch.from_numpy(g["logits_train_bf16_autocast"]).to(DEV)
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    _assert_as_close_as_stock_bf16(y, ref, ref_bf, f"{name} output", floor=2e-2, slack=1.5)
+    m.eval()
+    with torch.no_grad():
+        ye = m(x)
+    ref_e = torch.from_numpy(g["logits_eval_after_1_train_fwd"]).to(DEV)
+    assert _l2rel(ye, ref_e) <= 3e-2, _l2rel(ye, ref_e)
+
+
+@pytest.mark.parametrize("name,n,h,w", [("AttentionUNet", 2, 64, 64), ("R2UNet", 1, 64, 64), ("R2AttentionUNet", 1, 32, 48),
+                                        ("ResUNet", 2, 64, 48), ("NestedUNet", 2, 64, 64)])
+def test_variant_forward_backward_vs_oracle(name, n, h, w):
+    from oracle import unet_oracle as O
+
+    m = _make(name).to(DEV).train()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    images, labels = _inputs(11, n, h, w)
+    images, labels = images.to(DEV), labels.to(DEV)
+    out = m(images)
+    loss, _, dice_l = O.segmentation_loss(out, labels)
+    loss.backward()
+    names = O.param_names(sd)
+    ours = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    assert set(ours) == set(names)
+
+    def oracle_run(bf16):
+        s = {k: v.clone() for k, v in sd.items()}
+        for k in names:
+            s[k].requires_grad_(True)
+        lg, ls, _, dl = O.forward_loss(s, images, labels, bf16=bf16, training=True, model=name)
+        ls.backward()
+        return lg.detach().float(), ls.detach().float(), dl.detach().float(), {k: s[k].grad.float() for k in names}, s
+
+    lg32, ls32, dl32, g32, s32 = oracle_run(False)
+    lg16, ls16, dl16, g16, _ = oracle_run(True)
+    _assert_as_close_as_stock_bf16(out.detach(), lg32, lg16, f"{name} output", floor=2e-2, slack=1.5)
+    assert abs(float(dice_l) - float(dl32)) <= max(1e-3, 1.5 * abs(float(dl16) - float(dl32)))
+    assert abs(float(loss) - float(ls32)) <= 2e-2 * max(1.0, abs(float(ls32)))
+    gmax = max(float(v.abs().max()) for v in g32.values())
+    bad = []
+    for k in names:
+        if float(g32[k].abs().max()) < 1e-4 * gmax:
+            continue   # biases in front of train-mode BatchNorm: zero gradient up to rounding noise
+        e_ours, e_ref = _l2rel(ours[k], g32[k]), _l2rel(g16[k], g32[k])
+        if e_ours > max(2.5 * e_ref, 5e-2):
+            bad.append(f"{k}: ours {e_ours:.3g} vs bf16-autocast {e_ref:.3g}")
+    assert not bad, "\n".join(bad)
+    for k, v in m.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert torch.allclose(v, s32[k], rtol=3e-2, atol=3e-3), k
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(s32[k]), k
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_variant_trainer_step_vs_oracle(name):
+    """Fused training step (eager and CUDA-graph replays bit-identical) against oracle.train_step (train.py:255-301)."""
+    from jcfszxc_unet_b200 import builders
+    from jcfszxc_unet_b200.trainer import Trainer
+    from oracle import unet_oracle as O
+
+    lr = 1e-3
+    results = {}
+    for graph in (False, True):
+        m = _make(name).to(DEV).train()
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        tr = Trainer(m, lr=lr, use_cuda_graph=graph, builder=getattr(builders, BUILDERS[name]))
+        losses = []
+        for step in range(3):
+            images, labels = _inputs(100 + step, 2, 32, 32)
+            losses.append(float(tr.step(images.to(DEV), labels.to(DEV))))
+        results[graph] = (losses, {k: v.detach().clone() for k, v in m.state_dict().items()})
+    assert results[False][0] == results[True][0]
+    for k in results[False][1]:
+        assert torch.equal(results[False][1][k], results[True][1][k]), k
+    names = O.param_names(sd)
+    opt_state = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in names}
+    for step in range(3):
+        im, lb = _inputs(100 + step, 2, 32, 32)
+        ls, _, _ = O.train_step(sd, opt_state, im.to(DEV), lb.to(DEV), lr, bf16=False, model=name)
+        assert abs(results[True][0][step] - float(ls)) <= 3e-2 * max(1.0, abs(float(ls))), (step, results[True][0], float(ls))
+
+
+def test_variant_unsupported_shapes_fail_loudly():
+    m = _make("NestedUNet").to(DEV)
+    with pytest.raises(ValueError, match="divisible by 16"):
+        m(torch.zeros(1, 3, 40, 40, device=DEV))
+    m = _make("ResUNet").to(DEV)
+    with pytest.raises(ValueError, match="divisible by 8"):
+        m(torch.zeros(1, 3, 20, 20, device=DEV))
