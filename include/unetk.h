@@ -38,6 +38,11 @@ int64_t unetk_launch_count(void);
  * src is [A][B][T] fp32 (Conv2d: A=Cout,B=Cin,T=kh*kw; ConvTranspose2d: A=Cin,B=Cout,T=4).
  * dst_ab is bf16 [T][A][B], dst_ba is bf16 [T][B][A]; either may be NULL. */
 int unetk_pack_weight(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, void* stream);
+/* Every weight of a model in ONE launch.  table = device int64 [n][8], row = {src, dst_ab, dst_ba, A, B, T,
+ * first_tile, 0} where first_tile is the running sum of unetk_pack_tiles(A, B) over the preceding rows and
+ * total_tiles the sum over all rows.  T <= 9. */
+int64_t unetk_pack_tiles(int A, int B);
+int unetk_pack_weights(const int64_t* table, int n, int64_t total_tiles, void* stream);
 
 /* ---- 3x3 convolution, padding 1, stride 1 (nn.Conv2d, unet_parts.py:24,27 / 85,88 / 103 / 119) ----
  * fwd:   y[n,h,w,co] = bias[co] + sum_{r,s,ci} x[n,h+r-1,w+s-1,ci] * w[co,ci,r,s]
@@ -259,6 +264,10 @@ int unetk_gate_bwd_apply(const void* raw_g, int64_t raw_g_ld, const void* raw_x,
 /* ---- test infrastructure: tcgen05 descriptor-semantics probe (not on the product path) ---------- */
 int unetk_probe_umma(const void* a, const void* b, float* d, int mode, int shift, int base_offset,
                      void* stream);
+/* clocks (int64 [grid]) that one thread needs to issue and retire iters*4*(1+two_acc) tcgen05.mma of shape
+ * 128 x N x 16 (N = 64/128/256) from resident shared memory; A starts a_shift_rows*128 B into a swizzle atom. */
+int unetk_probe_mma_rate(int N, int grid, int a_shift_rows, int two_acc, int iters, int b_tiles, int64_t* out,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,8 @@ SIGNATURES = {
     "unetk_last_error": (C.c_char_p, []),
     "unetk_launch_count": (_i64, []),
     "unetk_pack_weight": (_i, [_fp, _vp, _vp, _i, _i, _i, _vp]),
+    "unetk_pack_tiles": (_i64, [_i, _i]),
+    "unetk_pack_weights": (_i, [_vp, _i, _i64, _vp]),
     "unetk_conv3x3_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv_stats_partial_floats": (_sz, [_i]),
     "unetk_conv3x3_fwd_bnstats": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -77,6 +79,7 @@ SIGNATURES = {
     "unetk_gate_bwd_apply": (_i, [_vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp,
                                   _i64, _vp, _i64, _i64, _i, _vp]),
     "unetk_probe_umma": (_i, [_vp, _vp, _fp, _i, _i, _i, _vp]),
+    "unetk_probe_mma_rate": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 

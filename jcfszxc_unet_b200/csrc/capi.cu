@@ -21,6 +21,11 @@ int unetk_pack_weight(const float* src, void* dst_ab, void* dst_ba, int A, int B
   return pack_weight_run(src, dst_ab, dst_ba, A, B, T, S(stream));
 }
 
+int64_t unetk_pack_tiles(int A, int B) { return (A > 0 && B > 0) ? pack_tiles(A, B) : 0; }
+int unetk_pack_weights(const int64_t* table, int n, int64_t total_tiles, void* stream) {
+  return pack_weights_run(reinterpret_cast<const long long*>(table), n, total_tiles, S(stream));
+}
+
 static WgradDesc conv_wgrad_desc(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw,
                                  int accumulate, int N, int H, int W, int Cin, int Cout, int ksize);
 
@@ -414,6 +419,11 @@ int unetk_gate_bwd_apply(const void* raw_g, int64_t raw_g_ld, const void* raw_x,
 
 int unetk_probe_umma(const void* a, const void* b, float* d, int mode, int shift, int base_offset, void* stream) {
   return probe_run(a, b, d, mode, shift, base_offset, S(stream));
+}
+int unetk_probe_mma_rate(int N, int grid, int a_shift_rows, int two_acc, int iters, int b_tiles, int64_t* out,
+                         void* stream) {
+  UNETK_CHECK(out != nullptr, -1, "probe_mma_rate: null output");
+  return probe_mma_rate_run(N, grid, a_shift_rows, two_acc, iters, b_tiles, reinterpret_cast<long long*>(out), S(stream));
 }
 
 }  // extern "C"

@@ -35,7 +35,12 @@ struct HCfg {
   static constexpr uint32_t kBBytes = BN * 128;                // one (tap, chunk) weight tile
   static constexpr int kBStages = (BN == 64) ? 6 : 4;
   static constexpr int kStaging = (BN == 64) ? 2 : 1;          // staging buffers for the epilogue
-  static constexpr uint32_t kTmemCols = 4 * BN;                // 2 tiles x 2 rows x BN
+  // Back-to-back MMAs that accumulate into the SAME TMEM tile retire one per ~141 clocks whatever N is
+  // (profiles/r01_mma_rate_probe.txt): a 128x64 MMA needs 32, so two output rows (two chains) cap the tensor pipe
+  // at 45 %.  With N = 64 there is TMEM to spare: each row gets kSplit accumulators that take alternate taps
+  // (4 independent chains) and the epilogue adds the partial sums.
+  static constexpr int kSplit = (BN == 64) ? 2 : 1;
+  static constexpr uint32_t kTmemCols = 4 * BN * kSplit;       // 2 tiles x 2 rows x kSplit x BN
   static constexpr uint32_t kSmemBytes = 2 * kHaloSlot + kBStages * kBBytes + kStaging * kStagingBytes + 1024 + 256;
 };
 
@@ -140,58 +145,81 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
+    {
+      // ------------------------------------------------------------ MMA issuer (warp-convergent, elected lane issues)
+      const bool issue = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
-      if (p.resident) { mbar_wait(w_full, 0); tc_fence_after(); }
+      if (p.resident) { mbar_wait_p(issue, w_full, 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
-        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1u);
+        mbar_wait_p(issue, &tempty[acc], ((it >> 1) & 1) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 2 * BN;
+        const uint32_t d_tmem = tmem_base + acc * 2 * BN * C::kSplit;   // [split][row][BN]
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&a_full[as], aph);
+          mbar_wait_p(issue, &a_full[as], aph);
           tc_fence_after();
           // Descriptors are built once per chunk and only ADVANCED per MMA (one 64-bit add each): with N = 64 an
           // MMA lasts ~32-48 clocks, so the single issuing thread must spend only a few instructions per MMA.
           const uint64_t a_desc0 = make_smem_desc(smem_u32(sA + as * kHaloSlot), 16, 1024, kLayoutSW128);
           const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 16, 1024, kLayoutSW128);
-          for (int t = 0; t < 9; ++t) {
-            uint64_t db0;
-            if (p.resident) {
-              db0 = desc_advance(b_desc0, static_cast<uint32_t>(kc * 9 + t) * C::kBBytes);
-            } else {
-              mbar_wait(&b_full[bs], bph);
-              tc_fence_after();
-              db0 = desc_advance(b_desc0, static_cast<uint32_t>(bs) * C::kBBytes);
-            }
-            // halo row of output row u and tap t: (u + dh + 1); halo column of output column 0: (dw + 1)
-            const uint64_t da0 = desc_advance(a_desc0, static_cast<uint32_t>(((p.dh[t] + 1) * kHaloW + p.dw[t] + 1) * 128));
-            if ((kc | t) == 0) {
-              umma_bf16(d_tmem, da0, db0, idesc, 0u);
-              umma_bf16(d_tmem + BN, desc_advance(da0, kHaloW * 128), db0, idesc, 0u);
-            } else {
-              umma_bf16_acc(d_tmem, da0, db0, idesc);
-              umma_bf16_acc(d_tmem + BN, desc_advance(da0, kHaloW * 128), db0, idesc);
+          // Taps are issued kSplit at a time, one per accumulator set, with the k-steps of the sets interleaved:
+          // consecutive MMAs then belong to 2*kSplit independent accumulation chains (row x set).
+#pragma unroll
+          for (int t0 = 0; t0 < 9; t0 += C::kSplit) {
+            const int nset = (t0 + C::kSplit <= 9) ? C::kSplit : 9 - t0;   // compile-time after unrolling
+            uint64_t da0[C::kSplit], db0[C::kSplit];
+#pragma unroll
+            for (int s = 0; s < C::kSplit; ++s) {
+              if (s < nset) {
+                const int t = t0 + s;
+                if (p.resident) {
+                  db0[s] = desc_advance(b_desc0, static_cast<uint32_t>(kc * 9 + t) * C::kBBytes);
+                } else {
+                  int st = bs + s;
+                  uint32_t ph = bph;
+                  if (st >= C::kBStages) { st -= C::kBStages; ph ^= 1u; }
+                  mbar_wait_p(issue, &b_full[st], ph);
+                  tc_fence_after();
+                  db0[s] = desc_advance(b_desc0, static_cast<uint32_t>(st) * C::kBBytes);
+                }
+                // halo row of output row u and tap t: (u + dh + 1); halo column of output column 0: (dw + 1)
+                da0[s] = desc_advance(a_desc0, static_cast<uint32_t>(((p.dh[t] + 1) * kHaloW + p.dw[t] + 1) * 128));
+              }
             }
 #pragma unroll
-            for (int k = 1; k < 4; ++k) {
-              const uint64_t db = desc_advance(db0, k * 32);
-              umma_bf16_acc(d_tmem, desc_advance(da0, k * 32), db, idesc);
-              umma_bf16_acc(d_tmem + BN, desc_advance(da0, kHaloW * 128 + k * 32), db, idesc);
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+              for (int s = 0; s < C::kSplit; ++s) {
+                if (s < nset) {
+                  const uint32_t d_set = d_tmem + static_cast<uint32_t>(s) * 2 * BN;
+                  const uint64_t da = desc_advance(da0[s], k * 32), db = desc_advance(db0[s], k * 32);
+                  if (t0 == 0 && k == 0) {   // the first MMA of every accumulator overwrites (first chunk only)
+                    umma_bf16_p(issue, d_set, da, db, idesc, kc != 0 ? 1u : 0u);
+                    umma_bf16_p(issue, d_set + BN, desc_advance(da, kHaloW * 128), db, idesc, kc != 0 ? 1u : 0u);
+                  } else {
+                    umma_bf16_acc_p(issue, d_set, da, db, idesc);
+                    umma_bf16_acc_p(issue, d_set + BN, desc_advance(da, kHaloW * 128), db, idesc);
+                  }
+                }
+              }
             }
             if (!p.resident) {
-              umma_commit(&b_empty[bs]);
-              if (++bs == C::kBStages) { bs = 0; bph ^= 1u; }
+#pragma unroll
+              for (int s = 0; s < C::kSplit; ++s) {
+                if (s < nset) {
+                  umma_commit_p(issue, &b_empty[bs]);
+                  if (++bs == C::kBStages) { bs = 0; bph ^= 1u; }
+                }
+              }
             }
           }
-          umma_commit(&a_empty[as]);  // all nine taps of this chunk have been issued
+          umma_commit_p(issue, &a_empty[as]);  // all nine taps of this chunk have been issued
           if (++as == 2) { as = 0; aph ^= 1u; }
         }
-        umma_commit(&tfull[acc]);
+        umma_commit_p(issue, &tfull[acc]);
       }
     }
   } else if (warp >= 2 && warp <= 5) {
@@ -219,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
 
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 2 * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 2 * BN * C::kSplit;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const bool row_ok = (h0 + u) < p.H;
@@ -238,6 +266,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
             tmem_ld32(taddr + u * BN + c * 64, r0);
             tmem_ld32(taddr + u * BN + c * 64 + 32, r1);
             tmem_ld_wait();
+            if constexpr (C::kSplit == 2) {   // add the second partial sum (odd taps)
+              uint32_t q0[32], q1[32];
+              tmem_ld32(taddr + 2 * BN + u * BN + c * 64, q0);
+              tmem_ld32(taddr + 2 * BN + u * BN + c * 64 + 32, q1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                r0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(q0[j]));
+                r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(q1[j]));
+              }
+            }
           }
           if (last) {
             tc_fence_before();

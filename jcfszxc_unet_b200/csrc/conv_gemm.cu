@@ -132,8 +132,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
+    {
+      // ------------------------------------------------------------ MMA issuer (warp-convergent, elected lane issues)
+      const bool issue = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, false, false);
       const uint64_t a_desc0 = make_smem_desc(smem_u32(smem), 16, 1024, kLayoutSW128);  // stage 0, k = 0
       int stage = 0;
@@ -142,24 +143,24 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        mbar_wait_p(issue, &tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_p(issue, &full_bar[stage], phase);
           tc_fence_after();
           // descriptors are advanced, not rebuilt: the issuing thread spends ~3 instructions per MMA
           const uint64_t da0 = desc_advance(a_desc0, static_cast<uint32_t>(stage) * C::kStageBytes);
           const uint64_t db0 = desc_advance(da0, kABytes);
-          if (kb == 0) umma_bf16(d_tmem, da0, db0, idesc, 0u);
-          else umma_bf16_acc(d_tmem, da0, db0, idesc);
+          if (kb == 0) umma_bf16_p(issue, d_tmem, da0, db0, idesc, 0u);
+          else umma_bf16_acc_p(issue, d_tmem, da0, db0, idesc);
 #pragma unroll
           for (int k = 1; k < kTileK / kUmmaK; ++k)
-            umma_bf16_acc(d_tmem, desc_advance(da0, k * kUmmaK * 2), desc_advance(db0, k * kUmmaK * 2), idesc);
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+            umma_bf16_acc_p(issue, d_tmem, desc_advance(da0, k * kUmmaK * 2), desc_advance(db0, k * kUmmaK * 2), idesc);
+          umma_commit_p(issue, &empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        umma_commit_p(issue, &tfull_bar[acc]);  // accumulator complete -> epilogue
       }
     }
   } else {

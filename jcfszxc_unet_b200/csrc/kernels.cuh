@@ -59,6 +59,11 @@ int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, 
                        cudaStream_t s);
 int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, float lr, float alpha, float eps, float wd,
                 float momentum, const float* clip, cudaStream_t s);
+int probe_mma_rate_run(int N, int grid, int a_shift_rows, int two_acc, int iters, int b_tiles, long long* out,
+                       cudaStream_t stream);
+// pack.cu
+long long pack_tiles(int A, int B);
+int pack_weights_run(const long long* table, int n, long long total_tiles, cudaStream_t stream);
 // resample.cu
 int add_n_run(void* dst, int64_t dst_ld, int accumulate, const void* const* src, const int64_t* src_ld, int nsrc,
               int64_t npix, int C, cudaStream_t s);

@@ -40,30 +40,42 @@ head_loss_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const floa
   for (int j = 0; j < 8; ++j) wv[j] = __ldg(w + sub * 8 + j);
   const float b = bias ? __ldg(bias) : 0.f;
   float s_bce = 0.f, s_py = 0.f, s_p = 0.f, s_y = 0.f;
-  // uniform trip count per warp: all lanes of a pixel group iterate together
-  for (int64_t pix0 = static_cast<int64_t>(blockIdx.x) * gpb; pix0 < npix; pix0 += static_cast<int64_t>(gridDim.x) * gpb) {
-    const int64_t pix = pix0 + grp;
-    float dot = 0.f;
-    if (pix < npix) {
-      float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * ld + sub * 8)), f);
+  // uniform trip count per block (all lanes of a pixel group iterate together); kU pixels per group are loaded
+  // before any is reduced, so every thread keeps kU 16-byte loads in flight (the first version had one: 2 TB/s)
+  constexpr int kU = 4;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * gpb;
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * gpb; base < npix; base += kU * step) {
+    uint4 v[kU];
+    float yv[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t pix = base + u * step + grp;
+      const bool ok = pix < npix;
+      v[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + pix * ld + sub * 8)) : make_uint4(0, 0, 0, 0);
+      yv[u] = (ok && sub == 0 && labels != nullptr) ? __ldg(labels + pix) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t pix = base + u * step + grp;
+      float f[8], dot = 0.f;
+      unpack8(v[u], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) dot = fmaf(f[j], wv[j], dot);
-    }
-    dot = group_sum(dot, lpp);
-    if (sub == 0 && pix < npix) {
-      // post_sigmoid: the model itself ends in nn.Sigmoid (ResUNet.py:47-50, UNetPP.py:105-106) and train.py
-      // still feeds that output to BCEWithLogits / sigmoid+dice, so the loss sees sigmoid(z) as its "logit"
-      const float z = post_sigmoid ? 1.f / (1.f + __expf(-(dot + b))) : dot + b;
-      logits[pix] = z;
-      if (labels != nullptr) {
-        const float y = __ldg(labels + pix);
-        s_bce += fmaxf(z, 0.f) - z * y + log1pf(__expf(-fabsf(z)));
-        float p = 1.f / (1.f + __expf(-z));
-        p = fminf(fmaxf(p, kClampLo), kClampHi);
-        s_py = fmaf(p, y, s_py);
-        s_p += p;
-        s_y += y;
+      dot = group_sum(dot, lpp);
+      if (sub == 0 && pix < npix) {
+        // post_sigmoid: the model itself ends in nn.Sigmoid (ResUNet.py:47-50, UNetPP.py:105-106) and train.py
+        // still feeds that output to BCEWithLogits / sigmoid+dice, so the loss sees sigmoid(z) as its "logit"
+        const float z = post_sigmoid ? 1.f / (1.f + __expf(-(dot + b))) : dot + b;
+        logits[pix] = z;
+        if (labels != nullptr) {
+          const float y = yv[u];
+          s_bce += fmaxf(z, 0.f) - z * y + log1pf(__expf(-fabsf(z)));
+          float p = 1.f / (1.f + __expf(-z));
+          p = fminf(fmaxf(p, kClampLo), kClampHi);
+          s_py = fmaf(p, y, s_py);
+          s_p += p;
+          s_y += y;
+        }
       }
     }
   }
@@ -127,29 +139,48 @@ head_loss_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const floa
   float inv_n = 0.f, cA = 0.f, cB = 0.f;
   if (dlogits == nullptr) { inv_n = __ldg(fin + 3); cA = __ldg(fin + 4); cB = __ldg(fin + 5); }
   float s_dz = 0.f;
-  for (int64_t pix = static_cast<int64_t>(blockIdx.x) * gpb + grp; pix < npix; pix += static_cast<int64_t>(gridDim.x) * gpb) {
-    float dz;
-    if (dlogits != nullptr) {  // gradient handed in by autograd (loss computed outside the library)
-      dz = gscale * __ldg(dlogits + pix);
-    } else {
-      const float z = __ldg(logits + pix), y = __ldg(labels + pix);
-      const float p = 1.f / (1.f + __expf(-z));
-      const float inside = (p >= kClampLo && p <= kClampHi) ? 1.f : 0.f;
-      dz = gscale * (0.5f * inv_n * (p - y) - 0.5f * (y * cA - cB) * p * (1.f - p) * inside);
-    }
-    if (post_sigmoid) {  // chain through the model's own output sigmoid: logits[] holds its value
-      const float o = __ldg(logits + pix);
-      dz *= o * (1.f - o);
-    }
-    float f[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * ld + sub * 8)), f);
+  constexpr int kU = 4;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * gpb;
+  for (int64_t p0 = static_cast<int64_t>(blockIdx.x) * gpb + grp; p0 < npix; p0 += kU * step) {
+    uint4 v[kU];
+    float dzv[kU];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[j] = fmaf(dz, f[j], acc[j]); o[j] = dz * wv[j]; }
-    uint4 u;
-    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
-    u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-    *reinterpret_cast<uint4*>(dx + pix * dx_ld + sub * 8) = u;
-    if (sub == 0) s_dz += dz;
+    for (int u = 0; u < kU; ++u) {
+      const int64_t pix = p0 + u * step;
+      const bool ok = pix < npix;
+      v[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + pix * ld + sub * 8)) : make_uint4(0, 0, 0, 0);
+      float dz = 0.f;
+      if (ok) {
+        if (dlogits != nullptr) {  // gradient handed in by autograd (loss computed outside the library)
+          dz = gscale * __ldg(dlogits + pix);
+        } else {
+          const float z = __ldg(logits + pix), y = __ldg(labels + pix);
+          const float p = 1.f / (1.f + __expf(-z));
+          const float inside = (p >= kClampLo && p <= kClampHi) ? 1.f : 0.f;
+          dz = gscale * (0.5f * inv_n * (p - y) - 0.5f * (y * cA - cB) * p * (1.f - p) * inside);
+        }
+        if (post_sigmoid) {  // chain through the model's own output sigmoid: logits[] holds its value
+          const float o = __ldg(logits + pix);
+          dz *= o * (1.f - o);
+        }
+      }
+      dzv[u] = dz;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t pix = p0 + u * step;
+      if (pix >= npix) break;
+      const float dz = dzv[u];
+      float f[8], o[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[j] = fmaf(dz, f[j], acc[j]); o[j] = dz * wv[j]; }
+      uint4 w4;
+      w4.x = pack_bf16x2(o[0], o[1]); w4.y = pack_bf16x2(o[2], o[3]);
+      w4.z = pack_bf16x2(o[4], o[5]); w4.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dx + pix * dx_ld + sub * 8) = w4;
+      if (sub == 0) s_dz += dz;
+    }
   }
   extern __shared__ float red[];  // [gpb][C + 1]
 #pragma unroll

@@ -1,33 +1,93 @@
 // Weight cache: fp32 PyTorch-layout master weights -> bf16 tap-major packs read by the TMA.
+//   src [A][B][T] fp32  ->  dst_ab [T][A][B] bf16 and/or dst_ba [T][B][A] bf16
+// One CTA transposes a 32 x 32 (a, b) tile for all T taps through shared memory, so global reads are contiguous
+// runs of 32*T floats and global writes are 64-byte runs in BOTH destinations (the first version wrote dst_ba with
+// a stride of A elements per thread: 0.58 ms per U-Net step for 21 weights; profiles/r01_step_profile_v3.txt).
+// The batched entry point packs every weight of a plan in ONE launch from a device-side table.
 #include "host_common.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace unetk {
 
 namespace {
-// src [A][B][T] fp32 -> dst_ab [T][A][B] bf16 and/or dst_ba [T][B][A] bf16
-__global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst_ab,
-                                   __nv_bfloat16* __restrict__ dst_ba, int A, int B, int T) {
-  const int64_t total = static_cast<int64_t>(A) * B * T;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    // iterate in destination-ab order so writes to dst_ab coalesce (weights are tiny either way)
-    const int b = static_cast<int>(i % B);
-    const int a = static_cast<int>((i / B) % A);
-    const int t = static_cast<int>(i / (static_cast<int64_t>(A) * B));
-    const __nv_bfloat16 v = __float2bfloat16_rn(src[(static_cast<int64_t>(a) * B + b) * T + t]);
-    if (dst_ab) dst_ab[i] = v;
-    if (dst_ba) dst_ba[(static_cast<int64_t>(t) * B + b) * A + a] = v;
+constexpr int kTile = 32;
+constexpr int kMaxT = 9;
+
+struct PackJob {   // one row of the device table (8 x int64)
+  const float* src;
+  __nv_bfloat16* dst_ab;
+  __nv_bfloat16* dst_ba;
+  long long A, B, T;
+  long long first_tile;   // index of this weight's first tile in the batched grid
+  long long pad;
+};
+
+__device__ __forceinline__ void pack_tile(const PackJob& j, int tile, float* s /* [32][32*T + 1] */) {
+  const int A = static_cast<int>(j.A), B = static_cast<int>(j.B), T = static_cast<int>(j.T);
+  const int tiles_b = (B + kTile - 1) / kTile;
+  const int a0 = (tile / tiles_b) * kTile, b0 = (tile % tiles_b) * kTile;
+  const int na = min(kTile, A - a0), nb = min(kTile, B - b0);
+  const int row = kTile * T + 1;
+  // load: row a of the tile is the contiguous run src[(a*B + b0)*T ... + nb*T)
+  for (int i = threadIdx.x; i < na * nb * T; i += blockDim.x) {
+    const int a = i / (nb * T), r = i % (nb * T);
+    s[a * row + r] = j.src[(static_cast<long long>(a0 + a) * B + b0) * T + r];
+  }
+  __syncthreads();
+  if (j.dst_ab != nullptr) {
+    for (int i = threadIdx.x; i < T * na * nb; i += blockDim.x) {
+      const int b = i % nb, a = (i / nb) % na, t = i / (nb * na);
+      j.dst_ab[(static_cast<long long>(t) * A + a0 + a) * B + b0 + b] = __float2bfloat16_rn(s[a * row + b * T + t]);
+    }
+  }
+  if (j.dst_ba != nullptr) {
+    for (int i = threadIdx.x; i < T * nb * na; i += blockDim.x) {
+      const int a = i % na, b = (i / na) % nb, t = i / (na * nb);
+      j.dst_ba[(static_cast<long long>(t) * B + b0 + b) * A + a0 + a] = __float2bfloat16_rn(s[a * row + b * T + t]);
+    }
   }
 }
+
+__global__ void __launch_bounds__(256) pack_weight_kernel(const PackJob job) {
+  extern __shared__ float smem_pack[];
+  pack_tile(job, blockIdx.x, smem_pack);
+}
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __restrict__ table, int n) {
+  extern __shared__ float smem_pack[];
+  // binary search: last job whose first_tile <= blockIdx.x
+  int lo = 0, hi = n - 1;
+  const long long tile = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].first_tile <= tile) lo = mid; else hi = mid - 1;
+  }
+  const PackJob j = table[lo];
+  pack_tile(j, static_cast<int>(tile - j.first_tile), smem_pack);
+}
+
+size_t tile_smem(int T) { return static_cast<size_t>(kTile) * (kTile * T + 1) * sizeof(float); }
 }  // namespace
 
+long long pack_tiles(int A, int B) {
+  return static_cast<long long>((A + kTile - 1) / kTile) * ((B + kTile - 1) / kTile);
+}
+
 int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, cudaStream_t stream) {
-  const int64_t total = static_cast<int64_t>(A) * B * T;
-  int blocks = static_cast<int>((total + 255) / 256);
-  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-  pack_weight_kernel<<<blocks, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst_ab),
-                                                 static_cast<__nv_bfloat16*>(dst_ba), A, B, T);
+  UNETK_CHECK(T <= kMaxT, -1, "pack_weight: T=%d > %d taps", T, kMaxT);
+  PackJob j{src, static_cast<__nv_bfloat16*>(dst_ab), static_cast<__nv_bfloat16*>(dst_ba), A, B, T, 0, 0};
+  pack_weight_kernel<<<static_cast<int>(pack_tiles(A, B)), 256, tile_smem(T), stream>>>(j);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+// table: device int64 [n][8] rows {src, dst_ab, dst_ba, A, B, T, first_tile, 0} with first_tile ascending from 0
+int pack_weights_run(const long long* table, int n, long long total_tiles, cudaStream_t stream) {
+  UNETK_CHECK(table != nullptr && n > 0 && total_tiles > 0 && total_tiles < (1ll << 31), -1, "pack_weights: bad arguments");
+  static_assert(sizeof(PackJob) == 64, "PackJob must be 8 x int64");
+  pack_weights_kernel<<<static_cast<int>(total_tiles), 256, tile_smem(kMaxT), stream>>>(
+      reinterpret_cast<const PackJob*>(table), n);
   UNETK_LAUNCHED();
   return 0;
 }

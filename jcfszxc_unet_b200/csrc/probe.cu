@@ -105,6 +105,92 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------
+// MMA issue-rate probe: one thread issues `iters` x 4 tcgen05.mma (K = 64 per group) from operands that already
+// sit in shared memory and reports clocks per MMA.  Answers "what does an M=128 x N MMA really cost when A is
+// (a) a 1024-byte-aligned tile, (b) a row-shifted view of a halo tile, (c) alternating between two accumulators"
+// — the numbers the thin-layer conv kernels are designed against (profiles/r01_mma_rate_probe.txt).
+template <int N>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int a_shift_rows, int two_acc, int iters, int b_tiles,
+                                                         long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  constexpr uint32_t kABytes = 4 * 130 * 128 + 1024;                 // a halo-sized A region
+  constexpr uint32_t kAReg = (kABytes + 1023u) & ~1023u;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kAReg;                                         // b_tiles x (N x 128 B)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + b_tiles * N * 128);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5;
+  // small finite bf16 values everywhere (0x3c00 = 2^-7): content does not matter, NaN/denormal garbage might
+  for (uint32_t i = threadIdx.x; i < (kAReg + static_cast<uint32_t>(b_tiles) * N * 128) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  fence_proxy_async_smem();
+  if (warp == 0) tmem_alloc<512>(slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, N, false, false);
+    const uint64_t a0 = make_smem_desc(smem_u32(sA) + a_shift_rows * 128, 16, 1024, kLayoutSW128);
+    const uint64_t b0 = make_smem_desc(smem_u32(sB), 16, 1024, kLayoutSW128);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint64_t db0 = desc_advance(b0, static_cast<uint32_t>(it % b_tiles) * (N * 128));
+      const uint64_t da0 = desc_advance(a0, static_cast<uint32_t>((it % 3) * 128));   // tap-like column shift
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // two_acc = number of EXTRA independent accumulators the MMAs rotate over (0, 1 or 3)
+        umma_bf16_acc(tmem, desc_advance(da0, k * 32), desc_advance(db0, k * 32), idesc);
+        if (two_acc >= 1) umma_bf16_acc(tmem + N, desc_advance(da0, 130 * 128 + k * 32), desc_advance(db0, k * 32), idesc);
+        if (two_acc >= 3) {
+          umma_bf16_acc(tmem + 2 * N, desc_advance(da0, 2 * 130 * 128 + k * 32), desc_advance(db0, k * 32), idesc);
+          umma_bf16_acc(tmem + 3 * N, desc_advance(da0, 3 * 130 * 128 + k * 32), desc_advance(db0, k * 32), idesc);
+        }
+      }
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+template <int N>
+static int mma_rate_launch(int grid, int shift, int two_acc, int iters, int b_tiles, long long* out, cudaStream_t s) {
+  const int smem = ((4 * 130 * 128 + 1024 + 1023) & ~1023) + b_tiles * N * 128 + 64 + 1024;
+  UNETK_CHECK(smem <= 227 * 1024, -1, "mma_rate: smem %d", smem);
+  UNETK_CUDA(cudaFuncSetAttribute(mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_rate_kernel<N><<<grid, 128, smem, s>>>(shift, two_acc, iters, b_tiles, out);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+// out: int64 [grid] clocks for iters*4*(1+two_acc) MMAs of shape 128 x N x 16
+int probe_mma_rate_run(int N, int grid, int a_shift_rows, int two_acc, int iters, int b_tiles, long long* out,
+                       cudaStream_t stream) {
+  UNETK_CHECK(grid >= 1 && iters >= 1 && b_tiles >= 1 && b_tiles <= 9 && a_shift_rows >= 0 && a_shift_rows < 8, -1,
+              "probe_mma_rate: bad arguments");
+  UNETK_CHECK((two_acc == 0 || two_acc == 1 || two_acc == 3) && (two_acc + 1) * N <= 512, -1,
+              "probe_mma_rate: extra accumulators 0/1/3 within 512 TMEM columns");
+  switch (N) {
+    case 64: return mma_rate_launch<64>(grid, a_shift_rows, two_acc, iters, b_tiles, out, stream);
+    case 128: return mma_rate_launch<128>(grid, a_shift_rows, two_acc, iters, b_tiles, out, stream);
+    case 256: return mma_rate_launch<256>(grid, a_shift_rows, two_acc, iters, b_tiles, out, stream);
+    default: UNETK_CHECK(false, -1, "probe_mma_rate: N must be 64, 128 or 256");
+  }
+  return 0;
+}
+
 // a: bf16 [144][64] (modes 0,1) or [144][128] (mode 2); b: bf16 [64][64]; d: fp32 [128][64]
 int probe_run(const void* a, const void* b, float* d, int mode, int shift, int bo, cudaStream_t stream) {
   ProbeParams p{};

@@ -186,6 +186,19 @@ __device__ __forceinline__ void umma_bf16_acc(uint32_t d_tmem, uint64_t a_desc, 
       "l"(a_desc), "l"(b_desc), "r"(idesc)
       : "memory");
 }
+// Predicated forms for a WARP-CONVERGENT issue loop: all 32 lanes run the loop (same barriers, same descriptor
+// arithmetic) and only the elected lane executes the tcgen05 instruction.  Inside an `if (lane == 0)` region ptxas
+// cannot keep the operands in uniform registers and wraps EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+// waterfall (~8 SASS instructions, 70-140 clocks per MMA on the single issuing thread: a 128x64 MMA needs 32).
+// In convergent code the same loop compiles to one UIADD3.64 per descriptor plus the UTCHMMA.
+__device__ __forceinline__ void umma_bf16_p(bool issue, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  if (issue) umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void umma_bf16_acc_p(bool issue, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc) {
+  if (issue) umma_bf16_acc(d_tmem, a_desc, b_desc, idesc);
+}
 // Advance a shared-memory descriptor by `bytes` (start-address field is in 16-byte units; the field cannot
 // overflow for addresses below 256 KB).
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) {
@@ -197,6 +210,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+// Barrier wait for the convergent issue loop: the issuing lane polls, the warp re-converges behind it (a spin loop
+// run by all lanes may leave the warp diverged, which sends ptxas back to the per-MMA waterfall).
+__device__ __forceinline__ void mbar_wait_p(bool issue, uint64_t* bar, uint32_t parity) {
+  if (issue) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void umma_commit_p(bool issue, uint64_t* bar) {
+  if (issue) umma_commit(bar);
 }
 // 32 lanes x 32 columns of fp32: thread i of the warp receives lane (base_lane+i), columns c..c+31.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {

@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // MMA issuer: warp-convergent loop, the elected lane issues (see umma_bf16_p in ptx.cuh)
+      const bool issue = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, true, true);
       int stage = 0;
       uint32_t phase = 0;
@@ -108,11 +110,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        mbar_wait_p(issue, &tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kt = kt0; kt < kt1; ++kt) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_p(issue, &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t p_base = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t q_base = p_base + 2 * kBoxBytes;
@@ -122,12 +124,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
             // kBoxBytes apart (LBO).
             const uint64_t da = make_smem_desc(p_base + k * 2048, kBoxBytes, 1024, kLayoutSW128);
             const uint64_t db = make_smem_desc(q_base + k * 2048, kBoxBytes, 1024, kLayoutSW128);
-            umma_bf16(d_tmem, da, db, idesc, (kt > kt0) || (k != 0));
+            umma_bf16_p(issue, d_tmem, da, db, idesc, (kt > kt0) || (k != 0));
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit_p(issue, &empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);
+        umma_commit_p(issue, &tfull_bar[acc]);
       }
     }
   } else {

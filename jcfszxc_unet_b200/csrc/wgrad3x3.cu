@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // MMA issuer: warp-convergent loop, the elected lane issues (see umma_bf16_p in ptx.cuh)
+      const bool issue = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -136,10 +138,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
         const int ks = item / items_per_split;
         const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
         const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
-        mbar_wait(tempty_bar, (it & 1) ^ 1u);
+        mbar_wait_p(issue, tempty_bar, (it & 1) ^ 1u);
         tc_fence_after();
         for (int kt = kt0; kt < kt1; ++kt) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_p(issue, &full_bar[stage], phase);
           tc_fence_after();
           // descriptors are advanced from per-kernel bases (few instructions per MMA on the issuing thread)
           const uint64_t dp0 = desc_advance(p_desc0, static_cast<uint32_t>(stage) * stage_bytes);
@@ -153,21 +155,21 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
             if constexpr (NT == 64) {
               // taps s = 0,1,2 as three overlapping 64-wide N atoms, 128 B (one pixel row) apart (LBO = 128 B)
               constexpr uint32_t idesc = make_idesc_bf16(128, 192, true, true);
-              if (first && k == 0) umma_bf16(tmem_base, da, dq, idesc, 0u);
-              else umma_bf16_acc(tmem_base, da, dq, idesc);
+              if (first && k == 0) umma_bf16_p(issue, tmem_base, da, dq, idesc, 0u);
+              else umma_bf16_acc_p(issue, tmem_base, da, dq, idesc);
             } else {
               constexpr uint32_t idesc = make_idesc_bf16(128, NT, true, true);
 #pragma unroll
               for (int s = 0; s < 3; ++s) {
-                if (first && k == 0) umma_bf16(tmem_base + s * NT, da, desc_advance(dq, s * 128), idesc, 0u);
-                else umma_bf16_acc(tmem_base + s * NT, da, desc_advance(dq, s * 128), idesc);
+                if (first && k == 0) umma_bf16_p(issue, tmem_base + s * NT, da, desc_advance(dq, s * 128), idesc, 0u);
+                else umma_bf16_acc_p(issue, tmem_base + s * NT, da, desc_advance(dq, s * 128), idesc);
               }
             }
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit_p(issue, &empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar);
+        umma_commit_p(issue, tfull_bar);
       }
     }
   } else {

@@ -58,6 +58,8 @@ class Plan:
         self.params = []           # parameters in registration order
         self.sync_sums = None      # optional hook(sums_view) -> None: all-reduce BN statistics (SyncBN)
         self.packs = {}            # id(weight) -> WeightPack shared by every op that applies that weight
+        self._pack_table = self._pack_ptrs = None
+        self._pack_tiles = 0
         self._g_init = {}          # gradient buffer -> set of channels already written during backward
         self._p_init = set()       # parameters whose gradient was already written during backward
 
@@ -138,9 +140,25 @@ class Plan:
         return wp
 
     # ---- execution ------------------------------------------------------------------------------
-    def refresh_weights(self, force=False):
+    def _build_pack_table(self):
+        lib = _lib.load()
+        rows, first = [], 0
         for wp in self.packs.values():
-            wp.refresh(force)
+            rows.append([wp.w.data_ptr(), wp.ab.data_ptr(), wp.ba.data_ptr(), wp.a, wp.b, wp.taps, first, 0])
+            first += lib.unetk_pack_tiles(wp.a, wp.b)
+        self._pack_ptrs = [r[0] for r in rows]
+        self._pack_table = torch.tensor(rows, dtype=torch.int64).to(self.device)
+        self._pack_tiles = first
+
+    def refresh_weights(self, force=False):
+        """Re-derive the bf16 kernel-layout weight caches from the fp32 masters: ONE batched launch for all of them."""
+        packs = list(self.packs.values())
+        if packs and (force or any(wp.stale() for wp in packs)):
+            if self._pack_table is None or self._pack_ptrs != [wp.w.data_ptr() for wp in packs]:
+                self._build_pack_table()   # masters were re-homed (Trainer's flat parameter buffer) or first use
+            _lib.call("unetk_pack_weights", self._pack_table.data_ptr(), len(packs), self._pack_tiles, _s())
+            for wp in packs:
+                wp.mark_fresh()
         for op in self.ops:
             op.refresh(force)
 
@@ -178,11 +196,11 @@ class WeightPack:
         self.ba = torch.empty((taps, b, a), dtype=BF16, device=weight.device)
         self._ver = -1
 
-    def refresh(self, force=False):
-        if force or self.w._version != self._ver:
-            _lib.call("unetk_pack_weight", self.w.data_ptr(), self.ab.data_ptr(), self.ba.data_ptr(), self.a, self.b,
-                      self.taps, _s())
-            self._ver = self.w._version
+    def stale(self):
+        return self.w._version != self._ver
+
+    def mark_fresh(self):
+        self._ver = self.w._version
 
 
 class ConvBNReLU:
