@@ -124,7 +124,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ sums, double npi
 
 // dz = gscale * [ 0.5 * (sigmoid(z) - y) / Npix  -  0.5 * (y*cA - cB) * p(1-p) * 1[clamp inactive] ]
 // dx[pix][c] = dz * w[c];  partial[blk][c] = sum dz * x[pix][c];  partial[blk][C] = sum dz
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)   // head_grid launches 4 blocks per SM: keep them all resident
 head_loss_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ w,
                      const float* __restrict__ labels, const float* __restrict__ logits,
                      const float* __restrict__ fin, const float* __restrict__ dlogits, float gscale, int post_sigmoid,

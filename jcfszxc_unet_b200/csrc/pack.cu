@@ -29,23 +29,22 @@ __device__ __forceinline__ void pack_tile(const PackJob& j, int tile, float* s /
   const int a0 = (tile / tiles_b) * kTile, b0 = (tile % tiles_b) * kTile;
   const int na = min(kTile, A - a0), nb = min(kTile, B - b0);
   const int row = kTile * T + 1;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads, no integer division below
   // load: row a of the tile is the contiguous run src[(a*B + b0)*T ... + nb*T)
-  for (int i = threadIdx.x; i < na * nb * T; i += blockDim.x) {
-    const int a = i / (nb * T), r = i % (nb * T);
-    s[a * row + r] = j.src[(static_cast<long long>(a0 + a) * B + b0) * T + r];
+  for (int a = ty; a < na; a += 8) {
+    const float* run = j.src + (static_cast<long long>(a0 + a) * B + b0) * T;
+    for (int r = tx; r < nb * T; r += 32) s[a * row + r] = run[r];
   }
   __syncthreads();
-  if (j.dst_ab != nullptr) {
-    for (int i = threadIdx.x; i < T * na * nb; i += blockDim.x) {
-      const int b = i % nb, a = (i / nb) % na, t = i / (nb * na);
-      j.dst_ab[(static_cast<long long>(t) * A + a0 + a) * B + b0 + b] = __float2bfloat16_rn(s[a * row + b * T + t]);
-    }
+  if (j.dst_ab != nullptr && tx < nb) {
+    for (int t = 0; t < T; ++t)
+      for (int a = ty; a < na; a += 8)
+        j.dst_ab[(static_cast<long long>(t) * A + a0 + a) * B + b0 + tx] = __float2bfloat16_rn(s[a * row + tx * T + t]);
   }
-  if (j.dst_ba != nullptr) {
-    for (int i = threadIdx.x; i < T * nb * na; i += blockDim.x) {
-      const int a = i % na, b = (i / na) % nb, t = i / (na * nb);
-      j.dst_ba[(static_cast<long long>(t) * B + b0 + b) * A + a0 + a] = __float2bfloat16_rn(s[a * row + b * T + t]);
-    }
+  if (j.dst_ba != nullptr && tx < na) {
+    for (int t = 0; t < T; ++t)
+      for (int b = ty; b < nb; b += 8)
+        j.dst_ba[(static_cast<long long>(t) * B + b0 + b) * A + a0 + tx] = __float2bfloat16_rn(s[tx * row + b * T + t]);
   }
 }
 

@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
 // sit in shared memory and reports clocks per MMA.  Answers "what does an M=128 x N MMA really cost when A is
 // (a) a 1024-byte-aligned tile, (b) a row-shifted view of a halo tile, (c) alternating between two accumulators"
 // — the numbers the thin-layer conv kernels are designed against (profiles/r01_mma_rate_probe.txt).
-template <int N>
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int a_shift_rows, int two_acc, int iters, int b_tiles,
+template <int N, int EX>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int a_shift_rows, int iters, int b_tiles,
                                                          long long* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int a_shift_rows, int 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
-  if (threadIdx.x == 0) {
+  if (warp == 1) {
+    // warp-convergent issue loop (elected lane issues): measures the tensor pipe, not the issuing thread
+    const bool issue = elect_one();
     constexpr uint32_t idesc = make_idesc_bf16(128, N, false, false);
     const uint64_t a0 = make_smem_desc(smem_u32(sA) + a_shift_rows * 128, 16, 1024, kLayoutSW128);
     const uint64_t b0 = make_smem_desc(smem_u32(sB), 16, 1024, kLayoutSW128);
@@ -143,19 +145,15 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int a_shift_rows, int 
       const uint64_t da0 = desc_advance(a0, static_cast<uint32_t>((it % 3) * 128));   // tap-like column shift
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        // two_acc = number of EXTRA independent accumulators the MMAs rotate over (0, 1 or 3)
-        umma_bf16_acc(tmem, desc_advance(da0, k * 32), desc_advance(db0, k * 32), idesc);
-        if (two_acc >= 1) umma_bf16_acc(tmem + N, desc_advance(da0, 130 * 128 + k * 32), desc_advance(db0, k * 32), idesc);
-        if (two_acc >= 3) {
-          umma_bf16_acc(tmem + 2 * N, desc_advance(da0, 2 * 130 * 128 + k * 32), desc_advance(db0, k * 32), idesc);
-          umma_bf16_acc(tmem + 3 * N, desc_advance(da0, 3 * 130 * 128 + k * 32), desc_advance(db0, k * 32), idesc);
-        }
+#pragma unroll
+        for (int e = 0; e <= EX; ++e)   // EX = number of EXTRA independent accumulators the MMAs rotate over
+          umma_bf16_acc_p(issue, tmem + e * N, desc_advance(da0, e * 130 * 128 + k * 32), desc_advance(db0, k * 32), idesc);
       }
     }
-    umma_commit(bar);
-    mbar_wait(bar, 0);
+    umma_commit_p(issue, bar);
+    mbar_wait_p(issue, bar, 0);
     const long long t1 = clock64();
-    out[blockIdx.x] = t1 - t0;
+    if (issue) out[blockIdx.x] = t1 - t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -165,12 +163,12 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int a_shift_rows, int 
   }
 }
 
-template <int N>
-static int mma_rate_launch(int grid, int shift, int two_acc, int iters, int b_tiles, long long* out, cudaStream_t s) {
+template <int N, int EX>
+static int mma_rate_launch(int grid, int shift, int iters, int b_tiles, long long* out, cudaStream_t s) {
   const int smem = ((4 * 130 * 128 + 1024 + 1023) & ~1023) + b_tiles * N * 128 + 64 + 1024;
   UNETK_CHECK(smem <= 227 * 1024, -1, "mma_rate: smem %d", smem);
-  UNETK_CUDA(cudaFuncSetAttribute(mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  mma_rate_kernel<N><<<grid, 128, smem, s>>>(shift, two_acc, iters, b_tiles, out);
+  UNETK_CUDA((cudaFuncSetAttribute(mma_rate_kernel<N, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+  mma_rate_kernel<N, EX><<<grid, 128, smem, s>>>(shift, iters, b_tiles, out);
   UNETK_LAUNCHED();
   return 0;
 }
@@ -182,12 +180,13 @@ int probe_mma_rate_run(int N, int grid, int a_shift_rows, int two_acc, int iters
               "probe_mma_rate: bad arguments");
   UNETK_CHECK((two_acc == 0 || two_acc == 1 || two_acc == 3) && (two_acc + 1) * N <= 512, -1,
               "probe_mma_rate: extra accumulators 0/1/3 within 512 TMEM columns");
-  switch (N) {
-    case 64: return mma_rate_launch<64>(grid, a_shift_rows, two_acc, iters, b_tiles, out, stream);
-    case 128: return mma_rate_launch<128>(grid, a_shift_rows, two_acc, iters, b_tiles, out, stream);
-    case 256: return mma_rate_launch<256>(grid, a_shift_rows, two_acc, iters, b_tiles, out, stream);
-    default: UNETK_CHECK(false, -1, "probe_mma_rate: N must be 64, 128 or 256");
-  }
+#define UNETK_RATE(NN, EE) if (N == NN && two_acc == EE) return mma_rate_launch<NN, EE>(grid, a_shift_rows, iters, b_tiles, out, stream)
+  UNETK_RATE(64, 0); UNETK_RATE(64, 1); UNETK_RATE(64, 3);
+  UNETK_RATE(128, 0); UNETK_RATE(128, 1); UNETK_RATE(128, 3);
+  UNETK_RATE(192, 0); UNETK_RATE(192, 1);
+  UNETK_RATE(256, 0); UNETK_RATE(256, 1);
+#undef UNETK_RATE
+  UNETK_CHECK(false, -1, "probe_mma_rate: unsupported (N, extra accumulators) = (%d, %d)", N, two_acc);
   return 0;
 }
 

@@ -155,14 +155,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
             if constexpr (NT == 64) {
               // taps s = 0,1,2 as three overlapping 64-wide N atoms, 128 B (one pixel row) apart (LBO = 128 B)
               constexpr uint32_t idesc = make_idesc_bf16(128, 192, true, true);
-              if (first && k == 0) umma_bf16_p(issue, tmem_base, da, dq, idesc, 0u);
-              else umma_bf16_acc_p(issue, tmem_base, da, dq, idesc);
+              umma_bf16_p(issue, tmem_base, da, dq, idesc, (first && k == 0) ? 0u : 1u);   // no control flow per MMA
             } else {
               constexpr uint32_t idesc = make_idesc_bf16(128, NT, true, true);
 #pragma unroll
               for (int s = 0; s < 3; ++s) {
-                if (first && k == 0) umma_bf16_p(issue, tmem_base + s * NT, da, desc_advance(dq, s * 128), idesc, 0u);
-                else umma_bf16_acc_p(issue, tmem_base + s * NT, da, desc_advance(dq, s * 128), idesc);
+                umma_bf16_p(issue, tmem_base + s * NT, da, desc_advance(dq, s * 128), idesc, (first && k == 0) ? 0u : 1u);
               }
             }
           }

@@ -18,7 +18,7 @@ def main():
     iters = 2048
     print(f"{'N':>4s} {'grid':>4s} {'shift':>5s} {'2acc':>4s} {'btiles':>6s} {'clk/MMA':>9s} {'ideal':>6s} {'TFLOP/s/SM@1.9GHz':>18s}")
     for grid in (148,):
-        for n in (64, 128, 256):
+        for n in (64, 128, 192, 256):
             for shift in (0, 3):
                 for two in (0, 1, 3):
                     if (two + 1) * n > 512:
