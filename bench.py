@@ -49,6 +49,33 @@ def unet_train_gflop_per_image(size: int) -> float:
     return (3.0 * fwd - stem) / 1e9
 
 
+# model name -> (module, class, plan builder, train GFLOP per image at 512^2 measured on the reference)
+MODELS = {
+    "UNet": ("UNetFamily.UNet", "UNet", "engine.build_unet_plan", 1155.1),
+    "AttentionUNet": ("UNetFamily.AttentionUNet", "AttentionUNet", "builders.build_attention_unet_plan", 1593.3),
+    "R2UNet": ("UNetFamily.R2UNet", "R2UNet", "builders.build_r2unet_plan", 3659.6),
+    "ResUNet": ("UNetFamily.ResUNet", "ResUNet", "builders.build_resunet_plan", 1704.5),
+    "NestedUNet": ("UNetFamily.UNetPP", "NestedUNet", "builders.build_nested_unet_plan", 3308.8 / 4.0),
+}
+
+
+def make_model(name):
+    import importlib
+
+    from jcfszxc_unet_b200 import builders, engine
+
+    mod, cls, builder, _ = MODELS[name]
+    ns = {"engine": engine, "builders": builders}
+    bmod, bfn = builder.split(".")
+    return getattr(importlib.import_module(mod), cls)(), getattr(ns[bmod], bfn)
+
+
+def train_gflop_per_image(name: str, size: int) -> float:
+    if name == "UNet":
+        return unet_train_gflop_per_image(size)
+    return MODELS[name][3] * (size / 512.0) ** 2   # every layer is a convolution: FLOPs scale with the pixel count
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -180,6 +207,19 @@ CONV_FLOPS = {
 }
 
 
+def ncu_traffic_per_launch(family, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed ncu
+    capture of this exact workload (profiles/r01_ncu_traffic.json, made by tools/ncu_traffic.py); None for any other
+    workload (a number taken under a profiler is never measured live)."""
+    if args.model != "UNet" or args.batch != 16 or args.size != 512:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            return json.load(f)[family]["bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def kernel_breakdown(records):
     """Group the per-call CUDA-event timings of one eager step into kernel families."""
     fam = {}
@@ -205,7 +245,6 @@ def run_ours(args):
     from jcfszxc_unet_b200 import _lib
     from jcfszxc_unet_b200.dp import DataParallel
     from jcfszxc_unet_b200.trainer import Trainer
-    from UNetFamily.UNet import UNet
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,9 +261,10 @@ def run_ours(args):
     W, K = max(3, args.warmup), args.steps
 
     torch.manual_seed(SEED)
-    model = UNet(3, 1).to(dev).train()
+    model, builder = make_model(args.model)
+    model = model.to(dev).train()
     dp = DataParallel()
-    tr = Trainer(model, lr=1e-6, use_cuda_graph=not args.no_graph, dp=dp)   # lr: reference default train.py:434
+    tr = Trainer(model, lr=1e-6, use_cuda_graph=not args.no_graph, dp=dp, builder=builder)   # lr: reference default train.py:434
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
     images = torch.rand(B, 3, S, S, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
     labels = (torch.rand(B, 1, S, S, device=dev, generator=g) < LABEL_DENSITY).float()
@@ -291,7 +331,7 @@ def run_ours(args):
     value = world * B * K / (ms_total / 1e3)
     e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
     peaks = measured_peaks()
-    gflop_img = unet_train_gflop_per_image(S)
+    gflop_img = train_gflop_per_image(args.model, S)
     # dominant kernel family (by time inside the step) and its live roofline
     conv_fams = {k: v for k, v in fam.items() if v["flops"] > 0}
     dom_name = max(conv_fams, key=lambda k: conv_fams[k]["ms"])
@@ -299,10 +339,10 @@ def run_ours(args):
     achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
     step_ms_eager = sum(v["ms"] for v in fam.values())
     roofline = {
-        "bound": "tensor", "kernel": {"tap_gemm": "conv_gemm_kernel (conv3x3 fwd/dgrad, ConvTranspose fwd/dgrad)",
-                                      "wgrad": "wgrad_kernel (+ordered reduce)"}[dom_name],
+        "bound": "tensor", "kernel": {"tap_gemm": "conv_gemm_kernel / conv3x3_halo_kernel (conv3x3 and 1x1 fwd/dgrad, ConvTranspose fwd/dgrad)",
+                                      "wgrad": "wgrad3x3_kernel / wgrad_kernel (+ordered reduce)"}[dom_name],
         "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+        "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic_per_launch(dom_name, args),
         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
         "launches": dom["calls"], "avg_launch_ms": dom["ms"] / dom["calls"],
         "share_of_step": dom["ms"] / step_ms_eager,
@@ -313,7 +353,7 @@ def run_ours(args):
                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
     }
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.model == "UNet":
         ips, ms, done, cores = cpu_reference_step_rate(S, 2, 3, 1, budget_s=25.0)
         cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"oracle port of train.py:255-301 (bf16 autocast) on the host, batch 2 of 3x{S}x{S}, 1 warm-up + {done} timed steps"}
@@ -321,8 +361,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"vanilla UNet(n_channels=3, n_classes=1) bf16 training step (BCE+dice, clip 1.0, RMSprop), "
-                               f"batch {B} per GPU, 3x{S}x{S} synthetic (BASELINE.json configs[1])",
+        "config": {"workload": (f"vanilla UNet(n_channels=3, n_classes=1) bf16 training step (BCE+dice, clip 1.0, RMSprop), "
+                                f"batch {B} per GPU, 3x{S}x{S} synthetic (BASELINE.json configs[1])") if args.model == "UNet" else
+                               (f"{args.model} bf16 training step (BCE+dice, clip 1.0, RMSprop), batch {B} per GPU, "
+                                f"3x{S}x{S} synthetic"),
                    "per_gpu_batch": B, "global_batch": B * world, "image": f"3x{S}x{S}", "parallelism": f"dp{world}",
                    "batchnorm": "per-rank batch statistics" if world > 1 else "batch statistics",
                    "cuda_graph": not args.no_graph,
@@ -350,6 +392,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE.json configs[1]: 16)")
     ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--model", default="UNet", choices=sorted(MODELS), help="default: the headline config (vanilla UNet)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -148,7 +148,11 @@ int unetk_bn_apply(const void* raw, int64_t raw_ld, const float* scale, const fl
  *   unetk_bn_bwd_reduce: sums = double[2][C] (sum g, sum g*xhat)      (SyncBN: all-reduce here)
  *   unetk_bn_bwd_apply : dgamma/dbeta (fp32, optional, accumulate!=0 adds), coef = fp32 scratch [2][C],
  *                        draw = gradient w.r.t. the raw conv output (bf16 NHWC). count = pixels behind sums.
- *                        draw_accumulate != 0: draw += (pre-activation BN whose input has other consumers). */
+ *                        draw_accumulate != 0: draw += (pre-activation BN whose input has other consumers).
+ *                        dconv_bias (optional, fp32 [C]): gradient of the bias of the convolution feeding this
+ *                        BatchNorm (conv_block / up_conv / Recurrent_block ..., unet_parts.py:85,103,119): batch
+ *                        statistics cancel a per-channel constant, so it is exactly zero and is written as such
+ *                        (left untouched when accumulate != 0) instead of reducing d(raw) once more. */
 int unetk_bn_bwd_reduce(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp,
                         int64_t gp_ld, const float* scale, const float* shift, const float* mean,
                         const float* invstd, float* partial, double* sums, int N, int H, int W, int C, int relu,
@@ -156,12 +160,13 @@ int unetk_bn_bwd_reduce(const void* raw, int64_t raw_ld, const void* g1, int64_t
 int unetk_bn_bwd_apply(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp,
                        int64_t gp_ld, const float* scale, const float* shift, const float* mean,
                        const float* invstd, const double* sums, double count, float* dgamma, float* dbeta,
-                       int accumulate, float* coef, void* draw, int64_t draw_ld, int draw_accumulate, int N, int H,
-                       int W, int C, int relu, void* stream);
+                       int accumulate, float* coef, float* dconv_bias, void* draw, int64_t draw_ld,
+                       int draw_accumulate, int N, int H, int W, int C, int relu, void* stream);
 /* The per-channel part of unetk_bn_bwd_apply alone: dgamma/dbeta and coef = [K0[C] | K1[C]] with
  * d(raw) = scale*g + K1*raw + K0 (used by the attention gate's fused backward; C >= 1). */
 int unetk_bn_bwd_coef(const double* sums, int C, double count, const float* scale, const float* mean,
-                      const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, void* stream);
+                      const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef,
+                      float* dconv_bias, void* stream);
 
 /* ---- MaxPool2d(2) standalone (unet_parts.py:43; indices as F.max_pool2d(return_indices=True)) ----
  * idx (optional) is int64 [N][C][H/2][W/2] holding h*W+w of the selected input element:

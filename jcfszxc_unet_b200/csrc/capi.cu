@@ -272,17 +272,18 @@ int unetk_bn_bwd_reduce(const void* raw, int64_t raw_ld, const void* g1, int64_t
 int unetk_bn_bwd_apply(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
                        const float* scale, const float* shift, const float* mean, const float* invstd,
                        const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
-                       void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C, int relu,
-                       void* stream) {
+                       float* dconv_bias, void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C,
+                       int relu, void* stream) {
   UNETK_CHECK(raw && scale && shift && mean && invstd && sums && coef && draw && count > 0, -1,
               "bn_bwd_apply: bad arguments");
   return bn_bwd_apply_run(raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, sums, count, dgamma, dbeta,
-                          accumulate, coef, draw, draw_ld, draw_accumulate, N, H, W, C, relu, S(stream));
+                          accumulate, coef, dconv_bias, draw, draw_ld, draw_accumulate, N, H, W, C, relu, S(stream));
 }
 int unetk_bn_bwd_coef(const double* sums, int C, double count, const float* scale, const float* mean,
-                      const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, void* stream) {
+                      const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, float* dconv_bias,
+                      void* stream) {
   UNETK_CHECK(sums && scale && mean && invstd && coef && count > 0, -1, "bn_bwd_coef: bad arguments");
-  return bn_bwd_coef_run(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef, S(stream));
+  return bn_bwd_coef_run(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef, dconv_bias, S(stream));
 }
 int unetk_maxpool2x2_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t* idx, int N, int H, int W, int C,
                          void* stream) {

@@ -510,9 +510,14 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_kernel(const BnBwdA
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int C, double count,
                                        const float* __restrict__ scale, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, float* dgamma, float* dbeta, int accumulate,
-                                       float* __restrict__ coef) {
+                                       float* __restrict__ coef, float* dconv_bias) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  // Bias of the convolution in FRONT of this BatchNorm (conv_block, up_conv, Recurrent_block, W_g/W_x/psi, ...):
+  // its gradient is sum_pixels d(raw) = scale*S0 + K1*M*mean + K0*M, which is identically zero (batch statistics
+  // remove any per-channel constant).  The reference's autograd sums the rounded d(raw) and gets rounding noise
+  // around zero; we write the exact value instead of spending a full pass over d(raw) per layer.
+  if (dconv_bias != nullptr && !accumulate) dconv_bias[c] = 0.f;
   const double s0 = sums[c], s1 = sums[C + c];
   const double is = invstd[c], sc = scale[c], mu = mean[c];
   const float db = static_cast<float>(s0), dg = static_cast<float>(is * s1);
@@ -742,9 +747,11 @@ int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g
 }
 
 int bn_bwd_coef_run(const double* sums, int C, double count, const float* scale, const float* mean,
-                    const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, cudaStream_t s) {
+                    const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, float* dconv_bias,
+                    cudaStream_t s) {
   UNETK_CHECK(C >= 1, -1, "bn_bwd_coef: C=%d", C);
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef,
+                                                         dconv_bias);
   UNETK_LAUNCHED();
   return 0;
 }
@@ -752,13 +759,14 @@ int bn_bwd_coef_run(const double* sums, int C, double count, const float* scale,
 int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
                      const float* scale, const float* shift, const float* mean, const float* invstd,
                      const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
-                     void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C, int relu,
-                     cudaStream_t s) {
+                     float* dconv_bias, void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C,
+                     int relu, cudaStream_t s) {
   BnBwdArgs A;
   if (int rc = bn_bwd_args(&A, raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, N, H, W, C, relu)) return rc;
   const bool pool = gp != nullptr;
   const int64_t units = pool ? static_cast<int64_t>(N) * (H / 2) * (W / 2) : static_cast<int64_t>(N) * H * W;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef,
+                                                         dconv_bias);
   UNETK_LAUNCHED();
   const int grid = bwd_grid(units, C);
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(draw);

@@ -43,8 +43,8 @@ int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g
 int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
                      const float* scale, const float* shift, const float* mean, const float* invstd,
                      const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
-                     void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C, int relu,
-                     cudaStream_t s);
+                     float* dconv_bias, void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C,
+                     int relu, cudaStream_t s);
 // loss.cu
 size_t head_partial_floats(int64_t npix, int C);
 int head_loss_fwd_run(const void* x, int64_t ld, const float* w, const float* bias, const float* labels, float* logits,
@@ -75,7 +75,8 @@ int copy_f32_strided_run(float* dst, int64_t ds, const float* src, int64_t ss, i
                          cudaStream_t s);
 // elementwise.cu
 int bn_bwd_coef_run(const double* sums, int C, double count, const float* scale, const float* mean,
-                    const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, cudaStream_t s);
+                    const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, float* dconv_bias,
+                    cudaStream_t s);
 // gate.cu
 size_t gate_partial_floats(int64_t npix, int F);
 int gate_fwd_run(const void* rawg, int64_t rawg_ld, const void* rawx, int64_t rawx_ld, const float* scg,

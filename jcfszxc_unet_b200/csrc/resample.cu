@@ -213,15 +213,32 @@ bilinear2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, __nv_bf
 }
 
 // Gather form of the backward: input pixel i receives from every output o whose (i0, i1) pair contains i.
-// With scale = (in-1)/(2in-1) < 1/2 those outputs lie in [ceil((i-1)/scale), floor((i+1)/scale)] (at most 5).
-__device__ __forceinline__ void contributors(float scale, int i, int in, int out, int* lo, int* hi) {
-  // conservative integer window; exact membership is re-tested with src_index
-  if (!(scale > 0.f)) { *lo = 0; *hi = out - 1; return; }   // in == 1: every output reads input 0
-  int a = static_cast<int>(floorf((i - 1) / scale)) - 1;
-  int b = static_cast<int>(ceilf((i + 1) / scale)) + 1;
-  if (a < 0) a = 0;
-  if (b > out - 1) b = out - 1;
-  *lo = a; *hi = b;
+// With scale = (in-1)/(2in-1) < 1/2 those outputs lie in [2i-2, 2i+3]; at most four of them really touch i.
+// The (output index, weight) lists of a row and of a column are built once per input pixel, so the inner
+// loop is nothing but <= 16 vector loads and FMAs (the first version re-derived the source index of every
+// candidate inside a 7 x 7 loop and ran at 4.5 ms per UNet++ step for ten tensors).
+struct Taps {
+  int idx[4];
+  float w[4];
+  int n;
+};
+__device__ __forceinline__ Taps contributors(float scale, int i, int in, int out) {
+  Taps t;
+  t.n = 0;
+  int lo = 2 * i - 2, hi = 2 * i + 3;
+  if (in == 1) { lo = 0; hi = out - 1; }   // every output reads input 0 with weight 1 (out == 2)
+  if (lo < 0) lo = 0;
+  if (hi > out - 1) hi = out - 1;
+  for (int o = lo; o <= hi; ++o) {
+    int i0, i1;
+    float l0, l1;
+    src_index(scale, o, in, &i0, &i1, &l0, &l1);
+    float w = 0.f;
+    if (i0 == i) w += l0;
+    if (i1 == i) w += l1;
+    if (w != 0.f && t.n < 4) { t.idx[t.n] = o; t.w[t.n] = w; ++t.n; }
+  }
+  return t;
 }
 
 template <bool ACC>
@@ -239,29 +256,22 @@ bilinear2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_ld, __nv_
     const uint32_t t = uu / W;
     const int h = static_cast<int>(t % H);
     const int n = static_cast<int>(t / H);
-    int hlo, hhi, wlo, whi;
-    contributors(sh, h, H, Ho, &hlo, &hhi);
-    contributors(sw, w, W, Wo, &wlo, &whi);
+    const Taps th = contributors(sh, h, H, Ho), tw = contributors(sw, w, W, Wo);
     float acc[8] = {};
-    for (int ho = hlo; ho <= hhi; ++ho) {
-      int h0, h1;
-      float lh0, lh1;
-      src_index(sh, ho, H, &h0, &h1, &lh0, &lh1);
-      float wh = 0.f;
-      if (h0 == h) wh += lh0;
-      if (h1 == h) wh += lh1;
-      if (wh == 0.f) continue;
-      for (int wo = wlo; wo <= whi; ++wo) {
-        int w0, w1;
-        float lw0, lw1;
-        src_index(sw, wo, W, &w0, &w1, &lw0, &lw1);
-        float ww = 0.f;
-        if (w0 == w) ww += lw0;
-        if (w1 == w) ww += lw1;
-        if (ww == 0.f) continue;
+    const __nv_bfloat16* base = dy + static_cast<int64_t>(n) * Ho * Wo * dy_ld + L.g * 8;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (a >= th.n) break;
+      uint4 v[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        v[b] = (b < tw.n) ? ldg16(base + (static_cast<int64_t>(th.idx[a]) * Wo + tw.idx[b]) * dy_ld) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (b >= tw.n) break;
         float f[8];
-        unpack8(ldg16(dy + ((static_cast<int64_t>(n) * Ho + ho) * Wo + wo) * dy_ld + L.g * 8), f);
-        const float k = wh * ww;
+        unpack8(v[b], f);
+        const float k = th.w[a] * tw.w[b];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(k, f[j], acc[j]);
       }

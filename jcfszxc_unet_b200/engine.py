@@ -331,8 +331,10 @@ class ConvBNReLU:
             count = self.raw.N * self.raw.H * self.raw.W
             if P.sync_sums is not None:
                 count = P.sync_sums(P.sums[: 2 * self.cout], count)
+            # the bias of a conv in front of a train-mode BatchNorm has an identically zero gradient: written by the
+            # BN backward's per-channel kernel instead of a column-sum pass over d(raw)
             ops.bn_bwd_apply(self.raw.t, g1, gp, sc, sh, mu, iv, P.sums, count, self.dgamma, self.dbeta, P.coef,
-                             self.raw.g, self.relu, accumulate=self.acc_bn)
+                             self.raw.g, self.relu, accumulate=self.acc_bn, dconv_bias=self.dbias)
             if not self._res_aliases_out():
                 ops.add_n(self.res.g, [g1], accumulate=self.acc_res)
         dy = self.raw.g
@@ -348,7 +350,7 @@ class ConvBNReLU:
                 ops.copy_f32_strided(self.dw, 1, self.dw3, 9, self.cout * self.cin, accumulate=self.acc_w, src_offset=4)
         else:
             ops.conv_wgrad(self.x.t, dy, self.dw, self.k, self.acc_w, self.stride, ws=P.ws)
-        if self.dbias is not None:
+        if self.dbias is not None and self.bn is None:
             ops.colsum(dy, P.partial, self.dbias, self.acc_b)
         if not self.stem and self.x.g is not None:
             ops.conv_dgrad(dy, self.pack.ba, self.x.g, self.k, self.acc_x, self.stride)
@@ -724,7 +726,7 @@ class AttentionGate(_Op):
         count = self.npix
         if P.sync_sums is not None:
             count = P.sync_sums(s1, count)
-        ops.bn_bwd_coef(s1, count, st1[0], st1[2], st1[3], dgam_1, dbet_1, self.coef1, acc)
+        ops.bn_bwd_coef(s1, count, st1[0], st1[2], st1[3], dgam_1, dbet_1, self.coef1, acc, dconv_bias=dbp)
         gp, gld = ops.nhwc(self.rawg.t)
         xp, xld = ops.nhwc(self.rawx.t)
         sg, sx = self.statg, self.statx
@@ -732,13 +734,13 @@ class AttentionGate(_Op):
         sums_g, sums_x = self.sums2[4:4 + 2 * F], self.sums2[4 + 2 * F:4 + 4 * F]
         _lib.call("unetk_gate_bwd_reduce", gp, gld, xp, xld, f(sg[0]), f(sg[1]), f(sg[2]), f(sx[0]), f(sx[1]), f(sx[2]),
                   f(wpsi), f(self.s), f(self.dz), f(st1[0]), f(self.coef1), P.partial.data_ptr(), sums_g.data_ptr(),
-                  sums_x.data_ptr(), f(dwp.view(-1)) if dwp is not None else None, f(dbp), int(acc), self.npix, F, _s())
+                  sums_x.data_ptr(), f(dwp.view(-1)) if dwp is not None else None, None, int(acc), self.npix, F, _s())
         cg_count = cx_count = self.npix
         if P.sync_sums is not None:
             cg_count = P.sync_sums(sums_g, self.npix)
             cx_count = P.sync_sums(sums_x, self.npix)
-        ops.bn_bwd_coef(sums_g, cg_count, sg[0], sg[2], sg[3], dgam_g, dbet_g, self.coefg, acc)
-        ops.bn_bwd_coef(sums_x, cx_count, sx[0], sx[2], sx[3], dgam_x, dbet_x, self.coefx, acc)
+        ops.bn_bwd_coef(sums_g, cg_count, sg[0], sg[2], sg[3], dgam_g, dbet_g, self.coefg, acc, dconv_bias=dbg)
+        ops.bn_bwd_coef(sums_x, cx_count, sx[0], sx[2], sx[3], dgam_x, dbet_x, self.coefx, acc, dconv_bias=dbx)
         dgp, dgld = ops.nhwc(self.rawg.g)
         dxrp, dxrld = ops.nhwc(self.rawx.g)
         _lib.call("unetk_gate_bwd_apply", gp, gld, xp, xld, f(sg[0]), f(sg[1]), f(sx[0]), f(sx[1]), f(wpsi), f(self.s),
@@ -747,8 +749,6 @@ class AttentionGate(_Op):
         for src, raw, pack, dw, db, a_in in ((self.g, self.rawg, self.packg, dwg, dbg, self.acc_g),
                                              (self.x, self.rawx, self.packx, dwx, dbx, self.acc_xw)):
             ops.conv_wgrad(src.t, raw.g, dw, 1, acc, 1, ws=P.ws)
-            if db is not None:
-                ops.colsum(raw.g, P.partial, db, acc)
             ops.conv_dgrad(raw.g, pack.ba, src.g, 1, a_in, 1)
 
 

@@ -242,21 +242,21 @@ def bn_bwd_reduce(raw, g1, gp, scale, shift, mean, invstd, partial, sums, relu=T
 
 
 def bn_bwd_apply(raw, g1, gp, scale, shift, mean, invstd, sums, count, dgamma, dbeta, coef, draw, relu=True,
-                 accumulate=False, draw_accumulate=False):
+                 accumulate=False, draw_accumulate=False, dconv_bias=None):
     n, h, w, c = raw.shape
     rp, rld = nhwc(raw)
     g1p, g1ld = nhwc(g1) if g1 is not None else (None, 0)
     gpp, gpld = nhwc(gp) if gp is not None else (None, 0)
     dp, dld = nhwc(draw)
     _lib.call("unetk_bn_bwd_apply", rp, rld, g1p, g1ld, gpp, gpld, _f32(scale), _f32(shift), _f32(mean), _f32(invstd),
-              sums.data_ptr(), float(count), _f32(dgamma), _f32(dbeta), int(accumulate), _f32(coef), dp, dld,
-              int(draw_accumulate), n, h, w, c, int(relu), _stream())
+              sums.data_ptr(), float(count), _f32(dgamma), _f32(dbeta), int(accumulate), _f32(coef), _f32(dconv_bias),
+              dp, dld, int(draw_accumulate), n, h, w, c, int(relu), _stream())
 
 
-def bn_bwd_coef(sums, count, scale, mean, invstd, dgamma, dbeta, coef, accumulate=False):
+def bn_bwd_coef(sums, count, scale, mean, invstd, dgamma, dbeta, coef, accumulate=False, dconv_bias=None):
     c = scale.numel()
     _lib.call("unetk_bn_bwd_coef", sums.data_ptr(), c, float(count), _f32(scale), _f32(mean), _f32(invstd),
-              _f32(dgamma), _f32(dbeta), int(accumulate), _f32(coef), _stream())
+              _f32(dgamma), _f32(dbeta), int(accumulate), _f32(coef), _f32(dconv_bias), _stream())
 
 
 def maxpool_fwd(x, y, idx=None):
