@@ -64,6 +64,19 @@ class DataParallel:
         self.all_reduce_sum_(flat_grad)
         return 1.0 if (self.sync_loss or not self.enabled) else 1.0 / self.world
 
+    def reduce_grads_async(self, bucket: torch.Tensor):
+        """Start the SUM all-reduce of one gradient bucket on the communication stream and return its handle (None
+        when single-process).  The caller keeps computing (the rest of the backward) and waits on the handle before
+        the optimizer: NCCL over NVLink runs beside the backward kernels instead of after them."""
+        if not self.enabled:
+            return None
+        return dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    @staticmethod
+    def wait(handle):
+        if handle is not None:
+            handle.wait()
+
     def broadcast_(self, t: torch.Tensor, src: int = 0):
         if self.enabled:
             dist.broadcast(t, src=src, group=self.group)

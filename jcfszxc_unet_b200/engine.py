@@ -172,9 +172,23 @@ class Plan:
         for op in self.ops:
             op.fwd()
 
-    def backward(self):
-        for op in reversed(self.ops):
+    def backward(self, lo: int = 0, hi: int | None = None):
+        """Backward of ops[lo:hi] in reverse order (the whole plan by default)."""
+        ops_ = self.ops[lo:hi]
+        for op in reversed(ops_):
             op.bwd()
+
+    def op_params(self, op):
+        """Parameters whose gradient `op` produces (every op keeps its modules as attributes)."""
+        out = []
+        for v in vars(op).values():
+            if isinstance(v, torch.nn.Module):
+                out += list(v.parameters(recurse=True))
+            elif isinstance(v, torch.nn.Parameter):
+                out.append(v)
+            elif isinstance(v, (list, tuple)):
+                out += [q for q in v if isinstance(q, torch.nn.Parameter)]
+        return out
 
     def grads(self):
         return [self.grad_of[id(p)] for p in self.params]

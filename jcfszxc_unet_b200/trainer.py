@@ -2,11 +2,15 @@
 
     forward -> 0.5*BCEWithLogits + 0.5*dice_loss -> backward -> clip_grad_norm_(1.0) -> RMSprop
 
-as three CUDA-graph segments with the two data-parallel collectives between them:
+as CUDA-graph segments with the data-parallel collectives between them:
 
     [pack weights, forward, head+loss sums]  --all-reduce(loss sums)-->
-    [loss finalize, backward]                --all-reduce(flat grads)-->
+    [loss finalize, backward of the decoder] --async all-reduce(decoder grads) on the NCCL stream ...
+    [backward of the encoder]                --all-reduce(encoder grads), wait for both-->
     [global-norm clip coefficient, RMSprop]
+
+The gradient all-reduce is bucketed in backward order (the decoder's gradients are the contiguous tail of the
+flat buffer and are complete half-way through the backward), so NCCL runs beside the encoder's backward kernels.
 
 Parameters, gradients and RMSprop state live in four flat fp32 buffers (the model's nn.Parameters are
 re-homed as views, so state_dict()/checkpoints keep working).  No host synchronisation happens inside
@@ -78,14 +82,48 @@ class Trainer:
         self.sq_partial = torch.empty(_lib.load().unetk_sqnorm_partial_floats(self.flat_g.numel()),
                                       dtype=torch.float32, device=dev)
         self._gscale = 1.0
+        self._split_op, self._split_off = self._find_bucket_split()
 
-    # three segments ---------------------------------------------------------------------------------
+    def _find_bucket_split(self):
+        """(k, o): the ops[k:] — run FIRST in the backward — own exactly the parameters stored at flat offsets >= o,
+        with about half of the gradient behind o.  (0, 0) when no such cut exists (single bucket)."""
+        base = self.flat_g.data_ptr()
+        ranges = []
+        for op in self.plan.ops:
+            lo, hi = None, None
+            for q in self.plan.op_params(op):
+                g = self.grad_views.get(id(q))
+                if g is None:
+                    continue
+                o = (g.data_ptr() - base) // 4
+                lo = o if lo is None else min(lo, o)
+                hi = o + g.numel() if hi is None else max(hi, o + g.numel())
+            ranges.append((lo, hi))
+        total = self.flat_g.numel()
+        n = len(ranges)
+        prefix_hi = [0] * (n + 1)            # max offset end owned by ops[:k]
+        for k in range(n):
+            prefix_hi[k + 1] = max(prefix_hi[k], ranges[k][1] or 0)
+        suffix_lo = [total] * (n + 1)        # min offset start owned by ops[k:]
+        for k in range(n - 1, -1, -1):
+            suffix_lo[k] = min(suffix_lo[k + 1], ranges[k][0] if ranges[k][0] is not None else total)
+        best = (0, 0)
+        for k in range(1, n):
+            if prefix_hi[k] <= suffix_lo[k] < total and suffix_lo[k] > 0:
+                if best == (0, 0) or abs(suffix_lo[k] - total // 2) < abs(best[1] - total // 2):
+                    best = (k, int(suffix_lo[k]))
+        return best
+
+    # segments ---------------------------------------------------------------------------------------
     def _seg_forward(self):
         self.plan.forward(self.images)
 
     def _seg_backward(self):
         self.plan.head.finalize_loss(self._npix_total)
-        self.plan.backward()
+        self.plan.backward(self._split_op, None)
+
+    def _seg_backward_tail(self):
+        self.plan.backward(0, self._split_op)
 
     def _seg_optim(self):
         ops.grad_clip_coef(self.flat_g, self._gscale, self.max_norm, self.sq_partial, self.clip)
@@ -105,10 +143,18 @@ class Trainer:
             self.graphs[1].replay()
         else:
             self._seg_backward()
-        if self.dp.enabled:
-            self.dp.reduce_grads(self.flat_g)
+        # decoder gradients (flat tail) are final: reduce them while the encoder's backward runs
+        h_tail = self.dp.reduce_grads_async(self.flat_g[self._split_off:]) if self._split_op > 0 else None
+        if self._split_op > 0:
+            if self.graphs is not None:
+                self.graphs[2].replay()
+            else:
+                self._seg_backward_tail()
+        h_head = self.dp.reduce_grads_async(self.flat_g[:self._split_off] if self._split_op > 0 else self.flat_g)
+        self.dp.wait(h_tail)
+        self.dp.wait(h_head)
         if self.graphs is not None:
-            self.graphs[2].replay()
+            self.graphs[3].replay()
         else:
             self._seg_optim()
 
@@ -116,7 +162,7 @@ class Trainer:
         # constants baked into the graphs
         graphs = []
         pool = None
-        for seg in (self._seg_forward_packed, self._seg_backward, self._seg_optim):
+        for seg in (self._seg_forward_packed, self._seg_backward, self._seg_backward_tail, self._seg_optim):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
                 seg()

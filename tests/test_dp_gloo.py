@@ -112,8 +112,16 @@ def _worker(rank, world, port, out_dir):
     loss = _loss_from_sums(local + (sums - local.detach()), npix)
     loss.backward()
     flat_g = torch.cat([sd[k].grad.flatten() for k in names])
+    # the Trainer's bucketed, overlapped reduction (decoder tail first, encoder head second) must equal ONE all-reduce
+    bucketed = flat_g.clone()
+    cut = bucketed.numel() // 2 + 3
+    h_tail = dp.reduce_grads_async(bucketed[cut:])
+    h_head = dp.reduce_grads_async(bucketed[:cut])
+    dp.wait(h_tail)
+    dp.wait(h_head)
     gscale = dp.reduce_grads(flat_g)       # SUM, not mean: the loss was already global
     assert gscale == 1.0
+    assert torch.equal(bucketed, flat_g)
     (clipped,), total = O.clip_grad_norm([flat_g * gscale], 1.0)
     # optimizer on the flat buffers, identical on every rank
     p = flat_p.clone()
