@@ -6,6 +6,8 @@
 // Reference semantics replaced: the first nn.Conv2d of DoubleConv `inc` (UNetFamily/UNet.py:21,
 // unet_parts.py:24) and its weight gradient.
 #include "host_common.cuh"
+
+#include <cstdlib>
 #include "ptx.cuh"
 
 namespace unetk {
@@ -170,8 +172,23 @@ int stem_grid(int N, int H, int W) {
   return tiles < cap ? tiles : cap;
 }
 
+// stem_tc.cu: the tensor-core versions (default); UNETK_STEM_TC=0 selects the CUDA-core kernels of this file
+bool stem_tc_ok(int Cin, int Cout);
+int stem_tc_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
+                    void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
+size_t stem_tc_wgrad_workspace(int N, int H, int W, int Cin, int Cout);
+int stem_tc_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy, int64_t dy_ld,
+                      float* dw, int accumulate, int N, int H, int W, int Cin, int Cout, void* ws, size_t ws_bytes,
+                      cudaStream_t s);
+static bool use_tc(int Cin, int Cout, int max_cout) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("UNETK_STEM_TC"); env = e ? atoi(e) : 1; }
+  return env && stem_tc_ok(Cin, Cout) && Cout <= max_cout;
+}
+
 int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
                  void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s) {
+  if (use_tc(Cin, Cout, 256)) return stem_tc_fwd_run(x, sn, sc, sh, sw, w, bias, y, y_ld, N, H, W, Cin, Cout, s);
   UNETK_CHECK(Cin >= 1 && Cin <= 4, -1, "stem: Cin=%d must be <= 4", Cin);
   UNETK_CHECK(Cout % 8 == 0 && Cout <= 64, -1, "stem: Cout=%d must be a multiple of 8 and <= 64", Cout);
   StemGeom G{x, sn, sc, sh, sw, N, H, W, Cin, Cout};
@@ -186,12 +203,16 @@ int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
 }
 
 size_t stem_wgrad_workspace(int N, int H, int W, int Cin) {
-  return static_cast<size_t>(stem_grid(N, H, W)) * 64 * 9 * Cin * sizeof(float);
+  const size_t a = static_cast<size_t>(stem_grid(N, H, W)) * 64 * 9 * Cin * sizeof(float);
+  const size_t b = stem_tc_wgrad_workspace(N, H, W, Cin, 128);   // the query does not know Cout: size for the largest
+  return a > b ? a : b;
 }
 
 int stem_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy, int64_t dy_ld,
                    float* dw, int accumulate, int N, int H, int W, int Cin, int Cout, void* ws, size_t ws_bytes,
                    cudaStream_t s) {
+  if (use_tc(Cin, Cout, 128))
+    return stem_tc_wgrad_run(x, sn, sc, sh, sw, dy, dy_ld, dw, accumulate, N, H, W, Cin, Cout, ws, ws_bytes, s);
   UNETK_CHECK(Cin >= 1 && Cin <= 4, -1, "stem: Cin=%d must be <= 4", Cin);
   UNETK_CHECK(Cout % 8 == 0 && Cout <= 64, -1, "stem: Cout=%d must be a multiple of 8 and <= 64", Cout);
   UNETK_CHECK(ws != nullptr && ws_bytes >= stem_wgrad_workspace(N, H, W, Cin), -1, "stem_wgrad: workspace too small");
