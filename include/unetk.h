@@ -64,6 +64,14 @@ int unetk_conv3x3_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, c
                               int Cout, void* stream);
 int unetk_conv3x3_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
                         int accumulate, int N, int H, int W, int Cin, int Cout, void* stream);
+/* dgrad that also returns sums = double[2][Cin]: per-channel (sum, sum of squares) over all pixels of the bf16 dx it
+ * wrote (no accumulate).  When dx is the gradient of a concat buffer [skip | up] (unet_parts.py:69), sums[0][C..2C)
+ * IS the bias gradient of the ConvTranspose2d that produced `up` (unet_parts.py:56-58): unetk_sums_to_f32 copies it
+ * out, which removes the column-sum pass over that gradient.  partial as for unetk_conv3x3_fwd_bnstats (Cin). */
+int unetk_conv3x3_dgrad_colsum(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
+                               float* partial, double* sums, int N, int H, int W, int Cin, int Cout, void* stream);
+/* out[i] (+)= (float)sums[i], i < n. */
+int unetk_sums_to_f32(const double* sums, int n, float* out, int accumulate, void* stream);
 size_t unetk_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int taps);
 int unetk_conv3x3_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw,
                         int accumulate, int N, int H, int W, int Cin, int Cout, void* workspace,
@@ -265,6 +273,37 @@ int unetk_gate_bwd_apply(const void* raw_g, int64_t raw_g_ld, const void* raw_x,
                          const float* dz, const float* sc1, const float* coef1, const float* coef_g,
                          const float* coef_x, void* draw_g, int64_t draw_g_ld, void* draw_x, int64_t draw_x_ld,
                          int64_t npix, int F_int, void* stream);
+
+/* ---- fp32 mode (BASELINE.json configs[0]: vanilla UNet fp32 forward; logits within 1e-4 of torch fp32) ----------
+ * The reference without autocast computes in fp32 (UNet.py:39-55 on unet_parts.py:17-79).  Here an fp32 value is
+ * carried as three bf16 terms (hi + mid + lo) and a product as six exact bf16 x bf16 terms accumulated in fp32 on the
+ * tensor core.  "Split tensor": bf16 NHWC with 6C channels [hi|hi|hi|mid|mid|lo]; "split pack": bf16 [T][R][6K] with
+ * the K axis [hi|mid|lo|hi|mid|hi] per input slice.  Forward only.
+ *   f32_pack_split3: dst[t][r][6K] from the fp32 master src[r*sr + k*sk + t*st]; `slices` (HOST array of n_slices ints
+ *                    summing to K) are the widths of the channel slices of the consumer's input (concat order).
+ *   f32_stem_conv3x3: 3x3 conv of the fp32 image (Cin <= 4, element strides sn,sc,sh,sw) in fp32 FMAs -> fp32 NHWC.
+ *   f32_conv3x3 / f32_convT2x2: x_split [N,H,W,Cin6], w_split [9|4][Cout][Cin6] -> y fp32 NHWC (+bias), y_ld in floats.
+ *   f32_stats: sums = double[2][C] (sum, sum sq) of an fp32 NHWC tensor; partial >= f32_stats_partial_doubles doubles.
+ *              Feed unetk_bn_finalize / unetk_bn_eval_fold as in the bf16 path.
+ *   f32_bn_split: v = relu?(raw*scale+shift) (scale/shift NULL: identity); writes any of: split (6C-wide slice),
+ *                 out_f32 (C-wide), pooled (split of MaxPool2d(2) of v, first max wins).
+ *   f32_head: logits[p] = bias + sum_c x[p,c]*w[c] (OutConv with n_classes == 1). */
+int unetk_f32_pack_split3(const float* src, void* dst, int64_t sr, int64_t sk, int64_t st, int R, int K, int T,
+                          const int* slices, int n_slices, void* stream);
+int unetk_f32_stem_conv3x3(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w,
+                           const float* bias, float* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout,
+                           void* stream);
+int unetk_f32_conv3x3(const void* x_split, int64_t x_ld, const void* w_split, const float* bias, float* y,
+                      int64_t y_ld, int N, int H, int W, int Cin6, int Cout, void* stream);
+int unetk_f32_convT2x2(const void* x_split, int64_t x_ld, const void* w_split, const float* bias, float* y,
+                       int64_t y_ld, int N, int H, int W, int Cin6, int Cout, void* stream);
+size_t unetk_f32_stats_partial_doubles(int64_t npix, int C);
+int unetk_f32_stats(const float* x, int64_t x_ld, int64_t npix, int C, double* partial, double* sums, void* stream);
+int unetk_f32_bn_split(const float* raw, int64_t raw_ld, const float* scale, const float* shift, void* split,
+                       int64_t split_ld, float* out_f32, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H,
+                       int W, int C, int relu, void* stream);
+int unetk_f32_head(const float* x, int64_t x_ld, const float* w, const float* bias, float* logits, int64_t npix, int C,
+                   void* stream);
 
 /* ---- test infrastructure: tcgen05 descriptor-semantics probe (not on the product path) ---------- */
 int unetk_probe_umma(const void* a, const void* b, float* d, int mode, int shift, int base_offset,

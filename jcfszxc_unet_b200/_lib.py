@@ -30,6 +30,8 @@ SIGNATURES = {
     "unetk_conv_stats_partial_floats": (_sz, [_i]),
     "unetk_conv3x3_fwd_bnstats": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv3x3_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv3x3_dgrad_colsum": (_i, [_vp, _i64, _vp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "unetk_sums_to_f32": (_i, [_vp, _i, _fp, _i, _vp]),
     "unetk_conv3x3s2_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv3x3s2_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv3x3s2_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
@@ -78,6 +80,14 @@ SIGNATURES = {
                                    _vp, _vp, _fp, _fp, _i, _i64, _i, _vp]),
     "unetk_gate_bwd_apply": (_i, [_vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp,
                                   _i64, _vp, _i64, _i64, _i, _vp]),
+    "unetk_f32_pack_split3": (_i, [_fp, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _vp]),
+    "unetk_f32_stem_conv3x3": (_i, [_fp, _i64, _i64, _i64, _i64, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_f32_conv3x3": (_i, [_vp, _i64, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_f32_convT2x2": (_i, [_vp, _i64, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_f32_stats_partial_doubles": (_sz, [_i64, _i]),
+    "unetk_f32_stats": (_i, [_fp, _i64, _i64, _i, _vp, _vp, _vp]),
+    "unetk_f32_bn_split": (_i, [_fp, _i64, _fp, _fp, _vp, _i64, _fp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_f32_head": (_i, [_fp, _i64, _fp, _fp, _fp, _i64, _i, _vp]),
     "unetk_probe_umma": (_i, [_vp, _vp, _fp, _i, _i, _i, _vp]),
     "unetk_probe_mma_rate": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
 }

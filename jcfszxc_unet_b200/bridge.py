@@ -49,6 +49,13 @@ def run_model(model: torch.nn.Module, builder, x: torch.Tensor) -> torch.Tensor:
     require_cuda_input(x, type(model).__name__)
     if x.dim() != 4:
         raise ValueError(f"expected [N,C,H,W], got {tuple(x.shape)}")
+    from . import get_precision
+    if get_precision() == "fp32":
+        from . import engine, f32
+        if builder is not engine.build_unet_plan:
+            raise NotImplementedError("fp32 mode covers the vanilla UNet (BASELINE.json configs[0]); "
+                                      f"{type(model).__name__} runs in bf16 only")
+        return f32.run_unet_f32(model, x)
     n, _, h, w = x.shape
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
     training_stats = model.training

@@ -32,13 +32,13 @@ static WgradDesc conv_wgrad_desc(const void* x, int64_t x_ld, const void* dy, in
 static int conv_fwd_like(const void* x, int64_t x_ld, const void* w, const float* bias, void* y, int64_t y_ld,
                          int N, int H, int W, int K, int ncols, int ksize, bool dgrad, void* stream,
                          float* stats_partial = nullptr, double* stats_sums = nullptr, int accumulate = 0,
-                         int a_step = 1) {
+                         int a_step = 1, int out_f32 = 0) {
   UNETK_CHECK(x && w && y && N > 0 && H > 0 && W > 0 && K > 0 && ncols > 0, -1, "conv: bad arguments");
   ConvGemmDesc d{};
   d.a = x; d.a_ld = x_ld; d.b = w; d.out = y; d.out_ld = y_ld; d.bias = bias;
   d.stats_partial = stats_partial; d.stats_sums = stats_sums;
   d.N = N; d.H = H; d.W = W; d.K = K; d.ncols = ncols; d.q_groups = 1;
-  d.a_step = a_step; d.out_step = 1; d.accumulate = accumulate;
+  d.a_step = a_step; d.out_step = 1; d.accumulate = accumulate; d.out_f32 = out_f32;
   d.taps = ksize * ksize; d.b_taps = d.taps;
   const int half = ksize / 2;
   for (int t = 0; t < d.taps; ++t) {
@@ -68,6 +68,15 @@ int unetk_conv3x3_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, voi
                         int N, int H, int W, int Cin, int Cout, void* stream) {
   return conv_fwd_like(dy, dy_ld, w_pack_t, nullptr, dx, dx_ld, N, H, W, Cout, Cin, 3, true, stream, nullptr, nullptr,
                        accumulate);
+}
+int unetk_conv3x3_dgrad_colsum(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
+                               float* partial, double* sums, int N, int H, int W, int Cin, int Cout, void* stream) {
+  UNETK_CHECK(partial && sums, -1, "conv3x3_dgrad_colsum: null statistics buffers");
+  return conv_fwd_like(dy, dy_ld, w_pack_t, nullptr, dx, dx_ld, N, H, W, Cout, Cin, 3, true, stream, partial, sums, 0);
+}
+int unetk_sums_to_f32(const double* sums, int n, float* out, int accumulate, void* stream) {
+  UNETK_CHECK(sums && out && n > 0, -1, "sums_to_f32: bad arguments");
+  return sums_to_f32_run(sums, n, out, accumulate, S(stream));
 }
 
 // ---- stride 2: forward = the same tap-GEMM with A coordinates 2*pos + (r-1, s-1) (TMA element stride 2)
@@ -416,6 +425,51 @@ int unetk_gate_bwd_apply(const void* raw_g, int64_t raw_g_ld, const void* raw_x,
               -1, "gate_bwd_apply: bad arguments");
   return gate_bwd_apply_run(raw_g, raw_g_ld, raw_x, raw_x_ld, sc_g, sh_g, sc_x, sh_x, w_psi, s, dz, sc1, coef1, coef_g,
                             coef_x, draw_g, draw_g_ld, draw_x, draw_x_ld, npix, F_int, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ fp32 mode
+int unetk_f32_pack_split3(const float* src, void* dst, int64_t sr, int64_t sk, int64_t st, int R, int K, int T,
+                          const int* slices, int n_slices, void* stream) {
+  UNETK_CHECK(src && dst && slices && R > 0 && K > 0 && T > 0, -1, "f32_pack_split3: bad arguments");
+  return f32_pack_split3_run(src, dst, sr, sk, st, R, K, T, slices, n_slices, S(stream));
+}
+int unetk_f32_stem_conv3x3(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w,
+                           const float* bias, float* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout,
+                           void* stream) {
+  UNETK_CHECK(x && w && y, -1, "f32_stem_conv3x3: null pointer");
+  return f32_stem_run(x, sn, sc, sh, sw, w, bias, y, y_ld, N, H, W, Cin, Cout, S(stream));
+}
+int unetk_f32_conv3x3(const void* x_split, int64_t x_ld, const void* w_split, const float* bias, float* y,
+                      int64_t y_ld, int N, int H, int W, int Cin6, int Cout, void* stream) {
+  return conv_fwd_like(x_split, x_ld, w_split, bias, y, y_ld, N, H, W, Cin6, Cout, 3, false, stream, nullptr, nullptr,
+                       0, 1, 1);
+}
+int unetk_f32_convT2x2(const void* x_split, int64_t x_ld, const void* w_split, const float* bias, float* y,
+                       int64_t y_ld, int N, int H, int W, int Cin6, int Cout, void* stream) {
+  UNETK_CHECK(x_split && w_split && y, -1, "f32_convT2x2: null pointer");
+  ConvGemmDesc d{};
+  d.a = x_split; d.a_ld = x_ld; d.b = w_split; d.b_taps = 1; d.out = y; d.out_ld = y_ld; d.bias = bias;
+  d.N = N; d.H = H; d.W = W; d.K = Cin6; d.ncols = Cout; d.q_groups = 4;
+  d.taps = 1; d.a_step = 1; d.out_step = 2; d.out_f32 = 1;
+  d.dh[0] = 0; d.dw[0] = 0; d.btap[0] = 0;
+  return conv_gemm_run(d, S(stream));
+}
+size_t unetk_f32_stats_partial_doubles(int64_t npix, int C) { return f32_stats_partial_doubles(npix, C); }
+int unetk_f32_stats(const float* x, int64_t x_ld, int64_t npix, int C, double* partial, double* sums, void* stream) {
+  UNETK_CHECK(x && partial && sums && npix > 0, -1, "f32_stats: bad arguments");
+  return f32_stats_run(x, x_ld, npix, C, partial, sums, S(stream));
+}
+int unetk_f32_bn_split(const float* raw, int64_t raw_ld, const float* scale, const float* shift, void* split,
+                       int64_t split_ld, float* out_f32, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H,
+                       int W, int C, int relu, void* stream) {
+  UNETK_CHECK(raw && (split || out_f32 || pooled) && N > 0 && H > 0 && W > 0, -1, "f32_bn_split: bad arguments");
+  return f32_bn_split_run(raw, raw_ld, scale, shift, split, split_ld, out_f32, out_ld, pooled, pooled_ld, N, H, W, C,
+                          relu, S(stream));
+}
+int unetk_f32_head(const float* x, int64_t x_ld, const float* w, const float* bias, float* logits, int64_t npix, int C,
+                   void* stream) {
+  UNETK_CHECK(x && w && logits && npix > 0 && C > 0, -1, "f32_head: bad arguments");
+  return f32_head_run(x, x_ld, w, bias, logits, npix, C, S(stream));
 }
 
 int unetk_probe_umma(const void* a, const void* b, float* d, int mode, int shift, int base_offset, void* stream) {

@@ -47,7 +47,7 @@ struct Cfg {
   static constexpr uint32_t kSmemBytes = kPipeBytes + 2 * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, bool F32OUT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN>;
@@ -69,7 +69,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    tma_prefetch_desc(&p.tmOut[0]);
+    if (!F32OUT) tma_prefetch_desc(&p.tmOut[0]);
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -191,6 +191,46 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      if constexpr (F32OUT) {
+        // fp32 output (f32path.cu): each thread owns one output pixel and writes its row of the accumulator as is
+        const int ph = h0 + (row >> p.tw_shift), pw = w0 + (row & (p.TW - 1));
+        const bool ok = ph < p.H && pw < p.W;
+        const long long Wout = static_cast<long long>(p.W) * p.out_step, Hout = static_cast<long long>(p.H) * p.out_step;
+        float* orow = p.out_f32 + ((static_cast<long long>(img) * Hout + static_cast<long long>(ph) * p.out_step + (q >> 1)) * Wout +
+                                   static_cast<long long>(pw) * p.out_step + (q & 1)) * p.out_ld;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          const int colbase = co0 + c * 32;
+          uint32_t r[32];
+          if (colbase < p.ncols) {   // warp-uniform
+            tmem_ld32(taddr + c * 32, r);
+            tmem_ld_wait();
+          }
+          if (c == BN / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          if (colbase >= p.ncols || !ok) continue;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const int col = colbase + v * 4;
+            if (col < p.ncols) {   // ncols is a multiple of 8
+              float4 o;
+              o.x = __uint_as_float(r[v * 4 + 0]);
+              o.y = __uint_as_float(r[v * 4 + 1]);
+              o.z = __uint_as_float(r[v * 4 + 2]);
+              o.w = __uint_as_float(r[v * 4 + 3]);
+              if (p.bias != nullptr) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              *reinterpret_cast<float4*>(orow + col) = o;
+            }
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int c = 0; c < BN / 64; ++c) {
         const int colbase = co0 + c * 64;
@@ -244,7 +284,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           bulk_commit();
         }
         if (p.stats_partial != nullptr && colbase + st_ch < p.ncols) {
-          // per-channel sum / sum of squares of the bf16 values just staged (rows outside the image excluded)
+          // per-channel sum / sum of squares of the bf16 values just staged (rows outside the image excluded).
+          // Measured and dropped: one 4-byte LDS per channel PAIR over 32 rows, fully unrolled with two independent
+          // chains per channel (64->64 @512^2 fwd 0.504 -> 0.596 ms): thin layers are bound by shared-memory
+          // bandwidth (the MMA re-reads A for every 64 output channels), not by this loop's latency.
           float s = 0.f, ss = 0.f;
           const int chunk16 = st_ch >> 3, within = (st_ch & 7) * 2;
           const int r_begin = st_half * 64;
@@ -271,7 +314,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       }
     }
     // all bulk stores of this thread must be complete before the CTA exits
-    if (leader) bulk_wait<0>();
+    if (leader && !F32OUT) bulk_wait<0>();
     if (p.stats_partial != nullptr) {
       // combine the two row-halves through the (now idle) staging buffer, then one partial row per CTA
       named_bar_sync(1, kEpiThreads);
@@ -307,18 +350,22 @@ __global__ void conv_stats_sums_kernel(const float* __restrict__ partial, int gr
   sums[i] = s;
 }
 
-template <int BN>
-int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
+template <int BN, bool F32OUT>
+int launch_t(const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    UNETK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UNETK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::kSmemBytes));
     configured = true;
   }
-  conv_gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  conv_gemm_kernel<BN, F32OUT><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
   UNETK_LAUNCHED();
   return 0;
+}
+template <int BN>
+int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
+  return p.out_f32 != nullptr ? launch_t<BN, true>(p, grid, stream) : launch_t<BN, false>(p, grid, stream);
 }
 
 int pick_bn(int ncols, int q_groups) {
@@ -357,7 +404,13 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   UNETK_CHECK(d.stats_sums == nullptr || (d.q_groups == 1 && d.stats_partial != nullptr), -1,
               "conv_gemm: fused statistics need q_groups == 1 and a partial buffer");
 
-  if (conv3x3_halo_eligible(d)) return conv3x3_halo_run(d, stream);  // wide images, <= 128 output channels
+  if (d.out_f32) {
+    UNETK_CHECK(!d.accumulate && d.stats_sums == nullptr, -1, "conv_gemm: the fp32 output path neither accumulates nor takes statistics");
+    UNETK_CHECK(d.out_ld % 4 == 0 && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0), -1,
+                "conv_gemm: fp32 output needs out_ld %% 4 == 0 and a 16-byte aligned bias");
+  } else if (conv3x3_halo_eligible(d)) {
+    return conv3x3_halo_run(d, stream);  // wide images, <= 128 output channels
+  }
 
   ConvGemmParams p{};
   const int BN = pick_bn(d.ncols, d.q_groups);
@@ -418,7 +471,11 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
     uint32_t es[3] = {1, 1, 1};
     if (int rc = make_tmap_bf16(&p.tmB, d.b, 3, dims, strides, box, es, true)) return rc;
   }
-  {
+  if (d.out_f32) {
+    p.out_f32 = static_cast<float*>(d.out);
+    p.out_ld = d.out_ld;
+    p.out_step = d.out_step;
+  } else {
     // Output seen on the grid of GEMM rows: pixel (h, w) of phase q lives at out[(s*h + qy) * Wout + s*w + qx].
     const int s = d.out_step;
     const int64_t Wout = static_cast<int64_t>(d.W) * s, Hout = static_cast<int64_t>(d.H) * s;

@@ -30,6 +30,7 @@ struct ConvGemmDesc {
   float* stats_partial;   // scratch, >= conv_gemm_stats_partial_floats(ncols) floats
   double* stats_sums;     // out: double [2][ncols] = per-channel (sum, sum of squares)
   int accumulate;         // != 0: out += result (TMA reduce-add, bf16) instead of out = result
+  int out_f32;            // != 0: `out` is fp32 (same NHWC view, out_ld in floats): the fp32-accuracy path of f32path.cu
 };
 
 // Kernel parameter block (passed by value, holds the TMA descriptors).
@@ -45,6 +46,9 @@ struct ConvGemmParams {
   int taps, kchunks, a_step;
   int accumulate;   // != 0: epilogue uses cp.reduce.async.bulk.tensor (.add) instead of a plain store
   int l2_prefetch;  // > 0: prefetch the A box of the tile `l2_prefetch` rounds ahead into L2
+  float* out_f32;   // non-null: fp32 output written straight from registers (no staging, no statistics)
+  long long out_ld; // fp32 path: floats between consecutive output pixels
+  int out_step;     // fp32 path: out pixel = out_step * pos + phase (2 for ConvTranspose fwd)
   int8_t dh[9], dw[9], btap[9];
 };
 

@@ -650,6 +650,16 @@ int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, f
   return 0;
 }
 
+__global__ void sums_to_f32_kernel(const double* __restrict__ sums, int n, float* __restrict__ out, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = accumulate ? out[i] + static_cast<float>(sums[i]) : static_cast<float>(sums[i]);
+}
+int sums_to_f32_run(const double* sums, int n, float* out, int accumulate, cudaStream_t s) {
+  sums_to_f32_kernel<<<(n + 127) / 128, 128, 0, s>>>(sums, n, out, accumulate);
+  UNETK_LAUNCHED();
+  return 0;
+}
+
 // grid for the Lanes-layout streaming kernels: one resident wave, >= 4 units per lane
 static int lanes_grid(int64_t units, int C, int blocks_per_sm) {
   int ppb = kThreads / (C / 8);

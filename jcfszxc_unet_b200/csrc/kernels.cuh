@@ -30,6 +30,7 @@ int bn_eval_fold_run(int C, const float* gamma, const float* beta, float eps, co
                      float* scale, float* shift, float* mean, float* invstd, cudaStream_t s);
 int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, float* out, int accumulate,
                cudaStream_t s);
+int sums_to_f32_run(const double* sums, int n, float* out, int accumulate, cudaStream_t s);
 int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const void* res,
                  int64_t res_ld, void* out, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W, int C,
                  int relu, cudaStream_t s);
@@ -97,4 +98,16 @@ int gate_bwd_apply_run(const void* rawg, int64_t rawg_ld, const void* rawx, int6
                        const float* dz, const float* sc1, const float* coef1, const float* coefg, const float* coefx,
                        void* drawg, int64_t drawg_ld, void* drawx, int64_t drawx_ld, int64_t npix, int F,
                        cudaStream_t st);
+// f32path.cu
+int f32_pack_split3_run(const float* src, void* dst, long long sr, long long sk, long long st, int R, int K, int T,
+                        const int* slices, int ns, cudaStream_t s);
+int f32_stem_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
+                 float* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
+size_t f32_stats_partial_doubles(long long npix, int C);
+int f32_stats_run(const float* x, int64_t ld, int64_t npix, int C, double* partial, double* sums, cudaStream_t s);
+int f32_bn_split_run(const float* raw, int64_t raw_ld, const float* scale, const float* shift, void* split,
+                     int64_t split_ld, float* out_f32, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H,
+                     int W, int C, int relu, cudaStream_t s);
+int f32_head_run(const float* x, int64_t ld, const float* w, const float* bias, float* logits, int64_t npix, int C,
+                 cudaStream_t s);
 }  // namespace unetk

@@ -61,6 +61,7 @@ class Plan:
         self._pack_table = self._pack_ptrs = None
         self._pack_tiles = 0
         self._g_init = {}          # gradient buffer -> set of channels already written during backward
+        self._g_writers = {}       # gradient buffer -> {channel: number of ops that write it during backward}
         self._p_init = set()       # parameters whose gradient was already written during backward
 
     # ---- allocation -----------------------------------------------------------------------------
@@ -102,9 +103,14 @@ class Plan:
         # gradient buffer writes it, every later one accumulates.  Tensors with several consumers (recurrent /
         # residual / dense-skip / gated variants) and shared weights (Recurrent_block) need no zero-fill pass.
         self._g_init.clear()
+        self._g_writers.clear()
         self._p_init.clear()
         for op in reversed(self.ops):
             op.plan_bwd(self)
+        if self.with_grad:
+            for op in self.ops:
+                if isinstance(op, ConvT2x2):
+                    op.fuse_bias_grad(self)
         return self
 
     def grad_acc(self, a: "Act") -> bool:
@@ -116,11 +122,21 @@ class Plan:
         c0 = a.g.storage_offset() % ld
         chans = set(range(c0, c0 + a.C))
         seen = self._g_init.setdefault((st, ld), set())
+        wr = self._g_writers.setdefault((st, ld), {})
+        for c in chans:
+            wr[c] = wr.get(c, 0) + 1
         hit = chans & seen
         if hit and hit != chans:
             raise RuntimeError("gradient buffer partially initialised: a builder wired overlapping channel slices")
         seen |= chans
         return bool(hit)
+
+    def sole_writer(self, a: "Act") -> bool:
+        """True if exactly one op writes each channel of `a.g` during backward (valid after finalize's walk)."""
+        st, ld = a.g.untyped_storage().data_ptr(), a.g.stride(2)
+        c0 = a.g.storage_offset() % ld
+        wr = self._g_writers.get((st, ld), {})
+        return all(wr.get(c, 0) == 1 for c in range(c0, c0 + a.C))
 
     def grad_written(self, a: "Act"):
         """Declare that `a.g` is filled from outside the plan (the loss gradient of a block-level plan)."""
@@ -267,6 +283,7 @@ class ConvBNReLU:
             if p is not None:
                 plan.register_param(p)
         self.acc_w = self.acc_b = self.acc_bn = self.acc_x = self.acc_res = False
+        self.colsum_sinks = []   # (channel offset in x, C, fp32 bias gradient, accumulate): see ConvT2x2.fuse_bias_grad
         plan.ops.append(self)
 
     def bind(self, plan):
@@ -367,7 +384,14 @@ class ConvBNReLU:
         if self.dbias is not None and self.bn is None:
             ops.colsum(dy, P.partial, self.dbias, self.acc_b)
         if not self.stem and self.x.g is not None:
-            ops.conv_dgrad(dy, self.pack.ba, self.x.g, self.k, self.acc_x, self.stride)
+            if self.colsum_sinks:
+                # the dgrad epilogue also sums its output per channel: the bias gradient of the ConvTranspose2d
+                # whose output is a channel slice of x (the concat buffer) comes for free
+                ops.conv_dgrad_colsum(dy, self.pack.ba, self.x.g, P.partial, P.sums)
+                for c0, c, db, acc in self.colsum_sinks:
+                    ops.sums_to_f32(P.sums, c0, c, db, acc)
+            else:
+                ops.conv_dgrad(dy, self.pack.ba, self.x.g, self.k, self.acc_x, self.stride)
 
 
 class ConvT2x2:
@@ -388,6 +412,7 @@ class ConvT2x2:
         if mod.bias is not None:
             plan.register_param(mod.bias)
         self.acc_w = self.acc_b = self.acc_x = False
+        self.fused_db = False
         plan.ops.append(self)
 
     def bind(self, plan):
@@ -401,6 +426,37 @@ class ConvT2x2:
         self.acc_b = plan.param_acc(self.mod.bias)
         if self.x.g is not None:
             self.acc_x = plan.grad_acc(self.x)
+
+    def fuse_bias_grad(self, plan):
+        """If `out` is a channel slice of a buffer whose gradient is written by exactly one 3x3 stride-1 conv dgrad
+        (the DoubleConv that consumes the concat, unet_parts.py:69-70), let that dgrad's epilogue produce the
+        bias gradient (the per-channel sum of out.g) instead of a separate column-sum pass."""
+        self.fused_db = False
+        if self.db is None or self.out.g is None or not plan.sole_writer(self.out):
+            return
+        og = self.out.g
+        st, ld = og.untyped_storage().data_ptr(), og.stride(2)
+        c0 = og.storage_offset() % ld
+        for op in plan.ops:
+            if not isinstance(op, ConvBNReLU) or op.stem or op.k != 3 or op.stride != 1 or op.x.g is None or op.acc_x:
+                continue
+            if op.x.C < 256:
+                # measured (B200, UNet 512^2): the statistics epilogue costs the 128-channel full-resolution dgrad
+                # +0.2 ms, more than the 0.13 ms column-sum pass it replaces; from 256 channels on it is a net gain
+                continue
+            xg = op.x.g
+            if xg.untyped_storage().data_ptr() != st or xg.stride(2) != ld or xg.shape[:3] != og.shape[:3]:
+                continue
+            x0 = xg.storage_offset() % ld
+            if xg.storage_offset() - x0 != og.storage_offset() - c0:
+                continue
+            if x0 <= c0 and c0 + self.cout <= x0 + op.x.C:
+                if (plan.partial.numel() < _lib.load().unetk_conv_stats_partial_floats(op.x.C)
+                        or plan.sums.numel() < 2 * op.x.C):
+                    return
+                op.colsum_sinks.append((c0 - x0, self.cout, self.db, self.acc_b))
+                self.fused_db = True
+                return
 
     def refresh(self, force=False):
         pass
@@ -416,7 +472,7 @@ class ConvT2x2:
         dyp, dyld = ops.nhwc(dy)
         _lib.call("unetk_convT2x2_wgrad", xp, xld, dyp, dyld, self.dw.data_ptr(), int(self.acc_w), self.x.N, self.x.H,
                   self.x.W, self.cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
-        if self.db is not None:
+        if self.db is not None and not self.fused_db:
             ops.colsum(dy, P.partial, self.db, self.acc_b)
         if self.x.g is not None:
             ops.convT_dgrad(dy, self.pack.ab, self.x.g, self.acc_x)

@@ -87,6 +87,24 @@ def conv_dgrad(dy, w_pack_t, dx, ksize: int = 3, accumulate: bool = False, strid
     return dx
 
 
+def conv_dgrad_colsum(dy, w_pack_t, dx, partial, sums):
+    """dx <- conv3x3^T(dy) and sums (fp64 [2,Cin]) <- per-channel (sum, sum sq) of the bf16 dx."""
+    n, h, w, cout = dy.shape
+    cin = dx.shape[3]
+    assert w_pack_t.shape == (9, cin, cout) and dx.shape[:3] == dy.shape[:3]
+    dyp, dyld = nhwc(dy)
+    dxp, dxld = nhwc(dx)
+    _lib.call("unetk_conv3x3_dgrad_colsum", dyp, dyld, w_pack_t.data_ptr(), dxp, dxld, partial.data_ptr(),
+              sums.data_ptr(), n, h, w, cin, cout, _stream())
+    return dx
+
+
+def sums_to_f32(sums, c0: int, c: int, out, accumulate=False):
+    """out[0:c] (+)= float(sums[c0:c0+c]) (sums: fp64 device vector)."""
+    assert sums.dtype == torch.float64 and out.numel() == c
+    _lib.call("unetk_sums_to_f32", sums.data_ptr() + 8 * c0, c, _f32(out), int(accumulate), _stream())
+
+
 def conv_fwd_stats(x, w_pack, bias, y, partial, sums, ksize: int = 3, stride: int = 1):
     """y <- conv(x) and sums (fp64 [2,Cout]) <- per-channel (sum, sum sq) of y; stride 2 only for 3x3.
     partial/sums None (stride 2 only) skips the statistics."""

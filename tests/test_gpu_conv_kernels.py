@@ -205,3 +205,86 @@ def test_convT2x2(n, h, w, cin, cout, ypad):
     wr = wt.clone().requires_grad_(True)
     F.conv_transpose2d(xr, wr, None, stride=2).backward(dy.float().permute(0, 3, 1, 2))
     assert (dw - wr.grad).abs().max().item() <= 2e-3 * wr.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,xpad,ypad", CONV_SHAPES[:4] + CONV_SHAPES[7:9])
+def test_conv3x3_dgrad_colsum(n, h, w, cin, cout, xpad, ypad):
+    """dgrad whose epilogue also returns the per-channel sums of dx (the ConvTranspose bias gradient when dx is the
+    gradient of a concat buffer): same dx as the plain dgrad, sums equal to the column sums of the stored bf16 dx."""
+    from jcfszxc_unet_b200 import _lib
+
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    g = torch.Generator(device=dev).manual_seed(7 + cin + cout)
+    _, dy = _nhwc_slice(n, h, w, cout, dev, *ypad)
+    dy.copy_(torch.randn(n, h, w, cout, device=dev, generator=g))
+    wt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * (1.0 / (3 * cout ** 0.5))
+    _, dx = _nhwc_slice(n, h, w, cin, dev, *xpad)
+    _, dx_ref = _nhwc_slice(n, h, w, cin, dev, *xpad)
+    _, w_pack_t = ops.pack_weight(wt, False, True)
+    partial = torch.empty(max(lib.unetk_conv_stats_partial_floats(cin), 4096), device=dev)
+    sums = torch.zeros(2 * cin, dtype=torch.float64, device=dev)
+    ops.conv_dgrad_colsum(dy, w_pack_t, dx, partial, sums)
+    ops.conv_dgrad(dy, w_pack_t, dx_ref, 3)
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx_ref)
+    col = dx.float().double().sum(dim=(0, 1, 2))
+    assert torch.allclose(sums[:cin], col, rtol=1e-5, atol=1e-4 * float(col.abs().max() + 1))
+    out = torch.full((cin // 2,), 3.0, device=dev)
+    ops.sums_to_f32(sums, cin // 2, cin // 2, out, accumulate=True)
+    torch.cuda.synchronize()
+    assert torch.allclose(out, 3.0 + col[cin // 2:].float(), rtol=1e-5, atol=1e-4 * float(col.abs().max() + 1))
+
+
+# ---- fp32 mode: six-term bf16 split on the tensor core (csrc/f32path.cu) against float64 ------------------------
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 32, 32, 64, 64), (2, 16, 24, 128, 256), (1, 20, 12, 72, 40),
+                                             (1, 8, 256, 64, 64), (1, 16, 16, 1024, 512)])
+def test_f32_conv3x3(n, h, w, cin, cout):
+    from jcfszxc_unet_b200 import f32
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(31 + cin + cout)
+    x = torch.randn(n, h, w, cin, device=dev, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * (1.0 / (3 * cin ** 0.5))
+    bias = torch.randn(cout, device=dev, generator=g)
+    y = f32.conv_f32(x, wt, bias)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), wt.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    ref32 = F.conv2d(x.permute(0, 3, 1, 2), wt, bias, padding=1).permute(0, 2, 3, 1)
+    err32 = (ref32.double() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"f32 conv3x3 {cin}->{cout}: ours vs fp64 {err:.3g}; torch fp32 (cuDNN) vs fp64 {err32:.3g}")
+    # the tensor core's fp32 accumulator truncates: ~3e-6 relative at K = 9*6*64, 3.6e-5 at K = 9*6*1024 (torch fp32: <1e-6); whole-network logits stay within 2.2e-5 (tests/test_gpu_unet.py), inside the 1e-4 budget
+    assert err <= 5e-5, err
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 16, 16, 128, 64), (2, 8, 8, 1024, 512)])
+def test_f32_convT2x2(n, h, w, cin, cout):
+    from jcfszxc_unet_b200 import f32
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(77 + cin + cout)
+    x = torch.randn(n, h, w, cin, device=dev, generator=g)
+    wt = torch.randn(cin, cout, 2, 2, device=dev, generator=g) * (1.0 / cin ** 0.5)
+    bias = torch.randn(cout, device=dev, generator=g)
+    y = f32.conv_f32(x, wt, bias, transposed=True)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(x.double().permute(0, 3, 1, 2), wt.double(), bias.double(), stride=2).permute(0, 2, 3, 1)
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"f32 convT2x2 {cin}->{cout}: ours vs fp64 {err:.3g}")
+    assert err <= 5e-5, err
+
+
+def test_f32_split_is_exact_to_24_bits():
+    from jcfszxc_unet_b200 import f32
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(1, 8, 8, 16, device=dev, generator=g) * torch.logspace(-6, 6, 16, device=dev)
+    s = f32.split_activation(x).float()
+    c = 16
+    hi, mid, lo = s[..., 0:c], s[..., 3 * c:4 * c], s[..., 5 * c:6 * c]
+    assert torch.equal(s[..., c:2 * c], hi) and torch.equal(s[..., 2 * c:3 * c], hi) and torch.equal(s[..., 4 * c:5 * c], mid)
+    rec = hi.double() + mid.double() + lo.double()
+    assert ((rec - x.double()).abs() <= x.abs().double() * 2.0 ** -23).all()

@@ -247,3 +247,70 @@ def test_unsupported_shapes_fail_loudly():
     m = _model().to(DEV)
     with pytest.raises(ValueError, match="divisible by 16"):
         m(torch.zeros(1, 3, 40, 40, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------ fp32 mode
+# north_star: "fp32 mode within 1e-4".  BASELINE.json configs[0]: vanilla UNet fp32 forward, batch 1, 3x512x512.
+F32_TOL = 1e-4
+
+
+def test_fp32_mode_matches_reference_golden():
+    """Golden fp32 logits of the UNMODIFIED reference (CPU, seed 42), train-mode and eval-mode BatchNorm."""
+    import jcfszxc_unet_b200 as U
+
+    g = np.load(os.path.join(GOLDEN, "unet_forward_seed42.npz"))
+    m = _model(42).to(DEV).train()
+    x = torch.from_numpy(g["images"]).to(DEV)
+    with U.precision("fp32"):
+        y = m(x)
+    ref = torch.from_numpy(g["logits_train"]).to(DEV)
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    print("fp32 mode, train BN: max rel", _rel(y, ref), "l2 rel", _l2rel(y, ref))
+    assert _rel(y, ref) <= F32_TOL and _l2rel(y, ref) <= F32_TOL, (_rel(y, ref), _l2rel(y, ref))
+    sd = m.state_dict()
+    assert int(sd["inc.double_conv.1.num_batches_tracked"]) == 1
+    assert torch.allclose(sd["inc.double_conv.1.running_mean"].cpu(), torch.from_numpy(g["running_mean_inc1"]), rtol=1e-4, atol=1e-6)
+    assert torch.allclose(sd["up4.conv.double_conv.4.running_var"].cpu(), torch.from_numpy(g["running_var_up4_4"]), rtol=1e-4, atol=1e-6)
+    m.eval()
+    with U.precision("fp32"):
+        ye = m(x)
+    ref_e = torch.from_numpy(g["logits_eval_after_1_train_fwd"]).to(DEV)
+    print("fp32 mode, eval BN: max rel", _rel(ye, ref_e), "l2 rel", _l2rel(ye, ref_e))
+    assert _rel(ye, ref_e) <= F32_TOL and _l2rel(ye, ref_e) <= F32_TOL, (_rel(ye, ref_e), _l2rel(ye, ref_e))
+    # the default precision is untouched outside the context
+    assert U.get_precision() == "bf16"
+
+
+@pytest.mark.parametrize("n,h,w,training", [(2, 64, 48, True), (1, 128, 96, False), (1, 512, 512, False)])
+def test_fp32_mode_vs_oracle(n, h, w, training):
+    """fp32 oracle (CPU) on the same weights and inputs; the last case is BASELINE.json configs[0] itself."""
+    import jcfszxc_unet_b200 as U
+    from oracle import unet_oracle as O
+
+    m = _model(42)
+    if not training:
+        # eval mode with non-trivial running statistics
+        gsd = torch.Generator().manual_seed(5)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_(0.2 * torch.randn(mod.num_features, generator=gsd))
+                mod.running_var.copy_(0.5 + torch.rand(mod.num_features, generator=gsd))
+    m = m.to(DEV).train(training)
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    images, _ = _inputs(13, n, h, w)
+    with torch.no_grad():
+        ref = O.unet_forward(images, sd, training=training)
+    with U.precision("fp32"):
+        y = m(images.to(DEV))
+    r, l2 = _rel(y.cpu(), ref), _l2rel(y.cpu(), ref)
+    print(f"fp32 mode vs oracle {n}x{h}x{w} training={training}: max rel {r:.3g} l2 rel {l2:.3g}")
+    assert r <= F32_TOL and l2 <= F32_TOL, (r, l2)
+
+
+def test_fp32_mode_rejects_other_models():
+    import jcfszxc_unet_b200 as U
+    from UNetFamily.AttentionUNet import AttentionUNet
+
+    m = AttentionUNet(3, 1).to(DEV)
+    with U.precision("fp32"), pytest.raises(NotImplementedError):
+        m(torch.rand(1, 3, 32, 32, device=DEV))
