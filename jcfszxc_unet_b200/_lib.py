@@ -11,7 +11,8 @@ import re
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libunetk.so"
+# UNETK_LIB: another build of the same ABI (A/B timing of kernel variants on one GPU box); default = the in-tree build
+LIB_PATH = Path(os.environ["UNETK_LIB"]).resolve() if os.environ.get("UNETK_LIB") else PKG / "libunetk.so"
 HEADER = PKG.parent / "include" / "unetk.h"
 
 _lib = None

@@ -41,7 +41,7 @@ struct HCfg {
   // (4 independent chains) and the epilogue adds the partial sums.
   static constexpr int kSplit = (BN == 64) ? 2 : 1;
   static constexpr uint32_t kTmemCols = 4 * BN * kSplit;       // 2 tiles x 2 rows x kSplit x BN
-  static constexpr uint32_t kSmemBytes = 2 * kHaloSlot + kBStages * kBBytes + kStaging * kStagingBytes + 1024 + 256;
+  static constexpr uint32_t kSmemBytes = 2 * kHaloSlot + kBStages * kBBytes + kStaging * kStagingBytes + 1024 + 256 + BN * 4 /*bias*/;
 };
 
 struct HaloParams {
@@ -52,6 +52,7 @@ struct HaloParams {
   float* stats_partial;
   int accumulate;  // != 0: out += tile (TMA reduce-add)
   int H, W, tiles_h, tiles_w, num_m_tiles, num_n_tiles, ncols, kchunks;
+  FastDiv fd_n_tiles, fd_tiles_w, fd_tiles_h;
   int resident;  // 1: all 9*kchunks weight tiles stay in smem for the whole kernel (they fit), no B ring
   int l2_prefetch;  // > 0: L2-prefetch the halo of the tile `l2_prefetch` rounds ahead
   int8_t dh[9], dw[9], btap[9];
@@ -105,10 +106,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       int as = 0;
       uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.num_n_tiles;
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int img = mt / (p.tiles_w * p.tiles_h);
+        uint32_t mt, tw, th, img, rest;
+        mt = p.fd_n_tiles.div(tile);
+        p.fd_tiles_w.divmod(mt, rest, tw);
+        p.fd_tiles_h.divmod(rest, img, th);
         const int h0 = th * 2, w0 = tw * kTW;
         if (p.l2_prefetch > 0) {
           // optional: pull the halo of the tile this CTA reaches `l2_prefetch` rounds from now into L2
@@ -240,18 +241,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     const int et = threadIdx.x - 64;
     const bool leader = (et == 0);
     const int st_ch = et & 63, st_half = et >> 6;
+    const uint32_t staging_a = smem_u32(staging);
+    const uint32_t row_sw = static_cast<uint32_t>(row & 7) << 4;   // 128B-swizzle XOR of this thread's staging row
+    uint32_t st_off[8];   // statistics: byte offset of channel st_ch in rows 8i+j of a staged chunk (swizzle resolved)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_off[j] = static_cast<uint32_t>(j * 128 + ((((st_ch >> 3) ^ j) << 4) + (st_ch & 7) * 2));
     float ssum[BN / 64], ssq[BN / 64];
 #pragma unroll
     for (int c = 0; c < BN / 64; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
     uint32_t chunk_ctr = 0;
     int it = 0;
+    // bias of this CTA's N tile -> shared memory once (see conv_gemm.cu)
+    const uint32_t bias_a = smem_u32(bars) + 256;
+    if (p.bias != nullptr) {
+      const int co_cta = static_cast<int>(blockIdx.x % p.num_n_tiles) * BN;
+      for (int i = et; i < BN; i += kEpiThreads) sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
+      named_bar_sync(1, kEpiThreads);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
-      const int nt = tile % p.num_n_tiles;
-      const int mt = tile / p.num_n_tiles;
-      const int tw = mt % p.tiles_w;
-      const int th = (mt / p.tiles_w) % p.tiles_h;
-      const int img = mt / (p.tiles_w * p.tiles_h);
+      uint32_t nt, mt, tw, th, img, rest;
+      p.fd_n_tiles.divmod(tile, mt, nt);
+      p.fd_tiles_w.divmod(mt, rest, tw);
+      p.fd_tiles_h.divmod(rest, img, th);
       const int h0 = th * 2, w0 = tw * kTW;
       const int co0 = nt * BN;
       const int valid_w = (p.W - w0 < kTW) ? (p.W - w0) : kTW;   // columns of this tile inside the image
@@ -259,14 +272,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 2 * BN * C::kSplit;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      // NOT unrolled: the epilogue is instruction-fetch bound (one warp per scheduler, nothing hides an L0 I-cache miss;
+      // stall_no_inst was 39 % of its samples with the 2-4x unrolled body), so the chunk body must stay resident
+#pragma unroll 1
+      for (int uc = 0; uc < 2 * (BN / 64); ++uc) {
+        const int u = (BN == 64) ? uc : (uc >> 1);
         const bool row_ok = (h0 + u) < p.H;
-#pragma unroll
-        for (int c = 0; c < BN / 64; ++c) {
+        {
+          const int c = (BN == 64) ? 0 : (uc & 1);
           const int colbase = co0 + c * 64;
           const bool live = row_ok && colbase < p.ncols;
-          const bool last = (u == 1) && (c == BN / 64 - 1);
+          const bool last = (uc == 2 * (BN / 64) - 1);
           uint8_t* buf = staging + (n_staging == 2 ? (chunk_ctr & 1u) : 0u) * kStagingBytes;
           if (live) {
             if (leader) { if (n_staging == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
@@ -296,7 +312,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
           }
           if (!live) continue;
           ++chunk_ctr;
-          uint8_t* rowp = buf + row * 128;
+          const uint32_t buf_a = staging_a + (buf - staging);
+          const uint32_t row_a = buf_a + row * 128;
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
             const uint32_t* src = (v < 4) ? &r0[v * 8] : &r1[(v - 4) * 8];
@@ -304,18 +321,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(src[j]);
             if (p.bias != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int col = colbase + v * 8 + j;
-                f[j] += (col < p.ncols) ? __ldg(p.bias + col) : 0.f;
-              }
+              const float4 b0 = lds128_f(bias_a + (c * 64 + v * 8) * 4), b1 = lds128_f(bias_a + (c * 64 + v * 8 + 4) * 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
             uint4 o;
             o.x = pack_bf16x2(f[0], f[1]);
             o.y = pack_bf16x2(f[2], f[3]);
             o.z = pack_bf16x2(f[4], f[5]);
             o.w = pack_bf16x2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(rowp + ((v ^ (row & 7)) << 4)) = o;
+            sts128(row_a + ((v << 4) ^ row_sw), o);
           }
           fence_proxy_async_smem();
           named_bar_sync(1, kEpiThreads);
@@ -325,20 +340,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
             bulk_commit();
           }
           if (p.stats_partial != nullptr && colbase + st_ch < p.ncols) {
-            float s = 0.f, ss = 0.f;
-            const int chunk16 = st_ch >> 3, within = (st_ch & 7) * 2;
+            float s = 0.f, ss = 0.f, s2 = 0.f, ss2 = 0.f;   // two chains
             const int r_begin = st_half * 64;
-            int r_end = r_begin + 64;
-            if (r_end > valid_w) r_end = valid_w;
-#pragma unroll 8
-            for (int r = r_begin; r < r_end; ++r) {
-              const uint16_t raw = *reinterpret_cast<const uint16_t*>(buf + r * 128 + ((chunk16 ^ (r & 7)) << 4) + within);
-              const float v = __uint_as_float(static_cast<uint32_t>(raw) << 16);
-              s += v;
-              ss = fmaf(v, v, ss);
+            uint32_t base = buf_a + r_begin * 128;
+#pragma unroll 1
+            for (int r8 = 0; r8 < 8; ++r8, base += 1024) {
+              uint32_t u[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) u[j] = lds_u16(base + st_off[j]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float v = __uint_as_float(u[j] << 16);
+                if (r_begin + r8 * 8 + j >= valid_w) v = 0.f;
+                if (j & 1) { s2 += v; ss2 = fmaf(v, v, ss2); } else { s += v; ss = fmaf(v, v, ss); }
+              }
             }
-            ssum[c] += s;
-            ssq[c] += ss;
+            s += s2;
+            ss += ss2;
+#pragma unroll
+            for (int k = 0; k < BN / 64; ++k) {   // c is a run-time value: predicated adds keep the sums in registers
+              if (k == c) { ssum[k] += s; ssq[k] += ss; }
+            }
           }
         }
       }
@@ -376,7 +398,7 @@ int launch(HaloParams& p, int grid, cudaStream_t stream) {
   }
   // weights resident when all 9*kchunks tiles fit next to the two halo slots and one staging buffer
   const uint32_t w_bytes = static_cast<uint32_t>(9 * p.kchunks) * C::kBBytes;
-  const uint32_t resident_smem = 2 * kHaloSlot + w_bytes + kStagingBytes + 1024 + 256;
+  const uint32_t resident_smem = 2 * kHaloSlot + w_bytes + kStagingBytes + 1024 + 256 + BN * 4;
   p.resident = (resident_smem <= 227 * 1024) ? 1 : 0;
   const uint32_t smem_bytes = p.resident ? resident_smem : C::kSmemBytes;
   conv3x3_halo_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(p);
@@ -406,6 +428,9 @@ int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.num_m_tiles = d.N * p.tiles_h * p.tiles_w;
   p.num_n_tiles = (d.ncols + BN - 1) / BN;
   p.ncols = d.ncols;
+  p.fd_n_tiles = FastDiv(p.num_n_tiles);
+  p.fd_tiles_w = FastDiv(p.tiles_w);
+  p.fd_tiles_h = FastDiv(p.tiles_h);
   p.kchunks = (d.K + 63) / 64;
   for (int t = 0; t < 9; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
   p.bias = d.bias;

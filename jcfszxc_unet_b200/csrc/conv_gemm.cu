@@ -44,7 +44,7 @@ struct Cfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 7);
   static constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: all powers of two >= 32
   static constexpr uint32_t kPipeBytes = kStages * kStageBytes;
-  static constexpr uint32_t kSmemBytes = kPipeBytes + 2 * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kSmemBytes = kPipeBytes + 2 * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
 
 template <int BN, bool F32OUT>
@@ -95,14 +95,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.num_n_tiles;
-        const int mt = tile / p.num_n_tiles;
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int img = mt / (p.tiles_w * p.tiles_h);
+        uint32_t nt, mt, tw, th, img, rest, q, ntq;
+        p.fd_n_tiles.divmod(tile, mt, nt);
+        p.fd_tiles_w.divmod(mt, rest, tw);
+        p.fd_tiles_h.divmod(rest, img, th);
+        p.fd_tiles_per_q.divmod(nt, q, ntq);
         const int h0 = th * p.TH, w0 = tw * p.TW;
-        const int q = nt / p.tiles_per_q;
-        const int brow = q * p.rows_per_q + (nt % p.tiles_per_q) * BN;
+        const int brow = q * p.rows_per_q + ntq * BN;
         if (p.l2_prefetch > 0) {
           // Streaming layers are latency-bound (the smem ring cannot hold enough bytes in flight to cover an HBM
           // miss): pull the A box of a tile this CTA will reach `l2_prefetch` rounds from now into L2.
@@ -170,22 +169,35 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int et = threadIdx.x - 64;         // 0..127
     const bool leader = (et == 0);
     const int st_ch = et & 63, st_half = et >> 6;  // statistics: this thread owns channel st_ch of every 64-chunk
+    const uint32_t staging_a = smem_u32(staging);
+    const uint32_t row_sw = static_cast<uint32_t>(row & 7) << 4;   // 128B-swizzle XOR of this thread's staging row
+    uint32_t st_off[8];   // statistics: byte offset of channel st_ch in rows 8i+j of a staged chunk (swizzle resolved)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_off[j] = static_cast<uint32_t>(j * 128 + ((((st_ch >> 3) ^ j) << 4) + (st_ch & 7) * 2));
     float ssum[BN / 64], ssq[BN / 64];
 #pragma unroll
     for (int c = 0; c < BN / 64; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
     uint32_t chunk_ctr = 0;
     int it = 0;
+    // bias of this CTA's N tile (the grid is a multiple of num_n_tiles: a CTA keeps its N tile) -> shared memory once;
+    // the per-element predicated __ldg it replaces was ~450 instructions of the chunk body
+    const uint32_t bias_a = smem_u32(bars) + 256;
+    if (!F32OUT && p.bias != nullptr) {
+      const int co_cta = static_cast<int>(blockIdx.x % p.num_n_tiles % p.tiles_per_q) * BN;
+      for (int i = et; i < BN; i += kEpiThreads) sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
+      named_bar_sync(1, kEpiThreads);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = tile % p.num_n_tiles;
-      const int mt = tile / p.num_n_tiles;
-      const int tw = mt % p.tiles_w;
-      const int th = (mt / p.tiles_w) % p.tiles_h;
-      const int img = mt / (p.tiles_w * p.tiles_h);
+      uint32_t nt, mt, tw, th, img, rest, q, ntq;
+      p.fd_n_tiles.divmod(tile, mt, nt);
+      p.fd_tiles_w.divmod(mt, rest, tw);
+      p.fd_tiles_h.divmod(rest, img, th);
+      p.fd_tiles_per_q.divmod(nt, q, ntq);
       const int h0 = th * p.TH, w0 = tw * p.TW;
-      const int q = nt / p.tiles_per_q;
-      const int co0 = (nt % p.tiles_per_q) * BN;
+      const int co0 = ntq * BN;
       const bool ragged = (h0 + p.TH > p.H) || (w0 + p.TW > p.W);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -231,7 +243,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         continue;
       }
-#pragma unroll
+      // NOT unrolled: the epilogue is instruction-fetch bound (one warp per scheduler, nothing hides an L0 I-cache
+      // miss; stall_no_inst was 39 % of its samples with the 2-4x unrolled body), so the loop body must stay resident
+#pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         const int colbase = co0 + c * 64;
         const bool live = colbase < p.ncols;  // false: whole chunk beyond the real channels (ragged N tile)
@@ -255,7 +269,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         if (!live) continue;
         ++chunk_ctr;
-        uint8_t* rowp = buf + row * 128;
+        const uint32_t buf_a = staging_a + (buf - staging);
+        const uint32_t row_a = buf_a + row * 128;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
           const uint32_t* src = (v < 4) ? &r0[v * 8] : &r1[(v - 4) * 8];
@@ -263,18 +278,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(src[j]);
           if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int col = colbase + v * 8 + j;
-              f[j] += (col < p.ncols) ? __ldg(p.bias + col) : 0.f;
-            }
+            const float4 b0 = lds128_f(bias_a + (c * 64 + v * 8) * 4), b1 = lds128_f(bias_a + (c * 64 + v * 8 + 4) * 4);
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
           }
           uint4 o;
           o.x = pack_bf16x2(f[0], f[1]);
           o.y = pack_bf16x2(f[2], f[3]);
           o.z = pack_bf16x2(f[4], f[5]);
           o.w = pack_bf16x2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(rowp + ((v ^ (row & 7)) << 4)) = o;  // 128B swizzle, conflict-free
+          sts128(row_a + ((v << 4) ^ row_sw), o);  // 128B swizzle, conflict-free
         }
         fence_proxy_async_smem();
         named_bar_sync(1, kEpiThreads);
@@ -288,28 +301,30 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           // Measured and dropped: one 4-byte LDS per channel PAIR over 32 rows, fully unrolled with two independent
           // chains per channel (64->64 @512^2 fwd 0.504 -> 0.596 ms): thin layers are bound by shared-memory
           // bandwidth (the MMA re-reads A for every 64 output channels), not by this loop's latency.
-          float s = 0.f, ss = 0.f;
-          const int chunk16 = st_ch >> 3, within = (st_ch & 7) * 2;
+          float s = 0.f, ss = 0.f, s2 = 0.f, ss2 = 0.f;   // two chains
           const int r_begin = st_half * 64;
-          if (!ragged) {
-#pragma unroll 8
-            for (int r = r_begin; r < r_begin + 64; ++r) {
-              const uint16_t raw = *reinterpret_cast<const uint16_t*>(buf + r * 128 + ((chunk16 ^ (r & 7)) << 4) + within);
-              const float v = __uint_as_float(static_cast<uint32_t>(raw) << 16);
-              s += v;
-              ss = fmaf(v, v, ss);
-            }
-          } else {
-            for (int r = r_begin; r < r_begin + 64; ++r) {
-              const bool ok = (h0 + (r >> p.tw_shift) < p.H) && (w0 + (r & (p.TW - 1)) < p.W);
-              const uint16_t raw = *reinterpret_cast<const uint16_t*>(buf + r * 128 + ((chunk16 ^ (r & 7)) << 4) + within);
-              const float v = ok ? __uint_as_float(static_cast<uint32_t>(raw) << 16) : 0.f;
-              s += v;
-              ss = fmaf(v, v, ss);
+          uint32_t base = buf_a + r_begin * 128;
+#pragma unroll 1
+          for (int r8 = 0; r8 < 8; ++r8, base += 1024) {
+            uint32_t u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = lds_u16(base + st_off[j]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v = __uint_as_float(u[j] << 16);
+              if (ragged) {
+                const int r = r_begin + r8 * 8 + j;
+                if (!((h0 + (r >> p.tw_shift) < p.H) && (w0 + (r & (p.TW - 1)) < p.W))) v = 0.f;
+              }
+              if (j & 1) { s2 += v; ss2 = fmaf(v, v, ss2); } else { s += v; ss = fmaf(v, v, ss); }
             }
           }
-          ssum[c] += s;
-          ssq[c] += ss;
+          s += s2;
+          ss += ss2;
+#pragma unroll
+          for (int k = 0; k < BN / 64; ++k) {   // c is a run-time value: predicated adds keep the sums in registers
+            if (k == c) { ssum[k] += s; ssq[k] += ss; }
+          }
         }
       }
     }
@@ -429,6 +444,10 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.tiles_h = (d.H + TH - 1) / TH;
   p.tiles_w = (d.W + TW - 1) / TW;
   p.num_m_tiles = d.N * p.tiles_h * p.tiles_w;
+  p.fd_n_tiles = FastDiv(p.num_n_tiles);
+  p.fd_tiles_w = FastDiv(p.tiles_w);
+  p.fd_tiles_h = FastDiv(p.tiles_h);
+  p.fd_tiles_per_q = FastDiv(p.tiles_per_q);
   p.taps = d.taps;
   p.kchunks = (d.K + kTileK - 1) / kTileK;
   p.a_step = d.a_step;

@@ -13,6 +13,8 @@ Buffer scheme (vanilla U-Net, reference UNetFamily/UNet.py:39-55):
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -440,9 +442,9 @@ class ConvT2x2:
         for op in plan.ops:
             if not isinstance(op, ConvBNReLU) or op.stem or op.k != 3 or op.stride != 1 or op.x.g is None or op.acc_x:
                 continue
-            if op.x.C < 256:
-                # measured (B200, UNet 512^2): the statistics epilogue costs the 128-channel full-resolution dgrad
-                # +0.2 ms, more than the 0.13 ms column-sum pass it replaces; from 256 channels on it is a net gain
+            if op.x.C < int(os.environ.get("UNETK_COLSUM_MIN_C", "128")):
+                # measured (B200, UNet 512^2, same box): 128-channel full-resolution dgrad 0.512 -> 0.597 ms with the
+                # statistics epilogue against a 0.13 ms column-sum pass; below 128 channels the pass is cheaper
                 continue
             xg = op.x.g
             if xg.untyped_storage().data_ptr() != st or xg.stride(2) != ld or xg.shape[:3] != og.shape[:3]:
