@@ -22,6 +22,7 @@
 #include "conv_gemm.cuh"
 #include "host_common.cuh"
 #include "ptx.cuh"
+#include "reduce2.cuh"
 
 #include <cstdlib>
 
@@ -356,13 +357,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 // sums[k][c] = sum over the CTAs that own channel c's N tile (CTA b owns tile b % num_n_tiles), fixed order
 __global__ void conv_stats_sums_kernel(const float* __restrict__ partial, int grid, int num_n_tiles, int BN, int C,
                                        double* __restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * C) return;
-  const int k = i / C, c = i % C;
+  const int i = blockIdx.x * kSum2Lanes + threadIdx.x;
+  const bool valid = i < 2 * C;
+  const int k = valid ? i / C : 0, c = valid ? i % C : 0;
   const int nt = c / BN, cc = c % BN;
-  double s = 0.0;
-  for (int b = nt; b < grid; b += num_n_tiles) s += partial[(static_cast<size_t>(b) * 2 + k) * BN + cc];
-  sums[i] = s;
+  const int count = (grid - nt + num_n_tiles - 1) / num_n_tiles;   // CTAs nt, nt + num_n_tiles, ...
+  const double s = sliced_ordered_sum(partial, count, valid, [&](int j) {
+    return (static_cast<size_t>(nt + j * num_n_tiles) * 2 + k) * BN + cc;
+  });
+  if (valid && threadIdx.y == 0) sums[i] = s;
 }
 
 template <int BN, bool F32OUT>
@@ -396,7 +399,7 @@ int pick_bn(int ncols, int q_groups) {
 
 int conv_stats_sums_launch(const float* partial, int grid, int num_n_tiles, int BN, int C, double* sums,
                            cudaStream_t stream) {
-  conv_stats_sums_kernel<<<(2 * C + 127) / 128, 128, 0, stream>>>(partial, grid, num_n_tiles, BN, C, sums);
+  conv_stats_sums_kernel<<<(2 * C + kSum2Lanes - 1) / kSum2Lanes, dim3(kSum2Lanes, kSum2Slices), 0, stream>>>(partial, grid, num_n_tiles, BN, C, sums);
   UNETK_LAUNCHED();
   return 0;
 }
@@ -517,9 +520,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   }
   if (rc) return rc;
   if (d.stats_sums != nullptr) {
-    conv_stats_sums_kernel<<<(2 * d.ncols + 127) / 128, 128, 0, stream>>>(d.stats_partial, grid, p.num_n_tiles, BN,
-                                                                        d.ncols, d.stats_sums);
-    UNETK_LAUNCHED();
+    return conv_stats_sums_launch(d.stats_partial, grid, p.num_n_tiles, BN, d.ncols, d.stats_sums, stream);
   }
   return 0;
 }

@@ -5,6 +5,8 @@
 // shared memory -> per-block partials, and finish with an ordered (deterministic) second stage.
 // Reference semantics replaced: nn.BatchNorm2d + nn.ReLU(inplace) + nn.MaxPool2d(2) inside
 // DoubleConv/Down (UNetFamily/utils/unet_parts.py:24-31,42-44) and their autograd backward.
+#include "reduce2.cuh"
+#include "fastdiv.cuh"
 #include "host_common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -95,11 +97,10 @@ __global__ void __launch_bounds__(kThreads) stats_kernel(const __nv_bfloat16* __
 // nn.BatchNorm2d (biased variance to normalise, unbiased for running_var, momentum 0.1).
 // Ordered (deterministic) second stage: sums[k][c] = sum over block partials, in double.
 __global__ void chan_sums_kernel(const float* __restrict__ partial, int nblk, int C, double* __restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * C) return;
-  double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += partial[static_cast<size_t>(b) * 2 * C + i];
-  sums[i] = s;
+  const int i = blockIdx.x * kSum2Lanes + threadIdx.x;
+  const bool valid = i < 2 * C;
+  const double s = sliced_ordered_sum(partial, nblk, valid, [&](int b) { return static_cast<size_t>(b) * 2 * C + i; });
+  if (valid && threadIdx.y == 0) sums[i] = s;
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double count,
@@ -144,11 +145,10 @@ __global__ void bn_eval_fold_kernel(int C, const float* gamma, const float* beta
 
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out,
                                        int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += partial[(static_cast<size_t>(b) * 2 + 0) * C + c];
-  out[c] = accumulate ? out[c] + static_cast<float>(s) : static_cast<float>(s);
+  const int c = blockIdx.x * kSum2Lanes + threadIdx.x;
+  const bool valid = c < C;
+  const double s = sliced_ordered_sum(partial, nblk, valid, [&](int b) { return (static_cast<size_t>(b) * 2 + 0) * C + c; });
+  if (valid && threadIdx.y == 0) out[c] = accumulate ? out[c] + static_cast<float>(s) : static_cast<float>(s);
 }
 
 // ------------------------------------------------------------------ forward apply
@@ -365,6 +365,7 @@ struct BnBwdArgs {
   const __nv_bfloat16* gp; int64_t gp_ld;   // may be null (pooled-resolution gradient)
   const float* scale; const float* shift; const float* mean; const float* invstd;
   int N, H, W, C, relu;
+  FastDiv fd_wu, fd_hu;   // pooled variants: division by W/2 and H/2 without a hardware divide
 };
 
 // masked gradient of one pixel x 8 channels: gm = (relu && !(bf16(raw*sc+sh) > 0)) ? 0 : g
@@ -473,13 +474,30 @@ __device__ __forceinline__ void bn_bwd_walk(const BnBwdArgs& A, const Lanes& L, 
   } else {
     const uint32_t Wu = static_cast<uint32_t>(A.W >> 1), Hu = static_cast<uint32_t>(A.H >> 1);
     const int64_t units = static_cast<int64_t>(A.N) * Hu * Wu;   // < 2^31 (checked on the host)
+    auto window = [&](int64_t u) -> int64_t {   // first pixel of window u
+      uint32_t wu, t, hu, n;
+      A.fd_wu.divmod(static_cast<uint32_t>(u), t, wu);
+      A.fd_hu.divmod(t, n, hu);
+      return (static_cast<int64_t>(n) * A.H + 2 * hu) * A.W + 2 * wu;
+    };
+    // The nine sectors of this thread's NEXT window are pulled into L2 while the current window is evaluated (the
+    // first version loaded, waited ~1 us for HBM and computed ~1 us, one window at a time: 45 % of the HBM peak on the
+    // 64-channel layer; holding two windows in registers instead spills at the 128-register budget of 2 blocks/SM).
     for (int64_t u = first; u < units; u += stride) {
-      const uint32_t uu = static_cast<uint32_t>(u);
-      const uint32_t wu = uu % Wu, t = uu / Wu;
-      const uint32_t hu = t % Hu, n = t / Hu;
-      const int64_t pix0 = (static_cast<int64_t>(n) * A.H + 2 * hu) * A.W + 2 * wu;
+      const int64_t pix0 = window(u);
       PoolWindow w;
       w.load(A, pix0, u, L.g);
+      const int64_t un = u + stride;
+      if (un < units) {
+        const int64_t pn = window(un);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t pix = pn + (q >> 1) * A.W + (q & 1);
+          prefetch_l2(A.raw + pix * A.raw_ld + L.g * 8);
+          if (A.g1) prefetch_l2(A.g1 + pix * A.g1_ld + L.g * 8);
+        }
+        prefetch_l2(A.gp + un * A.gp_ld + L.g * 8);
+      }
       w.visit(A, sc, sh, [&](int q, const float* gm, const float* r) { emit(pix0 + (q >> 1) * A.W + (q & 1), gm, r); });
     }
   }
@@ -609,7 +627,7 @@ int flat_grid(int64_t total) {
 size_t chan_partial_floats(int64_t units, int C) { return static_cast<size_t>(reduce_grid(units, C)) * 2 * C; }
 
 static int launch_sums(const float* partial, int nblk, int C, double* sums, cudaStream_t s) {
-  chan_sums_kernel<<<(2 * C + 127) / 128, 128, 0, s>>>(partial, nblk, C, sums);
+  chan_sums_kernel<<<(2 * C + kSum2Lanes - 1) / kSum2Lanes, dim3(kSum2Lanes, kSum2Slices), 0, s>>>(partial, nblk, C, sums);
   UNETK_LAUNCHED();
   return 0;
 }
@@ -645,7 +663,7 @@ int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, f
   const int grid = reduce_grid(npix, C);
   stats_kernel<<<grid, kThreads, reduce_smem(C, 2), s>>>(static_cast<const __nv_bfloat16*>(x), ld, npix, C, partial);
   UNETK_LAUNCHED();
-  colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, grid, C, out, accumulate);
+  colsum_finalize_kernel<<<(C + kSum2Lanes - 1) / kSum2Lanes, dim3(kSum2Lanes, kSum2Slices), 0, s>>>(partial, grid, C, out, accumulate);
   UNETK_LAUNCHED();
   return 0;
 }
@@ -736,7 +754,8 @@ static int bn_bwd_args(BnBwdArgs* A, const void* raw, int64_t raw_ld, const void
     UNETK_CHECK(static_cast<int64_t>(N) * (H / 2) * (W / 2) < (1ll << 31), -1, "bn_bwd: too many pooling windows");
   }
   *A = BnBwdArgs{static_cast<const __nv_bfloat16*>(raw), raw_ld, static_cast<const __nv_bfloat16*>(g1), g1_ld,
-                 static_cast<const __nv_bfloat16*>(gp), gp_ld, scale, shift, mean, invstd, N, H, W, C, relu};
+                 static_cast<const __nv_bfloat16*>(gp), gp_ld, scale, shift, mean, invstd, N, H, W, C, relu,
+                 FastDiv(static_cast<uint32_t>(W / 2 > 0 ? W / 2 : 1)), FastDiv(static_cast<uint32_t>(H / 2 > 0 ? H / 2 : 1))};
   return 0;
 }
 
