@@ -198,6 +198,7 @@ def run_reference_arm(args):
 CONV_FLOPS = {
     # name -> (index of N in args, taps, family)
     "unetk_conv3x3_fwd": (6, 9, "tap_gemm"), "unetk_conv3x3_dgrad": (6, 9, "tap_gemm"),
+    "unetk_conv3x3_dgrad_colsum": (7, 9, "tap_gemm"),
     "unetk_conv3x3_fwd_bnstats": (8, 9, "tap_gemm"), "unetk_conv1x1_fwd_bnstats": (8, 1, "tap_gemm"),
     "unetk_conv3x3s2_fwd": (8, 9, "tap_gemm"), "unetk_conv3x3s2_dgrad": (6, 9, "tap_gemm"),
     "unetk_conv1x1_fwd": (6, 1, "tap_gemm"), "unetk_conv1x1_dgrad": (6, 1, "tap_gemm"),
@@ -346,8 +347,10 @@ def run_ours(args):
         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
         "launches": dom["calls"], "avg_launch_ms": dom["ms"] / dom["calls"],
         "share_of_step": dom["ms"] / step_ms_eager,
-        "whole_step": {"achieved": value * gflop_img / 1e3, "frac": value * gflop_img / 1e3 / peaks["bf16_tflops_sustained"],
-                       "gflop_per_image": gflop_img},
+        # per GPU: images/s of ONE rank x algorithmic GFLOP per training image, against one GPU's peak
+        "whole_step": {"achieved": value / world * gflop_img / 1e3,
+                       "frac": value / world * gflop_img / 1e3 / peaks["bf16_tflops_sustained"],
+                       "gflop_per_image": gflop_img, "per": "gpu"},
         "families": {k: {"calls": v["calls"], "ms": round(v["ms"], 3),
                          **({"tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)} if v["flops"] else {})}
                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},

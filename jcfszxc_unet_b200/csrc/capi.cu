@@ -172,8 +172,9 @@ size_t unetk_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ta
   WgradDesc d = conv_wgrad_desc(nullptr, 0, nullptr, 0, nullptr, 0, N, H, W, Cin, Cout, ksize);
   size_t need = wgrad_workspace_bytes(d);
   if (taps == 9) {
-    const size_t need3 = wgrad3x3_workspace_bytes(N, H, W, Cout, Cin);
+    const size_t need3 = wgrad3x3_workspace_bytes(N, H, W, Cout, Cin), need3f = wgrad3x3_workspace_bytes(N, H, W, Cin, Cout);
     if (need3 > need) need = need3;
+    if (need3f > need) need = need3f;
   }
   return need;
 }
@@ -182,7 +183,10 @@ int unetk_conv3x3_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_
                         int N, int H, int W, int Cin, int Cout, void* workspace, size_t ws_bytes, void* stream) {
   UNETK_CHECK(x && dy && dw, -1, "conv3x3_wgrad: null pointer");
   // halo-reuse kernel (one activation load per filter row); shapes it does not cover use the per-tap kernel
-  const int rc3 = wgrad3x3_run(dy, dy_ld, x, x_ld, dw, accumulate, N, H, W, Cout, Cin, workspace, ws_bytes, S(stream));
+  // Cout <= 64 < Cin: swapped operands (all 128 MMA rows carry input channels), see wgrad3x3_run
+  const bool flip = Cout <= 64 && Cin >= 128;
+  const int rc3 = flip ? wgrad3x3_run(x, x_ld, dy, dy_ld, dw, accumulate, N, H, W, Cin, Cout, workspace, ws_bytes, S(stream), 1)
+                       : wgrad3x3_run(dy, dy_ld, x, x_ld, dw, accumulate, N, H, W, Cout, Cin, workspace, ws_bytes, S(stream));
   if (rc3 <= 0) return rc3;
   WgradDesc d = conv_wgrad_desc(x, x_ld, dy, dy_ld, dw, accumulate, N, H, W, Cin, Cout, 3);
   return wgrad_run(d, workspace, ws_bytes, S(stream));

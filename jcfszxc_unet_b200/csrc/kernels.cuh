@@ -12,7 +12,7 @@ int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, 
 // wgrad3x3.cu
 size_t wgrad3x3_workspace_bytes(int N, int H, int W, int M, int Nn);
 int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, float* dw, int accumulate, int N, int H,
-                 int W, int M, int Nn, void* workspace, size_t ws_bytes, cudaStream_t stream);
+                 int W, int M, int Nn, void* workspace, size_t ws_bytes, cudaStream_t stream, int flip = 0);
 // stem.cu
 int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
                  void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s);

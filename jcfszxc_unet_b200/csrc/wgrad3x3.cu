@@ -241,13 +241,29 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
   const uint32_t stage = 2 * kPBoxBytes + (pl->NT / 64) * pl->q_box_bytes;
   pl->smem_bytes = stages * stage + 1024 + 256;
   if (pl->smem_bytes > 227 * 1024) return false;
-  // items = 3 * m_tiles * n_tiles * ksplit: aim at ~2 items per SM, at least 8 k-blocks each
+  // items = 3 * m_tiles * n_tiles * ksplit run in waves of num_sms CTAs.  Pick the pixel split that minimises
+  //   waves * (k-blocks per item + ~12 k-blocks of epilogue) + 2 * ksplit (partial write + reduce),
+  // at least 8 k-blocks per item.  (1024 -> 1024 @32^2, 192 base items: the old "~2 items per SM" rule chose 1 split =
+  // two waves at 65 % occupancy; 3 splits make 3.9 waves.)
   const int base = 3 * pl->m_tiles * pl->n_tiles;
-  int ks = (2 * num_sms()) / base;
   const int cap = pl->pix_tiles / 8 > 0 ? pl->pix_tiles / 8 : 1;
-  if (ks > cap) ks = cap;
-  if (ks < 1) ks = 1;
-  pl->ksplit = ks;
+  if (base < 12) {
+    // few (m, n) tiles = the wide-image thin-channel layers, bound by the L2 -> SM path: measured on B200 (same box),
+    // one wave of long items is 10-50 % SLOWER there than two waves of ~2 items per SM (64 -> 64 @512^2: 0.56 vs
+    // 0.61-0.69 ms; 64 -> 128 @256^2: 0.17 vs 0.27 ms), so those keep the old rule.
+    int ks = (2 * num_sms()) / base;
+    if (ks > cap) ks = cap;
+    pl->ksplit = ks < 1 ? 1 : ks;
+    return true;
+  }
+  int best = 1;
+  long best_cost = -1;
+  for (int ks = 1; ks <= cap && ks <= 48; ++ks) {
+    const long waves = (static_cast<long>(base) * ks + num_sms() - 1) / num_sms();
+    const long cost = waves * ((pl->pix_tiles + ks - 1) / ks + 12) + 2L * ks;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ks; }
+  }
+  pl->ksplit = best;
   return true;
 }
 
@@ -274,9 +290,12 @@ size_t wgrad3x3_workspace_bytes(int N, int H, int W, int M, int Nn) {
   return static_cast<size_t>(pl.ksplit) * 9 * M * Nn * sizeof(float);
 }
 
-// dw[co][ci][3][3] (+)= dY (M = Cout channels) x X (Nn = Cin channels); returns 1 if the shape is not eligible
+// dw[co][ci][3][3] (+)= dY (M = Cout channels) x X (Nn = Cin channels); returns 1 if the shape is not eligible.
+// flip != 0: the operands are passed SWAPPED (first = X with M = Cin rows, second = dY with Nn = Cout columns), which
+// computes tap (2-r, 2-s) of the transposed filter: sum_px X[px] dY[px + d] = sum_px' dY[px'] X[px' - d].  Used when
+// Cout = 64 < Cin: the 128 MMA rows are then all real input channels instead of 64 output channels + 64 empty rows.
 int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, float* dw, int accumulate, int N, int H,
-                 int W, int M, int Nn, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+                 int W, int M, int Nn, void* workspace, size_t ws_bytes, cudaStream_t stream, int flip) {
   W3Plan pl;
   if (!make_plan(N, H, W, M, Nn, &pl)) return 1;
   UNETK_CHECK(dy_ld % 8 == 0 && x_ld % 8 == 0, -1, "wgrad3x3: pixel strides must be multiples of 8");
@@ -301,6 +320,8 @@ int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, flo
   if (int rc = mk(&p.tmQ, x, x_ld, Nn, 2)) return rc;
   int rc = (pl.NT == 128) ? launch<128>(p, pl, stream) : launch<64>(p, pl, stream);
   if (rc) return rc;
+  if (flip)   // rows are input channels (stride 9), columns output channels (stride Cin*9), taps reversed
+    return wgrad_reduce_launch(p.partial, dw + 8, pl.ksplit, 9, M, Nn, 9, static_cast<int64_t>(M) * 9, -1, accumulate, stream);
   return wgrad_reduce_launch(p.partial, dw, pl.ksplit, 9, M, Nn, static_cast<int64_t>(Nn) * 9, 9, 1, accumulate, stream);
 }
 

@@ -129,7 +129,15 @@ def test_conv3x3_dgrad(n, h, w, cin, cout, xpad, ypad):
     _close(dx, ref, "conv3x3_dgrad")
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout,xpad,ypad", CONV_SHAPES)
+WGRAD_EXTRA = [
+    # Cout <= 64 < Cin: the weight-gradient GEMM runs with swapped operands and reversed taps (wgrad3x3_run, flip)
+    (1, 16, 32, 128, 64, (0, 0), (0, 0)),
+    (2, 9, 20, 136, 40, (8, 0), (0, 24)),
+    (1, 4, 128, 256, 64, (0, 0), (64, 0)),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,xpad,ypad", CONV_SHAPES + WGRAD_EXTRA)
 def test_conv3x3_wgrad(n, h, w, cin, cout, xpad, ypad):
     ops = _ops()
     dev = torch.device("cuda:0")
