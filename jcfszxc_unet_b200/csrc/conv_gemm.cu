@@ -406,6 +406,8 @@ int conv_stats_sums_launch(const float* partial, int grid, int num_n_tiles, int 
 
 bool conv3x3_halo_eligible(const ConvGemmDesc& d);
 int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream);
+bool conv3x3_rows_eligible(const ConvGemmDesc& d);
+int conv3x3_rows_run(const ConvGemmDesc& d, cudaStream_t stream);
 
 size_t conv_gemm_stats_partial_floats(int ncols) {
   return static_cast<size_t>(num_sms()) * 2 * pick_bn(ncols, 1);
@@ -426,6 +428,8 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
     UNETK_CHECK(!d.accumulate && d.stats_sums == nullptr, -1, "conv_gemm: the fp32 output path neither accumulates nor takes statistics");
     UNETK_CHECK(d.out_ld % 4 == 0 && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0), -1,
                 "conv_gemm: fp32 output needs out_ld %% 4 == 0 and a 16-byte aligned bias");
+  } else if (conv3x3_rows_eligible(d)) {
+    return conv3x3_rows_run(d, stream);  // wide images, <= 64 output channels: filter rows stacked in N
   } else if (conv3x3_halo_eligible(d)) {
     return conv3x3_halo_run(d, stream);  // wide images, <= 128 output channels
   }

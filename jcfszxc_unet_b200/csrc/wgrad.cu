@@ -207,6 +207,32 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
+// Many pixel splits over a small filter (the 64-channel layers: 98 splits of a 64 x 64 x 9 filter): a 32 x 32 block
+// owns 32 (m, n) positions of one tap, slice y adds the splits y, y+32, ... and row 0 adds the 32 slice sums in order.
+__global__ void wgrad_reduce_sliced_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ksplit,
+                                           int taps, int M, int Nn, int64_t sm, int64_t sn, int64_t st, int accumulate,
+                                           FastDiv fd_n) {
+  __shared__ float red[32][33];
+  const uint32_t plane = static_cast<uint32_t>(M) * static_cast<uint32_t>(Nn);
+  const uint32_t j = blockIdx.x * 32 + threadIdx.x;
+  const int tap = blockIdx.y;
+  float s = 0.f;
+  if (j < plane) {
+    for (int k = threadIdx.y; k < ksplit; k += 32) s += __ldg(partial + (static_cast<size_t>(k) * taps + tap) * plane + j);
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < plane) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int y = 0; y < 32; ++y) t += red[y][threadIdx.x];
+    uint32_t m, n;
+    fd_n.divmod(j, m, n);
+    float* o = dw + m * sm + n * sn + tap * st;
+    *o = accumulate ? (*o + t) : t;
+  }
+}
+
 template <int BN>
 int launch(const WgradParams& p, cudaStream_t stream) {
   using C = WCfg<BN>;
@@ -250,6 +276,12 @@ int wgrad_reduce_launch(const float* partial, float* dw, int ksplit, int taps, i
   int blocks = static_cast<int>((plane + 255) / 256);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   const FastDiv fd(static_cast<uint32_t>(Nn));
+  if (ksplit >= 8) {
+    wgrad_reduce_sliced_kernel<<<dim3(static_cast<unsigned>((plane + 31) / 32), taps), dim3(32, 32), 0, stream>>>(
+        partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd);
+    UNETK_LAUNCHED();
+    return 0;
+  }
   switch (taps) {
     case 9: wgrad_reduce_kernel<9><<<blocks, 256, 0, stream>>>(partial, dw, ksplit, M, Nn, sm, sn, st, accumulate, fd); break;
     case 4: wgrad_reduce_kernel<4><<<blocks, 256, 0, stream>>>(partial, dw, ksplit, M, Nn, sm, sn, st, accumulate, fd); break;

@@ -16,6 +16,8 @@
 // that kernel re-read dY and X nine times and was HBM-bound on the 512^2 layers (138 TFLOP/s, 64->64).
 // Accumulators: 3 taps x NT fp32 columns in TMEM; fp32 partials + ordered reduce (deterministic).
 #include "host_common.cuh"
+
+#include <cstdlib>
 #include "ptx.cuh"
 #include "wgrad.cuh"
 
@@ -247,10 +249,12 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
   // two waves at 65 % occupancy; 3 splits make 3.9 waves.)
   const int base = 3 * pl->m_tiles * pl->n_tiles;
   const int cap = pl->pix_tiles / 8 > 0 ? pl->pix_tiles / 8 : 1;
-  if (base < 12) {
-    // few (m, n) tiles = the wide-image thin-channel layers, bound by the L2 -> SM path: measured on B200 (same box),
-    // one wave of long items is 10-50 % SLOWER there than two waves of ~2 items per SM (64 -> 64 @512^2: 0.56 vs
-    // 0.61-0.69 ms; 64 -> 128 @256^2: 0.17 vs 0.27 ms), so those keep the old rule.
+  static int rule = -1;
+  if (rule < 0) { const char* e = getenv("UNETK_WGRAD3_RULE"); rule = e ? atoi(e) : 0; }
+  if (base < 12 && rule == 0) {
+    // few (m, n) tiles = the wide-image thin-channel layers (L2 -> SM bound): ~2 items per SM.  The cost rule below
+    // would pick one wave of items twice as long; measured on the same box it makes no difference there
+    // (UNet step: 5.79-5.81 vs 5.61-5.80 ms over the 17 weight gradients), so these keep the simple rule.
     int ks = (2 * num_sms()) / base;
     if (ks > cap) ks = cap;
     pl->ksplit = ks < 1 ? 1 : ks;
