@@ -209,23 +209,24 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 
 // Many pixel splits over a small filter (the 64-channel layers: 98 splits of a 64 x 64 x 9 filter): a 32 x 32 block
 // owns 32 (m, n) positions of one tap, slice y adds the splits y, y+32, ... and row 0 adds the 32 slice sums in order.
+template <int S>   // S slices of the split axis per block (8, 16 or 32)
 __global__ void wgrad_reduce_sliced_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ksplit,
                                            int taps, int M, int Nn, int64_t sm, int64_t sn, int64_t st, int accumulate,
                                            FastDiv fd_n) {
-  __shared__ float red[32][33];
+  __shared__ float red[S][33];
   const uint32_t plane = static_cast<uint32_t>(M) * static_cast<uint32_t>(Nn);
   const uint32_t j = blockIdx.x * 32 + threadIdx.x;
   const int tap = blockIdx.y;
   float s = 0.f;
   if (j < plane) {
-    for (int k = threadIdx.y; k < ksplit; k += 32) s += __ldg(partial + (static_cast<size_t>(k) * taps + tap) * plane + j);
+    for (int k = threadIdx.y; k < ksplit; k += S) s += __ldg(partial + (static_cast<size_t>(k) * taps + tap) * plane + j);
   }
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && j < plane) {
     float t = 0.f;
-#pragma unroll 8
-    for (int y = 0; y < 32; ++y) t += red[y][threadIdx.x];
+#pragma unroll
+    for (int y = 0; y < S; ++y) t += red[y][threadIdx.x];
     uint32_t m, n;
     fd_n.divmod(j, m, n);
     float* o = dw + m * sm + n * sn + tap * st;
@@ -277,8 +278,13 @@ int wgrad_reduce_launch(const float* partial, float* dw, int ksplit, int taps, i
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   const FastDiv fd(static_cast<uint32_t>(Nn));
   if (ksplit >= 8) {
-    wgrad_reduce_sliced_kernel<<<dim3(static_cast<unsigned>((plane + 31) / 32), taps), dim3(32, 32), 0, stream>>>(
-        partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd);
+    const dim3 grid(static_cast<unsigned>((plane + 31) / 32), taps);
+    if (ksplit >= 64)
+      wgrad_reduce_sliced_kernel<32><<<grid, dim3(32, 32), 0, stream>>>(partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd);
+    else if (ksplit >= 24)
+      wgrad_reduce_sliced_kernel<16><<<grid, dim3(32, 16), 0, stream>>>(partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd);
+    else
+      wgrad_reduce_sliced_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd);
     UNETK_LAUNCHED();
     return 0;
   }

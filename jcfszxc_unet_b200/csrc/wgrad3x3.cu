@@ -35,6 +35,8 @@ constexpr uint32_t kPBoxBytes = kPix * 128;  // [64 px][64 ch] bf16
 struct W3Params {
   CUtensorMap tmP;  // dY: dims (M, W, H, N), box (64, TW, TH, 1)
   CUtensorMap tmQ;  // X : dims (Nn, W, H, N), box (64, TW+2, TH, 1)
+  CUtensorMap tmP2; // paired mode: dY box (64, 64, 2, 1) = two image rows, one per filter row of the pair
+  int paired;       // 1: M <= 64 -> the two halves of the 128 MMA rows carry two FILTER ROWS (see make_plan)
   float* partial;   // [ksplit][9][M][Nn]
   int TH, TW, tiles_h, tiles_w, pix_tiles;
   int m_tiles, n_tiles, ksplit;
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int items_per_split = 3 * p.m_tiles * p.n_tiles;
+  const int items_per_split = p.paired ? 2 * p.n_tiles : 3 * p.m_tiles * p.n_tiles;
   const int num_items = items_per_split * p.ksplit;
 
   if (warp == 0) {
@@ -94,8 +96,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       const uint32_t tx = 2 * kPBoxBytes + C::kQBoxes * p.q_tx_bytes;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int nt = item % p.n_tiles;
-        const int mt = (item / p.n_tiles) % p.m_tiles;
-        const int r = (item / (p.n_tiles * p.m_tiles)) % 3;
+        const int mt = p.paired ? 0 : (item / p.n_tiles) % p.m_tiles;
+        // paired: r is the filter-row GROUP g (0: rows 1|0, 1: row 2) and the X row is the k-block's own row
+        const int r = p.paired ? (item / p.n_tiles) % 2 : (item / (p.n_tiles * p.m_tiles)) % 3;
         const int ks = item / items_per_split;
         const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
         const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
@@ -108,6 +111,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
           uint8_t* sp = smem + stage * stage_bytes;
           uint8_t* sq = sp + 2 * kPBoxBytes;
           mbar_expect_tx(&full_bar[stage], tx);
+          if (p.paired) {
+            // X row q = h0 meets dY row q-r+1 under filter row r: group 0 loads dY rows (q, q+1) = filter rows (1, 0),
+            // group 1 loads rows (q-1, q) = filter rows (2, 1 [discarded]); rows outside the image read as zero
+            tma_load_4d(sp, &p.tmP2, &full_bar[stage], 0, w0, h0 - r, img);
+#pragma unroll
+            for (int b = 0; b < C::kQBoxes; ++b)
+              tma_load_4d(sq + b * p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT + b * 64, w0 - 1, h0, img);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
 #pragma unroll
           for (int b = 0; b < 2; ++b)
             tma_load_4d(sp + b * kPBoxBytes, &p.tmP, &full_bar[stage], mt * 128 + b * 64, w0, h0, img);
@@ -178,10 +191,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int nt = item % p.n_tiles;
-      const int mt = (item / p.n_tiles) % p.m_tiles;
-      const int r = (item / (p.n_tiles * p.m_tiles)) % 3;
+      const int mt = p.paired ? 0 : (item / p.n_tiles) % p.m_tiles;
+      int r = p.paired ? (item / p.n_tiles) % 2 : (item / (p.n_tiles * p.m_tiles)) % 3;
       const int ks = item / items_per_split;
-      const int m = mt * 128 + row;
+      int m = mt * 128 + row;
+      if (p.paired) {
+        // accumulator rows 0-63 = first dY row of the pair, 64-127 = second: group 0 -> filter rows (1, 0), group 1 -> (2, -)
+        const int half = row >> 6;
+        m = row & 63;
+        if (r == 0) r = 1 - half;
+        else { r = 2; if (half) m = p.M; }   // second half of group 1 repeats filter row 1: not stored
+      }
       mbar_wait(tfull_bar, it & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -221,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 }
 
 struct W3Plan {
-  int NT, TH, TW, tiles_h, tiles_w, pix_tiles, m_tiles, n_tiles, ksplit;
+  int NT, TH, TW, tiles_h, tiles_w, pix_tiles, m_tiles, n_tiles, ksplit, paired;
   uint32_t q_box_bytes, q_tx_bytes, smem_bytes;
 };
 
@@ -247,7 +267,13 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
   //   waves * (k-blocks per item + ~12 k-blocks of epilogue) + 2 * ksplit (partial write + reduce),
   // at least 8 k-blocks per item.  (1024 -> 1024 @32^2, 192 base items: the old "~2 items per SM" rule chose 1 split =
   // two waves at 65 % occupancy; 3 splits make 3.9 waves.)
-  const int base = 3 * pl->m_tiles * pl->n_tiles;
+  // M <= 64 (64-channel dY): half of the 128 MMA rows would be empty (59 % tensor-pipe activity for 30 % useful work,
+  // profiles/r01_ncu_wgrad3x3.txt).  With one image row per k-block (TW = 64) the second half is given the NEXT dY row,
+  // i.e. another filter row against the same X halo row: 2 work items per pixel range instead of 3.
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* e = getenv("UNETK_WGRAD3_PAIR"); pair_env = e ? atoi(e) : 1; }
+  pl->paired = (pair_env && M <= 64 && pl->NT == 64 && pl->TW == 64 && pl->TH == 1) ? 1 : 0;
+  const int base = pl->paired ? 2 * pl->n_tiles : 3 * pl->m_tiles * pl->n_tiles;
   const int cap = pl->pix_tiles / 8 > 0 ? pl->pix_tiles / 8 : 1;
   static int rule = -1;
   if (rule < 0) { const char* e = getenv("UNETK_WGRAD3_RULE"); rule = e ? atoi(e) : 0; }
@@ -278,7 +304,7 @@ int launch(const W3Params& p, const W3Plan& pl, cudaStream_t stream) {
     UNETK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int items = 3 * pl.m_tiles * pl.n_tiles * pl.ksplit;
+  const int items = (pl.paired ? 2 * pl.n_tiles : 3 * pl.m_tiles * pl.n_tiles) * pl.ksplit;
   const int grid = items < num_sms() ? items : num_sms();
   wgrad3x3_kernel<NT><<<grid, kThreads, pl.smem_bytes, stream>>>(p);
   UNETK_LAUNCHED();
@@ -311,6 +337,7 @@ int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, flo
   p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.ksplit = pl.ksplit;
   p.M = M; p.Nn = Nn;
   p.q_box_bytes = pl.q_box_bytes; p.q_tx_bytes = pl.q_tx_bytes;
+  p.paired = pl.paired;
   auto mk = [&](CUtensorMap* tm, const void* base, int64_t ld, int C, int halo) -> int {
     uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                         static_cast<uint64_t>(N)};
@@ -321,6 +348,14 @@ int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, flo
     return make_tmap_bf16(tm, base, 4, dims, strides, box, es, true);
   };
   if (int rc = mk(&p.tmP, dy, dy_ld, M, 0)) return rc;
+  if (pl.paired) {
+    uint64_t dims[4] = {static_cast<uint64_t>(M), static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(dy_ld) * 2, static_cast<uint64_t>(dy_ld) * 2 * W,
+                           static_cast<uint64_t>(dy_ld) * 2 * W * H};
+    uint32_t box[4] = {64, 64, 2, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (int rc = make_tmap_bf16(&p.tmP2, dy, 4, dims, strides, box, es, true)) return rc;
+  }
   if (int rc = mk(&p.tmQ, x, x_ld, Nn, 2)) return rc;
   int rc = (pl.NT == 128) ? launch<128>(p, pl, stream) : launch<64>(p, pl, stream);
   if (rc) return rc;
