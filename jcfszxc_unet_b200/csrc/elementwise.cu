@@ -398,25 +398,29 @@ struct PoolWindow {
   template <class Emit>
   __device__ __forceinline__ void visit(const BnBwdArgs& A, const float (&sc)[8], const float (&sh)[8],
                                         Emit&& emit) const {
-    int arg[8];
-    float gy[8], best[8], f[8];
-    unpack8(ur[0], f);
+    // pass 1: bf16-rounded activations of the four window pixels -> pooled argmax (2 bits per channel) and the
+    // ReLU mask (1 bit per pixel and channel), so that pass 2 does not evaluate the BatchNorm a second time
+    uint32_t argpack = 0, maskbits = 0;
+    {
+      float best[8], f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
-      best[j] = A.relu ? fmaxf(z, 0.f) : z;
-      arg[j] = 0;
-    }
+      for (int q = 0; q < 4; ++q) {
+        unpack8(ur[q], f);
 #pragma unroll
-    for (int q = 1; q < 4; ++q) {
-      unpack8(ur[q], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
-        const float v = A.relu ? fmaxf(z, 0.f) : z;
-        if (v > best[j] || v != v) { best[j] = v; arg[j] = q; }
+        for (int j = 0; j < 8; ++j) {
+          const float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
+          const float v = A.relu ? fmaxf(z, 0.f) : z;
+          if (!A.relu || z > 0.f) maskbits |= 1u << (q * 8 + j);
+          if (q == 0) {
+            best[j] = v;
+          } else if (v > best[j] || v != v) {
+            best[j] = v;
+            argpack = (argpack & ~(3u << (2 * j))) | (static_cast<uint32_t>(q) << (2 * j));
+          }
+        }
       }
     }
+    float gy[8];
     unpack8(ugp, gy);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -425,11 +429,8 @@ struct PoolWindow {
       unpack8(ug[q], gm);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        gm[j] += (arg[j] == q) ? gy[j] : 0.f;
-        if (A.relu) {
-          const float z = bf16_round(fmaf(r[j], sc[j], sh[j]));
-          gm[j] = (z > 0.f) ? gm[j] : 0.f;
-        }
+        if (((argpack >> (2 * j)) & 3u) == static_cast<uint32_t>(q)) gm[j] += gy[j];
+        if (!((maskbits >> (q * 8 + j)) & 1u)) gm[j] = 0.f;
       }
       emit(q, gm, r);
     }

@@ -8,6 +8,6 @@ for i in $(seq 1 $R); do
     lib=$A; [ $v = B ] && lib=$B
     UNETK_LIB=$lib timeout 300 python tools/profile_step.py > gpurun_out/ab_${v}_$i.txt 2>&1
     echo "== $v round $i: $(grep -E '^total' gpurun_out/ab_${v}_$i.txt)"
-    grep -E "^  unetk_(conv3x3_fwd_bnstats|conv3x3_dgrad|conv3x3_dgrad_colsum|conv3x3_wgrad|convT2x2_fwd|bn_bwd_reduce|convT2x2_wgrad|conv1x1_wgrad) " gpurun_out/ab_${v}_$i.txt
+    grep -E "^  unetk_(conv3x3_fwd_bnstats|conv3x3_dgrad|conv3x3_dgrad_colsum|conv3x3_wgrad|convT2x2_fwd|bn_bwd_reduce|bn_bwd_apply|bn_apply) " gpurun_out/ab_${v}_$i.txt
   done
 done
