@@ -274,6 +274,27 @@ int unetk_gate_bwd_apply(const void* raw_g, int64_t raw_g_ld, const void* raw_x,
                          const float* coef_x, void* draw_g, int64_t draw_g_ld, void* draw_x, int64_t draw_x_ld,
                          int64_t npix, int F_int, void* stream);
 
+/* ---- n_classes > 1 and the stand-alone Dice coefficient (unet_parts.py:73-79; utils/dice_score.py:13-59) ----------
+ * head_multi_fwd: OutConv with K = n_classes <= 8 outputs: logits[n][k][h][w] (fp32, NCHW as the reference returns it)
+ *                 = bias[k] + sum_c x[n,h,w,c] * w[k][c];  hw = H*W, C a power of two in [8,256].
+ * head_multi_bwd: given dlogits (same layout, scaled by gscale): dx (bf16 NHWC), dw[k][c], db[k] (fp32, (+)= when
+ *                 accumulate != 0); partial >= unetk_head_multi_partial_floats floats.
+ * dice_sums:      p, t fp32 [groups][n]; sums = double[groups][3] = (sum clamp(p,lo,hi)*t, sum clamp(p,lo,hi), sum t).
+ *                 dice_coeff sums over (H,W) per leading index or over everything (reduce_batch_first);
+ *                 multiclass_dice_coeff is the same call on the (batch x class)-flattened tensors.
+ * dice_bwd:       dp[g][i] = gout[0] * (coef[g][0]*t + coef[g][1]) where lo <= p <= hi, else 0. */
+size_t unetk_head_multi_partial_floats(int64_t npix, int C, int K);
+int unetk_head_multi_fwd(const void* x, int64_t x_ld, const float* w, const float* bias, float* logits, int N,
+                         int64_t hw, int C, int K, void* stream);
+int unetk_head_multi_bwd(const void* x, int64_t x_ld, const float* w, const float* dlogits, float gscale, void* dx,
+                         int64_t dx_ld, float* dw, float* db, int accumulate, int N, int64_t hw, int C, int K,
+                         float* partial, void* stream);
+size_t unetk_dice_partial_floats(int64_t groups, int64_t n);
+int unetk_dice_sums(const float* p, const float* t, int64_t groups, int64_t n, float lo, float hi, float* partial,
+                    double* sums, void* stream);
+int unetk_dice_bwd(const float* p, const float* t, const float* coef, const float* gout, int64_t groups, int64_t n,
+                   float lo, float hi, float* dp, void* stream);
+
 /* ---- fp32 mode (BASELINE.json configs[0]: vanilla UNet fp32 forward; logits within 1e-4 of torch fp32) ----------
  * The reference without autocast computes in fp32 (UNet.py:39-55 on unet_parts.py:17-79).  Here an fp32 value is
  * carried as three bf16 terms (hi + mid + lo) and a product as six exact bf16 x bf16 terms accumulated in fp32 on the

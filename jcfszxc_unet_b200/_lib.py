@@ -81,6 +81,12 @@ SIGNATURES = {
                                    _vp, _vp, _fp, _fp, _i, _i64, _i, _vp]),
     "unetk_gate_bwd_apply": (_i, [_vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp,
                                   _i64, _vp, _i64, _i64, _i, _vp]),
+    "unetk_head_multi_partial_floats": (_sz, [_i64, _i, _i]),
+    "unetk_head_multi_fwd": (_i, [_vp, _i64, _fp, _fp, _fp, _i, _i64, _i, _i, _vp]),
+    "unetk_head_multi_bwd": (_i, [_vp, _i64, _fp, _fp, _f, _vp, _i64, _fp, _fp, _i, _i, _i64, _i, _i, _fp, _vp]),
+    "unetk_dice_partial_floats": (_sz, [_i64, _i64]),
+    "unetk_dice_sums": (_i, [_fp, _fp, _i64, _i64, _f, _f, _fp, _vp, _vp]),
+    "unetk_dice_bwd": (_i, [_fp, _fp, _fp, _fp, _i64, _i64, _f, _f, _fp, _vp]),
     "unetk_f32_pack_split3": (_i, [_fp, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _vp]),
     "unetk_f32_stem_conv3x3": (_i, [_fp, _i64, _i64, _i64, _i64, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_f32_conv3x3": (_i, [_vp, _i64, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),

@@ -336,6 +336,37 @@ int unetk_head_bwd(const void* x, int64_t x_ld, const float* w, const float* lab
                            accumulate, npix, C, partial, S(stream));
 }
 
+// ------------------------------------------------------------------------------------------------ n_classes > 1, Dice
+size_t unetk_head_multi_partial_floats(int64_t npix, int C, int K) {
+  if (C < 8 || C % 8 || K < 1 || K > 8) return 0;
+  return head_multi_partial_floats(npix, C, K);
+}
+int unetk_head_multi_fwd(const void* x, int64_t x_ld, const float* w, const float* bias, float* logits, int N,
+                         int64_t hw, int C, int K, void* stream) {
+  UNETK_CHECK(x && w && logits && N > 0 && hw > 0, -1, "head_multi_fwd: bad arguments");
+  return head_multi_fwd_run(x, x_ld, w, bias, logits, N, hw, C, K, S(stream));
+}
+int unetk_head_multi_bwd(const void* x, int64_t x_ld, const float* w, const float* dlogits, float gscale, void* dx,
+                         int64_t dx_ld, float* dw, float* db, int accumulate, int N, int64_t hw, int C, int K,
+                         float* partial, void* stream) {
+  UNETK_CHECK(x && w && dlogits && dx && partial && N > 0 && hw > 0, -1, "head_multi_bwd: bad arguments");
+  return head_multi_bwd_run(x, x_ld, w, dlogits, gscale, dx, dx_ld, dw, db, accumulate, N, hw, C, K, partial, S(stream));
+}
+size_t unetk_dice_partial_floats(int64_t groups, int64_t n) {
+  if (groups < 1 || n < 1) return 0;
+  return dice_partial_floats(groups, n);
+}
+int unetk_dice_sums(const float* p, const float* t, int64_t groups, int64_t n, float lo, float hi, float* partial,
+                    double* sums, void* stream) {
+  UNETK_CHECK(p && t && partial && sums, -1, "dice_sums: null pointer");
+  return dice_sums_run(p, t, groups, n, lo, hi, partial, sums, S(stream));
+}
+int unetk_dice_bwd(const float* p, const float* t, const float* coef, const float* gout, int64_t groups, int64_t n,
+                   float lo, float hi, float* dp, void* stream) {
+  UNETK_CHECK(p && t && coef && gout && dp, -1, "dice_bwd: null pointer");
+  return dice_bwd_run(p, t, coef, gout, groups, n, lo, hi, dp, S(stream));
+}
+
 // ------------------------------------------------------------------------------------------------ optimizer
 size_t unetk_sqnorm_partial_floats(int64_t n) { return static_cast<size_t>(sqnorm_blocks(n)); }
 int unetk_grad_clip_coef(const float* g, int64_t n, float gscale, float max_norm, float* partial, float* out,

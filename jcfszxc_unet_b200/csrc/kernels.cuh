@@ -98,6 +98,18 @@ int gate_bwd_apply_run(const void* rawg, int64_t rawg_ld, const void* rawx, int6
                        const float* dz, const float* sc1, const float* coef1, const float* coefg, const float* coefx,
                        void* drawg, int64_t drawg_ld, void* drawx, int64_t drawx_ld, int64_t npix, int F,
                        cudaStream_t st);
+// multiclass.cu
+size_t head_multi_partial_floats(int64_t npix, int C, int K);
+int head_multi_fwd_run(const void* x, int64_t ld, const float* w, const float* bias, float* logits, int N, int64_t hw,
+                       int C, int K, cudaStream_t s);
+int head_multi_bwd_run(const void* x, int64_t ld, const float* w, const float* dlogits, float gscale, void* dx,
+                       int64_t dx_ld, float* dw, float* db, int accumulate, int N, int64_t hw, int C, int K,
+                       float* partial, cudaStream_t s);
+size_t dice_partial_floats(int64_t groups, int64_t n);
+int dice_sums_run(const float* p, const float* t, int64_t groups, int64_t n, float lo, float hi, float* partial,
+                  double* sums, cudaStream_t s);
+int dice_bwd_run(const float* p, const float* t, const float* coef, const float* gout, int64_t groups, int64_t n,
+                 float lo, float hi, float* dp, cudaStream_t s);
 // f32path.cu
 int f32_pack_split3_run(const float* src, void* dst, long long sr, long long sk, long long st, int R, int K, int T,
                         const int* slices, int ns, cudaStream_t s);

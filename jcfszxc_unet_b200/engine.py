@@ -572,6 +572,63 @@ class Head:
                      self.post_sigmoid)
 
 
+class HeadMulti:
+    """OutConv with n_classes > 1 (unet_parts.py:73-79): logits [N,K,H,W] fp32; the loss lives outside the library
+    (nn.CrossEntropyLoss at train.py:124, utils.dice_score.multiclass_dice_coeff) and autograd supplies dL/dlogits."""
+
+    def __init__(self, plan: Plan, x: Act, conv: torch.nn.Conv2d):
+        assert conv.kernel_size == (1, 1)
+        self.plan, self.x, self.conv = plan, x, conv
+        self.C, self.K = conv.in_channels, conv.out_channels
+        if not 1 <= self.K <= 8:
+            raise NotImplementedError(f"the output conv supports 1..8 classes, got {self.K}")
+        self.npix = x.N * x.H * x.W
+        self.logits = torch.empty((x.N, self.K, x.H, x.W), dtype=torch.float32, device=plan.device)
+        self.labels = None          # interface parity with Head (the fused loss is binary-only)
+        self.dlogits: torch.Tensor | None = None
+        self.gscale = 1.0
+        self.acc_w = False
+        plan.need(_lib.load().unetk_head_multi_partial_floats(self.npix, self.C, self.K), 0, self.C)
+        plan.register_param(conv.weight)
+        if conv.bias is not None:
+            plan.register_param(conv.bias)
+        plan.ops.append(self)
+
+    def bind(self, plan):
+        self.dw = plan.grad_of.get(id(self.conv.weight))
+        self.db = plan.grad_of.get(id(self.conv.bias)) if self.conv.bias is not None else None
+
+    def plan_bwd(self, plan):
+        if plan.with_grad:
+            self.acc_w = plan.param_acc(self.conv.weight) | plan.param_acc(self.conv.bias)
+            if self.x.g is not None and plan.grad_acc(self.x):
+                raise RuntimeError("HeadMulti: the input of the output conv must not have other consumers")
+
+    def refresh(self, force=False):
+        pass
+
+    def fwd(self):
+        if self.labels is not None:
+            raise NotImplementedError("the fused BCE+dice loss is binary (n_classes == 1); compute the loss on the logits")
+        xp, xld = ops.nhwc(self.x.t)
+        w = self.conv.weight.detach().view(self.K, self.C)
+        b = self.conv.bias.detach() if self.conv.bias is not None else None
+        _lib.call("unetk_head_multi_fwd", xp, xld, ops._f32(w), ops._f32(b), self.logits.data_ptr(), self.x.N,
+                  self.x.H * self.x.W, self.C, self.K, _s())
+
+    def bwd(self):
+        if self.dlogits is None:
+            raise RuntimeError("HeadMulti.bwd needs dL/dlogits")
+        xp, xld = ops.nhwc(self.x.t)
+        dxp, dxld = ops.nhwc(self.x.g)
+        w = self.conv.weight.detach().view(self.K, self.C)
+        dl = self.dlogits
+        assert dl.shape == self.logits.shape and dl.dtype == torch.float32 and dl.is_contiguous()
+        _lib.call("unetk_head_multi_bwd", xp, xld, ops._f32(w), dl.data_ptr(), float(self.gscale), dxp, dxld,
+                  ops._f32(self.dw.view(self.K, self.C)) if self.dw is not None else None, ops._f32(self.db),
+                  int(self.acc_w), self.x.N, self.x.H * self.x.W, self.C, self.K, self.plan.partial.data_ptr(), _s())
+
+
 class _Op:
     """Default no-op hooks of a plan op."""
 
@@ -861,5 +918,5 @@ def build_unet_plan(model, N: int, H: int, W: int, device, training: bool, grad_
         ConvBNReLU(P, cats[i], dc[0], dc[1], mid)
         y = P.act(h, w, dc[3].out_channels)
         ConvBNReLU(P, mid, dc[3], dc[4], y)
-    P.head = Head(P, y, model.outc.conv)
+    P.head = Head(P, y, model.outc.conv) if model.outc.conv.out_channels == 1 else HeadMulti(P, y, model.outc.conv)
     return P.finalize(grad_views)

@@ -73,6 +73,10 @@ class Trainer:
         self.images = torch.zeros((n, c, h, w), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
         self.labels = torch.zeros((n, 1, h, w), dtype=torch.float32, device=dev)
         head = self.plan.head
+        from .engine import Head
+        if not isinstance(head, Head):
+            raise NotImplementedError("Trainer fuses the reference's binary loss (train.py:264-278: BCE + dice on ONE logit map); "
+                                      "with n_classes > 1 use model(x), your loss and loss.backward()")
         head.labels = self.labels
         head.dlogits = None
         head.auto_finalize = False
