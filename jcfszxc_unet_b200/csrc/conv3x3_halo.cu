@@ -97,6 +97,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on global memory
+  pdl_trigger();
+  pdl_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
@@ -401,7 +404,7 @@ int launch(HaloParams& p, int grid, cudaStream_t stream) {
   const uint32_t resident_smem = 2 * kHaloSlot + w_bytes + kStagingBytes + 1024 + 256 + BN * 4;
   p.resident = (resident_smem <= 227 * 1024) ? 1 : 0;
   const uint32_t smem_bytes = p.resident ? resident_smem : C::kSmemBytes;
-  conv3x3_halo_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(p);
+  UNETK_CUDA(launch_pdl(conv3x3_halo_kernel<BN>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
   UNETK_LAUNCHED();
   return 0;
 }

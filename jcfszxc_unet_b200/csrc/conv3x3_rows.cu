@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on global memory
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -389,7 +392,7 @@ int conv3x3_rows_run(const ConvGemmDesc& d, cudaStream_t stream) {
     UNETK_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  conv3x3_rows_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  UNETK_CUDA(launch_pdl(conv3x3_rows_kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
   UNETK_LAUNCHED();
   if (d.stats_sums != nullptr) return conv_stats_sums_launch(d.stats_partial, grid, 1, 64, d.ncols, d.stats_sums, stream);
   return 0;

@@ -86,6 +86,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on global memory
+  pdl_trigger();
+  pdl_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kblocks = p.taps * p.kchunks;
@@ -357,6 +360,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 // sums[k][c] = sum over the CTAs that own channel c's N tile (CTA b owns tile b % num_n_tiles), fixed order
 __global__ void conv_stats_sums_kernel(const float* __restrict__ partial, int grid, int num_n_tiles, int BN, int C,
                                        double* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * kSum2Lanes + threadIdx.x;
   const bool valid = i < 2 * C;
   const int k = valid ? i / C : 0, c = valid ? i % C : 0;
@@ -377,7 +382,7 @@ int launch_t(const ConvGemmParams& p, int grid, cudaStream_t stream) {
                                     C::kSmemBytes));
     configured = true;
   }
-  conv_gemm_kernel<BN, F32OUT><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  UNETK_CUDA(launch_pdl(conv_gemm_kernel<BN, F32OUT>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, p));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -399,7 +404,7 @@ int pick_bn(int ncols, int q_groups) {
 
 int conv_stats_sums_launch(const float* partial, int grid, int num_n_tiles, int BN, int C, double* sums,
                            cudaStream_t stream) {
-  conv_stats_sums_kernel<<<(2 * C + kSum2Lanes - 1) / kSum2Lanes, dim3(kSum2Lanes, kSum2Slices), 0, stream>>>(partial, grid, num_n_tiles, BN, C, sums);
+  UNETK_CUDA(launch_pdl(conv_stats_sums_kernel, dim3((2 * C + kSum2Lanes - 1) / kSum2Lanes), dim3(kSum2Lanes, kSum2Slices), 0, stream, partial, grid, num_n_tiles, BN, C, sums));
   UNETK_LAUNCHED();
   return 0;
 }

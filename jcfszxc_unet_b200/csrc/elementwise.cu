@@ -66,6 +66,8 @@ __device__ __forceinline__ void block_reduce_store(float (&acc)[K][8], const Lan
 // ------------------------------------------------------------------ forward statistics
 __global__ void __launch_bounds__(kThreads) stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld,
                                                          int64_t npix, int C, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   Lanes L(C);
   float acc[2][8] = {};
   if (L.active) {
@@ -97,6 +99,8 @@ __global__ void __launch_bounds__(kThreads) stats_kernel(const __nv_bfloat16* __
 // nn.BatchNorm2d (biased variance to normalise, unbiased for running_var, momentum 0.1).
 // Ordered (deterministic) second stage: sums[k][c] = sum over block partials, in double.
 __global__ void chan_sums_kernel(const float* __restrict__ partial, int nblk, int C, double* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * kSum2Lanes + threadIdx.x;
   const bool valid = i < 2 * C;
   const double s = sliced_ordered_sum(partial, nblk, valid, [&](int b) { return static_cast<size_t>(b) * 2 * C + i; });
@@ -109,6 +113,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, doubl
                                    long long* num_batches_tracked, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (c >= C) return;
@@ -133,6 +139,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, doubl
 __global__ void bn_eval_fold_kernel(int C, const float* gamma, const float* beta, float eps, const float* rm,
                                     const float* rv, float* scale, float* shift, float* mean_out,
                                     float* invstd_out) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = 1.f / sqrtf(rv[c] + eps);
@@ -145,6 +153,8 @@ __global__ void bn_eval_fold_kernel(int C, const float* gamma, const float* beta
 
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out,
                                        int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * kSum2Lanes + threadIdx.x;
   const bool valid = c < C;
   const double s = sliced_ordered_sum(partial, nblk, valid, [&](int b) { return (static_cast<size_t>(b) * 2 + 0) * C + c; });
@@ -174,6 +184,8 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16*
                                                             const __nv_bfloat16* __restrict__ res, int64_t res_ld,
                                                             __nv_bfloat16* __restrict__ out, int64_t out_ld,
                                                             int64_t npix, int C, int relu) {
+  pdl_trigger();
+  pdl_wait();
   Lanes L(C);
   if (!L.active) return;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
@@ -239,6 +251,8 @@ __global__ void __launch_bounds__(kThreads)
 bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld, const float* __restrict__ scale,
                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int64_t out_ld,
                      __nv_bfloat16* __restrict__ pooled, int64_t pooled_ld, int N, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cg;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;  // multiple of cg
@@ -279,6 +293,8 @@ bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld, cons
 __global__ void __launch_bounds__(kThreads)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, __nv_bfloat16* __restrict__ y, int64_t y_ld,
                    long long* __restrict__ idx, int N, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cg;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
@@ -315,6 +331,8 @@ template <bool ACC>
 __global__ void __launch_bounds__(kThreads)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, const __nv_bfloat16* __restrict__ dy,
                    int64_t dy_ld, __nv_bfloat16* __restrict__ dx, int64_t dx_ld, int N, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cg;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
@@ -507,6 +525,8 @@ __device__ __forceinline__ void bn_bwd_walk(const BnBwdArgs& A, const Lanes& L, 
 // partial[blk][0][c] = sum gm, partial[blk][1][c] = sum gm * (raw - mean)
 template <bool POOL>
 __global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_kernel(const BnBwdArgs A, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   Lanes L(A.C);
   float acc[2][8] = {};
   if (L.active) {
@@ -530,6 +550,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int C, d
                                        const float* __restrict__ scale, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, float* dgamma, float* dbeta, int accumulate,
                                        float* __restrict__ coef, float* dconv_bias) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   // Bias of the convolution in FRONT of this BatchNorm (conv_block, up_conv, Recurrent_block, W_g/W_x/psi, ...):
@@ -553,6 +575,8 @@ template <bool POOL, bool ACC>
 __global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(const BnBwdArgs A, const float* __restrict__ coef, __nv_bfloat16* __restrict__ draw,
                     int64_t draw_ld) {
+  pdl_trigger();
+  pdl_wait();
   Lanes L(A.C);
   if (!L.active) return;
   const int g = L.g;
@@ -628,7 +652,7 @@ int flat_grid(int64_t total) {
 size_t chan_partial_floats(int64_t units, int C) { return static_cast<size_t>(reduce_grid(units, C)) * 2 * C; }
 
 static int launch_sums(const float* partial, int nblk, int C, double* sums, cudaStream_t s) {
-  chan_sums_kernel<<<(2 * C + kSum2Lanes - 1) / kSum2Lanes, dim3(kSum2Lanes, kSum2Slices), 0, s>>>(partial, nblk, C, sums);
+  UNETK_CUDA(launch_pdl(chan_sums_kernel, dim3((2 * C + kSum2Lanes - 1) / kSum2Lanes), dim3(dim3(kSum2Lanes, kSum2Slices)), 0, s, partial, nblk, C, sums));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -637,7 +661,7 @@ static int launch_sums(const float* partial, int nblk, int C, double* sums, cuda
 int bn_stats_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, double* sums, cudaStream_t s) {
   CHECK_C(C);
   const int grid = reduce_grid(npix, C);
-  stats_kernel<<<grid, kThreads, reduce_smem(C, 2), s>>>(static_cast<const __nv_bfloat16*>(x), ld, npix, C, partial);
+  UNETK_CUDA(launch_pdl(stats_kernel, dim3(grid), dim3(kThreads), reduce_smem(C, 2), s, static_cast<const __nv_bfloat16*>(x), ld, npix, C, partial));
   UNETK_LAUNCHED();
   return launch_sums(partial, grid, C, sums, s);
 }
@@ -645,15 +669,15 @@ int bn_stats_run(const void* x, int64_t ld, int64_t npix, int C, float* partial,
 int bn_finalize_run(const double* sums, int C, double count, const float* gamma, const float* beta, float eps,
                     float momentum, float* rm, float* rv, long long* nbt, float* scale, float* shift, float* mean,
                     float* invstd, cudaStream_t s) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, gamma, beta, eps, momentum, rm, rv, nbt, scale,
-                                                    shift, mean, invstd);
+  UNETK_CUDA(launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, s, sums, C, count, gamma, beta, eps, momentum, rm, rv, nbt, scale,
+                                                    shift, mean, invstd));
   UNETK_LAUNCHED();
   return 0;
 }
 
 int bn_eval_fold_run(int C, const float* gamma, const float* beta, float eps, const float* rm, const float* rv,
                      float* scale, float* shift, float* mean, float* invstd, cudaStream_t s) {
-  bn_eval_fold_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, gamma, beta, eps, rm, rv, scale, shift, mean, invstd);
+  UNETK_CUDA(launch_pdl(bn_eval_fold_kernel, dim3((C + 127) / 128), dim3(128), 0, s, C, gamma, beta, eps, rm, rv, scale, shift, mean, invstd));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -662,19 +686,21 @@ int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, f
                cudaStream_t s) {
   CHECK_C(C);
   const int grid = reduce_grid(npix, C);
-  stats_kernel<<<grid, kThreads, reduce_smem(C, 2), s>>>(static_cast<const __nv_bfloat16*>(x), ld, npix, C, partial);
+  UNETK_CUDA(launch_pdl(stats_kernel, dim3(grid), dim3(kThreads), reduce_smem(C, 2), s, static_cast<const __nv_bfloat16*>(x), ld, npix, C, partial));
   UNETK_LAUNCHED();
-  colsum_finalize_kernel<<<(C + kSum2Lanes - 1) / kSum2Lanes, dim3(kSum2Lanes, kSum2Slices), 0, s>>>(partial, grid, C, out, accumulate);
+  UNETK_CUDA(launch_pdl(colsum_finalize_kernel, dim3((C + kSum2Lanes - 1) / kSum2Lanes), dim3(dim3(kSum2Lanes, kSum2Slices)), 0, s, partial, grid, C, out, accumulate));
   UNETK_LAUNCHED();
   return 0;
 }
 
 __global__ void sums_to_f32_kernel(const double* __restrict__ sums, int n, float* __restrict__ out, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = accumulate ? out[i] + static_cast<float>(sums[i]) : static_cast<float>(sums[i]);
 }
 int sums_to_f32_run(const double* sums, int n, float* out, int accumulate, cudaStream_t s) {
-  sums_to_f32_kernel<<<(n + 127) / 128, 128, 0, s>>>(sums, n, out, accumulate);
+  UNETK_CUDA(launch_pdl(sums_to_f32_kernel, dim3((n + 127) / 128), dim3(128), 0, s, sums, n, out, accumulate));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -698,20 +724,19 @@ int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const floa
     UNETK_CHECK(H % 2 == 0 && W % 2 == 0 && relu, -1, "fused pool needs even H,W and relu");
     UNETK_CHECK(res == nullptr, -1, "bn_apply: fused pool and residual add cannot be combined");
     const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
-    bn_apply_pool_kernel<<<flat_grid_cg(total, C / 8), kThreads, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift, static_cast<__nv_bfloat16*>(out), out_ld,
-        static_cast<__nv_bfloat16*>(pooled), pooled_ld, N, H, W, C);
+    UNETK_CUDA(launch_pdl(bn_apply_pool_kernel, dim3(flat_grid_cg(total, C / 8)), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift, static_cast<__nv_bfloat16*>(out), out_ld,
+        static_cast<__nv_bfloat16*>(pooled), pooled_ld, N, H, W, C));
   } else {
     const int64_t npix = static_cast<int64_t>(N) * H * W;
     const int grid = lanes_grid(npix, C, 8);
     if (res != nullptr)
-      bn_apply_kernel<true><<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift,
+      UNETK_CUDA(launch_pdl(bn_apply_kernel<true>, dim3(grid), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift,
                                                       static_cast<const __nv_bfloat16*>(res), res_ld,
-                                                      static_cast<__nv_bfloat16*>(out), out_ld, npix, C, relu);
+                                                      static_cast<__nv_bfloat16*>(out), out_ld, npix, C, relu));
     else
-      bn_apply_kernel<false><<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift,
+      UNETK_CUDA(launch_pdl(bn_apply_kernel<false>, dim3(grid), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift,
                                                        nullptr, 0, static_cast<__nv_bfloat16*>(out), out_ld, npix, C,
-                                                       relu);
+                                                       relu));
   }
   UNETK_LAUNCHED();
   return 0;
@@ -722,8 +747,8 @@ int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long lon
   CHECK_C(C);
   const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
   if (total == 0) return 0;
-  maxpool_fwd_kernel<<<flat_grid(total), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
-                                                          static_cast<__nv_bfloat16*>(y), y_ld, idx, N, H, W, C);
+  UNETK_CUDA(launch_pdl(maxpool_fwd_kernel, dim3(flat_grid(total)), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(x), x_ld,
+                                                          static_cast<__nv_bfloat16*>(y), y_ld, idx, N, H, W, C));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -734,13 +759,13 @@ int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, 
   UNETK_CHECK(H % 2 == 0 && W % 2 == 0, -1, "maxpool_bwd: odd spatial size %dx%d not supported", H, W);
   const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
   if (accumulate)
-    maxpool_bwd_kernel<true><<<flat_grid(total), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
+    UNETK_CUDA(launch_pdl(maxpool_bwd_kernel<true>, dim3(flat_grid(total)), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(x), x_ld,
                                                                   static_cast<const __nv_bfloat16*>(dy), dy_ld,
-                                                                  static_cast<__nv_bfloat16*>(dx), dx_ld, N, H, W, C);
+                                                                  static_cast<__nv_bfloat16*>(dx), dx_ld, N, H, W, C));
   else
-    maxpool_bwd_kernel<false><<<flat_grid(total), kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
+    UNETK_CUDA(launch_pdl(maxpool_bwd_kernel<false>, dim3(flat_grid(total)), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(x), x_ld,
                                                                    static_cast<const __nv_bfloat16*>(dy), dy_ld,
-                                                                   static_cast<__nv_bfloat16*>(dx), dx_ld, N, H, W, C);
+                                                                   static_cast<__nv_bfloat16*>(dx), dx_ld, N, H, W, C));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -770,8 +795,8 @@ int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g
   const int64_t units = pool ? static_cast<int64_t>(N) * (H / 2) * (W / 2) : static_cast<int64_t>(N) * H * W;
   const int grid = bwd_grid(units, C);
   const size_t smem = reduce_smem(C, 2);
-  if (pool) bn_bwd_reduce_kernel<true><<<grid, kThreads, smem, s>>>(A, partial);
-  else bn_bwd_reduce_kernel<false><<<grid, kThreads, smem, s>>>(A, partial);
+  if (pool) UNETK_CUDA(launch_pdl(bn_bwd_reduce_kernel<true>, dim3(grid), dim3(kThreads), smem, s, A, partial));
+  else UNETK_CUDA(launch_pdl(bn_bwd_reduce_kernel<false>, dim3(grid), dim3(kThreads), smem, s, A, partial));
   UNETK_LAUNCHED();
   return launch_sums(partial, grid, C, sums, s);
 }
@@ -780,8 +805,8 @@ int bn_bwd_coef_run(const double* sums, int C, double count, const float* scale,
                     const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, float* dconv_bias,
                     cudaStream_t s) {
   UNETK_CHECK(C >= 1, -1, "bn_bwd_coef: C=%d", C);
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef,
-                                                         dconv_bias);
+  UNETK_CUDA(launch_pdl(bn_bwd_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, s, sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef,
+                                                         dconv_bias));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -795,17 +820,17 @@ int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1
   if (int rc = bn_bwd_args(&A, raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, N, H, W, C, relu)) return rc;
   const bool pool = gp != nullptr;
   const int64_t units = pool ? static_cast<int64_t>(N) * (H / 2) * (W / 2) : static_cast<int64_t>(N) * H * W;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef,
-                                                         dconv_bias);
+  UNETK_CUDA(launch_pdl(bn_bwd_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, s, sums, C, count, scale, mean, invstd, dgamma, dbeta, accumulate, coef,
+                                                         dconv_bias));
   UNETK_LAUNCHED();
   const int grid = bwd_grid(units, C);
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(draw);
   if (pool) {
-    if (draw_accumulate) bn_bwd_apply_kernel<true, true><<<grid, kThreads, 0, s>>>(A, coef, d, draw_ld);
-    else bn_bwd_apply_kernel<true, false><<<grid, kThreads, 0, s>>>(A, coef, d, draw_ld);
+    if (draw_accumulate) UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<true, true>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld));
+    else UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<true, false>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld));
   } else {
-    if (draw_accumulate) bn_bwd_apply_kernel<false, true><<<grid, kThreads, 0, s>>>(A, coef, d, draw_ld);
-    else bn_bwd_apply_kernel<false, false><<<grid, kThreads, 0, s>>>(A, coef, d, draw_ld);
+    if (draw_accumulate) UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<false, true>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld));
+    else UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<false, false>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld));
   }
   UNETK_LAUNCHED();
   return 0;

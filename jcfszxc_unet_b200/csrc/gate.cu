@@ -70,6 +70,8 @@ struct GateArgs {
 // ------------------------------------------------------------------ s = w_psi . relu(g1 + x1) + b
 __global__ void __launch_bounds__(kThreads)
 gate_fwd_kernel(const GateArgs A, float* __restrict__ s_out, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   const int lpp = A.F >> 3, gpb = kThreads / lpp;
   const int sub = threadIdx.x % lpp, grp = threadIdx.x / lpp;
   float scg[8], shg[8], scx[8], shx[8], wv[8];
@@ -122,6 +124,8 @@ gate_fwd_kernel(const GateArgs A, float* __restrict__ s_out, float* __restrict__
 }
 
 __global__ void pair_sums_kernel(const float* __restrict__ partial, int nblk, double* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
   const int k = threadIdx.x;
   if (k >= 2) return;
   double s = 0.0;
@@ -135,6 +139,8 @@ __global__ void __launch_bounds__(kThreads)
 gate_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, const float* __restrict__ s,
                   const float* __restrict__ sc1, const float* __restrict__ sh1, __nv_bfloat16* __restrict__ out,
                   int64_t out_ld, int64_t npix, int F) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = F >> 3;
   const int lpp = cg < 32 ? cg : 32, gpb = kThreads / lpp;
   const int sub = threadIdx.x % lpp, grp = threadIdx.x / lpp;
@@ -168,6 +174,8 @@ gate_bwd_psi_kernel(const __nv_bfloat16* __restrict__ dout, int64_t dout_ld, con
                     int64_t x_ld, const float* __restrict__ s, const float* __restrict__ sc1,
                     const float* __restrict__ sh1, const float* __restrict__ mean1, __nv_bfloat16* __restrict__ dx,
                     int64_t dx_ld, float* __restrict__ dz, float* __restrict__ partial, int64_t npix, int F) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = F >> 3;
   const int lpp = cg < 32 ? cg : 32, gpb = kThreads / lpp;
   const int sub = threadIdx.x % lpp, grp = threadIdx.x / lpp;
@@ -254,6 +262,8 @@ struct GateBwdArgs {
 // partial[blk][k][F], k: 0 sum da, 1 sum da*(rawg-mug), 2 sum da*(rawx-mux), 3 sum ds*a (dw_psi), 4 sum ds (channel 0 only)
 __global__ void __launch_bounds__(kThreads)
 gate_bwd_reduce_kernel(const GateBwdArgs B, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   const GateArgs& A = B.G;
   GLanes L(A.F);
   float acc[5][8] = {};
@@ -311,6 +321,8 @@ gate_bwd_reduce_kernel(const GateBwdArgs B, float* __restrict__ partial) {
 // sums_g = double[2][F] (S0, S1g), sums_x = double[2][F] (S0, S1x); dwpsi[F], dbpsi[1] (accumulate optional)
 __global__ void gate_bwd_sums_kernel(const float* __restrict__ partial, int nblk, int F, double* __restrict__ sums_g,
                                      double* __restrict__ sums_x, float* dwpsi, float* dbpsi, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 5 * F) return;
   const int k = i / F, c = i % F;
@@ -329,6 +341,8 @@ __global__ void __launch_bounds__(kThreads)
 gate_bwd_apply_kernel(const GateBwdArgs B, const float* __restrict__ coefg, const float* __restrict__ coefx,
                       __nv_bfloat16* __restrict__ drawg, int64_t drawg_ld, __nv_bfloat16* __restrict__ drawx,
                       int64_t drawx_ld) {
+  pdl_trigger();
+  pdl_wait();
   const GateArgs& A = B.G;
   GLanes L(A.F);
   if (!L.active) return;
@@ -411,9 +425,9 @@ int gate_fwd_run(const void* rawg, int64_t rawg_ld, const void* rawx, int64_t ra
   UNETK_CHECK(pow2_f(F), -1, "gate: F_int=%d must be a power of two in [8,256]", F);
   const GateArgs A = gate_args(rawg, rawg_ld, rawx, rawx_ld, scg, shg, scx, shx, wpsi, bpsi, npix, F);
   const int grid = pix_grid(npix, F / 8);
-  gate_fwd_kernel<<<grid, kThreads, 0, st>>>(A, s, partial);
+  UNETK_CUDA(launch_pdl(gate_fwd_kernel, dim3(grid), dim3(kThreads), 0, st, A, s, partial));
   UNETK_LAUNCHED();
-  pair_sums_kernel<<<1, 32, 0, st>>>(partial, grid, sums);
+  UNETK_CUDA(launch_pdl(pair_sums_kernel, dim3(1), dim3(32), 0, st, partial, grid, sums));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -423,8 +437,8 @@ int gate_apply_run(const void* x, int64_t x_ld, const float* s, const float* sc1
   UNETK_CHECK(F % 8 == 0 && F >= 8 && (F <= 256 ? pow2_f(F) : F <= 4096), -1,
               "gate_apply: F_l=%d must be a power of two <= 256 or a multiple of 8 in (256, 4096]", F);
   const int lpp = F / 8 < 32 ? F / 8 : 32;
-  gate_apply_kernel<<<pix_grid(npix, lpp, 4), kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_ld, s, sc1,
-                                                                sh1, static_cast<__nv_bfloat16*>(out), out_ld, npix, F);
+  UNETK_CUDA(launch_pdl(gate_apply_kernel, dim3(pix_grid(npix, lpp, 4)), dim3(kThreads), 0, st, static_cast<const __nv_bfloat16*>(x), x_ld, s, sc1,
+                                                                sh1, static_cast<__nv_bfloat16*>(out), out_ld, npix, F));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -440,11 +454,11 @@ int gate_bwd_psi_run(const void* dout, int64_t dout_ld, const void* x, int64_t x
   const __nv_bfloat16* xx = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(dx);
   if (dx_accumulate)
-    gate_bwd_psi_kernel<true><<<grid, kThreads, 0, st>>>(d, dout_ld, xx, x_ld, s, sc1, sh1, mean1, o, dx_ld, dz, partial, npix, F);
+    UNETK_CUDA(launch_pdl(gate_bwd_psi_kernel<true>, dim3(grid), dim3(kThreads), 0, st, d, dout_ld, xx, x_ld, s, sc1, sh1, mean1, o, dx_ld, dz, partial, npix, F));
   else
-    gate_bwd_psi_kernel<false><<<grid, kThreads, 0, st>>>(d, dout_ld, xx, x_ld, s, sc1, sh1, mean1, o, dx_ld, dz, partial, npix, F);
+    UNETK_CUDA(launch_pdl(gate_bwd_psi_kernel<false>, dim3(grid), dim3(kThreads), 0, st, d, dout_ld, xx, x_ld, s, sc1, sh1, mean1, o, dx_ld, dz, partial, npix, F));
   UNETK_LAUNCHED();
-  pair_sums_kernel<<<1, 32, 0, st>>>(partial, grid, sums);
+  UNETK_CUDA(launch_pdl(pair_sums_kernel, dim3(1), dim3(32), 0, st, partial, grid, sums));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -461,9 +475,9 @@ int gate_bwd_reduce_run(const void* rawg, int64_t rawg_ld, const void* rawx, int
   int ppb = kThreads / (F / 8);
   if (ppb < 1) ppb = 1;
   const size_t smem = static_cast<size_t>(ppb) * 5 * F * sizeof(float);
-  gate_bwd_reduce_kernel<<<grid, kThreads, smem, st>>>(B, partial);
+  UNETK_CUDA(launch_pdl(gate_bwd_reduce_kernel, dim3(grid), dim3(kThreads), smem, st, B, partial));
   UNETK_LAUNCHED();
-  gate_bwd_sums_kernel<<<(5 * F + 127) / 128, 128, 0, st>>>(partial, grid, F, sums_g, sums_x, dwpsi, dbpsi, accumulate);
+  UNETK_CUDA(launch_pdl(gate_bwd_sums_kernel, dim3((5 * F + 127) / 128), dim3(128), 0, st, partial, grid, F, sums_g, sums_x, dwpsi, dbpsi, accumulate));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -476,8 +490,8 @@ int gate_bwd_apply_run(const void* rawg, int64_t rawg_ld, const void* rawx, int6
   UNETK_CHECK(pow2_f(F), -1, "gate: F_int=%d must be a power of two in [8,256]", F);
   GateBwdArgs B{gate_args(rawg, rawg_ld, rawx, rawx_ld, scg, shg, scx, shx, wpsi, nullptr, npix, F), nullptr, nullptr,
                 s, dz, sc1, coef1};
-  gate_bwd_apply_kernel<<<chan_grid(npix, F), kThreads, 0, st>>>(B, coefg, coefx, static_cast<__nv_bfloat16*>(drawg),
-                                                                drawg_ld, static_cast<__nv_bfloat16*>(drawx), drawx_ld);
+  UNETK_CUDA(launch_pdl(gate_bwd_apply_kernel, dim3(chan_grid(npix, F)), dim3(kThreads), 0, st, B, coefg, coefx, static_cast<__nv_bfloat16*>(drawg),
+                                                                drawg_ld, static_cast<__nv_bfloat16*>(drawx), drawx_ld));
   UNETK_LAUNCHED();
   return 0;
 }

@@ -1,6 +1,7 @@
 #include "host_common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -24,6 +25,16 @@ const char* last_error() { return g_err; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  // Measured on B200 (UNet B=16 512^2, CUDA graphs, same box, 2 rounds): PDL off 24.12 / 23.85 ms per step, on 24.79 /
+  // 24.76 ms.  The kernels are persistent 1-CTA-per-SM grids that fill shared memory: a dependent CTA cannot become
+  // resident before its predecessor's CTA on that SM exits, so only ~1 us of prologue could overlap, and the early
+  // scheduling costs more than that.  Off by default; UNETK_PDL=1 enables it (every kernel honours griddepcontrol.wait).
+  if (v < 0) { const char* e = getenv("UNETK_PDL"); v = e ? atoi(e) : 0; }
+  return v != 0;
+}
 
 int num_sms() {
   static int cached = 0;

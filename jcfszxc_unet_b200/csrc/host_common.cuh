@@ -38,6 +38,28 @@ void count_launch();
     UNETK_CUDA(cudaGetLastError());   \
   } while (0)
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining
+// (its CTAs run their prologue — barrier init, TMEM allocation, descriptor prefetch — and then block in
+// griddepcontrol.wait until the predecessor has completed and flushed).  EVERY kernel launched through this helper
+// must execute pdl_wait() (ptx.cuh) before its first access to global memory.  Measured slower on the UNet step
+// (host_common.cu): a plain launch unless UNETK_PDL=1.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 long long launch_count();
 int num_sms();
 const char* last_error();

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(kThreads)
 head_loss_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ w,
                      const float* __restrict__ bias, const float* __restrict__ labels, float* __restrict__ logits,
                      int post_sigmoid, int64_t npix, int C, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   const int lpp = C >> 3;                 // lanes per pixel (power of two <= 32)
   const int gpb = kThreads / lpp;         // pixel groups per block
   const int sub = threadIdx.x % lpp, grp = threadIdx.x / lpp;
@@ -92,6 +94,8 @@ head_loss_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const floa
 }
 
 __global__ void loss_sums_kernel(const float* __restrict__ partial, int nblk, double* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
   const int k = threadIdx.x;
   if (k >= 4) return;
   double s = 0.0;
@@ -101,6 +105,8 @@ __global__ void loss_sums_kernel(const float* __restrict__ partial, int nblk, do
 
 // out[0]=loss out[1]=bce out[2]=dice out[3]=1/npix  out[4]=cA out[5]=cB  (d dice / d p_i = y_i*cA - cB)
 __global__ void loss_finalize_kernel(const double* __restrict__ sums, double npix_total, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x != 0) return;
   const double bce = sums[0] / npix_total;
   const double inter = 2.0 * sums[1];
@@ -130,6 +136,8 @@ head_loss_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const floa
                      const float* __restrict__ fin, const float* __restrict__ dlogits, float gscale, int post_sigmoid,
                      __nv_bfloat16* __restrict__ dx, int64_t dx_ld, int64_t npix, int C,
                      float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   const int lpp = C >> 3;
   const int gpb = kThreads / lpp;
   const int sub = threadIdx.x % lpp, grp = threadIdx.x / lpp;
@@ -196,6 +204,8 @@ head_loss_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const floa
 
 __global__ void head_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* dw, float* db,
                                          int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > C) return;
   double s = 0.0;
@@ -222,19 +232,19 @@ int head_loss_fwd_run(const void* x, int64_t ld, const float* w, const float* bi
                       int post_sigmoid, int64_t npix, int C, float* partial, double* sums, cudaStream_t s) {
   UNETK_CHECK(head_c_ok(C), -1, "head: C=%d must be a power of two in [8,256]", C);
   const int grid = head_grid(npix, C);
-  head_loss_fwd_kernel<<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, w, bias, labels, logits,
-                                                post_sigmoid, npix, C, partial);
+  UNETK_CUDA(launch_pdl(head_loss_fwd_kernel, dim3(grid), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(x), ld, w, bias, labels, logits,
+                                                post_sigmoid, npix, C, partial));
   UNETK_LAUNCHED();
   if (labels != nullptr) {
     UNETK_CHECK(sums != nullptr, -1, "head_loss_fwd: sums is null");
-    loss_sums_kernel<<<1, 32, 0, s>>>(partial, grid, sums);
+    UNETK_CUDA(launch_pdl(loss_sums_kernel, dim3(1), dim3(32), 0, s, partial, grid, sums));
     UNETK_LAUNCHED();
   }
   return 0;
 }
 
 int loss_finalize_run(const double* sums, double npix_total, float* out, cudaStream_t s) {
-  loss_finalize_kernel<<<1, 32, 0, s>>>(sums, npix_total, out);
+  UNETK_CUDA(launch_pdl(loss_finalize_kernel, dim3(1), dim3(32), 0, s, sums, npix_total, out));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -248,11 +258,11 @@ int head_loss_bwd_run(const void* x, int64_t ld, const float* w, const float* la
   const int grid = head_grid(npix, C);
   const int gpb = kThreads / (C / 8);
   const size_t smem = static_cast<size_t>(gpb) * (C + 1) * sizeof(float);
-  head_loss_bwd_kernel<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(x), ld, w, labels, logits, fin,
+  UNETK_CUDA(launch_pdl(head_loss_bwd_kernel, dim3(grid), dim3(kThreads), smem, s, static_cast<const __nv_bfloat16*>(x), ld, w, labels, logits, fin,
                                                    dlogits, gscale, post_sigmoid, static_cast<__nv_bfloat16*>(dx), dx_ld,
-                                                   npix, C, partial);
+                                                   npix, C, partial));
   UNETK_LAUNCHED();
-  head_bwd_finalize_kernel<<<(C + 1 + 127) / 128, 128, 0, s>>>(partial, grid, C, dw, db, accumulate);
+  UNETK_CUDA(launch_pdl(head_bwd_finalize_kernel, dim3((C + 1 + 127) / 128), dim3(128), 0, s, partial, grid, C, dw, db, accumulate));
   UNETK_LAUNCHED();
   return 0;
 }

@@ -13,6 +13,8 @@ constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) sqnorm_kernel(const float* __restrict__ g, int64_t n,
                                                           float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   float s = 0.f;
   const int64_t n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -37,6 +39,8 @@ __global__ void __launch_bounds__(kThreads) sqnorm_kernel(const float* __restric
 // the gradient (1/world_size after a sum all-reduce).
 __global__ void clip_finalize_kernel(const float* __restrict__ partial, int nblk, float gscale, float max_norm,
                                      float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x != 0) return;
   double s = 0.0;
   for (int b = 0; b < nblk; ++b) s += partial[b];
@@ -51,6 +55,8 @@ __global__ void __launch_bounds__(kThreads)
 rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq, float* __restrict__ buf,
                int64_t n, float lr, float alpha, float eps, float wd, float momentum,
                const float* __restrict__ clip) {
+  pdl_trigger();
+  pdl_wait();
   const float coef = clip ? __ldg(clip + 1) : 1.f;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * kThreads) {
@@ -83,9 +89,9 @@ int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, 
                        cudaStream_t s) {
   UNETK_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, -1, "grad buffer must be 16-byte aligned");
   const int nb = sqnorm_blocks(n);
-  sqnorm_kernel<<<nb, kThreads, 0, s>>>(g, n, partial);
+  UNETK_CUDA(launch_pdl(sqnorm_kernel, dim3(nb), dim3(kThreads), 0, s, g, n, partial));
   UNETK_LAUNCHED();
-  clip_finalize_kernel<<<1, 32, 0, s>>>(partial, nb, gscale, max_norm, out);
+  UNETK_CUDA(launch_pdl(clip_finalize_kernel, dim3(1), dim3(32), 0, s, partial, nb, gscale, max_norm, out));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -96,7 +102,7 @@ int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, floa
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
-  rmsprop_kernel<<<static_cast<int>(b), kThreads, 0, s>>>(p, g, sq, buf, n, lr, alpha, eps, wd, momentum, clip);
+  UNETK_CUDA(launch_pdl(rmsprop_kernel, dim3(static_cast<int>(b)), dim3(kThreads), 0, s, p, g, sq, buf, n, lr, alpha, eps, wd, momentum, clip));
   UNETK_LAUNCHED();
   return 0;
 }

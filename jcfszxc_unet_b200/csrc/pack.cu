@@ -49,11 +49,15 @@ __device__ __forceinline__ void pack_tile(const PackJob& j, int tile, float* s /
 }
 
 __global__ void __launch_bounds__(256) pack_weight_kernel(const PackJob job) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float smem_pack[];
   pack_tile(job, blockIdx.x, smem_pack);
 }
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob* __restrict__ table, int n) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float smem_pack[];
   // binary search: last job whose first_tile <= blockIdx.x
   int lo = 0, hi = n - 1;
@@ -76,7 +80,7 @@ long long pack_tiles(int A, int B) {
 int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, cudaStream_t stream) {
   UNETK_CHECK(T <= kMaxT, -1, "pack_weight: T=%d > %d taps", T, kMaxT);
   PackJob j{src, static_cast<__nv_bfloat16*>(dst_ab), static_cast<__nv_bfloat16*>(dst_ba), A, B, T, 0, 0};
-  pack_weight_kernel<<<static_cast<int>(pack_tiles(A, B)), 256, tile_smem(T), stream>>>(j);
+  UNETK_CUDA(launch_pdl(pack_weight_kernel, dim3(static_cast<int>(pack_tiles(A, B))), dim3(256), tile_smem(T), stream, j));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -85,8 +89,7 @@ int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, 
 int pack_weights_run(const long long* table, int n, long long total_tiles, cudaStream_t stream) {
   UNETK_CHECK(table != nullptr && n > 0 && total_tiles > 0 && total_tiles < (1ll << 31), -1, "pack_weights: bad arguments");
   static_assert(sizeof(PackJob) == 64, "PackJob must be 8 x int64");
-  pack_weights_kernel<<<static_cast<int>(total_tiles), 256, tile_smem(kMaxT), stream>>>(
-      reinterpret_cast<const PackJob*>(table), n);
+  UNETK_CUDA(launch_pdl(pack_weights_kernel, dim3(static_cast<int>(total_tiles)), dim3(256), tile_smem(kMaxT), stream, reinterpret_cast<const PackJob*>(table), n));
   UNETK_LAUNCHED();
   return 0;
 }

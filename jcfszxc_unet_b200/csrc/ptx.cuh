@@ -273,6 +273,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, b
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Programmatic dependent launch (host side: launch_pdl in host_common.cuh).  pdl_trigger(): dependents of this grid may
+// be scheduled from now on; pdl_wait(): block until the grids this one depends on have completed and their memory is
+// visible.  Nothing produced or still read by an earlier kernel may be touched before pdl_wait().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* gptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr));
 }

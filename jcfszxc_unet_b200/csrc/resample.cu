@@ -65,6 +65,8 @@ struct AddArgs {
 // Every partial sum is rounded to bf16, like the chain of bf16 tensor adds it replaces.
 template <int NSRC, bool ACC>
 __global__ void __launch_bounds__(kThreads) add_n_kernel(const AddArgs A) {
+  pdl_trigger();
+  pdl_wait();
   Lanes L(A.C);
   if (!L.active) return;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
@@ -123,9 +125,10 @@ __global__ void __launch_bounds__(kThreads) add_n_kernel(const AddArgs A) {
 }
 
 template <int NSRC>
-void launch_add(const AddArgs& A, int grid, cudaStream_t s) {
-  if (A.accumulate) add_n_kernel<NSRC, true><<<grid, kThreads, 0, s>>>(A);
-  else add_n_kernel<NSRC, false><<<grid, kThreads, 0, s>>>(A);
+int launch_add(const AddArgs& A, int grid, cudaStream_t s) {
+  if (A.accumulate) UNETK_CUDA(launch_pdl(add_n_kernel<NSRC, true>, dim3(grid), dim3(kThreads), 0, s, A));
+  else UNETK_CUDA(launch_pdl(add_n_kernel<NSRC, false>, dim3(grid), dim3(kThreads), 0, s, A));
+  return 0;
 }
 
 // ------------------------------------------------------------------ nearest 2x
@@ -135,6 +138,8 @@ template <bool BWD, bool ACC>
 __global__ void __launch_bounds__(kThreads)
 nearest2x_kernel(const __nv_bfloat16* __restrict__ src, int64_t src_ld, __nv_bfloat16* __restrict__ dst,
                  int64_t dst_ld, int N, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   // H, W: low-resolution size.  fwd: src low -> dst high.  bwd: src high (dy) -> dst low (dx).
   Lanes L(C);
   if (!L.active) return;
@@ -187,6 +192,8 @@ __device__ __forceinline__ void src_index(float scale, int o, int in, int* i0, i
 __global__ void __launch_bounds__(kThreads)
 bilinear2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, __nv_bfloat16* __restrict__ y, int64_t y_ld,
                       int N, int H, int W, int C, float sh, float sw) {
+  pdl_trigger();
+  pdl_wait();
   Lanes L(C);
   if (!L.active) return;
   const int Ho = 2 * H, Wo = 2 * W;
@@ -245,6 +252,8 @@ template <bool ACC>
 __global__ void __launch_bounds__(kThreads)
 bilinear2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_ld, __nv_bfloat16* __restrict__ dx,
                       int64_t dx_ld, int N, int H, int W, int C, float sh, float sw) {
+  pdl_trigger();
+  pdl_wait();
   Lanes L(C);
   if (!L.active) return;
   const int Ho = 2 * H, Wo = 2 * W;
@@ -289,6 +298,8 @@ bilinear2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_ld, __nv_
 
 __global__ void copy_f32_strided_kernel(float* __restrict__ dst, int64_t ds, const float* __restrict__ src, int64_t ss,
                                         int64_t n, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float v = src[i * ss];
@@ -330,9 +341,9 @@ int upsample_nearest2x_run(const void* src, int64_t src_ld, void* dst, int64_t d
   const int grid = lanes_grid(units, C, 2);
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(src);
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
-  if (!backward) nearest2x_kernel<false, false><<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C);
-  else if (accumulate) nearest2x_kernel<true, true><<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C);
-  else nearest2x_kernel<true, false><<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C);
+  if (!backward) UNETK_CUDA(launch_pdl(nearest2x_kernel<false, false>, dim3(grid), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C));
+  else if (accumulate) UNETK_CUDA(launch_pdl(nearest2x_kernel<true, true>, dim3(grid), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C));
+  else UNETK_CUDA(launch_pdl(nearest2x_kernel<true, false>, dim3(grid), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -348,9 +359,9 @@ int upsample_bilinear2x_run(const void* src, int64_t src_ld, void* dst, int64_t 
   const int grid = lanes_grid(units, C, 2);
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(src);
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
-  if (!backward) bilinear2x_fwd_kernel<<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C, sh, sw);
-  else if (accumulate) bilinear2x_bwd_kernel<true><<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C, sh, sw);
-  else bilinear2x_bwd_kernel<false><<<grid, kThreads, 0, s>>>(a, src_ld, d, dst_ld, N, H, W, C, sh, sw);
+  if (!backward) UNETK_CUDA(launch_pdl(bilinear2x_fwd_kernel, dim3(grid), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C, sh, sw));
+  else if (accumulate) UNETK_CUDA(launch_pdl(bilinear2x_bwd_kernel<true>, dim3(grid), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C, sh, sw));
+  else UNETK_CUDA(launch_pdl(bilinear2x_bwd_kernel<false>, dim3(grid), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C, sh, sw));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -360,7 +371,7 @@ int copy_f32_strided_run(float* dst, int64_t ds, const float* src, int64_t ss, i
   UNETK_CHECK(dst && src && n > 0 && ds > 0 && ss > 0, -1, "copy_f32_strided: bad arguments");
   int64_t b = (n + 255) / 256;
   if (b > 1024) b = 1024;
-  copy_f32_strided_kernel<<<static_cast<int>(b), 256, 0, s>>>(dst, ds, src, ss, n, accumulate);
+  UNETK_CUDA(launch_pdl(copy_f32_strided_kernel, dim3(static_cast<int>(b)), dim3(256), 0, s, dst, ds, src, ss, n, accumulate));
   UNETK_LAUNCHED();
   return 0;
 }

@@ -63,6 +63,8 @@ template <int CMAX>   // TMEM columns allocated = max Cout handled (64 / 128 / 2
 __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) stem_tc_fwd_kernel(const StemTc G, const float* __restrict__ wgt,
                                                             const float* __restrict__ bias,
                                                             __nv_bfloat16* __restrict__ y, int64_t y_ld, int num_tiles) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint8_t* sA = smem;                                  // [kChunks][128 rows][16 B] (12 KB); 16 KB: also output staging
@@ -194,7 +196,7 @@ int stem_tc_fwd_launch(const StemTc& G, const float* w, const float* bias, void*
   // stores run
   const int per_sm = (512 / CMAX) < 6 ? (512 / CMAX) : 6;   // 6 / 4 / 2
   const int grid = tiles < per_sm * num_sms() ? tiles : per_sm * num_sms();
-  stem_tc_fwd_kernel<CMAX><<<grid, kTile, smem, s>>>(G, w, bias, static_cast<__nv_bfloat16*>(y), y_ld, tiles);
+  UNETK_CUDA(launch_pdl(stem_tc_fwd_kernel<CMAX>, dim3(grid), dim3(kTile), smem, s, G, w, bias, static_cast<__nv_bfloat16*>(y), y_ld, tiles));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -211,6 +213,8 @@ struct StemTcW {
 
 __global__ void __launch_bounds__(kTile) stem_tc_wgrad_kernel(const __grid_constant__ StemTcW P, float* __restrict__ partial,
                                                               int num_tiles) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   constexpr uint32_t kBox = kTile * 128;               // 16 KB: [128 px][64 elements] bf16
@@ -299,6 +303,8 @@ __global__ void __launch_bounds__(kTile) stem_tc_wgrad_kernel(const __grid_const
 
 __global__ void stem_tc_wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ dw,
                                             int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
@@ -357,10 +363,10 @@ int stem_tc_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_
     UNETK_CUDA(cudaFuncSetAttribute(stem_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  stem_tc_wgrad_kernel<<<grid, kTile, smem, s>>>(P, static_cast<float*>(ws), static_cast<int>(tiles64));
+  UNETK_CUDA(launch_pdl(stem_tc_wgrad_kernel, dim3(grid), dim3(kTile), smem, s, P, static_cast<float*>(ws), static_cast<int>(tiles64)));
   UNETK_LAUNCHED();
   const int n = Cout * 9 * Cin;
-  stem_tc_wgrad_reduce_kernel<<<(n + 127) / 128, 128, 0, s>>>(static_cast<const float*>(ws), grid, n, dw, accumulate);
+  UNETK_CUDA(launch_pdl(stem_tc_wgrad_reduce_kernel, dim3((n + 127) / 128), dim3(128), 0, s, static_cast<const float*>(ws), grid, n, dw, accumulate));
   UNETK_LAUNCHED();
   return 0;
 }

@@ -64,6 +64,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on global memory
+  pdl_trigger();
+  pdl_wait();
 
   const int items_per_split = p.taps * p.m_tiles * p.n_tiles;
   const int num_items = items_per_split * p.ksplit;
@@ -190,6 +193,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
 template <int TAPS>
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ksplit, int M,
                                     int Nn, int64_t sm, int64_t sn, int64_t st, int accumulate, FastDiv fd_n) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t plane = static_cast<uint32_t>(M) * static_cast<uint32_t>(Nn);   // < 2^31 (checked on the host)
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < plane; j += gridDim.x * blockDim.x) {
     uint32_t m, n;
@@ -214,6 +219,8 @@ __global__ void wgrad_reduce_sliced_kernel(const float* __restrict__ partial, fl
                                            int taps, int M, int Nn, int64_t sm, int64_t sn, int64_t st, int accumulate,
                                            FastDiv fd_n) {
   __shared__ float red[S][33];
+  pdl_trigger();
+  pdl_wait();
   const uint32_t plane = static_cast<uint32_t>(M) * static_cast<uint32_t>(Nn);
   const uint32_t j = blockIdx.x * 32 + threadIdx.x;
   const int tap = blockIdx.y;
@@ -245,7 +252,7 @@ int launch(const WgradParams& p, cudaStream_t stream) {
   }
   const int items = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = items < num_sms() ? items : num_sms();
-  wgrad_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  UNETK_CUDA(launch_pdl(wgrad_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, p));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -280,18 +287,18 @@ int wgrad_reduce_launch(const float* partial, float* dw, int ksplit, int taps, i
   if (ksplit >= 8) {
     const dim3 grid(static_cast<unsigned>((plane + 31) / 32), taps);
     if (ksplit >= 64)
-      wgrad_reduce_sliced_kernel<32><<<grid, dim3(32, 32), 0, stream>>>(partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd);
+      UNETK_CUDA(launch_pdl(wgrad_reduce_sliced_kernel<32>, grid, dim3(32, 32), 0, stream, partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd));
     else if (ksplit >= 24)
-      wgrad_reduce_sliced_kernel<16><<<grid, dim3(32, 16), 0, stream>>>(partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd);
+      UNETK_CUDA(launch_pdl(wgrad_reduce_sliced_kernel<16>, grid, dim3(32, 16), 0, stream, partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd));
     else
-      wgrad_reduce_sliced_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd);
+      UNETK_CUDA(launch_pdl(wgrad_reduce_sliced_kernel<8>, grid, dim3(32, 8), 0, stream, partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd));
     UNETK_LAUNCHED();
     return 0;
   }
   switch (taps) {
-    case 9: wgrad_reduce_kernel<9><<<blocks, 256, 0, stream>>>(partial, dw, ksplit, M, Nn, sm, sn, st, accumulate, fd); break;
-    case 4: wgrad_reduce_kernel<4><<<blocks, 256, 0, stream>>>(partial, dw, ksplit, M, Nn, sm, sn, st, accumulate, fd); break;
-    case 1: wgrad_reduce_kernel<1><<<blocks, 256, 0, stream>>>(partial, dw, ksplit, M, Nn, sm, sn, st, accumulate, fd); break;
+    case 9: UNETK_CUDA(launch_pdl(wgrad_reduce_kernel<9>, dim3(blocks), dim3(256), 0, stream, partial, dw, ksplit, M, Nn, sm, sn, st, accumulate, fd)); break;
+    case 4: UNETK_CUDA(launch_pdl(wgrad_reduce_kernel<4>, dim3(blocks), dim3(256), 0, stream, partial, dw, ksplit, M, Nn, sm, sn, st, accumulate, fd)); break;
+    case 1: UNETK_CUDA(launch_pdl(wgrad_reduce_kernel<1>, dim3(blocks), dim3(256), 0, stream, partial, dw, ksplit, M, Nn, sm, sn, st, accumulate, fd)); break;
     default: UNETK_CHECK(false, -1, "wgrad_reduce: taps=%d (1, 4 or 9)", taps);
   }
   UNETK_LAUNCHED();

@@ -85,6 +85,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on global memory
+  pdl_trigger();
+  pdl_wait();
 
   const int items_per_split = p.paired ? 2 * p.n_tiles : 3 * p.m_tiles * p.n_tiles;
   const int num_items = items_per_split * p.ksplit;
@@ -306,7 +309,7 @@ int launch(const W3Params& p, const W3Plan& pl, cudaStream_t stream) {
   }
   const int items = (pl.paired ? 2 * pl.n_tiles : 3 * pl.m_tiles * pl.n_tiles) * pl.ksplit;
   const int grid = items < num_sms() ? items : num_sms();
-  wgrad3x3_kernel<NT><<<grid, kThreads, pl.smem_bytes, stream>>>(p);
+  UNETK_CUDA(launch_pdl(wgrad3x3_kernel<NT>, dim3(grid), dim3(kThreads), pl.smem_bytes, stream, p));
   UNETK_LAUNCHED();
   return 0;
 }
