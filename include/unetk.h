@@ -239,6 +239,23 @@ int unetk_upsample_bilinear2x_bwd(const void* dy, int64_t dy_ld, void* dx, int64
                                   int W, int C, void* stream);
 /* dst[i*dst_stride] (+)= src[i*src_stride], fp32, i < n: derived weight caches (a 1x1 stem kernel embedded in the
  * centre tap of the 3x3 stem kernel, RRCNN_block.Conv_1x1 on the image, unet_parts.py:143) and their gradients. */
+/* Training-batch assembly on the device (train.py:200-253: a Python loop of numpy slices + np.stack + a synchronous
+ * H2D copy per step in the reference).  images: fp32 pool, element strides (si_n, si_c, si_h, si_w) of the logical
+ * [Nimg, C, H, W] view; labels: fp32 pool [Nimg, H, W] with strides (sl_n, sl_h, sl_w); centers: device int32 [B][3] =
+ * (image index, x = index along H, y = index along W) as drawn from the reference's filtered sample map.  Writes
+ * out_images fp32 [B][P][P][C] (the channels_last batch of train.py:248-252) and out_labels fp32 [B][P][P]:
+ * patch b = rows [x - P/2, x + P/2) x columns [y - P/2, y + P/2).  Bit-exact copies.  labels / out_labels may both
+ * be NULL (inference: evaluate.py:72-79 cuts image patches only). */
+int unetk_gather_patches(const float* images, int64_t si_n, int64_t si_c, int64_t si_h, int64_t si_w, const float* labels,
+                         int64_t sl_n, int64_t sl_h, int64_t sl_w, const int32_t* centers, int B, int C, int P, int H,
+                         int W, float* out_images, float* out_labels, void* stream);
+/* Sliding-window inference on the device (predict_full_image, evaluate.py:28-96): acc / cnt are double [H][W] maps
+ * (zeroed by the caller).  tile_accumulate adds the B patch predictions logits[b] (fp32 [P][P], sigmoid applied when
+ * apply_sigmoid != 0) at their top-left corners pos[b] = (y, x) in batch order and counts the coverage;
+ * tile_finalize writes out = acc / cnt where cnt != 0, else 0. */
+int unetk_tile_accumulate(const float* logits, const int32_t* pos, int B, int P, int H, int W, int apply_sigmoid,
+                          double* acc, double* cnt, void* stream);
+int unetk_tile_finalize(const double* acc, const double* cnt, int64_t n, double* out, void* stream);
 int unetk_copy_f32_strided(float* dst, int64_t dst_stride, const float* src, int64_t src_stride, int64_t n,
                            int accumulate, void* stream);
 

@@ -72,6 +72,9 @@ SIGNATURES = {
     "unetk_upsample_nearest2x_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_upsample_bilinear2x_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
     "unetk_upsample_bilinear2x_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_gather_patches": (_i, [_fp, _i64, _i64, _i64, _i64, _fp, _i64, _i64, _i64, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
+    "unetk_tile_accumulate": (_i, [_fp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "unetk_tile_finalize": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "unetk_copy_f32_strided": (_i, [_fp, _i64, _fp, _i64, _i64, _i, _vp]),
     "unetk_gate_partial_floats": (_sz, [_i64, _i]),
     "unetk_gate_fwd": (_i, [_vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _i64, _i, _vp]),

@@ -411,6 +411,24 @@ int unetk_upsample_bilinear2x_bwd(const void* dy, int64_t dy_ld, void* dx, int64
   UNETK_CHECK(dy && dx, -1, "upsample_bilinear2x_bwd: null pointer");
   return upsample_bilinear2x_run(dy, dy_ld, dx, dx_ld, 1, accumulate, N, H, W, C, S(stream));
 }
+int unetk_gather_patches(const float* images, int64_t si_n, int64_t si_c, int64_t si_h, int64_t si_w, const float* labels,
+                         int64_t sl_n, int64_t sl_h, int64_t sl_w, const int32_t* centers, int B, int C, int P, int H,
+                         int W, float* out_images, float* out_labels, void* stream) {
+  UNETK_CHECK(images && centers && out_images && ((labels == nullptr) == (out_labels == nullptr)), -1,
+              "gather_patches: null pointer (labels and out_labels go together)");
+  UNETK_CHECK(B > 0 && C > 0 && P > 0 && P % 2 == 0 && H >= P && W >= P, -1, "gather_patches: B=%d C=%d P=%d H=%d W=%d", B, C, P, H, W);
+  return gather_patches_run(images, si_n, si_c, si_h, si_w, labels, sl_n, sl_h, sl_w, centers, B, C, P, H, W, out_images,
+                            out_labels, S(stream));
+}
+int unetk_tile_accumulate(const float* logits, const int32_t* pos, int B, int P, int H, int W, int apply_sigmoid,
+                          double* acc, double* cnt, void* stream) {
+  UNETK_CHECK(logits && pos && acc && cnt && B > 0 && P > 0 && H > 0 && W > 0, -1, "tile_accumulate: bad arguments");
+  return tile_accumulate_run(logits, pos, B, P, H, W, apply_sigmoid, acc, cnt, S(stream));
+}
+int unetk_tile_finalize(const double* acc, const double* cnt, int64_t n, double* out, void* stream) {
+  UNETK_CHECK(acc && cnt && out && n > 0, -1, "tile_finalize: bad arguments");
+  return tile_finalize_run(acc, cnt, n, out, S(stream));
+}
 int unetk_copy_f32_strided(float* dst, int64_t dst_stride, const float* src, int64_t src_stride, int64_t n,
                            int accumulate, void* stream) {
   return copy_f32_strided_run(dst, dst_stride, src, src_stride, n, accumulate, S(stream));

@@ -72,6 +72,12 @@ int upsample_nearest2x_run(const void* src, int64_t src_ld, void* dst, int64_t d
                            int N, int H, int W, int C, cudaStream_t s);
 int upsample_bilinear2x_run(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int backward, int accumulate,
                             int N, int H, int W, int C, cudaStream_t s);
+int gather_patches_run(const float* images, int64_t si_n, int64_t si_c, int64_t si_h, int64_t si_w, const float* labels,
+                       int64_t sl_n, int64_t sl_h, int64_t sl_w, const int* centers, int B, int C, int P, int H, int W,
+                       float* out_images, float* out_labels, cudaStream_t s);
+int tile_accumulate_run(const float* logits, const int* pos, int B, int P, int H, int W, int apply_sigmoid, double* acc,
+                        double* cnt, cudaStream_t s);
+int tile_finalize_run(const double* acc, const double* cnt, long long n, double* out, cudaStream_t s);
 int copy_f32_strided_run(float* dst, int64_t ds, const float* src, int64_t ss, int64_t n, int accumulate,
                          cudaStream_t s);
 // elementwise.cu

@@ -366,6 +366,96 @@ int upsample_bilinear2x_run(const void* src, int64_t src_ld, void* dst, int64_t 
   return 0;
 }
 
+// ------------------------------------------------------------------ patch gather (train.py:200-253 on the device)
+// out_images[b][i][j][c] = images[img_b][c][x_b - P/2 + i][y_b - P/2 + j]  (fp32, channels_last batch);
+// out_labels[b][i][j]    = labels[img_b][x_b - P/2 + i][y_b - P/2 + j].   centers = int32 [B][3] = (img, x, y).
+struct GatherArgs {
+  const float* images; long long si_n, si_c, si_h, si_w;
+  const float* labels; long long sl_n, sl_h, sl_w;
+  const int* centers;
+  float* out_images; float* out_labels;
+  int B, C, P, H, W;
+};
+__global__ void __launch_bounds__(kThreads) gather_patches_kernel(const GatherArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = static_cast<long long>(a.B) * a.P * a.P;
+  const int half = a.P / 2;
+  for (long long u = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; u < total;
+       u += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(u % a.P), i = static_cast<int>((u / a.P) % a.P), b = static_cast<int>(u / (static_cast<long long>(a.P) * a.P));
+    const int img = __ldg(a.centers + 3 * b), x = __ldg(a.centers + 3 * b + 1) - half + i, y = __ldg(a.centers + 3 * b + 2) - half + j;
+    const bool ok = x >= 0 && x < a.H && y >= 0 && y < a.W;   // the host validates the centres; never read out of bounds
+    const float* src = a.images + img * a.si_n + x * a.si_h + y * a.si_w;
+    float* dst = a.out_images + u * a.C;
+    for (int c = 0; c < a.C; ++c) dst[c] = ok ? __ldg(src + c * a.si_c) : 0.f;
+    if (a.out_labels != nullptr) a.out_labels[u] = ok ? __ldg(a.labels + img * a.sl_n + x * a.sl_h + y * a.sl_w) : 0.f;
+  }
+}
+int gather_patches_run(const float* images, int64_t si_n, int64_t si_c, int64_t si_h, int64_t si_w, const float* labels,
+                       int64_t sl_n, int64_t sl_h, int64_t sl_w, const int* centers, int B, int C, int P, int H, int W,
+                       float* out_images, float* out_labels, cudaStream_t s) {
+  GatherArgs a{images, si_n, si_c, si_h, si_w, labels, sl_n, sl_h, sl_w, centers, out_images, out_labels, B, C, P, H, W};
+  const long long total = static_cast<long long>(B) * P * P;
+  long long blocks = (total + kThreads - 1) / kThreads;
+  if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+  UNETK_CUDA(launch_pdl(gather_patches_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kThreads), 0, s, a));
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------ sliding-window inference (evaluate.py:28-96)
+// acc[h][w] += p_b[h - y_b][w - x_b] for every patch b of the batch covering (h, w), in batch order (the order of the
+// reference's accumulation loop, evaluate.py:84-86); cnt likewise += 1.  One thread per output pixel: no atomics.
+__global__ void __launch_bounds__(kThreads) tile_accumulate_kernel(const float* __restrict__ logits, const int* __restrict__ pos,
+                                                                   int B, int P, int H, int W, int apply_sigmoid,
+                                                                   double* __restrict__ acc, double* __restrict__ cnt) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = static_cast<long long>(H) * W;
+  for (long long u = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; u < total;
+       u += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(u % W), h = static_cast<int>(u / W);
+    double a = acc[u], c = cnt[u];
+    for (int b = 0; b < B; ++b) {
+      const int y = __ldg(pos + 2 * b), x = __ldg(pos + 2 * b + 1);
+      if (h >= y && h < y + P && w >= x && w < x + P) {
+        float v = __ldg(logits + (static_cast<long long>(b) * P + (h - y)) * P + (w - x));
+        if (apply_sigmoid) v = 1.f / (1.f + expf(-v));
+        a += static_cast<double>(v);
+        c += 1.0;
+      }
+    }
+    acc[u] = a;
+    cnt[u] = c;
+  }
+}
+__global__ void tile_finalize_kernel(const double* __restrict__ acc, const double* __restrict__ cnt, long long n,
+                                     double* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long u = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; u < n;
+       u += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[u] = cnt[u] != 0.0 ? acc[u] / cnt[u] : 0.0;   // np.divide(..., where=count != 0), evaluate.py:89-91
+}
+int tile_accumulate_run(const float* logits, const int* pos, int B, int P, int H, int W, int apply_sigmoid, double* acc,
+                        double* cnt, cudaStream_t s) {
+  const long long total = static_cast<long long>(H) * W;
+  long long blocks = (total + kThreads - 1) / kThreads;
+  if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+  UNETK_CUDA(launch_pdl(tile_accumulate_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kThreads), 0, s, logits, pos, B, P,
+                        H, W, apply_sigmoid, acc, cnt));
+  UNETK_LAUNCHED();
+  return 0;
+}
+int tile_finalize_run(const double* acc, const double* cnt, long long n, double* out, cudaStream_t s) {
+  long long blocks = (n + kThreads - 1) / kThreads;
+  if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+  UNETK_CUDA(launch_pdl(tile_finalize_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kThreads), 0, s, acc, cnt, n, out));
+  UNETK_LAUNCHED();
+  return 0;
+}
+
 int copy_f32_strided_run(float* dst, int64_t ds, const float* src, int64_t ss, int64_t n, int accumulate,
                          cudaStream_t s) {
   UNETK_CHECK(dst && src && n > 0 && ds > 0 && ss > 0, -1, "copy_f32_strided: bad arguments");
