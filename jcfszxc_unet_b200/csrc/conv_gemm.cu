@@ -42,8 +42,8 @@ template <int BN>
 struct Cfg {
   static constexpr uint32_t kBBytes = BN * kTileK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 7);
-  static constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: all powers of two >= 32
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 7));
+  static constexpr uint32_t kTmemCols = (BN == 192) ? 512 : 2 * BN;  // a power of two >= 32 (two BN-wide accumulators)
   static constexpr uint32_t kPipeBytes = kStages * kStageBytes;
   static constexpr uint32_t kSmemBytes = kPipeBytes + 2 * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
@@ -157,9 +157,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const uint64_t db0 = desc_advance(da0, kABytes);
           if (kb == 0) umma_bf16_p(issue, d_tmem, da0, db0, idesc, 0u);
           else umma_bf16_acc_p(issue, d_tmem, da0, db0, idesc);
+          // K tail: the last 64-channel chunk of every tap holds ksteps_last real 16-channel steps (the rest of the
+          // tile is TMA zero fill); K = 32 (UNet++'s 32-channel gradients) would otherwise issue 2x the MMAs
+          const int ksteps = ((kb + 1) % p.kchunks == 0) ? p.ksteps_last : kTileK / kUmmaK;
 #pragma unroll
           for (int k = 1; k < kTileK / kUmmaK; ++k)
-            umma_bf16_acc_p(issue, d_tmem, desc_advance(da0, k * kUmmaK * 2), desc_advance(db0, k * kUmmaK * 2), idesc);
+            if (k < ksteps)
+              umma_bf16_acc_p(issue, d_tmem, desc_advance(da0, k * kUmmaK * 2), desc_advance(db0, k * kUmmaK * 2), idesc);
           umma_commit_p(issue, &empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
@@ -397,7 +401,8 @@ int pick_bn(int ncols, int q_groups) {
     // phase's weight rows; those columns are never stored)
     return (ncols % 256 == 0) ? 256 : (ncols % 128 == 0 ? 128 : 64);
   }
-  return ncols >= 256 ? 256 : (ncols > 64 ? 128 : 64);
+  // 129..192 columns (UNet++ / ResUNet concat widths 160, 192): one 192-wide tile instead of two 128-wide ones
+  return ncols >= 256 ? 256 : (ncols > 128 && ncols <= 192 ? 192 : (ncols > 64 ? 128 : 64));
 }
 
 }  // namespace
@@ -462,6 +467,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.fd_tiles_per_q = FastDiv(p.tiles_per_q);
   p.taps = d.taps;
   p.kchunks = (d.K + kTileK - 1) / kTileK;
+  p.ksteps_last = ((d.K - 1) % kTileK) / kUmmaK + 1;
   p.a_step = d.a_step;
   for (int t = 0; t < d.taps; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
   p.bias = d.bias;
@@ -524,6 +530,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   int rc;
   switch (BN) {
     case 256: rc = launch<256>(p, grid, stream); break;
+    case 192: rc = launch<192>(p, grid, stream); break;
     case 128: rc = launch<128>(p, grid, stream); break;
     default: rc = launch<64>(p, grid, stream); break;
   }

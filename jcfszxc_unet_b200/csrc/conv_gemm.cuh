@@ -47,6 +47,7 @@ struct ConvGemmParams {
   int num_m_tiles, num_n_tiles, tiles_per_q, rows_per_q, ncols;
   FastDiv fd_n_tiles, fd_tiles_w, fd_tiles_h, fd_tiles_per_q;
   int taps, kchunks, a_step;
+  int ksteps_last;  // 16-channel MMA steps in the last 64-channel chunk of a tap (1..4)
   int accumulate;   // != 0: epilogue uses cp.reduce.async.bulk.tensor (.add) instead of a plain store
   int l2_prefetch;  // > 0: prefetch the A box of the tile `l2_prefetch` rounds ahead into L2
   float* out_f32;   // non-null: fp32 output written straight from registers (no staging, no statistics)

@@ -61,6 +61,10 @@ CONV_SHAPES = [
     (1, 7, 300, 72, 40, (8, 0), (0, 0)),       # K tail chunk, 40 output channels (weight rows zero-filled), 3 column tiles
     (1, 2, 128, 8, 8, (0, 0), (0, 0)),         # smallest channel counts, H < 4
     (3, 16, 128, 64, 64, (0, 0), (0, 0)),      # several tiles per CTA: accumulator double-buffering and ring wrap-around
+    # 129..192 output channels -> one 192-wide N tile; K not a multiple of 64 -> the last chunk issues fewer MMA steps
+    (1, 24, 40, 192, 32, (0, 0), (0, 0)),      # UNet++ 192 -> 32 (its dgrad is 32 -> 192: N = 192, two 16-channel steps)
+    (2, 12, 20, 160, 48, (32, 0), (0, 16)),    # 160 = 2.5 chunks; dgrad: N = 160 in a 192 tile, K = 48 (three steps)
+    (1, 16, 16, 32, 176, (0, 0), (0, 0)),      # forward with N = 176 (masked tail of the 192 tile), K = 32
 ]
 
 

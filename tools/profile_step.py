@@ -11,7 +11,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import CONV_FLOPS  # noqa: E402
+from bench import CONV_FLOPS, make_model  # noqa: E402
 from jcfszxc_unet_b200 import _lib  # noqa: E402
 from jcfszxc_unet_b200.trainer import Trainer  # noqa: E402
 from UNetFamily.UNet import UNet  # noqa: E402
@@ -22,11 +22,13 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--model", default="UNet")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(42)
-    model = UNet(3, 1).to(dev).train()
-    tr = Trainer(model, lr=1e-6, use_cuda_graph=False)
+    model, builder = make_model(a.model)
+    model = model.to(dev).train()
+    tr = Trainer(model, lr=1e-6, use_cuda_graph=False, builder=builder)
     g = torch.Generator(device=dev).manual_seed(42)
     images = torch.rand(a.batch, 3, a.size, a.size, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
     labels = (torch.rand(a.batch, 1, a.size, a.size, device=dev, generator=g) < 0.12).float()
