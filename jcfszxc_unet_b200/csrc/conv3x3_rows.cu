@@ -45,10 +45,17 @@ constexpr int kRows = 4;                          // output rows per tile
 constexpr int kHaloW = kTW + 2;
 constexpr uint32_t kRowBytes = kHaloW * 128;      // 16,640 B written by the TMA per (input row, 64-channel chunk)
 constexpr uint32_t kRowSlot = (kRowBytes + 1023u) & ~1023u;   // 17,408 B per ring slot (1024-aligned for SW128)
-constexpr uint32_t kWBlock = 64 * 128;            // one (kc, kw, kh) weight block: 64 rows x 64 k
-constexpr uint32_t kStagingBytes = 128 * 64 * 2;
 constexpr int kMaxSlots = 8;
-constexpr uint32_t kTmemCols = 512;               // 2 tiles x 4 rows x 64 channels
+
+// BW = accumulator block width = output channels per row block: 64, or 32 for the 32-channel layers of UNet++
+// (N = 96 for three filter rows; the staging tile then has 64-byte rows and the 64B swizzle).
+template <int BW>
+struct RCfg {
+  static constexpr uint32_t kWBlock = BW * 128;             // one (kc, kw, kh) weight block: BW rows x 64 k
+  static constexpr uint32_t kStagingBytes = 128 * BW * 2;   // 128 pixels x BW channels
+  static constexpr uint32_t kTmemCols = 2 * kRows * BW;     // 2 tiles x 4 rows x BW channels (512 / 256)
+  static constexpr int kGroups = kEpiThreads / BW;          // statistics: row groups (2 / 4) of BW rows each
+};
 
 struct RowsParams {
   CUtensorMap tmA;    // dims (K, W, H, N), box (64, 130, 1, 1)
@@ -59,11 +66,15 @@ struct RowsParams {
   int accumulate;
   int H, W, tiles_h, tiles_w, num_tiles, ncols, kchunks;
   int slots, n_staging;
+  int ksteps_last;   // 16-channel MMA steps of the last 64-channel chunk (K tail), 1..4
   FastDiv fd_tiles_w, fd_tiles_h;
   int8_t dh[9], dw[9], btap[9];
 };
 
+template <int BW>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_constant__ RowsParams p) {
+  using C = RCfg<BW>;
+  constexpr uint32_t kWBlock = C::kWBlock, kStagingBytes = C::kStagingBytes, kTmemCols = C::kTmemCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -132,9 +143,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer (warp-convergent, elected lane issues)
     const bool issue = elect_one();
-    constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, false, false);
-    constexpr uint32_t idesc128 = make_idesc_bf16(128, 128, false, false);
-    constexpr uint32_t idesc192 = make_idesc_bf16(128, 192, false, false);
+    constexpr uint32_t idesc64 = make_idesc_bf16(128, BW, false, false);        // one / two / three row blocks
+    constexpr uint32_t idesc128 = make_idesc_bf16(128, 2 * BW, false, false);
+    constexpr uint32_t idesc192 = make_idesc_bf16(128, 3 * BW, false, false);
     const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), 16, 1024, kLayoutSW128);
     const uint64_t w_desc0 = make_smem_desc(smem_u32(sW), 16, 1024, kLayoutSW128);
     int as = 0;
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
       const int acc = it & 1;
       mbar_wait_p(issue, &tempty[acc], ((it >> 1) & 1) ^ 1u);
       tc_fence_after();
-      const uint32_t d_tile = tmem_base + acc * (kRows * 64);
+      const uint32_t d_tile = tmem_base + acc * (kRows * BW);
 #pragma unroll
       for (int i = 0; i < kRows + 2; ++i) {
         // compile-time geometry of input row i (see the table in the header)
@@ -154,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
         const int nblk = jmax - jmin + 1;
         const int wslot0 = 2 - (i - jmin);              // first filter-row block of the stacked B operand
         const bool fresh = (i <= kRows - 1);            // accumulator block j = i is touched for the first time
-        const uint32_t d_row = d_tile + jmin * 64;
+        const uint32_t d_row = d_tile + jmin * BW;
         const uint32_t idesc = (nblk == 3) ? idesc192 : (nblk == 2 ? idesc128 : idesc64);
         const uint32_t idesc_rest = (nblk == 3) ? idesc128 : idesc64;   // the nblk-1 older blocks of a fresh row
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -162,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
           tc_fence_after();
           const uint64_t da_row = desc_advance(a_desc0, static_cast<uint32_t>(as) * kRowSlot);
           const uint64_t dw_kc = desc_advance(w_desc0, static_cast<uint32_t>(kc * 9 + wslot0) * kWBlock);
+          const int ksteps = (kc == p.kchunks - 1) ? p.ksteps_last : 4;   // K tail: skip the zero-filled steps
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const uint64_t da_kw = desc_advance(da_row, kw * 128);          // halo column kw = output column 0 shifted
@@ -169,11 +181,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t da = desc_advance(da_kw, k * 32), db = desc_advance(db_kw, k * 32);
+              if (k >= ksteps) continue;
               if (fresh && kw == 0 && k == 0) {
                 // first MMA onto a new accumulator block: older blocks accumulate, the new one is overwritten
                 // (first chunk only; later chunks accumulate everywhere)
                 if (nblk > 1) umma_bf16_acc_p(issue, d_row, da, db, idesc_rest);
-                umma_bf16_p(issue, d_row + (nblk - 1) * 64, da, desc_advance(db, (nblk - 1) * kWBlock), idesc64,
+                umma_bf16_p(issue, d_row + (nblk - 1) * BW, da, desc_advance(db, (nblk - 1) * kWBlock), idesc64,
                             kc != 0 ? 1u : 0u);
               } else {
                 umma_bf16_acc_p(issue, d_row, da, db, idesc);
@@ -192,19 +205,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
     const int row = quarter * 32 + lane;     // output column within the tile == TMEM lane
     const int et = threadIdx.x - 64;
     const bool leader = (et == 0);
-    const int st_ch = et & 63, st_half = et >> 6;
+    const int st_ch = et % BW, st_half = et / BW;     // statistics: channel x row group (BW rows per group)
     const uint32_t staging_a = smem_u32(staging);
-    const uint32_t row_sw = static_cast<uint32_t>(row & 7) << 4;
+    // staging rows are 2*BW bytes: 128B swizzle (16-byte chunk ^= row & 7) or 64B swizzle (chunk ^= (row >> 1) & 3)
+    const uint32_t row_sw = (BW == 64) ? (static_cast<uint32_t>(row & 7) << 4) : (static_cast<uint32_t>((row >> 1) & 3) << 4);
     uint32_t st_off[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      st_off[j] = static_cast<uint32_t>(j * 128 + ((((st_ch >> 3) ^ j) << 4) + (st_ch & 7) * 2));
+    for (int j = 0; j < 8; ++j) {
+      const int x = (BW == 64) ? j : ((j >> 1) & 3);
+      st_off[j] = static_cast<uint32_t>(j * (2 * BW) + ((((st_ch >> 3) ^ x) << 4) + (st_ch & 7) * 2));
+    }
     float ssum = 0.f, ssq = 0.f;
     uint32_t chunk_ctr = 0;
     int it = 0;
     const uint32_t bias_a = smem_u32(bars) + 256;
     if (p.bias != nullptr) {
-      if (et < 64) sts_f32(bias_a + et * 4, (et < p.ncols) ? __ldg(p.bias + et) : 0.f);
+      if (et < BW) sts_f32(bias_a + et * 4, (et < p.ncols) ? __ldg(p.bias + et) : 0.f);
       named_bar_sync(1, kEpiThreads);
     }
     const int n_staging = p.n_staging;
@@ -218,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
 
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * (kRows * 64);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * (kRows * BW);
 #pragma unroll 1
       for (int u = 0; u < kRows; ++u) {   // rolled on purpose: the body must stay resident in the L0 I-cache
         const bool live = (h0 + u) < p.H;
@@ -230,8 +246,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
         }
         uint32_t r0[32], r1[32];
         if (live) {
-          tmem_ld32(taddr + u * 64, r0);
-          tmem_ld32(taddr + u * 64 + 32, r1);
+          tmem_ld32(taddr + u * BW, r0);
+          if constexpr (BW == 64) tmem_ld32(taddr + u * BW + 32, r1);
           tmem_ld_wait();
         }
         if (last) {
@@ -242,9 +258,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
         if (!live) continue;
         ++chunk_ctr;
         const uint32_t buf_a = staging_a + buf_off;
-        const uint32_t row_a = buf_a + row * 128;
+        const uint32_t row_a = buf_a + row * (2 * BW);
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
+        for (int v = 0; v < BW / 8; ++v) {
           const uint32_t* src = (v < 4) ? &r0[v * 8] : &r1[(v - 4) * 8];
           float f[8];
 #pragma unroll
@@ -270,10 +286,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
         }
         if (p.stats_partial != nullptr && st_ch < p.ncols) {
           float s = 0.f, ss = 0.f, s2 = 0.f, ss2 = 0.f;
-          const int r_begin = st_half * 64;
-          uint32_t base = buf_a + r_begin * 128;
+          const int r_begin = st_half * BW;
+          uint32_t base = buf_a + r_begin * (2 * BW);
 #pragma unroll 1
-          for (int r8 = 0; r8 < 8; ++r8, base += 1024) {
+          for (int r8 = 0; r8 < BW / 8; ++r8, base += 8 * 2 * BW) {
             uint32_t x[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = lds_u16(base + st_off[j]);
@@ -292,11 +308,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
     if (leader) bulk_wait<0>();
     if (p.stats_partial != nullptr) {
       named_bar_sync(1, kEpiThreads);
-      float* red = reinterpret_cast<float*>(staging);  // [2 halves][2][64]
-      red[(st_half * 2 + 0) * 64 + st_ch] = ssum;
-      red[(st_half * 2 + 1) * 64 + st_ch] = ssq;
+      float* red = reinterpret_cast<float*>(staging);  // [groups][2][BW]
+      red[(st_half * 2 + 0) * BW + st_ch] = ssum;
+      red[(st_half * 2 + 1) * BW + st_ch] = ssq;
       named_bar_sync(1, kEpiThreads);
-      if (et < 2 * 64) p.stats_partial[static_cast<size_t>(blockIdx.x) * 2 * 64 + et] = red[et] + red[2 * 64 + et];
+      if (et < 2 * BW) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < C::kGroups; ++g) t += red[g * 2 * BW + et];
+        p.stats_partial[static_cast<size_t>(blockIdx.x) * 2 * BW + et] = t;
+      }
     }
   }
 
@@ -309,7 +330,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
 }
 
 // smem plan: resident weights + staging + as many row slots as fit (>= 3)
-bool rows_plan(int kchunks, int* slots, int* n_staging, uint32_t* smem_bytes) {
+bool rows_plan(int kchunks, int BW, int* slots, int* n_staging, uint32_t* smem_bytes) {
+  const uint32_t kWBlock = BW * 128, kStagingBytes = 128 * BW * 2;
   const uint32_t fixed = static_cast<uint32_t>(9 * kchunks) * kWBlock + 1024 /*align*/ + 256 /*barriers*/ + 256 /*bias*/;
   const uint32_t budget = 227 * 1024;
   for (int ns = 2; ns >= 1; --ns) {
@@ -335,13 +357,13 @@ bool conv3x3_rows_eligible(const ConvGemmDesc& d) {
   if (enabled < 0) { const char* e = getenv("UNETK_ROWS_CONV"); enabled = e ? atoi(e) : 1; }
   if (!enabled) return false;
   if (!(d.taps == 9 && d.a_step == 1 && d.out_step == 1 && d.q_groups == 1 && !d.out_f32 && d.W >= 128 && d.H >= 1 &&
-        d.ncols <= 64 && d.K >= 8 && d.K <= 128))
+        d.ncols <= 64 && d.K >= 8 && d.K <= (d.ncols <= 32 ? 256 : 128)))
     return false;
   for (int t = 0; t < 9; ++t)
     if (d.dh[t] < -1 || d.dh[t] > 1 || d.dw[t] < -1 || d.dw[t] > 1) return false;
   int s, ns;
   uint32_t bytes;
-  return rows_plan((d.K + 63) / 64, &s, &ns, &bytes);
+  return rows_plan((d.K + 63) / 64, d.ncols <= 32 ? 32 : 64, &s, &ns, &bytes);
 }
 
 // Same contract as conv_gemm_run for the shapes conv3x3_rows_eligible() accepts.
@@ -353,6 +375,8 @@ int conv3x3_rows_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.num_tiles = d.N * p.tiles_h * p.tiles_w;
   p.ncols = d.ncols;
   p.kchunks = (d.K + 63) / 64;
+  p.ksteps_last = ((d.K - 1) % 64) / 16 + 1;
+  const int BW = d.ncols <= 32 ? 32 : 64;
   p.fd_tiles_w = FastDiv(p.tiles_w);
   p.fd_tiles_h = FastDiv(p.tiles_h);
   for (int t = 0; t < 9; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
@@ -360,7 +384,7 @@ int conv3x3_rows_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.accumulate = d.accumulate;
   p.stats_partial = d.stats_sums ? d.stats_partial : nullptr;
   uint32_t smem_bytes = 0;
-  UNETK_CHECK(rows_plan(p.kchunks, &p.slots, &p.n_staging, &smem_bytes), -1, "conv3x3_rows: weights do not fit");
+  UNETK_CHECK(rows_plan(p.kchunks, BW, &p.slots, &p.n_staging, &smem_bytes), -1, "conv3x3_rows: weights do not fit");
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   {
     uint64_t dims[4] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
@@ -374,7 +398,7 @@ int conv3x3_rows_run(const ConvGemmDesc& d, cudaStream_t stream) {
   {
     uint64_t dims[3] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.ncols), static_cast<uint64_t>(d.b_taps)};
     uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * d.ncols};
-    uint32_t box[3] = {64, 64, 1};
+    uint32_t box[3] = {64, static_cast<uint32_t>(BW), 1};
     uint32_t es[3] = {1, 1, 1};
     if (int rc = make_tmap_bf16(&p.tmB, d.b, 3, dims, strides, box, es, true)) return rc;
   }
@@ -383,18 +407,20 @@ int conv3x3_rows_run(const ConvGemmDesc& d, cudaStream_t stream) {
                         static_cast<uint64_t>(d.N)};
     uint64_t strides[3] = {static_cast<uint64_t>(d.out_ld) * 2, static_cast<uint64_t>(d.out_ld) * 2 * d.W,
                            static_cast<uint64_t>(d.out_ld) * 2 * d.W * d.H};
-    uint32_t box[4] = {64, kTW, 1, 1};
+    uint32_t box[4] = {static_cast<uint32_t>(BW), kTW, 1, 1};
     uint32_t es[4] = {1, 1, 1, 1};
-    if (int rc = make_tmap_bf16(&p.tmOut, d.out, 4, dims, strides, box, es, true)) return rc;
+    if (int rc = make_tmap_bf16(&p.tmOut, d.out, 4, dims, strides, box, es, true, BW == 32 ? 64 : 128)) return rc;
   }
   static bool configured = false;
   if (!configured) {
-    UNETK_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UNETK_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UNETK_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  UNETK_CUDA(launch_pdl(conv3x3_rows_kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
+  if (BW == 32) UNETK_CUDA(launch_pdl(conv3x3_rows_kernel<32>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
+  else UNETK_CUDA(launch_pdl(conv3x3_rows_kernel<64>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
   UNETK_LAUNCHED();
-  if (d.stats_sums != nullptr) return conv_stats_sums_launch(d.stats_partial, grid, 1, 64, d.ncols, d.stats_sums, stream);
+  if (d.stats_sums != nullptr) return conv_stats_sums_launch(d.stats_partial, grid, 1, BW, d.ncols, d.stats_sums, stream);
   return 0;
 }
 

@@ -68,6 +68,6 @@ const char* last_error();
 // of dims[i+1]. OOB elements read as zero. Returns 0 or a negative code (error text set).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
-                   bool swizzle128);
+                   bool swizzle, int swizzle_bytes = 128);   // swizzle_bytes: 128 or 64 (box rows of 64 bytes)
 
 }  // namespace unetk

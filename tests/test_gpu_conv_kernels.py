@@ -61,6 +61,13 @@ CONV_SHAPES = [
     (1, 7, 300, 72, 40, (8, 0), (0, 0)),       # K tail chunk, 40 output channels (weight rows zero-filled), 3 column tiles
     (1, 2, 128, 8, 8, (0, 0), (0, 0)),         # smallest channel counts, H < 4
     (3, 16, 128, 64, 64, (0, 0), (0, 0)),      # several tiles per CTA: accumulator double-buffering and ring wrap-around
+    # <= 32 output channels -> the row-stacked kernel with 32-wide accumulator blocks (N = 96), 64-byte staging rows
+    (1, 9, 130, 96, 32, (0, 0), (0, 0)),       # K = 96: second chunk has two 16-channel steps
+    (2, 4, 128, 192, 32, (0, 0), (0, 32)),     # UNet++ 192 -> 32: three k-chunks, sliced output
+    (1, 6, 256, 32, 32, (32, 0), (0, 0)),      # 32 -> 32 (fwd and dgrad both take this path), sliced input
+    (1, 5, 140, 160, 24, (0, 0), (0, 8)),      # 24 output channels (weight rows zero-filled), K tail, ragged W
+    (3, 16, 128, 32, 32, (0, 0), (0, 0)),      # several tiles per CTA
+    (1, 8, 128, 256, 16, (0, 0), (0, 0)),      # four k-chunks: 4-slot row ring with a single staging buffer
     # 129..192 output channels -> one 192-wide N tile; K not a multiple of 64 -> the last chunk issues fewer MMA steps
     (1, 24, 40, 192, 32, (0, 0), (0, 0)),      # UNet++ 192 -> 32 (its dgrad is 32 -> 192: N = 192, two 16-channel steps)
     (2, 12, 20, 160, 48, (32, 0), (0, 16)),    # 160 = 2.5 chunks; dgrad: N = 160 in a 192 tile, K = 48 (three steps)
