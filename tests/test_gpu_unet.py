@@ -314,3 +314,36 @@ def test_fp32_mode_rejects_other_models():
     m = AttentionUNet(3, 1).to(DEV)
     with U.precision("fp32"), pytest.raises(NotImplementedError):
         m(torch.rand(1, 3, 32, 32, device=DEV))
+
+
+def test_trainer_prefetch_pipeline_is_bit_identical():
+    """Trainer.prefetch()/step(): the staged-input pipeline must train exactly like step(images, labels)."""
+    from jcfszxc_unet_b200.trainer import Trainer
+
+    batches = [_inputs(200 + i, 2, 32, 32) for i in range(4)]
+
+    def run(pipelined):
+        m = _model(42).to(DEV).train()
+        tr = Trainer(m, lr=1e-3, use_cuda_graph=True)
+        losses = []
+        x0, y0 = batches[0]
+        losses.append(float(tr.step(x0.to(DEV), y0.to(DEV))))
+        if pipelined:
+            pin = [(x.pin_memory(), y.pin_memory()) for x, y in batches]
+            tr.prefetch(*pin[1])
+            for i in range(1, 4):
+                loss = tr.step()
+                if i + 1 < 4:
+                    tr.prefetch(*pin[i + 1])
+                losses.append(float(loss))
+            with pytest.raises(RuntimeError):
+                tr.step()                                   # nothing staged
+        else:
+            for i in range(1, 4):
+                losses.append(float(tr.step(batches[i][0].to(DEV), batches[i][1].to(DEV))))
+        return losses, {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+    la, sa = run(False)
+    lb, sb = run(True)
+    assert la == lb, (la, lb)
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
