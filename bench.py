@@ -311,8 +311,10 @@ def run_ours(args):
     h_images.copy_(images.cpu())
     h_labels = torch.empty((B, 1, S, S), dtype=torch.float32, pin_memory=True)
     h_labels.copy_(labels.cpu())
-    for _ in range(2):
-        float(tr.step(h_images, h_labels))
+    float(tr.step(h_images, h_labels))
+    for _ in range(3):                                     # warm the pipeline itself (copy stream, staging batches)
+        tr.prefetch(h_images, h_labels)
+        float(tr.step())
     e2e_steps = max(3, min(K, 20))
     # Input pipeline of the public API: the H2D copy of step i+1 (pinned host memory -> staging batch, side stream) is
     # issued right after step i is launched, so it overlaps step i's compute; EVERY step still copies its own 64 MB
