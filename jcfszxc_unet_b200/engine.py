@@ -13,6 +13,7 @@ Buffer scheme (vanilla U-Net, reference UNetFamily/UNet.py:39-55):
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import torch
@@ -62,6 +63,11 @@ class Plan:
         self.packs = {}            # id(weight) -> WeightPack shared by every op that applies that weight
         self._pack_table = self._pack_ptrs = None
         self._pack_tiles = 0
+        # Weight gradients run on a low-priority side stream: nothing on the backward's critical path consumes them, so
+        # they fill the tensor cores while the HBM-bound BatchNorm passes of the next layer down run on the main stream.
+        self.overlap_wgrad = os.environ.get("UNETK_WGRAD_STREAM", "1") != "0"
+        self._side = None
+        self._side_dirty = False
         self._g_init = {}          # gradient buffer -> set of channels already written during backward
         self._g_writers = {}       # gradient buffer -> {channel: number of ops that write it during backward}
         self._p_init = set()       # parameters whose gradient was already written during backward
@@ -195,6 +201,32 @@ class Plan:
         ops_ = self.ops[lo:hi]
         for op in reversed(ops_):
             op.bwd()
+        self.join_side()
+
+    @contextlib.contextmanager
+    def wgrad_stream(self):
+        """Run the enclosed launches (weight gradients; they share the `ws` workspace and therefore one stream) on the
+        side stream, ordered after everything enqueued on the current stream so far."""
+        if not self.overlap_wgrad:
+            yield
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device, priority=0)     # 0 = low; the trainer captures at -1
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            yield
+        self._side_dirty = True
+
+    def join_side(self):
+        """The current stream waits for the side stream (end of a backward segment: gradients are complete)."""
+        if self._side_dirty:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self._side_dirty = False
 
     def op_params(self, op):
         """Parameters whose gradient `op` produces (every op keeps its modules as attributes)."""
@@ -371,18 +403,19 @@ class ConvBNReLU:
             if not self._res_aliases_out():
                 ops.add_n(self.res.g, [g1], accumulate=self.acc_res)
         dy = self.raw.g
-        if self.stem:
-            n, cin, h, w = P.image.x.shape
-            xp, sn, sc_, sh_, sw = ops._img(P.image.x)
-            dyp, dyld = ops.nhwc(dy)
-            three = self.w3 is None
-            dw = self.dw if three else self.dw3
-            _lib.call("unetk_stem_conv3x3_wgrad", xp, sn, sc_, sh_, sw, dyp, dyld, dw.data_ptr(),
-                      int(self.acc_w and three), n, h, w, cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
-            if not three:
-                ops.copy_f32_strided(self.dw, 1, self.dw3, 9, self.cout * self.cin, accumulate=self.acc_w, src_offset=4)
-        else:
-            ops.conv_wgrad(self.x.t, dy, self.dw, self.k, self.acc_w, self.stride, ws=P.ws)
+        with P.wgrad_stream():
+            if self.stem:
+                n, cin, h, w = P.image.x.shape
+                xp, sn, sc_, sh_, sw = ops._img(P.image.x)
+                dyp, dyld = ops.nhwc(dy)
+                three = self.w3 is None
+                dw = self.dw if three else self.dw3
+                _lib.call("unetk_stem_conv3x3_wgrad", xp, sn, sc_, sh_, sw, dyp, dyld, dw.data_ptr(),
+                          int(self.acc_w and three), n, h, w, cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
+                if not three:
+                    ops.copy_f32_strided(self.dw, 1, self.dw3, 9, self.cout * self.cin, accumulate=self.acc_w, src_offset=4)
+            else:
+                ops.conv_wgrad(self.x.t, dy, self.dw, self.k, self.acc_w, self.stride, ws=P.ws)
         if self.dbias is not None and self.bn is None:
             ops.colsum(dy, P.partial, self.dbias, self.acc_b)
         if not self.stem and self.x.g is not None:
@@ -472,8 +505,9 @@ class ConvT2x2:
         dy = self.out.g
         xp, xld = ops.nhwc(self.x.t)
         dyp, dyld = ops.nhwc(dy)
-        _lib.call("unetk_convT2x2_wgrad", xp, xld, dyp, dyld, self.dw.data_ptr(), int(self.acc_w), self.x.N, self.x.H,
-                  self.x.W, self.cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
+        with P.wgrad_stream():
+            _lib.call("unetk_convT2x2_wgrad", xp, xld, dyp, dyld, self.dw.data_ptr(), int(self.acc_w), self.x.N, self.x.H,
+                      self.x.W, self.cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
         if self.db is not None and not self.fused_db:
             ops.colsum(dy, P.partial, self.db, self.acc_b)
         if self.x.g is not None:
@@ -877,7 +911,8 @@ class AttentionGate(_Op):
                   F, _s())
         for src, raw, pack, dw, db, a_in in ((self.g, self.rawg, self.packg, dwg, dbg, self.acc_g),
                                              (self.x, self.rawx, self.packx, dwx, dbx, self.acc_xw)):
-            ops.conv_wgrad(src.t, raw.g, dw, 1, acc, 1, ws=P.ws)
+            with P.wgrad_stream():
+                ops.conv_wgrad(src.t, raw.g, dw, 1, acc, 1, ws=P.ws)
             ops.conv_dgrad(raw.g, pack.ba, src.g, 1, a_in, 1)
 
 

@@ -172,9 +172,12 @@ class Trainer:
         # constants baked into the graphs
         graphs = []
         pool = None
+        # captured on a HIGH-priority stream: the plan's weight-gradient side stream is low priority, so whenever a
+        # kernel of the critical path and a weight gradient are both ready, the critical path gets the SMs first
+        hp = torch.cuda.Stream(device=self.device, priority=-1)
         for seg in (self._seg_forward_packed, self._seg_backward, self._seg_backward_tail, self._seg_optim):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with torch.cuda.graph(g, pool=pool, stream=hp):
                 seg()
             pool = g.pool()
             graphs.append(g)
