@@ -283,12 +283,14 @@ def run_ours(args):
 
     # ---- per-kernel timing + launch count: one EAGER step, every C-ABI call bracketed by CUDA events --
     graphs, use_graph, tr.graphs, tr.use_graph = tr.graphs, tr.use_graph, None, False
+    overlap, tr.plan.overlap_wgrad = tr.plan.overlap_wgrad, False   # per-kernel durations: no side-stream co-scheduling
     with _lib.profile_calls() as prof:
         c0 = lib.unetk_launch_count()
         tr.step(images, labels)
         launches_per_step = lib.unetk_launch_count() - c0
     torch.cuda.synchronize()
     fam = kernel_breakdown(prof.records)
+    tr.plan.overlap_wgrad = overlap
     tr.graphs, tr.use_graph = graphs, use_graph
     tr.step(images, labels)
     torch.cuda.synchronize()

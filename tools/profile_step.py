@@ -35,6 +35,7 @@ def main():
     for _ in range(a.warmup):
         tr.step(images, labels)
     torch.cuda.synchronize()
+    tr.plan.overlap_wgrad = False      # one kernel at a time: clean per-call durations
     with _lib.profile_calls() as prof:
         tr.step(images, labels)
     torch.cuda.synchronize()
