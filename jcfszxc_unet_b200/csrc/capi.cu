@@ -183,8 +183,9 @@ int unetk_conv3x3_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_
                         int N, int H, int W, int Cin, int Cout, void* workspace, size_t ws_bytes, void* stream) {
   UNETK_CHECK(x && dy && dw, -1, "conv3x3_wgrad: null pointer");
   // halo-reuse kernel (one activation load per filter row); shapes it does not cover use the per-tap kernel
-  // Cout <= 64 < Cin: swapped operands (all 128 MMA rows carry input channels), see wgrad3x3_run
-  const bool flip = Cout <= 64 && Cin >= 128;
+  // Cout <= 64 and more input than output channels: swapped operands (the 128 MMA rows carry input channels, the
+  // narrow side goes to N where three taps share one MMA), see wgrad3x3_run
+  const bool flip = Cout <= 64 && Cin > Cout && Cin >= 96;
   const int rc3 = flip ? wgrad3x3_run(x, x_ld, dy, dy_ld, dw, accumulate, N, H, W, Cin, Cout, workspace, ws_bytes, S(stream), 1)
                        : wgrad3x3_run(dy, dy_ld, x, x_ld, dw, accumulate, N, H, W, Cout, Cin, workspace, ws_bytes, S(stream));
   if (rc3 <= 0) return rc3;
