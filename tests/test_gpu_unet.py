@@ -347,3 +347,43 @@ def test_trainer_prefetch_pipeline_is_bit_identical():
     lb, sb = run(True)
     assert la == lb, (la, lb)
     assert all(torch.equal(sa[k], sb[k]) for k in sa)
+
+
+# ------------------------------------------------------------------------------------------------ full size
+def test_full_size_properties_b16_512():
+    """BASELINE.json configs[1] at its real size (16 x 3 x 512 x 512), through size-independent properties:
+    (a) eval-mode logits of an image do not depend on the batch it sits in (bit-exact: same per-pixel arithmetic);
+    (b) a training step is deterministic (two trainers, same bits) and eager == CUDA-graph replay;
+    (c) the fused head+loss agrees with the reference recipe applied to the model's own logits."""
+    from jcfszxc_unet_b200.trainer import Trainer
+    from oracle import unet_oracle as O
+
+    g = torch.Generator(device=DEV).manual_seed(99)
+    x = torch.rand(16, 3, 512, 512, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    y = (torch.rand(16, 1, 512, 512, device=DEV, generator=g) < 0.12).float()
+    m = _model(42).to(DEV).eval()
+    with torch.no_grad():
+        y16 = m(x)
+        y1 = m(x[5:6])
+    assert torch.equal(y16[5:6], y1)
+
+    def run(graph):
+        mm = _model(42).to(DEV).train()
+        tr = Trainer(mm, lr=1e-4, use_cuda_graph=graph)
+        losses = [float(tr.step(x, y)) for _ in range(3)]
+        return losses, float(tr.loss_terms()[2]), mm
+
+    la, da, ma = run(True)
+    lb, db, mb = run(True)
+    lc, dc, _ = run(False)
+    assert la == lb and da == db                       # deterministic: no atomics, ordered reductions
+    assert la == lc and da == dc                       # graph replay == eager
+    assert all(torch.equal(p, q) for p, q in zip(ma.state_dict().values(), mb.state_dict().values()))
+    assert all(np.isfinite(v) for v in la) and la[2] < la[0] + 0.5
+
+    mm = _model(42).to(DEV).train()
+    tr = Trainer(mm, lr=1e-4, use_cuda_graph=False)
+    loss = float(tr.step(x, y))
+    logits = tr.plan.head.logits.clone()
+    ref_loss, ref_bce, ref_dice_l = O.segmentation_loss(logits, y)
+    assert abs(loss - float(ref_loss)) <= 1e-5 and abs((1 - float(tr.loss_terms()[2])) - float(ref_dice_l)) <= 1e-5
