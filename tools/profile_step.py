@@ -10,6 +10,7 @@ import sys
 
 import torch
 
+os.environ.setdefault("UNETK_WGRAD_STREAM", "0")   # one kernel at a time: clean per-call durations
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import CONV_FLOPS, make_model  # noqa: E402
 from jcfszxc_unet_b200 import _lib  # noqa: E402
@@ -35,7 +36,6 @@ def main():
     for _ in range(a.warmup):
         tr.step(images, labels)
     torch.cuda.synchronize()
-    tr.plan.overlap_wgrad = False      # one kernel at a time: clean per-call durations
     with _lib.profile_calls() as prof:
         tr.step(images, labels)
     torch.cuda.synchronize()
