@@ -123,6 +123,12 @@ int unetk_convT2x2_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy
 int unetk_stem_conv3x3_fwd(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w,
                            const float* bias, void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout,
                            void* stream);
+/* fwd_bnstats: the same conv, plus sums = double[2][Cout] = per-channel (sum, sum of squares) of the bf16 output —
+ * what unetk_bn_stats would return — from the kernel's epilogue; partial >= unetk_stem_stats_partial_floats floats. */
+size_t unetk_stem_stats_partial_floats(int N, int H, int W, int Cout);
+int unetk_stem_conv3x3_fwd_bnstats(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w,
+                                   const float* bias, void* y, int64_t y_ld, float* partial, double* sums, int N, int H,
+                                   int W, int Cin, int Cout, void* stream);
 size_t unetk_stem_wgrad_workspace(int N, int H, int W, int Cin);
 int unetk_stem_conv3x3_wgrad(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy,
                              int64_t dy_ld, float* dw, int accumulate, int N, int H, int W, int Cin, int Cout,
@@ -206,6 +212,26 @@ int unetk_loss_finalize(const double* sums, double npix_total, float* fin, void*
 int unetk_head_bwd(const void* x, int64_t x_ld, const float* w, const float* labels, const float* logits,
                    const float* fin, const float* dlogits, float gscale, int post_sigmoid, void* dx, int64_t dx_ld,
                    float* dw, float* db, int accumulate, int64_t npix, int C, float* partial, void* stream);
+
+/* ---- last BatchNorm(+ReLU) folded into the head (DoubleConv -> OutConv, UNet.py:54; unet_parts.py:24-31,73-79) ----
+ * The activation in front of OutConv, a = act(bf16(raw*scale + shift)), feeds nothing but the head and its gradient is
+ * rank one (dz[pix]*w[c]), so neither a nor d(a) is materialised.
+ * bn_head_fwd        : unetk_bn_apply + unetk_head_fwd in one pass over the conv output `raw` (same results).
+ * bn_head_bwd_reduce : one pass over `raw`: dz[pix] (fp32, kept for the apply pass), dw/db of the head ((+)= when
+ *                      accumulate), and sums = double[2][C] = the two BatchNorm backward sums of unetk_bn_bwd_reduce.
+ * bn_head_bwd_apply  : d(raw) from (raw, dz) and coef = [K0 | K1] of unetk_bn_bwd_coef.
+ * C power of two in [8,256]; partial >= unetk_bn_head_partial_floats(npix, C) floats. */
+size_t unetk_bn_head_partial_floats(int64_t npix, int C);
+int unetk_bn_head_fwd(const void* raw, int64_t raw_ld, const float* scale, const float* shift, int relu, const float* w,
+                      const float* bias, const float* labels, float* logits, int post_sigmoid, int64_t npix, int C,
+                      float* partial, double* sums, void* stream);
+int unetk_bn_head_bwd_reduce(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const float* mean,
+                             int relu, const float* w, const float* labels, const float* logits, const float* fin,
+                             const float* dlogits, float gscale, int post_sigmoid, float* dz, float* dw, float* db,
+                             int accumulate, double* sums, int64_t npix, int C, float* partial, void* stream);
+int unetk_bn_head_bwd_apply(const void* raw, int64_t raw_ld, const float* scale, const float* shift, int relu,
+                            const float* w, const float* dz, const float* coef, void* draw, int64_t draw_ld,
+                            int64_t npix, int C, void* stream);
 
 /* ---- optimizer tail on flat fp32 buffers (train.py:107-112,299-300) -------------------------------
  * grad_clip_coef: out[0] = gscale*||g||_2, out[1] = gscale*min(1, max_norm/(out[0]+1e-6)); partial >=

@@ -46,6 +46,8 @@ SIGNATURES = {
     "unetk_convT2x2_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "unetk_convT2x2_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "unetk_stem_conv3x3_fwd": (_i, [_fp, _i64, _i64, _i64, _i64, _fp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_stem_stats_partial_floats": (_sz, [_i, _i, _i, _i]),
+    "unetk_stem_conv3x3_fwd_bnstats": (_i, [_fp, _i64, _i64, _i64, _i64, _fp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "unetk_stem_wgrad_workspace": (_sz, [_i, _i, _i, _i]),
     "unetk_stem_conv3x3_wgrad": (_i, [_fp, _i64, _i64, _i64, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "unetk_chan_partial_floats": (_sz, [_i64, _i]),
@@ -63,6 +65,11 @@ SIGNATURES = {
     "unetk_head_partial_floats": (_sz, [_i64, _i]),
     "unetk_head_fwd": (_i, [_vp, _i64, _fp, _fp, _fp, _fp, _i, _i64, _i, _fp, _vp, _vp]),
     "unetk_loss_finalize": (_i, [_vp, C.c_double, _fp, _vp]),
+    "unetk_bn_head_partial_floats": (_sz, [_i64, _i]),
+    "unetk_bn_head_fwd": (_i, [_vp, _i64, _fp, _fp, _i, _fp, _fp, _fp, _fp, _i, _i64, _i, _fp, _vp, _vp]),
+    "unetk_bn_head_bwd_reduce": (_i, [_vp, _i64, _fp, _fp, _fp, _i, _fp, _fp, _fp, _fp, _fp, _f, _i, _fp, _fp, _fp, _i,
+                                      _vp, _i64, _i, _fp, _vp]),
+    "unetk_bn_head_bwd_apply": (_i, [_vp, _i64, _fp, _fp, _i, _fp, _fp, _fp, _vp, _i64, _i64, _i, _vp]),
     "unetk_head_bwd": (_i, [_vp, _i64, _fp, _fp, _fp, _fp, _fp, _f, _i, _vp, _i64, _fp, _fp, _i, _i64, _i, _fp, _vp]),
     "unetk_sqnorm_partial_floats": (_sz, [_i64]),
     "unetk_grad_clip_coef": (_i, [_fp, _i64, _f, _f, _fp, _fp, _vp]),

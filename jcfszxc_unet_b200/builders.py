@@ -15,6 +15,13 @@ def _hw(P: Plan, x):
 
 
 # ------------------------------------------------------------------------------------------------ blocks
+def _producer(P: Plan, y: Act):
+    """The unit that was emitted last, if it is the conv+BN(+ReLU) producing `y` (then the head is y's only consumer
+    and can take over that unit's BatchNorm passes, engine.Head)."""
+    op = P.ops[-1] if P.ops else None
+    return op if isinstance(op, ConvBNReLU) and op.out is y else None
+
+
 def emit_conv_pair(P: Plan, x, seq, out: Act | None = None, pooled: Act | None = None) -> Act:
     """seq = [conv3x3, BN, ReLU, conv3x3, BN, ReLU]: conv_block (unet_parts.py:82-96), DoubleConv (:17-34),
     NestedUNet's DoubleConv (UNetPP.py:15-28)."""
@@ -106,7 +113,7 @@ def build_attention_unet_plan(model, N, H, W, device, training, grad_views=None,
         emit_up_conv(P, y, up, d)
         AttentionGate(P, d, xs[lvl], att, cat.slice(0, C[lvl]))
         y = emit_conv_pair(P, cat, upc.conv)
-    P.head = Head(P, y, model.Conv_1x1)
+    P.head = Head(P, y, model.Conv_1x1, fuse=_producer(P, y))
     return P.finalize(grad_views)
 
 
@@ -252,5 +259,5 @@ def build_nested_unet_plan(model, N, H, W, device, training, grad_views=None, wi
     nested(2, 2)
     nested(1, 3)
     nested(0, 4)
-    P.head = Head(P, X[0, 4], model.final, post_sigmoid=True)
+    P.head = Head(P, X[0, 4], model.final, post_sigmoid=True, fuse=_producer(P, X[0, 4]))
     return P.finalize(grad_views)

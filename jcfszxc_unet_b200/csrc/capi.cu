@@ -238,6 +238,16 @@ int unetk_stem_conv3x3_fwd(const float* x, int64_t sn, int64_t sc, int64_t sh, i
   UNETK_CHECK(x && w && y, -1, "stem_fwd: null pointer");
   return stem_fwd_run(x, sn, sc, sh, sw, w, bias, y, y_ld, N, H, W, Cin, Cout, S(stream));
 }
+size_t unetk_stem_stats_partial_floats(int N, int H, int W, int Cout) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cout < 8 || Cout % 8) return 0;
+  return stem_stats_partial_floats(N, H, W, Cout);
+}
+int unetk_stem_conv3x3_fwd_bnstats(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w,
+                                   const float* bias, void* y, int64_t y_ld, float* partial, double* sums, int N, int H,
+                                   int W, int Cin, int Cout, void* stream) {
+  UNETK_CHECK(x && w && y && partial && sums, -1, "stem_fwd_bnstats: null pointer");
+  return stem_fwd_stats_run(x, sn, sc, sh, sw, w, bias, y, y_ld, partial, sums, N, H, W, Cin, Cout, S(stream));
+}
 size_t unetk_stem_wgrad_workspace(int N, int H, int W, int Cin) { return stem_wgrad_workspace(N, H, W, Cin); }
 int unetk_stem_conv3x3_wgrad(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy,
                              int64_t dy_ld, float* dw, int accumulate, int N, int H, int W, int Cin, int Cout,
@@ -335,6 +345,33 @@ int unetk_head_bwd(const void* x, int64_t x_ld, const float* w, const float* lab
   UNETK_CHECK(x && w && dx && partial && npix > 0, -1, "head_bwd: bad arguments");
   return head_loss_bwd_run(x, x_ld, w, labels, logits, fin, dlogits, gscale, post_sigmoid, dx, dx_ld, dw, db,
                            accumulate, npix, C, partial, S(stream));
+}
+
+size_t unetk_bn_head_partial_floats(int64_t npix, int C) {
+  if (C < 8 || C % 8) return 0;
+  return bn_head_partial_floats(npix, C);
+}
+int unetk_bn_head_fwd(const void* raw, int64_t raw_ld, const float* scale, const float* shift, int relu, const float* w,
+                      const float* bias, const float* labels, float* logits, int post_sigmoid, int64_t npix, int C,
+                      float* partial, double* sums, void* stream) {
+  UNETK_CHECK(raw && scale && shift && w && logits && partial && npix > 0, -1, "bn_head_fwd: bad arguments");
+  return bn_head_fwd_run(raw, raw_ld, scale, shift, relu, w, bias, labels, logits, post_sigmoid, npix, C, partial, sums,
+                         S(stream));
+}
+int unetk_bn_head_bwd_reduce(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const float* mean,
+                             int relu, const float* w, const float* labels, const float* logits, const float* fin,
+                             const float* dlogits, float gscale, int post_sigmoid, float* dz, float* dw, float* db,
+                             int accumulate, double* sums, int64_t npix, int C, float* partial, void* stream) {
+  UNETK_CHECK(raw && scale && shift && mean && w && dz && sums && partial && npix > 0, -1,
+              "bn_head_bwd_reduce: bad arguments");
+  return bn_head_bwd_reduce_run(raw, raw_ld, scale, shift, mean, relu, w, labels, logits, fin, dlogits, gscale,
+                                post_sigmoid, dz, dw, db, accumulate, sums, npix, C, partial, S(stream));
+}
+int unetk_bn_head_bwd_apply(const void* raw, int64_t raw_ld, const float* scale, const float* shift, int relu,
+                            const float* w, const float* dz, const float* coef, void* draw, int64_t draw_ld,
+                            int64_t npix, int C, void* stream) {
+  UNETK_CHECK(raw && scale && shift && w && dz && coef && draw && npix > 0, -1, "bn_head_bwd_apply: bad arguments");
+  return bn_head_bwd_apply_run(raw, raw_ld, scale, shift, relu, w, dz, coef, draw, draw_ld, npix, C, S(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ n_classes > 1, Dice

@@ -16,6 +16,10 @@ int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, flo
 // stem.cu
 int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
                  void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
+size_t stem_stats_partial_floats(int N, int H, int W, int Cout);
+int stem_fwd_stats_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
+                       void* y, int64_t y_ld, float* partial, double* sums, int N, int H, int W, int Cin, int Cout,
+                       cudaStream_t s);
 size_t stem_wgrad_workspace(int N, int H, int W, int Cin);
 int stem_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy, int64_t dy_ld,
                    float* dw, int accumulate, int N, int H, int W, int Cin, int Cout, void* ws, size_t ws_bytes,
@@ -54,6 +58,17 @@ int loss_finalize_run(const double* sums, double npix_total, float* out, cudaStr
 int head_loss_bwd_run(const void* x, int64_t ld, const float* w, const float* labels, const float* logits,
                       const float* fin, const float* dlogits, float gscale, int post_sigmoid, void* dx, int64_t dx_ld,
                       float* dw, float* db, int accumulate, int64_t npix, int C, float* partial, cudaStream_t s);
+size_t bn_head_partial_floats(int64_t npix, int C);
+int bn_head_fwd_run(const void* raw, int64_t ld, const float* scale, const float* shift, int relu, const float* w,
+                    const float* bias, const float* labels, float* logits, int post_sigmoid, int64_t npix, int C,
+                    float* partial, double* sums, cudaStream_t s);
+int bn_head_bwd_reduce_run(const void* raw, int64_t ld, const float* scale, const float* shift, const float* mean,
+                           int relu, const float* w, const float* labels, const float* logits, const float* fin,
+                           const float* dlogits, float gscale, int post_sigmoid, float* dz, float* dw, float* db,
+                           int accumulate, double* sums, int64_t npix, int C, float* partial, cudaStream_t s);
+int bn_head_bwd_apply_run(const void* raw, int64_t ld, const float* scale, const float* shift, int relu, const float* w,
+                          const float* dz, const float* coef, void* draw, int64_t draw_ld, int64_t npix, int C,
+                          cudaStream_t s);
 // optim.cu
 int sqnorm_blocks(int64_t n);
 int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, float* partial, float* out,

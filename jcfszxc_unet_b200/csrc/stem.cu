@@ -8,6 +8,7 @@
 #include "host_common.cuh"
 
 #include <cstdlib>
+#include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace unetk {
@@ -175,7 +176,10 @@ int stem_grid(int N, int H, int W) {
 // stem_tc.cu: the tensor-core versions (default); UNETK_STEM_TC=0 selects the CUDA-core kernels of this file
 bool stem_tc_ok(int Cin, int Cout);
 int stem_tc_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
-                    void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
+                    void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s,
+                    float* stats_partial = nullptr, double* stats_sums = nullptr);
+bool stem_tc_stats_ok(int Cin, int Cout);
+size_t stem_tc_stats_partial_floats(int N, int H, int W, int Cout);
 size_t stem_tc_wgrad_workspace(int N, int H, int W, int Cin, int Cout);
 int stem_tc_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy, int64_t dy_ld,
                       float* dw, int accumulate, int N, int H, int W, int Cin, int Cout, void* ws, size_t ws_bytes,
@@ -200,6 +204,24 @@ int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
     stem_fwd_kernel<32><<<grid, 128, 0, s>>>(G, w, bias, static_cast<__nv_bfloat16*>(y), y_ld, th, tw);
   UNETK_LAUNCHED();
   return 0;
+}
+
+// Stem conv + the BatchNorm statistics of its (bf16) output: in the tensor-core kernel's epilogue when it applies,
+// else the conv followed by the statistics pass (same sums).
+size_t stem_stats_partial_floats(int N, int H, int W, int Cout) {
+  const size_t a = chan_partial_floats(static_cast<int64_t>(N) * H * W, Cout);
+  const size_t b = (Cout % 64 == 0 && Cout <= 256) ? stem_tc_stats_partial_floats(N, H, W, Cout) : 0;
+  return a > b ? a : b;
+}
+int stem_fwd_stats_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
+                       void* y, int64_t y_ld, float* partial, double* sums, int N, int H, int W, int Cin, int Cout,
+                       cudaStream_t s) {
+  static int fuse = -1;
+  if (fuse < 0) { const char* e = getenv("UNETK_STEM_STATS"); fuse = e ? atoi(e) : 1; }
+  if (fuse && use_tc(Cin, Cout, 256) && stem_tc_stats_ok(Cin, Cout))
+    return stem_tc_fwd_run(x, sn, sc, sh, sw, w, bias, y, y_ld, N, H, W, Cin, Cout, s, partial, sums);
+  if (int rc = stem_fwd_run(x, sn, sc, sh, sw, w, bias, y, y_ld, N, H, W, Cin, Cout, s)) return rc;
+  return bn_stats_run(y, y_ld, static_cast<int64_t>(N) * H * W, Cout, partial, sums, s);
 }
 
 size_t stem_wgrad_workspace(int N, int H, int W, int Cin) {

@@ -19,6 +19,9 @@
 
 namespace unetk {
 
+int conv_stats_sums_launch(const float* partial, int grid, int num_n_tiles, int BN, int C, double* sums,
+                           cudaStream_t stream);   // conv_gemm.cu
+
 namespace {
 
 constexpr int kTile = 128;     // pixels per tile (consecutive along W)
@@ -62,7 +65,8 @@ __device__ __forceinline__ void load_patch(const StemTc& G, int n, int h, int w,
 template <int CMAX>   // TMEM columns allocated = max Cout handled (64 / 128 / 256): small CMAX => more CTAs per SM
 __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) stem_tc_fwd_kernel(const StemTc G, const float* __restrict__ wgt,
                                                             const float* __restrict__ bias,
-                                                            __nv_bfloat16* __restrict__ y, int64_t y_ld, int num_tiles) {
+                                                            __nv_bfloat16* __restrict__ y, int64_t y_ld, int num_tiles,
+                                                            float* __restrict__ stats_partial) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ uint8_t smem_raw[];
@@ -71,8 +75,11 @@ __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) st
   uint8_t* sB = sA + kTile * 128;                      // [kChunks][Cout rows][16 B]
   uint64_t* bar = reinterpret_cast<uint64_t*>(sB + kChunks * CMAX * 16);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  float* sStats = reinterpret_cast<float*>(bar + 8);   // [4 warps][2][CMAX]: BatchNorm sum / sum of squares (optional)
   const int tid = threadIdx.x, warp = tid >> 5;
   const int Cout = G.Cout, K = 9 * G.Cin;
+  if (stats_partial != nullptr)
+    for (int i = tid; i < 4 * 2 * CMAX; i += kTile) sStats[i] = 0.f;
 
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc<CMAX>(slot);
@@ -178,10 +185,35 @@ __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) st
             *reinterpret_cast<uint4*>(y + (static_cast<int64_t>(row) * G.W + ww) * y_ld + c0 + piece * 8) = val;
           }
         }
+        if (stats_partial != nullptr) {
+          // BatchNorm statistics of the bf16 values just stored: lane owns channels c0 + 2*lane, +1 and sums them
+          // over the warp's 32 staged rows (one 4-byte word per row: conflict-free), then adds into its own slot
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const int pc = lane >> 2, off = (lane & 3) * 4;
+          const int rows = min(32, G.W - (tw * kTile + warp * 32));
+#pragma unroll 8
+          for (int rr = 0; rr < rows; ++rr) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(wbuf + rr * 128 + ((pc ^ (rr & 7)) << 4) + off);
+            const float a = bf16_lo(v), b = bf16_hi(v);
+            s0 += a; q0 = fmaf(a, a, q0);
+            s1 += b; q1 = fmaf(b, b, q1);
+          }
+          float* st = sStats + warp * 2 * CMAX + c0 + 2 * lane;
+          st[0] += s0; st[1] += s1; st[CMAX] += q0; st[CMAX + 1] += q1;
+        }
       }
     }
     tc_fence_before();   // TMEM reads done before the next tile's MMAs overwrite the accumulator
     __syncthreads();     // ... and sA may be rewritten (its MMAs completed: the commit barrier was waited on)
+  }
+  if (stats_partial != nullptr) {   // partial[cta][2][Cout]; the loop's last __syncthreads ordered the slot updates
+    for (int i = tid; i < 2 * Cout; i += kTile) {
+      const int k = i / Cout, c = i % Cout;
+      float t = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 4; ++wq) t += sStats[wq * 2 * CMAX + k * CMAX + c];
+      stats_partial[static_cast<size_t>(blockIdx.x) * 2 * Cout + i] = t;
+    }
   }
   if (warp == 0) {
     tc_fence_after();
@@ -189,15 +221,27 @@ __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) st
   }
 }
 
+int stem_tc_fwd_grid(int tiles, int CMAX) {
+  const int per_sm = (512 / CMAX) < 6 ? (512 / CMAX) : 6;   // 6 / 4 / 2
+  return tiles < per_sm * num_sms() ? tiles : per_sm * num_sms();
+}
+
 template <int CMAX>
-int stem_tc_fwd_launch(const StemTc& G, const float* w, const float* bias, void* y, int64_t y_ld, int tiles, cudaStream_t s) {
-  const int smem = kTile * 128 + kChunks * CMAX * 16 + 64 + 128;
+int stem_tc_fwd_launch(const StemTc& G, const float* w, const float* bias, void* y, int64_t y_ld, int tiles, cudaStream_t s,
+                       float* stats_partial = nullptr, double* stats_sums = nullptr) {
+  const int smem = kTile * 128 + kChunks * CMAX * 16 + 64 + 128 + 4 * 2 * CMAX * 4;
   // CTAs per SM: bounded by TMEM (512 / CMAX columns); one CTA builds its patch tile while the others' MMAs /
   // stores run
-  const int per_sm = (512 / CMAX) < 6 ? (512 / CMAX) : 6;   // 6 / 4 / 2
-  const int grid = tiles < per_sm * num_sms() ? tiles : per_sm * num_sms();
-  UNETK_CUDA(launch_pdl(stem_tc_fwd_kernel<CMAX>, dim3(grid), dim3(kTile), smem, s, G, w, bias, static_cast<__nv_bfloat16*>(y), y_ld, tiles));
+  const int grid = stem_tc_fwd_grid(tiles, CMAX);
+  static bool configured = false;
+  if (!configured) {
+    UNETK_CUDA(cudaFuncSetAttribute(stem_tc_fwd_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  UNETK_CUDA(launch_pdl(stem_tc_fwd_kernel<CMAX>, dim3(grid), dim3(kTile), smem, s, G, w, bias, static_cast<__nv_bfloat16*>(y), y_ld, tiles,
+                        stats_partial));
   UNETK_LAUNCHED();
+  if (stats_partial != nullptr) return conv_stats_sums_launch(stats_partial, grid, 1, G.Cout, G.Cout, stats_sums, s);
   return 0;
 }
 
@@ -321,17 +365,28 @@ int stem_tc_wgrad_grid(int64_t tiles) {
 
 bool stem_tc_ok(int Cin, int Cout) { return Cin >= 1 && 9 * Cin <= kK && Cout % 16 == 0 && Cout >= 16 && Cout <= 256; }
 
+// BatchNorm statistics in the epilogue: whole 64-channel groups only (they are taken from the staged store tiles)
+bool stem_tc_stats_ok(int Cin, int Cout) { return stem_tc_ok(Cin, Cout) && Cout % 64 == 0; }
+size_t stem_tc_stats_partial_floats(int N, int H, int W, int Cout) {
+  const int64_t tiles = static_cast<int64_t>(N) * H * ((W + kTile - 1) / kTile);
+  const int cmax = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+  return static_cast<size_t>(stem_tc_fwd_grid(static_cast<int>(tiles < (1 << 30) ? tiles : (1 << 30)), cmax)) * 2 * Cout;
+}
+
 int stem_tc_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
-                    void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s) {
+                    void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s, float* stats_partial,
+                    double* stats_sums) {
   UNETK_CHECK(stem_tc_ok(Cin, Cout), -1, "stem_tc: Cin=%d Cout=%d not supported", Cin, Cout);
   UNETK_CHECK(y_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, -1, "stem_tc: output must be 16-byte aligned");
   StemTc G{x, sn, sc, sh, sw, N, H, W, Cin, Cout, (W + kTile - 1) / kTile};
   const int64_t tiles64 = static_cast<int64_t>(N) * H * G.tiles_w;
   UNETK_CHECK(tiles64 < (1ll << 31), -1, "stem_tc: too many tiles");
   const int tiles = static_cast<int>(tiles64);
-  if (Cout <= 64) return stem_tc_fwd_launch<64>(G, w, bias, y, y_ld, tiles, s);
-  if (Cout <= 128) return stem_tc_fwd_launch<128>(G, w, bias, y, y_ld, tiles, s);
-  return stem_tc_fwd_launch<256>(G, w, bias, y, y_ld, tiles, s);
+  UNETK_CHECK(stats_partial == nullptr || (stem_tc_stats_ok(Cin, Cout) && stats_sums != nullptr), -1,
+              "stem_tc: fused statistics need Cout %% 64 == 0");
+  if (Cout <= 64) return stem_tc_fwd_launch<64>(G, w, bias, y, y_ld, tiles, s, stats_partial, stats_sums);
+  if (Cout <= 128) return stem_tc_fwd_launch<128>(G, w, bias, y, y_ld, tiles, s, stats_partial, stats_sums);
+  return stem_tc_fwd_launch<256>(G, w, bias, y, y_ld, tiles, s, stats_partial, stats_sums);
 }
 
 size_t stem_tc_wgrad_workspace(int N, int H, int W, int Cin, int Cout) {

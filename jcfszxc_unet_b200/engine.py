@@ -306,8 +306,8 @@ class ConvBNReLU:
         self._wver = -1
         lib = _lib.load()
         units = N * H * W
-        plan.need(max(lib.unetk_chan_partial_floats(units, self.cout), lib.unetk_conv_stats_partial_floats(self.cout)),
-                  0, self.cout)
+        plan.need(max(lib.unetk_chan_partial_floats(units, self.cout), lib.unetk_conv_stats_partial_floats(self.cout),
+                      lib.unetk_stem_stats_partial_floats(N, H, W, self.cout) if self.stem else 0), 0, self.cout)
         if plan.with_grad:
             if self.stem:
                 plan.need(0, lib.unetk_stem_wgrad_workspace(N, H, W, self.cin))
@@ -317,6 +317,7 @@ class ConvBNReLU:
             if p is not None:
                 plan.register_param(p)
         self.acc_w = self.acc_b = self.acc_bn = self.acc_x = self.acc_res = False
+        self.head_fused = False  # set by Head(fuse=self): the head applies this unit's BatchNorm + ReLU itself
         self.colsum_sinks = []   # (channel offset in x, C, fp32 bias gradient, accumulate): see ConvT2x2.fuse_bias_grad
         plan.ops.append(self)
 
@@ -358,9 +359,11 @@ class ConvBNReLU:
         bias = self.conv.bias.detach() if self.conv.bias is not None else None
         batch_stats = bn is not None and (P.training or not bn.track_running_stats)
         if self.stem:
-            ops.stem_fwd(P.image.x, self.w3 if self.w3 is not None else self.conv.weight, bias, self.raw.t)
+            w = self.w3 if self.w3 is not None else self.conv.weight
             if batch_stats:
-                ops.bn_stats(self.raw.t, P.partial, P.sums)
+                ops.stem_fwd_stats(P.image.x, w, bias, self.raw.t, P.partial, P.sums)
+            else:
+                ops.stem_fwd(P.image.x, w, bias, self.raw.t)
         elif batch_stats:
             # conv epilogue also produces the per-channel (sum, sum of squares) of its bf16 output
             ops.conv_fwd_stats(self.x.t, self.pack.ab, bias, self.raw.t, P.partial, P.sums, self.k, self.stride)
@@ -383,12 +386,14 @@ class ConvBNReLU:
                             bn.num_batches_tracked if track else None, sc, sh, mu, iv)
         else:
             ops.bn_eval_fold(gamma, beta, bn.eps, bn.running_mean, bn.running_var, sc, sh, mu, iv)
+        if self.head_fused:
+            return   # `out` is never materialised: Head.fwd reads `raw` and (scale, shift)
         ops.bn_apply(self.raw.t, sc, sh, self.out.t, self.pooled.t if self.pooled is not None else None, self.relu,
                      self.res.t if self.res is not None else None)
 
     def bwd(self):
         P = self.plan
-        if self.bn is not None:
+        if self.bn is not None and not self.head_fused:   # fused: Head.bwd has already written raw.g and dgamma/dbeta
             sc, sh, mu, iv = self.stat[0], self.stat[1], self.stat[2], self.stat[3]
             g1 = self.out.g
             gp = self.pooled.g if self.pooled is not None else None
@@ -544,9 +549,13 @@ class Head:
     """OutConv (1x1, C -> 1) fused with sigmoid + BCE-with-logits + dice sums when labels are attached.
     Reference: unet_parts.py:73-79; train.py:264-278; utils/dice_score.py:13-59."""
 
-    def __init__(self, plan: Plan, x: Act, conv: torch.nn.Conv2d, post_sigmoid: bool = False):
+    def __init__(self, plan: Plan, x: Act, conv: torch.nn.Conv2d, post_sigmoid: bool = False,
+                 fuse: "ConvBNReLU | None" = None):
         """post_sigmoid: the model ends in nn.Sigmoid (ResUNet.py:47-50, UNetPP.py:105-106); `logits` then holds
-        sigmoid(conv) — the model output — which train.py:264-278 feeds to the loss as if it were a logit."""
+        sigmoid(conv) — the model output — which train.py:264-278 feeds to the loss as if it were a logit.
+        fuse: the ConvBNReLU unit that produces `x`, when the head is the ONLY consumer of x (UNet.py:53-54,
+        AttentionUNet.py:83-84, UNetPP.py:104-105): its BatchNorm + ReLU pass and their backward are folded into the
+        head's passes over the conv output, x and d(x) are never written (UNETK_FUSE_HEAD=0 keeps them apart)."""
         assert conv.kernel_size == (1, 1)
         if conv.out_channels != 1:
             raise NotImplementedError("the fused head supports n_classes == 1 (every BASELINE.json config)")
@@ -564,6 +573,13 @@ class Head:
         self.gscale = 1.0
         self.acc_w = False
         plan.need(_lib.load().unetk_head_partial_floats(self.npix, self.C), 0, self.C)
+        self.prod = None
+        if (fuse is not None and os.environ.get("UNETK_FUSE_HEAD", "1") != "0" and fuse.out is x and fuse.bn is not None
+                and fuse.res is None and fuse.pooled is None and self.C in (8, 16, 32, 64, 128, 256)):
+            self.prod = fuse
+            fuse.head_fused = True
+            plan.need(_lib.load().unetk_bn_head_partial_floats(self.npix, self.C), 0, self.C)
+            self.dz = torch.empty(self.npix, dtype=torch.float32, device=dev) if plan.with_grad else None
         plan.register_param(conv.weight)
         if conv.bias is not None:
             plan.register_param(conv.bias)
@@ -586,8 +602,13 @@ class Head:
         P = self.plan
         w = self.conv.weight.detach().view(-1)
         b = self.conv.bias.detach() if self.conv.bias is not None else None
-        ops.head_fwd(self.x.t, w, b, self.labels, self.logits, P.partial,
-                     self.loss_sums if self.labels is not None else None, self.post_sigmoid)
+        sums = self.loss_sums if self.labels is not None else None
+        if self.prod is not None:
+            u = self.prod
+            ops.bn_head_fwd(u.raw.t, u.stat[0], u.stat[1], u.relu, w, b, self.labels, self.logits, P.partial, sums,
+                            self.post_sigmoid)
+        else:
+            ops.head_fwd(self.x.t, w, b, self.labels, self.logits, P.partial, sums, self.post_sigmoid)
         if self.labels is not None and self.auto_finalize:
             npix = self.npix
             if self.sync_loss is not None:
@@ -601,6 +622,19 @@ class Head:
     def bwd(self):
         P = self.plan
         w = self.conv.weight.detach().view(-1)
+        if self.prod is not None:
+            u = self.prod
+            sc, sh, mu, iv = u.stat[0], u.stat[1], u.stat[2], u.stat[3]
+            ops.bn_head_bwd_reduce(u.raw.t, sc, sh, mu, u.relu, w, self.labels, self.logits, self.fin, self.dlogits,
+                                   self.gscale, self.dz, self.dw.view(-1) if self.dw is not None else None, self.db,
+                                   P.sums, P.partial, self.acc_w, self.post_sigmoid)
+            count = self.npix
+            if P.sync_sums is not None:
+                count = P.sync_sums(P.sums[: 2 * self.C], count)
+            ops.bn_bwd_coef(P.sums, count, sc, mu, iv, u.dgamma, u.dbeta, P.coef, accumulate=u.acc_bn,
+                            dconv_bias=u.dbias)
+            ops.bn_head_bwd_apply(u.raw.t, sc, sh, u.relu, w, self.dz, P.coef, u.raw.g)
+            return
         ops.head_bwd(self.x.t, w, self.labels, self.logits, self.fin, self.dlogits, self.gscale, self.x.g,
                      self.dw.view(-1) if self.dw is not None else None, self.db, P.partial, self.acc_w,
                      self.post_sigmoid)
@@ -952,6 +986,7 @@ def build_unet_plan(model, N: int, H: int, W: int, device, training: bool, grad_
         mid = P.act(h, w, dc[0].out_channels)
         ConvBNReLU(P, cats[i], dc[0], dc[1], mid)
         y = P.act(h, w, dc[3].out_channels)
-        ConvBNReLU(P, mid, dc[3], dc[4], y)
-    P.head = Head(P, y, model.outc.conv) if model.outc.conv.out_channels == 1 else HeadMulti(P, y, model.outc.conv)
+        last = ConvBNReLU(P, mid, dc[3], dc[4], y)
+    P.head = (Head(P, y, model.outc.conv, fuse=last) if model.outc.conv.out_channels == 1
+              else HeadMulti(P, y, model.outc.conv))
     return P.finalize(grad_views)

@@ -220,6 +220,17 @@ def chan_partial_floats(units: int, c: int) -> int:
     return _lib.load().unetk_chan_partial_floats(units, c)
 
 
+def stem_fwd_stats(x, w, bias, y, partial, sums):
+    """stem_fwd + bn_stats of its output in one launch (statistics from the conv epilogue)."""
+    n, cin, h, wd = x.shape
+    cout = y.shape[3]
+    xp, sn, sc, sh, sw = _img(x)
+    yp, yld = nhwc(y)
+    _lib.call("unetk_stem_conv3x3_fwd_bnstats", xp, sn, sc, sh, sw, _f32(w.detach()), _f32(bias), yp, yld,
+              partial.data_ptr(), sums.data_ptr(), n, h, wd, cin, cout, _stream())
+    return y
+
+
 def bn_stats(x, partial, sums):
     """sums (fp64 [2,C]) <- per-channel (sum, sum of squares) of x [N,H,W,C]."""
     n, h, w, c = x.shape
@@ -320,6 +331,36 @@ def head_bwd(x, w, labels, logits, fin, dlogits, gscale, dx, dw, db, partial, ac
     dxp, dxld = nhwc(dx)
     _lib.call("unetk_head_bwd", xp, xld, _f32(w), _f32(labels), _f32(logits), _f32(fin), _f32(dlogits), float(gscale),
               int(post_sigmoid), dxp, dxld, _f32(dw), _f32(db), int(accumulate), n * h * wd, c, partial.data_ptr(), _stream())
+
+
+def bn_head_partial_floats(npix: int, c: int) -> int:
+    return _lib.load().unetk_bn_head_partial_floats(npix, c)
+
+
+def bn_head_fwd(raw, scale, shift, relu, w, bias, labels, logits, partial, sums, post_sigmoid=False):
+    """unetk_bn_apply + unetk_head_fwd in one pass over the conv output (the activation is never written)."""
+    n, h, wd, c = raw.shape
+    rp, rld = nhwc(raw)
+    _lib.call("unetk_bn_head_fwd", rp, rld, _f32(scale), _f32(shift), int(relu), _f32(w), _f32(bias), _f32(labels),
+              _f32(logits), int(post_sigmoid), n * h * wd, c, partial.data_ptr(),
+              sums.data_ptr() if sums is not None else None, _stream())
+
+
+def bn_head_bwd_reduce(raw, scale, shift, mean, relu, w, labels, logits, fin, dlogits, gscale, dz, dw, db, sums, partial,
+                       accumulate=False, post_sigmoid=False):
+    n, h, wd, c = raw.shape
+    rp, rld = nhwc(raw)
+    _lib.call("unetk_bn_head_bwd_reduce", rp, rld, _f32(scale), _f32(shift), _f32(mean), int(relu), _f32(w), _f32(labels),
+              _f32(logits), _f32(fin), _f32(dlogits), float(gscale), int(post_sigmoid), _f32(dz), _f32(dw), _f32(db),
+              int(accumulate), sums.data_ptr(), n * h * wd, c, partial.data_ptr(), _stream())
+
+
+def bn_head_bwd_apply(raw, scale, shift, relu, w, dz, coef, draw):
+    n, h, wd, c = raw.shape
+    rp, rld = nhwc(raw)
+    dp, dld = nhwc(draw)
+    _lib.call("unetk_bn_head_bwd_apply", rp, rld, _f32(scale), _f32(shift), int(relu), _f32(w), _f32(dz), _f32(coef),
+              dp, dld, n * h * wd, c, _stream())
 
 
 def grad_clip_coef(g, gscale, max_norm, partial, out):

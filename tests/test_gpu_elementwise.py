@@ -181,6 +181,32 @@ def test_stem_conv(layout, cout, bias):
     assert (dw - refw).abs().max().item() <= 1e-3 * refw.abs().max().item()
 
 
+@pytest.mark.parametrize("n,h,w,cout,bias", [(2, 36, 40, 64, False), (1, 20, 200, 128, True), (3, 16, 128, 64, True),
+                                             (2, 24, 72, 32, True)])
+def test_stem_conv_with_fused_bn_statistics(n, h, w, cout, bias):
+    """unetk_stem_conv3x3_fwd_bnstats = unetk_stem_conv3x3_fwd + unetk_bn_stats (statistics of the bf16 output taken
+    in the conv epilogue; Cout = 32 takes the two-pass route inside the library): same output bits, same sums."""
+    ops = _ops()
+    from jcfszxc_unet_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(cout + w)
+    x = torch.rand(n, 3, h, w, device=DEV, generator=g)
+    wt = torch.randn(cout, 3, 3, 3, device=DEV, generator=g) * 0.2
+    b = torch.randn(cout, device=DEV, generator=g) if bias else None
+    npart = max(_lib.load().unetk_stem_stats_partial_floats(n, h, w, cout), ops.chan_partial_floats(n * h * w, cout), 4096)
+    partial = torch.empty(npart, device=DEV)
+    y_a = torch.empty(n, h, w, cout, device=DEV, dtype=torch.bfloat16)
+    y_b = torch.empty_like(y_a)
+    s_a = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    s_b = torch.zeros_like(s_a)
+    ops.stem_fwd(x, wt, b, y_a)
+    ops.bn_stats(y_a, partial, s_a)
+    ops.stem_fwd_stats(x, wt, b, y_b, partial, s_b)
+    assert torch.equal(y_a, y_b)
+    ref = torch.stack([y_a.double().sum(dim=(0, 1, 2)), (y_a.double() ** 2).sum(dim=(0, 1, 2))]).view(-1)
+    assert torch.allclose(s_b, ref, rtol=2e-6, atol=1e-4)
+    assert torch.allclose(s_b, s_a, rtol=2e-6, atol=1e-4)
+
+
 @pytest.mark.parametrize("c", [64, 32])
 def test_head_loss_forward_backward_vs_oracle(c):
     from oracle import unet_oracle as O
@@ -236,6 +262,98 @@ def test_head_loss_forward_backward_vs_oracle(c):
     ref_loss, _, ref_dl = O.segmentation_loss(torch.full((1, 1, 4, 8), -40.0, device=DEV), lt)
     assert float(ref_dl) == 0.0 and abs(float(fin[2]) - 1.0) <= 1e-6 and abs(float(fin[0]) - float(ref_loss)) <= 1e-6
     assert float(fin[4]) == 0.0 and float(fin[5]) == 0.0
+
+
+@pytest.mark.parametrize("n,h,w,c,relu,post_sigmoid,pad", [(2, 24, 40, 64, True, False, 0), (1, 20, 12, 32, True, True, 32),
+                                                          (3, 8, 8, 128, False, False, 0), (1, 3, 5, 8, True, False, 8)])
+def test_bn_head_fused_equals_separate_passes_and_oracle(n, h, w, c, relu, post_sigmoid, pad):
+    """DoubleConv's last BatchNorm+ReLU folded into OutConv + loss (unet_parts.py:24-31,73-79; train.py:264-278):
+    forward logits bit-identical to unetk_bn_apply -> unetk_head_fwd, backward equal to unetk_head_bwd ->
+    unetk_bn_bwd_reduce/apply up to the summation order, and both against autograd on the same graph."""
+    from oracle import unet_oracle as O
+
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(c + h)
+    buf = torch.zeros(n, h, w, c + pad, device=DEV, dtype=torch.bfloat16)
+    raw = buf[..., pad:]
+    raw.copy_(torch.randn(n, h, w, c, device=DEV, generator=g) * 1.5 + 0.2)
+    gamma = torch.rand(c, device=DEV, generator=g) + 0.5
+    beta = torch.randn(c, device=DEV, generator=g) * 0.3
+    wt = torch.randn(c, device=DEV, generator=g) * 0.3
+    b = torch.randn(1, device=DEV, generator=g)
+    labels = (torch.rand(n, 1, h, w, device=DEV, generator=g) < 0.12).float()
+    npix = n * h * w
+    partial = torch.empty(max(ops.bn_head_partial_floats(npix, c), ops.chan_partial_floats(npix, c), 4096), device=DEV)
+    sums = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
+    stat = torch.zeros(4, c, device=DEV)
+    ops.bn_stats(raw, partial, sums)
+    ops.bn_finalize(sums, npix, gamma, beta, 1e-5, 0.1, None, None, None, stat[0], stat[1], stat[2], stat[3])
+    # --- separate passes
+    out = torch.empty(n, h, w, c, device=DEV, dtype=torch.bfloat16)
+    ops.bn_apply(raw, stat[0], stat[1], out, None, relu)
+    ls_a, ls_b = torch.zeros(4, dtype=torch.float64, device=DEV), torch.zeros(4, dtype=torch.float64, device=DEV)
+    fin = torch.zeros(8, device=DEV)
+    logits_a, logits_b = torch.empty(n, 1, h, w, device=DEV), torch.empty(n, 1, h, w, device=DEV)
+    ops.head_fwd(out, wt, b, labels, logits_a, partial, ls_a, post_sigmoid)
+    ops.bn_head_fwd(raw, stat[0], stat[1], relu, wt, b, labels, logits_b, partial, ls_b, post_sigmoid)
+    assert torch.equal(logits_a, logits_b)
+    assert torch.allclose(ls_a, ls_b, rtol=1e-6, atol=1e-9)
+    ops.loss_finalize(ls_b, npix, fin)
+    dx = torch.empty_like(out)
+    dw_a, db_a = torch.zeros(c, device=DEV), torch.zeros(1, device=DEV)
+    ops.head_bwd(out, wt, labels, logits_a, fin, None, 1.0, dx, dw_a, db_a, partial, post_sigmoid=post_sigmoid)
+    dgamma_a, dbeta_a = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    coef = torch.zeros(2 * c, device=DEV)
+    draw_a = torch.empty(n, h, w, c, device=DEV, dtype=torch.bfloat16)
+    ops.bn_bwd_reduce(raw, dx, None, stat[0], stat[1], stat[2], stat[3], partial, sums, relu)
+    ops.bn_bwd_apply(raw, dx, None, stat[0], stat[1], stat[2], stat[3], sums, npix, dgamma_a, dbeta_a, coef, draw_a, relu)
+    # --- fused
+    dz = torch.empty(npix, device=DEV)
+    dw_b, db_b = torch.full((c,), 2.0, device=DEV), torch.full((1,), 3.0, device=DEV)
+    dgamma_b, dbeta_b = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    dbuf = torch.zeros(n, h, w, c + pad, device=DEV, dtype=torch.bfloat16)
+    draw_b = dbuf[..., pad:]
+    ops.bn_head_bwd_reduce(raw, stat[0], stat[1], stat[2], relu, wt, labels, logits_b, fin, None, 1.0, dz, dw_b, db_b, sums,
+                           partial, accumulate=True, post_sigmoid=post_sigmoid)
+    ops.bn_bwd_coef(sums, npix, stat[0], stat[2], stat[3], dgamma_b, dbeta_b, coef)
+    ops.bn_head_bwd_apply(raw, stat[0], stat[1], relu, wt, dz, coef, draw_b)
+    assert float(dbuf[..., :pad].abs().sum()) == 0.0
+    tol = lambda t: 1e-4 * t.abs().max().item() + 1e-12
+    assert torch.allclose(dw_b - 2.0, dw_a, rtol=1e-4, atol=max(tol(dw_a), 1e-6))          # accumulate=True adds
+    assert torch.allclose(db_b - 3.0, db_a, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(dgamma_b, dgamma_a, rtol=1e-4, atol=tol(dgamma_a))
+    assert torch.allclose(dbeta_b, dbeta_a, rtol=1e-4, atol=tol(dbeta_a))
+    # d(raw): same formula, sums differ in the last bits -> at most one bf16 ulp apart
+    d = (draw_a.float() - draw_b.float()).abs()
+    assert (d <= 2 ** -7 * draw_a.float().abs() + 1e-12).all()
+    # --- autograd on the same graph (bf16 rounding of the activation emulated straight-through)
+    x = raw.float().permute(0, 3, 1, 2).requires_grad_(True)
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    wr, br = wt.view(1, c, 1, 1).clone().requires_grad_(True), b.clone().requires_grad_(True)
+    z = F.batch_norm(x, None, None, gm, bt, True, 0.1, 1e-5)
+    z = z + (z.detach().bfloat16().float() - z.detach())
+    a = F.relu(z) if relu else z
+    y = F.conv2d(a, wr, br)
+    if post_sigmoid:
+        y = torch.sigmoid(y)
+    loss, _, _ = O.segmentation_loss(y, labels)
+    loss.backward()
+    assert torch.allclose(logits_b, y.detach(), rtol=1e-4, atol=1e-4)
+    assert abs(float(fin[0]) - float(loss)) <= 1e-5
+    ref = x.grad.permute(0, 2, 3, 1)
+    assert (draw_b.float() - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item()
+    assert torch.allclose(dw_b - 2.0, wr.grad.view(-1), rtol=2e-3, atol=2e-3 * wr.grad.abs().max().item())
+    assert torch.allclose(db_b - 3.0, br.grad, rtol=2e-3, atol=1e-6)
+    # (autograd keeps d(a) = dz*w in fp32 where both kernel paths round it to bf16, as the bf16 activation gradient is)
+    assert torch.allclose(dgamma_b, gm.grad, rtol=1e-2, atol=1e-2 * gm.grad.abs().max().item())
+    assert torch.allclose(dbeta_b, bt.grad, rtol=1e-2, atol=1e-2 * bt.grad.abs().max().item())
+    # gradient handed in by autograd (loss computed by the caller)
+    dlog = torch.randn(n, 1, h, w, device=DEV, generator=g)
+    ops.bn_head_bwd_reduce(raw, stat[0], stat[1], stat[2], relu, wt, None, logits_b if post_sigmoid else None, None, dlog,
+                           0.5, dz, dw_b, db_b, sums, partial, post_sigmoid=post_sigmoid)
+    exp = 0.5 * dlog.view(-1) * ((logits_b * (1 - logits_b)).view(-1) if post_sigmoid else 1.0)
+    assert torch.allclose(dz, exp, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(db_b, exp.sum().view(1), rtol=1e-4, atol=1e-5)
 
 
 def test_clip_and_rmsprop_vs_oracle():

@@ -185,6 +185,27 @@ def test_trainer_step_vs_oracle_train_step():
     assert abs(results[True][0][1] - float(g["loss1"])) <= 2e-2
 
 
+def test_fused_head_equals_separate_bn_and_head_passes(monkeypatch):
+    """The last DoubleConv's BatchNorm+ReLU folded into OutConv+loss (engine.Head `fuse`) against the same step with
+    the passes kept apart (UNETK_FUSE_HEAD=0): identical loss (the logits are bit-identical), gradients equal up to
+    the summation order of the two BatchNorm backward sums."""
+    from jcfszxc_unet_b200.trainer import Trainer
+
+    out = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("UNETK_FUSE_HEAD", fuse)
+        m = _model(42).to(DEV).train()
+        tr = Trainer(m, lr=1e-3, use_cuda_graph=False)
+        images, labels = _inputs(7, 2, 48, 64)
+        loss = float(tr.step(images.to(DEV), labels.to(DEV)))
+        assert (tr.plan.head.prod is not None) == (fuse == "1")
+        out[fuse] = (loss, tr.plan.head.logits.clone(), {k: tr.grad_views[id(p)].detach().clone() for k, p in m.named_parameters()})
+    assert out["1"][0] == out["0"][0]
+    assert torch.equal(out["1"][1], out["0"][1])
+    for k, g in out["0"][2].items():
+        assert _l2rel(out["1"][2][k], g) <= 2e-3, (k, _l2rel(out["1"][2][k], g))
+
+
 def test_blocks_standalone_vs_golden():
     from UNetFamily.utils.unet_parts import DoubleConv, Down, OutConv, Up
 
