@@ -220,7 +220,7 @@ int unetk_head_bwd(const void* x, int64_t x_ld, const float* w, const float* lab
  * bn_head_bwd_reduce : one pass over `raw`: dz[pix] (fp32, kept for the apply pass), dw/db of the head ((+)= when
  *                      accumulate), and sums = double[2][C] = the two BatchNorm backward sums of unetk_bn_bwd_reduce.
  * bn_head_bwd_apply  : d(raw) from (raw, dz) and coef = [K0 | K1] of unetk_bn_bwd_coef.
- * C power of two in [8,256]; partial >= unetk_bn_head_partial_floats(npix, C) floats. */
+ * C = 32 or 64 (the widths in front of OutConv in the U-Net family); partial >= unetk_bn_head_partial_floats(npix, C). */
 size_t unetk_bn_head_partial_floats(int64_t npix, int C);
 int unetk_bn_head_fwd(const void* raw, int64_t raw_ld, const float* scale, const float* shift, int relu, const float* w,
                       const float* bias, const float* labels, float* logits, int post_sigmoid, int64_t npix, int C,

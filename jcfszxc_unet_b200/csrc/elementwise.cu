@@ -5,6 +5,7 @@
 // shared memory -> per-block partials, and finish with an ordered (deterministic) second stage.
 // Reference semantics replaced: nn.BatchNorm2d + nn.ReLU(inplace) + nn.MaxPool2d(2) inside
 // DoubleConv/Down (UNetFamily/utils/unet_parts.py:24-31,42-44) and their autograd backward.
+#include <cstdlib>
 #include "reduce2.cuh"
 #include "fastdiv.cuh"
 #include "host_common.cuh"
@@ -183,13 +184,13 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ shift,
                                                             const __nv_bfloat16* __restrict__ res, int64_t res_ld,
                                                             __nv_bfloat16* __restrict__ out, int64_t out_ld,
-                                                            int64_t npix, int C, int relu) {
+                                                            int64_t npix, int C, int relu, int rev) {
   pdl_trigger();
   pdl_wait();
   Lanes L(C);
   if (!L.active) return;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
-  const int64_t first = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
+  int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+  int64_t first = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
   if (first >= npix) return;
   const int g = L.g;
   float sc[8], sh[8];
@@ -197,6 +198,9 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16*
   for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
   const bool r = relu != 0;
   int64_t left = (npix - first + stride - 1) / stride;
+  // rev: walk from the END of the tensor — the tail of `raw` was written last by the convolution that precedes this
+  // pass and is still in the 126 MB L2 (the head of a 0.5 GB tensor is not)
+  if (rev) { first += (left - 1) * stride; stride = -stride; }
   const __nv_bfloat16* pr = raw + first * raw_ld + g * 8;
   const __nv_bfloat16* ps = RES ? res + first * res_ld + g * 8 : nullptr;
   __nv_bfloat16* po = out + first * out_ld + g * 8;
@@ -250,19 +254,21 @@ __device__ __forceinline__ void argmax4(const float (&a)[4][8], float* best, int
 __global__ void __launch_bounds__(kThreads)
 bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld, const float* __restrict__ scale,
                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int64_t out_ld,
-                     __nv_bfloat16* __restrict__ pooled, int64_t pooled_ld, int N, int H, int W, int C) {
+                     __nv_bfloat16* __restrict__ pooled, int64_t pooled_ld, int N, int H, int W, int C,
+                     int rev) {
   pdl_trigger();
   pdl_wait();
   const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cg;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;  // multiple of cg
+  int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;  // multiple of cg
   int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x;
   if (i >= total) return;
   const int g = static_cast<int>(i % cg);
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
-  for (; i < total; i += stride) {
+  if (rev) { i += (total - 1 - i) / stride * stride; stride = -stride; }   // see bn_apply_kernel
+  for (; i < total && i >= 0; i += stride) {
     int64_t t = i / cg;
     const int wo = static_cast<int>(t % Wo); t /= Wo;
     const int ho = static_cast<int>(t % Ho);
@@ -384,6 +390,7 @@ struct BnBwdArgs {
   const float* scale; const float* shift; const float* mean; const float* invstd;
   int N, H, W, C, relu;
   FastDiv fd_wu, fd_hu;   // pooled variants: division by W/2 and H/2 without a hardware divide
+  int rev;                // walk from the end of the tensors (their tails are the L2-resident part, see bn_apply_kernel)
 };
 
 // masked gradient of one pixel x 8 channels: gm = (relu && !(bf16(raw*sc+sh) > 0)) ? 0 : g
@@ -416,39 +423,59 @@ struct PoolWindow {
   template <class Emit>
   __device__ __forceinline__ void visit(const BnBwdArgs& A, const float (&sc)[8], const float (&sh)[8],
                                         Emit&& emit) const {
-    // pass 1: bf16-rounded activations of the four window pixels -> pooled argmax (2 bits per channel) and the
-    // ReLU mask (1 bit per pixel and channel), so that pass 2 does not evaluate the BatchNorm a second time
-    uint32_t argpack = 0, maskbits = 0;
-    {
-      float best[8], f[8];
+    // Everything between the BatchNorm FMA and the per-channel sums runs on PACKED bf16 pairs (HMNMX2 / HSET2 /
+    // HADD2 / LOP3): the first version evaluated mask, arg-max and gradient select per element in fp32 with bit
+    // bookkeeping, ~23 instructions per element, which made the pooled passes issue-bound (55 % of the HBM peak
+    // against 88 % for the un-pooled ones).
+    // pass 1: activations of the four window pixels (bf16-rounded like the forward's) -> ReLU masks rm[q] and
+    // "beats the running maximum" masks m[q] (strict >: the first maximum wins, as in ATen's max_pool2d)
+    uint32_t rm[4][4], m[4][4], best[4];
+    const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        unpack8(ur[q], f);
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+      unpack8(ur[q], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
-          const float v = A.relu ? fmaxf(z, 0.f) : z;
-          if (!A.relu || z > 0.f) maskbits |= 1u << (q * 8 + j);
-          if (q == 0) {
-            best[j] = v;
-          } else if (v > best[j] || v != v) {
-            best[j] = v;
-            argpack = (argpack & ~(3u << (2 * j))) | (static_cast<uint32_t>(q) << (2 * j));
-          }
+      for (int p = 0; p < 4; ++p) {
+        const __nv_bfloat162 z = __floats2bfloat162_rn(fmaf(f[2 * p], sc[2 * p], sh[2 * p]),
+                                                       fmaf(f[2 * p + 1], sc[2 * p + 1], sh[2 * p + 1]));
+        const __nv_bfloat162 v = __hmax2(z, zero2);   // the fused pool always sits behind a ReLU (checked on the host)
+        rm[q][p] = __hgt2_mask(z, zero2);
+        const uint32_t vb = *reinterpret_cast<const uint32_t*>(&v);
+        if (q == 0) {
+          best[p] = vb;
+        } else {
+          const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&best[p]);
+          m[q][p] = __hgt2_mask(v, b);
+          const __nv_bfloat162 nb = __hmax2(b, v);
+          best[p] = *reinterpret_cast<const uint32_t*>(&nb);
         }
       }
     }
-    float gy[8];
-    unpack8(ugp, gy);
+    // one-hot arg-max masks: the LAST q that beat the running maximum holds it
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const uint32_t m1 = m[1][p], m2 = m[2][p], m3 = m[3][p];
+      m[2][p] = m2 & ~m3;
+      m[1][p] = m1 & ~(m2 | m3);
+      m[0][p] = ~(m1 | m2 | m3);
+    }
+    // pass 2: gm = relu-mask & (g1 + (arg-max ? gp : 0)); the sum of the two bf16 gradients is rounded to bf16, as
+    // autograd's accumulation of the two consumers' gradients into one bf16 tensor is
+    const uint32_t gy[4] = {ugp.x, ugp.y, ugp.z, ugp.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
+      const uint32_t g[4] = {ug[q].x, ug[q].y, ug[q].z, ug[q].w};
       float r[8], gm[8];
       unpack8(ur[q], r);
-      unpack8(ug[q], gm);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (((argpack >> (2 * j)) & 3u) == static_cast<uint32_t>(q)) gm[j] += gy[j];
-        if (!((maskbits >> (q * 8 + j)) & 1u)) gm[j] = 0.f;
+      for (int p = 0; p < 4; ++p) {
+        const uint32_t sel = gy[p] & m[q][p];
+        const __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&g[p]),
+                                           *reinterpret_cast<const __nv_bfloat162*>(&sel));
+        const uint32_t sb = *reinterpret_cast<const uint32_t*>(&sum) & rm[q][p];
+        gm[2 * p] = bf16_lo(sb);
+        gm[2 * p + 1] = bf16_hi(sb);
       }
       emit(q, gm, r);
     }
@@ -460,13 +487,14 @@ struct PoolWindow {
 template <bool POOL, class Emit>
 __device__ __forceinline__ void bn_bwd_walk(const BnBwdArgs& A, const Lanes& L, const float (&sc)[8],
                                             const float (&sh)[8], Emit&& emit) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
-  const int64_t first = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
+  int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+  int64_t first = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl;
   const bool relu = A.relu != 0;
   if constexpr (!POOL) {
     const int64_t npix = static_cast<int64_t>(A.N) * A.H * A.W;
     if (first >= npix) return;
     int64_t left = (npix - first + stride - 1) / stride;   // pixels this thread visits (one division per thread)
+    if (A.rev) { first += (left - 1) * stride; stride = -stride; }
     const __nv_bfloat16* pr = A.raw + first * A.raw_ld + L.g * 8;
     const __nv_bfloat16* pg = A.g1 + first * A.g1_ld + L.g * 8;
     const int64_t sr = stride * A.raw_ld, sg = stride * A.g1_ld;
@@ -502,12 +530,14 @@ __device__ __forceinline__ void bn_bwd_walk(const BnBwdArgs& A, const Lanes& L, 
     // The nine sectors of this thread's NEXT window are pulled into L2 while the current window is evaluated (the
     // first version loaded, waited ~1 us for HBM and computed ~1 us, one window at a time: 45 % of the HBM peak on the
     // 64-channel layer; holding two windows in registers instead spills at the 128-register budget of 2 blocks/SM).
-    for (int64_t u = first; u < units; u += stride) {
+    if (first >= units) return;
+    if (A.rev) { first += (units - 1 - first) / stride * stride; stride = -stride; }
+    for (int64_t u = first; u < units && u >= 0; u += stride) {
       const int64_t pix0 = window(u);
       PoolWindow w;
       w.load(A, pix0, u, L.g);
       const int64_t un = u + stride;
-      if (un < units) {
+      if (un < units && un >= 0) {
         const int64_t pn = window(un);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -647,6 +677,13 @@ int flat_grid(int64_t total) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------- host side
+// UNETK_REVERSE=0: every pass walks its tensors front to back (A/B of the L2-tail reuse)
+static int reverse_walk() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("UNETK_REVERSE"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 #define CHECK_C(C) UNETK_CHECK((C) % 8 == 0 && (C) >= 8 && (C) <= 2048, -1, "channel count %d must be a multiple of 8 in [8,2048]", (C))
 
 size_t chan_partial_floats(int64_t units, int C) { return static_cast<size_t>(reduce_grid(units, C)) * 2 * C; }
@@ -725,18 +762,18 @@ int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const floa
     UNETK_CHECK(res == nullptr, -1, "bn_apply: fused pool and residual add cannot be combined");
     const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
     UNETK_CUDA(launch_pdl(bn_apply_pool_kernel, dim3(flat_grid_cg(total, C / 8)), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift, static_cast<__nv_bfloat16*>(out), out_ld,
-        static_cast<__nv_bfloat16*>(pooled), pooled_ld, N, H, W, C));
+        static_cast<__nv_bfloat16*>(pooled), pooled_ld, N, H, W, C, reverse_walk()));
   } else {
     const int64_t npix = static_cast<int64_t>(N) * H * W;
     const int grid = lanes_grid(npix, C, 8);
     if (res != nullptr)
       UNETK_CUDA(launch_pdl(bn_apply_kernel<true>, dim3(grid), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift,
                                                       static_cast<const __nv_bfloat16*>(res), res_ld,
-                                                      static_cast<__nv_bfloat16*>(out), out_ld, npix, C, relu));
+                                                      static_cast<__nv_bfloat16*>(out), out_ld, npix, C, relu, reverse_walk()));
     else
       UNETK_CUDA(launch_pdl(bn_apply_kernel<false>, dim3(grid), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift,
                                                        nullptr, 0, static_cast<__nv_bfloat16*>(out), out_ld, npix, C,
-                                                       relu));
+                                                       relu, reverse_walk()));
   }
   UNETK_LAUNCHED();
   return 0;
@@ -777,11 +814,12 @@ static int bn_bwd_args(BnBwdArgs* A, const void* raw, int64_t raw_ld, const void
   UNETK_CHECK(g1 != nullptr || gp != nullptr, -1, "bn_bwd: no incoming gradient");
   if (gp != nullptr) {
     UNETK_CHECK(H % 2 == 0 && W % 2 == 0, -1, "bn_bwd: pooled gradient needs even H,W");
+    UNETK_CHECK(relu, -1, "bn_bwd: the fused max-pool sits behind a ReLU (unet_parts.py:28-29,43)");
     UNETK_CHECK(static_cast<int64_t>(N) * (H / 2) * (W / 2) < (1ll << 31), -1, "bn_bwd: too many pooling windows");
   }
   *A = BnBwdArgs{static_cast<const __nv_bfloat16*>(raw), raw_ld, static_cast<const __nv_bfloat16*>(g1), g1_ld,
                  static_cast<const __nv_bfloat16*>(gp), gp_ld, scale, shift, mean, invstd, N, H, W, C, relu,
-                 FastDiv(static_cast<uint32_t>(W / 2 > 0 ? W / 2 : 1)), FastDiv(static_cast<uint32_t>(H / 2 > 0 ? H / 2 : 1))};
+                 FastDiv(static_cast<uint32_t>(W / 2 > 0 ? W / 2 : 1)), FastDiv(static_cast<uint32_t>(H / 2 > 0 ? H / 2 : 1)), 0};
   return 0;
 }
 
@@ -792,6 +830,9 @@ int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g
   BnBwdArgs A;
   if (int rc = bn_bwd_args(&A, raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, N, H, W, C, relu)) return rc;
   const bool pool = gp != nullptr;
+  // back to front: the tail of g1 was written last by the dgrad that produced it; the apply pass then runs front to
+  // back and starts on what this pass touched last
+  A.rev = reverse_walk();
   const int64_t units = pool ? static_cast<int64_t>(N) * (H / 2) * (W / 2) : static_cast<int64_t>(N) * H * W;
   const int grid = bwd_grid(units, C);
   const size_t smem = reduce_smem(C, 2);

@@ -223,6 +223,7 @@ int head_grid(int64_t npix, int C) {
   if (b < 1) b = 1;
   return static_cast<int>(b);
 }
+bool bn_head_c_ok(int C) { return C == 32 || C == 64; }   // the widths in front of OutConv in the U-Net family
 bool head_c_ok(int C) { return C == 8 || C == 16 || C == 32 || C == 64 || C == 128 || C == 256; }
 
 
@@ -254,16 +255,24 @@ __device__ __forceinline__ float head_dz(const float* __restrict__ labels, const
   return dz;
 }
 
+// Thread layout of the two kernels below (LPP = C/8 lanes per pixel, GW = 32/LPP pixels per warp and load round,
+// kU = 8 load rounds in flight): a warp iteration covers S = 8*GW pixel "slots" s = u*GW + j.  The per-PIXEL math
+// (logit -> loss terms, or logit/label -> dz: exp, log1p, reciprocal, ~100 instructions) is done ONCE per pixel with
+// all 32 lanes busy — lane L owns slots L, L+32, ... — and moved to / from the lanes that hold the pixel's channels
+// with shuffles.  (The first version evaluated it in every lane of a pixel group, i.e. at 4 live results per 32
+// lanes, and ran at 1.2-2.1 TB/s: issue-bound.)
+template <int LPP>
 __global__ void __launch_bounds__(kThreads, 2)
 bn_head_fwd_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, const float* __restrict__ scale,
                    const float* __restrict__ shift, int relu, const float* __restrict__ w,
                    const float* __restrict__ bias, const float* __restrict__ labels, float* __restrict__ logits,
-                   int post_sigmoid, int64_t npix, int C, float* __restrict__ partial) {
+                   int post_sigmoid, int64_t npix, float* __restrict__ partial) {
   pdl_trigger();
   pdl_wait();
-  const int lpp = C >> 3;
-  const int gpb = kThreads / lpp;
-  const int sub = threadIdx.x % lpp, grp = threadIdx.x / lpp;
+  constexpr int GW = 32 / LPP, kU = 8, R = (kU * GW) / 32, gpb = kThreads / LPP;
+  static_assert(R >= 1, "C > 64 is not instantiated");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPP, grp = warp * GW + lane / LPP;
   float wv[8], sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -271,21 +280,28 @@ bn_head_fwd_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, const floa
   }
   const float b = bias ? __ldg(bias) : 0.f;
   float s_bce = 0.f, s_py = 0.f, s_p = 0.f, s_y = 0.f;
-  constexpr int kU = 8;
   const int64_t step = static_cast<int64_t>(gridDim.x) * gpb;
   for (int64_t base = static_cast<int64_t>(blockIdx.x) * gpb; base < npix; base += kU * step) {
     uint4 v[kU];
-    float yv[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int64_t pix = base + u * step + grp;
-      const bool ok = pix < npix;
-      v[u] = ok ? __ldg(reinterpret_cast<const uint4*>(raw + pix * ld + sub * 8)) : make_uint4(0, 0, 0, 0);
-      yv[u] = (ok && sub == 0 && labels != nullptr) ? __ldg(labels + pix) : 0.f;
+      v[u] = pix < npix ? __ldg(reinterpret_cast<const uint4*>(raw + pix * ld + sub * 8)) : make_uint4(0, 0, 0, 0);
     }
+    // the rows of the NEXT iteration go to L2 now (one lane per pixel row): with 16 warps per SM and a long compute
+    // phase per iteration the kernel was latency-bound on these loads (profiles/r02_ncu_stem_head.txt)
+    if (sub == 0) {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t pix = base + (kU + u) * step + grp;
+        if (pix < npix) prefetch_l2(raw + pix * ld);
+      }
+    }
+    float mine[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mine[r] = 0.f;
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int64_t pix = base + u * step + grp;
       float f[8], dot = 0.f;
       unpack8(v[u], f);
 #pragma unroll
@@ -293,12 +309,21 @@ bn_head_fwd_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, const floa
         const float z = bf16_round(fmaf(f[j], sc[j], sh[j]));
         dot = fmaf(relu ? fmaxf(z, 0.f) : z, wv[j], dot);
       }
-      dot = group_sum(dot, lpp);
-      if (sub == 0 && pix < npix) {
-        const float z = post_sigmoid ? 1.f / (1.f + __expf(-(dot + b))) : dot + b;
+      dot = group_sum(dot, LPP);
+      const float t = __shfl_sync(0xffffffffu, dot, (lane % GW) * LPP);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((lane + 32 * r) / GW == u) mine[r] = t;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int slot = lane + 32 * r;
+      const int64_t pix = base + (slot / GW) * step + warp * GW + slot % GW;
+      if (pix < npix) {
+        const float z = post_sigmoid ? 1.f / (1.f + __expf(-(mine[r] + b))) : mine[r] + b;
         logits[pix] = z;
         if (labels != nullptr) {
-          const float y = yv[u];
+          const float y = __ldg(labels + pix);
           s_bce += fmaxf(z, 0.f) - z * y + log1pf(__expf(-fabsf(z)));
           float p = 1.f / (1.f + __expf(-z));
           p = fminf(fmaxf(p, kClampLo), kClampHi);
@@ -311,7 +336,6 @@ bn_head_fwd_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, const floa
   }
   __shared__ float red[4][kThreads / 32];
   s_bce = warp_sum(s_bce); s_py = warp_sum(s_py); s_p = warp_sum(s_p); s_y = warp_sum(s_y);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { red[0][warp] = s_bce; red[1][warp] = s_py; red[2][warp] = s_p; red[3][warp] = s_y; }
   __syncthreads();
   if (threadIdx.x < 4) {
@@ -324,18 +348,20 @@ bn_head_fwd_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, const floa
 // partial[blk][0][c] = sum dz*a   (head dW)          partial[blk][1][c] = sum gm          (BN: S0)
 // partial[blk][2][c] = sum gm*(raw - mean) (BN: S1)  partial[blk][3C]   = sum dz          (head db)
 //   a = act(bf16(raw*scale+shift)),  gm = mask * bf16(dz*w[c]);   dz[pix] is kept (fp32) for the apply pass.
+template <int LPP>
 __global__ void __launch_bounds__(kThreads, 2)
 bn_head_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, const float* __restrict__ scale,
                           const float* __restrict__ shift, const float* __restrict__ mean, int relu,
                           const float* __restrict__ w, const float* __restrict__ labels,
                           const float* __restrict__ logits, const float* __restrict__ fin,
                           const float* __restrict__ dlogits, float gscale, int post_sigmoid,
-                          float* __restrict__ dz_out, int64_t npix, int C, float* __restrict__ partial) {
+                          float* __restrict__ dz_out, int64_t npix, float* __restrict__ partial) {
   pdl_trigger();
   pdl_wait();
-  const int lpp = C >> 3;
-  const int gpb = kThreads / lpp;
-  const int sub = threadIdx.x % lpp, grp = threadIdx.x / lpp;
+  constexpr int GW = 32 / LPP, kU = 8, R = (kU * GW) / 32, gpb = kThreads / LPP, C = 8 * LPP;
+  static_assert(R >= 1, "C > 64 is not instantiated");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPP, jg = lane / LPP, grp = warp * GW + jg;
   float wv[8], sc[8], sh[8], mu[8], acc[3][8] = {};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -345,23 +371,39 @@ bn_head_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, con
   float inv_n = 0.f, cA = 0.f, cB = 0.f;
   if (dlogits == nullptr) { inv_n = __ldg(fin + 3); cA = __ldg(fin + 4); cB = __ldg(fin + 5); }
   float s_dz = 0.f;
-  constexpr int kU = 8;
   const int64_t step = static_cast<int64_t>(gridDim.x) * gpb;
-  for (int64_t p0 = static_cast<int64_t>(blockIdx.x) * gpb + grp; p0 < npix; p0 += kU * step) {
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * gpb; base < npix; base += kU * step) {
     uint4 v[kU];
-    float dzv[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int64_t pix = p0 + u * step;
-      const bool ok = pix < npix;
-      v[u] = ok ? __ldg(reinterpret_cast<const uint4*>(raw + pix * ld + sub * 8)) : make_uint4(0, 0, 0, 0);
-      dzv[u] = ok ? head_dz(labels, logits, dlogits, gscale, post_sigmoid, inv_n, cA, cB, pix) : 0.f;
+      const int64_t pix = base + u * step + grp;
+      v[u] = pix < npix ? __ldg(reinterpret_cast<const uint4*>(raw + pix * ld + sub * 8)) : make_uint4(0, 0, 0, 0);
+    }
+    // the rows of the NEXT iteration go to L2 now (one lane per pixel row): with 16 warps per SM and a long compute
+    // phase per iteration the kernel was latency-bound on these loads (profiles/r02_ncu_stem_head.txt)
+    if (sub == 0) {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t pix = base + (kU + u) * step + grp;
+        if (pix < npix) prefetch_l2(raw + pix * ld);
+      }
+    }
+    float dzl[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int slot = lane + 32 * r;
+      const int64_t pix = base + (slot / GW) * step + warp * GW + slot % GW;
+      dzl[r] = 0.f;
+      if (pix < npix) {
+        dzl[r] = head_dz(labels, logits, dlogits, gscale, post_sigmoid, inv_n, cA, cB, pix);
+        dz_out[pix] = dzl[r];
+        s_dz += dzl[r];
+      }
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int64_t pix = p0 + u * step;
-      if (pix >= npix) break;
-      const float dz = dzv[u];
+      // slot u*GW + jg lives in lane (u*GW + jg) % 32 of round (u*GW) / 32; out-of-range pixels carry dz = 0, raw = 0
+      const float dz = __shfl_sync(0xffffffffu, dzl[(u * GW) / 32], (u * GW + jg) & 31);
       float f[8];
       unpack8(v[u], f);
 #pragma unroll
@@ -374,21 +416,25 @@ bn_head_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, con
         acc[1][j] += gm;
         acc[2][j] = fmaf(gm, f[j] - mu[j], acc[2][j]);
       }
-      if (sub == 0) { s_dz += dz; dz_out[pix] = dz; }
     }
   }
-  extern __shared__ float red[];  // [gpb][3C + 1]
-  const int row = 3 * C + 1;
+  extern __shared__ float red[];  // [gpb][3C] + [8 warps]
+  constexpr int row = 3 * C;
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[grp * row + k * C + sub * 8 + j] = acc[k][j];
-  if (sub == 0) red[grp * row + 3 * C] = s_dz;
+  s_dz = warp_sum(s_dz);
+  if (lane == 0) red[gpb * row + warp] = s_dz;
   __syncthreads();
-  for (int i = threadIdx.x; i < row; i += kThreads) {
+  for (int i = threadIdx.x; i <= row; i += kThreads) {
     float s = 0.f;
-    for (int g = 0; g < gpb; ++g) s += red[g * row + i];
-    partial[static_cast<size_t>(blockIdx.x) * row + i] = s;
+    if (i < row) {
+      for (int g = 0; g < gpb; ++g) s += red[g * row + i];
+    } else {
+      for (int g = 0; g < kThreads / 32; ++g) s += red[gpb * row + g];
+    }
+    partial[static_cast<size_t>(blockIdx.x) * (row + 1) + i] = s;
   }
 }
 
@@ -438,6 +484,13 @@ bn_head_bwd_apply_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, cons
       const bool ok = pix < npix;
       v[u] = ok ? __ldg(reinterpret_cast<const uint4*>(raw + pix * ld + sub * 8)) : make_uint4(0, 0, 0, 0);
       dzv[u] = ok ? __ldg(dz_in + pix) : 0.f;
+    }
+    if (sub == 0) {   // next iteration's rows -> L2
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t pix = p0 + (kU + u) * step;
+        if (pix < npix) prefetch_l2(raw + pix * ld);
+      }
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -521,10 +574,14 @@ size_t bn_head_partial_floats(int64_t npix, int C) {
 int bn_head_fwd_run(const void* raw, int64_t ld, const float* scale, const float* shift, int relu, const float* w,
                     const float* bias, const float* labels, float* logits, int post_sigmoid, int64_t npix, int C,
                     float* partial, double* sums, cudaStream_t s) {
-  UNETK_CHECK(head_c_ok(C), -1, "bn_head: C=%d must be a power of two in [8,256]", C);
+  UNETK_CHECK(bn_head_c_ok(C), -1, "bn_head: C=%d must be 32 or 64", C);
   const int grid = bn_head_grid(npix, C);
-  UNETK_CUDA(launch_pdl(bn_head_fwd_kernel, dim3(grid), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw), ld,
-                        scale, shift, relu, w, bias, labels, logits, post_sigmoid, npix, C, partial));
+  if (C == 64)
+    UNETK_CUDA(launch_pdl(bn_head_fwd_kernel<8>, dim3(grid), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw),
+                          ld, scale, shift, relu, w, bias, labels, logits, post_sigmoid, npix, partial));
+  else
+    UNETK_CUDA(launch_pdl(bn_head_fwd_kernel<4>, dim3(grid), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw),
+                          ld, scale, shift, relu, w, bias, labels, logits, post_sigmoid, npix, partial));
   UNETK_LAUNCHED();
   if (labels != nullptr) {
     UNETK_CHECK(sums != nullptr, -1, "bn_head_fwd: sums is null");
@@ -540,13 +597,18 @@ int bn_head_bwd_reduce_run(const void* raw, int64_t ld, const float* scale, cons
                            int accumulate, double* sums, int64_t npix, int C, float* partial, cudaStream_t s) {
   UNETK_CHECK(dlogits != nullptr || (labels && logits && fin), -1, "bn_head_bwd: need dlogits or (labels, logits, fin)");
   UNETK_CHECK(!post_sigmoid || logits != nullptr, -1, "bn_head_bwd: post_sigmoid needs the forward's output");
-  UNETK_CHECK(head_c_ok(C), -1, "bn_head: C=%d must be a power of two in [8,256]", C);
+  UNETK_CHECK(bn_head_c_ok(C), -1, "bn_head: C=%d must be 32 or 64", C);
   const int grid = bn_head_grid(npix, C);
   const int gpb = kThreads / (C / 8);
-  const size_t smem = static_cast<size_t>(gpb) * (3 * C + 1) * sizeof(float);
-  UNETK_CUDA(launch_pdl(bn_head_bwd_reduce_kernel, dim3(grid), dim3(kThreads), smem, s,
-                        static_cast<const __nv_bfloat16*>(raw), ld, scale, shift, mean, relu, w, labels, logits, fin,
-                        dlogits, gscale, post_sigmoid, dz, npix, C, partial));
+  const size_t smem = (static_cast<size_t>(gpb) * 3 * C + kThreads / 32) * sizeof(float);
+  if (C == 64)
+    UNETK_CUDA(launch_pdl(bn_head_bwd_reduce_kernel<8>, dim3(grid), dim3(kThreads), smem, s,
+                          static_cast<const __nv_bfloat16*>(raw), ld, scale, shift, mean, relu, w, labels, logits, fin,
+                          dlogits, gscale, post_sigmoid, dz, npix, partial));
+  else
+    UNETK_CUDA(launch_pdl(bn_head_bwd_reduce_kernel<4>, dim3(grid), dim3(kThreads), smem, s,
+                          static_cast<const __nv_bfloat16*>(raw), ld, scale, shift, mean, relu, w, labels, logits, fin,
+                          dlogits, gscale, post_sigmoid, dz, npix, partial));
   UNETK_LAUNCHED();
   UNETK_CUDA(launch_pdl(bn_head_bwd_sums_kernel, dim3((3 * C + 1 + kSum2Lanes - 1) / kSum2Lanes),
                         dim3(kSum2Lanes, kSum2Slices), 0, s, partial, grid, C, dw, db, accumulate, sums));
@@ -557,7 +619,7 @@ int bn_head_bwd_reduce_run(const void* raw, int64_t ld, const float* scale, cons
 int bn_head_bwd_apply_run(const void* raw, int64_t ld, const float* scale, const float* shift, int relu, const float* w,
                           const float* dz, const float* coef, void* draw, int64_t draw_ld, int64_t npix, int C,
                           cudaStream_t s) {
-  UNETK_CHECK(head_c_ok(C), -1, "bn_head: C=%d must be a power of two in [8,256]", C);
+  UNETK_CHECK(bn_head_c_ok(C), -1, "bn_head: C=%d must be 32 or 64", C);
   UNETK_CUDA(launch_pdl(bn_head_bwd_apply_kernel, dim3(bn_head_grid(npix, C)), dim3(kThreads), 0, s,
                         static_cast<const __nv_bfloat16*>(raw), ld, scale, shift, relu, w, dz, coef,
                         static_cast<__nv_bfloat16*>(draw), draw_ld, npix, C));

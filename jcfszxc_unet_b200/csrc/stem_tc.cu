@@ -13,9 +13,11 @@
 // a 16 x 3 x 512 x 512 batch; the output write alone (537 MB) takes 0.09 ms at HBM speed.
 // Reference semantics replaced: the first nn.Conv2d of DoubleConv / conv_block / NestedUNet.DoubleConv / ResUNet
 // input_layer + input_skip (UNet.py:21, unet_parts.py:24,85, UNetPP.py:18, ResUNet.py:23,30) and its weight gradient.
+#include "fastdiv.cuh"
 #include "host_common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include "reduce2.cuh"
 
 namespace unetk {
 
@@ -33,28 +35,50 @@ __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__floa
 struct StemTc {
   const float* x; int64_t sn, sc, sh, sw;  // fp32 image, element strides
   int N, H, W, Cin, Cout, tiles_w;
+  FastDiv fd_tw, fd_h;                     // tile -> (row, column tile), row -> (image, h) without hardware division
 };
 
-// patch of pixel (n, h, w): k = ci*9 + r*3 + s  ->  bf16(x[n, ci, h+r-1, w+s-1]) (0 outside), k >= 9*Cin -> 0
-__device__ __forceinline__ void load_patch(const StemTc& G, int n, int h, int w, bool live, uint32_t (&pk)[kK / 2]) {
+// tile -> pointer to x[n, 0, h, w] and (h, w) of this thread's pixel
+struct StemPix {
+  const float* p; int h, w, row, tw;
+};
+__device__ __forceinline__ StemPix stem_pix(const StemTc& G, int tile, int tid) {
+  uint32_t row, tw, n, h;
+  G.fd_tw.divmod(static_cast<uint32_t>(tile), row, tw);
+  G.fd_h.divmod(row, n, h);
+  StemPix q;
+  q.h = static_cast<int>(h); q.w = static_cast<int>(tw) * kTile + tid; q.row = static_cast<int>(row); q.tw = static_cast<int>(tw);
+  q.p = G.x + n * G.sn + h * G.sh + q.w * G.sw;
+  return q;
+}
+
+// patch of pixel (n, h, w): k = ci*9 + r*3 + s  ->  bf16(x[n, ci, h+r-1, w+s-1]) (0 outside), k >= 9*Cin -> 0.
+// Addresses are built from ONE pointer per pixel with +-stride steps: the first version multiplied four runtime
+// 64-bit strides per tap and spent 452 instructions on 27 loads (the kernel was issue-bound at 74 % issue-active,
+// profiles/r02_ncu_stem_head.txt).
+__device__ __forceinline__ void load_patch(const StemTc& G, const StemPix& q, uint32_t (&pk)[kK / 2]) {
   float v[kK];
 #pragma unroll
   for (int k = 0; k < kK; ++k) v[k] = 0.f;
-  if (live) {
+  if (q.w < G.W) {
+    const bool rok[3] = {q.h >= 1, true, q.h + 1 < G.H};
+    const bool cok[3] = {q.w >= 1, true, q.w + 1 < G.W};
+    const float* pc = q.p;
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) {
       if (ci < G.Cin) {
+        const float* pr = pc - G.sh;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          const int hh = h + r - 1;
-#pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int ww = w + s - 1;
-            if (hh >= 0 && hh < G.H && ww >= 0 && ww < G.W)
-              v[ci * 9 + r * 3 + s] = __ldg(G.x + n * G.sn + ci * G.sc + hh * G.sh + ww * G.sw);
+          if (rok[r]) {
+            if (cok[0]) v[ci * 9 + r * 3 + 0] = __ldg(pr - G.sw);
+            v[ci * 9 + r * 3 + 1] = __ldg(pr);
+            if (cok[2]) v[ci * 9 + r * 3 + 2] = __ldg(pr + G.sw);
           }
+          pr += G.sh;
         }
       }
+      pc += G.sc;
     }
   }
 #pragma unroll
@@ -76,10 +100,14 @@ __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) st
   uint64_t* bar = reinterpret_cast<uint64_t*>(sB + kChunks * CMAX * 16);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
   float* sStats = reinterpret_cast<float*>(bar + 8);   // [4 warps][2][CMAX]: BatchNorm sum / sum of squares (optional)
-  const int tid = threadIdx.x, warp = tid >> 5;
+  float* sBias = sStats + 4 * 2 * CMAX;                // [CMAX]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Cout = G.Cout, K = 9 * G.Cin;
   if (stats_partial != nullptr)
     for (int i = tid; i < 4 * 2 * CMAX; i += kTile) sStats[i] = 0.f;
+  const bool has_bias = bias != nullptr;
+  if (has_bias)
+    for (int i = tid; i < CMAX; i += kTile) sBias[i] = i < Cout ? __ldg(bias + i) : 0.f;
 
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc<CMAX>(slot);
@@ -105,23 +133,27 @@ __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) st
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((static_cast<uint32_t>(Cout) >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t lbo_a = kTile * 16, lbo_b = static_cast<uint32_t>(Cout) * 16;
   uint32_t parity = 0;
+  // loop-invariant pieces of the epilogue addressing (32-bit shared addresses, one 64-bit output pointer per tile)
+  const uint32_t sA_u = smem_u32(sA), wbuf_u = sA_u + warp * 4096, sBias_u = smem_u32(sBias);
+  const int piece = lane & 7, rsub = lane >> 3;                       // store phase: 16-byte piece / row within a group of 4
+  const int64_t lane_off = rsub * y_ld + piece * 8, step4 = 4 * y_ld;
+  uint32_t ld_off[8];                                                 // staged row i*4 + rsub, swizzled piece
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ld_off[i] = (i * 4 + rsub) * 128 + ((piece ^ ((i * 4 + rsub) & 7)) << 4);
+  uint32_t st_off[8];                                                 // statistics: row 8k' + k, this lane's channel pair
+#pragma unroll
+  for (int k = 0; k < 8; ++k) st_off[k] = k * 128 + (((lane >> 2) ^ k) << 4) + (lane & 3) * 4;
 
   // software pipeline: the patch of the NEXT tile is fetched (27 global loads per thread) while this tile's MMAs
   // and output stores are in flight
   uint32_t pk[kK / 2];
-  if (blockIdx.x < num_tiles) {
-    const int row0 = blockIdx.x / G.tiles_w;
-    load_patch(G, row0 / G.H, row0 % G.H, (blockIdx.x % G.tiles_w) * kTile + tid,
-               (blockIdx.x % G.tiles_w) * kTile + tid < G.W, pk);
-  }
+  StemPix cur = stem_pix(G, blockIdx.x < num_tiles ? blockIdx.x : 0, tid);
+  if (blockIdx.x < num_tiles) load_patch(G, cur, pk);
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int tw = tile % G.tiles_w;
-    const int row = tile / G.tiles_w;          // n * H + h
-    const int w = tw * kTile + tid;
-    const bool live = w < G.W;
+    const int tw = cur.tw, row = cur.row;
 #pragma unroll
     for (int c = 0; c < kChunks; ++c)
-      *reinterpret_cast<uint4*>(sA + (c * kTile + tid) * 16) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      sts128(sA_u + (c * kTile + tid) * 16, make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
     fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
     tc_fence_before();
     __syncthreads();
@@ -129,7 +161,7 @@ __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) st
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < kK / 16; ++ks) {
-        const uint64_t da = make_smem_desc(smem_u32(sA) + ks * 2 * lbo_a, lbo_a, 128, kLayoutNone);
+        const uint64_t da = make_smem_desc(sA_u + ks * 2 * lbo_a, lbo_a, 128, kLayoutNone);
         const uint64_t db = make_smem_desc(smem_u32(sB) + ks * 2 * lbo_b, lbo_b, 128, kLayoutNone);
         umma_bf16(tmem, da, db, idesc, ks != 0);
       }
@@ -138,8 +170,8 @@ __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) st
     {
       const int nt = tile + gridDim.x;
       if (nt < num_tiles) {
-        const int nrow = nt / G.tiles_w, nw = (nt % G.tiles_w) * kTile + tid;
-        load_patch(G, nrow / G.H, nrow % G.H, nw, nw < G.W, pk);
+        cur = stem_pix(G, nt, tid);
+        load_patch(G, cur, pk);
       }
     }
     mbar_wait(bar, parity);
@@ -148,12 +180,12 @@ __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) st
     // epilogue: thread = pixel = TMEM lane; Cout fp32 columns -> +bias -> bf16.  64-channel groups are transposed
     // through shared memory (the A tile's region is free once its MMAs retired) so that a warp store instruction
     // covers four whole 128-byte pixel rows instead of 16 bytes of 32 different rows (32x fewer LSU wavefronts).
-    __nv_bfloat16* o = y + (static_cast<int64_t>(row) * G.W + w) * y_ld;
+    const int w0 = tw * kTile + warp * 32;                    // first pixel column of this warp's 32 rows
+    const int rows = min(32, G.W - w0);                       // live rows (<= 0: the warp is past the image edge)
+    __nv_bfloat16* const orow = y + (static_cast<int64_t>(row) * G.W + w0) * y_ld;
     const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    const int lane = tid & 31;
     for (int c0 = 0; c0 < Cout; c0 += 64) {
       const bool full64 = c0 + 64 <= Cout;
-      uint8_t* wbuf = sA + warp * 4096;                     // this warp's 32 rows x 128 B
       if (full64) __syncwarp();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -166,37 +198,40 @@ __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) st
           const int cb = c0 + half * 32 + v * 8;
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]) + ((bias && cb + j < Cout) ? __ldg(bias + cb + j) : 0.f);
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]);
+          if (has_bias) {
+            const float4 b0 = lds128_f(sBias_u + cb * 4), b1 = lds128_f(sBias_u + cb * 4 + 16);
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
           uint4 u;
           u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
-          if (full64) *reinterpret_cast<uint4*>(wbuf + lane * 128 + (((half * 4 + v) ^ (lane & 7)) << 4)) = u;
-          else if (live && cb < Cout) *reinterpret_cast<uint4*>(o + cb) = u;
+          if (full64) sts128(wbuf_u + lane * 128 + (((half * 4 + v) ^ (lane & 7)) << 4), u);
+          else if (lane < rows && cb < Cout) *reinterpret_cast<uint4*>(orow + lane * y_ld + cb) = u;
         }
       }
       if (full64) {
         __syncwarp();
-        const int piece = lane & 7;
+        __nv_bfloat16* o = orow + lane_off + c0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + (lane >> 3);                 // row inside the warp's 32
-          const int ww = tw * kTile + warp * 32 + rr;
-          if (ww < G.W) {
-            const uint4 val = *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((piece ^ (rr & 7)) << 4));
-            *reinterpret_cast<uint4*>(y + (static_cast<int64_t>(row) * G.W + ww) * y_ld + c0 + piece * 8) = val;
-          }
+          if (i * 4 + rsub < rows) *reinterpret_cast<uint4*>(o) = lds128(wbuf_u + ld_off[i]);
+          o += step4;
         }
         if (stats_partial != nullptr) {
           // BatchNorm statistics of the bf16 values just stored: lane owns channels c0 + 2*lane, +1 and sums them
-          // over the warp's 32 staged rows (one 4-byte word per row: conflict-free), then adds into its own slot
+          // over the warp's staged rows (one 4-byte word per row: conflict-free), then adds into its own slot
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          const int pc = lane >> 2, off = (lane & 3) * 4;
-          const int rows = min(32, G.W - (tw * kTile + warp * 32));
-#pragma unroll 8
-          for (int rr = 0; rr < rows; ++rr) {
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(wbuf + rr * 128 + ((pc ^ (rr & 7)) << 4) + off);
-            const float a = bf16_lo(v), b = bf16_hi(v);
-            s0 += a; q0 = fmaf(a, a, q0);
-            s1 += b; q1 = fmaf(b, b, q1);
+          for (int r8 = 0; r8 < rows; r8 += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (r8 + k < rows) {
+                const uint32_t v = lds_u32(wbuf_u + r8 * 128 + st_off[k]);
+                const float a = bf16_lo(v), b = bf16_hi(v);
+                s0 += a; q0 = fmaf(a, a, q0);
+                s1 += b; q1 = fmaf(b, b, q1);
+              }
+            }
           }
           float* st = sStats + warp * 2 * CMAX + c0 + 2 * lane;
           st[0] += s0; st[1] += s1; st[CMAX] += q0; st[CMAX + 1] += q1;
@@ -229,7 +264,7 @@ int stem_tc_fwd_grid(int tiles, int CMAX) {
 template <int CMAX>
 int stem_tc_fwd_launch(const StemTc& G, const float* w, const float* bias, void* y, int64_t y_ld, int tiles, cudaStream_t s,
                        float* stats_partial = nullptr, double* stats_sums = nullptr) {
-  const int smem = kTile * 128 + kChunks * CMAX * 16 + 64 + 128 + 4 * 2 * CMAX * 4;
+  const int smem = kTile * 128 + kChunks * CMAX * 16 + 64 + 128 + 4 * 2 * CMAX * 4 + CMAX * 4;
   // CTAs per SM: bounded by TMEM (512 / CMAX columns); one CTA builds its patch tile while the others' MMAs /
   // stores run
   const int grid = stem_tc_fwd_grid(tiles, CMAX);
@@ -283,17 +318,15 @@ __global__ void __launch_bounds__(kTile) stem_tc_wgrad_kernel(const __grid_const
   uint32_t parity = 0;
   bool first = true;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int tw = tile % G.tiles_w;
-    const int row = tile / G.tiles_w;          // n * H + h
-    const int n = row / G.H, h = row % G.H;
-    const int w = tw * kTile + tid;
+    const StemPix cur = stem_pix(G, tile, tid);
+    const int tw = cur.tw, row = cur.row;
     if (tid == 0) {
       mbar_expect_tx(&bars[0], 2 * kBox);
       tma_load_3d(sA, &P.tmDy, &bars[0], 0, tw * kTile, row);
       tma_load_3d(sA + kBox, &P.tmDy, &bars[0], 64, tw * kTile, row);
     }
     uint32_t pk[kK / 2];
-    load_patch(G, n, h, w, w < G.W, pk);
+    load_patch(G, cur, pk);
     uint8_t* rowp = sB + tid * 128;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -345,15 +378,16 @@ __global__ void __launch_bounds__(kTile) stem_tc_wgrad_kernel(const __grid_const
   }
 }
 
+// 32 x 32 threads: 32 outputs per block, the CTA partials summed in 32 slices and then in a fixed order (the first
+// version walked up to 592 partials per thread: 47 us, profiles/r02_ncu_stem_head.txt)
 __global__ void stem_tc_wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ dw,
                                             int accumulate) {
   pdl_trigger();
   pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += partial[static_cast<size_t>(b) * n + i];   // fixed order: deterministic
-  dw[i] = accumulate ? dw[i] + static_cast<float>(s) : static_cast<float>(s);
+  const int i = blockIdx.x * kSum2Lanes + threadIdx.x;
+  const bool valid = i < n;
+  const double s = sliced_ordered_sum(partial, nblk, valid, [&](int b) { return static_cast<size_t>(b) * n + i; });
+  if (valid && threadIdx.y == 0) dw[i] = accumulate ? dw[i] + static_cast<float>(s) : static_cast<float>(s);
 }
 
 int stem_tc_wgrad_grid(int64_t tiles) {
@@ -378,7 +412,8 @@ int stem_tc_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t 
                     double* stats_sums) {
   UNETK_CHECK(stem_tc_ok(Cin, Cout), -1, "stem_tc: Cin=%d Cout=%d not supported", Cin, Cout);
   UNETK_CHECK(y_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, -1, "stem_tc: output must be 16-byte aligned");
-  StemTc G{x, sn, sc, sh, sw, N, H, W, Cin, Cout, (W + kTile - 1) / kTile};
+  StemTc G{x, sn, sc, sh, sw, N, H, W, Cin, Cout, (W + kTile - 1) / kTile,
+           FastDiv(static_cast<uint32_t>((W + kTile - 1) / kTile)), FastDiv(static_cast<uint32_t>(H))};
   const int64_t tiles64 = static_cast<int64_t>(N) * H * G.tiles_w;
   UNETK_CHECK(tiles64 < (1ll << 31), -1, "stem_tc: too many tiles");
   const int tiles = static_cast<int>(tiles64);
@@ -401,7 +436,8 @@ int stem_tc_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_
   UNETK_CHECK(ws != nullptr && ws_bytes >= stem_tc_wgrad_workspace(N, H, W, Cin, Cout), -1, "stem_tc_wgrad: workspace too small");
   UNETK_CHECK(dy_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, -1, "stem_tc_wgrad: dy must be 16-byte aligned");
   StemTcW P{};
-  P.G = StemTc{x, sn, sc, sh, sw, N, H, W, Cin, Cout, (W + kTile - 1) / kTile};
+  P.G = StemTc{x, sn, sc, sh, sw, N, H, W, Cin, Cout, (W + kTile - 1) / kTile,
+               FastDiv(static_cast<uint32_t>((W + kTile - 1) / kTile)), FastDiv(static_cast<uint32_t>(H))};
   const int64_t tiles64 = static_cast<int64_t>(N) * H * P.G.tiles_w;
   UNETK_CHECK(tiles64 < (1ll << 31), -1, "stem_tc_wgrad: too many tiles");
   {
@@ -421,7 +457,8 @@ int stem_tc_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_
   UNETK_CUDA(launch_pdl(stem_tc_wgrad_kernel, dim3(grid), dim3(kTile), smem, s, P, static_cast<float*>(ws), static_cast<int>(tiles64)));
   UNETK_LAUNCHED();
   const int n = Cout * 9 * Cin;
-  UNETK_CUDA(launch_pdl(stem_tc_wgrad_reduce_kernel, dim3((n + 127) / 128), dim3(128), 0, s, static_cast<const float*>(ws), grid, n, dw, accumulate));
+  UNETK_CUDA(launch_pdl(stem_tc_wgrad_reduce_kernel, dim3((n + kSum2Lanes - 1) / kSum2Lanes), dim3(kSum2Lanes, kSum2Slices), 0, s,
+                        static_cast<const float*>(ws), grid, n, dw, accumulate));
   UNETK_LAUNCHED();
   return 0;
 }

@@ -575,7 +575,7 @@ class Head:
         plan.need(_lib.load().unetk_head_partial_floats(self.npix, self.C), 0, self.C)
         self.prod = None
         if (fuse is not None and os.environ.get("UNETK_FUSE_HEAD", "1") != "0" and fuse.out is x and fuse.bn is not None
-                and fuse.res is None and fuse.pooled is None and self.C in (8, 16, 32, 64, 128, 256)):
+                and fuse.res is None and fuse.pooled is None and self.C in (32, 64)):
             self.prod = fuse
             fuse.head_fused = True
             plan.need(_lib.load().unetk_bn_head_partial_floats(self.npix, self.C), 0, self.C)
