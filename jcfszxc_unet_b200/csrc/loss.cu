@@ -289,7 +289,7 @@ bn_head_fwd_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, const floa
       v[u] = pix < npix ? __ldg(reinterpret_cast<const uint4*>(raw + pix * ld + sub * 8)) : make_uint4(0, 0, 0, 0);
     }
     // the rows of the NEXT iteration go to L2 now (one lane per pixel row): with 16 warps per SM and a long compute
-    // phase per iteration the kernel was latency-bound on these loads (profiles/r02_ncu_stem_head.txt)
+    // phase per iteration the kernel was latency-bound on these loads (profiles/r01_ncu_stem_head.txt)
     if (sub == 0) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
@@ -380,7 +380,7 @@ bn_head_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ raw, int64_t ld, con
       v[u] = pix < npix ? __ldg(reinterpret_cast<const uint4*>(raw + pix * ld + sub * 8)) : make_uint4(0, 0, 0, 0);
     }
     // the rows of the NEXT iteration go to L2 now (one lane per pixel row): with 16 warps per SM and a long compute
-    // phase per iteration the kernel was latency-bound on these loads (profiles/r02_ncu_stem_head.txt)
+    // phase per iteration the kernel was latency-bound on these loads (profiles/r01_ncu_stem_head.txt)
     if (sub == 0) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {

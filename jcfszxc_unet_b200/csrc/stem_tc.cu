@@ -55,7 +55,7 @@ __device__ __forceinline__ StemPix stem_pix(const StemTc& G, int tile, int tid) 
 // patch of pixel (n, h, w): k = ci*9 + r*3 + s  ->  bf16(x[n, ci, h+r-1, w+s-1]) (0 outside), k >= 9*Cin -> 0.
 // Addresses are built from ONE pointer per pixel with +-stride steps: the first version multiplied four runtime
 // 64-bit strides per tap and spent 452 instructions on 27 loads (the kernel was issue-bound at 74 % issue-active,
-// profiles/r02_ncu_stem_head.txt).
+// profiles/r01_ncu_stem_head.txt).
 __device__ __forceinline__ void load_patch(const StemTc& G, const StemPix& q, uint32_t (&pk)[kK / 2]) {
   float v[kK];
 #pragma unroll
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kTile) stem_tc_wgrad_kernel(const __grid_const
 }
 
 // 32 x 32 threads: 32 outputs per block, the CTA partials summed in 32 slices and then in a fixed order (the first
-// version walked up to 592 partials per thread: 47 us, profiles/r02_ncu_stem_head.txt)
+// version walked up to 592 partials per thread: 47 us, profiles/r01_ncu_stem_head.txt)
 __global__ void stem_tc_wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ dw,
                                             int accumulate) {
   pdl_trigger();

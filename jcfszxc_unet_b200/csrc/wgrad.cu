@@ -5,6 +5,7 @@
 // Split over pixel ranges (deterministic: fp32 partials + ordered reduce in wgrad_reduce_kernel).
 // Reference semantics replaced: autograd's weight gradient of nn.Conv2d(k=3,p=1 / k=1) and
 // nn.ConvTranspose2d(k=2,s=2) (UNetFamily/utils/unet_parts.py:24-31,56-58 in the reference).
+#include <cstdlib>
 #include "fastdiv.cuh"
 #include "host_common.cuh"
 #include "ptx.cuh"
@@ -212,6 +213,61 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
+// Few splits over a large filter (ksplit < 8): a 32 x 8 block owns a 32 (m) x 32 (n) tile of the filter for ALL taps.
+// Reads: 4 rows x TAPS independent 128-byte-per-warp loads per split and thread (the one-thread-per-(m, n) kernel above
+// had at most TAPS four-byte loads in flight and wrote every tap 36 B from its neighbour's: 1.1 TB/s on the
+// 1024 x 1024 x 9 filter, profiles/r01_ncu_launch_shares_v9.txt).  Writes: the tile goes through shared memory and
+// leaves in the order of dw's own contiguity — runs of 32*TAPS floats along n (sn < sm: conv weights
+// [Cout][Cin][kh][kw]) or along m (swapped operands / ConvTranspose2d [Cin][Cout][2][2]).  Same summation order over
+// the splits as wgrad_reduce_kernel: bit-identical results.
+template <int TAPS>
+__global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                                 int ksplit, int M, int Nn, int64_t sm, int64_t sn,
+                                                                 int64_t st, int accumulate) {
+  __shared__ float tile[32][32 * TAPS + 1];
+  pdl_trigger();
+  pdl_wait();
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int n0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const size_t plane = static_cast<size_t>(M) * Nn;
+  float acc[4][TAPS];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) acc[i][t] = 0.f;
+  const bool n_ok = n0 + tx < Nn;
+  for (int k = 0; k < ksplit; ++k) {
+    const float* pk = partial + static_cast<size_t>(k) * TAPS * plane + n0 + tx;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty + 8 * i;
+      if (n_ok && m < M) {
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) acc[i][t] += __ldg(pk + t * plane + static_cast<size_t>(m) * Nn);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) tile[ty + 8 * i][tx * TAPS + t] = acc[i][t];
+  __syncthreads();
+  const bool along_n = (sn < 0 ? -sn : sn) <= (sm < 0 ? -sm : sm);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int outer = ty + 8 * i;                     // m (runs along n) or n (runs along m)
+    for (int idx = tx; idx < 32 * TAPS; idx += 32) {
+      const int inner = idx / TAPS, t = idx - inner * TAPS;
+      const int m = along_n ? outer : inner, n = along_n ? inner : outer;
+      if (m0 + m < M && n0 + n < Nn) {
+        float* o = dw + (m0 + m) * sm + (n0 + n) * sn + t * st;
+        const float v = tile[m][n * TAPS + t];
+        *o = accumulate ? (*o + v) : v;
+      }
+    }
+  }
+}
+
 // Many pixel splits over a small filter (the 64-channel layers: 98 splits of a 64 x 64 x 9 filter): a 32 x 32 block
 // owns 32 (m, n) positions of one tap, slice y adds the splits y, y+32, ... and row 0 adds the 32 slice sums in order.
 template <int S>   // S slices of the split axis per block (8, 16 or 32)
@@ -292,6 +348,16 @@ int wgrad_reduce_launch(const float* partial, float* dw, int ksplit, int taps, i
       UNETK_CUDA(launch_pdl(wgrad_reduce_sliced_kernel<16>, grid, dim3(32, 16), 0, stream, partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd));
     else
       UNETK_CUDA(launch_pdl(wgrad_reduce_sliced_kernel<8>, grid, dim3(32, 8), 0, stream, partial, dw, ksplit, taps, M, Nn, sm, sn, st, accumulate, fd));
+    UNETK_LAUNCHED();
+    return 0;
+  }
+  static int tiled = -1;
+  if (tiled < 0) { const char* e = getenv("UNETK_WGRAD_REDUCE_TILED"); tiled = e ? atoi(e) : 1; }
+  if (tiled && (taps == 9 || taps == 4 || taps == 1)) {
+    const dim3 grid(static_cast<unsigned>((Nn + 31) / 32), static_cast<unsigned>((M + 31) / 32));
+    if (taps == 9) UNETK_CUDA(launch_pdl(wgrad_reduce_tiled_kernel<9>, grid, dim3(32, 8), 0, stream, partial, dw, ksplit, M, Nn, sm, sn, st, accumulate));
+    else if (taps == 4) UNETK_CUDA(launch_pdl(wgrad_reduce_tiled_kernel<4>, grid, dim3(32, 8), 0, stream, partial, dw, ksplit, M, Nn, sm, sn, st, accumulate));
+    else UNETK_CUDA(launch_pdl(wgrad_reduce_tiled_kernel<1>, grid, dim3(32, 8), 0, stream, partial, dw, ksplit, M, Nn, sm, sn, st, accumulate));
     UNETK_LAUNCHED();
     return 0;
   }

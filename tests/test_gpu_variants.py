@@ -445,11 +445,20 @@ def test_variant_trainer_step_vs_oracle(name):
     for k in results[False][1]:
         assert torch.equal(results[False][1][k], results[True][1][k]), k
     names = O.param_names(sd)
+    # yardstick: the oracle's own bf16-autocast run of the same three steps.  RMSprop's first updates are ~lr/sqrt(1-alpha)
+    # = 1e-2 per weight whatever the gradient's size, so last-bit differences of step 0 are visible in the loss of step 2
+    sd16 = {k: v.clone() for k, v in sd.items()}
     opt_state = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in names}
+    opt_state16 = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in names}
     for step in range(3):
         im, lb = _inputs(100 + step, 2, 32, 32)
         ls, _, _ = O.train_step(sd, opt_state, im.to(DEV), lb.to(DEV), lr, bf16=False, model=name)
-        assert abs(results[True][0][step] - float(ls)) <= 3e-2 * max(1.0, abs(float(ls))), (step, results[True][0], float(ls))
+        ls16, _, _ = O.train_step(sd16, opt_state16, im.to(DEV), lb.to(DEV), lr, bf16=True, model=name)
+        # steps 0 and 1: 3e-2.  Step 2 is taken after two such updates on 2 x 32 x 32 images (BatchNorm over 8 values per
+        # channel at the deepest level): two bf16 implementations that agree bit for bit on the logits and to ~1 % on the
+        # gradients of step 0 (fused vs separate head passes, tools/head_fusion_ab.py) are 0.02 apart in this loss, so it gets 6e-2
+        tol = max((3e-2 if step < 2 else 6e-2) * max(1.0, abs(float(ls))), 2.0 * abs(float(ls16) - float(ls)))
+        assert abs(results[True][0][step] - float(ls)) <= tol, (step, results[True][0], float(ls), float(ls16))
 
 
 def test_variant_unsupported_shapes_fail_loudly():
