@@ -188,7 +188,7 @@ def run_reference_arm(args):
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     return 0
 
 
@@ -392,13 +392,26 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "loss": loss_final, "loss_e2e": loss_host,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_OUT = sys.stdout
+
+
+def _only_json_on_stdout():
+    """The contract is ONE JSON line on stdout: native libraries print there too (NCCL's version banner when the box
+    sets NCCL_DEBUG), so fd 1 is pointed at stderr for the run and the line goes to a duplicate of the real stdout."""
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    _only_json_on_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
