@@ -463,7 +463,7 @@ int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream) {
   }
   {
     uint64_t dims[3] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.ncols), static_cast<uint64_t>(d.b_taps)};
-    uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * d.ncols};
+    uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * (d.b_rows ? d.b_rows : d.ncols)};
     uint32_t box[3] = {64, static_cast<uint32_t>(BN), 1};
     uint32_t es[3] = {1, 1, 1};
     if (int rc = make_tmap_bf16(&p.tmB, d.b, 3, dims, strides, box, es, true)) return rc;

@@ -419,6 +419,14 @@ int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream);
 bool conv3x3_rows_eligible(const ConvGemmDesc& d);
 int conv3x3_rows_run(const ConvGemmDesc& d, cudaStream_t stream);
 
+// see conv_gemm_run; UNETK_SPLIT_WIDE=0 disables, the value is the largest K that is split (default 64)
+static bool split_wide_thin(const ConvGemmDesc& d) {
+  static int kmax = -1;
+  if (kmax < 0) { const char* e = getenv("UNETK_SPLIT_WIDE"); kmax = e ? atoi(e) : 64; }
+  return kmax > 0 && d.taps == 9 && d.a_step == 1 && d.out_step == 1 && d.q_groups == 1 && !d.out_f32 &&
+         d.stats_partial == nullptr && d.W >= 128 && d.H >= 2 && d.ncols > 128 && d.K <= kmax;
+}
+
 size_t conv_gemm_stats_partial_floats(int ncols) {
   return static_cast<size_t>(num_sms()) * 2 * pick_bn(ncols, 1);
 }
@@ -438,6 +446,22 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
     UNETK_CHECK(!d.accumulate && d.stats_sums == nullptr, -1, "conv_gemm: the fp32 output path neither accumulates nor takes statistics");
     UNETK_CHECK(d.out_ld % 4 == 0 && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0), -1,
                 "conv_gemm: fp32 output needs out_ld %% 4 == 0 and a 16-byte aligned bias");
+  } else if (split_wide_thin(d)) {
+    // Wide output, thin reduction (the dgrad of UNet++'s concat-fed convs: 32 -> 160 / 192 channels at full
+    // resolution): the generic kernel re-streams 9 x BN x 64 weights through the pipeline for every 128-pixel tile
+    // and ran at 310-460 TFLOP/s; column slices of <= 128 channels take the halo / row-stacked kernels with their
+    // weights resident in shared memory.  The slices re-read the (thin) input, nothing else changes.
+    const int total = d.b_rows ? d.b_rows : d.ncols;
+    for (int c0 = 0; c0 < d.ncols; c0 += 128) {
+      ConvGemmDesc s = d;
+      s.ncols = d.ncols - c0 < 128 ? d.ncols - c0 : 128;
+      s.b_rows = total;
+      s.b = static_cast<const __nv_bfloat16*>(d.b) + static_cast<size_t>(c0) * d.K;
+      s.out = static_cast<__nv_bfloat16*>(d.out) + c0;
+      s.bias = d.bias ? d.bias + c0 : nullptr;
+      if (int rc = conv_gemm_run(s, stream)) return rc;
+    }
+    return 0;
   } else if (conv3x3_rows_eligible(d)) {
     return conv3x3_rows_run(d, stream);  // wide images, <= 64 output channels: filter rows stacked in N
   } else if (conv3x3_halo_eligible(d)) {
@@ -503,7 +527,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   {
     const uint64_t rows = static_cast<uint64_t>(d.ncols) * d.q_groups;
     uint64_t dims[3] = {static_cast<uint64_t>(d.K), rows, static_cast<uint64_t>(d.b_taps)};
-    uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * rows};
+    uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * (d.b_rows ? static_cast<uint64_t>(d.b_rows) : rows)};
     uint32_t box[3] = {kTileK, static_cast<uint32_t>(BN), 1};
     uint32_t es[3] = {1, 1, 1};
     if (int rc = make_tmap_bf16(&p.tmB, d.b, 3, dims, strides, box, es, true)) return rc;

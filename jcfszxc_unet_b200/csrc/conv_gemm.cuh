@@ -17,6 +17,7 @@ struct ConvGemmDesc {
   int64_t a_ld;
   const void* b;      // bf16 packed weights [b_taps][q_groups*ncols][K]
   int b_taps;
+  int b_rows;         // rows between two taps of `b` (0 = q_groups*ncols): > ncols when `b` is a row slice of a wider pack
   void* out;          // bf16 NHWC, spatial (H*out_step, W*out_step), pixel stride out_ld
   int64_t out_ld;
   const float* bias;  // fp32 [ncols] or null

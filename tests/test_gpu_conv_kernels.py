@@ -72,6 +72,12 @@ CONV_SHAPES = [
     (1, 24, 40, 192, 32, (0, 0), (0, 0)),      # UNet++ 192 -> 32 (its dgrad is 32 -> 192: N = 192, two 16-channel steps)
     (2, 12, 20, 160, 48, (32, 0), (0, 16)),    # 160 = 2.5 chunks; dgrad: N = 160 in a 192 tile, K = 48 (three steps)
     (1, 16, 16, 32, 176, (0, 0), (0, 0)),      # forward with N = 176 (masked tail of the 192 tile), K = 32
+    # W >= 128, > 128 output channels, K <= 64 (the dgrad of UNet++'s concat-fed convs): column slices of <= 128 channels
+    # through the halo / row-stacked kernels (conv_gemm_run, split_wide_thin)
+    (1, 6, 128, 160, 32, (0, 0), (0, 0)),      # dgrad 32 -> 160 = 128 + 32
+    (2, 4, 256, 192, 32, (32, 0), (0, 32)),    # dgrad 32 -> 192 = 128 + 64 into a sliced gradient buffer
+    (1, 5, 140, 320, 64, (0, 0), (0, 0)),      # dgrad 64 -> 320 = 128 + 128 + 64, ragged W
+    (1, 4, 128, 32, 176, (0, 0), (0, 16)),     # forward 32 -> 176 = 128 + 48 (no fused statistics)
 ]
 
 
