@@ -7,6 +7,8 @@
 //   torch.cat copies  NestedUNet dense skips                                    UNetPP.py:75-99
 //   nn.Upsample(scale_factor=2)  (nearest)  up_conv                             unet_parts.py:103
 //   nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)            UNetPP.py:44
+#include <cstdlib>
+#include "fastdiv.cuh"
 #include "host_common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -219,6 +221,83 @@ bilinear2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, __nv_bf
   }
 }
 
+// ---- 2 x 2 output block per thread.  With scale = (in-1)/(2in-1) < 1/2 the source pair of output 2k is (k-1, k) and
+// that of 2k+1 is (k, k+1) (clamped at the borders), so the four outputs (2k..2k+1, 2m..2m+1) read only the 3 x 3
+// inputs around (k, m): 9 loads and 72 bf16->fp32 conversions for four results instead of 16 and 128, one index
+// computation per block.  The per-pixel kernel above spent ~150 instructions per output and was issue-bound at
+// 2.5 TB/s (UNet++: 1.7 ms per step for ten tensors).  The weights still come from src_index (ATen's arithmetic) and
+// are attached to the loaded rows by comparing indices, so the borders (and H or W == 1) need no special case; in the
+// interior the expression is the per-pixel kernel's, lh0*(lw0*a + lw1*b) + lh1*(lw0*c + lw1*d).
+struct Pair3 {   // weights of the three loaded rows (or columns) k-1, k, k+1 for the even and the odd output
+  float e0, e1, o1, o2;
+};
+__device__ __forceinline__ Pair3 pair_weights(float scale, int k, int in) {
+  int i0, i1;
+  float l0, l1;
+  const int r0 = k > 0 ? k - 1 : 0, r1 = k, r2 = k + 1 < in ? k + 1 : in - 1;   // loaded (clamped) indices
+  Pair3 w;
+  src_index(scale, 2 * k, in, &i0, &i1, &l0, &l1);        // even output: rows r0, r1
+  w.e0 = (r0 == i0 ? l0 : 0.f) + (r0 == i1 ? l1 : 0.f);
+  w.e1 = (r1 != r0) ? (r1 == i0 ? l0 : 0.f) + (r1 == i1 ? l1 : 0.f) : 0.f;
+  src_index(scale, 2 * k + 1, in, &i0, &i1, &l0, &l1);    // odd output: rows r1, r2
+  w.o1 = (r1 == i0 ? l0 : 0.f) + (r1 == i1 ? l1 : 0.f);
+  w.o2 = (r2 != r1) ? (r2 == i0 ? l0 : 0.f) + (r2 == i1 ? l1 : 0.f) : 0.f;
+  return w;
+}
+
+__global__ void __launch_bounds__(kThreads)
+bilinear2x_fwd_block_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, __nv_bfloat16* __restrict__ y,
+                            int64_t y_ld, int N, int H, int W, int C, float sh, float sw, FastDiv fd_w, FastDiv fd_h) {
+  pdl_trigger();
+  pdl_wait();
+  Lanes L(C);
+  if (!L.active) return;
+  const int64_t units = static_cast<int64_t>(N) * H * W;     // one per input pixel = per 2 x 2 output block
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+  const int Wo = 2 * W;
+  for (int64_t u = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl; u < units; u += stride) {
+    uint32_t t, m, n, k;
+    fd_w.divmod(static_cast<uint32_t>(u), t, m);
+    fd_h.divmod(t, n, k);
+    const Pair3 wr = pair_weights(sh, static_cast<int>(k), H), wc = pair_weights(sw, static_cast<int>(m), W);
+    const int dk0 = k > 0 ? -1 : 0, dk2 = static_cast<int>(k) + 1 < H ? 1 : 0;
+    const int dm0 = m > 0 ? -1 : 0, dm2 = static_cast<int>(m) + 1 < W ? 1 : 0;
+    const __nv_bfloat16* p = x + u * x_ld + L.g * 8;          // input pixel (n, k, m)
+    const int64_t rs = static_cast<int64_t>(W) * x_ld;
+    uint4 v[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const __nv_bfloat16* pr = p + (j == 0 ? dk0 : (j == 2 ? dk2 : 0)) * rs;
+      v[j][0] = ldg16(pr + dm0 * x_ld);
+      v[j][1] = ldg16(pr);
+      v[j][2] = ldg16(pr + dm2 * x_ld);
+    }
+    float hx[3][2][8];                                        // row j, output column parity, channel
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float a[8], b[8], c[8];
+      unpack8(v[j][0], a); unpack8(v[j][1], b); unpack8(v[j][2], c);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        hx[j][0][q] = wc.e0 * a[q] + wc.e1 * b[q];
+        hx[j][1][q] = wc.o1 * b[q] + wc.o2 * c[q];
+      }
+    }
+    __nv_bfloat16* o = y + ((static_cast<int64_t>(n) * 2 * H + 2 * k) * Wo + 2 * m) * y_ld + L.g * 8;
+#pragma unroll
+    for (int oc = 0; oc < 2; ++oc) {
+      float e[8], od[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        e[q] = wr.e0 * hx[0][oc][q] + wr.e1 * hx[1][oc][q];
+        od[q] = wr.o1 * hx[1][oc][q] + wr.o2 * hx[2][oc][q];
+      }
+      stg16(o + oc * y_ld, pack8(e));
+      stg16(o + (static_cast<int64_t>(Wo) + oc) * y_ld, pack8(od));
+    }
+  }
+}
+
 // Gather form of the backward: input pixel i receives from every output o whose (i0, i1) pair contains i.
 // With scale = (in-1)/(2in-1) < 1/2 those outputs lie in [2i-2, 2i+3]; at most four of them really touch i.
 // The (output index, weight) lists of a row and of a column are built once per input pixel, so the inner
@@ -296,6 +375,99 @@ bilinear2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_ld, __nv_
   }
 }
 
+// ---- 2 x 2 INPUT block per thread: inputs (k..k+1, m..m+1) receive from the 6 x 6 outputs (2k-1..2k+4, 2m-1..2m+4);
+// input k takes rows 2k-1..2k+2 (positions 0..3 of the six), input k+1 rows 2k+1..2k+4 (positions 2..5).  Each output
+// row is reduced along W first (two 4-term sums), then added to the one or two input rows it feeds: 36 loads and
+// ~580 FMAs for four results against 64 loads and ~600 FMAs + four tap-list constructions in the per-pixel kernel
+// (2.6 ms per UNet++ step, issue-bound at 1.6 TB/s).  Weights from src_index, attached by comparing indices.
+struct Six {
+  float lo[4], hi[4];   // weight of output position j (lo) / j + 2 (hi) for the block's first / second input
+};
+__device__ __forceinline__ Six six_weights(float scale, int k, int in) {
+  Six w;
+  const int out = 2 * in;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int o = 2 * k - 1 + j;
+    float a = 0.f, b = 0.f;
+    if (o >= 0 && o < out) {
+      int i0, i1;
+      float l0, l1;
+      src_index(scale, o, in, &i0, &i1, &l0, &l1);
+      a = (i0 == k ? l0 : 0.f) + (i1 == k ? l1 : 0.f);
+      b = (i0 == k + 1 ? l0 : 0.f) + (i1 == k + 1 ? l1 : 0.f);
+    }
+    if (j < 4) w.lo[j] = a;
+    if (j >= 2) w.hi[j - 2] = b;
+  }
+  return w;
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(kThreads)
+bilinear2x_bwd_block_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_ld, __nv_bfloat16* __restrict__ dx,
+                            int64_t dx_ld, int N, int H, int W, int C, float sh, float sw, FastDiv fd_wb, FastDiv fd_hb) {
+  pdl_trigger();
+  pdl_wait();
+  Lanes L(C);
+  if (!L.active) return;
+  const int Hb = (H + 1) >> 1, Wb = (W + 1) >> 1, Ho = 2 * H, Wo = 2 * W;
+  const int64_t units = static_cast<int64_t>(N) * Hb * Wb;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * L.ppb;
+  for (int64_t u = static_cast<int64_t>(blockIdx.x) * L.ppb + L.pl; u < units; u += stride) {
+    uint32_t t, mb, n, kb;
+    fd_wb.divmod(static_cast<uint32_t>(u), t, mb);
+    fd_hb.divmod(t, n, kb);
+    const int k = 2 * static_cast<int>(kb), m = 2 * static_cast<int>(mb);
+    const Six wr = six_weights(sh, k, H), wc = six_weights(sw, m, W);
+    float acc[2][2][8] = {};
+    const __nv_bfloat16* base = dy + static_cast<int64_t>(n) * Ho * Wo * dy_ld + L.g * 8;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int r = 2 * k - 1 + j;
+      if (r < 0 || r >= Ho) continue;
+      const __nv_bfloat16* row = base + static_cast<int64_t>(r) * Wo * dy_ld;
+      uint4 v[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int c = 2 * m - 1 + i;
+        v[i] = (c >= 0 && c < Wo) ? ldg16(row + static_cast<int64_t>(c) * dy_ld) : make_uint4(0, 0, 0, 0);
+      }
+      float h0[8] = {}, h1[8] = {};
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        float f[8];
+        unpack8(v[i], f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (i < 4) h0[q] = fmaf(wc.lo[i], f[q], h0[q]);
+          if (i >= 2) h1[q] = fmaf(wc.hi[i - 2], f[q], h1[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (j < 4) { acc[0][0][q] = fmaf(wr.lo[j], h0[q], acc[0][0][q]); acc[0][1][q] = fmaf(wr.lo[j], h1[q], acc[0][1][q]); }
+        if (j >= 2) { acc[1][0][q] = fmaf(wr.hi[j - 2], h0[q], acc[1][0][q]); acc[1][1][q] = fmaf(wr.hi[j - 2], h1[q], acc[1][1][q]); }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (k + a >= H || m + b >= W) continue;
+        __nv_bfloat16* d = dx + ((static_cast<int64_t>(n) * H + k + a) * W + m + b) * dx_ld + L.g * 8;
+        if constexpr (ACC) {
+          float f[8];
+          unpack8(*reinterpret_cast<const uint4*>(d), f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[a][b][q] = f[q] + bf16_round(acc[a][b][q]);
+        }
+        stg16(d, pack8(acc[a][b]));
+      }
+    }
+  }
+}
+
 __global__ void copy_f32_strided_kernel(float* __restrict__ dst, int64_t ds, const float* __restrict__ src, int64_t ss,
                                         int64_t n, int accumulate) {
   pdl_trigger();
@@ -356,9 +528,27 @@ int upsample_bilinear2x_run(const void* src, int64_t src_ld, void* dst, int64_t 
   // area_pixel_compute_scale(align_corners=True): (in - 1) / (out - 1), 0 when out == 1 (cannot happen for 2x)
   const float sh = static_cast<float>(H - 1) / static_cast<float>(2 * H - 1);
   const float sw = static_cast<float>(W - 1) / static_cast<float>(2 * W - 1);
-  const int grid = lanes_grid(units, C, 2);
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(src);
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
+  static int block = -1;   // UNETK_BILINEAR_BLOCK=0: the one-pixel-per-thread kernels
+  if (block < 0) { const char* e = getenv("UNETK_BILINEAR_BLOCK"); block = e ? atoi(e) : 1; }
+  if (block) {
+    if (!backward) {
+      const int g = lanes_grid(static_cast<int64_t>(N) * H * W, C, 2);
+      UNETK_CUDA(launch_pdl(bilinear2x_fwd_block_kernel, dim3(g), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C, sh, sw,
+                            FastDiv(static_cast<uint32_t>(W)), FastDiv(static_cast<uint32_t>(H))));
+    } else {
+      const int hb = (H + 1) / 2, wb = (W + 1) / 2;
+      const int g = lanes_grid(static_cast<int64_t>(N) * hb * wb, C, 1);
+      if (accumulate) UNETK_CUDA(launch_pdl(bilinear2x_bwd_block_kernel<true>, dim3(g), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C, sh, sw,
+                                            FastDiv(static_cast<uint32_t>(wb)), FastDiv(static_cast<uint32_t>(hb))));
+      else UNETK_CUDA(launch_pdl(bilinear2x_bwd_block_kernel<false>, dim3(g), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C, sh, sw,
+                                 FastDiv(static_cast<uint32_t>(wb)), FastDiv(static_cast<uint32_t>(hb))));
+    }
+    UNETK_LAUNCHED();
+    return 0;
+  }
+  const int grid = lanes_grid(units, C, 2);
   if (!backward) UNETK_CUDA(launch_pdl(bilinear2x_fwd_kernel, dim3(grid), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C, sh, sw));
   else if (accumulate) UNETK_CUDA(launch_pdl(bilinear2x_bwd_kernel<true>, dim3(grid), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C, sh, sw));
   else UNETK_CUDA(launch_pdl(bilinear2x_bwd_kernel<false>, dim3(grid), dim3(kThreads), 0, s, a, src_ld, d, dst_ld, N, H, W, C, sh, sw));

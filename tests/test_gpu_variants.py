@@ -96,7 +96,7 @@ def test_add_n(nsrc, acc):
 
 
 @pytest.mark.parametrize("mode", ["nearest", "bilinear"])
-@pytest.mark.parametrize("n,h,w,c", [(2, 5, 7, 24), (1, 16, 16, 64), (1, 1, 3, 8)])
+@pytest.mark.parametrize("n,h,w,c", [(2, 5, 7, 24), (1, 16, 16, 64), (1, 1, 3, 8), (1, 33, 20, 32), (2, 3, 1, 16), (1, 64, 96, 128)])
 def test_upsample2x(mode, n, h, w, c):
     from jcfszxc_unet_b200 import ops
 
