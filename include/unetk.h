@@ -157,6 +157,12 @@ int unetk_bn_eval_fold(int C, const float* gamma, const float* beta, float eps, 
 int unetk_bn_apply(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const void* res,
                    int64_t res_ld, void* out, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W,
                    int C, int relu, void* stream);
+/* bn_apply_copies: bn_apply that also writes the activation to up to three more NHWC views (c0.. packed, NULL at the
+ * end) — the node of NestedUNet that is a member of several torch.cat's (UNetPP.py:80-97) leaves the BatchNorm pass
+ * in all of them at once instead of being re-read once per copy.  No residual input. */
+int unetk_bn_apply_copies(const void* raw, int64_t raw_ld, const float* scale, const float* shift, void* out,
+                          int64_t out_ld, void* pooled, int64_t pooled_ld, void* c0, int64_t c0_ld, void* c1, int64_t c1_ld,
+                          void* c2, int64_t c2_ld, int N, int H, int W, int C, int relu, void* stream);
 /* Backward of out = relu?(bn(raw)).  Incoming gradient = g1 (same resolution; may be NULL) + the scatter of
  * gp (gradient of the 2x2 max-pool of `out`; may be NULL) through the recomputed argmax (first max wins).
  *   unetk_bn_bwd_reduce: sums = double[2][C] (sum g, sum g*xhat)      (SyncBN: all-reduce here)

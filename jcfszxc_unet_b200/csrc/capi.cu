@@ -286,6 +286,18 @@ int unetk_bn_apply(const void* raw, int64_t raw_ld, const float* scale, const fl
   return bn_apply_run(raw, raw_ld, scale, shift, res, res_ld, out, out_ld, pooled, pooled_ld, N, H, W, C, relu,
                       S(stream));
 }
+int unetk_bn_apply_copies(const void* raw, int64_t raw_ld, const float* scale, const float* shift, void* out,
+                          int64_t out_ld, void* pooled, int64_t pooled_ld, void* c0, int64_t c0_ld, void* c1, int64_t c1_ld,
+                          void* c2, int64_t c2_ld, int N, int H, int W, int C, int relu, void* stream) {
+  UNETK_CHECK(raw && scale && shift && out, -1, "bn_apply_copies: null pointer");
+  void* cp[3] = {c0, c1, c2};
+  const int64_t ld[3] = {c0_ld, c1_ld, c2_ld};
+  int n = 0;
+  while (n < 3 && cp[n] != nullptr) ++n;
+  for (int k = n; k < 3; ++k) UNETK_CHECK(cp[k] == nullptr, -1, "bn_apply_copies: destinations must be packed (NULL only at the end)");
+  return bn_apply_run(raw, raw_ld, scale, shift, nullptr, 0, out, out_ld, pooled, pooled_ld, N, H, W, C, relu, S(stream), n,
+                      cp, ld);
+}
 int unetk_bn_bwd_reduce(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
                         const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
                         double* sums, int N, int H, int W, int C, int relu, void* stream) {

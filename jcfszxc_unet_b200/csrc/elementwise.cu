@@ -174,17 +174,23 @@ __device__ __forceinline__ void bn_relu8(const uint4& raw, const float* sc, cons
   }
 }
 
+// Extra destinations of the activation (NestedUNet: a node is a member of up to four torch.cat's, UNetPP.py:80-97):
+// written from the registers of the BatchNorm pass instead of re-reading the tensor once per copy.
+struct Copies {
+  __nv_bfloat16* p[3]; int64_t ld[3]; int n;
+};
+
 // Threads keep ONE channel group for the whole kernel and walk pixels with a constant pointer step (no division
 // in the loop); four 16-byte loads per tensor per thread are in flight per iteration.
 // RES: out = act(bn(raw)) + res  (the `x + x1` of Recurrent_block / RRCNN_block / ResidualConv,
 // unet_parts.py:128,146,475: a bf16 add of two bf16 tensors under autocast).
-template <bool RES>
+template <bool RES, bool COPIES>
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld,
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
                                                             const __nv_bfloat16* __restrict__ res, int64_t res_ld,
                                                             __nv_bfloat16* __restrict__ out, int64_t out_ld,
-                                                            int64_t npix, int C, int relu, int rev) {
+                                                            int64_t npix, int C, int relu, int rev, const Copies X) {
   pdl_trigger();
   pdl_wait();
   Lanes L(C);
@@ -205,7 +211,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16*
   const __nv_bfloat16* ps = RES ? res + first * res_ld + g * 8 : nullptr;
   __nv_bfloat16* po = out + first * out_ld + g * 8;
   const int64_t sr = stride * raw_ld, ss = stride * res_ld, so = stride * out_ld;
-  auto one = [&](const uint4& u, const uint4& v, __nv_bfloat16* dst) {
+  auto one = [&](const uint4& u, const uint4& v, __nv_bfloat16* dst, int64_t pix) {
     float a[8];
     bn_relu8(u, sc, sh, a, r);
     if constexpr (RES) {
@@ -214,8 +220,15 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16*
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] += f[j];
     }
-    stg16(dst, pack8(a));
+    const uint4 o = pack8(a);
+    stg16(dst, o);
+    if constexpr (COPIES) {
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+        if (e < X.n) stg16(X.p[e] + pix * X.ld[e] + g * 8, o);
+    }
   };
+  int64_t pix = first;
   for (; left >= 4; left -= 4) {
     uint4 u[4], v[4];
 #pragma unroll
@@ -224,13 +237,13 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const __nv_bfloat16*
       v[k] = RES ? ldg16(ps + k * ss) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) one(u[k], v[k], po + k * so);
-    pr += 4 * sr; po += 4 * so;
+    for (int k = 0; k < 4; ++k) one(u[k], v[k], po + k * so, pix + k * stride);
+    pr += 4 * sr; po += 4 * so; pix += 4 * stride;
     if constexpr (RES) ps += 4 * ss;
   }
   for (; left > 0; --left) {
-    one(ldg16(pr), RES ? ldg16(ps) : make_uint4(0, 0, 0, 0), po);
-    pr += sr; po += so;
+    one(ldg16(pr), RES ? ldg16(ps) : make_uint4(0, 0, 0, 0), po, pix);
+    pr += sr; po += so; pix += stride;
     if constexpr (RES) ps += ss;
   }
 }
@@ -251,11 +264,12 @@ __device__ __forceinline__ void argmax4(const float (&a)[4][8], float* best, int
   }
 }
 
+template <bool COPIES>
 __global__ void __launch_bounds__(kThreads)
 bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld, const float* __restrict__ scale,
                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int64_t out_ld,
                      __nv_bfloat16* __restrict__ pooled, int64_t pooled_ld, int N, int H, int W, int C,
-                     int rev) {
+                     int rev, const Copies X) {
   pdl_trigger();
   pdl_wait();
   const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
@@ -282,7 +296,14 @@ bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ raw, int64_t raw_ld, cons
     for (int q = 0; q < 4; ++q) {
       float a[8];
       bn_relu8(u[q], sc, sh, a, true);
-      stg16(out + (pix0 + (q >> 1) * W + (q & 1)) * out_ld + g * 8, pack8(a));
+      const uint4 o = pack8(a);
+      const int64_t pix = pix0 + (q >> 1) * W + (q & 1);
+      stg16(out + pix * out_ld + g * 8, o);
+      if constexpr (COPIES) {
+#pragma unroll
+        for (int e = 0; e < 3; ++e)
+          if (e < X.n) stg16(X.p[e] + pix * X.ld[e] + g * 8, o);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (q == 0) best[j] = a[j];
@@ -755,25 +776,43 @@ static int lanes_grid(int64_t units, int C, int blocks_per_sm) {
 
 int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const void* res,
                  int64_t res_ld, void* out, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W, int C,
-                 int relu, cudaStream_t s) {
+                 int relu, cudaStream_t s, int ncopies, void* const* copies, const int64_t* copies_ld) {
   CHECK_C(C);
+  UNETK_CHECK(ncopies >= 0 && ncopies <= 3, -1, "bn_apply: at most 3 extra destinations (got %d)", ncopies);
+  Copies X{};
+  X.n = ncopies;
+  for (int e = 0; e < ncopies; ++e) {
+    UNETK_CHECK(copies[e] != nullptr && copies_ld[e] >= C && copies_ld[e] % 8 == 0, -1, "bn_apply: bad extra destination %d", e);
+    X.p[e] = static_cast<__nv_bfloat16*>(copies[e]); X.ld[e] = copies_ld[e];
+  }
+  const __nv_bfloat16* rw = static_cast<const __nv_bfloat16*>(raw);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   if (pooled != nullptr) {
     UNETK_CHECK(H % 2 == 0 && W % 2 == 0 && relu, -1, "fused pool needs even H,W and relu");
     UNETK_CHECK(res == nullptr, -1, "bn_apply: fused pool and residual add cannot be combined");
     const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
-    UNETK_CUDA(launch_pdl(bn_apply_pool_kernel, dim3(flat_grid_cg(total, C / 8)), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift, static_cast<__nv_bfloat16*>(out), out_ld,
-        static_cast<__nv_bfloat16*>(pooled), pooled_ld, N, H, W, C, reverse_walk()));
+    const int grid = flat_grid_cg(total, C / 8);
+    __nv_bfloat16* pl = static_cast<__nv_bfloat16*>(pooled);
+    if (ncopies > 0)
+      UNETK_CUDA(launch_pdl(bn_apply_pool_kernel<true>, dim3(grid), dim3(kThreads), 0, s, rw, raw_ld, scale, shift, o, out_ld, pl,
+                            pooled_ld, N, H, W, C, reverse_walk(), X));
+    else
+      UNETK_CUDA(launch_pdl(bn_apply_pool_kernel<false>, dim3(grid), dim3(kThreads), 0, s, rw, raw_ld, scale, shift, o, out_ld, pl,
+                            pooled_ld, N, H, W, C, reverse_walk(), X));
   } else {
     const int64_t npix = static_cast<int64_t>(N) * H * W;
     const int grid = lanes_grid(npix, C, 8);
+    const __nv_bfloat16* rs = static_cast<const __nv_bfloat16*>(res);
+    UNETK_CHECK(ncopies == 0 || res == nullptr, -1, "bn_apply: extra destinations and a residual input cannot be combined");
     if (res != nullptr)
-      UNETK_CUDA(launch_pdl(bn_apply_kernel<true>, dim3(grid), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift,
-                                                      static_cast<const __nv_bfloat16*>(res), res_ld,
-                                                      static_cast<__nv_bfloat16*>(out), out_ld, npix, C, relu, reverse_walk()));
+      UNETK_CUDA(launch_pdl(bn_apply_kernel<true, false>, dim3(grid), dim3(kThreads), 0, s, rw, raw_ld, scale, shift, rs, res_ld, o,
+                            out_ld, npix, C, relu, reverse_walk(), X));
+    else if (ncopies > 0)
+      UNETK_CUDA(launch_pdl(bn_apply_kernel<false, true>, dim3(grid), dim3(kThreads), 0, s, rw, raw_ld, scale, shift, nullptr, 0, o,
+                            out_ld, npix, C, relu, reverse_walk(), X));
     else
-      UNETK_CUDA(launch_pdl(bn_apply_kernel<false>, dim3(grid), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(raw), raw_ld, scale, shift,
-                                                       nullptr, 0, static_cast<__nv_bfloat16*>(out), out_ld, npix, C,
-                                                       relu, reverse_walk()));
+      UNETK_CUDA(launch_pdl(bn_apply_kernel<false, false>, dim3(grid), dim3(kThreads), 0, s, rw, raw_ld, scale, shift, nullptr, 0, o,
+                            out_ld, npix, C, relu, reverse_walk(), X));
   }
   UNETK_LAUNCHED();
   return 0;

@@ -37,7 +37,8 @@ int colsum_run(const void* x, int64_t ld, int64_t npix, int C, float* partial, f
 int sums_to_f32_run(const double* sums, int n, float* out, int accumulate, cudaStream_t s);
 int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const void* res,
                  int64_t res_ld, void* out, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W, int C,
-                 int relu, cudaStream_t s);
+                 int relu, cudaStream_t s, int ncopies = 0, void* const* copies = nullptr,
+                 const int64_t* copies_ld = nullptr);
 int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long long* idx, int N, int H, int W, int C,
                     cudaStream_t s);
 int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,

@@ -318,6 +318,7 @@ class ConvBNReLU:
                 plan.register_param(p)
         self.acc_w = self.acc_b = self.acc_bn = self.acc_x = self.acc_res = False
         self.head_fused = False  # set by Head(fuse=self): the head applies this unit's BatchNorm + ReLU itself
+        self.copies = []         # more destinations of `out` (AddN copies folded into the BatchNorm pass, see AddN)
         self.colsum_sinks = []   # (channel offset in x, C, fp32 bias gradient, accumulate): see ConvT2x2.fuse_bias_grad
         plan.ops.append(self)
 
@@ -388,6 +389,10 @@ class ConvBNReLU:
             ops.bn_eval_fold(gamma, beta, bn.eps, bn.running_mean, bn.running_var, sc, sh, mu, iv)
         if self.head_fused:
             return   # `out` is never materialised: Head.fwd reads `raw` and (scale, shift)
+        if self.copies:
+            ops.bn_apply_copies(self.raw.t, sc, sh, self.out.t, [a.t for a in self.copies],
+                                self.pooled.t if self.pooled is not None else None, self.relu)
+            return
         ops.bn_apply(self.raw.t, sc, sh, self.out.t, self.pooled.t if self.pooled is not None else None, self.relu,
                      self.res.t if self.res is not None else None)
 
@@ -719,6 +724,16 @@ class AddN(_Op):
         assert 1 <= len(inputs) <= 4 and all((a.N, a.H, a.W, a.C) == (out.N, out.H, out.W, out.C) for a in inputs)
         self.plan, self.inputs, self.out = plan, inputs, out
         self.acc = [False] * len(inputs)
+        # a plain copy of a tensor that a conv+BatchNorm unit has just produced (the torch.cat members of NestedUNet,
+        # UNetPP.py:80-97) is written by that unit's BatchNorm pass itself; only the backward of this op remains
+        self.fused_fwd = False
+        if len(inputs) == 1 and os.environ.get("UNETK_FUSE_COPIES", "1") != "0":
+            for op in reversed(plan.ops[-8:]):
+                if isinstance(op, ConvBNReLU) and op.out is inputs[0]:
+                    if op.bn is not None and op.res is None and not op.head_fused and len(op.copies) < 3:
+                        op.copies.append(out)
+                        self.fused_fwd = True
+                    break
         plan.ops.append(self)
 
     def _alias(self, a):
@@ -729,7 +744,8 @@ class AddN(_Op):
             self.acc = [False if self._alias(a) else plan.grad_acc(a) for a in self.inputs]
 
     def fwd(self):
-        ops.add_n(self.out.t, [a.t for a in self.inputs])
+        if not self.fused_fwd:
+            ops.add_n(self.out.t, [a.t for a in self.inputs])
 
     def bwd(self):
         for a, acc in zip(self.inputs, self.acc):

@@ -261,6 +261,20 @@ def bn_apply(raw, scale, shift, out, pooled=None, relu=True, res=None):
               _stream())
 
 
+def bn_apply_copies(raw, scale, shift, out, copies, pooled=None, relu=True):
+    """bn_apply that also stores the activation into `copies` (1..3 more NHWC views of out's shape)."""
+    n, h, w, c = raw.shape
+    assert 1 <= len(copies) <= 3 and all(t.shape == out.shape for t in copies)
+    rp, rld = nhwc(raw)
+    op, old = nhwc(out)
+    pp, pld = nhwc(pooled) if pooled is not None else (None, 0)
+    args = []
+    for i in range(3):
+        args += list(nhwc(copies[i])) if i < len(copies) else [None, 0]
+    _lib.call("unetk_bn_apply_copies", rp, rld, _f32(scale), _f32(shift), op, old, pp, pld, *args, n, h, w, c, int(relu),
+              _stream())
+
+
 def bn_bwd_reduce(raw, g1, gp, scale, shift, mean, invstd, partial, sums, relu=True):
     n, h, w, c = raw.shape
     rp, rld = nhwc(raw)

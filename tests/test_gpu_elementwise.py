@@ -80,6 +80,32 @@ def test_bn_apply_fused_pool_equals_separate_and_matches_torch(n, h, w, c):
     assert torch.equal(pooled, pooled2)
 
 
+@pytest.mark.parametrize("n,h,w,c,pool,ncopy", [(2, 16, 16, 32, False, 3), (1, 8, 12, 64, True, 2), (1, 6, 10, 24, True, 1),
+                                                 (3, 5, 7, 128, False, 1)])
+def test_bn_apply_with_extra_destinations(n, h, w, c, pool, ncopy):
+    """unetk_bn_apply_copies = unetk_bn_apply + one unetk_add_n copy per extra destination (the members of NestedUNet's
+    torch.cat's, UNetPP.py:80-97): same bits in every destination, nothing written outside the channel slices."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(n * c + h)
+    raw = (torch.randn(n, h, w, c, device=DEV, generator=g) * 2).bfloat16()
+    sc = torch.rand(c, device=DEV, generator=g) + 0.5
+    sh = torch.randn(c, device=DEV, generator=g) * 0.3
+    ref = torch.empty(n, h, w, c, device=DEV, dtype=torch.bfloat16)
+    ref_pool = torch.empty(n, h // 2, w // 2, c, device=DEV, dtype=torch.bfloat16) if pool else None
+    ops.bn_apply(raw, sc, sh, ref, ref_pool, True)
+    out = torch.empty_like(ref)
+    out_pool = torch.empty_like(ref_pool) if pool else None
+    bufs = [torch.full((n, h, w, c + 8 * (e + 1) + 16), 7.0, device=DEV, dtype=torch.bfloat16) for e in range(ncopy)]
+    views = [b[..., 8 * (e + 1): 8 * (e + 1) + c] for e, b in enumerate(bufs)]
+    ops.bn_apply_copies(raw, sc, sh, out, views, out_pool, True)
+    assert torch.equal(out, ref)
+    if pool:
+        assert torch.equal(out_pool, ref_pool)
+    for e, (b, v) in enumerate(zip(bufs, views)):
+        assert torch.equal(v, ref)
+        assert bool((b[..., : 8 * (e + 1)] == 7.0).all()) and bool((b[..., 8 * (e + 1) + c:] == 7.0).all())
+
+
 def test_maxpool_indices_bit_exact_golden_and_live():
     """Indices must equal F.max_pool2d(..., return_indices=True) bit for bit: ties (first max wins),
     NaN (always taken, last wins), +inf.  Golden = reference torch output on CPU; live = torch on this GPU."""
