@@ -64,6 +64,12 @@ int unetk_conv3x3_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, c
                               int Cout, void* stream);
 int unetk_conv3x3_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
                         int accumulate, int N, int H, int W, int Cin, int Cout, void* stream);
+/* dgrad of input channels [col0, col0 + ncols) only, written to its own NHWC view dx (ncols channels): the input of a
+ * conv that reads a torch.cat (NestedUNet, UNetPP.py:80-97) is made of members whose gradients live in different
+ * buffers, so each member's columns go (accumulate != 0: bf16 reduce-add) straight to that member's gradient instead
+ * of through a concat-gradient buffer and one add pass per member.  w_pack_t is the whole pack [9][Cin_total][Cout]. */
+int unetk_conv3x3_dgrad_cols(const void* dy, int64_t dy_ld, const void* w_pack_t, int Cin_total, int col0, void* dx,
+                             int64_t dx_ld, int accumulate, int N, int H, int W, int ncols, int Cout, void* stream);
 /* dgrad that also returns sums = double[2][Cin]: per-channel (sum, sum of squares) over all pixels of the bf16 dx it
  * wrote (no accumulate).  When dx is the gradient of a concat buffer [skip | up] (unet_parts.py:69), sums[0][C..2C)
  * IS the bias gradient of the ConvTranspose2d that produced `up` (unet_parts.py:56-58): unetk_sums_to_f32 copies it

@@ -31,6 +31,7 @@ SIGNATURES = {
     "unetk_conv_stats_partial_floats": (_sz, [_i]),
     "unetk_conv3x3_fwd_bnstats": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv3x3_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "unetk_conv3x3_dgrad_cols": (_i, [_vp, _i64, _vp, _i, _i, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv3x3_dgrad_colsum": (_i, [_vp, _i64, _vp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "unetk_sums_to_f32": (_i, [_vp, _i, _fp, _i, _vp]),
     "unetk_conv3x3s2_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -32,10 +32,15 @@ static WgradDesc conv_wgrad_desc(const void* x, int64_t x_ld, const void* dy, in
 static int conv_fwd_like(const void* x, int64_t x_ld, const void* w, const float* bias, void* y, int64_t y_ld,
                          int N, int H, int W, int K, int ncols, int ksize, bool dgrad, void* stream,
                          float* stats_partial = nullptr, double* stats_sums = nullptr, int accumulate = 0,
-                         int a_step = 1, int out_f32 = 0) {
+                         int a_step = 1, int out_f32 = 0, int b_rows = 0, int col0 = 0) {
   UNETK_CHECK(x && w && y && N > 0 && H > 0 && W > 0 && K > 0 && ncols > 0, -1, "conv: bad arguments");
+  UNETK_CHECK(b_rows == 0 || (col0 >= 0 && col0 + ncols <= b_rows && col0 % 8 == 0), -1,
+              "conv: column slice [%d, %d) of %d weight rows", col0, col0 + ncols, b_rows);
   ConvGemmDesc d{};
-  d.a = x; d.a_ld = x_ld; d.b = w; d.out = y; d.out_ld = y_ld; d.bias = bias;
+  d.a = x; d.a_ld = x_ld; d.out = y; d.out_ld = y_ld; d.bias = bias;
+  // column slice of a wider pack: rows col0 .. col0 + ncols of every tap (the taps stay b_rows rows apart)
+  d.b = static_cast<const __nv_bfloat16*>(w) + static_cast<size_t>(col0) * K;
+  d.b_rows = b_rows;
   d.stats_partial = stats_partial; d.stats_sums = stats_sums;
   d.N = N; d.H = H; d.W = W; d.K = K; d.ncols = ncols; d.q_groups = 1;
   d.a_step = a_step; d.out_step = 1; d.accumulate = accumulate; d.out_f32 = out_f32;
@@ -68,6 +73,11 @@ int unetk_conv3x3_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, voi
                         int N, int H, int W, int Cin, int Cout, void* stream) {
   return conv_fwd_like(dy, dy_ld, w_pack_t, nullptr, dx, dx_ld, N, H, W, Cout, Cin, 3, true, stream, nullptr, nullptr,
                        accumulate);
+}
+int unetk_conv3x3_dgrad_cols(const void* dy, int64_t dy_ld, const void* w_pack_t, int Cin_total, int col0, void* dx,
+                             int64_t dx_ld, int accumulate, int N, int H, int W, int ncols, int Cout, void* stream) {
+  return conv_fwd_like(dy, dy_ld, w_pack_t, nullptr, dx, dx_ld, N, H, W, Cout, ncols, 3, true, stream, nullptr, nullptr,
+                       accumulate, 1, 0, Cin_total, col0);
 }
 int unetk_conv3x3_dgrad_colsum(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
                                float* partial, double* sums, int N, int H, int W, int Cin, int Cout, void* stream) {

@@ -319,6 +319,10 @@ class ConvBNReLU:
         self.acc_w = self.acc_b = self.acc_bn = self.acc_x = self.acc_res = False
         self.head_fused = False  # set by Head(fuse=self): the head applies this unit's BatchNorm + ReLU itself
         self.copies = []         # more destinations of `out` (AddN copies folded into the BatchNorm pass, see AddN)
+        # x is a torch.cat whose members' gradients live elsewhere: [(first channel, channels, Act whose .g receives
+        # those columns of the dgrad)], set by the builder (builders.build_nested_unet_plan); None: dgrad writes x.g
+        self.x_parts = None
+        self.part_acc = []
         self.colsum_sinks = []   # (channel offset in x, C, fp32 bias gradient, accumulate): see ConvT2x2.fuse_bias_grad
         plan.ops.append(self)
 
@@ -345,7 +349,10 @@ class ConvBNReLU:
         self.acc_w = plan.param_acc(self.conv.weight)
         self.acc_b = plan.param_acc(self.conv.bias)
         if not self.stem and self.x.g is not None:
-            self.acc_x = plan.grad_acc(self.x)
+            if self.x_parts is not None:
+                self.part_acc = [plan.grad_acc(t) for _, _, t in self.x_parts]
+            else:
+                self.acc_x = plan.grad_acc(self.x)
 
     def refresh(self, force=False):
         if self.w3 is not None:
@@ -428,7 +435,10 @@ class ConvBNReLU:
                 ops.conv_wgrad(self.x.t, dy, self.dw, self.k, self.acc_w, self.stride, ws=P.ws)
         if self.dbias is not None and self.bn is None:
             ops.colsum(dy, P.partial, self.dbias, self.acc_b)
-        if not self.stem and self.x.g is not None:
+        if not self.stem and self.x.g is not None and self.x_parts is not None:
+            for (c0, c, t), acc in zip(self.x_parts, self.part_acc):
+                ops.conv_dgrad_cols(dy, self.pack.ba, c0, t.g, acc)
+        elif not self.stem and self.x.g is not None:
             if self.colsum_sinks:
                 # the dgrad epilogue also sums its output per channel: the bias gradient of the ConvTranspose2d
                 # whose output is a channel slice of x (the concat buffer) comes for free
@@ -727,6 +737,7 @@ class AddN(_Op):
         # a plain copy of a tensor that a conv+BatchNorm unit has just produced (the torch.cat members of NestedUNet,
         # UNetPP.py:80-97) is written by that unit's BatchNorm pass itself; only the backward of this op remains
         self.fused_fwd = False
+        self.scattered = False   # the consumers' dgrads write the input's gradient themselves (ConvBNReLU.x_parts)
         if len(inputs) == 1 and os.environ.get("UNETK_FUSE_COPIES", "1") != "0":
             for op in reversed(plan.ops[-8:]):
                 if isinstance(op, ConvBNReLU) and op.out is inputs[0]:
@@ -740,7 +751,7 @@ class AddN(_Op):
         return a.g is None or a.g.data_ptr() == self.out.g.data_ptr()
 
     def plan_bwd(self, plan):
-        if plan.with_grad:
+        if plan.with_grad and not self.scattered:
             self.acc = [False if self._alias(a) else plan.grad_acc(a) for a in self.inputs]
 
     def fwd(self):
@@ -748,6 +759,8 @@ class AddN(_Op):
             ops.add_n(self.out.t, [a.t for a in self.inputs])
 
     def bwd(self):
+        if self.scattered:
+            return
         for a, acc in zip(self.inputs, self.acc):
             if not self._alias(a):
                 ops.add_n(a.g, [self.out.g], accumulate=acc)

@@ -70,6 +70,18 @@ def conv_fwd(x, w_pack, bias, y, ksize: int = 3):
     return y
 
 
+def conv_dgrad_cols(dy, w_pack_t, col0: int, dx, accumulate: bool = False):
+    """dx (+)<- the input-channel slice [col0, col0 + dx.C) of conv3x3^T(dy); w_pack_t is the whole pack [9,Cin,Cout]."""
+    n, h, w, cout = dy.shape
+    taps, cin_total, cout_w = w_pack_t.shape
+    assert taps == 9 and cout_w == cout and dx.shape[:3] == dy.shape[:3] and col0 + dx.shape[3] <= cin_total
+    dyp, dyld = nhwc(dy)
+    dxp, dxld = nhwc(dx)
+    _lib.call("unetk_conv3x3_dgrad_cols", dyp, dyld, w_pack_t.data_ptr(), cin_total, col0, dxp, dxld, int(accumulate),
+              n, h, w, dx.shape[3], cout, _stream())
+    return dx
+
+
 def conv_dgrad(dy, w_pack_t, dx, ksize: int = 3, accumulate: bool = False, stride: int = 1):
     """dx (+)<- conv^T(dy): dy [N,H,W,Cout], w_pack_t bf16 [k*k,Cin,Cout], dx [N,stride*H,stride*W,Cin]."""
     n, h, w, cout = dy.shape

@@ -153,6 +153,36 @@ def test_conv3x3_dgrad(n, h, w, cin, cout, xpad, ypad):
     _close(dx, ref, "conv3x3_dgrad")
 
 
+@pytest.mark.parametrize("n,h,w,parts,cout", [(1, 6, 128, [32, 32, 64], 32), (2, 5, 40, [64, 128], 64), (1, 4, 256, [32, 32, 32, 32, 64], 32),
+                                                 (1, 3, 130, [24, 40], 16)])
+def test_conv3x3_dgrad_column_slices(n, h, w, parts, cout):
+    """unetk_conv3x3_dgrad_cols: every member of a concat input gets its own columns of the dgrad, written (or bf16
+    reduce-added) straight into that member's gradient view: equal to the matching slice of the whole dgrad."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    cin = sum(parts)
+    g = torch.Generator(device=dev).manual_seed(cin + cout + w)
+    dy = torch.randn(n, h, w, cout, device=dev, generator=g).to(torch.bfloat16)
+    wt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * (1.0 / (3 * cout ** 0.5))
+    _, w_pack_t = ops.pack_weight(wt, False, True)
+    whole = torch.empty(n, h, w, cin, device=dev, dtype=torch.bfloat16)
+    ops.conv_dgrad(dy, w_pack_t, whole, 3)
+    ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt.bfloat16().float(), padding=1).permute(0, 2, 3, 1)
+    _close(whole, ref, "conv3x3_dgrad")
+    c0 = 0
+    for k, c in enumerate(parts):
+        buf = torch.zeros(n, h, w, c + 24, device=dev, dtype=torch.bfloat16)     # a slice of a wider gradient buffer
+        view = buf[..., 8:8 + c]
+        ops.conv_dgrad_cols(dy, w_pack_t, c0, view, accumulate=False)
+        _close(view, ref[..., c0:c0 + c], f"dgrad_cols part {k}")
+        assert float(buf[..., :8].abs().max()) == 0 and float(buf[..., 8 + c:].abs().max()) == 0
+        base = torch.randn(n, h, w, c, device=dev, generator=g).to(torch.bfloat16)
+        view.copy_(base)
+        ops.conv_dgrad_cols(dy, w_pack_t, c0, view, accumulate=True)
+        _close(view, base.float() + ref[..., c0:c0 + c], f"dgrad_cols accumulate part {k}")
+        c0 += c
+
+
 WGRAD_EXTRA = [
     # Cout <= 64 < Cin: the weight-gradient GEMM runs with swapped operands and reversed taps (wgrad3x3_run, flip)
     (1, 16, 32, 128, 64, (0, 0), (0, 0)),
