@@ -19,6 +19,8 @@ GradScaler/fp16 autocast is replaced by bf16 as BASELINE.json asks, SURVEY.md §
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import engine, ops
@@ -63,6 +65,7 @@ class Trainer:
         self.sq_partial = None
         self.plan = None
         self.graphs = None
+        self._single_graph = False
         self.images = self.labels = None
         self.steps_done = 0
         # input pipeline (prefetch / step()): two staging batches in HBM filled by a copy stream
@@ -140,8 +143,21 @@ class Trainer:
         ops.rmsprop_step(self.flat_p, self.flat_g, self.sq, self.buf, self.lr, self.alpha, self.eps, self.wd,
                          self.momentum, self.clip)
 
+    def _seg_all(self):
+        """The whole iteration as one launch sequence: single process, nothing to exchange between the segments."""
+        self.plan.refresh_weights(force=True)
+        self._seg_forward()
+        self.plan.head.finalize_loss(self._npix_total)
+        self.plan.backward(0, None)
+        self._seg_optim()
+
     def _run_segments(self):
         head = self.plan.head
+        if self.graphs is not None and self._single_graph:
+            # one CUDA graph per step: the weight-gradient side stream is joined once, in front of the optimizer,
+            # instead of at the end of each backward segment
+            self.graphs[0].replay()
+            return
         if self.graphs is not None:
             self.graphs[0].replay()
         else:
@@ -175,7 +191,10 @@ class Trainer:
         # captured on a HIGH-priority stream: the plan's weight-gradient side stream is low priority, so whenever a
         # kernel of the critical path and a weight gradient are both ready, the critical path gets the SMs first
         hp = torch.cuda.Stream(device=self.device, priority=-1)
-        for seg in (self._seg_forward_packed, self._seg_backward, self._seg_backward_tail, self._seg_optim):
+        self._single_graph = not self.dp.enabled and os.environ.get("UNETK_SINGLE_GRAPH", "1") != "0"
+        segments = ((self._seg_all,) if self._single_graph else
+                    (self._seg_forward_packed, self._seg_backward, self._seg_backward_tail, self._seg_optim))
+        for seg in segments:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, stream=hp):
                 seg()

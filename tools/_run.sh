@@ -1,7 +1,6 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench66_n8.json 2> gpurun_out/bench66_n8.err
-echo "rc=$?"; python -c "
-import json
-for ln in open('gpurun_out/bench66_n8.json'):
-    if ln.startswith('{'):
-        d=json.loads(ln); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d.get('loss'), d['clocks'])"
-tail -3 gpurun_out/bench66_n8.err
+python -m pytest tests/test_gpu_unet.py -m gpu -x -q 2>&1 | grep -E "^E  |passed|failed|Error" | head -20
+run() { python bench.py --no-cpu-baseline --steps 30 --warmup 5 "${@:2}" 2>>gpurun_out/b67.err | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('$1', round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['value'],1), d['clocks']['sm_mhz'])"; }
+for i in 1 2; do
+UNETK_SINGLE_GRAPH=0 run four_graphs
+run one_graph
+done
