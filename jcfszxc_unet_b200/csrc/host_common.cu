@@ -26,6 +26,12 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+int pdl_small_grid() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("UNETK_PDL_SMALL"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 bool pdl_enabled() {
   static int v = -1;
   // Measured on B200 (UNet B=16 512^2, CUDA graphs, same box, 2 rounds): PDL off 24.12 / 23.85 ms per step, on 24.79 /

@@ -44,6 +44,7 @@ void count_launch();
 // must execute pdl_wait() (ptx.cuh) before its first access to global memory.  Measured slower on the UNet step
 // (host_common.cu): a plain launch unless UNETK_PDL=1.
 bool pdl_enabled();
+int pdl_small_grid();   // UNETK_PDL_SMALL=n: grids of <= n blocks (the one-block second stages / finalize kernels) use PDL
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args&&... args) {
@@ -56,7 +57,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_enabled() || static_cast<long long>(grid.x) * grid.y * grid.z <= pdl_small_grid()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -35,8 +35,10 @@ constexpr uint32_t kPBoxBytes = kPix * 128;  // [64 px][64 ch] bf16
 struct W3Params {
   CUtensorMap tmP;  // dY: dims (M, W, H, N), box (64, TW, TH, 1)
   CUtensorMap tmQ;  // X : dims (Nn, W, H, N), box (64, TW+2, TH, 1)
-  CUtensorMap tmP2; // paired mode: dY box (64, 64, 2, 1) = two image rows, one per filter row of the pair
-  int paired;       // 1: M <= 64 -> the two halves of the 128 MMA rows carry two FILTER ROWS (see make_plan)
+  CUtensorMap tmP2; // paired mode: dY box (64, 64, 2 or 3, 1) = image rows, one per filter row
+  int paired;       // 1: M <= 64 -> the two halves of the 128 MMA rows carry two FILTER ROWS (see make_plan);
+                    // 2: the same with BOTH row groups in one work item (three dY rows per X row, two accumulators)
+  int stages;       // pipeline depth actually used (<= W3Cfg::kStages)
   float* partial;   // [ksplit][9][M][Nn]
   int TH, TW, tiles_h, tiles_w, pix_tiles;
   int m_tiles, n_tiles, ksplit;
@@ -49,7 +51,7 @@ template <int NT>
 struct W3Cfg {
   static constexpr int kQBoxes = NT / 64;
   static constexpr int kStages = (NT == 128) ? 5 : 7;
-  static constexpr uint32_t kTmemCols = (3 * NT > 256) ? 512 : 256;
+  static constexpr uint32_t kTmemCols = 512;   // NT = 64 merged mode: two 192-column accumulators
 };
 
 template <int NT>
@@ -58,8 +60,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  const uint32_t stage_bytes = 2 * kPBoxBytes + C::kQBoxes * p.q_box_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * stage_bytes);
+  const bool merged = p.paired == 2;
+  const uint32_t p_boxes = merged ? 3u : 2u;
+  const uint32_t stage_bytes = p_boxes * kPBoxBytes + C::kQBoxes * p.q_box_bytes;
+  const int nstages = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nstages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tfull_bar = bars + 2 * C::kStages;   // [1]
@@ -89,14 +94,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   pdl_trigger();
   pdl_wait();
 
-  const int items_per_split = p.paired ? 2 * p.n_tiles : 3 * p.m_tiles * p.n_tiles;
+  const int items_per_split = merged ? p.n_tiles : (p.paired ? 2 * p.n_tiles : 3 * p.m_tiles * p.n_tiles);
   const int num_items = items_per_split * p.ksplit;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = 2 * kPBoxBytes + C::kQBoxes * p.q_tx_bytes;
+      const uint32_t tx = p_boxes * kPBoxBytes + C::kQBoxes * p.q_tx_bytes;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int nt = item % p.n_tiles;
         const int mt = p.paired ? 0 : (item / p.n_tiles) % p.m_tiles;
@@ -112,16 +117,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
           const int h0 = th * p.TH, w0 = tw * p.TW;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sp = smem + stage * stage_bytes;
-          uint8_t* sq = sp + 2 * kPBoxBytes;
+          uint8_t* sq = sp + p_boxes * kPBoxBytes;
           mbar_expect_tx(&full_bar[stage], tx);
           if (p.paired) {
             // X row q = h0 meets dY row q-r+1 under filter row r: group 0 loads dY rows (q, q+1) = filter rows (1, 0),
             // group 1 loads rows (q-1, q) = filter rows (2, 1 [discarded]); rows outside the image read as zero
-            tma_load_4d(sp, &p.tmP2, &full_bar[stage], 0, w0, h0 - r, img);
+            // merged: dY rows (q-1, q, q+1) in one box; the two MMAs of a k-step read rows (q, q+1) and (q-1, q)
+            tma_load_4d(sp, &p.tmP2, &full_bar[stage], 0, w0, merged ? h0 - 1 : h0 - r, img);
 #pragma unroll
             for (int b = 0; b < C::kQBoxes; ++b)
               tma_load_4d(sq + b * p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT + b * 64, w0 - 1, h0, img);
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            if (++stage == nstages) { stage = 0; phase ^= 1u; }
             continue;
           }
 #pragma unroll
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 #pragma unroll
           for (int b = 0; b < C::kQBoxes; ++b)
             tma_load_4d(sq + b * p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT + b * 64, w0 - 1, h0 + r - 1, img);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       for (int k = 0; k < kPix / 16; ++k)
         q_off[k] = static_cast<uint32_t>((k / steps_per_row) * row_pitch + (k % steps_per_row) * 16) * 128;
       const uint64_t p_desc0 = make_smem_desc(smem_u32(smem), kPBoxBytes, 1024, kLayoutSW128);
-      const uint64_t q_desc0 = make_smem_desc(smem_u32(smem) + 2 * kPBoxBytes, (NT == 64) ? 128u : p.q_box_bytes, 1024,
+      const uint64_t q_desc0 = make_smem_desc(smem_u32(smem) + p_boxes * kPBoxBytes, (NT == 64) ? 128u : p.q_box_bytes, 1024,
                                               kLayoutSW128);
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int ks = item / items_per_split;
@@ -173,7 +179,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
             if constexpr (NT == 64) {
               // taps s = 0,1,2 as three overlapping 64-wide N atoms, 128 B (one pixel row) apart (LBO = 128 B)
               constexpr uint32_t idesc = make_idesc_bf16(128, 192, true, true);
-              umma_bf16_p(issue, tmem_base, da, dq, idesc, (first && k == 0) ? 0u : 1u);   // no control flow per MMA
+              if (merged) {   // uniform per launch
+                // rows (q, q+1) -> filter rows (1, 0) in columns 0..191; rows (q-1, q) -> filter rows (2, [1]) in 192..383
+                umma_bf16_p(issue, tmem_base, desc_advance(da, kPBoxBytes), dq, idesc, (first && k == 0) ? 0u : 1u);
+                umma_bf16_p(issue, tmem_base + 192, da, dq, idesc, (first && k == 0) ? 0u : 1u);
+              } else {
+                umma_bf16_p(issue, tmem_base, da, dq, idesc, (first && k == 0) ? 0u : 1u);   // no control flow per MMA
+              }
             } else {
               constexpr uint32_t idesc = make_idesc_bf16(128, NT, true, true);
 #pragma unroll
@@ -183,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
             }
           }
           umma_commit_p(issue, &empty_bar[stage]);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
         umma_commit_p(issue, tfull_bar);
       }
@@ -195,35 +207,39 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int nt = item % p.n_tiles;
       const int mt = p.paired ? 0 : (item / p.n_tiles) % p.m_tiles;
-      int r = p.paired ? (item / p.n_tiles) % 2 : (item / (p.n_tiles * p.m_tiles)) % 3;
+      const int r_item = p.paired ? (item / p.n_tiles) % 2 : (item / (p.n_tiles * p.m_tiles)) % 3;
       const int ks = item / items_per_split;
-      int m = mt * 128 + row;
-      if (p.paired) {
-        // accumulator rows 0-63 = first dY row of the pair, 64-127 = second: group 0 -> filter rows (1, 0), group 1 -> (2, -)
-        const int half = row >> 6;
-        m = row & 63;
-        if (r == 0) r = 1 - half;
-        else { r = 2; if (half) m = p.M; }   // second half of group 1 repeats filter row 1: not stored
-      }
       mbar_wait(tfull_bar, it & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int s = 0; s < 3; ++s) {
-        float* dst = p.partial + ((static_cast<size_t>(ks) * 9 + r * 3 + s) * p.M + m) * p.Nn + nt * NT;
+      for (int a = 0; a < (merged ? 2 : 1); ++a) {   // merged: accumulator 0 = row group 0, accumulator 1 = group 1
+        int r = merged ? a : r_item;
+        int m = mt * 128 + row;
+        if (p.paired) {
+          // accumulator rows 0-63 = first dY row of the pair, 64-127 = second: group 0 -> filter rows (1, 0), group 1 -> (2, -)
+          const int half = row >> 6;
+          m = row & 63;
+          if (r == 0) r = 1 - half;
+          else { r = 2; if (half) m = p.M; }   // second half of group 1 repeats filter row 1: not stored
+        }
 #pragma unroll 1
-        for (int c = 0; c < NT / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + s * NT + c * 32, v);
-          tmem_ld_wait();
-          if (m < p.M) {
+        for (int s = 0; s < 3; ++s) {
+          float* dst = p.partial + ((static_cast<size_t>(ks) * 9 + r * 3 + s) * p.M + m) * p.Nn + nt * NT;
+#pragma unroll 1
+          for (int c = 0; c < NT / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(taddr + a * 192 + s * NT + c * 32, v);
+            tmem_ld_wait();
+            if (m < p.M) {
 #pragma unroll
-            for (int x = 0; x < 8; ++x) {
-              const int col = nt * NT + c * 32 + x * 4;
-              if (col < p.Nn) {
-                float4 o = make_float4(__uint_as_float(v[x * 4]), __uint_as_float(v[x * 4 + 1]),
-                                       __uint_as_float(v[x * 4 + 2]), __uint_as_float(v[x * 4 + 3]));
-                *reinterpret_cast<float4*>(dst + c * 32 + x * 4) = o;
+              for (int x = 0; x < 8; ++x) {
+                const int col = nt * NT + c * 32 + x * 4;
+                if (col < p.Nn) {
+                  float4 o = make_float4(__uint_as_float(v[x * 4]), __uint_as_float(v[x * 4 + 1]),
+                                         __uint_as_float(v[x * 4 + 2]), __uint_as_float(v[x * 4 + 3]));
+                  *reinterpret_cast<float4*>(dst + c * 32 + x * 4) = o;
+                }
               }
             }
           }
@@ -244,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 }
 
 struct W3Plan {
-  int NT, TH, TW, tiles_h, tiles_w, pix_tiles, m_tiles, n_tiles, ksplit, paired;
+  int NT, TH, TW, tiles_h, tiles_w, pix_tiles, m_tiles, n_tiles, ksplit, paired, stages;
   uint32_t q_box_bytes, q_tx_bytes, smem_bytes;
 };
 
@@ -262,8 +278,17 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
   pl->n_tiles = (Nn + pl->NT - 1) / pl->NT;
   pl->q_tx_bytes = static_cast<uint32_t>(pl->TH * (tw + 2) * 128);
   pl->q_box_bytes = (pl->q_tx_bytes + 1023u) & ~1023u;
-  const int stages = pl->NT == 128 ? 5 : 7;
-  const uint32_t stage = 2 * kPBoxBytes + (pl->NT / 64) * pl->q_box_bytes;
+  static int pair_env = -1, merge_env = -1;
+  if (pair_env < 0) { const char* e = getenv("UNETK_WGRAD3_PAIR"); pair_env = e ? atoi(e) : 1; }
+  if (merge_env < 0) { const char* e = getenv("UNETK_WGRAD3_MERGE"); merge_env = e ? atoi(e) : 1; }
+  pl->paired = (pair_env && M <= 64 && pl->NT == 64 && pl->TW == 64 && pl->TH == 1) ? (merge_env ? 2 : 1) : 0;
+  // merged: both filter-row groups in one pass over the pixels.  The 64-channel layers are bound by the L2 -> SM
+  // fabric (3.25 GB through the crossbar per 64 -> 64 launch = 9 TB/s at 60 % tensor-pipe activity,
+  // profiles/r01_ncu_top_kernels_v6.txt): one X row + THREE dY rows per k-block (33.8 KB per 768 MMA clocks) instead of
+  // one X row + two dY rows per group (2 x 24.6 KB)
+  const int stages = pl->NT == 128 ? 5 : (pl->paired == 2 ? 6 : 7);
+  pl->stages = stages;
+  const uint32_t stage = (pl->paired == 2 ? 3 : 2) * kPBoxBytes + (pl->NT / 64) * pl->q_box_bytes;
   pl->smem_bytes = stages * stage + 1024 + 256;
   if (pl->smem_bytes > 227 * 1024) return false;
   // items = 3 * m_tiles * n_tiles * ksplit run in waves of num_sms CTAs.  Pick the pixel split that minimises
@@ -273,10 +298,7 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
   // M <= 64 (64-channel dY): half of the 128 MMA rows would be empty (59 % tensor-pipe activity for 30 % useful work,
   // profiles/r01_ncu_wgrad3x3.txt).  With one image row per k-block (TW = 64) the second half is given the NEXT dY row,
   // i.e. another filter row against the same X halo row: 2 work items per pixel range instead of 3.
-  static int pair_env = -1;
-  if (pair_env < 0) { const char* e = getenv("UNETK_WGRAD3_PAIR"); pair_env = e ? atoi(e) : 1; }
-  pl->paired = (pair_env && M <= 64 && pl->NT == 64 && pl->TW == 64 && pl->TH == 1) ? 1 : 0;
-  const int base = pl->paired ? 2 * pl->n_tiles : 3 * pl->m_tiles * pl->n_tiles;
+  const int base = pl->paired == 2 ? pl->n_tiles : (pl->paired ? 2 * pl->n_tiles : 3 * pl->m_tiles * pl->n_tiles);
   const int cap = pl->pix_tiles / 8 > 0 ? pl->pix_tiles / 8 : 1;
   static int rule = -1;
   if (rule < 0) { const char* e = getenv("UNETK_WGRAD3_RULE"); rule = e ? atoi(e) : 0; }
@@ -284,7 +306,7 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
     // few (m, n) tiles = the wide-image thin-channel layers (L2 -> SM bound): ~2 items per SM.  The cost rule below
     // would pick one wave of items twice as long; measured on the same box it makes no difference there
     // (UNet step: 5.79-5.81 vs 5.61-5.80 ms over the 17 weight gradients), so these keep the simple rule.
-    int ks = (2 * num_sms()) / base;
+    int ks = (2 * num_sms()) / (pl->paired == 2 ? 2 * base : base);   // merged items are twice as long: one wave
     if (ks > cap) ks = cap;
     pl->ksplit = ks < 1 ? 1 : ks;
     return true;
@@ -307,7 +329,7 @@ int launch(const W3Params& p, const W3Plan& pl, cudaStream_t stream) {
     UNETK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int items = (pl.paired ? 2 * pl.n_tiles : 3 * pl.m_tiles * pl.n_tiles) * pl.ksplit;
+  const int items = (pl.paired == 2 ? pl.n_tiles : (pl.paired ? 2 * pl.n_tiles : 3 * pl.m_tiles * pl.n_tiles)) * pl.ksplit;
   const int grid = items < num_sms() ? items : num_sms();
   UNETK_CUDA(launch_pdl(wgrad3x3_kernel<NT>, dim3(grid), dim3(kThreads), pl.smem_bytes, stream, p));
   UNETK_LAUNCHED();
@@ -341,6 +363,7 @@ int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, flo
   p.M = M; p.Nn = Nn;
   p.q_box_bytes = pl.q_box_bytes; p.q_tx_bytes = pl.q_tx_bytes;
   p.paired = pl.paired;
+  p.stages = pl.stages;
   auto mk = [&](CUtensorMap* tm, const void* base, int64_t ld, int C, int halo) -> int {
     uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                         static_cast<uint64_t>(N)};
@@ -355,7 +378,7 @@ int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, flo
     uint64_t dims[4] = {static_cast<uint64_t>(M), static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(N)};
     uint64_t strides[3] = {static_cast<uint64_t>(dy_ld) * 2, static_cast<uint64_t>(dy_ld) * 2 * W,
                            static_cast<uint64_t>(dy_ld) * 2 * W * H};
-    uint32_t box[4] = {64, 64, 2, 1};
+    uint32_t box[4] = {64, 64, pl.paired == 2 ? 3u : 2u, 1};
     uint32_t es[4] = {1, 1, 1, 1};
     if (int rc = make_tmap_bf16(&p.tmP2, dy, 4, dims, strides, box, es, true)) return rc;
   }
