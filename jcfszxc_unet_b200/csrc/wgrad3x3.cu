@@ -39,6 +39,8 @@ struct W3Params {
   int paired;       // 1: M <= 64 -> the two halves of the 128 MMA rows carry two FILTER ROWS (see make_plan);
                     // 2: the same with BOTH row groups in one work item (three dY rows per X row, two accumulators)
   int stages;       // pipeline depth actually used (<= W3Cfg::kStages)
+  int rows2;        // 1 (NT = 64, TH = 1, not paired): filter rows 0 and 1 share one pass (two halo rows of Q, two
+                    // accumulators), filter row 2 runs alone: the first operand is read twice instead of three times
   float* partial;   // [ksplit][9][M][Nn]
   int TH, TW, tiles_h, tiles_w, pix_tiles;
   int m_tiles, n_tiles, ksplit;
@@ -62,7 +64,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
                                              ~static_cast<uintptr_t>(1023));
   const bool merged = p.paired == 2;
   const uint32_t p_boxes = merged ? 3u : 2u;
-  const uint32_t stage_bytes = p_boxes * kPBoxBytes + C::kQBoxes * p.q_box_bytes;
+  const bool rows2 = p.rows2 != 0;
+  const uint32_t q_boxes = rows2 ? 2u : static_cast<uint32_t>(C::kQBoxes);
+  const uint32_t stage_bytes = p_boxes * kPBoxBytes + q_boxes * p.q_box_bytes;
   const int nstages = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nstages * stage_bytes);
   uint64_t* full_bar = bars;
@@ -94,20 +98,38 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   pdl_trigger();
   pdl_wait();
 
-  const int items_per_split = merged ? p.n_tiles : (p.paired ? 2 * p.n_tiles : 3 * p.m_tiles * p.n_tiles);
+  const int items_per_split = merged ? p.n_tiles : (p.paired ? 2 * p.n_tiles : (rows2 ? 2 : 3) * p.m_tiles * p.n_tiles);
+  // item -> (n tile, m tile, filter row or row group r, pixel split ks, g).  rows2: the long items (g = 0: filter rows
+  // 0 + 1) come first, then the short ones (g = 1: row 2), so that a CTA striding over the items gets one of each
+  auto decode = [&](int item, int& nt, int& mt, int& r, int& ks, int& g) {
+    if (rows2) {
+      const int mn = p.m_tiles * p.n_tiles, per_g = mn * p.ksplit;
+      g = item / per_g;
+      const int rem = item - g * per_g;
+      ks = rem / mn;
+      const int t = rem - ks * mn;
+      mt = t / p.n_tiles;
+      nt = t - mt * p.n_tiles;
+      r = g ? 2 : 0;
+    } else {
+      nt = item % p.n_tiles;
+      mt = p.paired ? 0 : (item / p.n_tiles) % p.m_tiles;
+      r = p.paired ? (item / p.n_tiles) % 2 : (item / (p.n_tiles * p.m_tiles)) % 3;
+      ks = item / items_per_split;
+      g = 0;
+    }
+  };
   const int num_items = items_per_split * p.ksplit;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = p_boxes * kPBoxBytes + C::kQBoxes * p.q_tx_bytes;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int nt = item % p.n_tiles;
-        const int mt = p.paired ? 0 : (item / p.n_tiles) % p.m_tiles;
-        // paired: r is the filter-row GROUP g (0: rows 1|0, 1: row 2) and the X row is the k-block's own row
-        const int r = p.paired ? (item / p.n_tiles) % 2 : (item / (p.n_tiles * p.m_tiles)) % 3;
-        const int ks = item / items_per_split;
+        // paired: r is the filter-row GROUP (0: rows 1|0, 1: row 2) and the X row is the k-block's own row
+        int nt, mt, r, ks, g;
+        decode(item, nt, mt, r, ks, g);
+        const uint32_t tx = p_boxes * kPBoxBytes + (rows2 ? (g == 0 ? 2u : 1u) : static_cast<uint32_t>(C::kQBoxes)) * p.q_tx_bytes;
         const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
         const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
         for (int kt = kt0; kt < kt1; ++kt) {
@@ -133,9 +155,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 #pragma unroll
           for (int b = 0; b < 2; ++b)
             tma_load_4d(sp + b * kPBoxBytes, &p.tmP, &full_bar[stage], mt * 128 + b * 64, w0, h0, img);
+          if (rows2) {   // NT == 64: one 64-channel box per halo row; g == 0: rows h0-1 (filter row 0) and h0 (row 1)
+            tma_load_4d(sq, &p.tmQ, &full_bar[stage], nt * NT, w0 - 1, h0 + r - 1, img);
+            if (g == 0) tma_load_4d(sq + p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT, w0 - 1, h0, img);
+          } else {
 #pragma unroll
-          for (int b = 0; b < C::kQBoxes; ++b)
-            tma_load_4d(sq + b * p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT + b * 64, w0 - 1, h0 + r - 1, img);
+            for (int b = 0; b < C::kQBoxes; ++b)
+              tma_load_4d(sq + b * p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT + b * 64, w0 - 1, h0 + r - 1, img);
+          }
           if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -159,7 +186,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       const uint64_t q_desc0 = make_smem_desc(smem_u32(smem) + p_boxes * kPBoxBytes, (NT == 64) ? 128u : p.q_box_bytes, 1024,
                                               kLayoutSW128);
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const int ks = item / items_per_split;
+        int nt_, mt_, r_, ks, g;
+        decode(item, nt_, mt_, r_, ks, g);
+        const bool two_rows = rows2 && g == 0;
         const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
         const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
         mbar_wait_p(issue, tempty_bar, (it & 1) ^ 1u);
@@ -185,6 +214,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
                 umma_bf16_p(issue, tmem_base + 192, da, dq, idesc, (first && k == 0) ? 0u : 1u);
               } else {
                 umma_bf16_p(issue, tmem_base, da, dq, idesc, (first && k == 0) ? 0u : 1u);   // no control flow per MMA
+                if (two_rows)   // uniform per item: the second halo row (filter row 1) against the same first operand
+                  umma_bf16_p(issue, tmem_base + 192, da, desc_advance(dq, p.q_box_bytes), idesc, (first && k == 0) ? 0u : 1u);
               }
             } else {
               constexpr uint32_t idesc = make_idesc_bf16(128, NT, true, true);
@@ -205,16 +236,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     const int row = quarter * 32 + lane;
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const int nt = item % p.n_tiles;
-      const int mt = p.paired ? 0 : (item / p.n_tiles) % p.m_tiles;
-      const int r_item = p.paired ? (item / p.n_tiles) % 2 : (item / (p.n_tiles * p.m_tiles)) % 3;
-      const int ks = item / items_per_split;
+      int nt, mt, r_item, ks, g;
+      decode(item, nt, mt, r_item, ks, g);
       mbar_wait(tfull_bar, it & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int a = 0; a < (merged ? 2 : 1); ++a) {   // merged: accumulator 0 = row group 0, accumulator 1 = group 1
-        int r = merged ? a : r_item;
+      for (int a = 0; a < ((merged || (rows2 && g == 0)) ? 2 : 1); ++a) {
+        // merged: accumulator 0 = row group 0, accumulator 1 = group 1; rows2 (g == 0): accumulator a = filter row a
+        int r = merged ? a : (rows2 && g == 0 ? a : r_item);
         int m = mt * 128 + row;
         if (p.paired) {
           // accumulator rows 0-63 = first dY row of the pair, 64-127 = second: group 0 -> filter rows (1, 0), group 1 -> (2, -)
@@ -260,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 }
 
 struct W3Plan {
-  int NT, TH, TW, tiles_h, tiles_w, pix_tiles, m_tiles, n_tiles, ksplit, paired, stages;
+  int NT, TH, TW, tiles_h, tiles_w, pix_tiles, m_tiles, n_tiles, ksplit, paired, stages, rows2;
   uint32_t q_box_bytes, q_tx_bytes, smem_bytes;
 };
 
@@ -286,9 +316,14 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
   // fabric (3.25 GB through the crossbar per 64 -> 64 launch = 9 TB/s at 60 % tensor-pipe activity,
   // profiles/r01_ncu_top_kernels_v6.txt): one X row + THREE dY rows per k-block (33.8 KB per 768 MMA clocks) instead of
   // one X row + two dY rows per group (2 x 24.6 KB)
-  const int stages = pl->NT == 128 ? 5 : (pl->paired == 2 ? 6 : 7);
+  // rows2: more than 64 rows against <= 64 columns (swapped 128 -> 64, UNet++'s 96..192 -> 32): same fabric bound,
+  // the first operand (16 KB per k-block) was read once per filter row; filter rows 0 and 1 now share it
+  static int rows2_env = -1;
+  if (rows2_env < 0) { const char* e = getenv("UNETK_WGRAD3_ROWS2"); rows2_env = e ? atoi(e) : 1; }
+  pl->rows2 = (rows2_env && !pl->paired && pl->NT == 64 && pl->TW == 64 && pl->TH == 1) ? 1 : 0;
+  const int stages = pl->NT == 128 ? 5 : ((pl->paired == 2 || pl->rows2) ? 6 : 7);
   pl->stages = stages;
-  const uint32_t stage = (pl->paired == 2 ? 3 : 2) * kPBoxBytes + (pl->NT / 64) * pl->q_box_bytes;
+  const uint32_t stage = (pl->paired == 2 ? 3 : 2) * kPBoxBytes + (pl->rows2 ? 2 : pl->NT / 64) * pl->q_box_bytes;
   pl->smem_bytes = stages * stage + 1024 + 256;
   if (pl->smem_bytes > 227 * 1024) return false;
   // items = 3 * m_tiles * n_tiles * ksplit run in waves of num_sms CTAs.  Pick the pixel split that minimises
@@ -298,7 +333,7 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
   // M <= 64 (64-channel dY): half of the 128 MMA rows would be empty (59 % tensor-pipe activity for 30 % useful work,
   // profiles/r01_ncu_wgrad3x3.txt).  With one image row per k-block (TW = 64) the second half is given the NEXT dY row,
   // i.e. another filter row against the same X halo row: 2 work items per pixel range instead of 3.
-  const int base = pl->paired == 2 ? pl->n_tiles : (pl->paired ? 2 * pl->n_tiles : 3 * pl->m_tiles * pl->n_tiles);
+  const int base = pl->paired == 2 ? pl->n_tiles : (pl->paired ? 2 * pl->n_tiles : (pl->rows2 ? 2 : 3) * pl->m_tiles * pl->n_tiles);
   const int cap = pl->pix_tiles / 8 > 0 ? pl->pix_tiles / 8 : 1;
   static int rule = -1;
   if (rule < 0) { const char* e = getenv("UNETK_WGRAD3_RULE"); rule = e ? atoi(e) : 0; }
@@ -329,7 +364,7 @@ int launch(const W3Params& p, const W3Plan& pl, cudaStream_t stream) {
     UNETK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int items = (pl.paired == 2 ? pl.n_tiles : (pl.paired ? 2 * pl.n_tiles : 3 * pl.m_tiles * pl.n_tiles)) * pl.ksplit;
+  const int items = (pl.paired == 2 ? pl.n_tiles : (pl.paired ? 2 * pl.n_tiles : (pl.rows2 ? 2 : 3) * pl.m_tiles * pl.n_tiles)) * pl.ksplit;
   const int grid = items < num_sms() ? items : num_sms();
   UNETK_CUDA(launch_pdl(wgrad3x3_kernel<NT>, dim3(grid), dim3(kThreads), pl.smem_bytes, stream, p));
   UNETK_LAUNCHED();
@@ -364,6 +399,7 @@ int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, flo
   p.q_box_bytes = pl.q_box_bytes; p.q_tx_bytes = pl.q_tx_bytes;
   p.paired = pl.paired;
   p.stages = pl.stages;
+  p.rows2 = pl.rows2;
   auto mk = [&](CUtensorMap* tm, const void* base, int64_t ld, int C, int halo) -> int {
     uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                         static_cast<uint64_t>(N)};
