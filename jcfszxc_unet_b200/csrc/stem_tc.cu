@@ -30,8 +30,6 @@ constexpr int kTile = 128;     // pixels per tile (consecutive along W)
 constexpr int kK = 48;         // padded patch width (>= 9 * Cin for Cin <= 5)
 constexpr int kChunks = kK / 8;
 
-__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
 struct StemTc {
   const float* x; int64_t sn, sc, sh, sw;  // fp32 image, element strides
   int N, H, W, Cin, Cout, tiles_w;
