@@ -137,59 +137,208 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU baseline (the oracle port of the reference step) — also the `--impl reference` arm
+# The reference's own implementation: `--impl reference` (host cores) and `--impl torch_cuda` (cuDNN on the same B200)
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(size: int, batch: int, steps: int, warmup: int, budget_s: float | None = None):
-    """Times oracle.train_step (train.py:255-301 restated, bf16 autocast) on the host cores.
-    Returns (images_per_s, ms_per_step, steps_done, cores)."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+REF_CLASSES = {"UNet": ("UNet", "UNet"), "AttentionUNet": ("AttentionUNet", "AttentionUNet"), "R2UNet": ("R2UNet", "R2UNet"),
+               "ResUNet": ("ResUNet", "ResUNet"), "NestedUNet": ("UNetPP", "NestedUNet")}
+
+
+def _import_reference():
+    """The UNMODIFIED reference modules from baseline/_ref (baseline/install_ref.py), or None when it is not installed.
+    The reference's package is called `UNetFamily`, like this repository's drop-in: a process uses ONE of them, so the
+    repository root leaves sys.path here (the reference arms never touch our package or our kernels)."""
+    import importlib
+    import types
+
     import torch
 
-    from oracle import unet_oracle as O
-    from UNetFamily.UNet import UNet
+    if not os.path.isdir(os.path.join(REF_DIR, "UNetFamily")):
+        return None
+    if "UNetFamily" in sys.modules and not getattr(sys.modules["UNetFamily"], "__path__", [""])[0].startswith(REF_DIR):
+        raise RuntimeError("the reference arm must not share a process with this repository's UNetFamily package")
+    sys.dont_write_bytecode = True
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != ROOT]
+    _t, _l = types.ModuleType("timm"), types.ModuleType("timm.layers")     # SURVEY.md Appendix A: unet_parts.py:14
+    _l.trunc_normal_ = torch.nn.init.trunc_normal_
+    _t.layers = _l
+    sys.modules.setdefault("timm", _t)
+    sys.modules.setdefault("timm.layers", _l)
+    sys.path.insert(0, REF_DIR)
+    mods = {name: importlib.import_module(f"UNetFamily.{mod}") for name, (mod, _) in REF_CLASSES.items()}
+    dice = importlib.import_module("utils.dice_score")
+    return mods, dice
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+
+def make_reference_step(model_name: str, device, size: int, batch: int):
+    """One iteration of train.py:255-301 around the reference's own modules (bf16 autocast as BASELINE.json asks;
+    GradScaler is a no-op for bf16; the NaN probes and loss.item() of the reference loop — host syncs — are left out,
+    which only helps the baseline).  Returns (kind, step_fn): kind "reference" = the unmodified modules from
+    baseline/_ref, "port" = oracle/unet_oracle.py's pinned functional restatement when baseline/_ref is absent."""
+    import torch
+
+    ref = _import_reference()
     torch.manual_seed(SEED)
-    model = UNet(3, 1)
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    names = O.param_names(sd)
-    opt_state = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in names}
     g = torch.Generator().manual_seed(SEED)
-    images = torch.rand(batch, 3, size, size, generator=g).contiguous(memory_format=torch.channels_last)
+    images = torch.rand(batch, 3, size, size, generator=g)
     labels = (torch.rand(batch, 1, size, size, generator=g) < LABEL_DENSITY).float()
-    for _ in range(warmup):
-        O.train_step(sd, opt_state, images, labels, 1e-6, bf16=True)
-    t0 = time.perf_counter()
-    done = 0
-    for _ in range(steps):
-        O.train_step(sd, opt_state, images, labels, 1e-6, bf16=True)
-        done += 1
-        if budget_s is not None and time.perf_counter() - t0 > budget_s:
-            break
-    dt = time.perf_counter() - t0
-    return batch * done / dt, 1e3 * dt / done, done, torch.get_num_threads()
+    images = images.to(device=device, dtype=torch.float32, memory_format=torch.channels_last)   # train.py:248-253
+    labels = labels.to(device=device, dtype=torch.float32)
+    dt = torch.device(device).type
+    if ref is not None:
+        mods, dice = ref
+        mod, cls = REF_CLASSES[model_name]
+        model = getattr(mods[model_name], cls)().to(device=device, memory_format=torch.channels_last).train()  # train.py:523-525
+        opt = torch.optim.RMSprop(model.parameters(), lr=1e-6, weight_decay=1e-8, momentum=0.999)             # train.py:107-112
+        criterion = torch.nn.BCEWithLogitsLoss()                                                             # train.py:124
+
+        def step():
+            with torch.autocast(dt, dtype=torch.bfloat16):
+                masks_pred = model(images)
+                masks_pred_sigmoid = torch.sigmoid(masks_pred)
+                bce_loss = criterion(masks_pred, labels)
+                d = dice.dice_loss(masks_pred_sigmoid.squeeze(1), labels.squeeze(1), multiclass=False)
+                loss = 0.5 * bce_loss + 0.5 * d
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            return loss
+
+        return "reference", step
+    from oracle import unet_oracle as O
+
+    model, _ = make_model(model_name)
+    sd = {k: v.detach().clone().to(device) for k, v in model.state_dict().items()}
+    names = O.param_names(sd)
+    for k in names:
+        if sd[k].dim() == 4:
+            sd[k] = sd[k].contiguous(memory_format=torch.channels_last)
+        sd[k].requires_grad_(True)
+    params = [sd[k] for k in names]
+    opt = torch.optim.RMSprop(params, lr=1e-6, weight_decay=1e-8, momentum=0.999)
+
+    def step():
+        _, loss, _, _ = O.forward_loss(sd, images, labels, bf16=True, training=True, model=model_name)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    return "port", step
 
 
 def run_reference_arm(args):
+    """The reference's CPU implementation of the step on the box's host cores, all threads, a bounded sample per step."""
+    import torch
+
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    batch = 2
-    ips, ms, done, cores = cpu_reference_step_rate(args.size, batch, args.steps, max(1, args.warmup))
-    sample = (f"oracle port of train.py:255-301 (bf16 autocast, reference modules' arithmetic via torch.nn.functional), "
-              f"batch {batch} of 3x{args.size}x{args.size} per step, {done} timed steps, {cores} host threads")
+    batch = args.ref_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind, step = make_reference_step(args.model, "cpu", args.size, batch)
+    warm = max(1, args.warmup) if args.budget is None else 1
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        step()
+        done += 1
+        if args.budget is not None and time.perf_counter() - t0 > args.budget:
+            break
+    dt = time.perf_counter() - t0
+    ips, ms = batch * done / dt, 1e3 * dt / done
+    threads = torch.get_num_threads()
+    what = ("UNMODIFIED reference modules (baseline/_ref) in the loop body of train.py:255-301" if kind == "reference" else
+            "oracle port of train.py:255-301 (the reference modules' arithmetic via torch.nn.functional)")
+    sample = (f"{what}, bf16 autocast, {args.model}, batch {batch} of 3x{args.size}x{args.size} per step, "
+              f"{warm} warm-up + {done} timed steps, {threads} host threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-        "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"vanilla UNet(3,1) bf16 training step (BCE+dice, clip 1.0, RMSprop), 3x{args.size}x{args.size} synthetic; "
-                               f"CPU arm runs a bounded sample: batch {batch} per step", "sample_batch": batch},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"{_workload(args.model, args.size)}; CPU arm runs a bounded sample: batch {batch} per step",
+                   "sample_batch": batch},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=_OUT, flush=True)
     return 0
+
+
+def run_torch_cuda_arm(args):
+    """Stock PyTorch on the SAME B200: the reference's real GPU path (train.py:248-256,525: channels_last + autocast, cuDNN
+    underneath), same model / batch / seeds / step definition as our arm; timed with cudnn.benchmark off + deterministic
+    (what the reference sets, utils/utils.py:30-31) and on (the strongest stock setting).  `value` is the faster one."""
+    import torch
+
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "torch_cuda", "unavailable": "no CUDA device"}), file=_OUT, flush=True)
+        return 0
+    dev = torch.device("cuda", args.device_index)
+    torch.cuda.set_device(dev)
+    B, S, K, W = args.batch, args.size, args.steps, max(3, args.warmup)
+    out = {}
+    kind = None
+    settings = (("cudnn_benchmark_on", True),) if args.cudnn_on_only else (("cudnn_reference_settings", False), ("cudnn_benchmark_on", True))
+    for label, bench_on in settings:
+        torch.backends.cudnn.benchmark = bench_on
+        torch.backends.cudnn.deterministic = not bench_on
+        kind, step = make_reference_step(args.model, dev, S, B)
+        for _ in range(W):
+            step()
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(K):
+            loss = step()
+        end.record()
+        torch.cuda.synchronize()
+        ms = start.elapsed_time(end) / K
+        out[label] = {"images_per_s": B * 1e3 / ms, "ms_per_step": ms, "loss": float(loss),
+                      "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30}
+        del step
+        torch.cuda.empty_cache()
+    best = max(out.values(), key=lambda v: v["images_per_s"])
+    line = {
+        "impl": "torch_cuda", "metric": METRIC, "value": best["images_per_s"], "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": _workload(args.model, S), "per_gpu_batch": B, "image": f"3x{S}x{S}"},
+        "kind": ("UNMODIFIED reference modules (baseline/_ref)" if kind == "reference" else "oracle port (torch.nn.functional)")
+                + f", stock torch {torch.__version__} + cuDNN {torch.backends.cudnn.version()}, channels_last, bf16 autocast, "
+                  "torch.optim.RMSprop + clip_grad_norm_, no host sync inside a step",
+        "settings": out,
+    }
+    print(json.dumps(line), file=_OUT, flush=True)
+    return 0
+
+
+def _workload(model: str, size: int) -> str:
+    if model == "UNet":
+        return f"vanilla UNet(n_channels=3, n_classes=1) bf16 training step (BCE+dice, clip 1.0, RMSprop), 3x{size}x{size} synthetic"
+    return f"{model} bf16 training step (BCE+dice, clip 1.0, RMSprop), 3x{size}x{size} synthetic"
+
+
+def _child_json(argv, timeout):
+    """Run another arm of this file in a child process (the reference arms must not share a process with our package)
+    and parse its single JSON line; a failure is reported, never hidden."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), *argv], capture_output=True, text=True, timeout=timeout,
+                           cwd=ROOT, env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"timed out after {timeout}s"}
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"unavailable": (r.stderr.strip().splitlines() or ["no output"])[-1][:300]}
+    return json.loads(lines[-1])
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -239,33 +388,28 @@ def kernel_breakdown(records):
     return fam
 
 
-def run_ours(args):
+def _free_cuda():
+    import gc
+
+    import torch
+
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def measure_ours(model_name, B, S, K, W, dev, dp, world, rank, local_rank, graph=True, detail=True, e2e=True):
+    """Build the model + Trainer, warm up, and time K steps of our arm.  Returns a dict of raw measurements (every rank)."""
     import torch
     import torch.distributed as dist
 
     from jcfszxc_unet_b200 import _lib
-    from jcfszxc_unet_b200.dp import DataParallel
     from jcfszxc_unet_b200.trainer import Trainer
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (our arm) needs a CUDA device: the U-Net hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    B, S = args.batch, args.size
-    W, K = max(3, args.warmup), args.steps
-
     torch.manual_seed(SEED)
-    model, builder = make_model(args.model)
+    model, builder = make_model(model_name)
     model = model.to(dev).train()
-    dp = DataParallel()
-    tr = Trainer(model, lr=1e-6, use_cuda_graph=not args.no_graph, dp=dp, builder=builder)   # lr: reference default train.py:434
+    tr = Trainer(model, lr=1e-6, use_cuda_graph=graph, dp=dp, builder=builder)   # lr: reference default train.py:434
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
     images = torch.rand(B, 3, S, S, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
     labels = (torch.rand(B, 1, S, S, device=dev, generator=g) < LABEL_DENSITY).float()
@@ -279,7 +423,7 @@ def run_ours(args):
     for _ in range(W):
         tr.step(images, labels)
     torch.cuda.synchronize()
-    launches_before = lib.unetk_launch_count()
+    out = {"trainer": tr}
 
     # ---- per-kernel timing + launch count: one EAGER step, every C-ABI call bracketed by CUDA events --
     graphs, use_graph, tr.graphs, tr.use_graph = tr.graphs, tr.use_graph, None, False
@@ -287,9 +431,9 @@ def run_ours(args):
     with _lib.profile_calls() as prof:
         c0 = lib.unetk_launch_count()
         tr.step(images, labels)
-        launches_per_step = lib.unetk_launch_count() - c0
+        out["launches_per_step"] = lib.unetk_launch_count() - c0
     torch.cuda.synchronize()
-    fam = kernel_breakdown(prof.records)
+    out["families"] = kernel_breakdown(prof.records) if detail else None
     tr.plan.overlap_wgrad = overlap
     tr.graphs, tr.use_graph = graphs, use_graph
     tr.step(images, labels)
@@ -304,9 +448,11 @@ def run_ours(args):
         tr.step(images, labels)
     end.record()
     barrier()
-    ms_total = dp.max_over_ranks(start.elapsed_time(end), dev)
-    clocks = sampler.stop() if sampler else None
-    loss_final = float(tr.loss_terms()[0])
+    out["ms_total"] = dp.max_over_ranks(start.elapsed_time(end), dev)
+    out["clocks"] = sampler.stop() if sampler else None
+    out["loss"] = float(tr.loss_terms()[0])
+    if not e2e:
+        return out
 
     # ---- end to end: host (pinned) inputs copied in every step, loss read back every step --------------
     h_images = torch.empty((B, S, S, 3), dtype=torch.float32, pin_memory=True).permute(0, 3, 1, 2)  # channels_last, pinned
@@ -331,14 +477,76 @@ def run_ours(args):
         loss_host = float(loss_dev)                        # D2H read of the step's result: synchronises every step
     end.record()
     barrier()
-    e2e_ms = dp.max_over_ranks(start.elapsed_time(end), dev)
-    h2d = h_images.numel() * 4 + h_labels.numel() * 4
+    out["e2e_ms"] = dp.max_over_ranks(start.elapsed_time(end), dev)
+    out["e2e_steps"] = e2e_steps
+    out["h2d"] = h_images.numel() * 4 + h_labels.numel() * 4
+    out["loss_e2e"] = loss_host
+    return out
+
+
+def replicas_in_sync(tr, dp, dev):
+    """Data parallel: every rank's parameters must be bit-identical after the timed steps (same reduced gradients, same
+    optimizer arithmetic).  Compares an integer checksum of the flat fp32 parameter buffer across ranks."""
+    import torch
+    import torch.distributed as dist
+
+    bits = tr.flat_p.view(torch.int32).to(torch.int64)
+    mine = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=dev) % 65521 + 1)).sum()])
+    if not dp.enabled:
+        return True
+    all_ = [torch.zeros_like(mine) for _ in range(dp.world)]
+    dist.all_gather(all_, mine)
+    return all(bool(torch.equal(a, all_[0])) for a in all_)
+
+
+# BASELINE.json configs[2..4] at their per-GPU batches on the 8-GPU box they are quoted on
+VARIANTS = (("AttentionUNet", 16, 512), ("R2UNet", 8, 512), ("ResUNet", 8, 512), ("NestedUNet", 4, 1024))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from jcfszxc_unet_b200 import _lib
+    from jcfszxc_unet_b200.dp import DataParallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: the U-Net hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    S = args.size
+    strong = args.scaling == "strong"
+    if strong:
+        gb = args.global_batch or args.batch
+        if gb % world:
+            raise ValueError(f"--global-batch {gb} is not divisible by {world} ranks")
+        B = gb // world
+    else:
+        B = args.batch
+    W, K = max(3, args.warmup), args.steps
+    dp = DataParallel()
+    m = measure_ours(args.model, B, S, K, W, dev, dp, world, rank, local_rank, graph=not args.no_graph)
+    tr = m.pop("trainer")
+    in_sync = replicas_in_sync(tr, dp, dev) if world > 1 else None
+    buckets = getattr(tr, "bucket_report", lambda: None)()
+    del tr
+    _free_cuda()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
+    fam = m["families"]
+    ms_total, e2e_ms, e2e_steps = m["ms_total"], m["e2e_ms"], m["e2e_steps"]
+    launches_per_step = m["launches_per_step"]
     ms_per_step = ms_total / K
     value = world * B * K / (ms_total / 1e3)
     e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
@@ -366,36 +574,73 @@ def run_ours(args):
                          **({"tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)} if v["flops"] else {})}
                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
     }
+    solo = world == 1
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and args.model == "UNet":
-        ips, ms, done, cores = cpu_reference_step_rate(S, 2, 3, 1, budget_s=25.0)
-        cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"oracle port of train.py:255-301 (bf16 autocast) on the host, batch 2 of 3x{S}x{S}, 1 warm-up + {done} timed steps"}
+    if solo and not args.no_cpu_baseline and args.model == "UNet":
+        # the reference's CPU implementation on this box's host cores: a child process (it imports the reference's own
+        # `UNetFamily` package, which cannot share an interpreter with ours), bounded to ~25 s of CPU work
+        d = _child_json(["--impl", "reference", "--steps", "3", "--warmup", "1", "--budget", "25", "--size", str(S)], 400)
+        cpu = d.get("cpu_baseline") or {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": d.get("unavailable")}
+    gpu_base = None
+    if solo and not args.no_gpu_baseline:
+        # stock PyTorch (cuDNN, channels_last, bf16 autocast) running the reference's modules on this same B200
+        d = _child_json(["--impl", "torch_cuda", "--model", args.model, "--batch", str(B), "--size", str(S), "--steps", "10",
+                         "--warmup", "3", "--device-index", str(local_rank)], 600)
+        gpu_base = _gpu_baseline_block(d, value)
+    variants = None
+    if solo and args.variants and args.model == "UNet" and not strong:
+        variants = {}
+        for name, vb, vs in VARIANTS:
+            try:
+                vm = measure_ours(name, vb, vs, 5, 3, dev, dp, 1, 0, local_rank, graph=True, detail=False, e2e=False)
+                vm.pop("trainer")
+                _free_cuda()
+                ips = vb * 5 / (vm["ms_total"] / 1e3)
+                gf = train_gflop_per_image(name, vs)
+                slot = {"per_gpu_batch": vb, "image": f"3x{vs}x{vs}", "value": ips, "unit": UNIT, "ms_per_step": vm["ms_total"] / 5,
+                        "steps": 5, "warmup": 3, "whole_step_frac": ips * gf / 1e3 / peaks["bf16_tflops_sustained"],
+                        "gflop_per_image": gf, "launches_per_step": int(vm["launches_per_step"]), "loss": vm["loss"]}
+                if not args.no_gpu_baseline:
+                    d = _child_json(["--impl", "torch_cuda", "--model", name, "--batch", str(vb), "--size", str(vs), "--steps", "5",
+                                     "--warmup", "3", "--cudnn-on-only", "--device-index", str(local_rank)], 600)
+                    slot["gpu_baseline"] = _gpu_baseline_block(d, ips)
+                variants[name] = slot
+            except Exception as e:  # a variant that fails is reported as such, the headline line still prints
+                variants[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                _free_cuda()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": (f"vanilla UNet(n_channels=3, n_classes=1) bf16 training step (BCE+dice, clip 1.0, RMSprop), "
-                                f"batch {B} per GPU, 3x{S}x{S} synthetic (BASELINE.json configs[1])") if args.model == "UNet" else
-                               (f"{args.model} bf16 training step (BCE+dice, clip 1.0, RMSprop), batch {B} per GPU, "
-                                f"3x{S}x{S} synthetic"),
+        "config": {"workload": _workload(args.model, S) + f", batch {B} per GPU" + (" (BASELINE.json configs[1])" if args.model == "UNet" and B == 16 and S == 512 else ""),
                    "per_gpu_batch": B, "global_batch": B * world, "image": f"3x{S}x{S}", "parallelism": f"dp{world}",
                    "batchnorm": "per-rank batch statistics" if world > 1 else "batch statistics",
                    "cuda_graph": not args.no_graph,
                    "l2": "no explicit flush: every step streams ~17 GB of activations/gradients, far beyond the 126 MB L2"},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+        "clocks": m["clocks"],
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4, "steps": e2e_steps,
                 "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": int(launches_per_step * K),
         "launches_per_step": int(launches_per_step),
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "loss": loss_final, "loss_e2e": loss_host,
+        "gpu_baseline": gpu_base,
+        "variants": variants,
+        "replicas_in_sync": in_sync,
+        "grad_buckets": buckets,
+        "loss": m["loss"], "loss_e2e": m["loss_e2e"],
     }
     print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _gpu_baseline_block(d, ours_value):
+    if "unavailable" in d or "value" not in d:
+        return {"value": None, "unit": UNIT, "unavailable": d.get("unavailable", "no result")}
+    return {"value": d["value"], "unit": UNIT, "ms_per_step": d["ms_per_step"], "kind": d["kind"], "settings": d["settings"],
+            "steps": d["steps"], "warmup": d["warmup"], "ours_over_stock": ours_value / d["value"]}
 
 
 _OUT = sys.stdout
@@ -416,15 +661,27 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_cuda"])
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE.json configs[1]: 16)")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--model", default="UNet", choices=sorted(MODELS), help="default: the headline config (vanilla UNet)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch-CUDA (cuDNN) leg")
+    ap.add_argument("--no-variants", dest="variants", action="store_false",
+                    help="skip the short runs of BASELINE.json configs[2..4] (AttentionUNet, R2UNet, ResUNet, NestedUNet)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: --global-batch is split over the ranks (BASELINE.json configs[2]: AttentionUNet, 16)")
+    ap.add_argument("--global-batch", type=int, default=None)
+    ap.add_argument("--ref-batch", type=int, default=2, help="reference CPU arm: images per step of its bounded sample")
+    ap.add_argument("--budget", type=float, default=None, help="reference CPU arm: stop after this many seconds")
+    ap.add_argument("--device-index", type=int, default=0)
+    ap.add_argument("--cudnn-on-only", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.impl == "torch_cuda":
+        return run_torch_cuda_arm(args)
     return run_ours(args)
 
 

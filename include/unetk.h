@@ -256,6 +256,11 @@ int unetk_grad_clip_coef(const float* g, int64_t n, float gscale, float max_norm
 int unetk_rmsprop_step(float* p, const float* g, float* square_avg, float* momentum_buf, int64_t n, float lr,
                        float alpha, float eps, float weight_decay, float momentum, const float* clip,
                        void* stream);
+/* rmsprop_step_dev: the same update with hyper = {lr, alpha, eps, weight_decay, momentum} (5 floats) read from
+ *                 DEVICE memory at run time: a captured CUDA graph follows optimizer.param_groups[0]["lr"] changes
+ *                 (the reference's ReduceLROnPlateau, train.py:114-122,355).  momentum_buf must not be NULL. */
+int unetk_rmsprop_step_dev(float* p, const float* g, float* square_avg, float* momentum_buf, int64_t n,
+                           const float* hyper, const float* clip, void* stream);
 
 /* ---- glue of the U-Net variants (bf16 NHWC views, C multiple of 8) ---------------------------------
  * add_n: dst = [dst +] a [+ b [+ c [+ d]]] with every partial sum rounded to bf16 (a chain of bf16 tensor adds:

@@ -24,3 +24,10 @@ def precision(mode: str):
         yield
     finally:
         _precision = prev
+
+
+def clear_plans(module) -> None:
+    """Free the cached execution plans (activation / gradient buffers) of `module` and its sub-modules."""
+    from .bridge import clear_plans as _clear
+
+    _clear(module)

@@ -76,6 +76,7 @@ SIGNATURES = {
     "unetk_sqnorm_partial_floats": (_sz, [_i64]),
     "unetk_grad_clip_coef": (_i, [_fp, _i64, _f, _f, _fp, _fp, _vp]),
     "unetk_rmsprop_step": (_i, [_fp, _fp, _fp, _fp, _i64, _f, _f, _f, _f, _f, _fp, _vp]),
+    "unetk_rmsprop_step_dev": (_i, [_fp, _fp, _fp, _fp, _i64, _fp, _fp, _vp]),
     "unetk_add_n": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp]),
     "unetk_upsample_nearest2x_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
     "unetk_upsample_nearest2x_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),

@@ -56,7 +56,7 @@ class _BlockFunction(torch.autograd.Function):
                 gin.append(None)
             else:
                 gin.append(bp.inputs[i].g.permute(0, 3, 1, 2).to(ctx.in_dtypes[i]))
-        grads = tuple(g.clone() if p.requires_grad else None for p, g in zip(plan.params, plan.grads()))
+        grads = tuple(g if p.requires_grad else None for p, g in zip(plan.params, plan.grads()))
         return (None, None) + tuple(gin) + grads
 
 
@@ -66,11 +66,10 @@ def _run(module, key_extra, build, xs):
     need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in module.parameters()) or
                                              any(x.requires_grad for x in xs))
     key = (tuple(tuple(x.shape) for x in xs), xs[0].device.index, module.training, need_grad, key_extra)
-    cache = module.__dict__.setdefault("_unetk_plans", {})
-    bp = cache.get(key)
+    cache = bridge.plan_cache(module)
+    bp = cache.lookup(key)
     if bp is None:
-        bp = build(module.training, need_grad)
-        cache[key] = bp
+        bp = cache.insert(key, build(module.training, need_grad))
     if need_grad:
         return _BlockFunction.apply(bp, len(xs), *xs, *bp.plan.params)
     with torch.no_grad():

@@ -3,9 +3,65 @@ whole-network plan differentiable, so `model(x)` is a drop-in for the reference 
 (train.py:256, evaluate.py:259-275 in the reference) while every FLOP runs in libunetk.so."""
 from __future__ import annotations
 
+import collections
+import os
+
 import torch
 
 from . import _lib
+
+
+class PlanCache(collections.OrderedDict):
+    """Per-module LRU of execution plans, keyed by (shape, device, mode).
+
+    It lives in the module's `__dict__` (so it dies with the module: plans hold references to the module's parameters)
+    but never travels: `torch.save(model)` — the reference's checkpoint format, train.py:374 — and `copy.deepcopy` see an
+    EMPTY builtin dict in its place.  A plan owns CUDA streams (not picklable), every activation / gradient buffer of
+    its shape (GBs) and tables keyed by id(parameter) (meaningless in another process); and a pickle that named a class
+    of this package could not be loaded by the reference.  At most UNETK_PLAN_CACHE (default 4) plans are kept per
+    module; the least recently used one is dropped (ragged last chunks of predict_full_image, the full-validation-set
+    batch, varying batch sizes)."""
+
+    LIMIT = max(1, int(os.environ.get("UNETK_PLAN_CACHE", "4")))
+
+    def __reduce__(self):
+        return (dict, ())
+
+    def __reduce_ex__(self, protocol):
+        return (dict, ())
+
+    def __deepcopy__(self, memo):
+        return {}
+
+    def __copy__(self):
+        return {}
+
+    def lookup(self, key):
+        plan = self.get(key)
+        if plan is not None:
+            self.move_to_end(key)
+        return plan
+
+    def insert(self, key, plan):
+        self[key] = plan
+        while len(self) > self.LIMIT:
+            self.popitem(last=False)
+        return plan
+
+
+def plan_cache(module: torch.nn.Module) -> PlanCache:
+    cache = module.__dict__.get("_unetk_plans")
+    if not isinstance(cache, PlanCache):     # first use, or a plain dict left by unpickling / deepcopy
+        cache = module.__dict__["_unetk_plans"] = PlanCache()
+    return cache
+
+
+def clear_plans(module: torch.nn.Module) -> None:
+    """Drop every cached plan (and its activation / gradient buffers) of `module` and of its sub-modules."""
+    for m in module.modules():
+        c = m.__dict__.get("_unetk_plans")
+        if c:
+            c.clear()
 
 
 class _PlanFunction(torch.autograd.Function):
@@ -32,7 +88,9 @@ class _PlanFunction(torch.autograd.Function):
         plan.head.gscale = 1.0
         plan.backward()
         plan.head.dlogits = None
-        grads = tuple(g.clone() if p.requires_grad else None for p, g in zip(plan.params, plan.grads()))
+        # views of the plan's gradient buffers: autograd's AccumulateGrad copies them into .grad (it cannot steal a
+        # tensor the plan still references), so no second copy is made here
+        grads = tuple(g if p.requires_grad else None for p, g in zip(plan.params, plan.grads()))
         return (None, None) + grads
 
 
@@ -60,12 +118,15 @@ def run_model(model: torch.nn.Module, builder, x: torch.Tensor) -> torch.Tensor:
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
     training_stats = model.training
     key = (n, h, w, x.device.index, training_stats, need_grad)
-    plans = model.__dict__.setdefault("_unetk_plans", {})
-    plan = plans.get(key)
+    if need_grad and x.requires_grad:
+        raise NotImplementedError(
+            f"{type(model).__name__}: the input requires grad, but the fused plan does not produce d(loss)/d(image) "
+            "(the stem's input gradient is not on the training path, train.py:255-301); detach the input")
+    plans = plan_cache(model)
+    plan = plans.lookup(key)
     if plan is None:
         # a plan with gradient buffers only when a backward can follow; BN mode follows model.training
-        plan = builder(model, n, h, w, x.device, training_stats, None, need_grad)
-        plans[key] = plan
+        plan = plans.insert(key, builder(model, n, h, w, x.device, training_stats, None, need_grad))
     if need_grad:
         return _PlanFunction.apply(plan, x, *plan.params)
     with torch.no_grad():

@@ -437,7 +437,12 @@ int unetk_grad_clip_coef(const float* g, int64_t n, float gscale, float max_norm
 int unetk_rmsprop_step(float* p, const float* g, float* square_avg, float* momentum_buf, int64_t n, float lr,
                        float alpha, float eps, float weight_decay, float momentum, const float* clip, void* stream) {
   UNETK_CHECK(p && g && square_avg && n > 0 && (momentum <= 0.f || momentum_buf), -1, "rmsprop_step: bad arguments");
-  return rmsprop_run(p, g, square_avg, momentum_buf, n, lr, alpha, eps, weight_decay, momentum, clip, S(stream));
+  return rmsprop_run(p, g, square_avg, momentum_buf, n, lr, alpha, eps, weight_decay, momentum, clip, nullptr, S(stream));
+}
+int unetk_rmsprop_step_dev(float* p, const float* g, float* square_avg, float* momentum_buf, int64_t n,
+                           const float* hyper, const float* clip, void* stream) {
+  UNETK_CHECK(p && g && square_avg && momentum_buf && hyper && n > 0, -1, "rmsprop_step_dev: bad arguments");
+  return rmsprop_run(p, g, square_avg, momentum_buf, n, 0.f, 0.f, 0.f, 0.f, 1.f, clip, hyper, S(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ variants glue

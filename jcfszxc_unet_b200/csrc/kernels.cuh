@@ -75,7 +75,7 @@ int sqnorm_blocks(int64_t n);
 int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, float* partial, float* out,
                        cudaStream_t s);
 int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, float lr, float alpha, float eps, float wd,
-                float momentum, const float* clip, cudaStream_t s);
+                float momentum, const float* clip, const float* hyper, cudaStream_t s);
 int probe_mma_rate_run(int N, int grid, int a_shift_rows, int two_acc, int iters, int b_tiles, long long* out,
                        cudaStream_t stream);
 // pack.cu

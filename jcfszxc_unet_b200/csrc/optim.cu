@@ -75,9 +75,13 @@ __device__ __forceinline__ void rmsprop_one(float& pv, float gv0, float& sqv, fl
 // 16-byte vectors, two per thread and array in flight (the scalar version below ran at 72 % of the HBM peak)
 __global__ void __launch_bounds__(kThreads)
 rmsprop4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ sq, float4* __restrict__ buf,
-                int64_t n4, float lr, float alpha, float eps, float wd, float momentum, const float* __restrict__ clip) {
+                int64_t n4, float lr, float alpha, float eps, float wd, float momentum, const float* __restrict__ clip,
+                const float* __restrict__ hyper) {
   pdl_trigger();
   pdl_wait();
+  // hyper != NULL: {lr, alpha, eps, weight_decay, momentum} live in device memory, so a CUDA graph that captured this
+  // launch follows later changes of the learning rate (ReduceLROnPlateau in the reference loop, train.py:114-122,355)
+  if (hyper) { lr = __ldg(hyper); alpha = __ldg(hyper + 1); eps = __ldg(hyper + 2); wd = __ldg(hyper + 3); momentum = __ldg(hyper + 4); }
   const float coef = clip ? __ldg(clip + 1) : 1.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < n4; i += 2 * stride) {
@@ -103,9 +107,10 @@ rmsprop4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __
 __global__ void __launch_bounds__(kThreads)
 rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq, float* __restrict__ buf,
                int64_t n, float lr, float alpha, float eps, float wd, float momentum,
-               const float* __restrict__ clip) {
+               const float* __restrict__ clip, const float* __restrict__ hyper) {
   pdl_trigger();
   pdl_wait();
+  if (hyper) { lr = __ldg(hyper); alpha = __ldg(hyper + 1); eps = __ldg(hyper + 2); wd = __ldg(hyper + 3); momentum = __ldg(hyper + 4); }
   const float coef = clip ? __ldg(clip + 1) : 1.f;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * kThreads) {
@@ -146,7 +151,7 @@ int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, 
 }
 
 int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, float lr, float alpha, float eps, float wd,
-                float momentum, const float* clip, cudaStream_t s) {
+                float momentum, const float* clip, const float* hyper, cudaStream_t s) {
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(sq) |
                          reinterpret_cast<uintptr_t>(buf)) & 15) == 0;
@@ -156,7 +161,7 @@ int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, floa
     if (b > cap) b = cap;
     UNETK_CUDA(launch_pdl(rmsprop4_kernel, dim3(static_cast<int>(b)), dim3(kThreads), 0, s, reinterpret_cast<float4*>(p),
                           reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(sq), reinterpret_cast<float4*>(buf), n4,
-                          lr, alpha, eps, wd, momentum, clip));
+                          lr, alpha, eps, wd, momentum, clip, hyper));
     UNETK_LAUNCHED();
   }
   const int64_t done = n4 * 4, rest = n - done;   // tail (or everything, for unaligned buffers): scalar kernel
@@ -165,7 +170,7 @@ int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, floa
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     UNETK_CUDA(launch_pdl(rmsprop_kernel, dim3(static_cast<int>(b)), dim3(kThreads), 0, s, p + done, g + done, sq + done,
-                          buf + done, rest, lr, alpha, eps, wd, momentum, clip));
+                          buf + done, rest, lr, alpha, eps, wd, momentum, clip, hyper));
     UNETK_LAUNCHED();
   }
   return 0;

@@ -20,8 +20,11 @@ import torch.distributed as dist
 
 
 class DataParallel:
-    def __init__(self, group=None, sync_bn: bool = False, sync_loss: bool = True):
+    def __init__(self, group=None, sync_bn: bool = False, sync_loss: bool = True, enabled: bool | None = None):
+        """enabled=False: a single-process instance inside an initialised process group (reference runs in tests)."""
         self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if enabled is not None:
+            self.enabled = self.enabled and enabled
         self.group = group
         self.world = dist.get_world_size(group) if self.enabled else 1
         self.rank = dist.get_rank(group) if self.enabled else 0

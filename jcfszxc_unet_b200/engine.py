@@ -196,12 +196,29 @@ class Plan:
         for op in self.ops:
             op.fwd()
 
-    def backward(self, lo: int = 0, hi: int | None = None):
-        """Backward of ops[lo:hi] in reverse order (the whole plan by default)."""
+    def backward(self, lo: int = 0, hi: int | None = None, join: bool = True):
+        """Backward of ops[lo:hi] in reverse order (the whole plan by default).  join=False leaves the weight-gradient
+        side stream un-joined (a later segment, or behind_both_streams(), picks it up)."""
         ops_ = self.ops[lo:hi]
         for op in reversed(ops_):
             op.bwd()
-        self.join_side()
+        if join:
+            self.join_side()
+
+    @contextlib.contextmanager
+    def behind_both_streams(self):
+        """Run the enclosed launches (gradient all-reduces) ordered after everything enqueued so far on the main
+        stream AND on the weight-gradient side stream, without stalling the main stream: they are issued from the side
+        stream once it has waited for the main stream's current position."""
+        if self._side is None or not self._side_dirty:
+            yield
+            return
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            yield
 
     @contextlib.contextmanager
     def wgrad_stream(self):
@@ -248,6 +265,29 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
+def weight_stamp(w) -> tuple:
+    """(torch version counter, library generation) of a master weight.  torch bumps `_version` on in-place torch ops
+    (optimizer.step(), load_state_dict, init); kernels of this library that update parameters through raw pointers
+    (Trainer's fused RMSprop, also inside CUDA-graph replays) cannot, so the Trainer that owns a parameter attaches a
+    shared generation counter to it (`_unetk_gen`, bumped once per step) and every derived cache — bf16 weight packs
+    of ANY plan of the model, fp32-mode splits, the embedded 1x1 stem kernel — compares both."""
+    h = getattr(w, "_unetk_gen", None)
+    return (w._version, h[0] if h is not None else 0)
+
+
+def bn_momentum(bn, training: bool) -> float:
+    """nn.BatchNorm2d's exponential_average_factor: `momentum`, or — momentum=None — the cumulative moving average
+    1 / num_batches_tracked (counted AFTER this forward's increment, torch/nn/modules/batchnorm.py).  The cumulative
+    factor needs the host value of the counter: one sync per BatchNorm, and not capturable into a CUDA graph."""
+    if bn.momentum is not None:
+        return float(bn.momentum)
+    if not (training and bn.track_running_stats):
+        return 0.0
+    if torch.cuda.is_current_stream_capturing():
+        raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative average) cannot run inside a CUDA graph")
+    return 1.0 / float(int(bn.num_batches_tracked) + 1)
+
+
 class WeightPack:
     """bf16 kernel-layout copies of one fp32 master weight [A,B,kh,kw]: ab = [T][A][B], ba = [T][B][A].
     A derived cache: re-packed when the master changes, shared by all ops using the weight."""
@@ -258,13 +298,13 @@ class WeightPack:
         self.w, self.a, self.b, self.taps = weight, a, b, taps
         self.ab = torch.empty((taps, a, b), dtype=BF16, device=weight.device)
         self.ba = torch.empty((taps, b, a), dtype=BF16, device=weight.device)
-        self._ver = -1
+        self._stamp = None
 
     def stale(self):
-        return self.w._version != self._ver
+        return weight_stamp(self.w) != self._stamp
 
     def mark_fresh(self):
-        self._ver = self.w._version
+        self._stamp = weight_stamp(self.w)
 
 
 class ConvBNReLU:
@@ -303,7 +343,7 @@ class ConvBNReLU:
         if self.stem and k == 1:
             self.w3 = torch.zeros((self.cout, self.cin, 3, 3), dtype=torch.float32, device=plan.device)
             self.dw3 = torch.zeros_like(self.w3) if plan.with_grad else None
-        self._wver = -1
+        self._wstamp = None
         lib = _lib.load()
         units = N * H * W
         plan.need(max(lib.unetk_chan_partial_floats(units, self.cout), lib.unetk_conv_stats_partial_floats(self.cout),
@@ -357,10 +397,10 @@ class ConvBNReLU:
     def refresh(self, force=False):
         if self.w3 is not None:
             w = self.conv.weight
-            if force or w._version != self._wver:
+            if force or weight_stamp(w) != self._wstamp:
                 # 1x1 kernel -> centre tap (index 4 of 9) of the zero-padded 3x3 stem kernel
                 ops.copy_f32_strided(self.w3, 9, w.detach(), 1, self.cout * self.cin, dst_offset=4)
-                self._wver = w._version
+                self._wstamp = weight_stamp(w)
 
     def fwd(self):
         P, bn = self.plan, self.bn
@@ -389,7 +429,7 @@ class ConvBNReLU:
             if P.sync_sums is not None:
                 count = P.sync_sums(P.sums[: 2 * self.cout], count)
             track = bn.track_running_stats and P.training
-            ops.bn_finalize(P.sums, count, gamma, beta, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+            ops.bn_finalize(P.sums, count, gamma, beta, bn.eps, bn_momentum(bn, P.training),
                             bn.running_mean if track else None, bn.running_var if track else None,
                             bn.num_batches_tracked if track else None, sc, sh, mu, iv)
         else:
@@ -827,7 +867,7 @@ class BNAct(_Op):
             if P.sync_sums is not None:
                 count = P.sync_sums(P.sums[: 2 * self.x.C], count)
             track = bn.track_running_stats and P.training
-            ops.bn_finalize(P.sums, count, gamma, beta, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+            ops.bn_finalize(P.sums, count, gamma, beta, bn.eps, bn_momentum(bn, P.training),
                             bn.running_mean if track else None, bn.running_var if track else None,
                             bn.num_batches_tracked if track else None, sc, sh, mu, iv)
         else:
@@ -911,7 +951,7 @@ class AttentionGate(_Op):
             if P.sync_sums is not None:
                 count = P.sync_sums(sums, count)
             track = bn.track_running_stats and P.training
-            ops.bn_finalize(sums, count, gamma, beta, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+            ops.bn_finalize(sums, count, gamma, beta, bn.eps, bn_momentum(bn, P.training),
                             bn.running_mean if track else None, bn.running_var if track else None,
                             bn.num_batches_tracked if track else None, sc, sh, mu, iv)
         else:

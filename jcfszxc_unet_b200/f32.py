@@ -15,7 +15,7 @@ import ctypes
 
 import torch
 
-from . import _lib, ops
+from . import _lib, engine, ops
 
 BF16 = torch.bfloat16
 
@@ -37,17 +37,19 @@ class _SplitPack:
             self.sr, self.sk, self.st = weight.shape[1] * 9, 9, 1
         assert sum(slices) == self.K
         self.pack = torch.empty((self.T, self.R, 6 * self.K), dtype=BF16, device=weight.device)
-        self._ver = -1
+        self._stamp = None
 
     def refresh(self):
-        if self.w._version == self._ver:
+        from .engine import weight_stamp
+
+        if weight_stamp(self.w) == self._stamp:
             return
         w = self.w.detach()
         assert w.is_contiguous() and w.dtype == torch.float32
         arr = (ctypes.c_int * len(self.slices))(*self.slices)
         _lib.call("unetk_f32_pack_split3", w.data_ptr(), self.pack.data_ptr(), self.sr, self.sk, self.st, self.R, self.K,
                   self.T, arr, len(self.slices), _s())
-        self._ver = self.w._version
+        self._stamp = weight_stamp(self.w)
 
 
 def split_activation(x: torch.Tensor) -> torch.Tensor:
@@ -175,7 +177,7 @@ class UNetF32Plan:
             if self.training or not bn.track_running_stats:
                 _lib.call("unetk_f32_stats", raw.data_ptr(), cout, npix, cout, self.partial.data_ptr(), self.sums.data_ptr(), _s())
                 track = bn.track_running_stats and self.training
-                ops.bn_finalize(self.sums, npix, gamma, beta, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                ops.bn_finalize(self.sums, npix, gamma, beta, bn.eps, engine.bn_momentum(bn, self.training),
                                 bn.running_mean if track else None, bn.running_var if track else None,
                                 bn.num_batches_tracked if track else None, sc, sh, mu, iv)
             else:
@@ -221,9 +223,11 @@ def run_unet_f32(model, x: torch.Tensor) -> torch.Tensor:
     """model(x) in fp32 mode: cached plan per (shape, BatchNorm mode).  Forward only: the result carries no graph."""
     n, _, h, w = x.shape
     key = ("f32", n, h, w, x.device.index, model.training)
-    plans = model.__dict__.setdefault("_unetk_plans", {})
-    plan = plans.get(key)
+    from .bridge import plan_cache
+
+    plans = plan_cache(model)
+    plan = plans.lookup(key)
     if plan is None:
-        plan = plans[key] = UNetF32Plan(model, n, h, w, x.device, model.training)
+        plan = plans.insert(key, UNetF32Plan(model, n, h, w, x.device, model.training))
     with torch.no_grad():
         return plan.forward(x).clone()

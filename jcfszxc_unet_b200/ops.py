@@ -399,6 +399,11 @@ def rmsprop_step(p, g, sq, buf, lr, alpha, eps, wd, momentum, clip):
               float(eps), float(wd), float(momentum), _f32(clip), _stream())
 
 
+def rmsprop_step_dev(p, g, sq, buf, hyper, clip):
+    """hyper: device fp32 [lr, alpha, eps, weight_decay, momentum] (read by the kernel at run time)."""
+    _lib.call("unetk_rmsprop_step_dev", _f32(p), _f32(g), _f32(sq), _f32(buf), p.numel(), _f32(hyper), _f32(clip), _stream())
+
+
 # ------------------------------------------------------------------------------------------------
 # glue of the U-Net variants: residual adds / slice copies, 2x up-sampling, attention gate
 # ------------------------------------------------------------------------------------------------

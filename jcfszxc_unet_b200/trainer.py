@@ -2,24 +2,30 @@
 
     forward -> 0.5*BCEWithLogits + 0.5*dice_loss -> backward -> clip_grad_norm_(1.0) -> RMSprop
 
-as CUDA-graph segments with the data-parallel collectives between them:
+as ONE CUDA graph per rank.  In data-parallel runs the collectives are part of that graph:
 
-    [pack weights, forward, head+loss sums]  --all-reduce(loss sums)-->
-    [loss finalize, backward of the decoder] --async all-reduce(decoder grads) on the NCCL stream ...
-    [backward of the encoder]                --all-reduce(encoder grads), wait for both-->
-    [global-norm clip coefficient, RMSprop]
+    [pack weights, forward, head + loss sums] -> all-reduce(4 loss sums) -> [loss finalize, backward ...
+      ... after the op that completes a gradient bucket: all-reduce(bucket) on the NCCL stream, beside the rest of
+          the backward ...] -> wait -> [global-norm clip coefficient, RMSprop]
 
-The gradient all-reduce is bucketed in backward order (the decoder's gradients are the contiguous tail of the
-flat buffer and are complete half-way through the backward), so NCCL runs beside the encoder's backward kernels.
+The flat gradient is cut into ~8 buckets by byte count in the order the backward completes it (decoder first, stem
+last), so what is still un-reduced when the backward ends is the last, small bucket (the first layers' parameters).
+When the NCCL calls cannot be captured (older stacks) the same program runs as one graph per kernel segment with the
+collectives launched between them; `use_cuda_graph=False` runs it eagerly.  All three orders are the same launch
+sequence and give the same bits.
 
-Parameters, gradients and RMSprop state live in four flat fp32 buffers (the model's nn.Parameters are
-re-homed as views, so state_dict()/checkpoints keep working).  No host synchronisation happens inside
-step(); the loss is returned as a device scalar.  bf16 needs no GradScaler (the reference's
-GradScaler/fp16 autocast is replaced by bf16 as BASELINE.json asks).
+Parameters, gradients and RMSprop state live in four flat fp32 buffers (the model's nn.Parameters are re-homed as
+views, so state_dict()/checkpoints keep working).  The learning rate and the other RMSprop hyper-parameters are read
+by the kernel from device memory (`set_lr`), so a schedule (the reference's ReduceLROnPlateau, train.py:114-122,355)
+takes effect inside captured graphs too.  No host synchronisation happens inside step(); the loss is returned as a
+device scalar.  bf16 needs no GradScaler (the reference's GradScaler/fp16 autocast is replaced by bf16 as
+BASELINE.json asks).
 """
 from __future__ import annotations
 
+import functools
 import os
+import sys
 
 import torch
 
@@ -30,12 +36,14 @@ from .dp import DataParallel
 class Trainer:
     def __init__(self, model: torch.nn.Module, lr: float = 1e-6, weight_decay: float = 1e-8,
                  momentum: float = 0.999, alpha: float = 0.99, eps: float = 1e-8, max_norm: float = 1.0,
-                 builder=None, use_cuda_graph: bool = True, dp: DataParallel | None = None):
+                 builder=None, use_cuda_graph: bool = True, dp: DataParallel | None = None,
+                 grad_buckets: int | None = None):
         self.model = model
-        self.lr, self.wd, self.momentum, self.alpha, self.eps, self.max_norm = lr, weight_decay, momentum, alpha, eps, max_norm
+        self._max_norm = max_norm
         self.builder = builder or engine.build_unet_plan
         self.dp = dp or DataParallel()
-        self.use_graph = use_cuda_graph and not self.dp.sync_bn  # SyncBN puts collectives between kernels
+        self.use_graph = use_cuda_graph and not self.dp.sync_bn  # SyncBN puts host-side collectives between kernels
+        self.grad_buckets = grad_buckets or int(os.environ.get("UNETK_GRAD_BUCKETS", "8"))
         params = [p for p in model.parameters()]
         if not params or not params[0].is_cuda:
             raise RuntimeError("Trainer: move the model to a CUDA device first (no CPU fallback on this path)")
@@ -52,20 +60,33 @@ class Trainer:
         self.sq = torch.zeros_like(self.flat_p)
         self.buf = torch.zeros_like(self.flat_p)
         self.grad_views = {}
+        # The fused optimizer updates the parameters through raw pointers (also inside graph replays), behind torch's
+        # version counter: every parameter carries this shared generation, bumped once per step, so that derived caches
+        # of OTHER plans of the model (the eval plan behind model(x) in validation, predict_full_image) re-pack their
+        # bf16 weights after training steps (engine.weight_stamp).
+        self._gen = [0]
         with torch.no_grad():
             for p, o in zip(params, offs):
                 v = self.flat_p[o:o + p.numel()].view(p.shape)
                 v.copy_(p.data)
                 p.data = v
+                p._unetk_gen = self._gen
                 self.grad_views[id(p)] = self.flat_g[o:o + p.numel()].view(p.shape)
         self.n_params = total
         if self.dp.enabled:
-            self.dp.broadcast_(self.flat_p, 0)  # replicas start identical
+            self.dp.broadcast_(self.flat_p, 0)  # replicas start identical: parameters ...
+            for b in model.buffers():           # ... and BatchNorm running statistics (a loaded checkpoint on rank 0)
+                self.dp.broadcast_(b, 0)
+        # {lr, alpha, eps, weight_decay, momentum}: read from device memory by the RMSprop kernel
+        self._hyper_host = [float(lr), float(alpha), float(eps), float(weight_decay), float(momentum)]
+        self.hyper = torch.tensor(self._hyper_host, dtype=torch.float32, device=dev)
         self.clip = torch.zeros(2, dtype=torch.float32, device=dev)
         self.sq_partial = None
         self.plan = None
         self.graphs = None
-        self._single_graph = False
+        self.graph_mode = "eager"   # "single" (one graph, collectives inside) | "segments" | "eager"
+        self._program = None
+        self._handles = []
         self.images = self.labels = None
         self.steps_done = 0
         # input pipeline (prefetch / step()): two staging batches in HBM filled by a copy stream
@@ -74,6 +95,32 @@ class Trainer:
         self._stage_ready = self._stage_free = None
         self._staged = []           # slots holding a batch not yet consumed, in order
         self._stage_next = 0
+
+    # ---- hyper-parameters ----------------------------------------------------------------------------
+    def _set_hyper(self, i: int, v: float):
+        self._hyper_host[i] = float(v)
+        self.hyper[i:i + 1].fill_(float(v))     # a tiny fill on the current stream: ordered before the next step
+
+    lr = property(lambda self: self._hyper_host[0], lambda self, v: self._set_hyper(0, v))
+    alpha = property(lambda self: self._hyper_host[1], lambda self, v: self._set_hyper(1, v))
+    eps = property(lambda self: self._hyper_host[2], lambda self, v: self._set_hyper(2, v))
+    wd = property(lambda self: self._hyper_host[3], lambda self, v: self._set_hyper(3, v))
+    momentum = property(lambda self: self._hyper_host[4], lambda self, v: self._set_hyper(4, v))
+
+    def set_lr(self, lr: float) -> None:
+        """What `optimizer.param_groups[0]["lr"] = lr` (ReduceLROnPlateau.step, train.py:355) does in the reference;
+        effective from the next step on, in eager and in graph mode alike."""
+        self.lr = lr
+
+    @property
+    def max_norm(self):
+        return self._max_norm
+
+    @max_norm.setter
+    def max_norm(self, v):
+        if float(v) != self._max_norm:
+            self._max_norm = float(v)
+            self.graphs = None      # a launch argument of the clip kernel: re-capture
 
     # ------------------------------------------------------------------------------------------------
     def _build(self, n, c, h, w):
@@ -95,116 +142,160 @@ class Trainer:
         self.sq_partial = torch.empty(_lib.load().unetk_sqnorm_partial_floats(self.flat_g.numel()),
                                       dtype=torch.float32, device=dev)
         self._gscale = 1.0
-        self._split_op, self._split_off = self._find_bucket_split()
+        self._cuts = self._plan_buckets(self.grad_buckets) if self.dp.enabled else []
+        self._program = self._make_program()
 
-    def _find_bucket_split(self):
-        """(k, o): the ops[k:] — run FIRST in the backward — own exactly the parameters stored at flat offsets >= o,
-        with about half of the gradient behind o.  (0, 0) when no such cut exists (single bucket)."""
-        base = self.flat_g.data_ptr()
-        ranges = []
-        for op in self.plan.ops:
-            lo, hi = None, None
+    def _plan_buckets(self, nbuckets: int):
+        """[(k, [(lo, hi), ...])] in backward order: once the backward of ops[k:] has run, the flat-gradient ranges
+        [lo, hi) (floats) are final and are all-reduced while ops[:k] still run.  A parameter is final after the
+        backward of the FIRST op (in forward order) that uses it; ranges are emitted whenever about total/nbuckets
+        bytes have become final, the rest (the first layers) after the last op."""
+        base, total = self.flat_g.data_ptr(), self.flat_g.numel()
+        final_at = {}
+        for i, op in enumerate(self.plan.ops):
             for q in self.plan.op_params(op):
                 g = self.grad_views.get(id(q))
-                if g is None:
-                    continue
-                o = (g.data_ptr() - base) // 4
-                lo = o if lo is None else min(lo, o)
-                hi = o + g.numel() if hi is None else max(hi, o + g.numel())
-            ranges.append((lo, hi))
-        total = self.flat_g.numel()
-        n = len(ranges)
-        prefix_hi = [0] * (n + 1)            # max offset end owned by ops[:k]
-        for k in range(n):
-            prefix_hi[k + 1] = max(prefix_hi[k], ranges[k][1] or 0)
-        suffix_lo = [total] * (n + 1)        # min offset start owned by ops[k:]
-        for k in range(n - 1, -1, -1):
-            suffix_lo[k] = min(suffix_lo[k + 1], ranges[k][0] if ranges[k][0] is not None else total)
-        best = (0, 0)
-        for k in range(1, n):
-            if prefix_hi[k] <= suffix_lo[k] < total and suffix_lo[k] > 0:
-                if best == (0, 0) or abs(suffix_lo[k] - total // 2) < abs(best[1] - total // 2):
-                    best = (k, int(suffix_lo[k]))
-        return best
+                if g is not None:
+                    o = (g.data_ptr() - base) // 4
+                    prev = final_at.get(o)
+                    final_at[o] = (i if prev is None else min(prev[0], i), o + (g.numel() + 3) // 4 * 4)
+        covered = sorted((o, hi) for o, (_, hi) in final_at.items())
+        # parameters no op of the plan touches keep a zero gradient: they ride in the last bucket
+        pos, rest = 0, []
+        for o, hi in covered:
+            if o > pos:
+                rest.append((0, pos, o))
+            pos = max(pos, hi)
+        if pos < total:
+            rest.append((0, pos, total))
+        items = sorted([(k, o, hi) for o, (k, hi) in final_at.items()] + rest, key=lambda t: (-t[0], t[1]))
+        thr = max(1, total // max(1, nbuckets))
+        cuts, ready, ready_n, done = [], [], 0, 0
+        for j, (k, lo, hi) in enumerate(items):
+            ready.append((lo, hi))
+            ready_n += hi - lo
+            done += hi - lo
+            last_of_op = j + 1 == len(items) or items[j + 1][0] != k
+            # towards the end of the backward the buckets shrink geometrically (a bucket goes out as soon as it is at
+            # least as large as everything still to come), so what is reduced AFTER the last op is small
+            big_enough = ready_n >= thr or (nbuckets > 1 and ready_n >= max(1 << 16, total - done))
+            if last_of_op and (big_enough or j + 1 == len(items)):
+                cuts.append((k if j + 1 < len(items) else 0, self._coalesce(ready)))
+                ready, ready_n = [], 0
+        return cuts
 
-    # segments ---------------------------------------------------------------------------------------
-    def _seg_forward(self):
-        self.plan.forward(self.images)
-
-    def _seg_backward(self):
-        self.plan.head.finalize_loss(self._npix_total)
-        self.plan.backward(self._split_op, None)
-
-    def _seg_backward_tail(self):
-        self.plan.backward(0, self._split_op)
-
-    def _seg_optim(self):
-        ops.grad_clip_coef(self.flat_g, self._gscale, self.max_norm, self.sq_partial, self.clip)
-        ops.rmsprop_step(self.flat_p, self.flat_g, self.sq, self.buf, self.lr, self.alpha, self.eps, self.wd,
-                         self.momentum, self.clip)
-
-    def _seg_all(self):
-        """The whole iteration as one launch sequence: single process, nothing to exchange between the segments."""
-        self.plan.refresh_weights(force=True)
-        self._seg_forward()
-        self.plan.head.finalize_loss(self._npix_total)
-        self.plan.backward(0, None)
-        self._seg_optim()
-
-    def _run_segments(self):
-        head = self.plan.head
-        if self.graphs is not None and self._single_graph:
-            # one CUDA graph per step: the weight-gradient side stream is joined once, in front of the optimizer,
-            # instead of at the end of each backward segment
-            self.graphs[0].replay()
-            return
-        if self.graphs is not None:
-            self.graphs[0].replay()
-        else:
-            self.plan.refresh_weights(force=True)
-            self._seg_forward()
-        if self.dp.sync_loss:
-            self.dp.reduce_loss_sums(head.loss_sums, head.npix)
-        if self.graphs is not None:
-            self.graphs[1].replay()
-        else:
-            self._seg_backward()
-        # decoder gradients (flat tail) are final: reduce them while the encoder's backward runs
-        h_tail = self.dp.reduce_grads_async(self.flat_g[self._split_off:]) if self._split_op > 0 else None
-        if self._split_op > 0:
-            if self.graphs is not None:
-                self.graphs[2].replay()
+    @staticmethod
+    def _coalesce(ranges):
+        out = []
+        for lo, hi in sorted(ranges):
+            if out and lo <= out[-1][1]:
+                out[-1][1] = max(out[-1][1], hi)
             else:
-                self._seg_backward_tail()
-        h_head = self.dp.reduce_grads_async(self.flat_g[:self._split_off] if self._split_op > 0 else self.flat_g)
-        self.dp.wait(h_tail)
-        self.dp.wait(h_head)
-        if self.graphs is not None:
-            self.graphs[3].replay()
-        else:
-            self._seg_optim()
+                out.append([lo, hi])
+        return [(lo, hi) for lo, hi in out]
 
-    def _capture(self):
-        # constants baked into the graphs
-        graphs = []
-        pool = None
-        # captured on a HIGH-priority stream: the plan's weight-gradient side stream is low priority, so whenever a
-        # kernel of the critical path and a weight gradient are both ready, the critical path gets the SMs first
-        hp = torch.cuda.Stream(device=self.device, priority=-1)
-        self._single_graph = not self.dp.enabled and os.environ.get("UNETK_SINGLE_GRAPH", "1") != "0"
-        segments = ((self._seg_all,) if self._single_graph else
-                    (self._seg_forward_packed, self._seg_backward, self._seg_backward_tail, self._seg_optim))
-        for seg in segments:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool, stream=hp):
-                seg()
-            pool = g.pool()
-            graphs.append(g)
-        self.graphs = graphs
+    def bucket_report(self):
+        """What bench.py prints as `grad_buckets`: MB per all-reduce call in launch order, and how the step is run."""
+        if not self.dp.enabled or self.plan is None:
+            return None
+        return {"mode": self.graph_mode, "calls_mb": [[round((hi - lo) * 4 / 2**20, 2) for lo, hi in rs] for _, rs in self._cuts],
+                "cut_after_op": [k for k, _ in self._cuts], "ops": len(self.plan.ops)}
+
+    # program ------------------------------------------------------------------------------------------
+    def _make_program(self):
+        """The step as a list of ("k", fn) kernel-launch segments and ("c", fn) collectives, in launch order."""
+        P, head = self.plan, self.plan.head
+        prog = [("k", self._seg_forward_packed)]
+        if self.dp.sync_loss:
+            prog.append(("c", lambda: self.dp.reduce_loss_sums(head.loss_sums, head.npix)))
+        hi, first = len(P.ops), True
+        for k, ranges in self._cuts:
+            if k < hi or first:
+                prog.append(("k", functools.partial(self._seg_backward, k, hi, first)))
+                hi, first = k, False
+            prog.append(("c", functools.partial(self._launch_bucket, ranges)))
+        if hi > 0 or first:
+            prog.append(("k", functools.partial(self._seg_backward, 0, hi, first)))
+        if self._cuts:
+            prog.append(("c", self._wait_buckets))
+        prog.append(("k", self._seg_optim))
+        return prog
 
     def _seg_forward_packed(self):
         self.plan.refresh_weights(force=True)  # the optimizer updates weights behind torch's version counter
-        self._seg_forward()
+        self.plan.forward(self.images)
+
+    def _seg_backward(self, lo, hi, first):
+        if first:
+            self.plan.head.finalize_loss(self._npix_total)
+        # the weight-gradient side stream is joined where a captured segment ends, and before the optimizer
+        self.plan.backward(lo, hi, join=(self.graph_mode == "segments" or lo == 0))
+
+    def _launch_bucket(self, ranges):
+        """SUM all-reduce of gradient ranges that are final, issued behind BOTH the main stream (BatchNorm / bias
+        gradients) and the weight-gradient side stream, without making the main stream wait for either."""
+        with self.plan.behind_both_streams():
+            for lo, hi in ranges:
+                self._handles.append(self.dp.reduce_grads_async(self.flat_g[lo:hi]))
+
+    def _wait_buckets(self):
+        for h in self._handles:
+            self.dp.wait(h)
+        self._handles = []
+
+    def _seg_optim(self):
+        ops.grad_clip_coef(self.flat_g, self._gscale, self._max_norm, self.sq_partial, self.clip)
+        ops.rmsprop_step_dev(self.flat_p, self.flat_g, self.sq, self.buf, self.hyper, self.clip)
+
+    def _run_segments(self):
+        if self.graphs is not None and self.graph_mode == "single":
+            self.graphs[0].replay()
+        elif self.graphs is not None:
+            it = iter(self.graphs)
+            for kind, fn in self._program:
+                if kind == "k":
+                    next(it).replay()
+                else:
+                    fn()
+        else:
+            for _, fn in self._program:
+                fn()
+        self._gen[0] += 1
+
+    def _capture(self):
+        """Capture the step.  On a HIGH-priority stream: the plan's weight-gradient side stream is low priority, so
+        whenever a kernel of the critical path and a weight gradient are both ready, the critical path gets the SMs."""
+        hp = torch.cuda.Stream(device=self.device, priority=-1)
+        want_single = os.environ.get("UNETK_SINGLE_GRAPH", "1") != "0" and (
+            not self.dp.enabled or os.environ.get("UNETK_DP_GRAPH", "1") != "0")
+        if want_single:
+            self.graph_mode = "single"
+            try:
+                g = torch.cuda.CUDAGraph()
+                # thread_local: NCCL's watchdog thread may query events while this thread captures
+                with torch.cuda.graph(g, stream=hp, capture_error_mode="thread_local"):
+                    for _, fn in self._program:
+                        fn()
+                self.graphs = [g]
+                return
+            except Exception as e:  # NCCL calls that cannot be captured on this stack: one graph per kernel segment
+                if not self.dp.enabled:
+                    raise
+                print(f"[unetk] single-graph capture with NCCL failed ({type(e).__name__}: {e}); using per-segment graphs",
+                      file=sys.stderr)
+                self._handles = []
+                torch.cuda.synchronize()
+        self.graph_mode = "segments"
+        graphs, pool = [], None
+        for kind, fn in self._program:
+            if kind != "k":
+                continue
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, stream=hp):
+                fn()
+            pool = g.pool()
+            graphs.append(g)
+        self.graphs = graphs
 
     # ------------------------------------------------------------------------------------------------
     def step(self, images: torch.Tensor | None = None, labels: torch.Tensor | None = None) -> torch.Tensor:

@@ -57,14 +57,28 @@ def _l2rel(a, b):
 
 
 def _assert_as_close_as_stock_bf16(ours, ref32, ref16, what, floor, slack):
-    """Within `floor` of the fp32 oracle (tensor-level and worst-element relative error), or — where bf16 storage
-    itself cannot do better — within `slack` x the deviation of the reference's own bf16-autocast path."""
-    l2, mx = _l2rel(ours, ref32), _rel(ours, ref32)
-    l2_ref, mx_ref = _l2rel(ref16, ref32), _rel(ref16, ref32)
-    msg = f"{what}: ours l2 {l2:.4g} max {mx:.4g} | reference bf16-autocast l2 {l2_ref:.4g} max {mx_ref:.4g}"
-    print(msg)
-    assert l2 <= max(floor, slack * l2_ref), msg
-    assert mx <= max(floor, slack * mx_ref), msg
+    """The shared acceptance rule (tests/_parity.py): within min(max(floor, slack x the reference's own bf16-autocast
+    deviation), ceiling) of the fp32 reference; ceiling 5e-2 for activations / logits, 1.5e-1 for gradients."""
+    from _parity import GRAD_CEILING, LOGIT_CEILING, assert_close_bf16
+
+    assert_close_bf16(ours, ref32, ref16, what, floor, slack, LOGIT_CEILING if floor <= 2e-2 else GRAD_CEILING)
+
+
+def _whole_output_check(ours, ref32, ref16, what) -> bool:
+    """Whole-model output under the ceiling rule when the input is informative; otherwise (the randomly initialised gated /
+    recurrent variants, whose own bf16-autocast reference run is 0.26 ... 1.1 away from its fp32 run) the numbers are
+    recorded, nothing wider is asserted, and the caller relies on the teacher-forced block checks."""
+    from _parity import LOGIT_CEILING, assert_close_bf16, informative, l2rel, record, rel
+
+    if informative(ref32, ref16, 1.25, LOGIT_CEILING):
+        assert_close_bf16(ours, ref32, ref16, what)
+        return True
+    record(f"{what}: ours vs fp32 l2 {l2rel(ours, ref32):.4g} max {rel(ours, ref32):.4g} | reference bf16-autocast vs fp32 l2 "
+           f"{l2rel(ref16, ref32):.4g} max {rel(ref16, ref32):.4g} | ours vs reference-bf16 l2 {l2rel(ours, ref16):.4g} — UNINFORMATIVE "
+           "input (reference bf16 beyond the ceiling): not asserted; see the teacher-forced block lines")
+    # sanity only (claims no parity): not further from fp32 than 1.5 x the reference's own bf16 run
+    assert l2rel(ours, ref32) <= 1.5 * l2rel(ref16, ref32), what
+    return False
 
 
 def _nhwc(t):
@@ -350,7 +364,7 @@ def test_variant_forward_matches_reference_golden(name):
     ref = torch.from_numpy(g["logits_train"]).to(DEV)
     ref_bf = torch.from_numpy(g["logits_train_bf16_autocast"]).to(DEV)
     assert y.shape == ref.shape and y.dtype == torch.float32
-    _assert_as_close_as_stock_bf16(y, ref, ref_bf, f"{name} output", floor=2e-2, slack=1.5)
+    _whole_output_check(y, ref, ref_bf, f"[golden {name} {tuple(x.shape)}] output")
     m.eval()
     with torch.no_grad():
         ye = m(x)
@@ -400,19 +414,17 @@ def test_variant_forward_backward_vs_oracle(name, n, h, w):
 
     lg32, ls32, dl32, g32, s32 = oracle_run(False)
     lg16, ls16, dl16, g16, s16 = oracle_run(True)
-    _assert_as_close_as_stock_bf16(out.detach(), lg32, lg16, f"{name} output", floor=2e-2, slack=1.5)
-    assert abs(float(dice_l) - float(dl32)) <= max(1e-3, 1.5 * abs(float(dl16) - float(dl32)))
+    from _parity import check_blocks_teacher_forced, check_param_grads
+
+    tag = f"[whole {name} {n}x3x{h}x{w}]"
+    informative = _whole_output_check(out.detach(), lg32, lg16, tag + " output")
+    dice_tol = 1e-3 if informative else max(1e-3, min(1.5 * abs(float(dl16) - float(dl32)), 5e-3))
+    assert abs(float(dice_l) - float(dl32)) <= dice_tol, (float(dice_l), float(dl32), float(dl16))
     assert abs(float(loss) - float(ls32)) <= 2e-2 * max(1.0, abs(float(ls32)))
-    ours, g32, g16 = _group_scalars({k: ours[k] for k in names}), _group_scalars(g32), _group_scalars(g16)
-    gmax = max(float(v.abs().max()) for v in g32.values())
-    bad = []
-    for k in g32:
-        if float(g32[k].abs().max()) < 1e-4 * gmax:
-            continue   # biases in front of train-mode BatchNorm: zero gradient up to rounding noise
-        e_ours, e_ref = _l2rel(ours[k], g32[k]), _l2rel(g16[k], g32[k])
-        if e_ours > max(2.5 * e_ref, 5e-2):
-            bad.append(f"{k}: ours {e_ours:.3g} vs bf16-autocast {e_ref:.3g}")
-    assert not bad, "\n".join(bad)
+    check_param_grads({k: ours[k] for k in names}, g32, g16, tag)
+    # the comparison that is informative for every variant: each block on the fp32 oracle's own activations
+    m.zero_grad(set_to_none=True)
+    check_blocks_teacher_forced(O, m, name, images, backward=True, tag=f"[blocks {n}x3x{h}x{w}] ")
     # running statistics follow nn.BatchNorm2d; deep in the recurrent variants they inherit the bf16 noise of the
     # activations, so the yardstick is again the reference's own bf16-autocast run
     for k, v in m.state_dict().items():
