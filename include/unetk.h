@@ -202,6 +202,23 @@ int unetk_maxpool2x2_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int
 int unetk_maxpool2x2_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
                          int accumulate, int N, int H, int W, int C, void* stream);
 
+/* ---- SegNet-style pool / unpool pair (UNetFamily/SegNet.py:89-138: F.max_pool2d(return_indices=True) ...
+ *      F.max_unpool2d(z, idx, 2, 2)) ---------------------------------------------------------------------------
+ * maxpool2x2_fwd_codes: the same pooling rule as maxpool2x2_fwd; the arg-max leaves as a compact CODE, one byte per
+ *   pooled element (window position 0..3, row-major), NHWC uint8 [N][H/2][W/2][C] (8-byte aligned): 1 B per element
+ *   instead of the 8 B of an int64 index.
+ * max_unpool2x2: out [N][2Ho][2Wo][C] <- x [N][Ho][Wo][C]: the selected window position gets the value, the other
+ *   three get zero (every output element is written: no zero-fill, no scatter).  `where` is the byte codes
+ *   (where_is_idx = 0) or int64 indices [N][C][Ho][Wo] holding h*(2Wo)+w as F.max_pool2d(kernel 2, stride 2) returns
+ *   them (where_is_idx = 1; each index lies inside its own window).  Equal to F.max_unpool2d bit for bit.
+ * max_unpool2x2_bwd: dx[pooled] (+)= dy[selected position]. */
+int unetk_maxpool2x2_fwd_codes(const void* x, int64_t x_ld, void* y, int64_t y_ld, uint8_t* code, int N, int H, int W,
+                               int C, void* stream);
+int unetk_max_unpool2x2(const void* x, int64_t x_ld, const void* where, int where_is_idx, void* out, int64_t out_ld,
+                        int N, int Ho, int Wo, int C, void* stream);
+int unetk_max_unpool2x2_bwd(const void* dy, int64_t dy_ld, const void* where, int where_is_idx, void* dx,
+                            int64_t dx_ld, int accumulate, int N, int Ho, int Wo, int C, void* stream);
+
 /* ---- per-channel column sum (bias gradients of ConvTranspose2d / biased convs) -------------------- */
 int unetk_colsum(const void* x, int64_t x_ld, int64_t npix, int C, float* partial, float* out, int accumulate,
                  void* stream);
@@ -385,14 +402,6 @@ int unetk_f32_bn_split(const float* raw, int64_t raw_ld, const float* scale, con
                        int W, int C, int relu, void* stream);
 int unetk_f32_head(const float* x, int64_t x_ld, const float* w, const float* bias, float* logits, int64_t npix, int C,
                    void* stream);
-
-/* ---- test infrastructure: tcgen05 descriptor-semantics probe (not on the product path) ---------- */
-int unetk_probe_umma(const void* a, const void* b, float* d, int mode, int shift, int base_offset,
-                     void* stream);
-/* clocks (int64 [grid]) that one thread needs to issue and retire iters*4*(1+two_acc) tcgen05.mma of shape
- * 128 x N x 16 (N = 64/128/256) from resident shared memory; A starts a_shift_rows*128 B into a swizzle atom. */
-int unetk_probe_mma_rate(int N, int grid, int a_shift_rows, int two_acc, int iters, int b_tiles, int64_t* out,
-                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,9 @@ SIGNATURES = {
     "unetk_bn_bwd_coef": (_i, [_vp, _i, C.c_double, _fp, _fp, _fp, _fp, _fp, _i, _fp, _fp, _vp]),
     "unetk_maxpool2x2_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
     "unetk_maxpool2x2_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_maxpool2x2_fwd_codes": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
+    "unetk_max_unpool2x2": (_i, [_vp, _i64, _vp, _i, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "unetk_max_unpool2x2_bwd": (_i, [_vp, _i64, _vp, _i, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_colsum": (_i, [_vp, _i64, _i64, _i, _fp, _fp, _i, _vp]),
     "unetk_head_partial_floats": (_sz, [_i64, _i]),
     "unetk_head_fwd": (_i, [_vp, _i64, _fp, _fp, _fp, _fp, _i, _i64, _i, _fp, _vp, _vp]),
@@ -108,8 +111,6 @@ SIGNATURES = {
     "unetk_f32_stats": (_i, [_fp, _i64, _i64, _i, _vp, _vp, _vp]),
     "unetk_f32_bn_split": (_i, [_fp, _i64, _fp, _fp, _vp, _i64, _fp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_f32_head": (_i, [_fp, _i64, _fp, _fp, _fp, _i64, _i, _vp]),
-    "unetk_probe_umma": (_i, [_vp, _vp, _fp, _i, _i, _i, _vp]),
-    "unetk_probe_mma_rate": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 

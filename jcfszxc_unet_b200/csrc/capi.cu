@@ -336,6 +336,21 @@ int unetk_maxpool2x2_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int
   UNETK_CHECK(x && y, -1, "maxpool_fwd: null pointer");
   return maxpool_fwd_run(x, x_ld, y, y_ld, reinterpret_cast<long long*>(idx), N, H, W, C, S(stream));
 }
+int unetk_maxpool2x2_fwd_codes(const void* x, int64_t x_ld, void* y, int64_t y_ld, uint8_t* code, int N, int H, int W,
+                               int C, void* stream) {
+  UNETK_CHECK(x && y && code, -1, "maxpool_fwd_codes: null pointer");
+  return maxpool_codes_run(x, x_ld, y, y_ld, code, N, H, W, C, S(stream));
+}
+int unetk_max_unpool2x2(const void* x, int64_t x_ld, const void* where, int where_is_idx, void* out, int64_t out_ld,
+                        int N, int Ho, int Wo, int C, void* stream) {
+  UNETK_CHECK(x && where && out, -1, "max_unpool: null pointer");
+  return max_unpool_run(x, x_ld, where, where_is_idx, out, out_ld, N, Ho, Wo, C, S(stream));
+}
+int unetk_max_unpool2x2_bwd(const void* dy, int64_t dy_ld, const void* where, int where_is_idx, void* dx,
+                            int64_t dx_ld, int accumulate, int N, int Ho, int Wo, int C, void* stream) {
+  UNETK_CHECK(dy && where && dx, -1, "max_unpool_bwd: null pointer");
+  return max_unpool_bwd_run(dy, dy_ld, where, where_is_idx, dx, dx_ld, accumulate, N, Ho, Wo, C, S(stream));
+}
 int unetk_maxpool2x2_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
                          int accumulate, int N, int H, int W, int C, void* stream) {
   UNETK_CHECK(x && dy && dx, -1, "maxpool_bwd: null pointer");
@@ -588,15 +603,6 @@ int unetk_f32_head(const float* x, int64_t x_ld, const float* w, const float* bi
                    void* stream) {
   UNETK_CHECK(x && w && logits && npix > 0 && C > 0, -1, "f32_head: bad arguments");
   return f32_head_run(x, x_ld, w, bias, logits, npix, C, S(stream));
-}
-
-int unetk_probe_umma(const void* a, const void* b, float* d, int mode, int shift, int base_offset, void* stream) {
-  return probe_run(a, b, d, mode, shift, base_offset, S(stream));
-}
-int unetk_probe_mma_rate(int N, int grid, int a_shift_rows, int two_acc, int iters, int b_tiles, int64_t* out,
-                         void* stream) {
-  UNETK_CHECK(out != nullptr, -1, "probe_mma_rate: null output");
-  return probe_mma_rate_run(N, grid, a_shift_rows, two_acc, iters, b_tiles, reinterpret_cast<long long*>(out), S(stream));
 }
 
 }  // extern "C"

@@ -394,11 +394,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
 template <int BN>
 int launch(HaloParams& p, int grid, cudaStream_t stream) {
   using C = HCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    UNETK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static DeviceOnce once;
+  UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
   // weights resident when all 9*kchunks tiles fit next to the two halo slots and one staging buffer
   const uint32_t w_bytes = static_cast<uint32_t>(9 * p.kchunks) * C::kBBytes;
   const uint32_t resident_smem = 2 * kHaloSlot + w_bytes + kStagingBytes + 1024 + 256 + BN * 4;

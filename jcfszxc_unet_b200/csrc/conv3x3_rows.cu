@@ -411,12 +411,11 @@ int conv3x3_rows_run(const ConvGemmDesc& d, cudaStream_t stream) {
     uint32_t es[4] = {1, 1, 1, 1};
     if (int rc = make_tmap_bf16(&p.tmOut, d.out, 4, dims, strides, box, es, true, BW == 32 ? 64 : 128)) return rc;
   }
-  static bool configured = false;
-  if (!configured) {
-    UNETK_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UNETK_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static DeviceOnce once;
+  UNETK_CUDA(once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e != cudaSuccess ? e : cudaFuncSetAttribute(conv3x3_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }));
   if (BW == 32) UNETK_CUDA(launch_pdl(conv3x3_rows_kernel<32>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
   else UNETK_CUDA(launch_pdl(conv3x3_rows_kernel<64>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
   UNETK_LAUNCHED();

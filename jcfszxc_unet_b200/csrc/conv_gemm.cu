@@ -380,12 +380,10 @@ __global__ void conv_stats_sums_kernel(const float* __restrict__ partial, int gr
 template <int BN, bool F32OUT>
 int launch_t(const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    UNETK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    C::kSmemBytes));
-    configured = true;
-  }
+  static DeviceOnce once;
+  UNETK_CUDA(once.run([] {
+    return cudaFuncSetAttribute(conv_gemm_kernel<BN, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  }));
   UNETK_CUDA(launch_pdl(conv_gemm_kernel<BN, F32OUT>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, p));
   UNETK_LAUNCHED();
   return 0;

@@ -8,12 +8,12 @@
 namespace unetk {
 
 namespace {
-std::mutex g_err_mu;
-char g_err[1024] = "";
+// errno-style: each thread sees the text of ITS last failing call (the autograd worker thread that runs a backward
+// must not read, or overwrite, the message of a forward failing on the main thread)
+thread_local char g_err[1024] = "";
 }  // namespace
 
 void set_error(const char* fmt, ...) {
-  std::lock_guard<std::mutex> lk(g_err_mu);
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -43,16 +43,16 @@ bool pdl_enabled() {
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 148;
+  static std::atomic<int> cached[64];   // per device ordinal; 0 = not queried yet
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::atomic<int>& slot = cached[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
-  return cached;
+  return n;
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

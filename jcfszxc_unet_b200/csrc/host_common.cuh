@@ -3,9 +3,11 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 
 namespace unetk {
 
@@ -62,8 +64,30 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 long long launch_count();
-int num_sms();
-const char* last_error();
+int num_sms();             // SM count of the CURRENT device (cached per device)
+const char* last_error();  // the calling thread's last error text (thread-local, errno-style)
+
+// One-time, per-device, thread-safe set-up of a kernel (cudaFuncSetAttribute for > 48 KB of dynamic shared memory is a
+// per-device property of the function): `static DeviceOnce once; UNETK_CUDA(once.run([&] { return cudaFunc...; }));`
+// A process that drives several devices, or calls from autograd worker threads, configures every (kernel, device) pair
+// exactly once (re-entrant, no hidden process-wide state).
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  std::mutex mu;
+  template <class Fn>
+  cudaError_t run(Fn&& fn) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.load(std::memory_order_relaxed) & bit) return cudaSuccess;
+    e = fn();
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
 
 // A bf16 tensor map with up to 5 dims. dims[0] is the contiguous one; strides_bytes[i] is the stride
 // of dims[i+1]. OOB elements read as zero. Returns 0 or a negative code (error text set).

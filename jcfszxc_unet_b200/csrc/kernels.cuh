@@ -7,7 +7,6 @@
 
 namespace unetk {
 const char* last_error();
-int probe_run(const void* a, const void* b, float* d, int mode, int shift, int bo, cudaStream_t stream);
 int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, cudaStream_t stream);
 // wgrad3x3.cu
 size_t wgrad3x3_workspace_bytes(int N, int H, int W, int M, int Nn);
@@ -41,6 +40,13 @@ int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const floa
                  const int64_t* copies_ld = nullptr);
 int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long long* idx, int N, int H, int W, int C,
                     cudaStream_t s);
+// unpool.cu
+int maxpool_codes_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, uint8_t* code, int N, int H, int W, int C,
+                      cudaStream_t s);
+int max_unpool_run(const void* x, int64_t x_ld, const void* where, int is_idx, void* out, int64_t out_ld, int N, int Ho,
+                   int Wo, int C, cudaStream_t s);
+int max_unpool_bwd_run(const void* dy, int64_t dy_ld, const void* where, int is_idx, void* dx, int64_t dx_ld, int accumulate,
+                       int N, int Ho, int Wo, int C, cudaStream_t s);
 int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
                     int accumulate, int N, int H, int W, int C, cudaStream_t s);
 int bn_bwd_reduce_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const void* gp, int64_t gp_ld,
@@ -76,8 +82,6 @@ int grad_clip_coef_run(const float* g, int64_t n, float gscale, float max_norm, 
                        cudaStream_t s);
 int rmsprop_run(float* p, const float* g, float* sq, float* buf, int64_t n, float lr, float alpha, float eps, float wd,
                 float momentum, const float* clip, const float* hyper, cudaStream_t s);
-int probe_mma_rate_run(int N, int grid, int a_shift_rows, int two_acc, int iters, int b_tiles, long long* out,
-                       cudaStream_t stream);
 // pack.cu
 long long pack_tiles(int A, int B);
 int pack_weights_run(const long long* table, int n, long long total_tiles, cudaStream_t stream);

@@ -266,11 +266,8 @@ int stem_tc_fwd_launch(const StemTc& G, const float* w, const float* bias, void*
   // CTAs per SM: bounded by TMEM (512 / CMAX columns); one CTA builds its patch tile while the others' MMAs /
   // stores run
   const int grid = stem_tc_fwd_grid(tiles, CMAX);
-  static bool configured = false;
-  if (!configured) {
-    UNETK_CUDA(cudaFuncSetAttribute(stem_tc_fwd_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static DeviceOnce once;
+  UNETK_CUDA(once.run([smem] { return cudaFuncSetAttribute(stem_tc_fwd_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));
   UNETK_CUDA(launch_pdl(stem_tc_fwd_kernel<CMAX>, dim3(grid), dim3(kTile), smem, s, G, w, bias, static_cast<__nv_bfloat16*>(y), y_ld, tiles,
                         stats_partial));
   UNETK_LAUNCHED();
@@ -447,11 +444,8 @@ int stem_tc_wgrad_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_
   }
   const int grid = stem_tc_wgrad_grid(tiles64);
   const int smem = 3 * kTile * 128 + 64 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    UNETK_CUDA(cudaFuncSetAttribute(stem_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static DeviceOnce once;
+  UNETK_CUDA(once.run([smem] { return cudaFuncSetAttribute(stem_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));
   UNETK_CUDA(launch_pdl(stem_tc_wgrad_kernel, dim3(grid), dim3(kTile), smem, s, P, static_cast<float*>(ws), static_cast<int>(tiles64)));
   UNETK_LAUNCHED();
   const int n = Cout * 9 * Cin;

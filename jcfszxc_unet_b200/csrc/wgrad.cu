@@ -300,12 +300,8 @@ __global__ void wgrad_reduce_sliced_kernel(const float* __restrict__ partial, fl
 template <int BN>
 int launch(const WgradParams& p, cudaStream_t stream) {
   using C = WCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    UNETK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    C::kSmemBytes));
-    configured = true;
-  }
+  static DeviceOnce once;
+  UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); }));
   const int items = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = items < num_sms() ? items : num_sms();
   UNETK_CUDA(launch_pdl(wgrad_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, p));

@@ -359,11 +359,8 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
 
 template <int NT>
 int launch(const W3Params& p, const W3Plan& pl, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    UNETK_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static DeviceOnce once;
+  UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(wgrad3x3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
   const int items = (pl.paired == 2 ? pl.n_tiles : (pl.paired ? 2 * pl.n_tiles : (pl.rows2 ? 2 : 3) * pl.m_tiles * pl.n_tiles)) * pl.ksplit;
   const int grid = items < num_sms() ? items : num_sms();
   UNETK_CUDA(launch_pdl(wgrad3x3_kernel<NT>, dim3(grid), dim3(kThreads), pl.smem_bytes, stream, p));

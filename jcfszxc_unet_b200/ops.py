@@ -330,6 +330,42 @@ def maxpool_bwd(x, dy, dx, accumulate=False):
     _lib.call("unetk_maxpool2x2_bwd", xp, xld, dyp, dyld, dxp, dxld, int(accumulate), n, h, w, c, _stream())
 
 
+def maxpool_fwd_codes(x, y, code):
+    """MaxPool2d(2) whose arg-max leaves as byte codes: code uint8 NHWC [N, H/2, W/2, C] (window position 0..3)."""
+    n, h, w, c = x.shape
+    assert code.dtype == torch.uint8 and code.is_contiguous() and tuple(code.shape) == (n, h // 2, w // 2, c)
+    xp, xld = nhwc(x)
+    yp, yld = nhwc(y)
+    _lib.call("unetk_maxpool2x2_fwd_codes", xp, xld, yp, yld, code.data_ptr(), n, h, w, c, _stream())
+
+
+def _where(where, n, ho, wo, c):
+    if where.dtype == torch.uint8:
+        assert where.is_contiguous() and tuple(where.shape) == (n, ho, wo, c), "codes: uint8 NHWC [N, Ho, Wo, C]"
+        return 0
+    assert where.dtype == torch.int64 and where.is_contiguous() and tuple(where.shape) == (n, c, ho, wo), \
+        "indices: int64 [N, C, Ho, Wo] as F.max_pool2d(return_indices=True) returns them"
+    return 1
+
+
+def max_unpool(x, where, out):
+    """F.max_unpool2d(x, idx, 2, 2) on NHWC bf16 views (SegNet.py:115-138); `where`: byte codes or int64 indices."""
+    n, ho, wo, c = x.shape
+    assert tuple(out.shape) == (n, 2 * ho, 2 * wo, c)
+    xp, xld = nhwc(x)
+    op, old = nhwc(out)
+    _lib.call("unetk_max_unpool2x2", xp, xld, where.data_ptr(), _where(where, n, ho, wo, c), op, old, n, ho, wo, c, _stream())
+
+
+def max_unpool_bwd(dy, where, dx, accumulate=False):
+    n, ho, wo, c = dx.shape
+    assert tuple(dy.shape) == (n, 2 * ho, 2 * wo, c)
+    gp, gld = nhwc(dy)
+    dp, dld = nhwc(dx)
+    _lib.call("unetk_max_unpool2x2_bwd", gp, gld, where.data_ptr(), _where(where, n, ho, wo, c), dp, dld, int(accumulate),
+              n, ho, wo, c, _stream())
+
+
 def colsum(x, partial, out, accumulate=False):
     n, h, w, c = x.shape
     xp, xld = nhwc(x)

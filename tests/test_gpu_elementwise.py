@@ -424,3 +424,56 @@ def test_colsum():
     assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3)
     ops.colsum(x, partial, out, accumulate=True)
     assert torch.allclose(out, 2 * ref, rtol=1e-4, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------ pool / unpool pair
+@pytest.mark.parametrize("n,h,w,c,pad", [(2, 8, 12, 16, (0, 0)), (1, 64, 96, 64, (8, 24)), (3, 2, 2, 8, (0, 0)), (1, 130, 70, 40, (0, 8))])
+def test_max_unpool_bit_exact(n, h, w, c, pad):
+    """SegNet-style pool / unpool (SegNet.py:89-138): byte codes and int64 indices both reproduce F.max_unpool2d bit
+    for bit (ties, NaN and inf included), into channel slices of wider buffers; backward = gather."""
+    import torch.nn.functional as F
+
+    from jcfszxc_unet_b200 import ops
+    from oracle import unet_oracle as O
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(h * w + c)
+    x = torch.randn(n, h, w, c, device=dev, generator=g).bfloat16()
+    x[0, 0, :2, :] = 1.0                                   # ties inside a window
+    x[0, -1, -1, 0] = float("nan")
+    x[0, 1, 1, 1] = float("inf")
+    ho, wo = h // 2, w // 2
+    xn = x.float().permute(0, 3, 1, 2)
+    p_ref, idx_ref = F.max_pool2d(xn, 2, 2, return_indices=True)
+    # forward with codes
+    y = torch.empty(n, ho, wo, c, device=dev, dtype=torch.bfloat16)
+    code = torch.full((n, ho, wo, c), 255, device=dev, dtype=torch.uint8)
+    ops.maxpool_fwd_codes(x, y, code)
+    assert torch.equal(y.float().permute(0, 3, 1, 2).nan_to_num(7.0), p_ref.nan_to_num(7.0))
+    assert int(code.max()) <= 3
+    # the codes name the element ATen's indices name
+    cq = code.permute(0, 3, 1, 2).long()
+    hh = torch.arange(ho, device=dev).view(1, 1, ho, 1) * 2 + (cq >> 1)
+    ww = torch.arange(wo, device=dev).view(1, 1, 1, wo) * 2 + (cq & 1)
+    assert torch.equal(hh * w + ww, idx_ref)
+    # unpool of fresh values z through both index forms, into a channel slice of a wider buffer
+    z = torch.randn(n, ho, wo, c, device=dev, generator=g).bfloat16()
+    zn = z.float().permute(0, 3, 1, 2).contiguous()
+    ref = F.max_unpool2d(zn, idx_ref, 2, 2)
+    assert np.array_equal(O.max_unpool2x2_numpy(zn.cpu().numpy(), idx_ref.cpu().numpy()), ref.cpu().numpy())   # the oracle
+    for where in (code, idx_ref.contiguous()):
+        buf = torch.full((n, h, w, pad[0] + c + pad[1]), -3.0, device=dev, dtype=torch.bfloat16)
+        out = buf[..., pad[0]:pad[0] + c]
+        ops.max_unpool(z, where, out)
+        assert torch.equal(out.float().permute(0, 3, 1, 2), ref)
+        assert (buf[..., :pad[0]] == -3.0).all() and (buf[..., pad[0] + c:] == -3.0).all()
+        # backward: gather, plain and accumulating
+        dy = torch.randn(n, h, w, c, device=dev, generator=g).bfloat16()
+        dref = dy.float().permute(0, 3, 1, 2).flatten(2).gather(2, idx_ref.flatten(2)).view(n, c, ho, wo)
+        dx = torch.empty(n, ho, wo, c, device=dev, dtype=torch.bfloat16)
+        ops.max_unpool_bwd(dy, where, dx)
+        assert torch.equal(dx.float().permute(0, 3, 1, 2), dref)
+        base = torch.randn(n, ho, wo, c, device=dev, generator=g).bfloat16()
+        dx2 = base.clone()
+        ops.max_unpool_bwd(dy, where, dx2, accumulate=True)
+        assert torch.equal(dx2, (base.float() + dref.permute(0, 2, 3, 1)).bfloat16())

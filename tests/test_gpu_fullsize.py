@@ -17,8 +17,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from _parity import (LOGIT_CEILING, assert_close_bf16, check_blocks_teacher_forced, check_param_grads, informative, l2rel,
-                     record, rel)
+from _parity import check_blocks_teacher_forced, check_close, check_param_grads, l2rel, record
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -107,16 +106,11 @@ def _whole_model_step(name, n, h, w, backward=True):
     lg16, ls16, dl16, g16, st16 = _oracle_run(O, name, sd, images, labels, True, backward)
     record(f"{tag} loss ours {loss:.6f} fp32 {ls32:.6f} bf16-autocast {ls16:.6f} | dice-loss ours {dice_l:.6f} fp32 {dl32:.6f} "
            f"bf16-autocast {dl16:.6f}")
-    ok = informative(lg32, lg16, 1.25, LOGIT_CEILING)
+    ok = check_close(logits, lg32, lg16, f"{tag} logits") != "uninformative"
     if ok:
-        assert_close_bf16(logits, lg32, lg16, f"{tag} logits")
         assert abs(dice_l - dl32) <= 1e-3, (dice_l, dl32)
     else:
-        record(f"{tag} logits: ours vs fp32 l2 {l2rel(logits, lg32):.4g} max {rel(logits, lg32):.4g} | reference bf16-autocast vs fp32 "
-               f"l2 {l2rel(lg16, lg32):.4g} max {rel(lg16, lg32):.4g} | ours vs reference-bf16 l2 {l2rel(logits, lg16):.4g} — "
-               "UNINFORMATIVE input for a whole-model comparison (the reference's own bf16 run is beyond the ceiling): NOT "
-               "asserted here; this model's arithmetic is asserted block by block (teacher forced) below")
-        # what stays meaningful: the averaged quantities
+        # averaged quantities stay meaningful; the model's arithmetic is asserted block by block (teacher forced) below
         assert abs(dice_l - dl32) <= max(1e-3, min(1.5 * abs(dl16 - dl32), 5e-3)), (dice_l, dl32, dl16)
     assert abs(loss - ls32) <= 2e-2 * max(1.0, abs(ls32)), (loss, ls32)
     if backward:

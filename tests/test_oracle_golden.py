@@ -131,3 +131,23 @@ def test_product_path_has_no_cpu_fallback():
     m = _our_unet()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 3, 32, 32))
+
+
+def test_max_unpool_restatement_matches_torch():
+    """SegNet's pool / unpool pair (SegNet.py:89-138): the numpy restatement of F.max_unpool2d against torch itself on
+    CPU, on indices produced by F.max_pool2d(kernel 2, stride 2) including ties and NaN."""
+    import torch
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 5, 8, 12, generator=g)
+    x[0, 0, 0, :4] = 1.0                       # ties
+    x[1, 2, 3, 5] = float("nan")
+    p, idx = F.max_pool2d(x, 2, 2, return_indices=True)
+    z = torch.randn(p.shape, generator=g)
+    ref = F.max_unpool2d(z, idx, 2, 2)
+    got = O.max_unpool2x2_numpy(z.numpy(), idx.numpy())
+    assert np.array_equal(got, ref.numpy())
+    pv, pidx = O.maxpool2x2_with_indices_numpy(x.numpy())
+    assert np.array_equal(pidx, idx.numpy())
+    assert np.array_equal(O.max_unpool2x2_numpy(pv, pidx), F.max_unpool2d(p, idx, 2, 2).numpy(), equal_nan=True)

@@ -8,7 +8,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from jcfszxc_unet_b200 import _lib  # noqa: E402
+from tools.probe import build as _lib  # noqa: E402  (tools/probe/libunetk_probe.so, not the product library)
 
 
 def main():
