@@ -219,6 +219,12 @@ int unetk_max_unpool2x2(const void* x, int64_t x_ld, const void* where, int wher
 int unetk_max_unpool2x2_bwd(const void* dy, int64_t dy_ld, const void* where, int where_is_idx, void* dx,
                             int64_t dx_ld, int accumulate, int N, int Ho, int Wo, int C, void* stream);
 
+/* ---- F.pad of the Up block (unet_parts.py:64-67) and its backward (a crop) -------------------------------------
+ * dst[n,y,x,:] = src[n,y-oy,x-ox,:] where that lies inside src, else 0.  dst [N][Hd][Wd][C] / src [N][Hs][Ws][C] are
+ * bf16 NHWC views with pixel strides dst_ld / src_ld.  Forward: (oy, ox) = (diffY/2, diffX/2); backward: negated. */
+int unetk_shift_copy(void* dst, int64_t dst_ld, int Hd, int Wd, const void* src, int64_t src_ld, int Hs, int Ws, int oy,
+                     int ox, int N, int C, void* stream);
+
 /* ---- per-channel column sum (bias gradients of ConvTranspose2d / biased convs) -------------------- */
 int unetk_colsum(const void* x, int64_t x_ld, int64_t npix, int C, float* partial, float* out, int accumulate,
                  void* stream);

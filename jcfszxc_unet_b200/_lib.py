@@ -66,6 +66,7 @@ SIGNATURES = {
     "unetk_maxpool2x2_fwd_codes": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
     "unetk_max_unpool2x2": (_i, [_vp, _i64, _vp, _i, _vp, _i64, _i, _i, _i, _i, _vp]),
     "unetk_max_unpool2x2_bwd": (_i, [_vp, _i64, _vp, _i, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_shift_copy": (_i, [_vp, _i64, _i, _i, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "unetk_colsum": (_i, [_vp, _i64, _i64, _i, _fp, _fp, _i, _vp]),
     "unetk_head_partial_floats": (_sz, [_i64, _i]),
     "unetk_head_fwd": (_i, [_vp, _i64, _fp, _fp, _fp, _fp, _i, _i64, _i, _fp, _vp, _vp]),

@@ -129,9 +129,10 @@ def run_down(mod, x):
 def run_up(mod, x1, x2):
     n, c1, h1, w1 = x1.shape
     _, c2, h2, w2 = x2.shape
-    if (h2, w2) != (2 * h1, 2 * w1):
-        raise ValueError("Up: the skip must be exactly 2x the low-resolution input on this path "
-                         f"(got {h1}x{w1} and {h2}x{w2}); the F.pad branch of unet_parts.py:64-67 is not implemented")
+    dy_, dx_ = h2 - 2 * h1, w2 - 2 * w1
+    if dy_ < 0 or dx_ < 0:
+        raise ValueError(f"Up: the skip ({h2}x{w2}) is smaller than the up-sampled input ({2 * h1}x{2 * w1}); negative F.pad "
+                         "(cropping) never happens inside a U-Net and is not on this path")
     cup = mod.up.out_channels
     _check_c(c1, "Up")
     _check_c(c2, "Up")
@@ -141,7 +142,12 @@ def run_up(mod, x1, x2):
         lo = P.act(h1, w1, c1)
         cat = P.act(h2, w2, c2 + cup)
         skip = cat.slice(0, c2)            # cat([x2, up(x1)]) order of unet_parts.py:69
-        ConvT2x2(P, lo, mod.up, cat.slice(c2, cup))
+        if dy_ or dx_:                     # F.pad branch of unet_parts.py:64-67
+            tmp = P.act(2 * h1, 2 * w1, cup)
+            ConvT2x2(P, lo, mod.up, tmp)
+            engine.PadInto(P, tmp, cat.slice(c2, cup), dy_ // 2, dx_ // 2)
+        else:
+            ConvT2x2(P, lo, mod.up, cat.slice(c2, cup))
         out = _emit_double_conv(P, cat, mod.conv)
         return _BlockPlan(P.finalize(), [lo, skip], out, False)
 

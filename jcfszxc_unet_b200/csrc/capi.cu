@@ -336,6 +336,11 @@ int unetk_maxpool2x2_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int
   UNETK_CHECK(x && y, -1, "maxpool_fwd: null pointer");
   return maxpool_fwd_run(x, x_ld, y, y_ld, reinterpret_cast<long long*>(idx), N, H, W, C, S(stream));
 }
+int unetk_shift_copy(void* dst, int64_t dst_ld, int Hd, int Wd, const void* src, int64_t src_ld, int Hs, int Ws, int oy,
+                     int ox, int N, int C, void* stream) {
+  UNETK_CHECK(dst && src && Hd >= 0 && Wd >= 0 && Hs >= 0 && Ws >= 0, -1, "shift_copy: bad arguments");
+  return shift_copy_run(dst, dst_ld, Hd, Wd, src, src_ld, Hs, Ws, oy, ox, N, C, S(stream));
+}
 int unetk_maxpool2x2_fwd_codes(const void* x, int64_t x_ld, void* y, int64_t y_ld, uint8_t* code, int N, int H, int W,
                                int C, void* stream) {
   UNETK_CHECK(x && y && code, -1, "maxpool_fwd_codes: null pointer");

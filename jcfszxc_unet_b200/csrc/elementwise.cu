@@ -395,6 +395,28 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld, const __nv
       stg16(dx + pix * dx_ld + g * 8, pack8(o));
     }
   }
+  if constexpr (!ACC) {
+    // odd H / W (MaxPool2d floors): the last row / column belongs to no window and gets a zero gradient
+    const int64_t extra_w = (W & 1) ? static_cast<int64_t>(N) * H * cg : 0;             // pixels (n, h, W-1)
+    const int64_t extra_h = (H & 1) ? static_cast<int64_t>(N) * (W - (W & 1)) * cg : 0;  // pixels (n, H-1, w < 2*Wo)
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < extra_w + extra_h;
+         i += static_cast<int64_t>(gridDim.x) * kThreads) {
+      int64_t pix;
+      int g;
+      if (i < extra_w) {
+        g = static_cast<int>(i % cg);
+        const int64_t t = i / cg;
+        pix = (t / H * H + t % H) * W + (W - 1);
+      } else {
+        const int64_t j = i - extra_w;
+        g = static_cast<int>(j % cg);
+        const int64_t t = j / cg;
+        const int Wv = W - (W & 1);
+        pix = (t / Wv * H + (H - 1)) * W + t % Wv;
+      }
+      stg16(dx + pix * dx_ld + g * 8, make_uint4(0, 0, 0, 0));
+    }
+  }
 }
 
 // ------------------------------------------------------------------ backward of BN(+ReLU)(+pool,+skip add)
@@ -832,8 +854,7 @@ int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long lon
 int maxpool_bwd_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
                     int accumulate, int N, int H, int W, int C, cudaStream_t s) {
   CHECK_C(C);
-  UNETK_CHECK(H % 2 == 0 && W % 2 == 0, -1, "maxpool_bwd: odd spatial size %dx%d not supported", H, W);
-  const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
+  const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8) + 1;   // +1: the odd-edge loop runs even without windows
   if (accumulate)
     UNETK_CUDA(launch_pdl(maxpool_bwd_kernel<true>, dim3(flat_grid(total)), dim3(kThreads), 0, s, static_cast<const __nv_bfloat16*>(x), x_ld,
                                                                   static_cast<const __nv_bfloat16*>(dy), dy_ld,

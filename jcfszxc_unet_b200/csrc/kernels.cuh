@@ -40,6 +40,9 @@ int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const floa
                  const int64_t* copies_ld = nullptr);
 int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long long* idx, int N, int H, int W, int C,
                     cudaStream_t s);
+// pad.cu
+int shift_copy_run(void* dst, int64_t dst_ld, int Hd, int Wd, const void* src, int64_t src_ld, int Hs, int Ws, int oy, int ox,
+                   int N, int C, cudaStream_t s);
 // unpool.cu
 int maxpool_codes_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, uint8_t* code, int N, int H, int W, int C,
                       cudaStream_t s);

@@ -828,6 +828,29 @@ class Upsample2x(_Op):
             ops.upsample2x_bwd(self.out.g, self.x.g, self.mode, self.acc_x)
 
 
+class PadInto(_Op):
+    """F.pad of the Up block (unet_parts.py:64-67): the ConvTranspose output `x` (2h x 2w) lands at offset (oy, ox) =
+    (diffY // 2, diffX // 2) inside `out`, the up half of the concat buffer (the skip's size), with a zero border.
+    Only inputs whose sides are not multiples of 16 take this op (MaxPool2d floors); otherwise the ConvTranspose writes
+    the concat slice directly.  Backward: the crop of out.g."""
+
+    def __init__(self, plan: Plan, x: Act, out: Act, oy: int, ox: int):
+        assert x.C == out.C and x.N == out.N and 0 <= oy <= out.H - x.H and 0 <= ox <= out.W - x.W
+        self.plan, self.x, self.out, self.oy, self.ox = plan, x, out, oy, ox
+        plan.ops.append(self)
+
+    def plan_bwd(self, plan):
+        if plan.with_grad and self.x.g is not None and plan.grad_acc(self.x):
+            raise RuntimeError("PadInto: the padded tensor must not have other consumers")
+
+    def fwd(self):
+        ops.shift_copy(self.out.t, self.x.t, self.oy, self.ox)
+
+    def bwd(self):
+        if self.x.g is not None:
+            ops.shift_copy(self.x.g, self.out.g, -self.oy, -self.ox)
+
+
 class BNAct(_Op):
     """Stand-alone BatchNorm2d (+ReLU) on an existing activation: the pre-activation of ResidualConv
     (unet_parts.py:458-459).  Statistics pass + apply in forward; reduce + apply in backward, accumulating
@@ -1026,32 +1049,48 @@ def _require(cond, msg):
 
 def build_unet_plan(model, N: int, H: int, W: int, device, training: bool, grad_views=None,
                     with_grad: bool | None = None) -> Plan:
-    """Wire the vanilla U-Net (reference UNetFamily/UNet.py:14-55) into a Plan."""
-    _require(H % 16 == 0 and W % 16 == 0 and H >= 16 and W >= 16,
-             f"UNet plan needs H, W divisible by 16 (got {H}x{W}); F.pad of odd sizes is not on this path")
+    """Wire the vanilla U-Net (reference UNetFamily/UNet.py:14-55) into a Plan.  Any H, W >= 16: where a level's size
+    is odd, MaxPool2d floors (the fused pool is replaced by the stand-alone op) and the Up block pads the ConvTranspose
+    output to the skip's size (unet_parts.py:64-67, PadInto) — exactly what the reference does."""
+    _require(H >= 16 and W >= 16, f"UNet plan needs H, W >= 16 (got {H}x{W}): four 2x2 max-pools")
     P = Plan(device, N, H, W, training, with_grad)
     dcs = [model.inc.double_conv] + [getattr(model, f"down{i}").maxpool_conv[1].double_conv for i in range(1, 5)]
     C = [dc[3].out_channels for dc in dcs]
+    hs, ws = [H], [W]
+    for _ in range(4):
+        hs.append(hs[-1] // 2)
+        ws.append(ws[-1] // 2)
     # cat[i] = [skip_i | up_i]; gradients of both halves live in one buffer as well
-    cats = [P.act(H >> i, W >> i, 2 * C[i]) for i in range(4)]
+    cats = [P.act(hs[i], ws[i], 2 * C[i]) for i in range(4)]
     x = P.image
     for i, dc in enumerate(dcs):
-        h, w = H >> i, W >> i
+        h, w = hs[i], ws[i]
         mid = P.act(h, w, dc[0].out_channels)
         ConvBNReLU(P, x, dc[0], dc[1], mid)
         if i < 4:
             out = cats[i].slice(0, C[i])
-            pooled = P.act(h >> 1, w >> 1, C[i])
+            pooled = P.act(hs[i + 1], ws[i + 1], C[i])
         else:
             out, pooled = P.act(h, w, C[i]), None
-        ConvBNReLU(P, mid, dc[3], dc[4], out, pooled)
+        if pooled is not None and (h % 2 or w % 2):
+            ConvBNReLU(P, mid, dc[3], dc[4], out)
+            MaxPool2x2(P, out, pooled)          # odd size: the last row / column belongs to no window
+        else:
+            ConvBNReLU(P, mid, dc[3], dc[4], out, pooled)
         x = pooled if pooled is not None else out
     y = x
     for j, i in enumerate((3, 2, 1, 0)):
         up = getattr(model, f"up{j + 1}")
-        ConvT2x2(P, y, up.up, cats[i].slice(C[i], C[i]))
+        dst = cats[i].slice(C[i], C[i])
+        dy_, dx_ = hs[i] - 2 * y.H, ws[i] - 2 * y.W
+        if dy_ or dx_:
+            tmp = P.act(2 * y.H, 2 * y.W, C[i])
+            ConvT2x2(P, y, up.up, tmp)
+            PadInto(P, tmp, dst, dy_ // 2, dx_ // 2)
+        else:
+            ConvT2x2(P, y, up.up, dst)
         dc = up.conv.double_conv
-        h, w = H >> i, W >> i
+        h, w = hs[i], ws[i]
         mid = P.act(h, w, dc[0].out_channels)
         ConvBNReLU(P, cats[i], dc[0], dc[1], mid)
         y = P.act(h, w, dc[3].out_channels)

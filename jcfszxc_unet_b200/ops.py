@@ -366,6 +366,16 @@ def max_unpool_bwd(dy, where, dx, accumulate=False):
               n, ho, wo, c, _stream())
 
 
+def shift_copy(dst, src, oy: int, ox: int):
+    """dst[n,y,x,:] = src[n,y-oy,x-ox,:] inside src, else 0 (F.pad of Up, unet_parts.py:64-67; negative offsets crop)."""
+    n, hd, wd, c = dst.shape
+    _, hs, ws, _ = src.shape
+    assert src.shape[0] == n and src.shape[3] == c
+    dp, dld = nhwc(dst)
+    sp, sld = nhwc(src)
+    _lib.call("unetk_shift_copy", dp, dld, hd, wd, sp, sld, hs, ws, int(oy), int(ox), n, c, _stream())
+
+
 def colsum(x, partial, out, accumulate=False):
     n, h, w, c = x.shape
     xp, xld = nhwc(x)

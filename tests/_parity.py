@@ -24,7 +24,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REPORT = os.environ.get("UNETK_PARITY_REPORT", os.path.join(ROOT, "gpurun_out", "r02_parity_report.txt"))
 
 LOGIT_FLOOR, LOGIT_CEILING = 2e-2, 5e-2        # north_star: "logits within 2e-2 relative"
-GRAD_FLOOR, GRAD_CEILING = 5e-2, 1.5e-1        # gradients: bf16 noise of every layer above accumulates
+# gradients: sums over up to 4.2 M pixels of products of bf16 values whose noise every layer above has amplified; the
+# reference's OWN bf16 weight gradients of a single RRCNN block are 0.07-0.20 away from fp32.  A gradient tensor is
+# asserted within max(5e-2, 1.5 x the reference's own bf16 deviation), never looser than 0.25 (a missing term, a wrong
+# scale or a sign error shows up as 0.3 ... 2).
+GRAD_FLOOR, GRAD_CEILING, GRAD_SLACK = 5e-2, 2.5e-1, 1.5
 
 
 def record(line: str) -> None:
@@ -97,7 +101,7 @@ def check_param_grads(ours: dict, g32: dict, g16: dict, tag: str) -> tuple:
     for k in g32:
         if float(g32[k].abs().max()) < 1e-4 * gmax:
             continue   # conv bias in front of a train-mode BatchNorm: zero gradient up to rounding noise
-        st = check_close(ours[k], g32[k], g16[k], f"{tag} d {k}", GRAD_FLOOR, 2.5, GRAD_CEILING, use_max=False)
+        st = check_close(ours[k], g32[k], g16[k], f"{tag} d {k}", GRAD_FLOOR, GRAD_SLACK, GRAD_CEILING, use_max=False)
         n_ok += st != "uninformative"
         n_weak += st == "uninformative"
     keys = [k for k in g32]
@@ -198,10 +202,13 @@ def check_blocks_teacher_forced(O, model, name: str, images, backward: bool = Tr
         what = f"{tag}{name} {prefix.rstrip('.')} ({fname}, in {'+'.join(str(tuple(t.shape)) for t in ins)})"
 
         def oracle(bf16):
-            s = {k: v.clone() for k, v in local.items()}
+            # the "fp32" role is played by float64 on the GPU: cuDNN's fp32 (TF32 off) convolution on channels_last input
+            # returns wrong results at some benchmark shapes (profiles/r02_cudnn_fp32_channels_last_wrong.txt)
+            cast = (lambda t: t.clone()) if bf16 else (lambda t: t.double() if t.is_floating_point() else t.clone())
+            s = {k: cast(v) for k, v in local.items()}
             for k in pnames:
                 s[k].requires_grad_(backward)
-            xs = [t.clone().requires_grad_(backward and not image_in) for t in ins]
+            xs = [cast(t).requires_grad_(backward and not image_in) for t in ins]
             with O.autocast_ctx(dev.type, bf16):
                 y = fn(*xs, s, prefix, *extra)
             return y, xs, s
@@ -216,11 +223,11 @@ def check_blocks_teacher_forced(O, model, name: str, images, backward: bool = Tr
             continue
         gy = torch.randn(y32.shape, device=dev, generator=gen).bfloat16().float()
         (yo.float() * gy).sum().backward()
-        (y32.float() * gy).sum().backward()
+        (y32 * gy.double()).sum().backward()
         (y16.float() * gy).sum().backward()
         if not image_in:
             for i, (a, b, c) in enumerate(zip(xo, x32, x16)):
-                counts[check_close(a.grad, b.grad, c.grad, what + f" d input{i}", GRAD_FLOOR, 2.0, GRAD_CEILING, use_max=False)] += 1
+                counts[check_close(a.grad, b.grad, c.grad, what + f" d input{i}", GRAD_FLOOR, GRAD_SLACK, GRAD_CEILING, use_max=False)] += 1
         ours = _group_scalars({k: p.grad for k, p in ((prefix + n_, p_) for n_, p_ in sub.named_parameters())})
         g32 = _group_scalars({k: s32[k].grad for k in pnames})
         g16 = _group_scalars({k: s16[k].grad.float() for k in pnames})
@@ -228,11 +235,11 @@ def check_blocks_teacher_forced(O, model, name: str, images, backward: bool = Tr
         for k in g32:
             if float(g32[k].abs().max()) < 1e-4 * gmax:
                 continue   # conv bias in front of a train-mode BatchNorm: zero gradient up to rounding noise
-            counts[check_close(ours[k], g32[k], g16[k], what + f" d {k}", GRAD_FLOOR, 2.0, GRAD_CEILING, use_max=False)] += 1
+            counts[check_close(ours[k], g32[k], g16[k], what + f" d {k}", GRAD_FLOOR, GRAD_SLACK, GRAD_CEILING, use_max=False)] += 1
         sub.zero_grad(set_to_none=True)
         clear_plans(sub)
     record(f"{tag}{name}: {len(tape.records)} blocks teacher-forced; comparisons passed against the fp32 oracle: {counts['fp32']}, against "
            f"the bf16-autocast oracle: {counts['like']}, uninformative (sanity bound only): {counts['uninformative']}")
     done = counts["fp32"] + counts["like"]
-    assert counts["uninformative"] <= 0.2 * (done + counts["uninformative"]), "too few informative comparisons"
+    assert counts["uninformative"] <= 0.25 * (done + counts["uninformative"]), "too few informative comparisons"
     return len(tape.records)

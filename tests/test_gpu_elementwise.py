@@ -477,3 +477,43 @@ def test_max_unpool_bit_exact(n, h, w, c, pad):
         dx2 = base.clone()
         ops.max_unpool_bwd(dy, where, dx2, accumulate=True)
         assert torch.equal(dx2, (base.float() + dref.permute(0, 2, 3, 1)).bfloat16())
+
+
+@pytest.mark.parametrize("n,hs,ws,hd,wd,oy,ox,c", [(2, 6, 8, 7, 9, 0, 0, 16), (1, 4, 4, 7, 6, 1, 1, 8), (2, 7, 9, 6, 8, 0, 0, 24), (1, 5, 5, 5, 5, 0, 0, 8),
+                                                   (1, 7, 9, 5, 6, -1, -2, 8)])
+def test_shift_copy_is_f_pad(n, hs, ws, hd, wd, oy, ox, c):
+    """unetk_shift_copy == F.pad (zero border, unet_parts.py:64-67) and, with negated offsets, its backward (a crop)."""
+    from jcfszxc_unet_b200 import ops
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(hs * wd + c)
+    src = torch.randn(n, hs, ws, c, device=dev, generator=g).bfloat16()
+    buf = torch.full((n, hd, wd, c + 16), 9.0, device=dev, dtype=torch.bfloat16)
+    dst = buf[..., 8:8 + c]
+    ops.shift_copy(dst, src, oy, ox)
+    if hd >= hs:   # pad
+        ref = F.pad(src.permute(0, 3, 1, 2), [ox, wd - ws - ox, oy, hd - hs - oy]).permute(0, 2, 3, 1)
+    else:          # crop (negative pad)
+        ref = src[:, -oy:-oy + hd, -ox:-ox + wd] if (oy or ox) else src[:, :hd, :wd]
+    assert torch.equal(dst, ref)
+    assert (buf[..., :8] == 9.0).all() and (buf[..., 8 + c:] == 9.0).all()
+
+
+@pytest.mark.parametrize("n,h,w,c", [(1, 7, 9, 8), (2, 5, 6, 16), (1, 6, 5, 8)])
+def test_maxpool_odd_sizes_floor(n, h, w, c):
+    """MaxPool2d(2) floors odd sizes; the last row / column belongs to no window: zero gradient (written, not skipped)."""
+    from jcfszxc_unet_b200 import ops
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(h * w)
+    x = torch.randn(n, h, w, c, device=dev, generator=g).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 2)
+    gy = torch.randn(yr.shape, device=dev, generator=g).bfloat16().float()
+    yr.backward(gy)
+    y = torch.empty(n, h // 2, w // 2, c, device=dev, dtype=torch.bfloat16)
+    ops.maxpool_fwd(x, y)
+    assert torch.equal(y.float().permute(0, 3, 1, 2), yr.detach())
+    dx = torch.full((n, h, w, c), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.maxpool_bwd(x, gy.permute(0, 2, 3, 1).contiguous().bfloat16(), dx)
+    assert torch.equal(dx.float().permute(0, 3, 1, 2), xr.grad)

@@ -61,8 +61,17 @@ def _inputs(seed, n, h, w):
 
 
 def _oracle_run(O, name, sd, images, labels, bf16, backward=True):
+    """bf16=True: the oracle under bf16 autocast (stock cuDNN kernels).  bf16=False: the oracle in FLOAT64 — stronger
+    than the fp32 run it stands in for, and necessary: cuDNN's fp32 (TF32 off) convolution on channels_last input is wrong
+    by O(1) in ~3 % of the outputs at two layer shapes of this very step (1024->512 @64^2 and 512->256 @128^2 at batch 16;
+    tools/diag_conv_ref.py, profiles/r02_cudnn_fp32_channels_last_wrong.txt), which put the first round-2 run of this test
+    5.8 % away from BOTH bf16 implementations."""
     names = O.param_names(sd)
-    s = {k: v.clone() for k, v in sd.items()}
+    if bf16:
+        s = {k: v.clone() for k, v in sd.items()}
+    else:
+        s = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+        images, labels = images.double(), labels.double()
     for k in names:
         s[k].requires_grad_(backward)
     with torch.set_grad_enabled(backward):
@@ -70,7 +79,7 @@ def _oracle_run(O, name, sd, images, labels, bf16, backward=True):
         if backward:
             ls.backward()
     grads = {k: s[k].grad.float() for k in names} if backward else None
-    out = lg.detach().float(), float(ls), float(dl), grads, {k: v.detach() for k, v in s.items() if "running" in k}
+    out = lg.detach().float(), float(ls), float(dl), grads, {k: v.detach().float() for k, v in s.items() if "running" in k}
     del s, lg, ls
     torch.cuda.empty_cache()
     return out
@@ -162,9 +171,14 @@ def test_conv3x3_real_shapes_b16(s, cin, cout):
     partial = torch.empty(max(lib.unetk_conv_stats_partial_floats(cout), lib.unetk_chan_partial_floats(n * s * s, cout), 4096), device=DEV)
     sums = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
     ops.conv_fwd_stats(x, w_ab, None, y, partial, sums, 3, 1)
-    xn = x.float().permute(0, 3, 1, 2)
-    ref = F.conv2d(xn, wt.bfloat16().float(), None, padding=1).permute(0, 2, 3, 1)
+    xn = x.double().permute(0, 3, 1, 2)           # float64 references: see _oracle_run
+    wq = wt.bfloat16().double()
+    ref = F.conv2d(xn, wq, None, padding=1).permute(0, 2, 3, 1)
     _close(y, ref, what + " fwd", 1.2e-2)
+    with torch.autocast("cuda", dtype=torch.bfloat16):    # like for like: cuDNN's bf16 kernel on the same inputs
+        like = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, padding=1).permute(0, 2, 3, 1)
+    assert l2rel(y, like) <= 1e-3, ("fwd vs cuDNN bf16", l2rel(y, like))
+    del like
     yd = y.double()
     s_ref = torch.cat([yd.sum(dim=(0, 1, 2)), (yd * yd).sum(dim=(0, 1, 2))])
     assert torch.allclose(sums, s_ref, rtol=1e-4, atol=1e-4 * float(s_ref.abs().max())), (sums - s_ref).abs().max()
@@ -172,8 +186,8 @@ def test_conv3x3_real_shapes_b16(s, cin, cout):
     # dgrad
     dx = torch.empty(n, s, s, cin, device=DEV, dtype=torch.bfloat16)
     ops.conv_dgrad(dy, w_ba, dx, 3)
-    dyn = dy.float().permute(0, 3, 1, 2)
-    ref = F.conv_transpose2d(dyn, wt.bfloat16().float(), padding=1).permute(0, 2, 3, 1)
+    dyn = dy.double().permute(0, 3, 1, 2)
+    ref = F.conv_transpose2d(dyn, wq, padding=1).permute(0, 2, 3, 1)
     _close(dx, ref, what + " dgrad", 1.2e-2)
     del ref
     # wgrad: K = 16 * s * s pixels
@@ -197,20 +211,21 @@ def test_convT2x2_real_shapes_b16(s, cin, cout):
     w_dgrad, w_fwd = ops.pack_weight(wt)
     what = f"convT2x2 {cin}->{cout} @{s}^2"
     ops.convT_fwd(x, w_fwd, bias, y)
-    xn = x.float().permute(0, 3, 1, 2)
-    ref = F.conv_transpose2d(xn, wt.bfloat16().float(), bias, stride=2).permute(0, 2, 3, 1)
+    xn = x.double().permute(0, 3, 1, 2)
+    wq = wt.bfloat16().double()
+    ref = F.conv_transpose2d(xn, wq, bias.double(), stride=2).permute(0, 2, 3, 1)
     _close(y, ref, what + " fwd", 1.2e-2)
     assert float(cat[..., :cout].abs().max()) == 0
     dyc = torch.randn(n, 2 * s, 2 * s, 2 * cout, device=DEV, generator=g).bfloat16()
     dy = dyc[..., cout:]
     dx = torch.empty_like(x)
     ops.convT_dgrad(dy, w_dgrad, dx)
-    dyn = dy.float().permute(0, 3, 1, 2)
-    ref = F.conv2d(dyn, wt.bfloat16().float(), stride=2).permute(0, 2, 3, 1)
+    dyn = dy.double().permute(0, 3, 1, 2)
+    ref = F.conv2d(dyn, wq, stride=2).permute(0, 2, 3, 1)
     _close(dx, ref, what + " dgrad", 1.2e-2)
     dw = torch.empty(cin, cout, 2, 2, device=DEV)
     ops.convT_wgrad(x, dy, dw)
-    wr = wt.clone().requires_grad_(True)
+    wr = wt.double().requires_grad_(True)
     F.conv_transpose2d(xn, wr, None, stride=2).backward(dyn)
     _close(dw, wr.grad, what + " wgrad", 2e-3)
 

@@ -57,11 +57,15 @@ def _l2rel(a, b):
 
 
 def _assert_as_close_as_stock_bf16(ours, ref32, ref16, what, floor, slack):
-    """The shared acceptance rule (tests/_parity.py): within min(max(floor, slack x the reference's own bf16-autocast
-    deviation), ceiling) of the fp32 reference; ceiling 5e-2 for activations / logits, 1.5e-1 for gradients."""
-    from _parity import GRAD_CEILING, LOGIT_CEILING, assert_close_bf16
+    """The shared acceptance rule (tests/_parity.check_close).  Activations / logits (floor 2e-2) must pass against the
+    fp32 or the bf16-autocast oracle under the 5e-2 ceiling; gradient tensors (floor 5e-2) are judged at tensor level
+    with the gradient thresholds, and may be recorded as uninformative where the reference's own two runs disagree."""
+    from _parity import GRAD_CEILING, GRAD_FLOOR, GRAD_SLACK, assert_close_bf16, check_close
 
-    assert_close_bf16(ours, ref32, ref16, what, floor, slack, LOGIT_CEILING if floor <= 2e-2 else GRAD_CEILING)
+    if floor <= 2e-2:
+        assert_close_bf16(ours, ref32, ref16, what, floor, slack)
+    else:
+        check_close(ours, ref32, ref16, what, GRAD_FLOOR, GRAD_SLACK, GRAD_CEILING, use_max=False)
 
 
 def _whole_output_check(ours, ref32, ref16, what) -> bool:
