@@ -88,6 +88,105 @@ def _ref_train_step(model, opt, images, labels, bf16):
     return loss.detach(), masks_pred.detach(), bce_loss.detach(), dice.detach(), grads
 
 
+def _extract(path, picker):
+    """Parse a reference script that cannot be imported (h5py / matplotlib at module level) and return the AST nodes
+    `picker(tree)` selects — the UNMODIFIED statements, compiled below as they stand."""
+    import ast
+
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    return picker(tree)
+
+
+def _pin_sampler_and_tiling(O):
+    """(f2) train.py:126-155 + :201-241 (patch pools, the valid-centre filter, the random draw and the slicing loop) and
+    (f3) evaluate.py:28-96 (predict_full_image) are executed FROM THE REFERENCE'S SOURCE TEXT: the statements are cut
+    out of the files with `ast` (train_model's body cannot be imported — it needs HDF5 files, wandb-style logging and a
+    torch-1.x scheduler signature — and evaluate.py imports h5py / matplotlib at module level) and compiled unchanged
+    inside thin wrappers that only supply their free variables.  oracle.patch_sample_map / patch_batch /
+    predict_full_image must reproduce them bit for bit."""
+    import ast
+
+    out = []
+    # ---- evaluate.py: predict_full_image is a top-level function: compile it as is ----------------------------------
+    fn = _extract(os.path.join(REF, "evaluate.py"),
+                  lambda t: next(n for n in t.body if isinstance(n, ast.FunctionDef) and n.name == "predict_full_image"))
+    assert (fn.lineno, fn.end_lineno) == (28, 96), (fn.lineno, fn.end_lineno)
+    ns = {"np": np, "torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "evaluate.py", "exec"), ns)
+    ref_predict = ns["predict_full_image"]
+
+    class Tiny(torch.nn.Module):          # any deterministic fully-convolutional model works as the probe
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.c = torch.nn.Conv2d(3, 1, 3, padding=1)
+
+        def forward(self, x):
+            return self.c(x)
+
+    model = Tiny()
+    rng = np.random.RandomState(3)
+    for (h, w, ps, ov, bs) in ((70, 90, 32, 0.5, 4), (64, 64, 32, 0.25, 3), (50, 47, 16, 0.5, 5), (40, 40, 64, 0.5, 2)):
+        image = rng.rand(h, w, 3).astype(np.float32)
+        a = ref_predict(model, torch.device("cpu"), image, patch_size=ps, overlap=ov, batch_size=bs)
+        b = O.predict_full_image(lambda t: model(t), image, patch_size=ps, overlap=ov, batch_size=bs)
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), (h, w, ps, ov, bs)
+    out.append("predict_full_image (evaluate.py:28-96, compiled from the reference's source): bit-exact on 4 tilings incl. "
+               "ragged borders and a patch larger than the image")
+
+    # ---- train.py: statements of train_model's body -------------------------------------------------------------------
+    def pick(tree):
+        tm = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "train_model")
+        setup = [n for n in tm.body if 126 <= n.lineno <= 155]
+
+        def find_step_loop(nodes):
+            for n in nodes:
+                for sub in ast.walk(n):
+                    if isinstance(sub, ast.For) and isinstance(sub.target, ast.Name) and sub.target.id == "step":
+                        return sub
+            raise AssertionError("for step in range(steps) not found")
+
+        loop = find_step_loop(tm.body)
+        draw = [n for n in loop.body if 201 <= n.lineno <= 241]
+        return setup, draw
+
+    setup, draw = _extract(os.path.join(REF, "train.py"), pick)
+    assert setup and setup[0].lineno == 127 and draw and draw[0].lineno == 201 and draw[-1].end_lineno == 241, \
+        ([n.lineno for n in setup], [n.lineno for n in draw])
+    src = ast.Module(body=[
+        ast.FunctionDef(name="ref_setup", args=ast.arguments(posonlyargs=[], args=[ast.arg("train_dataset"), ast.arg("patch_size")],
+                                                             kwonlyargs=[], kw_defaults=[], defaults=[]),
+                        body=setup + [ast.parse("return images_data_pool, labels_data_pool, filtered_sample_map, half_patch").body[0]],
+                        decorator_list=[], type_params=[]),
+        ast.FunctionDef(name="ref_batch", args=ast.arguments(posonlyargs=[], args=[ast.arg(a) for a in (
+            "images_data_pool", "labels_data_pool", "filtered_sample_map", "half_patch", "batch_size")],
+            kwonlyargs=[], kw_defaults=[], defaults=[]),
+                        body=draw + [ast.parse("return batch_images, batch_labels").body[0]], decorator_list=[], type_params=[]),
+    ], type_ignores=[])
+    ast.fix_missing_locations(src)
+    ns = {"np": np, "torch": torch}
+    exec(compile(src, "train.py", "exec"), ns)
+    rng = np.random.RandomState(11)
+    n, hw, ps, bs = 3, 48, 16, 6
+    images = rng.rand(n, hw, hw, 3).astype(np.float32)              # HDF5 layout: [N, W, H, C]
+    masks = (rng.rand(n, hw, hw) < 0.3).astype(np.uint8)
+    labels = (rng.rand(n, hw, hw) < 0.1).astype(np.uint8)
+    pool, lpool, fmap, half = ns["ref_setup"]({"images": images, "masks": masks, "labels": labels}, ps)
+    omap = O.patch_sample_map(masks, ps)
+    assert all(np.array_equal(a, b) for a, b in zip(fmap, omap)) and half == ps // 2
+    for seed in (0, 1, 2):
+        np.random.seed(seed)                                         # the reference draws from the global numpy RNG
+        bi, bl = ns["ref_batch"](pool, lpool, fmap, half, bs)
+        ri = torch.from_numpy(bi).to(dtype=torch.float32, memory_format=torch.channels_last)     # train.py:245-253
+        rl = torch.from_numpy(bl).to(dtype=torch.float32)
+        oi, ol = O.patch_batch(images, labels, omap, bs, ps, np.random.RandomState(seed))
+        assert torch.equal(ri, oi) and torch.equal(rl, ol) and ri.stride() == oi.stride(), seed
+    out.append("patch pools + valid-centre filter (train.py:127-155) and the random draw + slicing loop + np.stack (:201-241), compiled "
+               "from the reference's source: sample map and 3 seeded batches bit-exact")
+    return out
+
+
 def main():
     global REF_DICE
     ref_unet, ref_parts, REF_DICE = _import_reference()
@@ -344,6 +443,9 @@ def main():
         vb[f"residual_conv_s{stride}_y"] = y.numpy()
     np.savez_compressed(os.path.join(GOLDEN, "variant_blocks_seeds11to17.npz"), **vb)
     report.append("conv_block / up_conv / Recurrent_block / RRCNN_block / Attention_block / ResidualConv(s1,s2): bit-exact")
+
+    # ---- 7. training-batch assembly and sliding-window inference: the reference's SOURCE TEXT, extracted ----------
+    report += _pin_sampler_and_tiling(O)
 
     print("ORACLE PINNED against /root/reference:")
     for r in report:

@@ -26,9 +26,9 @@ REPORT = os.environ.get("UNETK_PARITY_REPORT", os.path.join(ROOT, "gpurun_out", 
 LOGIT_FLOOR, LOGIT_CEILING = 2e-2, 5e-2        # north_star: "logits within 2e-2 relative"
 # gradients: sums over up to 4.2 M pixels of products of bf16 values whose noise every layer above has amplified; the
 # reference's OWN bf16 weight gradients of a single RRCNN block are 0.07-0.20 away from fp32.  A gradient tensor is
-# asserted within max(5e-2, 1.5 x the reference's own bf16 deviation), never looser than 0.25 (a missing term, a wrong
+# asserted within max(5e-2, 2 x the reference's own bf16 deviation), never looser than 0.25 (a missing term, a wrong
 # scale or a sign error shows up as 0.3 ... 2).
-GRAD_FLOOR, GRAD_CEILING, GRAD_SLACK = 5e-2, 2.5e-1, 1.5
+GRAD_FLOOR, GRAD_CEILING, GRAD_SLACK = 5e-2, 2.5e-1, 2.0
 
 
 def record(line: str) -> None:

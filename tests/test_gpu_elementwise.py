@@ -517,3 +517,74 @@ def test_maxpool_odd_sizes_floor(n, h, w, c):
     dx = torch.full((n, h, w, c), float("nan"), device=dev, dtype=torch.bfloat16)
     ops.maxpool_bwd(x, gy.permute(0, 2, 3, 1).contiguous().bfloat16(), dx)
     assert torch.equal(dx.float().permute(0, 3, 1, 2), xr.grad)
+
+
+def test_abi_is_reentrant_across_threads():
+    """the C ABI is called from the main thread (forward) and from autograd worker threads (backward).
+    (1) forward on the main thread, backward explicitly on another Python thread: same gradients as in one thread;
+    (2) unetk_last_error is per thread: a failing call on a worker thread neither clobbers nor reads the main thread's
+    message; (3) kernels that need > 48 KB of shared memory launch from a thread that never called them before."""
+    import threading
+
+    from jcfszxc_unet_b200 import _lib, ops
+    from UNetFamily.utils.unet_parts import DoubleConv
+
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    dc = DoubleConv(64, 64).to(dev).train()
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.randn(2, 64, 16, 160, device=dev, generator=g)
+    gy = torch.randn(2, 64, 16, 160, device=dev, generator=g)
+
+    def grads(threaded):
+        dc.zero_grad(set_to_none=True)
+        y = dc(x)
+        if threaded:
+            err = []
+
+            def work():
+                try:
+                    torch.cuda.set_device(dev)
+                    (y.float() * gy).sum().backward()
+                except Exception as e:  # pragma: no cover
+                    err.append(e)
+
+            t = threading.Thread(target=work)
+            t.start()
+            t.join()
+            assert not err, err
+        else:
+            (y.float() * gy).sum().backward()
+        torch.cuda.synchronize()
+        return [p.grad.clone() for p in dc.parameters()]
+
+    a, b = grads(False), grads(True)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+    # per-thread error text
+    bad = torch.zeros(1, 4, 4, 12, device=dev, dtype=torch.bfloat16)          # C = 12: not a multiple of 8
+    out = torch.zeros(1, 2, 2, 12, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(_lib.UnetkError, match="multiple of 8"):
+        ops.maxpool_fwd(bad, out)
+    main_msg = lib.unetk_last_error()
+    seen = {}
+
+    def worker():
+        torch.cuda.set_device(dev)
+        seen["before"] = lib.unetk_last_error()
+        rc = lib.unetk_shift_copy(out.data_ptr(), 12, 2, 2, bad.data_ptr(), 12, 4, 4, 0, 0, 1, 12, None)
+        seen["rc"], seen["after"] = rc, lib.unetk_last_error()
+        # first use of a big-shared-memory kernel from this thread
+        xw = torch.randn(1, 8, 128, 64, device=dev).bfloat16()
+        w_ab, _ = ops.pack_weight(torch.randn(64, 64, 3, 3, device=dev) * 0.05, True, False)
+        yw = torch.empty(1, 8, 128, 64, device=dev, dtype=torch.bfloat16)
+        ops.conv_fwd(xw, w_ab, None, yw, 3)
+        torch.cuda.synchronize()
+        seen["conv_ok"] = bool(torch.isfinite(yw.float()).all())
+
+    t = threading.Thread(target=worker)
+    t.start()
+    t.join()
+    assert seen["before"] in (b"", None) and seen["rc"] != 0 and b"shift_copy" in seen["after"] and seen["conv_ok"]
+    assert lib.unetk_last_error() == main_msg and b"multiple of 8" in main_msg
