@@ -64,30 +64,42 @@ def clear_plans(module: torch.nn.Module) -> None:
             c.clear()
 
 
+def plan_heads(plan):
+    """The output heads of a plan: one, or four with UNet++'s deep supervision (UNetPP.py:93-102)."""
+    return getattr(plan, "heads", None) or [plan.head]
+
+
 class _PlanFunction(torch.autograd.Function):
-    """forward: plan.forward(x) -> fp32 logits; backward: plan.backward(dlogits) -> parameter gradients.
-    Parameters are passed as inputs only so that autograd routes their gradients."""
+    """forward: plan.forward(x) -> fp32 logits (one tensor per head); backward: plan.backward(dlogits) -> parameter
+    gradients.  Parameters are passed as inputs only so that autograd routes their gradients."""
 
     @staticmethod
     def forward(ctx, plan, x, *params):
-        plan.head.labels = None
+        heads = plan_heads(plan)
+        for h in heads:
+            h.labels = None
         plan.forward(x)
         ctx.plan = plan
         ctx.generation = plan.generation
-        return plan.head.logits.clone()
+        outs = tuple(h.logits.clone() for h in heads)
+        return outs if len(outs) > 1 else outs[0]
 
     @staticmethod
-    def backward(ctx, dlogits):
+    def backward(ctx, *dlogits):
         plan = ctx.plan
         if plan.generation != ctx.generation:
             raise RuntimeError(
                 "jcfszxc_unet_b200: the activations saved for this backward were overwritten by a later forward "
                 "of the same shape; call backward before the next forward (static-buffer plans)")
-        plan.head.labels = None
-        plan.head.dlogits = dlogits.contiguous().float()
-        plan.head.gscale = 1.0
+        heads = plan_heads(plan)
+        for h, d in zip(heads, dlogits):
+            h.labels = None
+            # an output the loss did not use gets a zero gradient
+            h.dlogits = d.contiguous().float() if d is not None else torch.zeros_like(h.logits)
+            h.gscale = 1.0
         plan.backward()
-        plan.head.dlogits = None
+        for h in heads:
+            h.dlogits = None
         # views of the plan's gradient buffers: autograd's AccumulateGrad copies them into .grad (it cannot steal a
         # tensor the plan still references), so no second copy is made here
         grads = tuple(g if p.requires_grad else None for p, g in zip(plan.params, plan.grads()))
@@ -128,8 +140,12 @@ def run_model(model: torch.nn.Module, builder, x: torch.Tensor) -> torch.Tensor:
         # a plan with gradient buffers only when a backward can follow; BN mode follows model.training
         plan = plans.insert(key, builder(model, n, h, w, x.device, training_stats, None, need_grad))
     if need_grad:
-        return _PlanFunction.apply(plan, x, *plan.params)
+        out = _PlanFunction.apply(plan, x, *plan.params)
+        return list(out) if isinstance(out, tuple) else out
     with torch.no_grad():
-        plan.head.labels = None
+        heads = plan_heads(plan)
+        for h in heads:
+            h.labels = None
         plan.forward(x)
-        return plan.head.logits.clone()
+        outs = [h.logits.clone() for h in heads]
+        return outs if len(outs) > 1 else outs[0]

@@ -196,14 +196,13 @@ def build_resunet_plan(model, N, H, W, device, training, grad_views=None, with_g
 
 
 def build_nested_unet_plan(model, N, H, W, device, training, grad_views=None, with_grad=None) -> Plan:
-    """NestedUNet.forward (UNetFamily/UNetPP.py:73-107), deepsupervision=False (the reference's fixed setting, :37).
+    """NestedUNet.forward (UNetFamily/UNetPP.py:73-107); deepsupervision=False is the reference's fixed setting (:37),
+    True adds the heads final1..final3 on X[0][1..3] (:93-100) next to final4 on X[0][4].
 
     Node X[i][j] is produced straight into the concat buffer of the first node that reads it (conv{i}_{j+1}) and
     copied into the later ones (the reference re-copies all of them in every torch.cat); the bilinear up-sampling
     writes into the last slice of its consumer's concat buffer."""
     _check16(H, W, "NestedUNet")
-    if getattr(model, "deepsupervision", False):
-        raise NotImplementedError("NestedUNet(deepsupervision=True) is not on this path (the reference hard-codes False)")
     P = Plan(device, N, H, W, training, with_grad)
     nb = [model.conv0_0.conv[0].out_channels, model.conv1_0.conv[0].out_channels, model.conv2_0.conv[0].out_channels,
           model.conv3_0.conv[0].out_channels, model.conv4_0.conv[0].out_channels]
@@ -272,5 +271,13 @@ def build_nested_unet_plan(model, N, H, W, device, training, grad_views=None, wi
     nested(2, 2)
     nested(1, 3)
     nested(0, 4)
-    P.head = Head(P, X[0, 4], model.final, post_sigmoid=True, fuse=_producer(P, X[0, 4]))
+    if getattr(model, "deepsupervision", False):
+        last = _producer(P, X[0, 4])
+        # X[0][1..3] also feed the later nodes: their heads keep a private gradient buffer that is added to the node's
+        # gradient (Head(own_grad=True)); X[0][4] feeds only final4, whose head takes over the node's BatchNorm passes
+        P.heads = [Head(P, X[0, k], getattr(model, f"final{k}"), post_sigmoid=True, own_grad=True) for k in (1, 2, 3)]
+        P.heads.append(Head(P, X[0, 4], model.final4, post_sigmoid=True, fuse=last))
+        P.head = P.heads[-1]
+    else:
+        P.head = Head(P, X[0, 4], model.final, post_sigmoid=True, fuse=_producer(P, X[0, 4]))
     return P.finalize(grad_views)

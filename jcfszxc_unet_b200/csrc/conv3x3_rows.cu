@@ -62,6 +62,8 @@ struct RowsParams {
   CUtensorMap tmB;    // dims (K, ncols, 9), box (64, 64, 1)
   CUtensorMap tmOut;  // dims (ncols, W, H, N), box (64, 128, 1, 1)
   const float* bias;
+  const float* scale;   // non-null: eval-mode BatchNorm fold, out = relu?(acc * scale + bias) (the AFFINE instantiation)
+  int relu;
   float* stats_partial;
   int accumulate;
   int H, W, tiles_h, tiles_w, num_tiles, ncols, kchunks;
@@ -71,7 +73,7 @@ struct RowsParams {
   int8_t dh[9], dw[9], btap[9];
 };
 
-template <int BW>
+template <int BW, bool AFFINE>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_constant__ RowsParams p) {
   using C = RCfg<BW>;
   constexpr uint32_t kWBlock = C::kWBlock, kStagingBytes = C::kStagingBytes, kTmemCols = C::kTmemCols;
@@ -219,8 +221,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
     uint32_t chunk_ctr = 0;
     int it = 0;
     const uint32_t bias_a = smem_u32(bars) + 256;
+    const uint32_t scale_a = bias_a + 256;
     if (p.bias != nullptr) {
-      if (et < BW) sts_f32(bias_a + et * 4, (et < p.ncols) ? __ldg(p.bias + et) : 0.f);
+      if (et < BW) {
+        sts_f32(bias_a + et * 4, (et < p.ncols) ? __ldg(p.bias + et) : 0.f);
+        if constexpr (AFFINE) sts_f32(scale_a + et * 4, (et < p.ncols) ? __ldg(p.scale + et) : 0.f);
+      }
       named_bar_sync(1, kEpiThreads);
     }
     const int n_staging = p.n_staging;
@@ -265,7 +271,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(src[j]);
-          if (p.bias != nullptr) {
+          if constexpr (AFFINE) {
+            const float4 b0 = lds128_f(bias_a + (v * 8) * 4), b1 = lds128_f(bias_a + (v * 8 + 4) * 4);
+            const float4 s0 = lds128_f(scale_a + (v * 8) * 4), s1 = lds128_f(scale_a + (v * 8 + 4) * 4);
+            f[0] = fmaf(f[0], s0.x, b0.x); f[1] = fmaf(f[1], s0.y, b0.y); f[2] = fmaf(f[2], s0.z, b0.z); f[3] = fmaf(f[3], s0.w, b0.w);
+            f[4] = fmaf(f[4], s1.x, b1.x); f[5] = fmaf(f[5], s1.y, b1.y); f[6] = fmaf(f[6], s1.z, b1.z); f[7] = fmaf(f[7], s1.w, b1.w);
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+          } else if (p.bias != nullptr) {
             const float4 b0 = lds128_f(bias_a + (v * 8) * 4), b1 = lds128_f(bias_a + (v * 8 + 4) * 4);
             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
@@ -332,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
 // smem plan: resident weights + staging + as many row slots as fit (>= 3)
 bool rows_plan(int kchunks, int BW, int* slots, int* n_staging, uint32_t* smem_bytes) {
   const uint32_t kWBlock = BW * 128, kStagingBytes = 128 * BW * 2;
-  const uint32_t fixed = static_cast<uint32_t>(9 * kchunks) * kWBlock + 1024 /*align*/ + 256 /*barriers*/ + 256 /*bias*/;
+  const uint32_t fixed = static_cast<uint32_t>(9 * kchunks) * kWBlock + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias | scale*/;
   const uint32_t budget = 227 * 1024;
   for (int ns = 2; ns >= 1; --ns) {
     const uint32_t rest = fixed + ns * kStagingBytes;
@@ -381,6 +396,8 @@ int conv3x3_rows_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.fd_tiles_h = FastDiv(p.tiles_h);
   for (int t = 0; t < 9; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
   p.bias = d.bias;
+  p.scale = d.scale;
+  p.relu = d.relu;
   p.accumulate = d.accumulate;
   p.stats_partial = d.stats_sums ? d.stats_partial : nullptr;
   uint32_t smem_bytes = 0;
@@ -413,11 +430,17 @@ int conv3x3_rows_run(const ConvGemmDesc& d, cudaStream_t stream) {
   }
   static DeviceOnce once;
   UNETK_CUDA(once.run([] {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    return e != cudaSuccess ? e : cudaFuncSetAttribute(conv3x3_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaSuccess;
+    auto set = [&e](auto kernel) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); };
+    set(conv3x3_rows_kernel<64, false>); set(conv3x3_rows_kernel<32, false>);
+    set(conv3x3_rows_kernel<64, true>); set(conv3x3_rows_kernel<32, true>);
+    return e;
   }));
-  if (BW == 32) UNETK_CUDA(launch_pdl(conv3x3_rows_kernel<32>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
-  else UNETK_CUDA(launch_pdl(conv3x3_rows_kernel<64>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
+  if (p.scale != nullptr) {
+    if (BW == 32) UNETK_CUDA(launch_pdl(conv3x3_rows_kernel<32, true>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
+    else UNETK_CUDA(launch_pdl(conv3x3_rows_kernel<64, true>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
+  } else if (BW == 32) UNETK_CUDA(launch_pdl(conv3x3_rows_kernel<32, false>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
+  else UNETK_CUDA(launch_pdl(conv3x3_rows_kernel<64, false>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
   UNETK_LAUNCHED();
   if (d.stats_sums != nullptr) return conv_stats_sums_launch(d.stats_partial, grid, 1, BW, d.ncols, d.stats_sums, stream);
   return 0;

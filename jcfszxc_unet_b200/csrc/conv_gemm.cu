@@ -45,10 +45,12 @@ struct Cfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 7));
   static constexpr uint32_t kTmemCols = (BN == 192) ? 512 : 2 * BN;  // a power of two >= 32 (two BN-wide accumulators)
   static constexpr uint32_t kPipeBytes = kStages * kStageBytes;
-  static constexpr uint32_t kSmemBytes = kPipeBytes + 2 * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+  static constexpr uint32_t kSmemBytes = kPipeBytes + 2 * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 8 /*bias | scale*/;
 };
 
-template <int BN, bool F32OUT>
+// AFFINE: the eval-mode BatchNorm fold, out = relu?(acc * scale + shift) — its own instantiation, so the training kernels'
+// epilogue (instruction-fetch bound, see below) does not carry the extra code.
+template <int BN, bool F32OUT, bool AFFINE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN>;
@@ -191,9 +193,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // bias of this CTA's N tile (the grid is a multiple of num_n_tiles: a CTA keeps its N tile) -> shared memory once;
     // the per-element predicated __ldg it replaces was ~450 instructions of the chunk body
     const uint32_t bias_a = smem_u32(bars) + 256;
+    const uint32_t scale_a = bias_a + BN * 4;
     if (!F32OUT && p.bias != nullptr) {
       const int co_cta = static_cast<int>(blockIdx.x % p.num_n_tiles % p.tiles_per_q) * BN;
-      for (int i = et; i < BN; i += kEpiThreads) sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
+      for (int i = et; i < BN; i += kEpiThreads) {
+        sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
+        if constexpr (AFFINE) sts_f32(scale_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.scale + co_cta + i) : 0.f);
+      }
       named_bar_sync(1, kEpiThreads);
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -285,7 +291,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(src[j]);
-          if (p.bias != nullptr) {
+          if constexpr (AFFINE) {
+            const float4 b0 = lds128_f(bias_a + (c * 64 + v * 8) * 4), b1 = lds128_f(bias_a + (c * 64 + v * 8 + 4) * 4);
+            const float4 s0 = lds128_f(scale_a + (c * 64 + v * 8) * 4), s1 = lds128_f(scale_a + (c * 64 + v * 8 + 4) * 4);
+            f[0] = fmaf(f[0], s0.x, b0.x); f[1] = fmaf(f[1], s0.y, b0.y); f[2] = fmaf(f[2], s0.z, b0.z); f[3] = fmaf(f[3], s0.w, b0.w);
+            f[4] = fmaf(f[4], s1.x, b1.x); f[5] = fmaf(f[5], s1.y, b1.y); f[6] = fmaf(f[6], s1.z, b1.z); f[7] = fmaf(f[7], s1.w, b1.w);
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+          } else if (p.bias != nullptr) {
             const float4 b0 = lds128_f(bias_a + (c * 64 + v * 8) * 4), b1 = lds128_f(bias_a + (c * 64 + v * 8 + 4) * 4);
             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
@@ -377,20 +392,21 @@ __global__ void conv_stats_sums_kernel(const float* __restrict__ partial, int gr
   if (valid && threadIdx.y == 0) sums[i] = s;
 }
 
-template <int BN, bool F32OUT>
+template <int BN, bool F32OUT, bool AFFINE>
 int launch_t(const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
   static DeviceOnce once;
   UNETK_CUDA(once.run([] {
-    return cudaFuncSetAttribute(conv_gemm_kernel<BN, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    return cudaFuncSetAttribute(conv_gemm_kernel<BN, F32OUT, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   }));
-  UNETK_CUDA(launch_pdl(conv_gemm_kernel<BN, F32OUT>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, p));
+  UNETK_CUDA(launch_pdl(conv_gemm_kernel<BN, F32OUT, AFFINE>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, p));
   UNETK_LAUNCHED();
   return 0;
 }
 template <int BN>
 int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
-  return p.out_f32 != nullptr ? launch_t<BN, true>(p, grid, stream) : launch_t<BN, false>(p, grid, stream);
+  if (p.out_f32 != nullptr) return launch_t<BN, true, false>(p, grid, stream);
+  return p.scale != nullptr ? launch_t<BN, false, true>(p, grid, stream) : launch_t<BN, false, false>(p, grid, stream);
 }
 
 int pick_bn(int ncols, int q_groups) {
@@ -440,6 +456,8 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   UNETK_CHECK(d.stats_sums == nullptr || (d.q_groups == 1 && d.stats_partial != nullptr), -1,
               "conv_gemm: fused statistics need q_groups == 1 and a partial buffer");
 
+  UNETK_CHECK(d.scale == nullptr || (d.bias != nullptr && !d.accumulate && !d.out_f32 && d.stats_sums == nullptr), -1,
+              "conv_gemm: the affine (folded BatchNorm) epilogue needs a shift vector and excludes accumulate / fp32 output / statistics");
   if (d.out_f32) {
     UNETK_CHECK(!d.accumulate && d.stats_sums == nullptr, -1, "conv_gemm: the fp32 output path neither accumulates nor takes statistics");
     UNETK_CHECK(d.out_ld % 4 == 0 && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0), -1,
@@ -457,6 +475,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
       s.b = static_cast<const __nv_bfloat16*>(d.b) + static_cast<size_t>(c0) * d.K;
       s.out = static_cast<__nv_bfloat16*>(d.out) + c0;
       s.bias = d.bias ? d.bias + c0 : nullptr;
+      s.scale = d.scale ? d.scale + c0 : nullptr;
       if (int rc = conv_gemm_run(s, stream)) return rc;
     }
     return 0;
@@ -493,6 +512,8 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.a_step = d.a_step;
   for (int t = 0; t < d.taps; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
   p.bias = d.bias;
+  p.scale = d.scale;
+  p.relu = d.relu;
   p.accumulate = d.accumulate;
   p.stats_partial = d.stats_sums ? d.stats_partial : nullptr;
   {

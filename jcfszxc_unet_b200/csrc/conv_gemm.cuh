@@ -21,6 +21,10 @@ struct ConvGemmDesc {
   void* out;          // bf16 NHWC, spatial (H*out_step, W*out_step), pixel stride out_ld
   int64_t out_ld;
   const float* bias;  // fp32 [ncols] or null
+  // Eval-mode BatchNorm (+ReLU) folded into the epilogue: out = relu?(acc * scale[c] + bias[c]) with bias = the folded
+  // shift (beta - mean*scale + conv_bias*scale).  scale == null: out = acc + bias as before.
+  const float* scale;
+  int relu;
   int N, H, W;        // grid of GEMM rows (one row per (n,h,w))
   int K;              // reduction channels per tap
   int ncols;          // output channels (per phase q)
@@ -42,6 +46,8 @@ struct ConvGemmParams {
   CUtensorMap tmB;
   CUtensorMap tmOut[4];  // one per output phase q (only [0] unless ConvTranspose fwd)
   const float* bias;
+  const float* scale;    // non-null: affine epilogue (the AFFINE kernel instantiation)
+  int relu;
   float* stats_partial;  // [gridDim][2][BN] or null
   int H, W;
   int TH, TW, tw_shift, tiles_h, tiles_w;

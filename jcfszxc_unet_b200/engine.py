@@ -605,12 +605,14 @@ class Head:
     Reference: unet_parts.py:73-79; train.py:264-278; utils/dice_score.py:13-59."""
 
     def __init__(self, plan: Plan, x: Act, conv: torch.nn.Conv2d, post_sigmoid: bool = False,
-                 fuse: "ConvBNReLU | None" = None):
+                 fuse: "ConvBNReLU | None" = None, own_grad: bool = False):
         """post_sigmoid: the model ends in nn.Sigmoid (ResUNet.py:47-50, UNetPP.py:105-106); `logits` then holds
         sigmoid(conv) — the model output — which train.py:264-278 feeds to the loss as if it were a logit.
         fuse: the ConvBNReLU unit that produces `x`, when the head is the ONLY consumer of x (UNet.py:53-54,
         AttentionUNet.py:83-84, UNetPP.py:104-105): its BatchNorm + ReLU pass and their backward are folded into the
-        head's passes over the conv output, x and d(x) are never written (UNETK_FUSE_HEAD=0 keeps them apart)."""
+        head's passes over the conv output, x and d(x) are never written (UNETK_FUSE_HEAD=0 keeps them apart).
+        own_grad: x has other consumers (the deep-supervision heads of UNet++ on X[0][1..3], UNetPP.py:93-100): the head
+        writes d(x) into a private buffer which one add pass folds into x.g."""
         assert conv.kernel_size == (1, 1)
         if conv.out_channels != 1:
             raise NotImplementedError("the fused head supports n_classes == 1 (every BASELINE.json config)")
@@ -627,6 +629,8 @@ class Head:
         self.auto_finalize = True                   # trainer.py finalizes itself (collective between graph segments)
         self.gscale = 1.0
         self.acc_w = False
+        self.own_grad, self.acc_x = own_grad, False
+        self.xg = torch.empty((x.N, x.H, x.W, x.C), dtype=BF16, device=dev) if (own_grad and plan.with_grad) else None
         plan.need(_lib.load().unetk_head_partial_floats(self.npix, self.C), 0, self.C)
         self.prod = None
         if (fuse is not None and os.environ.get("UNETK_FUSE_HEAD", "1") != "0" and fuse.out is x and fuse.bn is not None
@@ -647,8 +651,10 @@ class Head:
     def plan_bwd(self, plan):
         if plan.with_grad:
             self.acc_w = plan.param_acc(self.conv.weight) | plan.param_acc(self.conv.bias)
-            if self.x.g is not None and plan.grad_acc(self.x):
-                raise RuntimeError("Head: the input of the output conv must not have other consumers")
+            if self.x.g is not None:
+                self.acc_x = plan.grad_acc(self.x)
+                if self.acc_x and not self.own_grad:
+                    raise RuntimeError("Head: the input of the output conv has other consumers; build it with own_grad=True")
 
     def refresh(self, force=False):
         pass
@@ -690,9 +696,12 @@ class Head:
                             dconv_bias=u.dbias)
             ops.bn_head_bwd_apply(u.raw.t, sc, sh, u.relu, w, self.dz, P.coef, u.raw.g)
             return
-        ops.head_bwd(self.x.t, w, self.labels, self.logits, self.fin, self.dlogits, self.gscale, self.x.g,
+        ops.head_bwd(self.x.t, w, self.labels, self.logits, self.fin, self.dlogits, self.gscale,
+                     self.xg if self.own_grad else self.x.g,
                      self.dw.view(-1) if self.dw is not None else None, self.db, P.partial, self.acc_w,
                      self.post_sigmoid)
+        if self.own_grad:
+            ops.add_n(self.x.g, [self.xg], accumulate=self.acc_x)
 
 
 class HeadMulti:

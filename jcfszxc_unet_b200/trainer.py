@@ -128,14 +128,24 @@ class Trainer:
         self.plan = self.builder(self.model, n, h, w, dev, True, self.grad_views, True)
         self.images = torch.zeros((n, c, h, w), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
         self.labels = torch.zeros((n, 1, h, w), dtype=torch.float32, device=dev)
-        head = self.plan.head
+        from .bridge import plan_heads
         from .engine import Head
-        if not isinstance(head, Head):
+        self.heads = plan_heads(self.plan)
+        if not all(isinstance(h, Head) for h in self.heads):
             raise NotImplementedError("Trainer fuses the reference's binary loss (train.py:264-278: BCE + dice on ONE logit map); "
                                       "with n_classes > 1 use model(x), your loss and loss.backward()")
-        head.labels = self.labels
-        head.dlogits = None
-        head.auto_finalize = False
+        # UNet++ with deep supervision (UNetPP.py:93-102) returns four maps; the loss is the MEAN over the heads of the
+        # reference recipe (0.5 BCE + 0.5 dice) applied to each map: every head back-propagates 1/4 of it.
+        # The heads' loss sums share one buffer so that data-parallel ranks all-reduce them in one call.
+        nh = len(self.heads)
+        self.loss_sums = torch.zeros((nh, 4), dtype=torch.float64, device=dev)
+        self.loss_mean = torch.zeros((), dtype=torch.float32, device=dev)
+        for k, head in enumerate(self.heads):
+            head.labels = self.labels
+            head.dlogits = None
+            head.auto_finalize = False
+            head.gscale = 1.0 / nh
+            head.loss_sums = self.loss_sums[k]
         if self.dp.sync_bn:
             self.plan.sync_sums = self.dp.reduce_bn_sums
         from . import _lib
@@ -207,7 +217,7 @@ class Trainer:
         P, head = self.plan, self.plan.head
         prog = [("k", self._seg_forward_packed)]
         if self.dp.sync_loss:
-            prog.append(("c", lambda: self.dp.reduce_loss_sums(head.loss_sums, head.npix)))
+            prog.append(("c", lambda: self.dp.reduce_loss_sums(self.loss_sums, head.npix)))
         hi, first = len(P.ops), True
         for k, ranges in self._cuts:
             if k < hi or first:
@@ -227,7 +237,8 @@ class Trainer:
 
     def _seg_backward(self, lo, hi, first):
         if first:
-            self.plan.head.finalize_loss(self._npix_total)
+            for h in self.heads:
+                h.finalize_loss(self._npix_total)
         # the weight-gradient side stream is joined where a captured segment ends, and before the optimizer
         self.plan.backward(lo, hi, join=(self.graph_mode == "segments" or lo == 0))
 
@@ -261,6 +272,13 @@ class Trainer:
             for _, fn in self._program:
                 fn()
         self._gen[0] += 1
+
+    def _loss(self):
+        """The step's loss as a device scalar: the head's, or the mean over the deep-supervision heads."""
+        if len(self.heads) == 1:
+            return self.heads[0].fin[0]
+        torch.stack([h.fin[0] for h in self.heads]).mean(dim=0, out=self.loss_mean)
+        return self.loss_mean
 
     def _capture(self):
         """Capture the step.  On a HIGH-priority stream: the plan's weight-gradient side stream is low priority, so
@@ -308,7 +326,7 @@ class Trainer:
                 self._capture()
             self._run_segments()
             self.steps_done += 1
-            return self.plan.head.fin[0]
+            return self._loss()
         n, c, h, w = images.shape
         if self.plan is None:
             self._build(n, c, h, w)
@@ -325,7 +343,7 @@ class Trainer:
             self._capture()
         self._run_segments()
         self.steps_done += 1
-        return self.plan.head.fin[0]
+        return self._loss()
 
     # ------------------------------------------------------------------------------------------------
     def prefetch(self, images: torch.Tensor, labels: torch.Tensor) -> None:
@@ -368,8 +386,11 @@ class Trainer:
         self._stage_free[k].record(main)
 
     def loss_terms(self):
-        """(loss, bce, dice) of the last step as device scalars."""
-        f = self.plan.head.fin
+        """(loss, bce, dice) of the last step as device scalars (deep supervision: means over the four heads)."""
+        if len(self.heads) == 1:
+            f = self.heads[0].fin
+            return f[0], f[1], f[2]
+        f = torch.stack([h.fin[:3] for h in self.heads]).mean(dim=0)
         return f[0], f[1], f[2]
 
     def grad_norm(self):

@@ -444,6 +444,57 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "variant_blocks_seeds11to17.npz"), **vb)
     report.append("conv_block / up_conv / Recurrent_block / RRCNN_block / Attention_block / ResidualConv(s1,s2): bit-exact")
 
+    # ---- 6b. UNet++ deep supervision: the reference class with its hard-coded attribute forced on ------------------
+    from UNetFamily import UNetPP as ref_pp
+
+    class _DS(ref_pp.NestedUNet):
+        """`self.deepsupervision = False` (UNetPP.py:38) becomes True; everything else is the reference's code."""
+
+        def __setattr__(self, k, v):
+            super().__setattr__(k, True if k == "deepsupervision" else v)
+
+    torch.manual_seed(42)
+    mds = _DS()
+    assert mds.deepsupervision and hasattr(mds, "final4") and not hasattr(mds, "final")
+    sd0 = {k: v.detach().clone() for k, v in mds.state_dict().items()}
+    images, labels = _inputs(7, 2, 32, 32)
+    mds.train()
+    with torch.no_grad():
+        y_ref = mds(images)
+        y_or = O.FORWARDS["NestedUNetDS"](images, {k: v.clone() for k, v in sd0.items()}, True)
+    assert len(y_ref) == 4 and all(torch.equal(a, b) for a, b in zip(y_ref, y_or)), "deep-supervision forward differs"
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        torch.manual_seed(42)
+        m2 = _DS().train()
+        y_bf = [o.float() for o in m2(images)]
+    mds.eval()
+    with torch.no_grad():
+        y_eval = mds(images)
+    # the documented loss (mean over the heads of train.py:264-278) and its gradients through the reference modules
+    torch.manual_seed(42)
+    m3 = _DS().train()
+    outs = m3(images)
+    crit = torch.nn.BCEWithLogitsLoss()
+    loss = sum(0.5 * crit(o, labels) + 0.5 * REF_DICE.dice_loss(torch.sigmoid(o).squeeze(1), labels.squeeze(1), multiclass=False)
+               for o in outs) / 4
+    loss.backward()
+    s3 = {k: v.clone() for k, v in sd0.items()}
+    for k in O.param_names(s3):
+        s3[k].requires_grad_(True)
+    _, lo, _, _ = O.forward_loss(s3, images, labels, bf16=False, training=True, model="NestedUNetDS")
+    lo.backward()
+    assert torch.equal(loss.detach(), lo.detach())
+    for k, p_ in m3.named_parameters():
+        assert torch.equal(p_.grad, s3[k].grad), k
+    np.savez_compressed(os.path.join(GOLDEN, "nestedunet_ds_seed42.npz"), images=images.numpy(), labels=labels.numpy(),
+                        **{f"out{k + 1}_train": y_ref[k].numpy() for k in range(4)},
+                        **{f"out{k + 1}_train_bf16_autocast": y_bf[k].numpy() for k in range(4)},
+                        **{f"out{k + 1}_eval": y_eval[k].numpy() for k in range(4)}, loss=np.float64(loss.item()),
+                        grad_final1_weight=m3.final1.weight.grad.numpy(), grad_conv0_0_w=m3.conv0_0.conv[0].weight.grad.numpy(),
+                        keys=np.array(list(sd0.keys())), final1_weight=sd0["final1.weight"].numpy())
+    report.append("NestedUNet with deepsupervision forced on (UNetPP.py:65-69,93-102): 4 outputs train/eval, mean-of-heads loss and "
+                  "all gradients bit-exact")
+
     # ---- 7. training-batch assembly and sliding-window inference: the reference's SOURCE TEXT, extracted ----------
     report += _pin_sampler_and_tiling(O)
 

@@ -20,7 +20,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _say(rank, msg):
+    print(f"[dp_worker rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
+    import faulthandler
+
+    faulthandler.dump_traceback_later(150, exit=True)      # a hang prints every thread's stack and ends the process
     from jcfszxc_unet_b200.dp import DataParallel
     from jcfszxc_unet_b200.trainer import Trainer
     from UNetFamily.UNet import UNet
@@ -54,6 +61,7 @@ def main():
         return all(torch.equal(a, all_[0]) for a in all_)
 
     report = {}
+    _say(rank, "eager data-parallel run")
     tr_e, l_e = run(False)
     assert in_sync(tr_e), "eager data-parallel replicas diverged"
     # 3. bucket schedule
@@ -68,20 +76,27 @@ def main():
     assert tail_mb < 2.0, f"the bucket reduced after the backward is {tail_mb:.2f} MB"
     report["buckets_mb"] = [round(sum(b - a for a, b in rs) * 4 / 2**20, 2) for _, rs in cuts]
     # 1. graph modes
+    _say(rank, "single-graph run")
     tr_g, l_g = run(True)
     report["graph_mode"] = tr_g.graph_mode
     assert in_sync(tr_g), "graph-mode replicas diverged"
     assert l_g == l_e, (l_g, l_e)
     assert torch.equal(tr_g.flat_p, tr_e.flat_p) and torch.equal(tr_g.sq, tr_e.sq), "single-graph DP != eager DP"
+    _say(rank, "per-segment graphs run")
     tr_s, l_s = run(True, env={"UNETK_DP_GRAPH": "0"})
     assert tr_s.graph_mode == "segments"
     assert l_s == l_e and torch.equal(tr_s.flat_p, tr_e.flat_p), "per-segment graphs != eager DP"
+    _say(rank, "one-bucket run")
     tr_1, l_1 = run(True, buckets=1)
     assert l_1 == l_e and torch.equal(tr_1.flat_p, tr_e.flat_p), "bucket count changed the result"
     del tr_g, tr_s, tr_1
     # 2. global batch, sync_bn: equal to one process on the whole batch
+    _say(rank, "sync_bn run")
+    faulthandler.cancel_dump_traceback_later()
+    faulthandler.dump_traceback_later(150, exit=True)
     tr_b, l_b = run(False, sync_bn=True)
     assert in_sync(tr_b)
+    _say(rank, "single-process reference run")
     torch.manual_seed(42)                        # rank 0's initial weights are what the broadcast distributed
     m1 = UNet(3, 1).to(dev).train()
     t1 = Trainer(m1, lr=lr, use_cuda_graph=False, dp=DataParallel(enabled=False))
@@ -92,6 +107,8 @@ def main():
     for a, b in zip(l_b, l_1p):
         assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), (l_b, l_1p)
     # gradient norm of the first step is the global one on every rank
+    _say(rank, "done")
+    faulthandler.cancel_dump_traceback_later()
     dist.barrier()
     if rank == 0:
         print("DP_WORKER_OK " + json.dumps(report), flush=True)

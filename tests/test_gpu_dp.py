@@ -17,7 +17,7 @@ def test_two_rank_nccl_parity():
     env.pop("UNETK_DP_GRAPH", None)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "dp_worker.py")],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+                       capture_output=True, text=True, timeout=420, cwd=ROOT, env=env)
     tail = (r.stdout + "\n" + r.stderr)[-4000:]
     assert r.returncode == 0 and "DP_WORKER_OK" in r.stdout, tail
     print([ln for ln in r.stdout.splitlines() if "DP_WORKER_OK" in ln][-1])

@@ -478,3 +478,100 @@ def test_variant_unsupported_shapes_fail_loudly():
     m = _make("ResUNet").to(DEV)
     with pytest.raises(ValueError, match="divisible by 8"):
         m(torch.zeros(1, 3, 20, 20, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------ deep supervision
+def _make_ds(seed=42):
+    from UNetFamily.UNetPP import NestedUNet
+
+    torch.manual_seed(seed)
+    return NestedUNet(3, 1, deepsupervision=True)
+
+
+def test_deep_supervision_forward_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "nestedunet_ds_seed42.npz"))
+    m = _make_ds().to(DEV).train()
+    x = torch.from_numpy(g["images"]).to(DEV)
+    with torch.no_grad():
+        ys = m(x)
+    assert isinstance(ys, list) and len(ys) == 4
+    for k, y in enumerate(ys):
+        ref = torch.from_numpy(g[f"out{k + 1}_train"]).to(DEV)
+        ref_bf = torch.from_numpy(g[f"out{k + 1}_train_bf16_autocast"]).to(DEV)
+        assert y.shape == ref.shape and y.dtype == torch.float32
+        assert _whole_output_check(y, ref, ref_bf, f"[golden NestedUNet deep supervision] output{k + 1}")
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 64, 64)])
+def test_deep_supervision_forward_backward_vs_oracle(n, h, w):
+    """model(x) -> four maps; the documented loss (mean over the heads of train.py:264-278) through autograd: outputs,
+    loss and every parameter gradient against the oracle (pinned to the reference class with deepsupervision on)."""
+    from _parity import check_param_grads
+    from oracle import unet_oracle as O
+
+    m = _make_ds().to(DEV).train()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    images, labels = _inputs(11, n, h, w)
+    images, labels = images.to(DEV), labels.to(DEV)
+    outs = m(images)
+    loss = sum(O.segmentation_loss(o, labels)[0] for o in outs) / 4
+    loss.backward()
+    names = O.param_names(sd)
+    ours = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    assert set(ours) == set(names)
+
+    def oracle_run(bf16):
+        s = {k: (v.clone() if bf16 or not v.is_floating_point() else v.double()) for k, v in sd.items()}
+        for k in names:
+            s[k].requires_grad_(True)
+        x, y = (images, labels) if bf16 else (images.double(), labels.double())
+        lg, ls, _, _ = O.forward_loss(s, x, y, bf16=bf16, training=True, model="NestedUNetDS")
+        ls.backward()
+        return [o.detach().float() for o in lg], float(ls), {k: s[k].grad.float() for k in names}
+
+    lg32, ls32, g32 = oracle_run(False)
+    lg16, _, g16 = oracle_run(True)
+    tag = f"[whole NestedUNet deep supervision {n}x3x{h}x{w}]"
+    for k in range(4):
+        assert _whole_output_check(outs[k].detach(), lg32[k], lg16[k], f"{tag} output{k + 1}")
+    assert abs(float(loss) - ls32) <= 2e-2 * max(1.0, abs(ls32))
+    check_param_grads({k: ours[k] for k in names}, g32, g16, tag)
+    # an unused output contributes a zero gradient: only head 4 in the loss == gradient of the plain model's loss path
+    m.zero_grad(set_to_none=True)
+    outs = m(images)
+    O.segmentation_loss(outs[3], labels)[0].backward()
+    assert m.final1.weight.grad is None or float(m.final1.weight.grad.abs().max()) == 0.0
+    assert float(m.final4.weight.grad.abs().max()) > 0
+
+
+def test_deep_supervision_trainer_vs_oracle():
+    """Fused training step with four heads: eager == CUDA graph bit for bit; three losses against oracle.train_step."""
+    from jcfszxc_unet_b200 import builders
+    from jcfszxc_unet_b200.trainer import Trainer
+    from oracle import unet_oracle as O
+
+    lr = 1e-3
+    results = {}
+    for graph in (False, True):
+        m = _make_ds().to(DEV).train()
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        tr = Trainer(m, lr=lr, use_cuda_graph=graph, builder=builders.build_nested_unet_plan)
+        losses = []
+        for step in range(3):
+            images, labels = _inputs(100 + step, 2, 32, 32)
+            losses.append(float(tr.step(images.to(DEV), labels.to(DEV))))
+        results[graph] = (losses, {k: v.detach().clone() for k, v in m.state_dict().items()})
+        assert len(tr.heads) == 4
+    assert results[False][0] == results[True][0]
+    for k in results[False][1]:
+        assert torch.equal(results[False][1][k], results[True][1][k]), k
+    names = O.param_names(sd)
+    sd16 = {k: v.clone() for k, v in sd.items()}
+    opt_state = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in names}
+    opt_state16 = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in names}
+    for step in range(3):
+        im, lb = _inputs(100 + step, 2, 32, 32)
+        ls, _, _ = O.train_step(sd, opt_state, im.to(DEV), lb.to(DEV), lr, bf16=False, model="NestedUNetDS")
+        ls16, _, _ = O.train_step(sd16, opt_state16, im.to(DEV), lb.to(DEV), lr, bf16=True, model="NestedUNetDS")
+        tol = max((3e-2 if step < 2 else 6e-2) * max(1.0, abs(float(ls))), 2.0 * abs(float(ls16) - float(ls)))
+        assert abs(results[True][0][step] - float(ls)) <= tol, (step, results[True][0], float(ls), float(ls16))

@@ -108,3 +108,31 @@ def test_variants_refuse_cpu_tensors():
     m = _make("ResUNet")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 3, 16, 16))
+
+
+# ------------------------------------------------------------------------------------------------ deep supervision
+def test_deep_supervision_module_and_oracle_match_reference():
+    """BASELINE.json configs[4] names UNet++ "deep supervision" (UNetPP.py:65-69, 93-102; hard-coded off in the
+    reference).  Golden vectors come from the reference class with the attribute forced on: our module must create the
+    same parameters with the same draws, and the oracle must replay outputs, the mean-of-heads loss and gradients."""
+    from UNetFamily.UNetPP import NestedUNet
+
+    g = np.load(os.path.join(GOLDEN, "nestedunet_ds_seed42.npz"), allow_pickle=False)
+    torch.manual_seed(42)
+    m = NestedUNet(3, 1, deepsupervision=True)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    assert list(sd.keys()) == [str(k) for k in g["keys"]] and "final4.bias" in sd and "final.weight" not in sd
+    assert np.array_equal(sd["final1.weight"].numpy(), g["final1_weight"])            # same RNG draws
+    assert NestedUNet().deepsupervision is False and "final.weight" in NestedUNet().state_dict()   # the default is the reference's
+    images, labels = _t(g["images"]), _t(g["labels"])
+    with torch.no_grad():
+        y = O.FORWARDS["NestedUNetDS"](images, {k: v.clone() for k, v in sd.items()}, True)
+    assert all(np.array_equal(y[k].numpy(), g[f"out{k + 1}_train"]) for k in range(4))
+    s = {k: v.clone() for k, v in sd.items()}
+    for k in O.param_names(s):
+        s[k].requires_grad_(True)
+    _, loss, _, _ = O.forward_loss(s, images, labels, bf16=False, training=True, model="NestedUNetDS")
+    loss.backward()
+    assert float(loss) == float(g["loss"])
+    assert np.array_equal(s["final1.weight"].grad.numpy(), g["grad_final1_weight"])
+    assert np.array_equal(s["conv0_0.conv.0.weight"].grad.numpy(), g["grad_conv0_0_w"])
