@@ -160,6 +160,21 @@ int unetk_bn_finalize(const double* sums, int C, double count, const float* gamm
 int unetk_bn_eval_fold(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
                        const float* running_var, float* scale, float* shift, float* mean, float* invstd,
                        void* stream);
+/* Eval mode, BatchNorm folded into the producing conv's epilogue (north_star: "BatchNorm-fold plus ReLU fused into the
+ * epilogue"; what evaluate.py:259-275 runs): the conv writes the post-BN(+ReLU) activation directly, the raw conv
+ * output and the bn_apply pass do not exist.
+ *   unetk_bn_eval_fold_bias    : scale = gamma*invstd, shift = beta - mean*scale + conv_bias*scale (conv_bias may be NULL)
+ *   unetk_conv3x3_fwd_affine   : y = relu?(conv3x3(x, w_pack) * scale + shift), stride 1 or 2, padding 1; N, Ho, Wo = output
+ *   unetk_stem_conv3x3_fwd_affine: the same for the image-input conv (fp32 image, fp32 weights [Cout][Cin][3][3])
+ * scale / shift: fp32 [Cout], 16-byte aligned. */
+int unetk_bn_eval_fold_bias(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
+                            const float* running_var, const float* conv_bias, float* scale, float* shift, void* stream);
+int unetk_conv3x3_fwd_affine(const void* x, int64_t x_ld, const void* w_pack, const float* scale, const float* shift,
+                             int relu, void* y, int64_t y_ld, int N, int Ho, int Wo, int Cin, int Cout, int stride,
+                             void* stream);
+int unetk_stem_conv3x3_fwd_affine(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w,
+                                  const float* scale, const float* shift, int relu, void* y, int64_t y_ld, int N, int H,
+                                  int W, int Cin, int Cout, void* stream);
 int unetk_bn_apply(const void* raw, int64_t raw_ld, const float* scale, const float* shift, const void* res,
                    int64_t res_ld, void* out, int64_t out_ld, void* pooled, int64_t pooled_ld, int N, int H, int W,
                    int C, int relu, void* stream);

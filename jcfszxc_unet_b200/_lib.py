@@ -55,6 +55,9 @@ SIGNATURES = {
     "unetk_bn_stats": (_i, [_vp, _i64, _i64, _i, _fp, _vp, _vp]),
     "unetk_bn_finalize": (_i, [_vp, _i, C.c_double, _fp, _fp, _f, _f, _fp, _fp, _vp, _fp, _fp, _fp, _fp, _vp]),
     "unetk_bn_eval_fold": (_i, [_i, _fp, _fp, _f, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
+    "unetk_bn_eval_fold_bias": (_i, [_i, _fp, _fp, _f, _fp, _fp, _fp, _fp, _fp, _vp]),
+    "unetk_conv3x3_fwd_affine": (_i, [_vp, _i64, _vp, _fp, _fp, _i, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "unetk_stem_conv3x3_fwd_affine": (_i, [_fp, _i64, _i64, _i64, _i64, _fp, _fp, _fp, _i, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_bn_apply": (_i, [_vp, _i64, _fp, _fp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_bn_apply_copies": (_i, [_vp, _i64, _fp, _fp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_bn_bwd_reduce": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -59,6 +59,36 @@ int unetk_conv3x3_fwd(const void* x, int64_t x_ld, const void* w_pack, const flo
                       int N, int H, int W, int Cin, int Cout, void* stream) {
   return conv_fwd_like(x, x_ld, w_pack, bias, y, y_ld, N, H, W, Cin, Cout, 3, false, stream);
 }
+// eval-mode BatchNorm (+ReLU) folded into the conv epilogue: y = relu?(conv(x) * scale + shift), stride 1 or 2
+int unetk_conv3x3_fwd_affine(const void* x, int64_t x_ld, const void* w_pack, const float* scale, const float* shift,
+                             int relu, void* y, int64_t y_ld, int N, int Ho, int Wo, int Cin, int Cout, int stride,
+                             void* stream) {
+  UNETK_CHECK(x && w_pack && y && scale && shift && N > 0 && Ho > 0 && Wo > 0 && Cin > 0 && Cout > 0, -1, "conv3x3_fwd_affine: bad arguments");
+  UNETK_CHECK(stride == 1 || stride == 2, -1, "conv3x3_fwd_affine: stride %d", stride);
+  ConvGemmDesc d{};
+  d.a = x; d.a_ld = x_ld; d.out = y; d.out_ld = y_ld; d.bias = shift; d.scale = scale; d.relu = relu;
+  d.b = w_pack;
+  d.N = N; d.H = Ho; d.W = Wo; d.K = Cin; d.ncols = Cout; d.q_groups = 1;
+  d.a_step = stride; d.out_step = 1;
+  d.taps = 9; d.b_taps = 9;
+  for (int t = 0; t < 9; ++t) {
+    d.dh[t] = static_cast<int8_t>(t / 3 - 1);
+    d.dw[t] = static_cast<int8_t>(t % 3 - 1);
+    d.btap[t] = static_cast<int8_t>(t);
+  }
+  return conv_gemm_run(d, S(stream));
+}
+int unetk_stem_conv3x3_fwd_affine(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w,
+                                  const float* scale, const float* shift, int relu, void* y, int64_t y_ld, int N, int H,
+                                  int W, int Cin, int Cout, void* stream) {
+  UNETK_CHECK(x && w && y && scale && shift, -1, "stem_conv3x3_fwd_affine: null pointer");
+  return stem_fwd_affine_run(x, sn, sc, sh, sw, w, scale, shift, relu, y, y_ld, N, H, W, Cin, Cout, S(stream));
+}
+int unetk_bn_eval_fold_bias(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
+                            const float* running_var, const float* conv_bias, float* scale, float* shift, void* stream) {
+  UNETK_CHECK(running_mean && running_var && scale && shift && C > 0, -1, "bn_eval_fold_bias: bad arguments");
+  return bn_eval_fold_bias_run(C, gamma, beta, eps, running_mean, running_var, conv_bias, scale, shift, S(stream));
+}
 size_t unetk_conv_stats_partial_floats(int Cout) {
   if (Cout < 8 || Cout % 8) return 0;
   return conv_gemm_stats_partial_floats(Cout);

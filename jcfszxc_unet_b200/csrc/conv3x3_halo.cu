@@ -41,7 +41,7 @@ struct HCfg {
   // (4 independent chains) and the epilogue adds the partial sums.
   static constexpr int kSplit = (BN == 64) ? 2 : 1;
   static constexpr uint32_t kTmemCols = 4 * BN * kSplit;       // 2 tiles x 2 rows x kSplit x BN
-  static constexpr uint32_t kSmemBytes = 2 * kHaloSlot + kBStages * kBBytes + kStaging * kStagingBytes + 1024 + 256 + BN * 8 /*bias | scale*/;
+  static constexpr uint32_t kSmemBytes = 2 * kHaloSlot + kBStages * kBBytes + kStaging * kStagingBytes + 1024 + 256 + BN * 4 /*bias*/;
 };
 
 struct HaloParams {
@@ -259,13 +259,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     int it = 0;
     // bias of this CTA's N tile -> shared memory once (see conv_gemm.cu)
     const uint32_t bias_a = smem_u32(bars) + 256;
-    const uint32_t scale_a = bias_a + BN * 4;
+    const float* scale_g = nullptr;   // AFFINE: read through the read-only cache (see conv_gemm.cu)
     if (p.bias != nullptr) {
       const int co_cta = static_cast<int>(blockIdx.x % p.num_n_tiles) * BN;
-      for (int i = et; i < BN; i += kEpiThreads) {
-        sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
-        if constexpr (AFFINE) sts_f32(scale_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.scale + co_cta + i) : 0.f);
-      }
+      for (int i = et; i < BN; i += kEpiThreads) sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
+      if constexpr (AFFINE) scale_g = p.scale + co_cta;
       named_bar_sync(1, kEpiThreads);
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -331,7 +329,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(src[j]);
             if constexpr (AFFINE) {
               const float4 b0 = lds128_f(bias_a + (c * 64 + v * 8) * 4), b1 = lds128_f(bias_a + (c * 64 + v * 8 + 4) * 4);
-              const float4 s0 = lds128_f(scale_a + (c * 64 + v * 8) * 4), s1 = lds128_f(scale_a + (c * 64 + v * 8 + 4) * 4);
+              float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+              if (colbase + v * 8 < p.ncols) {
+                s0 = __ldg(reinterpret_cast<const float4*>(scale_g + c * 64 + v * 8));
+                s1 = __ldg(reinterpret_cast<const float4*>(scale_g + c * 64 + v * 8 + 4));
+              }
               f[0] = fmaf(f[0], s0.x, b0.x); f[1] = fmaf(f[1], s0.y, b0.y); f[2] = fmaf(f[2], s0.z, b0.z); f[3] = fmaf(f[3], s0.w, b0.w);
               f[4] = fmaf(f[4], s1.x, b1.x); f[5] = fmaf(f[5], s1.y, b1.y); f[6] = fmaf(f[6], s1.z, b1.z); f[7] = fmaf(f[7], s1.w, b1.w);
               if (p.relu) {
@@ -413,7 +415,7 @@ int launch_t(HaloParams& p, int grid, cudaStream_t stream) {
   UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(conv3x3_halo_kernel<BN, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
   // weights resident when all 9*kchunks tiles fit next to the two halo slots and one staging buffer
   const uint32_t w_bytes = static_cast<uint32_t>(9 * p.kchunks) * C::kBBytes;
-  const uint32_t resident_smem = 2 * kHaloSlot + w_bytes + kStagingBytes + 1024 + 256 + BN * 8;
+  const uint32_t resident_smem = 2 * kHaloSlot + w_bytes + kStagingBytes + 1024 + 256 + BN * 4;
   p.resident = (resident_smem <= 227 * 1024) ? 1 : 0;
   const uint32_t smem_bytes = p.resident ? resident_smem : C::kSmemBytes;
   UNETK_CUDA(launch_pdl(conv3x3_halo_kernel<BN, AFFINE>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));

@@ -221,12 +221,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
     uint32_t chunk_ctr = 0;
     int it = 0;
     const uint32_t bias_a = smem_u32(bars) + 256;
-    const uint32_t scale_a = bias_a + 256;
     if (p.bias != nullptr) {
-      if (et < BW) {
-        sts_f32(bias_a + et * 4, (et < p.ncols) ? __ldg(p.bias + et) : 0.f);
-        if constexpr (AFFINE) sts_f32(scale_a + et * 4, (et < p.ncols) ? __ldg(p.scale + et) : 0.f);
-      }
+      if (et < BW) sts_f32(bias_a + et * 4, (et < p.ncols) ? __ldg(p.bias + et) : 0.f);
       named_bar_sync(1, kEpiThreads);
     }
     const int n_staging = p.n_staging;
@@ -273,7 +269,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(src[j]);
           if constexpr (AFFINE) {
             const float4 b0 = lds128_f(bias_a + (v * 8) * 4), b1 = lds128_f(bias_a + (v * 8 + 4) * 4);
-            const float4 s0 = lds128_f(scale_a + (v * 8) * 4), s1 = lds128_f(scale_a + (v * 8 + 4) * 4);
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;   // scale through the read-only cache (see conv_gemm.cu)
+            if (v * 8 < p.ncols) {
+              s0 = __ldg(reinterpret_cast<const float4*>(p.scale + v * 8));
+              s1 = __ldg(reinterpret_cast<const float4*>(p.scale + v * 8 + 4));
+            }
             f[0] = fmaf(f[0], s0.x, b0.x); f[1] = fmaf(f[1], s0.y, b0.y); f[2] = fmaf(f[2], s0.z, b0.z); f[3] = fmaf(f[3], s0.w, b0.w);
             f[4] = fmaf(f[4], s1.x, b1.x); f[5] = fmaf(f[5], s1.y, b1.y); f[6] = fmaf(f[6], s1.z, b1.z); f[7] = fmaf(f[7], s1.w, b1.w);
             if (p.relu) {
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_rows_kernel(const __grid_
 // smem plan: resident weights + staging + as many row slots as fit (>= 3)
 bool rows_plan(int kchunks, int BW, int* slots, int* n_staging, uint32_t* smem_bytes) {
   const uint32_t kWBlock = BW * 128, kStagingBytes = 128 * BW * 2;
-  const uint32_t fixed = static_cast<uint32_t>(9 * kchunks) * kWBlock + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias | scale*/;
+  const uint32_t fixed = static_cast<uint32_t>(9 * kchunks) * kWBlock + 1024 /*align*/ + 256 /*barriers*/ + 256 /*bias*/;
   const uint32_t budget = 227 * 1024;
   for (int ns = 2; ns >= 1; --ns) {
     const uint32_t rest = fixed + ns * kStagingBytes;

@@ -45,7 +45,7 @@ struct Cfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 7));
   static constexpr uint32_t kTmemCols = (BN == 192) ? 512 : 2 * BN;  // a power of two >= 32 (two BN-wide accumulators)
   static constexpr uint32_t kPipeBytes = kStages * kStageBytes;
-  static constexpr uint32_t kSmemBytes = kPipeBytes + 2 * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 8 /*bias | scale*/;
+  static constexpr uint32_t kSmemBytes = kPipeBytes + 2 * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
 
 // AFFINE: the eval-mode BatchNorm fold, out = relu?(acc * scale + shift) — its own instantiation, so the training kernels'
@@ -193,13 +193,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // bias of this CTA's N tile (the grid is a multiple of num_n_tiles: a CTA keeps its N tile) -> shared memory once;
     // the per-element predicated __ldg it replaces was ~450 instructions of the chunk body
     const uint32_t bias_a = smem_u32(bars) + 256;
-    const uint32_t scale_a = bias_a + BN * 4;
+    // AFFINE: the scale vector is read through the read-only cache (every thread of the CTA reads the same 32 bytes at a
+    // time: one broadcast transaction); the 227 KB of shared memory are full (BN = 256: 4 stages + 2 staging buffers)
+    const float* scale_g = nullptr;
     if (!F32OUT && p.bias != nullptr) {
       const int co_cta = static_cast<int>(blockIdx.x % p.num_n_tiles % p.tiles_per_q) * BN;
-      for (int i = et; i < BN; i += kEpiThreads) {
-        sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
-        if constexpr (AFFINE) sts_f32(scale_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.scale + co_cta + i) : 0.f);
-      }
+      for (int i = et; i < BN; i += kEpiThreads) sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
+      if constexpr (AFFINE) scale_g = p.scale + co_cta;
       named_bar_sync(1, kEpiThreads);
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -293,7 +293,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(src[j]);
           if constexpr (AFFINE) {
             const float4 b0 = lds128_f(bias_a + (c * 64 + v * 8) * 4), b1 = lds128_f(bias_a + (c * 64 + v * 8 + 4) * 4);
-            const float4 s0 = lds128_f(scale_a + (c * 64 + v * 8) * 4), s1 = lds128_f(scale_a + (c * 64 + v * 8 + 4) * 4);
+            // (live chunk: colbase + 64 <= round_up(ncols, 8); ncols % 8 == 0 and the group starts at a multiple of 8)
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+            if (colbase + v * 8 < p.ncols) {
+              s0 = __ldg(reinterpret_cast<const float4*>(scale_g + c * 64 + v * 8));
+              s1 = __ldg(reinterpret_cast<const float4*>(scale_g + c * 64 + v * 8 + 4));
+            }
             f[0] = fmaf(f[0], s0.x, b0.x); f[1] = fmaf(f[1], s0.y, b0.y); f[2] = fmaf(f[2], s0.z, b0.z); f[3] = fmaf(f[3], s0.w, b0.w);
             f[4] = fmaf(f[4], s1.x, b1.x); f[5] = fmaf(f[5], s1.y, b1.y); f[6] = fmaf(f[6], s1.z, b1.z); f[7] = fmaf(f[7], s1.w, b1.w);
             if (p.relu) {
@@ -456,6 +461,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   UNETK_CHECK(d.stats_sums == nullptr || (d.q_groups == 1 && d.stats_partial != nullptr), -1,
               "conv_gemm: fused statistics need q_groups == 1 and a partial buffer");
 
+  UNETK_CHECK(d.scale == nullptr || (reinterpret_cast<uintptr_t>(d.scale) & 15) == 0, -1, "conv_gemm: scale must be 16-byte aligned");
   UNETK_CHECK(d.scale == nullptr || (d.bias != nullptr && !d.accumulate && !d.out_f32 && d.stats_sums == nullptr), -1,
               "conv_gemm: the affine (folded BatchNorm) epilogue needs a shift vector and excludes accumulate / fp32 output / statistics");
   if (d.out_f32) {

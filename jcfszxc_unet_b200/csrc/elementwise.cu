@@ -152,6 +152,20 @@ __global__ void bn_eval_fold_kernel(int C, const float* gamma, const float* beta
   invstd_out[c] = invstd;
 }
 
+// eval mode, for the conv epilogue fold: scale = gamma * invstd, shift = beta - mean * scale + conv_bias * scale
+__global__ void bn_eval_fold_bias_kernel(int C, const float* gamma, const float* beta, float eps, const float* rm,
+                                         const float* rv, const float* conv_bias, float* scale, float* shift) {
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.f / sqrtf(rv[c] + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = fmaf(conv_bias ? conv_bias[c] - rm[c] : -rm[c], sc, b);
+}
+
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out,
                                        int accumulate) {
   pdl_trigger();
@@ -758,6 +772,13 @@ int bn_finalize_run(const double* sums, int C, double count, const float* gamma,
 int bn_eval_fold_run(int C, const float* gamma, const float* beta, float eps, const float* rm, const float* rv,
                      float* scale, float* shift, float* mean, float* invstd, cudaStream_t s) {
   UNETK_CUDA(launch_pdl(bn_eval_fold_kernel, dim3((C + 127) / 128), dim3(128), 0, s, C, gamma, beta, eps, rm, rv, scale, shift, mean, invstd));
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+int bn_eval_fold_bias_run(int C, const float* gamma, const float* beta, float eps, const float* rm, const float* rv,
+                          const float* conv_bias, float* scale, float* shift, cudaStream_t s) {
+  UNETK_CUDA(launch_pdl(bn_eval_fold_bias_kernel, dim3((C + 127) / 128), dim3(128), 0, s, C, gamma, beta, eps, rm, rv, conv_bias, scale, shift));
   UNETK_LAUNCHED();
   return 0;
 }

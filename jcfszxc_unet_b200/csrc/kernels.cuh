@@ -40,6 +40,11 @@ int bn_apply_run(const void* raw, int64_t raw_ld, const float* scale, const floa
                  const int64_t* copies_ld = nullptr);
 int maxpool_fwd_run(const void* x, int64_t x_ld, void* y, int64_t y_ld, long long* idx, int N, int H, int W, int C,
                     cudaStream_t s);
+int bn_eval_fold_bias_run(int C, const float* gamma, const float* beta, float eps, const float* rm, const float* rv,
+                          const float* conv_bias, float* scale, float* shift, cudaStream_t s);
+int stem_fwd_affine_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* scale,
+                        const float* shift, int relu, void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout,
+                        cudaStream_t s);
 // pad.cu
 int shift_copy_run(void* dst, int64_t dst_ld, int Hd, int Wd, const void* src, int64_t src_ld, int Hs, int Ws, int oy, int ox,
                    int N, int C, cudaStream_t s);

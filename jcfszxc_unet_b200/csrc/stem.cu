@@ -177,7 +177,7 @@ int stem_grid(int N, int H, int W) {
 bool stem_tc_ok(int Cin, int Cout);
 int stem_tc_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
                     void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s,
-                    float* stats_partial = nullptr, double* stats_sums = nullptr);
+                    float* stats_partial = nullptr, double* stats_sums = nullptr, const float* scale = nullptr, int relu = 0);
 bool stem_tc_stats_ok(int Cin, int Cout);
 size_t stem_tc_stats_partial_floats(int N, int H, int W, int Cout);
 size_t stem_tc_wgrad_workspace(int N, int H, int W, int Cin, int Cout);
@@ -188,6 +188,13 @@ static bool use_tc(int Cin, int Cout, int max_cout) {
   static int env = -1;
   if (env < 0) { const char* e = getenv("UNETK_STEM_TC"); env = e ? atoi(e) : 1; }
   return env && stem_tc_ok(Cin, Cout) && Cout <= max_cout;
+}
+
+int stem_fwd_affine_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* scale,
+                        const float* shift, int relu, void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout,
+                        cudaStream_t s) {
+  UNETK_CHECK(stem_tc_ok(Cin, Cout) && Cout <= 256, -1, "stem (affine): Cin=%d Cout=%d not supported", Cin, Cout);
+  return stem_tc_fwd_run(x, sn, sc, sh, sw, w, shift, y, y_ld, N, H, W, Cin, Cout, s, nullptr, nullptr, scale, relu);
 }
 
 int stem_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,

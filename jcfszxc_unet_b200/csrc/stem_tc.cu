@@ -34,6 +34,8 @@ struct StemTc {
   const float* x; int64_t sn, sc, sh, sw;  // fp32 image, element strides
   int N, H, W, Cin, Cout, tiles_w;
   FastDiv fd_tw, fd_h;                     // tile -> (row, column tile), row -> (image, h) without hardware division
+  const float* scale = nullptr;            // forward only: eval-mode BatchNorm fold, y = relu?(acc * scale + bias)
+  int relu = 0;
 };
 
 // tile -> pointer to x[n, 0, h, w] and (h, w) of this thread's pixel
@@ -197,7 +199,17 @@ __global__ void __launch_bounds__(kTile, (512 / CMAX) < 6 ? (512 / CMAX) : 6) st
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]);
-          if (has_bias) {
+          if (G.scale != nullptr) {   // eval-mode BatchNorm fold (bias holds the folded shift)
+            const float4 b0 = lds128_f(sBias_u + cb * 4), b1 = lds128_f(sBias_u + cb * 4 + 16);
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+            if (cb < Cout) { s0 = __ldg(reinterpret_cast<const float4*>(G.scale + cb)); s1 = __ldg(reinterpret_cast<const float4*>(G.scale + cb + 4)); }
+            f[0] = fmaf(f[0], s0.x, b0.x); f[1] = fmaf(f[1], s0.y, b0.y); f[2] = fmaf(f[2], s0.z, b0.z); f[3] = fmaf(f[3], s0.w, b0.w);
+            f[4] = fmaf(f[4], s1.x, b1.x); f[5] = fmaf(f[5], s1.y, b1.y); f[6] = fmaf(f[6], s1.z, b1.z); f[7] = fmaf(f[7], s1.w, b1.w);
+            if (G.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+          } else if (has_bias) {
             const float4 b0 = lds128_f(sBias_u + cb * 4), b1 = lds128_f(sBias_u + cb * 4 + 16);
             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
@@ -404,14 +416,18 @@ size_t stem_tc_stats_partial_floats(int N, int H, int W, int Cout) {
 
 int stem_tc_fwd_run(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w, const float* bias,
                     void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, cudaStream_t s, float* stats_partial,
-                    double* stats_sums) {
+                    double* stats_sums, const float* scale, int relu) {
   UNETK_CHECK(stem_tc_ok(Cin, Cout), -1, "stem_tc: Cin=%d Cout=%d not supported", Cin, Cout);
+  UNETK_CHECK(scale == nullptr || (bias != nullptr && stats_partial == nullptr && (reinterpret_cast<uintptr_t>(scale) & 15) == 0 && Cout % 8 == 0),
+              -1, "stem_tc: the affine epilogue needs a 16-byte aligned scale, a shift vector, Cout %% 8 == 0 and no statistics");
   UNETK_CHECK(y_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, -1, "stem_tc: output must be 16-byte aligned");
   StemTc G{x, sn, sc, sh, sw, N, H, W, Cin, Cout, (W + kTile - 1) / kTile,
            FastDiv(static_cast<uint32_t>((W + kTile - 1) / kTile)), FastDiv(static_cast<uint32_t>(H))};
   const int64_t tiles64 = static_cast<int64_t>(N) * H * G.tiles_w;
   UNETK_CHECK(tiles64 < (1ll << 31), -1, "stem_tc: too many tiles");
   const int tiles = static_cast<int>(tiles64);
+  G.scale = scale;
+  G.relu = relu;
   UNETK_CHECK(stats_partial == nullptr || (stem_tc_stats_ok(Cin, Cout) && stats_sums != nullptr), -1,
               "stem_tc: fused statistics need Cout %% 64 == 0");
   if (Cout <= 64) return stem_tc_fwd_launch<64>(G, w, bias, y, y_ld, tiles, s, stats_partial, stats_sums);

@@ -336,7 +336,13 @@ class ConvBNReLU:
             if self.cin % 8 or self.cout % 8:
                 raise ValueError(f"conv {self.cin}->{self.cout}: channel counts must be multiples of 8 on the tensor-core path")
         assert out.C == self.cout
-        self.raw = plan.act(H, W, self.cout) if bn is not None else out
+        # Eval-mode plans fold BatchNorm (+ReLU) into the conv epilogue (north_star; evaluate.py:259-275 runs eval mode): the
+        # conv writes `out` directly, `raw` and the bn_apply pass do not exist.  Not for units with a residual add, and
+        # given up again by consumers that need the raw conv output (Head(fuse=...) takes over the BatchNorm itself).
+        self.fold = (bn is not None and not plan.training and not plan.with_grad and bn.track_running_stats and res is None
+                     and k == 3 and (not self.stem or (self.cout % 16 == 0 and self.cout <= 256))
+                     and os.environ.get("UNETK_EVAL_FOLD", "1") != "0")
+        self.raw = out if bn is None else (None if self.fold else plan.act(H, W, self.cout))
         self.stat = plan.vec(self.cout, 4) if bn is not None else None  # scale, shift, mean, invstd
         self.pack = None if self.stem else plan.pack_of(conv.weight, k * k)
         self.w3 = self.dw3 = None
@@ -402,7 +408,28 @@ class ConvBNReLU:
                 ops.copy_f32_strided(self.w3, 9, w.detach(), 1, self.cout * self.cin, dst_offset=4)
                 self._wstamp = weight_stamp(w)
 
+    def unfold(self):
+        """A consumer needs the raw conv output after all: give the unit its `raw` buffer back."""
+        if self.fold:
+            self.fold = False
+            self.raw = self.plan.act(self.out.H, self.out.W, self.cout)
+
+    def _fwd_folded(self):
+        P, bn = self.plan, self.bn
+        sc, sh = self.stat[0], self.stat[1]
+        ops.bn_eval_fold_bias(bn.weight.detach() if bn.weight is not None else None, bn.bias.detach() if bn.bias is not None else None,
+                              bn.eps, bn.running_mean, bn.running_var, self.conv.bias.detach() if self.conv.bias is not None else None,
+                              sc, sh)
+        if self.stem:
+            ops.stem_fwd_affine(P.image.x, (self.w3 if self.w3 is not None else self.conv.weight).detach(), sc, sh, self.relu, self.out.t)
+        else:
+            ops.conv_fwd_affine(self.x.t, self.pack.ab, sc, sh, self.relu, self.out.t, self.stride)
+        if self.pooled is not None:
+            ops.maxpool_fwd(self.out.t, self.pooled.t)
+
     def fwd(self):
+        if self.fold:
+            return self._fwd_folded()
         P, bn = self.plan, self.bn
         bias = self.conv.bias.detach() if self.conv.bias is not None else None
         batch_stats = bn is not None and (P.training or not bn.track_running_stats)
@@ -636,6 +663,7 @@ class Head:
         if (fuse is not None and os.environ.get("UNETK_FUSE_HEAD", "1") != "0" and fuse.out is x and fuse.bn is not None
                 and fuse.res is None and fuse.pooled is None and self.C in (32, 64)):
             self.prod = fuse
+            fuse.unfold()
             fuse.head_fused = True
             plan.need(_lib.load().unetk_bn_head_partial_floats(self.npix, self.C), 0, self.C)
             self.dz = torch.empty(self.npix, dtype=torch.float32, device=dev) if plan.with_grad else None
@@ -790,7 +818,7 @@ class AddN(_Op):
         if len(inputs) == 1 and os.environ.get("UNETK_FUSE_COPIES", "1") != "0":
             for op in reversed(plan.ops[-8:]):
                 if isinstance(op, ConvBNReLU) and op.out is inputs[0]:
-                    if op.bn is not None and op.res is None and not op.head_fused and len(op.copies) < 3:
+                    if op.bn is not None and op.res is None and not op.head_fused and len(op.copies) < 3 and not op.fold:
                         op.copies.append(out)
                         self.fused_fwd = True
                     break

@@ -262,6 +262,30 @@ def bn_eval_fold(gamma, beta, eps, rm, rv, scale, shift, mean, invstd):
               _f32(shift), _f32(mean), _f32(invstd), _stream())
 
 
+def bn_eval_fold_bias(gamma, beta, eps, rm, rv, conv_bias, scale, shift):
+    _lib.call("unetk_bn_eval_fold_bias", scale.numel(), _f32(gamma), _f32(beta), float(eps), _f32(rm), _f32(rv), _f32(conv_bias),
+              _f32(scale), _f32(shift), _stream())
+
+
+def conv_fwd_affine(x, w_pack, scale, shift, relu, y, stride: int = 1):
+    """y = relu?(conv3x3(x) * scale + shift): eval-mode BatchNorm folded into the conv epilogue."""
+    n, ho, wo, cout = y.shape
+    cin = x.shape[3]
+    assert x.shape[1] == stride * ho and x.shape[2] == stride * wo
+    xp, xld = nhwc(x)
+    yp, yld = nhwc(y)
+    _lib.call("unetk_conv3x3_fwd_affine", xp, xld, w_pack.data_ptr(), _f32(scale), _f32(shift), int(relu), yp, yld, n, ho, wo,
+              cin, cout, int(stride), _stream())
+
+
+def stem_fwd_affine(x, w, scale, shift, relu, y):
+    xp, sn, sc, sh, sw = _img(x)
+    n, cin, h, wd = x.shape
+    yp, yld = nhwc(y)
+    _lib.call("unetk_stem_conv3x3_fwd_affine", xp, sn, sc, sh, sw, _f32(w), _f32(scale), _f32(shift), int(relu), yp, yld,
+              n, h, wd, cin, y.shape[3], _stream())
+
+
 def bn_apply(raw, scale, shift, out, pooled=None, relu=True, res=None):
     """out <- relu?(bn(raw)) [+ res]; pooled (optional) <- 2x2 max-pool of out."""
     n, h, w, c = raw.shape

@@ -613,3 +613,53 @@ def test_input_requiring_grad_is_refused():
     x = torch.rand(1, 3, 32, 32, device=DEV, requires_grad=True)
     with pytest.raises(NotImplementedError, match="requires grad"):
         m(x)
+
+
+# ------------------------------------------------------------------------------------------------ eval-mode BatchNorm fold
+@pytest.mark.parametrize("name,n,h,w", [("UNet", 2, 64, 160), ("UNet", 1, 256, 256), ("NestedUNet", 1, 64, 128), ("ResUNet", 1, 64, 64),
+                                        ("AttentionUNet", 1, 32, 160)])
+def test_eval_forward_folds_batchnorm_into_the_conv_epilogue(name, n, h, w, monkeypatch):
+    """north_star: "BatchNorm-fold plus ReLU fused into the epilogue".  In eval mode (what evaluate.py:259-275 runs) every
+    conv3x3 -> BatchNorm -> ReLU unit is ONE kernel: no bn_apply launch, no raw conv output.  The folded forward must
+    agree with the un-folded one (one bf16 rounding less per unit) and with the oracle's eval forward."""
+    import importlib
+
+    from jcfszxc_unet_b200 import _lib, clear_plans
+    from oracle import unet_oracle as O
+
+    mod, cls = {"UNet": ("UNetFamily.UNet", "UNet"), "NestedUNet": ("UNetFamily.UNetPP", "NestedUNet"),
+                "ResUNet": ("UNetFamily.ResUNet", "ResUNet"), "AttentionUNet": ("UNetFamily.AttentionUNet", "AttentionUNet")}[name]
+    torch.manual_seed(42)
+    m = getattr(importlib.import_module(mod), cls)()
+    g = torch.Generator().manual_seed(5)
+    for sub in m.modules():                        # non-trivial running statistics
+        if isinstance(sub, torch.nn.BatchNorm2d):
+            sub.running_mean.copy_(0.2 * torch.randn(sub.num_features, generator=g))
+            sub.running_var.copy_(0.5 + torch.rand(sub.num_features, generator=g))
+    m = m.to(DEV).eval()
+    x, _ = _inputs(17, n, h, w)
+    x = x.to(DEV)
+    with torch.no_grad():
+        with _lib.profile_calls() as prof:
+            y_fold = m(x)
+        torch.cuda.synchronize()
+        calls = prof.summary()
+        monkeypatch.setenv("UNETK_EVAL_FOLD", "0")
+        clear_plans(m)
+        with _lib.profile_calls() as prof0:
+            y_plain = m(x)
+        torch.cuda.synchronize()
+        calls0 = prof0.summary()
+        sd = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+        ref = O.FORWARDS[name](x.double(), sd, False).float()
+    monkeypatch.delenv("UNETK_EVAL_FOLD")
+    clear_plans(m)
+    n_fold = calls.get("unetk_conv3x3_fwd_affine", [0])[0] + calls.get("unetk_stem_conv3x3_fwd_affine", [0])[0]
+    assert n_fold > 0 and "unetk_conv3x3_fwd_affine" not in calls0
+    if name in ("UNet", "NestedUNet"):             # every BatchNorm of these models follows a 3x3 conv
+        assert "unetk_bn_apply" not in calls and "unetk_bn_apply_copies" not in calls, sorted(calls)
+    assert calls.get("unetk_bn_apply", [0])[0] < calls0.get("unetk_bn_apply", [0])[0] + calls0.get("unetk_bn_apply_copies", [0])[0]
+    print(f"{name} eval {n}x{h}x{w}: folded vs plain l2 {_l2rel(y_fold, y_plain):.3g}; folded vs oracle(fp64) l2 {_l2rel(y_fold, ref):.3g}; "
+          f"plain vs oracle l2 {_l2rel(y_plain, ref):.3g}; launches {sum(c for c, _ in calls.values())} vs {sum(c for c, _ in calls0.values())}")
+    assert _l2rel(y_fold, y_plain) <= 2e-2
+    assert _l2rel(y_fold, ref) <= max(2e-2, 1.25 * _l2rel(y_plain, ref)) and _l2rel(y_fold, ref) <= 5e-2
