@@ -277,7 +277,7 @@ class Trainer:
         """The step's loss as a device scalar: the head's, or the mean over the deep-supervision heads."""
         if len(self.heads) == 1:
             return self.heads[0].fin[0]
-        torch.stack([h.fin[0] for h in self.heads]).mean(dim=0, out=self.loss_mean)
+        torch.mean(torch.stack([h.fin[0] for h in self.heads]), dim=0, out=self.loss_mean)
         return self.loss_mean
 
     def _capture(self):
