@@ -359,15 +359,17 @@ CONV_FLOPS = {
 
 def ncu_traffic_per_launch(family, args):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed ncu
-    capture of this exact workload (profiles/r01_ncu_traffic.json, made by tools/ncu_traffic.py); None for any other
+    capture of this exact workload (profiles/r02_ncu_traffic.json, made by tools/ncu_traffic.py); None for any other
     workload (a number taken under a profiler is never measured live)."""
     if args.model != "UNet" or args.batch != 16 or args.size != 512:
         return None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
-            return json.load(f)[family]["bytes_per_launch"]
-    except Exception:
-        return None
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):     # the latest capture of this workload
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)[family]["bytes_per_launch"]
+        except Exception:
+            continue
+    return None
 
 
 def kernel_breakdown(records):
@@ -536,6 +538,7 @@ def run_ours(args):
     tr = m.pop("trainer")
     in_sync = replicas_in_sync(tr, dp, dev) if world > 1 else None
     buckets = getattr(tr, "bucket_report", lambda: None)()
+    tr.close()          # the captured graph holds NCCL kernels: release it before the process group is destroyed
     del tr
     _free_cuda()
 
@@ -593,7 +596,7 @@ def run_ours(args):
         for name, vb, vs in VARIANTS:
             try:
                 vm = measure_ours(name, vb, vs, 5, 3, dev, dp, 1, 0, local_rank, graph=True, detail=False, e2e=False)
-                vm.pop("trainer")
+                vm.pop("trainer").close()
                 _free_cuda()
                 ips = vb * 5 / (vm["ms_total"] / 1e3)
                 gf = train_gflop_per_image(name, vs)

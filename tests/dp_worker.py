@@ -52,7 +52,10 @@ def main():
         torch.cuda.synchronize()
         for k in (env or {}):
             os.environ.pop(k)
+        made.append(tr)
         return tr, losses
+
+    made = []
 
     def in_sync(t):
         mine = torch.cat([t.flat_p, t.sq, t.buf]).view(torch.int32)
@@ -100,6 +103,7 @@ def main():
     torch.manual_seed(42)                        # rank 0's initial weights are what the broadcast distributed
     m1 = UNet(3, 1).to(dev).train()
     t1 = Trainer(m1, lr=lr, use_cuda_graph=False, dp=DataParallel(enabled=False))
+    made.append(t1)
     l_1p = [float(t1.step(images[s].to(dev), labels[s].to(dev))) for s in range(3)]
     report["loss_dp_syncbn"], report["loss_single_process"] = l_b, l_1p
     # same arithmetic, another summation order (per-rank partial sums): fp32/bf16 rounding differences only
@@ -108,11 +112,18 @@ def main():
         assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), (l_b, l_1p)
     # gradient norm of the first step is the global one on every rank
     _say(rank, "done")
-    faulthandler.cancel_dump_traceback_later()
     dist.barrier()
     if rank == 0:
         print("DP_WORKER_OK " + json.dumps(report), flush=True)
+    # captured graphs hold NCCL kernels: release them before the communicator goes away (Trainer.close)
+    faulthandler.cancel_dump_traceback_later()
+    faulthandler.dump_traceback_later(60, exit=True)
+    for t in made:
+        t.close()
+    del tr_e, tr_b, t1, made
     dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
+    _say(rank, "process group destroyed")
 
 
 if __name__ == "__main__":
