@@ -521,6 +521,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the all-reduce kernels get the SMs the trainer leaves them (Trainer.sm_reserve) and no more
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("UNETK_DP_SM_RESERVE", "4"))
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     S = args.size

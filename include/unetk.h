@@ -160,6 +160,13 @@ int unetk_bn_finalize(const double* sums, int C, double count, const float* gamm
 int unetk_bn_eval_fold(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
                        const float* running_var, float* scale, float* shift, float* mean, float* invstd,
                        void* stream);
+/* Persistent kernels size their grids for the SM count of the current device.  unetk_set_sm_limit(n > 0) makes the
+ * launches of the CALLING THREAD use at most n SMs (0 restores all; returns the previous limit): a data-parallel
+ * trainer leaves a few SMs to the NCCL all-reduce kernels that run beside the backward — a persistent grid of one CTA
+ * per SM otherwise waits for the SMs NCCL holds and its late CTAs double the kernel's duration. */
+int unetk_set_sm_limit(int n);
+int unetk_device_sms(void);
+
 /* Eval mode, BatchNorm folded into the producing conv's epilogue (north_star: "BatchNorm-fold plus ReLU fused into the
  * epilogue"; what evaluate.py:259-275 runs): the conv writes the post-BN(+ReLU) activation directly, the raw conv
  * output and the bn_apply pass do not exist.

@@ -24,6 +24,8 @@ SIGNATURES = {
     "unetk_abi_version": (_i, []),
     "unetk_last_error": (C.c_char_p, []),
     "unetk_launch_count": (_i64, []),
+    "unetk_set_sm_limit": (_i, [_i]),
+    "unetk_device_sms": (_i, []),
     "unetk_pack_weight": (_i, [_fp, _vp, _vp, _i, _i, _i, _vp]),
     "unetk_pack_tiles": (_i64, [_i, _i]),
     "unetk_pack_weights": (_i, [_vp, _i, _i64, _vp]),

@@ -89,6 +89,8 @@ int unetk_bn_eval_fold_bias(int C, const float* gamma, const float* beta, float 
   UNETK_CHECK(running_mean && running_var && scale && shift && C > 0, -1, "bn_eval_fold_bias: bad arguments");
   return bn_eval_fold_bias_run(C, gamma, beta, eps, running_mean, running_var, conv_bias, scale, shift, S(stream));
 }
+int unetk_set_sm_limit(int n) { return set_sm_limit(n); }
+int unetk_device_sms(void) { return device_sms(); }
 size_t unetk_conv_stats_partial_floats(int Cout) {
   if (Cout < 8 || Cout % 8) return 0;
   return conv_gemm_stats_partial_floats(Cout);

@@ -42,7 +42,21 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+namespace {
+thread_local int g_sm_limit = 0;   // > 0: persistent grids of this thread use at most this many SMs (unetk_set_sm_limit)
+}
+int set_sm_limit(int n) {
+  const int prev = g_sm_limit;
+  g_sm_limit = n > 0 ? n : 0;
+  return prev;
+}
+
 int num_sms() {
+  const int real = device_sms();
+  return (g_sm_limit > 0 && g_sm_limit < real) ? g_sm_limit : real;
+}
+
+int device_sms() {
   static std::atomic<int> cached[64];   // per device ordinal; 0 = not queried yet
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;

@@ -64,7 +64,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 long long launch_count();
-int num_sms();             // SM count of the CURRENT device (cached per device)
+int device_sms();          // SM count of the CURRENT device (cached per device)
+int num_sms();             // what grids are sized for: device_sms(), or the calling thread's limit (set_sm_limit)
+int set_sm_limit(int n);   // n > 0: persistent kernels launched by THIS thread use at most n SMs; 0: all.  Returns the old limit
 const char* last_error();  // the calling thread's last error text (thread-local, errno-style)
 
 // One-time, per-device, thread-safe set-up of a kernel (cudaFuncSetAttribute for > 48 KB of dynamic shared memory is a

@@ -44,6 +44,8 @@ class Trainer:
         self.dp = dp or DataParallel()
         self.use_graph = use_cuda_graph and not self.dp.sync_bn  # SyncBN puts host-side collectives between kernels
         self.grad_buckets = grad_buckets or int(os.environ.get("UNETK_GRAD_BUCKETS", "8"))
+        # SMs left to NCCL while gradient buckets are in flight (see _launch_bucket); pair it with NCCL_MAX_CTAS
+        self.sm_reserve = int(os.environ.get("UNETK_DP_SM_RESERVE", "4")) if self.dp.enabled else 0
         params = [p for p in model.parameters()]
         if not params or not params[0].is_cuda:
             raise RuntimeError("Trainer: move the model to a CUDA device first (no CPU fallback on this path)")
@@ -208,7 +210,7 @@ class Trainer:
         """What bench.py prints as `grad_buckets`: MB per all-reduce call in launch order, and how the step is run."""
         if not self.dp.enabled or self.plan is None:
             return None
-        return {"mode": self.graph_mode, "calls_mb": [[round((hi - lo) * 4 / 2**20, 2) for lo, hi in rs] for _, rs in self._cuts],
+        return {"mode": self.graph_mode, "sm_reserve": self.sm_reserve, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), "calls_mb": [[round((hi - lo) * 4 / 2**20, 2) for lo, hi in rs] for _, rs in self._cuts],
                 "cut_after_op": [k for k, _ in self._cuts], "ops": len(self.plan.ops)}
 
     # program ------------------------------------------------------------------------------------------
@@ -248,11 +250,22 @@ class Trainer:
         with self.plan.behind_both_streams():
             for lo, hi in ranges:
                 self._handles.append(self.dp.reduce_grads_async(self.flat_g[lo:hi]))
+        if self.sm_reserve > 0:
+            # From here to _wait_buckets NCCL kernels run beside the backward.  The tensor-core kernels are persistent
+            # grids of one CTA per SM with a static tile order: with NCCL holding k SMs, k of their CTAs start only when
+            # something else ends and the kernel takes twice as long — the all-reduce time is then added to the step
+            # instead of hidden (measured: +0.43 ms at 2 GPUs, +1.05 ms at 8).  Launch them a few SMs narrower instead.
+            from . import _lib
+            lib = _lib.load()
+            lib.unetk_set_sm_limit(max(1, lib.unetk_device_sms() - self.sm_reserve))
 
     def _wait_buckets(self):
         for h in self._handles:
             self.dp.wait(h)
         self._handles = []
+        if self.sm_reserve > 0:
+            from . import _lib
+            _lib.load().unetk_set_sm_limit(0)
 
     def _seg_optim(self):
         ops.grad_clip_coef(self.flat_g, self._gscale, self._max_norm, self.sq_partial, self.clip)

@@ -91,8 +91,14 @@ def main():
     assert l_s == l_e and torch.equal(tr_s.flat_p, tr_e.flat_p), "per-segment graphs != eager DP"
     _say(rank, "one-bucket run")
     tr_1, l_1 = run(True, buckets=1)
-    assert l_1 == l_e and torch.equal(tr_1.flat_p, tr_e.flat_p), "bucket count changed the result"
-    del tr_g, tr_s, tr_1
+    # one bucket = nothing overlaps the backward = no SMs set aside (Trainer.sm_reserve): other split-K orders in the
+    # weight gradients, so equal up to summation order only
+    assert all(abs(a - b) <= 1e-4 * max(1.0, abs(b)) for a, b in zip(l_1, l_e)), (l_1, l_e)
+    assert torch.allclose(tr_1.flat_p, tr_e.flat_p, rtol=0, atol=5e-3), "bucket count changed the result"
+    tr_0, l_0 = run(True, env={"UNETK_DP_SM_RESERVE": "0"})
+    assert in_sync(tr_0) and tr_0.sm_reserve == 0
+    assert all(abs(a - b) <= 1e-4 * max(1.0, abs(b)) for a, b in zip(l_0, l_e)), (l_0, l_e)
+    del tr_g, tr_s, tr_1, tr_0
     # 2. global batch, sync_bn: equal to one process on the whole batch
     _say(rank, "sync_bn run")
     faulthandler.cancel_dump_traceback_later()
