@@ -10,6 +10,25 @@ using namespace unetk;
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
+// Scratch sizes depend on grid sizes, grid sizes on the SM count the launching thread may use (unetk_set_sm_limit), and
+// not monotonically (wave-aware split-K).  Every size query therefore answers for ANY limit a caller may set later:
+// the maximum over "all SMs" ... "all but kMaxSmReserve".
+namespace {
+constexpr int kMaxSmReserve = 16;
+template <class F>
+size_t max_over_sm_limits(F&& f) {
+  const int prev = set_sm_limit(0), real = device_sms();
+  size_t m = 0;
+  for (int r = 0; r <= kMaxSmReserve && r < real; ++r) {
+    set_sm_limit(r == 0 ? 0 : real - r);
+    const size_t v = f();
+    if (v > m) m = v;
+  }
+  set_sm_limit(prev);
+  return m;
+}
+}  // namespace
+
 extern "C" {
 
 int unetk_abi_version(void) { return UNETK_ABI_VERSION; }
@@ -89,11 +108,15 @@ int unetk_bn_eval_fold_bias(int C, const float* gamma, const float* beta, float 
   UNETK_CHECK(running_mean && running_var && scale && shift && C > 0, -1, "bn_eval_fold_bias: bad arguments");
   return bn_eval_fold_bias_run(C, gamma, beta, eps, running_mean, running_var, conv_bias, scale, shift, S(stream));
 }
-int unetk_set_sm_limit(int n) { return set_sm_limit(n); }
+int unetk_set_sm_limit(int n) {
+  const int real = device_sms();
+  if (n > 0 && n < real - kMaxSmReserve) n = real - kMaxSmReserve;   // scratch buffers were sized for at most that reserve
+  return set_sm_limit(n);
+}
 int unetk_device_sms(void) { return device_sms(); }
 size_t unetk_conv_stats_partial_floats(int Cout) {
   if (Cout < 8 || Cout % 8) return 0;
-  return conv_gemm_stats_partial_floats(Cout);
+  return max_over_sm_limits([&] { return conv_gemm_stats_partial_floats(Cout); });
 }
 int unetk_conv3x3_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y,
                               int64_t y_ld, float* partial, double* sums, int N, int H, int W, int Cin, int Cout,
@@ -204,7 +227,7 @@ static WgradDesc conv_wgrad_desc(const void* x, int64_t x_ld, const void* dy, in
   return d;
 }
 
-size_t unetk_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int taps) {
+static size_t conv_wgrad_workspace_now(int N, int H, int W, int Cin, int Cout, int taps) {
   if (taps == 4) {  // ConvTranspose
     WgradDesc d{};
     d.N = N; d.H = H; d.W = W; d.taps = 4; d.M = Cin; d.Nn = Cout;
@@ -219,6 +242,9 @@ size_t unetk_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ta
     if (need3f > need) need = need3f;
   }
   return need;
+}
+size_t unetk_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int taps) {
+  return max_over_sm_limits([&] { return conv_wgrad_workspace_now(N, H, W, Cin, Cout, taps); });
 }
 
 int unetk_conv3x3_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw, int accumulate,
@@ -282,7 +308,7 @@ int unetk_stem_conv3x3_fwd(const float* x, int64_t sn, int64_t sc, int64_t sh, i
 }
 size_t unetk_stem_stats_partial_floats(int N, int H, int W, int Cout) {
   if (N <= 0 || H <= 0 || W <= 0 || Cout < 8 || Cout % 8) return 0;
-  return stem_stats_partial_floats(N, H, W, Cout);
+  return max_over_sm_limits([&] { return stem_stats_partial_floats(N, H, W, Cout); });
 }
 int unetk_stem_conv3x3_fwd_bnstats(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const float* w,
                                    const float* bias, void* y, int64_t y_ld, float* partial, double* sums, int N, int H,
@@ -290,7 +316,9 @@ int unetk_stem_conv3x3_fwd_bnstats(const float* x, int64_t sn, int64_t sc, int64
   UNETK_CHECK(x && w && y && partial && sums, -1, "stem_fwd_bnstats: null pointer");
   return stem_fwd_stats_run(x, sn, sc, sh, sw, w, bias, y, y_ld, partial, sums, N, H, W, Cin, Cout, S(stream));
 }
-size_t unetk_stem_wgrad_workspace(int N, int H, int W, int Cin) { return stem_wgrad_workspace(N, H, W, Cin); }
+size_t unetk_stem_wgrad_workspace(int N, int H, int W, int Cin) {
+  return max_over_sm_limits([&] { return stem_wgrad_workspace(N, H, W, Cin); });
+}
 int unetk_stem_conv3x3_wgrad(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, const void* dy,
                              int64_t dy_ld, float* dw, int accumulate, int N, int H, int W, int Cin, int Cout,
                              void* workspace, size_t ws_bytes, void* stream) {
@@ -302,7 +330,7 @@ int unetk_stem_conv3x3_wgrad(const float* x, int64_t sn, int64_t sc, int64_t sh,
 // ------------------------------------------------------------------------------------------------ BN / pool
 size_t unetk_chan_partial_floats(int64_t units, int C) {
   if (C < 8 || C % 8) return 0;
-  return chan_partial_floats(units, C);
+  return max_over_sm_limits([&] { return chan_partial_floats(units, C); });
 }
 int unetk_bn_stats(const void* x, int64_t x_ld, int64_t npix, int C, float* partial, double* sums, void* stream) {
   UNETK_CHECK(x && partial && sums && npix > 0, -1, "bn_stats: bad arguments");
@@ -402,7 +430,7 @@ int unetk_colsum(const void* x, int64_t x_ld, int64_t npix, int C, float* partia
 // ------------------------------------------------------------------------------------------------ head / loss
 size_t unetk_head_partial_floats(int64_t npix, int C) {
   if (C < 8 || C % 8) return 0;
-  return head_partial_floats(npix, C);
+  return max_over_sm_limits([&] { return head_partial_floats(npix, C); });
 }
 int unetk_head_fwd(const void* x, int64_t x_ld, const float* w, const float* bias, const float* labels, float* logits,
                    int post_sigmoid, int64_t npix, int C, float* partial, double* sums, void* stream) {
@@ -423,7 +451,7 @@ int unetk_head_bwd(const void* x, int64_t x_ld, const float* w, const float* lab
 
 size_t unetk_bn_head_partial_floats(int64_t npix, int C) {
   if (C < 8 || C % 8) return 0;
-  return bn_head_partial_floats(npix, C);
+  return max_over_sm_limits([&] { return bn_head_partial_floats(npix, C); });
 }
 int unetk_bn_head_fwd(const void* raw, int64_t raw_ld, const float* scale, const float* shift, int relu, const float* w,
                       const float* bias, const float* labels, float* logits, int post_sigmoid, int64_t npix, int C,
@@ -451,7 +479,7 @@ int unetk_bn_head_bwd_apply(const void* raw, int64_t raw_ld, const float* scale,
 // ------------------------------------------------------------------------------------------------ n_classes > 1, Dice
 size_t unetk_head_multi_partial_floats(int64_t npix, int C, int K) {
   if (C < 8 || C % 8 || K < 1 || K > 8) return 0;
-  return head_multi_partial_floats(npix, C, K);
+  return max_over_sm_limits([&] { return head_multi_partial_floats(npix, C, K); });
 }
 int unetk_head_multi_fwd(const void* x, int64_t x_ld, const float* w, const float* bias, float* logits, int N,
                          int64_t hw, int C, int K, void* stream) {
@@ -466,7 +494,7 @@ int unetk_head_multi_bwd(const void* x, int64_t x_ld, const float* w, const floa
 }
 size_t unetk_dice_partial_floats(int64_t groups, int64_t n) {
   if (groups < 1 || n < 1) return 0;
-  return dice_partial_floats(groups, n);
+  return max_over_sm_limits([&] { return dice_partial_floats(groups, n); });
 }
 int unetk_dice_sums(const float* p, const float* t, int64_t groups, int64_t n, float lo, float hi, float* partial,
                     double* sums, void* stream) {
@@ -480,7 +508,9 @@ int unetk_dice_bwd(const float* p, const float* t, const float* coef, const floa
 }
 
 // ------------------------------------------------------------------------------------------------ optimizer
-size_t unetk_sqnorm_partial_floats(int64_t n) { return static_cast<size_t>(sqnorm_blocks(n)); }
+size_t unetk_sqnorm_partial_floats(int64_t n) {
+  return max_over_sm_limits([&] { return static_cast<size_t>(sqnorm_blocks(n)); });
+}
 int unetk_grad_clip_coef(const float* g, int64_t n, float gscale, float max_norm, float* partial, float* out,
                          void* stream) {
   UNETK_CHECK(g && partial && out && n > 0, -1, "grad_clip_coef: bad arguments");
@@ -552,7 +582,9 @@ int unetk_copy_f32_strided(float* dst, int64_t dst_stride, const float* src, int
 }
 
 // ------------------------------------------------------------------------------------------------ attention gate
-size_t unetk_gate_partial_floats(int64_t npix, int F_int) { return gate_partial_floats(npix, F_int); }
+size_t unetk_gate_partial_floats(int64_t npix, int F_int) {
+  return max_over_sm_limits([&] { return gate_partial_floats(npix, F_int); });
+}
 int unetk_gate_fwd(const void* raw_g, int64_t raw_g_ld, const void* raw_x, int64_t raw_x_ld, const float* sc_g,
                    const float* sh_g, const float* sc_x, const float* sh_x, const float* w_psi, const float* b_psi,
                    float* s, float* partial, double* sums, int64_t npix, int F_int, void* stream) {
@@ -624,7 +656,9 @@ int unetk_f32_convT2x2(const void* x_split, int64_t x_ld, const void* w_split, c
   d.dh[0] = 0; d.dw[0] = 0; d.btap[0] = 0;
   return conv_gemm_run(d, S(stream));
 }
-size_t unetk_f32_stats_partial_doubles(int64_t npix, int C) { return f32_stats_partial_doubles(npix, C); }
+size_t unetk_f32_stats_partial_doubles(int64_t npix, int C) {
+  return max_over_sm_limits([&] { return f32_stats_partial_doubles(npix, C); });
+}
 int unetk_f32_stats(const float* x, int64_t x_ld, int64_t npix, int C, double* partial, double* sums, void* stream) {
   UNETK_CHECK(x && partial && sums && npix > 0, -1, "f32_stats: bad arguments");
   return f32_stats_run(x, x_ld, npix, C, partial, sums, S(stream));
