@@ -350,3 +350,42 @@ def test_f32_split_is_exact_to_24_bits():
     assert torch.equal(s[..., c:2 * c], hi) and torch.equal(s[..., 2 * c:3 * c], hi) and torch.equal(s[..., 4 * c:5 * c], mid)
     rec = hi.double() + mid.double() + lo.double()
     assert ((rec - x.double()).abs() <= x.abs().double() * 2.0 ** -23).all()
+
+
+def test_sm_limit_keeps_results_and_scratch_sizes_valid():
+    """unetk_set_sm_limit: persistent kernels launched by this thread use fewer SMs (a data-parallel trainer leaves some to
+    NCCL).  Results stay correct, scratch sizes queried BEFORE the limit was set stay sufficient (the queries answer for
+    every limit down to device_sms - 16), and the limit is clamped to that range."""
+    from jcfszxc_unet_b200 import _lib
+
+    ops = _ops()
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    real = lib.unetk_device_sms()
+    assert real > 32
+    n, h, w, cin, cout = 4, 64, 128, 128, 64
+    g = torch.Generator(device=dev).manual_seed(77)
+    x = torch.randn(n, h, w, cin, device=dev, generator=g).bfloat16()
+    dy = torch.randn(n, h, w, cout, device=dev, generator=g).bfloat16()
+    wt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * 0.03
+    w_ab, _ = ops.pack_weight(wt, True, False)
+    ws = torch.empty(lib.unetk_conv_wgrad_workspace(n, h, w, cin, cout, 9), dtype=torch.uint8, device=dev)   # sized at full width
+    partial = torch.empty(max(lib.unetk_conv_stats_partial_floats(cout), 4096), device=dev)
+    ref_y = F.conv2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float(), None, padding=1).permute(0, 2, 3, 1)
+    ref_dw = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
+    try:
+        for limit in (0, real - 4, real - 16, real - 13, 7):
+            prev = lib.unetk_set_sm_limit(limit)
+            assert prev >= 0
+            y = torch.empty(n, h, w, cout, device=dev, dtype=torch.bfloat16)
+            sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+            ops.conv_fwd_stats(x, w_ab, None, y, partial, sums, 3, 1)
+            _close(y, ref_y, f"conv fwd under sm limit {limit}")
+            assert torch.allclose(sums[:cout], y.double().sum(dim=(0, 1, 2)), rtol=1e-4, atol=1e-2)
+            dw = torch.full((cout, cin, 3, 3), float("nan"), device=dev)
+            ops.conv_wgrad(x, dy, dw, 3, ws=ws)
+            torch.cuda.synchronize()
+            assert (dw - ref_dw).abs().max().item() <= 2e-3 * ref_dw.abs().max().item()
+        assert lib.unetk_set_sm_limit(0) == real - 16          # the request for 7 SMs was clamped to device_sms - 16
+    finally:
+        lib.unetk_set_sm_limit(0)
