@@ -3,6 +3,9 @@
 // are "MN-major" UMMA tiles: a TMA box of (64 channels, TW, TH, 1) lands as [64 pixels][64 ch] with
 // 128B swizzle, which is exactly the canonical MN-major SW128 atom sequence (8 pixel rows per atom).
 // Split over pixel ranges (deterministic: fp32 partials + ordered reduce in wgrad_reduce_kernel).
+// Tap packing (tpn > 1): when the taps differ only in the Q operand's offset (ConvTranspose2d: the four output phases of
+// dY against ONE X tile) and Nn <= 128, the Q boxes of tpn taps sit side by side in one N = tpn * Nn tile: X is read once
+// instead of once per tap and the MMA runs at N = 256 instead of N = 64 (half rate, profiles/r01_mma_rate_probe.txt).
 // Reference semantics replaced: autograd's weight gradient of nn.Conv2d(k=3,p=1 / k=1) and
 // nn.ConvTranspose2d(k=2,s=2) (UNetFamily/utils/unet_parts.py:24-31,56-58 in the reference).
 #include <cstdlib>
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   pdl_trigger();
   pdl_wait();
 
-  const int items_per_split = p.taps * p.m_tiles * p.n_tiles;
+  const int items_per_split = p.tgroups * p.m_tiles * p.n_tiles;
   const int num_items = items_per_split * p.ksplit;
 
   if (warp == 0) {
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int nt = item % p.n_tiles;
         const int mt = (item / p.n_tiles) % p.m_tiles;
-        const int tap = (item / (p.n_tiles * p.m_tiles)) % p.taps;
+        const int tap = ((item / (p.n_tiles * p.m_tiles)) % p.tgroups) * p.tpn;   // first tap of the item's group
         const int ks = item / items_per_split;
         const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
         const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
@@ -97,9 +100,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
 #pragma unroll
           for (int b = 0; b < 2; ++b)
             tma_load_4d(sp + b * kBoxBytes, &p.tmP, &full_bar[stage], mt * 128 + b * 64, pw, ph, img);
+          if (p.tpn > 1) {
+            // box b = 64 channels of tap (tap + b*64/Nn): the taps of the group side by side in N
 #pragma unroll
-          for (int b = 0; b < BN / 64; ++b)
-            tma_load_4d(sq + b * kBoxBytes, &p.tmQ, &full_bar[stage], nt * BN + b * 64, qw, qh, img);
+            for (int b = 0; b < BN / 64; ++b) {
+              const int tb = tap + (b * 64) / p.Nn;
+              tma_load_4d(sq + b * kBoxBytes, &p.tmQ, &full_bar[stage], (b * 64) % p.Nn, p.q_step * w0 + p.q_dw[tb],
+                          p.q_step * h0 + p.q_dh[tb], img);
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b)
+              tma_load_4d(sq + b * kBoxBytes, &p.tmQ, &full_bar[stage], nt * BN + b * 64, qw, qh, img);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -147,11 +160,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int nt = item % p.n_tiles;
       const int mt = (item / p.n_tiles) % p.m_tiles;
-      const int tap = (item / (p.n_tiles * p.m_tiles)) % p.taps;
+      const int tap = ((item / (p.n_tiles * p.m_tiles)) % p.tgroups) * p.tpn;
       const int ks = item / items_per_split;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m = mt * 128 + row;
+      const size_t tap_stride = static_cast<size_t>(p.M) * p.Nn;
       float* dst = p.partial + ((static_cast<size_t>(ks) * p.taps + tap) * p.M + m) * p.Nn + nt * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -162,13 +176,20 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
         if (m < p.M) {
+          // packed taps: columns [j*Nn, (j+1)*Nn) of the tile are tap (tap + j); a 32-column chunk never straddles two
+          float* dc = dst + c * 32;
+          int col0 = nt * BN + c * 32;
+          if (p.tpn > 1) {
+            const int j = (c * 32) / p.Nn;
+            col0 = c * 32 - j * p.Nn;
+            dc = dst + j * tap_stride + col0;
+          }
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
-            const int col = nt * BN + c * 32 + v * 4;
-            if (col < p.Nn) {
+            if (col0 + v * 4 < p.Nn) {
               float4 o = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
                                      __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
-              *reinterpret_cast<float4*>(dst + c * 32 + v * 4) = o;
+              *reinterpret_cast<float4*>(dc + v * 4) = o;
             }
           }
         }
@@ -302,15 +323,29 @@ int launch(const WgradParams& p, cudaStream_t stream) {
   using C = WCfg<BN>;
   static DeviceOnce once;
   UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); }));
-  const int items = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
+  const int items = p.tgroups * p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = items < num_sms() ? items : num_sms();
   UNETK_CUDA(launch_pdl(wgrad_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, p));
   UNETK_LAUNCHED();
   return 0;
 }
 
-void plan(const WgradDesc& d, int* BN, int* ksplit, int* TH, int* TW, int* pix_tiles) {
-  *BN = d.Nn >= 256 ? 256 : (d.Nn > 64 ? 128 : 64);
+// taps that can share one N tile: same P offsets, Nn a whole number of 64-channel boxes, tpn * Nn <= 256
+int taps_per_tile(const WgradDesc& d) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("UNETK_WGRAD_PACK_TAPS"); env = e ? atoi(e) : 1; }
+  if (!env || d.taps < 2 || (d.Nn != 64 && d.Nn != 128)) return 1;
+  for (int t = 1; t < d.taps; ++t)
+    if (d.p_dh[t] != d.p_dh[0] || d.p_dw[t] != d.p_dw[0]) return 1;
+  int tpn = 256 / d.Nn;
+  while (tpn > 1 && d.taps % tpn) tpn >>= 1;
+  return tpn;
+}
+
+void plan(const WgradDesc& d, int* BN, int* ksplit, int* TH, int* TW, int* pix_tiles, int* tpn_out = nullptr) {
+  const int tpn = taps_per_tile(d);
+  if (tpn_out) *tpn_out = tpn;
+  *BN = tpn > 1 ? tpn * d.Nn : (d.Nn >= 256 ? 256 : (d.Nn > 64 ? 128 : 64));
   int tw = 64;
   while (tw > d.W) tw >>= 1;
   if (tw < 1) tw = 1;
@@ -318,8 +353,8 @@ void plan(const WgradDesc& d, int* BN, int* ksplit, int* TH, int* TW, int* pix_t
   *TH = kPix / tw;
   const int tiles_h = (d.H + *TH - 1) / *TH, tiles_w = (d.W + tw - 1) / tw;
   *pix_tiles = d.N * tiles_h * tiles_w;
-  const int m_tiles = (d.M + 127) / 128, n_tiles = (d.Nn + *BN - 1) / *BN;
-  const int base = d.taps * m_tiles * n_tiles;
+  const int m_tiles = (d.M + 127) / 128, n_tiles = tpn > 1 ? 1 : (d.Nn + *BN - 1) / *BN;
+  const int base = (d.taps / tpn) * m_tiles * n_tiles;
   int ks = (2 * num_sms() + base - 1) / base;
   const int cap = *pix_tiles / 8 > 0 ? *pix_tiles / 8 : 1;
   if (ks > cap) ks = cap;
@@ -379,13 +414,14 @@ int wgrad_run(const WgradDesc& d, void* workspace, size_t ws_bytes, cudaStream_t
   UNETK_CHECK(d.taps >= 1 && d.taps <= 9, -1, "wgrad: taps=%d", d.taps);
   WgradParams p{};
   int BN;
-  plan(d, &BN, &p.ksplit, &p.TH, &p.TW, &p.pix_tiles);
+  plan(d, &BN, &p.ksplit, &p.TH, &p.TW, &p.pix_tiles, &p.tpn);
+  p.tgroups = d.taps / p.tpn;
   const size_t need = static_cast<size_t>(p.ksplit) * d.taps * d.M * d.Nn * sizeof(float);
   UNETK_CHECK(workspace != nullptr && ws_bytes >= need, -1, "wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
   p.tiles_h = (d.H + p.TH - 1) / p.TH;
   p.tiles_w = (d.W + p.TW - 1) / p.TW;
   p.m_tiles = (d.M + 127) / 128;
-  p.n_tiles = (d.Nn + BN - 1) / BN;
+  p.n_tiles = p.tpn > 1 ? 1 : (d.Nn + BN - 1) / BN;
   p.taps = d.taps;
   p.M = d.M; p.Nn = d.Nn;
   p.p_step = d.p_step; p.q_step = d.q_step;

@@ -28,6 +28,8 @@ struct WgradParams {
   float* partial;
   int TH, TW, tiles_h, tiles_w, pix_tiles;
   int m_tiles, n_tiles, taps, ksplit;
+  int tpn;      // taps packed side by side in one N tile (1: one tap per item); BN = tpn * Nn, n_tiles = 1 when > 1
+  int tgroups;  // taps / tpn
   int M, Nn;
   int p_step, q_step;
   int8_t p_dh[9], p_dw[9], q_dh[9], q_dw[9];
