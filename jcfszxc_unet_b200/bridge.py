@@ -98,6 +98,7 @@ class _PlanFunction(torch.autograd.Function):
             h.dlogits = d.contiguous().float() if d is not None else torch.zeros_like(h.logits)
             h.gscale = 1.0
         plan.backward()
+        plan.awaiting_backward = False
         for h in heads:
             h.dlogits = None
         # views of the plan's gradient buffers: autograd's AccumulateGrad copies them into .grad (it cannot steal a
@@ -140,6 +141,17 @@ def run_model(model: torch.nn.Module, builder, x: torch.Tensor) -> torch.Tensor:
         # a plan with gradient buffers only when a backward can follow; BN mode follows model.training
         plan = plans.insert(key, builder(model, n, h, w, x.device, training_stats, None, need_grad))
     if need_grad:
+        if getattr(plan, "awaiting_backward", False):
+            # a second forward of this shape while the first one's backward is still to come (loss(model(a)) + loss(model(b)),
+            # train.py:256-297 semantics): a plan's activations are static buffers, so the second forward gets a twin plan
+            # instead of overwriting them.  One twin per shape: a third un-backwarded forward reuses the older plan, whose
+            # stale backward then raises (generation check) rather than returning wrong gradients.
+            twin = plans.lookup(key + ("twin",))
+            if twin is None:
+                twin = plans.insert(key + ("twin",), builder(model, n, h, w, x.device, training_stats, None, need_grad))
+            if not getattr(twin, "awaiting_backward", False):
+                plan = twin
+        plan.awaiting_backward = True
         out = _PlanFunction.apply(plan, x, *plan.params)
         return list(out) if isinstance(out, tuple) else out
     with torch.no_grad():

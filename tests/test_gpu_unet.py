@@ -663,3 +663,23 @@ def test_eval_forward_folds_batchnorm_into_the_conv_epilogue(name, n, h, w, monk
           f"plain vs oracle l2 {_l2rel(y_plain, ref):.3g}; launches {sum(c for c, _ in calls.values())} vs {sum(c for c, _ in calls0.values())}")
     assert _l2rel(y_fold, y_plain) <= 2e-2
     assert _l2rel(y_fold, ref) <= max(2e-2, 1.25 * _l2rel(y_plain, ref)) and _l2rel(y_fold, ref) <= 5e-2
+
+
+def test_two_forwards_before_backward():
+    """loss(model(a)) + loss(model(b)) with ONE backward (train.py:256-297 semantics under e.g. gradient accumulation over
+    two crops): the second forward of the same shape must not overwrite the activations the first backward needs."""
+    m = _model(42).to(DEV).train()
+    xa, _ = _inputs(31, 2, 32, 32)
+    xb, _ = _inputs(32, 2, 32, 32)
+    xa, xb = xa.to(DEV), xb.to(DEV)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    # reference order: one forward + backward at a time, gradients accumulate in .grad
+    m(xa).square().mean().backward()
+    m(xb).square().mean().backward()
+    ref = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.load_state_dict(sd)
+    m.zero_grad(set_to_none=True)
+    ya, yb = m(xa), m(xb)                      # two forwards ...
+    (ya.square().mean() + yb.square().mean()).backward()      # ... one backward through both
+    for k, p in m.named_parameters():
+        assert torch.allclose(p.grad, ref[k], rtol=1e-5, atol=1e-7), k
