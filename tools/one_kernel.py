@@ -41,6 +41,8 @@ def main():
         "conv1x1_fwd": lambda: ops.conv_fwd(x, w_ab, None, y, 1),
         "conv1x1_dgrad": lambda: ops.conv_dgrad(dy, w_ba, dx, 1),
         "conv1x1_wgrad": lambda: ops.conv_wgrad(x, dy, dw, 1, ws=ws),
+        "conv3x3_fwd": lambda: ops.conv_fwd(x, w_ab, None, y, 3),
+        "bn_stats": lambda: ops.bn_stats(y, partial, sums),
         "conv3x3_fwd_stats": lambda: ops.conv_fwd_stats(x, w_ab, None, y, partial, sums, 3, 1),
         "conv3x3_dgrad": lambda: ops.conv_dgrad(dy, w_ba, dx, 3),
         "conv3x3_wgrad": lambda: ops.conv_wgrad(x, dy, dw, 3, ws=ws),
