@@ -354,6 +354,10 @@ CONV_FLOPS = {
     "unetk_convT2x2_fwd": (6, 4, "tap_gemm"), "unetk_convT2x2_dgrad": (6, 4, "tap_gemm"),
     "unetk_conv3x3_wgrad": (6, 9, "wgrad"), "unetk_conv1x1_wgrad": (6, 1, "wgrad"), "unetk_convT2x2_wgrad": (6, 4, "wgrad"),
     "unetk_conv3x3s2_wgrad": (6, 9, "wgrad"),
+    # sub-pixel up-conv (H, W = the low-resolution size): 16 taps EXECUTED per low-resolution pixel; the reference's
+    # formulation of the same result (conv3x3 on the 2x up-sampled tensor) is 36 — the kernel tables count what ran
+    "unetk_upconv3x3_fwd": (8, 16, "tap_gemm"), "unetk_upconv3x3_dgrad": (6, 16, "tap_gemm"),
+    "unetk_upconv3x3_wgrad": (6, 16, "wgrad"),
 }
 
 

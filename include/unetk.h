@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define UNETK_ABI_VERSION 2
+#define UNETK_ABI_VERSION 3
 
 int unetk_abi_version(void);
 const char* unetk_last_error(void);
@@ -39,8 +39,9 @@ int64_t unetk_launch_count(void);
  * dst_ab is bf16 [T][A][B], dst_ba is bf16 [T][B][A]; either may be NULL. */
 int unetk_pack_weight(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, void* stream);
 /* Every weight of a model in ONE launch.  table = device int64 [n][8], row = {src, dst_ab, dst_ba, A, B, T,
- * first_tile, 0} where first_tile is the running sum of unetk_pack_tiles(A, B) over the preceding rows and
- * total_tiles the sum over all rows.  T <= 9. */
+ * first_tile, mode} where first_tile is the running sum of unetk_pack_tiles(A, B) over the preceding rows and
+ * total_tiles the sum over all rows.  T <= 9.  mode 0: the packs above; mode 1 (T = 9): the sub-pixel packs of an
+ * up_conv weight (dst_ab = dst_fwd, dst_ba = dst_dgrad of unetk_pack_upconv_weight, 16*A*B elements each). */
 int64_t unetk_pack_tiles(int A, int B);
 int unetk_pack_weights(const int64_t* table, int n, int64_t total_tiles, void* stream);
 
@@ -121,6 +122,30 @@ int unetk_convT2x2_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, vo
 int unetk_convT2x2_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw,
                          int accumulate, int N, int H, int W, int Cin, int Cout, void* workspace,
                          size_t ws_bytes, void* stream);
+
+/* ---- up_conv: nn.Upsample(scale_factor=2) (nearest) -> nn.Conv2d(k=3,p=1) (unet_parts.py:99-111) ---
+ * Sub-pixel form: phase (qy,qx) of the 2x output grid is a 2x2-tap convolution of the LOW-resolution input whose
+ * window starts at (qy-1,qx-1); 3x3 taps that read the same low-resolution pixel are pre-summed in fp32 and rounded to
+ * bf16 once (qy=0: {kh0},{kh1+kh2}; qy=1: {kh0+kh1},{kh2}; same along kw).  2.25x fewer FLOPs than the conv on the
+ * up-sampled tensor, which (like its gradient) is never materialised.  x is [N,H,W,Cin]; y, dy are [N,2H,2W,Cout].
+ *   pack_upconv_weight: src = fp32 master [Cout][Cin][3][3] -> dst_fwd bf16 [4 (u*2+v)][4 (qy*2+qx)][Cout][Cin],
+ *                       dst_dgrad bf16 [16 (q*4+u*2+v)][Cin][Cout] (either may be NULL).  unetk_pack_weights builds the
+ *                       same packs for table rows whose last column is 1.
+ *   fwd:    y = bias + conv; partial/sums (both or neither): fused per-channel (sum, sum sq) of the bf16 output as in
+ *           conv3x3_fwd_bnstats (partial >= unetk_conv_stats_partial_floats(Cout)).  fwd_affine: eval-mode BN fold.
+ *   dgrad:  dx[N,H,W,Cin] (+)= the input gradient (w_up_t = dst_dgrad).
+ *   wgrad:  dw fp32 [Cout][Cin][3][3] (+)= the gradient of the 3x3 MASTER weight (the sixteen sub-filter gradients are
+ *           folded back by the reduce step); workspace >= unetk_upconv_wgrad_workspace bytes. */
+int unetk_pack_upconv_weight(const float* src, void* dst_fwd, void* dst_dgrad, int Cout, int Cin, void* stream);
+int unetk_upconv3x3_fwd(const void* x, int64_t x_ld, const void* w_up, const float* bias, void* y, int64_t y_ld,
+                        float* partial, double* sums, int N, int H, int W, int Cin, int Cout, void* stream);
+int unetk_upconv3x3_fwd_affine(const void* x, int64_t x_ld, const void* w_up, const float* scale, const float* shift,
+                               int relu, void* y, int64_t y_ld, int N, int H, int W, int Cin, int Cout, void* stream);
+int unetk_upconv3x3_dgrad(const void* dy, int64_t dy_ld, const void* w_up_t, void* dx, int64_t dx_ld, int accumulate,
+                          int N, int H, int W, int Cin, int Cout, void* stream);
+size_t unetk_upconv_wgrad_workspace(int N, int H, int W, int Cin, int Cout);
+int unetk_upconv3x3_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw, int accumulate,
+                          int N, int H, int W, int Cin, int Cout, void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- stem convolution (network input, Cin <= 4; UNet.py:21 -> unet_parts.py:24) -------------------
  * Reads the fp32 image through arbitrary element strides (sn,sc,sh,sw) — NCHW or channels_last — rounds

@@ -45,6 +45,12 @@ SIGNATURES = {
     "unetk_conv1x1_fwd_bnstats": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv1x1_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "unetk_conv1x1_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "unetk_pack_upconv_weight": (_i, [_fp, _vp, _vp, _i, _i, _vp]),
+    "unetk_upconv3x3_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "unetk_upconv3x3_fwd_affine": (_i, [_vp, _i64, _vp, _fp, _fp, _i, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "unetk_upconv3x3_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "unetk_upconv_wgrad_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "unetk_upconv3x3_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "unetk_convT2x2_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "unetk_convT2x2_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "unetk_convT2x2_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
@@ -141,8 +147,8 @@ def load() -> C.CDLL:
         fn.restype = res
         fn.argtypes = args
     got = lib.unetk_abi_version()
-    if got != 2:
-        raise RuntimeError(f"libunetk.so ABI version {got}, expected 2")
+    if got != 3:
+        raise RuntimeError(f"libunetk.so ABI version {got}, expected 3")
     _lib = lib
     return lib
 

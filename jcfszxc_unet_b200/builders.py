@@ -36,7 +36,14 @@ def emit_conv_pair(P: Plan, x, seq, out: Act | None = None, pooled: Act | None =
 
 
 def emit_up_conv(P: Plan, x: Act, mod, out: Act | None = None) -> Act:
-    """up_conv.forward (unet_parts.py:99-111): nearest 2x -> conv3x3(bias) -> BN -> ReLU."""
+    """up_conv.forward (unet_parts.py:99-111): nearest 2x -> conv3x3(bias) -> BN -> ReLU.  Default: ONE unit in sub-pixel
+    form on the low-resolution tensor (ConvBNReLU(up=True): 2.25x fewer FLOPs, no up-sampled tensor);
+    UNETK_UPCONV_SUBPIXEL=0 materialises the up-sampled tensor and runs the 3x3 conv on it."""
+    conv = mod.up[1]
+    if os.environ.get("UNETK_UPCONV_SUBPIXEL", "1") != "0" and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0:
+        out = out if out is not None else P.act(2 * x.H, 2 * x.W, conv.out_channels)
+        ConvBNReLU(P, x, conv, mod.up[2], out, up=True)
+        return out
     up = P.act(2 * x.H, 2 * x.W, x.C)
     Upsample2x(P, x, up, "nearest")
     out = out if out is not None else P.act(up.H, up.W, mod.up[1].out_channels)

@@ -121,8 +121,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
         for (int t = 0; t < p.taps; ++t) {
-          const int ah = p.a_step * h0 + p.dh[t];
-          const int aw = p.a_step * w0 + p.dw[t];
+          const int ah = p.a_step * h0 + p.dh[t] + p.q_shift * static_cast<int>(q >> 1);
+          const int aw = p.a_step * w0 + p.dw[t] + p.q_shift * static_cast<int>(q & 1);
           const int bt = p.btap[t];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -397,6 +397,26 @@ __global__ void conv_stats_sums_kernel(const float* __restrict__ partial, int gr
   if (valid && threadIdx.y == 0) sums[i] = s;
 }
 
+// Output phases (q_groups > 1, the sub-pixel up-conv): channel c's N tile is owned by the CTAs b with
+// (b % num_n_tiles) % tiles_per_q == c / BN — one group of grid / num_n_tiles CTAs per phase (the grid is a multiple of
+// num_n_tiles); summed phase by phase in a fixed order.
+__global__ void conv_stats_sums_q_kernel(const float* __restrict__ partial, int grid, int tiles_per_q, int q_groups, int BN,
+                                         int C, double* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * kSum2Lanes + threadIdx.x;
+  const bool valid = i < 2 * C;
+  const int k = valid ? i / C : 0, c = valid ? i % C : 0;
+  const int nt = c / BN, cc = c % BN;
+  const int num_n_tiles = tiles_per_q * q_groups;
+  const int rounds = grid / num_n_tiles;
+  const double s = sliced_ordered_sum(partial, rounds * q_groups, valid, [&](int j) {
+    const int q = j % q_groups, r = j / q_groups;
+    return (static_cast<size_t>(q * tiles_per_q + nt + r * num_n_tiles) * 2 + k) * BN + cc;
+  });
+  if (valid && threadIdx.y == 0) sums[i] = s;
+}
+
 template <int BN, bool F32OUT, bool AFFINE>
 int launch_t(const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
@@ -457,9 +477,9 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   UNETK_CHECK((reinterpret_cast<uintptr_t>(d.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d.b) & 15) == 0,
               -1, "conv_gemm: pointers must be 16-byte aligned");
-  UNETK_CHECK(d.taps >= 1 && d.taps <= 9, -1, "conv_gemm: taps=%d", d.taps);
-  UNETK_CHECK(d.stats_sums == nullptr || (d.q_groups == 1 && d.stats_partial != nullptr), -1,
-              "conv_gemm: fused statistics need q_groups == 1 and a partial buffer");
+  UNETK_CHECK(d.taps >= 1 && d.taps <= 16, -1, "conv_gemm: taps=%d", d.taps);
+  UNETK_CHECK(d.stats_sums == nullptr || d.stats_partial != nullptr, -1, "conv_gemm: fused statistics need a partial buffer");
+  UNETK_CHECK(d.q_groups == 1 || d.q_groups == 4, -1, "conv_gemm: q_groups=%d (1 or 4)", d.q_groups);
 
   UNETK_CHECK(d.scale == nullptr || (reinterpret_cast<uintptr_t>(d.scale) & 15) == 0, -1, "conv_gemm: scale must be 16-byte aligned");
   UNETK_CHECK(d.scale == nullptr || (d.bias != nullptr && !d.accumulate && !d.out_f32 && d.stats_sums == nullptr), -1,
@@ -516,6 +536,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.kchunks = (d.K + kTileK - 1) / kTileK;
   p.ksteps_last = ((d.K - 1) % kTileK) / kUmmaK + 1;
   p.a_step = d.a_step;
+  p.q_shift = d.q_shift;
   for (int t = 0; t < d.taps; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
   p.bias = d.bias;
   p.scale = d.scale;
@@ -585,6 +606,12 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   }
   if (rc) return rc;
   if (d.stats_sums != nullptr) {
+    if (d.q_groups > 1) {
+      UNETK_CUDA(launch_pdl(conv_stats_sums_q_kernel, dim3((2 * d.ncols + kSum2Lanes - 1) / kSum2Lanes), dim3(kSum2Lanes, kSum2Slices),
+                            0, stream, static_cast<const float*>(d.stats_partial), grid, p.tiles_per_q, d.q_groups, BN, d.ncols, d.stats_sums));
+      UNETK_LAUNCHED();
+      return 0;
+    }
     return conv_stats_sums_launch(d.stats_partial, grid, p.num_n_tiles, BN, d.ncols, d.stats_sums, stream);
   }
   return 0;

@@ -29,11 +29,14 @@ struct ConvGemmDesc {
   int K;              // reduction channels per tap
   int ncols;          // output channels (per phase q)
   int q_groups;       // 1, or 4 for ConvTranspose fwd (output phase q=(dy,dx) selects weight rows + out pixel)
-  int taps;
+  int taps;             // <= 16
   int a_step;         // A coordinate = a_step*pos + offset (2 for ConvTranspose dgrad)
   int out_step;       // out coordinate = out_step*pos + phase (2 for ConvTranspose fwd)
-  int8_t dh[9], dw[9], btap[9];
-  // Optional fused BatchNorm statistics of the bf16 output (q_groups == 1 only):
+  int8_t dh[16], dw[16], btap[16];
+  // != 0: phase q = (qy, qx) reads A at dh[t] + q_shift*qy, dw[t] + q_shift*qx (the sub-pixel form of nearest-2x + conv3x3:
+  // phase (qy, qx) of the output is a 2x2-tap conv of the low-resolution input whose window starts at (qy-1, qx-1))
+  int q_shift;
+  // Optional fused BatchNorm statistics of the bf16 output (every output pixel of every phase counted once):
   float* stats_partial;   // scratch, >= conv_gemm_stats_partial_floats(ncols) floats
   double* stats_sums;     // out: double [2][ncols] = per-channel (sum, sum of squares)
   int accumulate;         // != 0: out += result (TMA reduce-add, bf16) instead of out = result
@@ -60,7 +63,8 @@ struct ConvGemmParams {
   float* out_f32;   // non-null: fp32 output written straight from registers (no staging, no statistics)
   long long out_ld; // fp32 path: floats between consecutive output pixels
   int out_step;     // fp32 path: out pixel = out_step * pos + phase (2 for ConvTranspose fwd)
-  int8_t dh[9], dw[9], btap[9];
+  int q_shift;      // A offset added per output phase: (q >> 1, q & 1) * q_shift
+  int8_t dh[16], dw[16], btap[16];
 };
 
 size_t conv_gemm_stats_partial_floats(int ncols);

@@ -8,6 +8,7 @@
 namespace unetk {
 const char* last_error();
 int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, int T, cudaStream_t stream);
+int pack_upconv_weight_run(const float* src, void* dst_fwd, void* dst_dgrad, int Cout, int Cin, cudaStream_t stream);
 // wgrad3x3.cu
 size_t wgrad3x3_workspace_bytes(int N, int H, int W, int M, int Nn);
 int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, float* dw, int accumulate, int N, int H,

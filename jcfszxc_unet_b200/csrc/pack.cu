@@ -20,8 +20,24 @@ struct PackJob {   // one row of the device table (8 x int64)
   __nv_bfloat16* dst_ba;
   long long A, B, T;
   long long first_tile;   // index of this weight's first tile in the batched grid
-  long long pad;
+  long long mode;         // 0: plain tap-major packs; 1: sub-pixel packs of an up_conv weight (T = 9), see pack_tile_up
 };
+
+// nearest-2x up-sampling followed by conv3x3(pad 1) (up_conv, unet_parts.py:99-111 in the reference) is, per output phase
+// q = (qy, qx) of the 2x grid, a 2x2-tap convolution of the LOW-resolution input whose window starts at (qy-1, qx-1):
+// rows kh of the 3x3 filter that read the same low-resolution row collapse into one tap,
+//   qy = 0: u = 0 <- {kh 0},    u = 1 <- {kh 1, 2};      qy = 1: u = 0 <- {kh 0, 1}, u = 1 <- {kh 2}   (same along kw).
+// The sums are taken in fp32 from the masters and rounded to bf16 once.  Layouts (A = Cout, B = Cin, t4 = u*2 + v):
+//   dst_ab = forward  B operand [t4][q][Cout][Cin]   (tap-major, rows q*Cout + co, K = Cin)
+//   dst_ba = dgrad    B operand [q*4 + t4][Cin][Cout] (16 taps, rows ci, K = Cout)
+__device__ __forceinline__ float up_tap(const float* w9, int qy, int qx, int u, int v) {
+  const int h0 = (qy == 0) ? (u == 0 ? 0 : 1) : (u == 0 ? 0 : 2), h1 = (qy == 0) ? (u == 0 ? 0 : 2) : (u == 0 ? 1 : 2);
+  const int w0 = (qx == 0) ? (v == 0 ? 0 : 1) : (v == 0 ? 0 : 2), w1 = (qx == 0) ? (v == 0 ? 0 : 2) : (v == 0 ? 1 : 2);
+  float acc = 0.f;
+  for (int kh = h0; kh <= h1; ++kh)
+    for (int kw = w0; kw <= w1; ++kw) acc += w9[kh * 3 + kw];
+  return acc;
+}
 
 __device__ __forceinline__ void pack_tile(const PackJob& j, int tile, float* s /* [32][32*T + 1] */) {
   const int A = static_cast<int>(j.A), B = static_cast<int>(j.B), T = static_cast<int>(j.T);
@@ -54,6 +70,27 @@ __device__ __forceinline__ void pack_tile(const PackJob& j, int tile, float* s /
     }
   }
   __syncthreads();
+  if (j.mode == 1) {   // T == 9 (checked on the host)
+    if (j.dst_ab != nullptr && tx < nb) {
+      for (int a = ty; a < na; a += 8) {
+        const float* w9 = s + a * row + tx * 9;
+        for (int q = 0; q < 4; ++q)
+          for (int t4 = 0; t4 < 4; ++t4)
+            j.dst_ab[(static_cast<long long>(t4 * 4 + q) * A + a0 + a) * B + b0 + tx] =
+                __float2bfloat16_rn(up_tap(w9, q >> 1, q & 1, t4 >> 1, t4 & 1));
+      }
+    }
+    if (j.dst_ba != nullptr && tx < na) {
+      for (int b = ty; b < nb; b += 8) {
+        const float* w9 = s + tx * row + b * 9;
+        for (int q = 0; q < 4; ++q)
+          for (int t4 = 0; t4 < 4; ++t4)
+            j.dst_ba[(static_cast<long long>(q * 4 + t4) * B + b0 + b) * A + a0 + tx] =
+                __float2bfloat16_rn(up_tap(w9, q >> 1, q & 1, t4 >> 1, t4 & 1));
+      }
+    }
+    return;
+  }
   if (j.dst_ab != nullptr && tx < nb) {
     for (int t = 0; t < T; ++t)
       for (int a = ty; a < na; a += 8)
@@ -103,7 +140,14 @@ int pack_weight_run(const float* src, void* dst_ab, void* dst_ba, int A, int B, 
   return 0;
 }
 
-// table: device int64 [n][8] rows {src, dst_ab, dst_ba, A, B, T, first_tile, 0} with first_tile ascending from 0
+int pack_upconv_weight_run(const float* src, void* dst_fwd, void* dst_dgrad, int Cout, int Cin, cudaStream_t stream) {
+  PackJob j{src, static_cast<__nv_bfloat16*>(dst_fwd), static_cast<__nv_bfloat16*>(dst_dgrad), Cout, Cin, 9, 0, 1};
+  UNETK_CUDA(launch_pdl(pack_weight_kernel, dim3(static_cast<int>(pack_tiles(Cout, Cin))), dim3(256), tile_smem(9), stream, j));
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+// table: device int64 [n][8] rows {src, dst_ab, dst_ba, A, B, T, first_tile, mode} with first_tile ascending from 0
 int pack_weights_run(const long long* table, int n, long long total_tiles, cudaStream_t stream) {
   UNETK_CHECK(table != nullptr && n > 0 && total_tiles > 0 && total_tiles < (1ll << 31), -1, "pack_weights: bad arguments");
   static_assert(sizeof(PackJob) == 64, "PackJob must be 8 x int64");

@@ -318,6 +318,42 @@ __global__ void wgrad_reduce_sliced_kernel(const float* __restrict__ partial, fl
   }
 }
 
+// Sub-pixel up-conv (nearest 2x + conv3x3 as four 2x2-tap convs, see pack.cu): partial[ks][q*4 + u*2 + v][M][Nn] holds the
+// gradients of the sixteen (phase, window tap) filters; every 3x3 tap (kh, kw) was summed into window tap
+// (u, v) = (U(qy, kh), U(qx, kw)) of EACH phase, so its gradient is the sum of those four.  U(0, k) = k > 0, U(1, k) = k > 1.
+__global__ void wgrad_reduce_upfold_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ksplit, int M,
+                                           int Nn, int64_t sm, int64_t sn, int64_t st, int accumulate, FastDiv fd_n) {
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t plane = static_cast<uint32_t>(M) * static_cast<uint32_t>(Nn);
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < plane; j += gridDim.x * blockDim.x) {
+    uint32_t m, n;
+    fd_n.divmod(j, m, n);
+    float g[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) g[t] = 0.f;
+    for (int k = 0; k < ksplit; ++k) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) g[t] += __ldg(partial + (static_cast<size_t>(k) * 16 + t) * plane + j);
+    }
+    float* o = dw + m * sm + n * sn;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int u = (q >> 1) == 0 ? (kh > 0) : (kh > 1), v = (q & 1) == 0 ? (kw > 0) : (kw > 1);
+          s += g[q * 4 + u * 2 + v];
+        }
+        const int t = kh * 3 + kw;
+        o[t * st] = accumulate ? (o[t * st] + s) : s;
+      }
+    }
+  }
+}
+
 template <int BN>
 int launch(const WgradParams& p, cudaStream_t stream) {
   using C = WCfg<BN>;
@@ -411,7 +447,8 @@ size_t wgrad_workspace_bytes(const WgradDesc& d) {
 int wgrad_run(const WgradDesc& d, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   UNETK_CHECK(d.M % 8 == 0 && d.Nn % 8 == 0, -1, "wgrad: channel counts must be multiples of 8 (M=%d N=%d)", d.M, d.Nn);
   UNETK_CHECK(d.p_ld % 8 == 0 && d.q_ld % 8 == 0, -1, "wgrad: pixel strides must be multiples of 8");
-  UNETK_CHECK(d.taps >= 1 && d.taps <= 9, -1, "wgrad: taps=%d", d.taps);
+  UNETK_CHECK(d.taps >= 1 && d.taps <= 16, -1, "wgrad: taps=%d", d.taps);
+  UNETK_CHECK(!d.fold_up || d.taps == 16, -1, "wgrad: the sub-pixel fold needs 16 taps");
   WgradParams p{};
   int BN;
   plan(d, &BN, &p.ksplit, &p.TH, &p.TW, &p.pix_tiles, &p.tpn);
@@ -450,6 +487,16 @@ int wgrad_run(const WgradDesc& d, void* workspace, size_t ws_bytes, cudaStream_t
     default: rc = launch<64>(p, stream); break;
   }
   if (rc) return rc;
+  if (d.fold_up) {
+    const int64_t plane = static_cast<int64_t>(d.M) * d.Nn;
+    UNETK_CHECK(plane < (1ll << 31), -1, "wgrad: M*N too large");
+    int blocks = static_cast<int>((plane + 255) / 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    UNETK_CUDA(launch_pdl(wgrad_reduce_upfold_kernel, dim3(blocks), dim3(256), 0, stream, static_cast<const float*>(p.partial), d.dw,
+                          p.ksplit, d.M, d.Nn, d.dw_sm, d.dw_sn, d.dw_st, d.accumulate, FastDiv(static_cast<uint32_t>(d.Nn))));
+    UNETK_LAUNCHED();
+    return 0;
+  }
   return wgrad_reduce_launch(p.partial, d.dw, p.ksplit, d.taps, d.M, d.Nn, d.dw_sm, d.dw_sn, d.dw_st, d.accumulate, stream);
 }
 

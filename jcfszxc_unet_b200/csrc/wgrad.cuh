@@ -19,7 +19,10 @@ struct WgradDesc {
   int N, H, W;    // reduction grid
   int M, Nn, taps;
   int p_step, q_step;
-  int8_t p_dh[9], p_dw[9], q_dh[9], q_dw[9];
+  int8_t p_dh[16], p_dw[16], q_dh[16], q_dw[16];
+  // != 0 (taps == 16): the taps are the (phase q, window tap t4) pairs of the sub-pixel up-conv, index q*4 + t4, and the
+  // reduce step folds them into the nine taps of the 3x3 filter it came from (wgrad_reduce_upfold_kernel)
+  int fold_up;
 };
 
 struct WgradParams {
@@ -32,7 +35,7 @@ struct WgradParams {
   int tgroups;  // taps / tpn
   int M, Nn;
   int p_step, q_step;
-  int8_t p_dh[9], p_dw[9], q_dh[9], q_dw[9];
+  int8_t p_dh[16], p_dw[16], q_dh[16], q_dw[16];
 };
 
 size_t wgrad_workspace_bytes(const WgradDesc& d);

@@ -188,10 +188,11 @@ class Plan:
         self._p_writers[id(p)] = self._p_writers.get(id(p), 0) + 1
         return hit
 
-    def pack_of(self, weight, taps: int, transposed_conv: bool = False) -> "WeightPack":
+    def pack_of(self, weight, taps: int, transposed_conv: bool = False, up: bool = False) -> "WeightPack":
         wp = self.packs.get(id(weight))
         if wp is None:
-            wp = self.packs[id(weight)] = WeightPack(weight, taps)
+            wp = self.packs[id(weight)] = WeightPack(weight, taps, up)
+        assert wp.up == up, "a weight cannot serve a plain conv and a sub-pixel up-conv at once"
         return wp
 
     # ---- execution ------------------------------------------------------------------------------
@@ -199,7 +200,7 @@ class Plan:
         lib = _lib.load()
         rows, first = [], 0
         for wp in self.packs.values():
-            rows.append([wp.w.data_ptr(), wp.ab.data_ptr(), wp.ba.data_ptr(), wp.a, wp.b, wp.taps, first, 0])
+            rows.append([wp.w.data_ptr(), wp.ab.data_ptr(), wp.ba.data_ptr(), wp.a, wp.b, wp.taps, first, int(wp.up)])
             first += lib.unetk_pack_tiles(wp.a, wp.b)
         self._pack_ptrs = [r[0] for r in rows]
         self._pack_table = torch.tensor(rows, dtype=torch.int64).to(self.device)
@@ -323,12 +324,19 @@ class WeightPack:
     """bf16 kernel-layout copies of one fp32 master weight [A,B,kh,kw]: ab = [T][A][B], ba = [T][B][A].
     A derived cache: re-packed when the master changes, shared by all ops using the weight."""
 
-    def __init__(self, weight, taps):
+    def __init__(self, weight, taps, up: bool = False):
         a, b = weight.shape[0], weight.shape[1]
         assert weight.numel() == a * b * taps
-        self.w, self.a, self.b, self.taps = weight, a, b, taps
-        self.ab = torch.empty((taps, a, b), dtype=BF16, device=weight.device)
-        self.ba = torch.empty((taps, b, a), dtype=BF16, device=weight.device)
+        self.w, self.a, self.b, self.taps, self.up = weight, a, b, taps, up
+        if up:
+            # sub-pixel packs of an up_conv weight (csrc/pack.cu): ab = forward [4 taps][4 phases][Cout][Cin],
+            # ba = dgrad [16 = phase*4 + tap][Cin][Cout]; 3x3 taps that read the same low-resolution pixel pre-summed
+            assert taps == 9
+            self.ab = torch.empty((4, 4, a, b), dtype=BF16, device=weight.device)
+            self.ba = torch.empty((16, b, a), dtype=BF16, device=weight.device)
+        else:
+            self.ab = torch.empty((taps, a, b), dtype=BF16, device=weight.device)
+            self.ba = torch.empty((taps, b, a), dtype=BF16, device=weight.device)
         self._stamp = None
 
     def stale(self):
@@ -349,7 +357,10 @@ class ConvBNReLU:
     Recurrent_block :119-128, RRCNN_block :143-146, ResidualConv :458-475, NestedUNet DoubleConv UNetPP.py:18-25."""
 
     def __init__(self, plan: Plan, x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d | None, out: Act,
-                 pooled: Act | None = None, relu: bool = True, res: Act | None = None):
+                 pooled: Act | None = None, relu: bool = True, res: Act | None = None, up: bool = False):
+        """up: `x` is the LOW-resolution input of an up_conv (unet_parts.py:103-104, nn.Upsample(scale_factor=2) then
+        this 3x3 conv): the conv runs in sub-pixel form — four 2x2-tap convs of x, one per output phase, 2.25x fewer FLOPs —
+        and the up-sampled tensor and its gradient are never materialised (unetk_upconv3x3_*)."""
         k, stride = conv.kernel_size[0], conv.stride[0]
         assert conv.kernel_size in ((3, 3), (1, 1)) and conv.padding == (k // 2, k // 2) and conv.stride == (stride, stride)
         assert stride == 1 or (stride == 2 and k == 3)
@@ -358,12 +369,15 @@ class ConvBNReLU:
         self.k, self.stride = k, stride
         self.stem = isinstance(x, Image)
         assert not (self.stem and stride != 1)
+        self.up = up
+        assert not up or (k == 3 and stride == 1 and not self.stem)
         if bn is None:
             assert pooled is None and res is None and not relu, "a conv without BatchNorm writes its output as is"
         self.cin, self.cout = conv.in_channels, conv.out_channels
         N, H, W = out.N, out.H, out.W
         if not self.stem:
-            assert (x.H, x.W) == (stride * H, stride * W) and x.C == self.cin, "conv input does not match its output"
+            assert ((2 * x.H, 2 * x.W) == (H, W) if up else (x.H, x.W) == (stride * H, stride * W)) and x.C == self.cin, \
+                "conv input does not match its output"
             if self.cin % 8 or self.cout % 8:
                 raise ValueError(f"conv {self.cin}->{self.cout}: channel counts must be multiples of 8 on the tensor-core path")
         assert out.C == self.cout
@@ -375,7 +389,7 @@ class ConvBNReLU:
                      and os.environ.get("UNETK_EVAL_FOLD", "1") != "0")
         self.raw = out if bn is None else (None if self.fold else plan.act(H, W, self.cout))
         self.stat = plan.vec(self.cout, 4) if bn is not None else None  # scale, shift, mean, invstd
-        self.pack = None if self.stem else plan.pack_of(conv.weight, k * k)
+        self.pack = None if self.stem else plan.pack_of(conv.weight, k * k, up=up)
         self.w3 = self.dw3 = None
         if self.stem and k == 1:
             self.w3 = torch.zeros((self.cout, self.cin, 3, 3), dtype=torch.float32, device=plan.device)
@@ -388,6 +402,8 @@ class ConvBNReLU:
         if plan.with_grad:
             if self.stem:
                 plan.need(0, lib.unetk_stem_wgrad_workspace(N, H, W, self.cin))
+            elif up:
+                plan.need(0, lib.unetk_upconv_wgrad_workspace(N, x.H, x.W, self.cin, self.cout))
             else:
                 plan.need(0, lib.unetk_conv_wgrad_workspace(N, H, W, self.cin, self.cout, k * k))
         for p in (conv.weight, conv.bias) + ((bn.weight, bn.bias) if bn is not None else ()):
@@ -454,6 +470,8 @@ class ConvBNReLU:
                               sc, sh)
         if self.stem:
             ops.stem_fwd_affine(P.image.x, (self.w3 if self.w3 is not None else self.conv.weight).detach(), sc, sh, self.relu, self.out.t)
+        elif self.up:
+            ops.upconv_fwd_affine(self.x.t, self.pack.ab, sc, sh, self.relu, self.out.t)
         else:
             ops.conv_fwd_affine(self.x.t, self.pack.ab, sc, sh, self.relu, self.out.t, self.stride)
         if self.pooled is not None:
@@ -471,6 +489,9 @@ class ConvBNReLU:
                 ops.stem_fwd_stats(P.image.x, w, bias, self.raw.t, P.partial, P.sums)
             else:
                 ops.stem_fwd(P.image.x, w, bias, self.raw.t)
+        elif self.up:
+            ops.upconv_fwd(self.x.t, self.pack.ab, bias, self.raw.t, P.partial if batch_stats else None,
+                           P.sums if batch_stats else None)
         elif batch_stats:
             # conv epilogue also produces the per-channel (sum, sum of squares) of its bf16 output
             ops.conv_fwd_stats(self.x.t, self.pack.ab, bias, self.raw.t, P.partial, P.sums, self.k, self.stride)
@@ -530,6 +551,8 @@ class ConvBNReLU:
                           int(self.acc_w and three), n, h, w, cin, self.cout, P.ws.data_ptr(), P.ws.numel(), _s())
                 if not three:
                     ops.copy_f32_strided(self.dw, 1, self.dw3, 9, self.cout * self.cin, accumulate=self.acc_w, src_offset=4)
+            elif self.up:
+                ops.upconv_wgrad(self.x.t, dy, self.dw, self.acc_w, ws=P.ws)
             else:
                 ops.conv_wgrad(self.x.t, dy, self.dw, self.k, self.acc_w, self.stride, ws=P.ws)
         if self.dbias is not None and self.bn is None:
@@ -537,7 +560,10 @@ class ConvBNReLU:
                 ops.copy_f32_strided(self.dbias, 1, self.bias_from, 1, self.cout, accumulate=self.acc_b)
             else:
                 ops.colsum(dy, P.partial, self.dbias, self.acc_b)
-        if not self.stem and self.x.g is not None and self.x_parts is not None:
+        if self.up:
+            if self.x.g is not None:
+                ops.upconv_dgrad(dy, self.pack.ba, self.x.g, self.acc_x)
+        elif not self.stem and self.x.g is not None and self.x_parts is not None:
             for (c0, c, t), acc in zip(self.x_parts, self.part_acc):
                 ops.conv_dgrad_cols(dy, self.pack.ba, c0, t.g, acc)
         elif not self.stem and self.x.g is not None:
@@ -595,7 +621,7 @@ class ConvT2x2:
         st, ld = og.untyped_storage().data_ptr(), og.stride(2)
         c0 = og.storage_offset() % ld
         for op in plan.ops:
-            if not isinstance(op, ConvBNReLU) or op.stem or op.k != 3 or op.stride != 1 or op.x.g is None or op.acc_x:
+            if not isinstance(op, ConvBNReLU) or op.stem or op.up or op.k != 3 or op.stride != 1 or op.x.g is None or op.acc_x:
                 continue
             if op.x.C < int(os.environ.get("UNETK_COLSUM_MIN_C", "128")):
                 # measured (B200, UNet 512^2, same box): 128-channel full-resolution dgrad 0.512 -> 0.597 ms with the

@@ -195,6 +195,69 @@ def convT_wgrad(x, dy, dw, accumulate: bool = False):
     return dw
 
 
+# ---- up_conv (nearest 2x + conv3x3) in sub-pixel form: x is the LOW-resolution tensor, y / dy are 2x larger
+def pack_upconv_weight(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = True):
+    """fp32 [Cout,Cin,3,3] -> (bf16 [4 taps, 4 phases, Cout, Cin] | None, bf16 [16, Cin, Cout] | None)."""
+    cout, cin = w.shape[0], w.shape[1]
+    assert tuple(w.shape[2:]) == (3, 3)
+    fwd = torch.empty((4, 4, cout, cin), dtype=torch.bfloat16, device=w.device) if want_fwd else None
+    dg = torch.empty((16, cin, cout), dtype=torch.bfloat16, device=w.device) if want_dgrad else None
+    _lib.call("unetk_pack_upconv_weight", _f32(w.detach()), fwd.data_ptr() if fwd is not None else None,
+              dg.data_ptr() if dg is not None else None, cout, cin, _stream())
+    return fwd, dg
+
+
+def upconv_fwd(x, w_up, bias, y, partial=None, sums=None):
+    """y [N,2H,2W,Cout] <- conv3x3(nearest2x(x [N,H,W,Cin])) (+bias); optional fused BatchNorm sums (fp64 [2,Cout])."""
+    n, h, w, cin = x.shape
+    cout = y.shape[3]
+    assert w_up.numel() == 16 * cout * cin and y.shape[1] == 2 * h and y.shape[2] == 2 * w
+    xp, xld = nhwc(x)
+    yp, yld = nhwc(y)
+    _lib.call("unetk_upconv3x3_fwd", xp, xld, w_up.data_ptr(), _f32(bias), yp, yld,
+              partial.data_ptr() if partial is not None else None, sums.data_ptr() if sums is not None else None,
+              n, h, w, cin, cout, _stream())
+    return y
+
+
+def upconv_fwd_affine(x, w_up, scale, shift, relu, y):
+    n, h, w, cin = x.shape
+    cout = y.shape[3]
+    assert w_up.numel() == 16 * cout * cin and y.shape[1] == 2 * h and y.shape[2] == 2 * w
+    xp, xld = nhwc(x)
+    yp, yld = nhwc(y)
+    _lib.call("unetk_upconv3x3_fwd_affine", xp, xld, w_up.data_ptr(), _f32(scale), _f32(shift), int(relu), yp, yld,
+              n, h, w, cin, cout, _stream())
+    return y
+
+
+def upconv_dgrad(dy, w_up_t, dx, accumulate: bool = False):
+    """dx [N,H,W,Cin] (+)<- dy [N,2H,2W,Cout]; w_up_t bf16 [16,Cin,Cout]."""
+    n, h, w, cin = dx.shape
+    cout = dy.shape[3]
+    assert w_up_t.numel() == 16 * cout * cin and dy.shape[1] == 2 * h and dy.shape[2] == 2 * w
+    dyp, dyld = nhwc(dy)
+    dxp, dxld = nhwc(dx)
+    _lib.call("unetk_upconv3x3_dgrad", dyp, dyld, w_up_t.data_ptr(), dxp, dxld, int(accumulate), n, h, w, cin, cout,
+              _stream())
+    return dx
+
+
+def upconv_wgrad(x, dy, dw, accumulate: bool = False, ws=None):
+    """dw (fp32 [Cout,Cin,3,3], the 3x3 master's gradient) (+)<- x [N,H,W,Cin], dy [N,2H,2W,Cout]."""
+    n, h, w, cin = x.shape
+    cout = dy.shape[3]
+    assert dw.shape == (cout, cin, 3, 3) and dw.dtype == torch.float32 and dw.is_contiguous()
+    assert dy.shape[1] == 2 * h and dy.shape[2] == 2 * w
+    if ws is None:
+        ws = workspace(_lib.load().unetk_upconv_wgrad_workspace(n, h, w, cin, cout), x.device)
+    xp, xld = nhwc(x)
+    dyp, dyld = nhwc(dy)
+    _lib.call("unetk_upconv3x3_wgrad", xp, xld, dyp, dyld, dw.data_ptr(), int(accumulate), n, h, w, cin, cout,
+              ws.data_ptr(), ws.numel(), _stream())
+    return dw
+
+
 # ------------------------------------------------------------------------------------------------
 # stem (network-input conv), BatchNorm/ReLU/MaxPool, head + loss, optimizer
 # ------------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@ path, independently of torch, so that the checker does not rest on "the same lib
     conv_transpose2d k=2 s=2               torch.nn.ConvTranspose2d  weight [Cin,Cout,2,2], non-overlapping scatter
     batch_norm (train / eval)              torch.nn.BatchNorm2d      biased variance to normalise, unbiased for running_var
     relu, sigmoid, max_pool2d(2) + indices, nearest 2x / bilinear 2x (align_corners=True) up-sampling
+    nearest 2x + conv3x3 as four 2x2-tap convs of the low-resolution input (the sub-pixel identity of the CUDA up-conv)
     bce_with_logits (mean)                 torch.nn.BCEWithLogitsLoss  max(z,0) - z*y + log1p(exp(-|z|))
     unet_forward                           UNetFamily/UNet.py:39-55 on UNetFamily/utils/unet_parts.py:17-79
 
@@ -97,6 +98,64 @@ def max_pool2x2(x):
 
 def upsample_nearest2x(x):
     return x.repeat(2, axis=2).repeat(2, axis=3)
+
+
+# ---- nearest 2x + conv3x3 in sub-pixel form: the identity the CUDA up-conv kernels compute by (csrc/pack.cu, capi.cu
+# unetk_upconv3x3_*).  Restated here so that the identity itself — which 3x3 taps collapse into which 2x2 window tap of
+# which output phase, and how the sixteen sub-filter gradients fold back — is pinned on the CPU against the reference's
+# own formulation (unet_parts.py:103-104: nn.Upsample(scale_factor=2) then nn.Conv2d(k=3, p=1)).
+def _subpixel_rows(q, u):
+    """3x3 taps along one axis that read window tap u of output phase q: q=0: {0}, {1,2}; q=1: {0,1}, {2}."""
+    return ((0,), (1, 2))[u] if q == 0 else ((0, 1), (2,))[u]
+
+
+def subpixel_weights(w):
+    """w [Cout,Cin,3,3] -> wq [qy,qx,u,v,Cout,Cin]: phase (qy,qx) of the 2x grid is a 2x2-tap conv of the LOW-resolution
+    input whose window starts at (qy-1, qx-1)."""
+    cout, cin = w.shape[:2]
+    wq = np.zeros((2, 2, 2, 2, cout, cin), dtype=np.float64)
+    for qy in range(2):
+        for qx in range(2):
+            for u in range(2):
+                for v in range(2):
+                    for kh in _subpixel_rows(qy, u):
+                        for kw in _subpixel_rows(qx, v):
+                            wq[qy, qx, u, v] += w[:, :, kh, kw]
+    return wq
+
+
+def upconv_subpixel(x, w, b=None):
+    """conv2d(upsample_nearest2x(x), w, b) computed on the low-resolution x: y[n,:,2i+qy,2j+qx] = b + sum_{u,v}
+    wq[qy,qx,u,v] @ x[n,:,i+qy-1+u,j+qx-1+v] (zero outside)."""
+    n, cin, h, wd = x.shape
+    wq = subpixel_weights(w)
+    cout = w.shape[0]
+    xp = np.zeros((n, cin, h + 2, wd + 2), dtype=np.float64)
+    xp[:, :, 1:-1, 1:-1] = x
+    y = np.zeros((n, cout, 2 * h, 2 * wd), dtype=np.float64)
+    for qy in range(2):
+        for qx in range(2):
+            for u in range(2):
+                for v in range(2):
+                    patch = xp[:, :, qy + u:qy + u + h, qx + v:qx + v + wd]
+                    y[:, :, qy::2, qx::2] += np.einsum("nchw,oc->nohw", patch, wq[qy, qx, u, v])
+    if b is not None:
+        y += np.asarray(b, dtype=np.float64).reshape(1, -1, 1, 1)
+    return y
+
+
+def fold_subpixel_wgrad(g):
+    """g [qy,qx,u,v,Cout,Cin] (gradients of the sixteen sub-filters) -> dw [Cout,Cin,3,3]: tap (kh,kw) was summed into
+    window tap (U(qy,kh), U(qx,kw)) of every phase, U(0,k) = k>0, U(1,k) = k>1."""
+    dw = np.zeros(g.shape[4:] + (3, 3), dtype=np.float64)
+    for kh in range(3):
+        for kw in range(3):
+            for qy in range(2):
+                for qx in range(2):
+                    u = int(kh > 0) if qy == 0 else int(kh > 1)
+                    v = int(kw > 0) if qx == 0 else int(kw > 1)
+                    dw[:, :, kh, kw] += g[qy, qx, u, v]
+    return dw
 
 
 def upsample_bilinear2x_align_corners(x):

@@ -31,7 +31,7 @@ def _ctype_of(decl: str):
 
 def test_library_builds_and_loads():
     lib = _lib.load()
-    assert lib.unetk_abi_version() == 2
+    assert lib.unetk_abi_version() == 3
     assert lib.unetk_last_error() is not None
 
 

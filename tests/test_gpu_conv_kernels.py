@@ -389,3 +389,114 @@ def test_sm_limit_keeps_results_and_scratch_sizes_valid():
         assert lib.unetk_set_sm_limit(0) == real - 16          # the request for 7 SMs was clamped to device_sms - 16
     finally:
         lib.unetk_set_sm_limit(0)
+
+
+UPCONV_SHAPES = [
+    # n, h, w (LOW resolution), cin, cout, ypad(lo,hi)
+    (2, 8, 8, 64, 32, (0, 0)),        # the block test's shape; BN = 64, four phases
+    (1, 32, 32, 1024, 512, (0, 0)),   # Up5 of the models: BN = 256, 16 k-chunks per tap
+    (2, 16, 16, 128, 64, (64, 0)),    # output = upper slice of a concat buffer
+    (1, 5, 7, 16, 8, (0, 0)),         # odd sizes: every border of the 2x2 windows, ragged tiles
+    (1, 3, 130, 64, 64, (0, 64)),     # TW = 128, two column tiles (the second one ragged), sliced output
+    (1, 64, 64, 256, 128, (0, 0)),    # BN = 128
+    (3, 2, 2, 24, 40, (0, 0)),        # deepest level of a 32 x 32 image; channel counts that are not multiples of 64
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,ypad", UPCONV_SHAPES)
+def test_upconv3x3_subpixel(n, h, w, cin, cout, ypad):
+    """up_conv's nn.Upsample(scale_factor=2) -> nn.Conv2d(k=3,p=1) (unet_parts.py:103-104) in sub-pixel form on the
+    low-resolution tensor: packs bit-exact against the oracle's restatement of the identity, forward (+ fused BatchNorm
+    sums), input gradient (plain and accumulating) and the folded 3x3 weight gradient against torch on the up-sampled
+    tensor."""
+    from jcfszxc_unet_b200 import _lib
+    from oracle import numpy_ops as NO
+
+    ops = _ops()
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(3 + cin + cout + h)
+    x = torch.randn(n, h, w, cin, device=dev, generator=g).bfloat16()
+    wt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * (1.0 / (3 * cin ** 0.5))
+    bias = torch.randn(cout, device=dev, generator=g)
+    w_fwd, w_dg = ops.pack_upconv_weight(wt)
+    # packs: the fp32 sums of the taps that share a low-resolution pixel, rounded to bf16 once
+    wq = NO.subpixel_weights(wt.double().cpu().numpy())            # [qy,qx,u,v,Cout,Cin] in float64
+    wq32 = torch.zeros(2, 2, 2, 2, cout, cin, device=dev)
+    for qy in range(2):
+        for qx in range(2):
+            for u in range(2):
+                for v in range(2):
+                    acc = torch.zeros(cout, cin, device=dev)
+                    for kh in NO._subpixel_rows(qy, u):             # same order as the kernel: kh outer, kw inner
+                        for kw in NO._subpixel_rows(qx, v):
+                            acc = acc + wt[:, :, kh, kw]
+                    wq32[qy, qx, u, v] = acc
+    assert (wq32.double().cpu() - torch.from_numpy(wq)).abs().max().item() <= 1e-6
+    exp_fwd = wq32.permute(2, 3, 0, 1, 4, 5).reshape(4, 4, cout, cin).bfloat16()          # [t4][q][Cout][Cin]
+    exp_dg = wq32.reshape(16, cout, cin).transpose(1, 2).contiguous().bfloat16()          # [q*4+t4][Cin][Cout]
+    assert torch.equal(w_fwd, exp_fwd) and torch.equal(w_dg, exp_dg)
+
+    xr = x.float().permute(0, 3, 1, 2)
+    up = F.interpolate(xr, scale_factor=2, mode="nearest")
+    ybuf, y = _nhwc_slice(n, 2 * h, 2 * w, cout, dev, *ypad, fill=5.0)
+    partial = torch.empty(max(lib.unetk_conv_stats_partial_floats(cout), 4096), device=dev)
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+    ops.upconv_fwd(x, w_fwd, bias, y, partial, sums)
+    # like-for-like reference: the four phase convs with the SAME bf16 sub-filters, fp32 accumulation
+    refq = torch.zeros(n, cout, 2 * h, 2 * w, device=dev)
+    xp = F.pad(xr, (1, 1, 1, 1))
+    wb = exp_fwd.float().reshape(2, 2, 2, 2, cout, cin)   # [u][v][qy][qx]
+    for qy in range(2):
+        for qx in range(2):
+            for u in range(2):
+                for v in range(2):
+                    patch = xp[:, :, qy + u:qy + u + h, qx + v:qx + v + w]
+                    refq[:, :, qy::2, qx::2] += torch.einsum("nchw,oc->nohw", patch, wb[u, v, qy, qx])
+    refq += bias.view(1, -1, 1, 1)
+    _close(y, refq.permute(0, 2, 3, 1), "upconv_fwd vs the same bf16 sub-filters")
+    # and the reference's own formulation (bf16 3x3 weights on the up-sampled tensor): one extra weight rounding apart
+    ref33 = F.conv2d(up, wt.bfloat16().float(), bias, padding=1).permute(0, 2, 3, 1)
+    _close(y, ref33, "upconv_fwd vs conv3x3(nearest2x(x))")
+    if ypad[0]:
+        assert (ybuf[..., :ypad[0]] == 5.0).all()
+    if ypad[1]:
+        assert (ybuf[..., ypad[0] + cout:] == 5.0).all()
+    yd = y.float().double()
+    s_ref = torch.stack([yd.sum(dim=(0, 1, 2)), (yd * yd).sum(dim=(0, 1, 2))]).reshape(-1)
+    assert (sums - s_ref).abs().max().item() <= 1e-3 * max(1.0, s_ref.abs().max().item())
+    y2buf, y2 = _nhwc_slice(n, 2 * h, 2 * w, cout, dev, *ypad)
+    ops.upconv_fwd(x, w_fwd, bias, y2)
+    assert torch.equal(y2, y)
+
+    # eval-mode fold: relu(conv * scale + shift)
+    scale = torch.rand(cout, device=dev, generator=g) + 0.5
+    shift = torch.randn(cout, device=dev, generator=g)
+    y3 = torch.empty(n, 2 * h, 2 * w, cout, device=dev, dtype=torch.bfloat16)
+    ops.upconv_fwd_affine(x, w_fwd, scale, shift, True, y3)
+    ref3 = torch.relu((refq - bias.view(1, -1, 1, 1)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    _close(y3, ref3, "upconv_fwd_affine")
+
+    _, dy = _nhwc_slice(n, 2 * h, 2 * w, cout, dev, *ypad)
+    dy.copy_(torch.randn(n, 2 * h, 2 * w, cout, device=dev, generator=g))
+    dyr = dy.float().permute(0, 3, 1, 2)
+    upr = up.clone().requires_grad_(True)
+    wr = wt.bfloat16().float().requires_grad_(True)
+    F.conv2d(upr, wr, None, padding=1).backward(dyr)
+    dx_ref = (upr.grad[:, :, 0::2, 0::2] + upr.grad[:, :, 0::2, 1::2] + upr.grad[:, :, 1::2, 0::2] + upr.grad[:, :, 1::2, 1::2])
+    dx = torch.full_like(x, 7.0)
+    ops.upconv_dgrad(dy, w_dg, dx)
+    _close(dx, dx_ref.permute(0, 2, 3, 1), "upconv_dgrad")
+    base = torch.randn(n, h, w, cin, device=dev, generator=g).bfloat16()
+    dx2 = base.clone()
+    ops.upconv_dgrad(dy, w_dg, dx2, accumulate=True)
+    _close(dx2, (base.float() + dx.float()), "upconv_dgrad accumulate")
+
+    # weight gradient: mathematically the same sum as the 3x3 conv's on the up-sampled tensor (operands are bf16-exact)
+    dw = torch.full((cout, cin, 3, 3), 9.0, device=dev)
+    ops.upconv_wgrad(x, dy, dw)
+    dw_ref = torch.nn.grad.conv2d_weight(up.double(), (cout, cin, 3, 3), dyr.double(), padding=1).float()
+    assert (dw - dw_ref).abs().max().item() <= 2e-3 * dw_ref.abs().max().item()
+    dw2 = dw.clone()
+    ops.upconv_wgrad(x, dy, dw2, accumulate=True)
+    assert (dw2 - 2 * dw).abs().max().item() <= 1e-5 * dw.abs().max().item()

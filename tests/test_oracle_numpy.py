@@ -80,3 +80,29 @@ def test_numpy_unet_forward_matches_reference_golden():
     ye = N.unet_forward(x, sd, training=False)
     ref_e = g["logits_eval_after_1_train_fwd"]
     assert np.abs(ye - ref_e).max() <= 1e-4 * np.abs(ref_e).max()
+
+
+def test_subpixel_upconv_identity_vs_torch_float64():
+    """nearest 2x + conv3x3(pad 1) == four 2x2-tap convs of the low-resolution input with pre-summed taps (the form the
+    CUDA up-conv kernels compute in), forward and weight-gradient fold, against the reference's formulation
+    (unet_parts.py:103-104) in torch float64; odd sizes, so that every border case of the window is hit."""
+    x, w, b = _r(2, 5, 5, 7, seed=21), _r(4, 5, 3, 3, seed=22), _r(4, seed=23)
+    xt = torch.from_numpy(x)
+    wt = torch.from_numpy(w).requires_grad_(True)
+    ref = F.conv2d(F.interpolate(xt, scale_factor=2, mode="nearest"), wt, torch.from_numpy(b), padding=1)
+    _close(N.upconv_subpixel(x, w, b), ref.detach().numpy())
+    _close(N.upconv_subpixel(x, w), N.conv2d(N.upsample_nearest2x(x), w))
+    # gradients of the sixteen sub-filters (autograd through the restated forward), folded back to the 3x3 filter
+    dy = torch.from_numpy(_r(*ref.shape, seed=24))
+    ref.backward(dy)
+    wq = torch.from_numpy(N.subpixel_weights(w)).requires_grad_(True)
+    xp = F.pad(xt, (1, 1, 1, 1))
+    y = torch.zeros_like(ref)
+    for qy in range(2):
+        for qx in range(2):
+            for u in range(2):
+                for v in range(2):
+                    patch = xp[:, :, qy + u:qy + u + 5, qx + v:qx + v + 7]
+                    y[:, :, qy::2, qx::2] += torch.einsum("nchw,oc->nohw", patch, wq[qy, qx, u, v])
+    y.backward(dy)
+    _close(N.fold_subpixel_wgrad(wq.grad.numpy()), wt.grad.numpy())
