@@ -368,11 +368,18 @@ static WgradDesc upconv_wgrad_desc(const void* x, int64_t x_ld, const void* dy, 
 }
 size_t unetk_upconv_wgrad_workspace(int N, int H, int W, int Cin, int Cout) {
   if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return 0;
-  return max_over_sm_limits([&] { return wgrad_workspace_bytes(upconv_wgrad_desc(nullptr, 0, nullptr, 0, nullptr, 0, N, H, W, Cin, Cout)); });
+  return max_over_sm_limits([&] {
+    const size_t a = wgrad_workspace_bytes(upconv_wgrad_desc(nullptr, 0, nullptr, 0, nullptr, 0, N, H, W, Cin, Cout));
+    const size_t b = wgrad_up_workspace_bytes(N, H, W, Cin, Cout);
+    return a > b ? a : b;
+  });
 }
 int unetk_upconv3x3_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw, int accumulate,
                           int N, int H, int W, int Cin, int Cout, void* workspace, size_t ws_bytes, void* stream) {
   UNETK_CHECK(x && dy && dw && N > 0 && H > 0 && W > 0, -1, "upconv3x3_wgrad: bad arguments");
+  // all four taps of a phase from one halo load (wgrad_up.cu); shapes it does not cover (W < 16) use the per-tap kernel
+  const int rc = wgrad_up_run(x, x_ld, dy, dy_ld, dw, accumulate, N, H, W, Cin, Cout, workspace, ws_bytes, S(stream));
+  if (rc <= 0) return rc;
   return wgrad_run(upconv_wgrad_desc(x, x_ld, dy, dy_ld, dw, accumulate, N, H, W, Cin, Cout), workspace, ws_bytes, S(stream));
 }
 

@@ -18,6 +18,8 @@ namespace unetk {
 
 int wgrad_reduce_launch(const float* partial, float* dw, int ksplit, int taps, int M, int Nn, int64_t sm, int64_t sn,
                         int64_t st, int accumulate, cudaStream_t stream);
+int wgrad_upfold_launch(const float* partial, float* dw, int ksplit, int M, int Nn, int64_t sm, int64_t sn, int64_t st,
+                        int accumulate, cudaStream_t stream);
 
 namespace {
 
@@ -438,6 +440,18 @@ int wgrad_reduce_launch(const float* partial, float* dw, int ksplit, int taps, i
   return 0;
 }
 
+int wgrad_upfold_launch(const float* partial, float* dw, int ksplit, int M, int Nn, int64_t sm, int64_t sn, int64_t st,
+                        int accumulate, cudaStream_t stream) {
+  const int64_t plane = static_cast<int64_t>(M) * Nn;
+  UNETK_CHECK(plane < (1ll << 31), -1, "wgrad_upfold: M*N too large");
+  int blocks = static_cast<int>((plane + 255) / 256);
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  UNETK_CUDA(launch_pdl(wgrad_reduce_upfold_kernel, dim3(blocks), dim3(256), 0, stream, partial, dw, ksplit, M, Nn, sm, sn, st,
+                        accumulate, FastDiv(static_cast<uint32_t>(Nn))));
+  UNETK_LAUNCHED();
+  return 0;
+}
+
 size_t wgrad_workspace_bytes(const WgradDesc& d) {
   int BN, ks, TH, TW, pt;
   plan(d, &BN, &ks, &TH, &TW, &pt);
@@ -487,16 +501,7 @@ int wgrad_run(const WgradDesc& d, void* workspace, size_t ws_bytes, cudaStream_t
     default: rc = launch<64>(p, stream); break;
   }
   if (rc) return rc;
-  if (d.fold_up) {
-    const int64_t plane = static_cast<int64_t>(d.M) * d.Nn;
-    UNETK_CHECK(plane < (1ll << 31), -1, "wgrad: M*N too large");
-    int blocks = static_cast<int>((plane + 255) / 256);
-    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-    UNETK_CUDA(launch_pdl(wgrad_reduce_upfold_kernel, dim3(blocks), dim3(256), 0, stream, static_cast<const float*>(p.partial), d.dw,
-                          p.ksplit, d.M, d.Nn, d.dw_sm, d.dw_sn, d.dw_st, d.accumulate, FastDiv(static_cast<uint32_t>(d.Nn))));
-    UNETK_LAUNCHED();
-    return 0;
-  }
+  if (d.fold_up) return wgrad_upfold_launch(p.partial, d.dw, p.ksplit, d.M, d.Nn, d.dw_sm, d.dw_sn, d.dw_st, d.accumulate, stream);
   return wgrad_reduce_launch(p.partial, d.dw, p.ksplit, d.taps, d.M, d.Nn, d.dw_sm, d.dw_sn, d.dw_st, d.accumulate, stream);
 }
 

@@ -298,7 +298,10 @@ def _block_case(name):
 
     return {
         "conv_block": (lambda: P.conv_block(64, 32), [(2, 64, 16, 16)], lambda xs, sd: O.conv_block(xs[0], sd, "", True)),
-        "up_conv": (lambda: P.up_conv(64, 32), [(2, 64, 8, 8)], lambda xs, sd: O.up_conv(xs[0], sd, "", True)),
+        # 32 x 32 input (8192 output pixels per channel): the BatchNorm beta / input gradients of this block are sums over
+        # ReLU masks, a handful of mask flips (outputs within one bf16 rounding of zero) decide their distance from fp32,
+        # and with 512 pixels per channel that distance scatters by 2x between two equally accurate bf16 runs
+        "up_conv": (lambda: P.up_conv(64, 32), [(2, 64, 32, 32)], lambda xs, sd: O.up_conv(xs[0], sd, "", True)),
         "recurrent": (lambda: P.Recurrent_block(32, t=2), [(2, 32, 16, 16)], lambda xs, sd: O.recurrent_block(xs[0], sd, "", True, 2)),
         "rrcnn": (lambda: P.RRCNN_block(64, 32, t=2), [(2, 64, 16, 16)], lambda xs, sd: O.rrcnn_block(xs[0], sd, "", True, 2)),
         "attention": (lambda: P.Attention_block(64, 64, 32), [(2, 64, 16, 16), (2, 64, 16, 16)],
