@@ -12,6 +12,11 @@
 // Pipeline: warp0 = TMA producer (A halo ring of 2, B ring per tap), warp1 = MMA issuer, warps2-5 =
 // epilogue (TMEM -> bf16 -> swizzled smem -> TMA store, optional fused BatchNorm statistics), accumulators
 // double-buffered in TMEM (2 tiles x 2 rows x BN columns).
+//
+// TAPS = 4, phases: the sub-pixel up-conv (nearest 2x + conv3x3 as four 2x2-tap convs of the low-resolution tensor,
+// capi.cu unetk_upconv3x3_fwd).  The four output phases are four groups of N tiles (q = nt / tiles_per_q) that share the
+// SAME halo — phase (qy, qx) reads it one row / one pixel further in — use their own weight rows (q * ncols + co) and
+// store through their own stride-2 view of the output.
 #include "conv_gemm.cuh"
 #include "host_common.cuh"
 #include "ptx.cuh"
@@ -47,7 +52,7 @@ struct HCfg {
 struct HaloParams {
   CUtensorMap tmA;    // dims (K, W, H, N), box (64, 130, 4, 1)
   CUtensorMap tmB;    // dims (K, ncols, 9), box (64, BN, 1)
-  CUtensorMap tmOut;  // dims (ncols, W, H, N), box (64, 128, 1, 1)
+  CUtensorMap tmOut[4];  // dims (ncols, W, H, N), box (64, 128, 1, 1); one per output phase ([0] only unless phased)
   const float* bias;
   const float* scale;   // non-null: eval-mode BatchNorm fold, out = relu?(acc * scale + bias) (the AFFINE instantiation)
   int relu;
@@ -55,12 +60,14 @@ struct HaloParams {
   int accumulate;  // != 0: out += tile (TMA reduce-add)
   int H, W, tiles_h, tiles_w, num_m_tiles, num_n_tiles, ncols, kchunks;
   FastDiv fd_n_tiles, fd_tiles_w, fd_tiles_h;
-  int resident;  // 1: all 9*kchunks weight tiles stay in smem for the whole kernel (they fit), no B ring
+  int resident;  // 1: all TAPS*kchunks weight tiles stay in smem for the whole kernel (they fit), no B ring
+  int tiles_per_q;  // N tiles per output phase (num_n_tiles = tiles_per_q * phases)
+  int q_shift;      // halo offset added per phase: (q >> 1, q & 1) * q_shift
   int l2_prefetch;  // > 0: L2-prefetch the halo of the tile `l2_prefetch` rounds ahead
   int8_t dh[9], dw[9], btap[9];
 };
 
-template <int BN, bool AFFINE>
+template <int BN, bool AFFINE, int TAPS>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_constant__ HaloParams p) {
   using C = HCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -68,7 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;                                   // [2][kHaloSlot]
   uint8_t* sB = sA + 2 * kHaloSlot;                     // [kBStages][kBBytes]
-  const uint32_t b_region = p.resident ? static_cast<uint32_t>(9 * p.kchunks) * C::kBBytes : C::kBStages * C::kBBytes;
+  const uint32_t b_region = p.resident ? static_cast<uint32_t>(TAPS * p.kchunks) * C::kBBytes : C::kBStages * C::kBBytes;
   const int n_staging = p.resident ? 1 : C::kStaging;
   uint8_t* staging = sB + b_region;                     // [n_staging][16 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + n_staging * kStagingBytes);
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    tma_prefetch_desc(&p.tmOut);
+    tma_prefetch_desc(&p.tmOut[0]);
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
@@ -141,17 +148,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       if (p.resident) {
         // grid is a multiple of num_n_tiles => this CTA always works on N tile blockIdx % num_n_tiles
         const int nt = blockIdx.x % p.num_n_tiles;
-        mbar_expect_tx(w_full, static_cast<uint32_t>(9 * p.kchunks) * C::kBBytes);
+        mbar_expect_tx(w_full, static_cast<uint32_t>(TAPS * p.kchunks) * C::kBBytes);
         for (int kc = 0; kc < p.kchunks; ++kc)
-          for (int t = 0; t < 9; ++t)
-            tma_load_3d(sB + (kc * 9 + t) * C::kBBytes, &p.tmB, w_full, kc * 64, nt * BN, p.btap[t]);
+          for (int t = 0; t < TAPS; ++t)
+            tma_load_3d(sB + (kc * TAPS + t) * C::kBBytes, &p.tmB, w_full, kc * 64, nt * BN, p.btap[t]);
       } else {
         int bs = 0;
         uint32_t bph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           const int nt = tile % p.num_n_tiles;
           for (int kc = 0; kc < p.kchunks; ++kc) {
-            for (int t = 0; t < 9; ++t) {
+            for (int t = 0; t < TAPS; ++t) {
               mbar_wait(&b_empty[bs], bph ^ 1u);
               mbar_expect_tx(&b_full[bs], C::kBBytes);
               tma_load_3d(sB + bs * C::kBBytes, &p.tmB, &b_full[bs], kc * 64, nt * BN, p.btap[t]);
@@ -175,6 +182,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         mbar_wait_p(issue, &tempty[acc], ((it >> 1) & 1) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 2 * BN * C::kSplit;   // [split][row][BN]
+        // output phase of this tile's N tile: its window starts (qy, qx) * q_shift further into the halo
+        const int q = (tile % p.num_n_tiles) / p.tiles_per_q;
+        const int q_halo = ((q >> 1) * kHaloW + (q & 1)) * p.q_shift;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait_p(issue, &a_full[as], aph);
           tc_fence_after();
@@ -185,15 +195,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
           // Taps are issued kSplit at a time, one per accumulator set, with the k-steps of the sets interleaved:
           // consecutive MMAs then belong to 2*kSplit independent accumulation chains (row x set).
 #pragma unroll
-          for (int t0 = 0; t0 < 9; t0 += C::kSplit) {
-            const int nset = (t0 + C::kSplit <= 9) ? C::kSplit : 9 - t0;   // compile-time after unrolling
+          for (int t0 = 0; t0 < TAPS; t0 += C::kSplit) {
+            const int nset = (t0 + C::kSplit <= TAPS) ? C::kSplit : TAPS - t0;   // compile-time after unrolling
             uint64_t da0[C::kSplit], db0[C::kSplit];
 #pragma unroll
             for (int s = 0; s < C::kSplit; ++s) {
               if (s < nset) {
                 const int t = t0 + s;
                 if (p.resident) {
-                  db0[s] = desc_advance(b_desc0, static_cast<uint32_t>(kc * 9 + t) * C::kBBytes);
+                  db0[s] = desc_advance(b_desc0, static_cast<uint32_t>(kc * TAPS + t) * C::kBBytes);
                 } else {
                   int st = bs + s;
                   uint32_t ph = bph;
@@ -203,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
                   db0[s] = desc_advance(b_desc0, static_cast<uint32_t>(st) * C::kBBytes);
                 }
                 // halo row of output row u and tap t: (u + dh + 1); halo column of output column 0: (dw + 1)
-                da0[s] = desc_advance(a_desc0, static_cast<uint32_t>(((p.dh[t] + 1) * kHaloW + p.dw[t] + 1) * 128));
+                da0[s] = desc_advance(a_desc0, static_cast<uint32_t>(((p.dh[t] + 1) * kHaloW + p.dw[t] + 1 + q_halo) * 128));
               }
             }
 #pragma unroll
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
               }
             }
           }
-          umma_commit_p(issue, &a_empty[as]);  // all nine taps of this chunk have been issued
+          umma_commit_p(issue, &a_empty[as]);  // all taps of this chunk have been issued
           if (++as == 2) { as = 0; aph ^= 1u; }
         }
         umma_commit_p(issue, &tfull[acc]);
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     const uint32_t bias_a = smem_u32(bars) + 256;
     const float* scale_g = nullptr;   // AFFINE: read through the read-only cache (see conv_gemm.cu)
     if (p.bias != nullptr) {
-      const int co_cta = static_cast<int>(blockIdx.x % p.num_n_tiles) * BN;
+      const int co_cta = static_cast<int>(blockIdx.x % p.num_n_tiles % p.tiles_per_q) * BN;
       for (int i = et; i < BN; i += kEpiThreads) sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
       if constexpr (AFFINE) scale_g = p.scale + co_cta;
       named_bar_sync(1, kEpiThreads);
@@ -273,7 +283,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       p.fd_tiles_w.divmod(mt, rest, tw);
       p.fd_tiles_h.divmod(rest, img, th);
       const int h0 = th * 2, w0 = tw * kTW;
-      const int co0 = nt * BN;
+      const int q = static_cast<int>(nt) / p.tiles_per_q;      // output phase (0 unless phased)
+      const int co0 = (static_cast<int>(nt) - q * p.tiles_per_q) * BN;
       const int valid_w = (p.W - w0 < kTW) ? (p.W - w0) : kTW;   // columns of this tile inside the image
 
       mbar_wait(&tfull[acc], (it >> 1) & 1);
@@ -355,8 +366,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
           fence_proxy_async_smem();
           named_bar_sync(1, kEpiThreads);
           if (leader) {
-            if (p.accumulate) tma_reduce_add_4d(&p.tmOut, buf, colbase, w0, h0 + u, img);
-            else tma_store_4d(&p.tmOut, buf, colbase, w0, h0 + u, img);
+            if (p.accumulate) tma_reduce_add_4d(&p.tmOut[q], buf, colbase, w0, h0 + u, img);
+            else tma_store_4d(&p.tmOut[q], buf, colbase, w0, h0 + u, img);
             bulk_commit();
           }
           if (p.stats_partial != nullptr && colbase + st_ch < p.ncols) {
@@ -408,35 +419,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   }
 }
 
-template <int BN, bool AFFINE>
+template <int BN, bool AFFINE, int TAPS>
 int launch_t(HaloParams& p, int grid, cudaStream_t stream) {
   using C = HCfg<BN>;
   static DeviceOnce once;
-  UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(conv3x3_halo_kernel<BN, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
-  // weights resident when all 9*kchunks tiles fit next to the two halo slots and one staging buffer
-  const uint32_t w_bytes = static_cast<uint32_t>(9 * p.kchunks) * C::kBBytes;
+  UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(conv3x3_halo_kernel<BN, AFFINE, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
+  // weights resident when all TAPS*kchunks tiles fit next to the two halo slots and one staging buffer
+  const uint32_t w_bytes = static_cast<uint32_t>(TAPS * p.kchunks) * C::kBBytes;
   const uint32_t resident_smem = 2 * kHaloSlot + w_bytes + kStagingBytes + 1024 + 256 + BN * 4;
   p.resident = (resident_smem <= 227 * 1024) ? 1 : 0;
   const uint32_t smem_bytes = p.resident ? resident_smem : C::kSmemBytes;
-  UNETK_CUDA(launch_pdl(conv3x3_halo_kernel<BN, AFFINE>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
+  UNETK_CUDA(launch_pdl(conv3x3_halo_kernel<BN, AFFINE, TAPS>, dim3(grid), dim3(kThreads), smem_bytes, stream, p));
   UNETK_LAUNCHED();
   return 0;
 }
 template <int BN>
-int launch(HaloParams& p, int grid, cudaStream_t stream) {
-  return p.scale != nullptr ? launch_t<BN, true>(p, grid, stream) : launch_t<BN, false>(p, grid, stream);
+int launch(HaloParams& p, int grid, cudaStream_t stream, int taps) {
+  if (taps == 4) return p.scale != nullptr ? launch_t<BN, true, 4>(p, grid, stream) : launch_t<BN, false, 4>(p, grid, stream);
+  return p.scale != nullptr ? launch_t<BN, true, 9>(p, grid, stream) : launch_t<BN, false, 9>(p, grid, stream);
 }
 
 }  // namespace
 
 int conv_stats_sums_launch(const float* partial, int grid, int num_n_tiles, int BN, int C, double* sums,
                            cudaStream_t stream);
+int conv_stats_sums_q_launch(const float* partial, int grid, int tiles_per_q, int q_groups, int BN, int C, double* sums,
+                             cudaStream_t stream);
+
+// the four-phase sub-pixel up-conv (capi.cu upconv_fwd_desc): 2x2 window taps at (-1..0, -1..0) + the phase
+static bool halo_phased(const ConvGemmDesc& d) {
+  if (!(d.taps == 4 && d.q_groups == 4 && d.q_shift == 1 && d.out_step == 2 && d.b_taps == 4 && !d.out_f32)) return false;
+  for (int t = 0; t < 4; ++t)
+    if (d.dh[t] < -1 || d.dh[t] > 0 || d.dw[t] < -1 || d.dw[t] > 0) return false;
+  return d.ncols == 64 || d.ncols == 128;   // an N tile must not straddle two phases' weight rows
+}
 
 bool conv3x3_halo_eligible(const ConvGemmDesc& d) {
-  static int enabled = -1;
+  static int enabled = -1, up = -1;
   if (enabled < 0) { const char* e = getenv("UNETK_HALO_CONV"); enabled = e ? atoi(e) : 1; }
-  return enabled && d.taps == 9 && d.a_step == 1 && d.out_step == 1 && d.q_groups == 1 && d.W >= 128 && d.H >= 2 &&
-         d.ncols <= 128 && d.K >= 8;
+  if (up < 0) { const char* e = getenv("UNETK_HALO_UPCONV"); up = e ? atoi(e) : 1; }
+  if (!(enabled && d.a_step == 1 && d.W >= 128 && d.H >= 2 && d.ncols <= 128 && d.K >= 8)) return false;
+  if (d.taps == 9 && d.out_step == 1 && d.q_groups == 1) return true;
+  return up && halo_phased(d);
 }
 
 // Same contract as conv_gemm_run for the shapes conv3x3_halo_eligible() accepts.
@@ -447,13 +471,16 @@ int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream) {
   p.tiles_h = (d.H + 1) / 2;
   p.tiles_w = (d.W + kTW - 1) / kTW;
   p.num_m_tiles = d.N * p.tiles_h * p.tiles_w;
-  p.num_n_tiles = (d.ncols + BN - 1) / BN;
+  const bool phased = d.q_groups > 1;
+  p.tiles_per_q = (d.ncols + BN - 1) / BN;
+  p.num_n_tiles = p.tiles_per_q * d.q_groups;
+  p.q_shift = d.q_shift;
   p.ncols = d.ncols;
   p.fd_n_tiles = FastDiv(p.num_n_tiles);
   p.fd_tiles_w = FastDiv(p.tiles_w);
   p.fd_tiles_h = FastDiv(p.tiles_h);
   p.kchunks = (d.K + 63) / 64;
-  for (int t = 0; t < 9; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
+  for (int t = 0; t < d.taps; ++t) { p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t]; p.btap[t] = d.btap[t]; }
   p.bias = d.bias;
   p.scale = d.scale;
   p.relu = d.relu;
@@ -482,24 +509,34 @@ int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream) {
     if (int rc = make_tmap_bf16(&p.tmA, d.a, 4, dims, strides, box, es, true)) return rc;
   }
   {
-    uint64_t dims[3] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.ncols), static_cast<uint64_t>(d.b_taps)};
-    uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * (d.b_rows ? d.b_rows : d.ncols)};
+    const uint64_t rows = static_cast<uint64_t>(d.ncols) * d.q_groups;   // phased: weight rows q * ncols + co
+    uint64_t dims[3] = {static_cast<uint64_t>(d.K), rows, static_cast<uint64_t>(d.b_taps)};
+    uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * (d.b_rows ? static_cast<uint64_t>(d.b_rows) : rows)};
     uint32_t box[3] = {64, static_cast<uint32_t>(BN), 1};
     uint32_t es[3] = {1, 1, 1};
     if (int rc = make_tmap_bf16(&p.tmB, d.b, 3, dims, strides, box, es, true)) return rc;
   }
   {
+    // output seen on the grid of GEMM rows: pixel (h, w) of phase q lives at out[(s*h + qy) * Wout + s*w + qx] (s = out_step)
+    const int s = phased ? d.out_step : 1;
+    const int64_t Wout = static_cast<int64_t>(d.W) * s, Hout = static_cast<int64_t>(d.H) * s;
     uint64_t dims[4] = {static_cast<uint64_t>(d.ncols), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
                         static_cast<uint64_t>(d.N)};
-    uint64_t strides[3] = {static_cast<uint64_t>(d.out_ld) * 2, static_cast<uint64_t>(d.out_ld) * 2 * d.W,
-                           static_cast<uint64_t>(d.out_ld) * 2 * d.W * d.H};
+    uint64_t strides[3] = {static_cast<uint64_t>(d.out_ld) * 2 * s, static_cast<uint64_t>(d.out_ld) * 2 * Wout * s,
+                           static_cast<uint64_t>(d.out_ld) * 2 * Wout * Hout};
     uint32_t box[4] = {64, kTW, 1, 1};
     uint32_t es[4] = {1, 1, 1, 1};
-    if (int rc = make_tmap_bf16(&p.tmOut, d.out, 4, dims, strides, box, es, true)) return rc;
+    for (int q = 0; q < d.q_groups; ++q) {
+      const uint8_t* base = static_cast<const uint8_t*>(d.out) + (static_cast<int64_t>(q >> 1) * Wout + (q & 1)) * d.out_ld * 2;
+      if (int rc = make_tmap_bf16(&p.tmOut[q], base, 4, dims, strides, box, es, true)) return rc;
+    }
   }
-  const int rc = (BN == 128) ? launch<128>(p, grid, stream) : launch<64>(p, grid, stream);
+  const int rc = (BN == 128) ? launch<128>(p, grid, stream, d.taps) : launch<64>(p, grid, stream, d.taps);
   if (rc) return rc;
-  if (d.stats_sums != nullptr) return conv_stats_sums_launch(d.stats_partial, grid, p.num_n_tiles, BN, d.ncols, d.stats_sums, stream);
+  if (d.stats_sums != nullptr) {
+    if (phased) return conv_stats_sums_q_launch(d.stats_partial, grid, p.tiles_per_q, d.q_groups, BN, d.ncols, d.stats_sums, stream);
+    return conv_stats_sums_launch(d.stats_partial, grid, p.num_n_tiles, BN, d.ncols, d.stats_sums, stream);
+  }
   return 0;
 }
 

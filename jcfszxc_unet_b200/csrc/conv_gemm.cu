@@ -453,6 +453,14 @@ int conv_stats_sums_launch(const float* partial, int grid, int num_n_tiles, int 
   return 0;
 }
 
+int conv_stats_sums_q_launch(const float* partial, int grid, int tiles_per_q, int q_groups, int BN, int C, double* sums,
+                             cudaStream_t stream) {
+  UNETK_CUDA(launch_pdl(conv_stats_sums_q_kernel, dim3((2 * C + kSum2Lanes - 1) / kSum2Lanes), dim3(kSum2Lanes, kSum2Slices), 0, stream,
+                        partial, grid, tiles_per_q, q_groups, BN, C, sums));
+  UNETK_LAUNCHED();
+  return 0;
+}
+
 bool conv3x3_halo_eligible(const ConvGemmDesc& d);
 int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream);
 bool conv3x3_rows_eligible(const ConvGemmDesc& d);
@@ -606,12 +614,8 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   }
   if (rc) return rc;
   if (d.stats_sums != nullptr) {
-    if (d.q_groups > 1) {
-      UNETK_CUDA(launch_pdl(conv_stats_sums_q_kernel, dim3((2 * d.ncols + kSum2Lanes - 1) / kSum2Lanes), dim3(kSum2Lanes, kSum2Slices),
-                            0, stream, static_cast<const float*>(d.stats_partial), grid, p.tiles_per_q, d.q_groups, BN, d.ncols, d.stats_sums));
-      UNETK_LAUNCHED();
-      return 0;
-    }
+    if (d.q_groups > 1)
+      return conv_stats_sums_q_launch(d.stats_partial, grid, p.tiles_per_q, d.q_groups, BN, d.ncols, d.stats_sums, stream);
     return conv_stats_sums_launch(d.stats_partial, grid, p.num_n_tiles, BN, d.ncols, d.stats_sums, stream);
   }
   return 0;

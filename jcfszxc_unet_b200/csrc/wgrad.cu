@@ -356,6 +356,46 @@ __global__ void wgrad_reduce_upfold_kernel(const float* __restrict__ partial, fl
   }
 }
 
+// The same fold for MANY pixel splits over a small filter (the full-resolution up-conv: 148 splits of a 128 x 64 filter; the
+// kernel above would walk them with 32 blocks of dependent loads: 0.3 ms): a 32 x S block owns 32 (m, n) positions of one
+// 3x3 tap, slice y adds the four sub-filter planes of the splits y, y+S, ... and row 0 adds the S slice sums in order.
+template <int S>
+__global__ void wgrad_reduce_upfold_sliced_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ksplit, int M,
+                                                  int Nn, int64_t sm, int64_t sn, int64_t st, int accumulate, FastDiv fd_n) {
+  __shared__ float red[S][33];
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t plane = static_cast<uint32_t>(M) * static_cast<uint32_t>(Nn);
+  const uint32_t j = blockIdx.x * 32 + threadIdx.x;
+  const int t9 = blockIdx.y, kh = t9 / 3, kw = t9 - kh * 3;
+  int src[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int u = (q >> 1) == 0 ? (kh > 0) : (kh > 1), v = (q & 1) == 0 ? (kw > 0) : (kw > 1);
+    src[q] = q * 4 + u * 2 + v;
+  }
+  float s = 0.f;
+  if (j < plane) {
+    for (int k = threadIdx.y; k < ksplit; k += S) {
+      const float* pk = partial + static_cast<size_t>(k) * 16 * plane + j;
+      // same association as the unsliced kernel is NOT required (each kernel is deterministic by itself)
+      s += (__ldg(pk + src[0] * static_cast<size_t>(plane)) + __ldg(pk + src[1] * static_cast<size_t>(plane))) +
+           (__ldg(pk + src[2] * static_cast<size_t>(plane)) + __ldg(pk + src[3] * static_cast<size_t>(plane)));
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < plane) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < S; ++y) t += red[y][threadIdx.x];
+    uint32_t m, n;
+    fd_n.divmod(j, m, n);
+    float* o = dw + m * sm + n * sn + t9 * st;
+    *o = accumulate ? (*o + t) : t;
+  }
+}
+
 template <int BN>
 int launch(const WgradParams& p, cudaStream_t stream) {
   using C = WCfg<BN>;
@@ -444,6 +484,16 @@ int wgrad_upfold_launch(const float* partial, float* dw, int ksplit, int M, int 
                         int accumulate, cudaStream_t stream) {
   const int64_t plane = static_cast<int64_t>(M) * Nn;
   UNETK_CHECK(plane < (1ll << 31), -1, "wgrad_upfold: M*N too large");
+  const FastDiv fd(static_cast<uint32_t>(Nn));
+  if (ksplit >= 8) {
+    const dim3 grid(static_cast<unsigned>((plane + 31) / 32), 9);
+    if (ksplit >= 64)
+      UNETK_CUDA(launch_pdl(wgrad_reduce_upfold_sliced_kernel<32>, grid, dim3(32, 32), 0, stream, partial, dw, ksplit, M, Nn, sm, sn, st, accumulate, fd));
+    else
+      UNETK_CUDA(launch_pdl(wgrad_reduce_upfold_sliced_kernel<8>, grid, dim3(32, 8), 0, stream, partial, dw, ksplit, M, Nn, sm, sn, st, accumulate, fd));
+    UNETK_LAUNCHED();
+    return 0;
+  }
   int blocks = static_cast<int>((plane + 255) / 256);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   UNETK_CUDA(launch_pdl(wgrad_reduce_upfold_kernel, dim3(blocks), dim3(256), 0, stream, partial, dw, ksplit, M, Nn, sm, sn, st,

@@ -400,6 +400,8 @@ UPCONV_SHAPES = [
     (1, 3, 130, 64, 64, (0, 64)),     # TW = 128, two column tiles (the second one ragged), sliced output
     (1, 64, 64, 256, 128, (0, 0)),    # BN = 128
     (3, 2, 2, 24, 40, (0, 0)),        # deepest level of a 32 x 32 image; channel counts that are not multiples of 64
+    (1, 4, 128, 256, 128, (0, 0)),    # low-resolution W >= 128: the four phases on the halo kernel (conv3x3_halo.cu, TAPS = 4), BN = 128, weight ring
+    (2, 3, 256, 128, 64, (64, 0)),    # the same with BN = 64, resident weights over two k-chunks, odd H, sliced output
     (1, 6, 20, 72, 40, (0, 0)),       # halo weight-gradient kernel (W >= 16), Cout <= 64 mode: ragged W, ragged channels
     (1, 16, 16, 192, 136, (0, 8)),    # the same, Cout > 64 mode: two m tiles (the second half empty), ragged second n tile
 ]
