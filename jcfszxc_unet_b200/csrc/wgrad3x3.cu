@@ -41,6 +41,11 @@ struct W3Params {
   int stages;       // pipeline depth actually used (<= W3Cfg::kStages)
   int rows2;        // 1 (NT = 64, TH = 1, not paired): filter rows 0 and 1 share one pass (two halo rows of Q, two
                     // accumulators), filter row 2 runs alone: the first operand is read twice instead of three times
+                    // 2: the nine taps split 5 + 4 over two EQUALLY long items that run side by side (g = 0: filter row 0
+                    // + taps 0, 1 of row 1; g = 1: tap 2 of row 1 + filter row 2): the 128 x 576 fp32 gradient does not fit
+                    // one SM's TMEM (512 columns), so two CTAs must sweep the pixels — but in step, on neighbouring SMs,
+                    // so that the second one finds the first operand in L2 (the 1 + 1/2 split re-read it from HBM:
+                    // 3.26 GB of DRAM traffic for 1.61 GB of operands, profiles/r02_ncu_tensor_pipe.txt)
   float* partial;   // [ksplit][9][M][Nn]
   int TH, TW, tiles_h, tiles_w, pix_tiles;
   int m_tiles, n_tiles, ksplit;
@@ -65,6 +70,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   const bool merged = p.paired == 2;
   const uint32_t p_boxes = merged ? 3u : 2u;
   const bool rows2 = p.rows2 != 0;
+  const bool balanced = p.rows2 == 2;
   const uint32_t q_boxes = rows2 ? 2u : static_cast<uint32_t>(C::kQBoxes);
   const uint32_t stage_bytes = p_boxes * kPBoxBytes + q_boxes * p.q_box_bytes;
   const int nstages = p.stages;
@@ -102,7 +108,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   // item -> (n tile, m tile, filter row or row group r, pixel split ks, g).  rows2: the long items (g = 0: filter rows
   // 0 + 1) come first, then the short ones (g = 1: row 2), so that a CTA striding over the items gets one of each
   auto decode = [&](int item, int& nt, int& mt, int& r, int& ks, int& g) {
-    if (rows2) {
+    if (balanced) {   // the two halves of a pixel range on neighbouring CTAs
+      g = item & 1;
+      const int rem = item >> 1, mn = p.m_tiles * p.n_tiles;
+      ks = rem / mn;
+      const int t = rem - ks * mn;
+      mt = t / p.n_tiles;
+      nt = t - mt * p.n_tiles;
+      r = g ? 2 : 0;
+    } else if (rows2) {
       const int mn = p.m_tiles * p.n_tiles, per_g = mn * p.ksplit;
       g = item / per_g;
       const int rem = item - g * per_g;
@@ -129,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
         // paired: r is the filter-row GROUP (0: rows 1|0, 1: row 2) and the X row is the k-block's own row
         int nt, mt, r, ks, g;
         decode(item, nt, mt, r, ks, g);
-        const uint32_t tx = p_boxes * kPBoxBytes + (rows2 ? (g == 0 ? 2u : 1u) : static_cast<uint32_t>(C::kQBoxes)) * p.q_tx_bytes;
+        const uint32_t tx = p_boxes * kPBoxBytes + (rows2 ? ((g == 0 || balanced) ? 2u : 1u) : static_cast<uint32_t>(C::kQBoxes)) * p.q_tx_bytes;
         const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
         const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
         for (int kt = kt0; kt < kt1; ++kt) {
@@ -157,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
             tma_load_4d(sp + b * kPBoxBytes, &p.tmP, &full_bar[stage], mt * 128 + b * 64, w0, h0, img);
           if (rows2) {   // NT == 64: one 64-channel box per halo row; g == 0: rows h0-1 (filter row 0) and h0 (row 1)
             tma_load_4d(sq, &p.tmQ, &full_bar[stage], nt * NT, w0 - 1, h0 + r - 1, img);
-            if (g == 0) tma_load_4d(sq + p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT, w0 - 1, h0, img);
+            if (g == 0 || balanced) tma_load_4d(sq + p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT, w0 - 1, h0, img);
           } else {
 #pragma unroll
             for (int b = 0; b < C::kQBoxes; ++b)
@@ -189,6 +203,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
         int nt_, mt_, r_, ks, g;
         decode(item, nt_, mt_, r_, ks, g);
         const bool two_rows = rows2 && g == 0;
+        // balanced: the second MMA of a k-step takes taps 0, 1 (g = 0: N = 128) or tap 2 (g = 1: N = 64, two pixels in)
+        // of filter row 1 from the second halo row
+        const uint32_t idesc_b = (g == 0) ? make_idesc_bf16(128, 128, true, true) : make_idesc_bf16(128, 64, true, true);
+        const uint32_t shift_b = p.q_box_bytes + ((g == 0) ? 0u : 256u);
         const int kt0 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * ks / p.ksplit);
         const int kt1 = static_cast<int>(static_cast<int64_t>(p.pix_tiles) * (ks + 1) / p.ksplit);
         mbar_wait_p(issue, tempty_bar, (it & 1) ^ 1u);
@@ -214,7 +232,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
                 umma_bf16_p(issue, tmem_base + 192, da, dq, idesc, (first && k == 0) ? 0u : 1u);
               } else {
                 umma_bf16_p(issue, tmem_base, da, dq, idesc, (first && k == 0) ? 0u : 1u);   // no control flow per MMA
-                if (two_rows)   // uniform per item: the second halo row (filter row 1) against the same first operand
+                if (balanced)   // uniform per launch
+                  umma_bf16_p(issue, tmem_base + 192, da, desc_advance(dq, shift_b), idesc_b, (first && k == 0) ? 0u : 1u);
+                else if (two_rows)   // uniform per item: the second halo row (filter row 1) against the same first operand
                   umma_bf16_p(issue, tmem_base + 192, da, desc_advance(dq, p.q_box_bytes), idesc, (first && k == 0) ? 0u : 1u);
               }
             } else {
@@ -242,9 +262,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int a = 0; a < ((merged || (rows2 && g == 0)) ? 2 : 1); ++a) {
+      for (int a = 0; a < ((merged || balanced || (rows2 && g == 0)) ? 2 : 1); ++a) {
         // merged: accumulator 0 = row group 0, accumulator 1 = group 1; rows2 (g == 0): accumulator a = filter row a
-        int r = merged ? a : (rows2 && g == 0 ? a : r_item);
+        // balanced: accumulator 0 = filter row 0 (g = 0) or 2 (g = 1), accumulator 1 = taps [0, 2) / [2, 3) of filter row 1
+        int r = merged ? a : (balanced ? (a ? 1 : r_item) : (rows2 && g == 0 ? a : r_item));
+        const int s_lo = (balanced && a == 1 && g == 1) ? 2 : 0, s_hi = (balanced && a == 1 && g == 0) ? 2 : 3;
         int m = mt * 128 + row;
         if (p.paired) {
           // accumulator rows 0-63 = first dY row of the pair, 64-127 = second: group 0 -> filter rows (1, 0), group 1 -> (2, -)
@@ -254,12 +276,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
           else { r = 2; if (half) m = p.M; }   // second half of group 1 repeats filter row 1: not stored
         }
 #pragma unroll 1
-        for (int s = 0; s < 3; ++s) {
+        for (int s = s_lo; s < s_hi; ++s) {
           float* dst = p.partial + ((static_cast<size_t>(ks) * 9 + r * 3 + s) * p.M + m) * p.Nn + nt * NT;
 #pragma unroll 1
           for (int c = 0; c < NT / 32; ++c) {
             uint32_t v[32];
-            tmem_ld32(taddr + a * 192 + s * NT + c * 32, v);
+            tmem_ld32(taddr + a * 192 + (s - s_lo) * NT + c * 32, v);
             tmem_ld_wait();
             if (m < p.M) {
 #pragma unroll
@@ -319,8 +341,8 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
   // rows2: more than 64 rows against <= 64 columns (swapped 128 -> 64, UNet++'s 96..192 -> 32): same fabric bound,
   // the first operand (16 KB per k-block) was read once per filter row; filter rows 0 and 1 now share it
   static int rows2_env = -1;
-  if (rows2_env < 0) { const char* e = getenv("UNETK_WGRAD3_ROWS2"); rows2_env = e ? atoi(e) : 1; }
-  pl->rows2 = (rows2_env && !pl->paired && pl->NT == 64 && pl->TW == 64 && pl->TH == 1) ? 1 : 0;
+  if (rows2_env < 0) { const char* e = getenv("UNETK_WGRAD3_ROWS2"); rows2_env = e ? atoi(e) : 2; }
+  pl->rows2 = (rows2_env && !pl->paired && pl->NT == 64 && pl->TW == 64 && pl->TH == 1) ? (rows2_env == 1 ? 1 : 2) : 0;
   const int stages = pl->NT == 128 ? 5 : ((pl->paired == 2 || pl->rows2) ? 6 : 7);
   pl->stages = stages;
   const uint32_t stage = (pl->paired == 2 ? 3 : 2) * kPBoxBytes + (pl->rows2 ? 2 : pl->NT / 64) * pl->q_box_bytes;

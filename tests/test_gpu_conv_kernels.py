@@ -188,6 +188,7 @@ WGRAD_EXTRA = [
     (1, 16, 32, 128, 64, (0, 0), (0, 0)),
     (2, 9, 20, 136, 40, (8, 0), (0, 24)),
     (1, 4, 128, 256, 64, (0, 0), (64, 0)),
+    (1, 3, 70, 96, 32, (0, 0), (0, 0)),      # UNet++'s 96 -> 32: the 5 + 4 tap split with half-empty N atoms, ragged W
 ]
 
 
