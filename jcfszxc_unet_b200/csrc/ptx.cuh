@@ -104,6 +104,28 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// ---- thread-block clusters (CTA pairs): multicast loads, cluster-wide barrier
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of every CTA of the cluster (release / acquire: barrier initialisations and shared-memory writes before
+// the barrier are visible to the peers after it)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+// The box lands at the SAME shared-memory offset in every CTA of `cta_mask`, and every destination CTA's mbarrier at
+// the offset of `bar` receives the complete_tx for the bytes written into that CTA.
+__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                               int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+
 // Pull a box into L2 only (no smem, no barrier): extends the bytes in flight beyond what the smem ring holds.
 __device__ __forceinline__ void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
@@ -211,6 +233,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
+// the same arrive delivered to the mbarrier at this offset in EVERY CTA of `cta_mask` (a shared-memory slot that a peer's
+// multicast load also fills is free only when the MMAs of all CTAs that read it have retired)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
 // Barrier wait for the convergent issue loop: the issuing lane polls, the warp re-converges behind it (a spin loop
 // run by all lanes may leave the warp diverged, which sends ptxas back to the per-MMA waterfall).
 __device__ __forceinline__ void mbar_wait_p(bool issue, uint64_t* bar, uint32_t parity) {
@@ -219,6 +249,9 @@ __device__ __forceinline__ void mbar_wait_p(bool issue, uint64_t* bar, uint32_t 
 }
 __device__ __forceinline__ void umma_commit_p(bool issue, uint64_t* bar) {
   if (issue) umma_commit(bar);
+}
+__device__ __forceinline__ void umma_commit_mc_p(bool issue, uint64_t* bar, uint16_t cta_mask) {
+  if (issue) umma_commit_mc(bar, cta_mask);
 }
 // 32 lanes x 32 columns of fp32: thread i of the warp receives lane (base_lane+i), columns c..c+31.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {

@@ -18,6 +18,7 @@
 #include "host_common.cuh"
 
 #include <cstdlib>
+#include <mutex>
 #include "ptx.cuh"
 #include "wgrad.cuh"
 
@@ -61,7 +62,13 @@ struct W3Cfg {
   static constexpr uint32_t kTmemCols = 512;   // NT = 64 merged mode: two 192-column accumulators
 };
 
-template <int NT>
+// PAIR (NT = 64, rows2 == 2 only): launched as clusters of two CTAs = the two halves (g = 0 / 1) of a pixel range.  What
+// both halves read — the first operand's tile and the middle halo row — is fetched from L2 ONCE per pair and multicast
+// into both CTAs' shared memory (each CTA loads one of the two 64-channel boxes; the halo row alternates), which takes
+// the L2 -> SM traffic per CTA from 32.5 to ~20.5 KB per k-block: the kernel was bound by that fabric (4.36 GB at
+// 7.7 TB/s, 57 % tensor-pipe activity, profiles/r02_ncu_wgrad_pair.txt), not by HBM.  A stage is free again when the MMAs
+// of BOTH CTAs have retired (multicast commit onto both empty barriers).
+template <int NT, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_constant__ W3Params p) {
   using C = W3Cfg<NT>;
   extern __shared__ uint8_t smem_raw[];
@@ -89,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     tma_prefetch_desc(&p.tmQ);
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], PAIR ? 2 : 1);
     }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, 4);
@@ -100,6 +107,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  uint32_t rank = 0;
+  if constexpr (PAIR) {
+    rank = cluster_ctarank();   // == blockIdx.x & 1 == g of every item of this CTA (even grid, balanced decode)
+    cluster_sync_all();         // the peer's barriers exist before anything of ours can land on them
+  }
   // programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on global memory
   pdl_trigger();
   pdl_wait();
@@ -163,6 +175,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
 #pragma unroll
             for (int b = 0; b < C::kQBoxes; ++b)
               tma_load_4d(sq + b * p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT + b * 64, w0 - 1, h0, img);
+            if (++stage == nstages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          if constexpr (PAIR) {
+            // tx (above) counts what LANDS in this CTA: both boxes of the first operand (one from the peer), the private
+            // halo row and the shared one (from whichever CTA's turn it is)
+            tma_load_4d_mc(sp + rank * kPBoxBytes, &p.tmP, &full_bar[stage], mt * 128 + static_cast<int>(rank) * 64, w0, h0, img, 0x3);
+            tma_load_4d(sq, &p.tmQ, &full_bar[stage], nt * NT, w0 - 1, h0 + r - 1, img);
+            if (((static_cast<uint32_t>(kt) ^ rank) & 1u) == 0)
+              tma_load_4d_mc(sq + p.q_box_bytes, &p.tmQ, &full_bar[stage], nt * NT, w0 - 1, h0, img, 0x3);
             if (++stage == nstages) { stage = 0; phase ^= 1u; }
             continue;
           }
@@ -245,7 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
               }
             }
           }
-          umma_commit_p(issue, &empty_bar[stage]);
+          if constexpr (PAIR) umma_commit_mc_p(issue, &empty_bar[stage], 0x3);   // frees the slot in BOTH CTAs
+          else umma_commit_p(issue, &empty_bar[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
         umma_commit_p(issue, tfull_bar);
@@ -309,6 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_cons
     tc_fence_after();
     tmem_dealloc<C::kTmemCols>(tmem_base);
   }
+  // a CTA's shared memory (barriers the peer's commits arrive on, slots its loads write) must outlive the peer's work
+  if constexpr (PAIR) cluster_sync_all();
 }
 
 struct W3Plan {
@@ -382,10 +407,63 @@ bool make_plan(int N, int H, int W, int M, int Nn, W3Plan* pl) {
 template <int NT>
 int launch(const W3Params& p, const W3Plan& pl, cudaStream_t stream) {
   static DeviceOnce once;
-  UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(wgrad3x3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
+  UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(wgrad3x3_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
   const int items = (pl.paired == 2 ? pl.n_tiles : (pl.paired ? 2 * pl.n_tiles : (pl.rows2 ? 2 : 3) * pl.m_tiles * pl.n_tiles)) * pl.ksplit;
   const int grid = items < num_sms() ? items : num_sms();
-  UNETK_CUDA(launch_pdl(wgrad3x3_kernel<NT>, dim3(grid), dim3(kThreads), pl.smem_bytes, stream, p));
+  UNETK_CUDA(launch_pdl(wgrad3x3_kernel<NT, false>, dim3(grid), dim3(kThreads), pl.smem_bytes, stream, p));
+  UNETK_LAUNCHED();
+  return 0;
+}
+
+// CTA pairs the device can keep resident with this kernel's shared memory (GPCs with an odd number of free SMs leave one
+// out): cached per device
+int max_pairs(uint32_t smem_bytes) {
+  static std::mutex mu;
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cached[dev & 63] == 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * 148);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, wgrad3x3_kernel<64, true>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
+    cached[dev & 63] = n;
+  }
+  return cached[dev & 63];
+}
+
+// rows2 == 2 as clusters of two CTAs (the g = 0 / g = 1 halves of a pixel range) with multicast loads; > 0: not launched
+int launch_pair(const W3Params& p, const W3Plan& pl, cudaStream_t stream) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("UNETK_WGRAD3_CLUSTER"); env = e ? atoi(e) : 1; }
+  if (!env) return 1;
+  static DeviceOnce once;
+  UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(wgrad3x3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
+  const int pairs_fit = max_pairs(pl.smem_bytes);
+  if (pairs_fit <= 0) return 1;
+  const int pair_items = pl.m_tiles * pl.n_tiles * pl.ksplit;
+  int pairs = num_sms() / 2;
+  if (pairs > pairs_fit) pairs = pairs_fit;
+  if (pairs > pair_items) pairs = pair_items;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  UNETK_CUDA(cudaLaunchKernelEx(&cfg, wgrad3x3_kernel<64, true>, p));
   UNETK_LAUNCHED();
   return 0;
 }
@@ -438,7 +516,9 @@ int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, flo
     if (int rc = make_tmap_bf16(&p.tmP2, dy, 4, dims, strides, box, es, true)) return rc;
   }
   if (int rc = mk(&p.tmQ, x, x_ld, Nn, 2)) return rc;
-  int rc = (pl.NT == 128) ? launch<128>(p, pl, stream) : launch<64>(p, pl, stream);
+  int rc = 1;
+  if (pl.rows2 == 2) rc = launch_pair(p, pl, stream);
+  if (rc > 0) rc = (pl.NT == 128) ? launch<128>(p, pl, stream) : launch<64>(p, pl, stream);
   if (rc) return rc;
   if (flip)   // rows are input channels (stride 9), columns output channels (stride Cin*9), taps reversed
     return wgrad_reduce_launch(p.partial, dw + 8, pl.ksplit, 9, M, Nn, 9, static_cast<int64_t>(M) * 9, -1, accumulate, stream);

@@ -36,7 +36,19 @@ def main():
     sums = torch.zeros(2 * max(cin, cout), dtype=torch.float64, device=dev)
     ws = torch.empty(lib.unetk_conv_wgrad_workspace(n, s, s, cin, cout, k * k), dtype=torch.uint8, device=dev)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # sub-pixel up-conv (cin -> cout, --s = the LOW-resolution size; y / dy are 2s x 2s)
+    up = a.what.startswith("upconv")
+    if up:
+        w3 = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * 0.05
+        w_up, w_up_t = ops.pack_upconv_weight(w3)
+        y2 = torch.empty(n, 2 * s, 2 * s, cout, device=dev, dtype=torch.bfloat16)
+        dy2 = torch.randn(n, 2 * s, 2 * s, cout, device=dev, generator=g).bfloat16()
+        dw3 = torch.empty(cout, cin, 3, 3, device=dev)
+        ws_up = torch.empty(lib.unetk_upconv_wgrad_workspace(n, s, s, cin, cout), dtype=torch.uint8, device=dev)
     fn = {
+        "upconv_fwd": lambda: ops.upconv_fwd(x, w_up, None, y2, partial, sums),
+        "upconv_dgrad": lambda: ops.upconv_dgrad(dy2, w_up_t, dx),
+        "upconv_wgrad": lambda: ops.upconv_wgrad(x, dy2, dw3, ws=ws_up),
         "conv1x1_fwd_stats": lambda: ops.conv_fwd_stats(x, w_ab, None, y, partial, sums, 1, 1),
         "conv1x1_fwd": lambda: ops.conv_fwd(x, w_ab, None, y, 1),
         "conv1x1_dgrad": lambda: ops.conv_dgrad(dy, w_ba, dx, 1),
