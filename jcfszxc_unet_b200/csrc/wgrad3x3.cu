@@ -65,9 +65,9 @@ struct W3Cfg {
 // PAIR (NT = 64, rows2 == 2 only): launched as clusters of two CTAs = the two halves (g = 0 / 1) of a pixel range.  What
 // both halves read — the first operand's tile and the middle halo row — is fetched from L2 ONCE per pair and multicast
 // into both CTAs' shared memory (each CTA loads one of the two 64-channel boxes; the halo row alternates), which takes
-// the L2 -> SM traffic per CTA from 32.5 to ~20.5 KB per k-block: the kernel was bound by that fabric (4.36 GB at
-// 7.7 TB/s, 57 % tensor-pipe activity, profiles/r02_ncu_wgrad_pair.txt), not by HBM.  A stage is free again when the MMAs
-// of BOTH CTAs have retired (multicast commit onto both empty barriers).
+// the L2 reads per CTA from 32.5 to ~20.5 KB per k-block (measured: L2 traffic 5.5 -> 4.4 GB per launch, time unchanged,
+// profiles/r02_ncu_wgrad_pair.txt: the limit is shared-memory bandwidth, see launch_pair).  A stage is free again when the
+// MMAs of BOTH CTAs have retired (multicast commit onto both empty barriers).
 template <int NT, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_constant__ W3Params p) {
   using C = W3Cfg<NT>;
@@ -443,7 +443,10 @@ int max_pairs(uint32_t smem_bytes) {
 // rows2 == 2 as clusters of two CTAs (the g = 0 / g = 1 halves of a pixel range) with multicast loads; > 0: not launched
 int launch_pair(const W3Params& p, const W3Plan& pl, cudaStream_t stream) {
   static int env = -1;
-  if (env < 0) { const char* e = getenv("UNETK_WGRAD3_CLUSTER"); env = e ? atoi(e) : 1; }
+  // Off by default: measured neutral (0.571 -> 0.562 ms on 128 -> 64 @512^2, L2 traffic 5.5 -> 4.4 GB, tensor pipe 57 % either
+  // way, profiles/r02_ncu_wgrad_pair.txt) — the kernel is bound by shared-memory bandwidth (MMA operand reads + TMA fills,
+  // ~166 B/clk wanted of ~128), which a multicast does not lower: every CTA still receives all its bytes.
+  if (env < 0) { const char* e = getenv("UNETK_WGRAD3_CLUSTER"); env = e ? atoi(e) : 0; }
   if (!env) return 1;
   static DeviceOnce once;
   UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(wgrad3x3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));

@@ -505,3 +505,33 @@ def test_upconv3x3_subpixel(n, h, w, cin, cout, ypad):
     dw2 = dw.clone()
     ops.upconv_wgrad(x, dy, dw2, accumulate=True)
     assert (dw2 - 2 * dw).abs().max().item() <= 1e-5 * dw.abs().max().item()
+
+
+def test_conv3x3_wgrad_cta_pairs_subprocess():
+    """The rows2 weight gradient launched as clusters of two CTAs with TMA-multicast operands (UNETK_WGRAD3_CLUSTER=1, read
+    once per process => a child process): same results as the default launch on the three shapes that take the 5 + 4 tap
+    split (cluster barrier, multicast loads, multicast commit onto both CTAs' empty barriers)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import torch, sys
+sys.path.insert(0, %r)
+from jcfszxc_unet_b200 import ops
+dev = torch.device("cuda:0")
+for (n, h, w, cin, cout) in [(1, 4, 128, 256, 64), (1, 3, 70, 96, 32), (2, 64, 512, 128, 64)]:
+    g = torch.Generator(device=dev).manual_seed(cin + cout)
+    x = torch.randn(n, h, w, cin, device=dev, generator=g).bfloat16()
+    dy = torch.randn(n, h, w, cout, device=dev, generator=g).bfloat16()
+    dw = torch.full((cout, cin, 3, 3), float("nan"), device=dev)
+    ops.conv_wgrad(x, dy, dw, 3)
+    ref = torch.nn.grad.conv2d_weight(x.double().permute(0, 3, 1, 2), (cout, cin, 3, 3), dy.double().permute(0, 3, 1, 2), padding=1)
+    err = (dw.double() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), (n, h, w, cin, cout, err)
+print("pairs ok")
+''' % root
+    env = dict(os.environ, UNETK_WGRAD3_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "pairs ok" in r.stdout, r.stdout + r.stderr
