@@ -279,7 +279,9 @@ bool make_plan(int N, int H, int W, int M, int Nn, WUPlan* pl) {
   const int base = (pl->NT == 128 ? 4 : 2) * pl->m_tiles * pl->n_tiles;
   const int cap = pl->pix_tiles / 8 > 0 ? pl->pix_tiles / 8 : 1;
   if (base < 12) {
-    int ks = (2 * num_sms()) / base;
+    // one item per SM (the items are equally long): half the partials of the "~2 items per SM" rule of wgrad3x3.cu, and
+    // the fold-reduce over them was 20 % of the call (profiles/r02_ncu_upconv.txt)
+    int ks = num_sms() / base;
     if (ks > cap) ks = cap;
     pl->ksplit = ks < 1 ? 1 : ks;
     return true;
