@@ -4,8 +4,8 @@
 //   G[q][u][v][ci][co] = sum_{n,i,j} X[n, i, j, ci] * dYq[n, i - (qy-1+u), j - (qx-1+v), co],   dYq[ii, jj] = dY[2 ii + qy, 2 jj + qx]
 //
 // with the pixel index as the reduction dimension (both operands MN-major, as in wgrad3x3.cu).  The per-tap kernel
-// (wgrad.cu) loads a fresh X and dY tile for every tap: 96 B/clk per SM through the L2 -> SM fabric, which delivers ~40-60
-// (230-760 TFLOP/s on the four up-convs of AttentionUNet, profiles/r02_*).  Here one work item owns all FOUR taps of one
+// (wgrad.cu) loads a fresh X and dY tile for every tap and issues one MMA per pair of tiles: operand reads and TMA fills want
+// far more than the ~128 B/clk of shared memory (230-760 TFLOP/s on AttentionUNet, profiles/r02_*).  Here one work item owns all FOUR taps of one
 // phase: per 64-pixel k-block it loads
 //   P: the X tile                       box (64 ch, TW, TH)           -> [64 px][64 ch]  x 2 (M = 128 input channels)
 //   Q: ONE halo tile of the phase view  box (64 ch, TW+1, TH+1), element stride 2 over dY, starting at phase pixel
