@@ -235,6 +235,14 @@ int unetk_bn_bwd_apply(const void* raw, int64_t raw_ld, const void* g1, int64_t 
                        const float* invstd, const double* sums, double count, float* dgamma, float* dbeta,
                        int accumulate, float* coef, float* dconv_bias, void* draw, int64_t draw_ld,
                        int draw_accumulate, int N, int H, int W, int C, int relu, void* stream);
+/* unetk_bn_bwd_apply for a unit whose output was relu(bn(raw)) + res (Recurrent_block / RRCNN_block, unet_parts.py:125-146):
+ * the same pass also delivers d(res) = g1 into dres (dres_accumulate != 0: dres += g1, one bf16 rounding), instead of a
+ * separate add pass over g1.  No fused pool. */
+int unetk_bn_bwd_apply_res(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, const double* sums, double count,
+                           float* dgamma, float* dbeta, int accumulate, float* coef, float* dconv_bias, void* draw,
+                           int64_t draw_ld, int draw_accumulate, void* dres, int64_t dres_ld, int dres_accumulate, int N,
+                           int H, int W, int C, int relu, void* stream);
 /* The per-channel part of unetk_bn_bwd_apply alone: dgamma/dbeta and coef = [K0[C] | K1[C]] with
  * d(raw) = scale*g + K1*raw + K0 (used by the attention gate's fused backward; C >= 1). */
 int unetk_bn_bwd_coef(const double* sums, int C, double count, const float* scale, const float* mean,

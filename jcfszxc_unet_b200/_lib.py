@@ -71,6 +71,8 @@ SIGNATURES = {
     "unetk_bn_bwd_reduce": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "unetk_bn_bwd_apply": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _vp, C.c_double, _fp, _fp, _i,
                                 _fp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "unetk_bn_bwd_apply_res": (_i, [_vp, _i64, _vp, _i64, _fp, _fp, _fp, _fp, _vp, C.c_double, _fp, _fp, _i, _fp, _fp, _vp, _i64, _i,
+                               _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "unetk_bn_bwd_coef": (_i, [_vp, _i, C.c_double, _fp, _fp, _fp, _fp, _fp, _i, _fp, _fp, _vp]),
     "unetk_maxpool2x2_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
     "unetk_maxpool2x2_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),

@@ -469,6 +469,17 @@ int unetk_bn_bwd_apply(const void* raw, int64_t raw_ld, const void* g1, int64_t 
   return bn_bwd_apply_run(raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, sums, count, dgamma, dbeta,
                           accumulate, coef, dconv_bias, draw, draw_ld, draw_accumulate, N, H, W, C, relu, S(stream));
 }
+int unetk_bn_bwd_apply_res(const void* raw, int64_t raw_ld, const void* g1, int64_t g1_ld, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, const double* sums, double count,
+                           float* dgamma, float* dbeta, int accumulate, float* coef, float* dconv_bias, void* draw,
+                           int64_t draw_ld, int draw_accumulate, void* dres, int64_t dres_ld, int dres_accumulate, int N,
+                           int H, int W, int C, int relu, void* stream) {
+  UNETK_CHECK(raw && g1 && scale && shift && mean && invstd && sums && coef && draw && dres && count > 0, -1,
+              "bn_bwd_apply_res: bad arguments");
+  return bn_bwd_apply_run(raw, raw_ld, g1, g1_ld, nullptr, 0, scale, shift, mean, invstd, sums, count, dgamma, dbeta,
+                          accumulate, coef, dconv_bias, draw, draw_ld, draw_accumulate, N, H, W, C, relu, S(stream), dres,
+                          dres_ld, dres_accumulate);
+}
 int unetk_bn_bwd_coef(const double* sums, int C, double count, const float* scale, const float* mean,
                       const float* invstd, float* dgamma, float* dbeta, int accumulate, float* coef, float* dconv_bias,
                       void* stream) {

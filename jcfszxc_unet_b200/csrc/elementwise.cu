@@ -658,10 +658,13 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int C, d
 
 // ACC: draw += (bf16 read-modify-write) instead of draw = ; used when `draw` is the gradient of a tensor that has
 // other consumers (pre-activation BatchNorm of ResidualConv, unet_parts.py:458-459).
-template <bool POOL, bool ACC>
+// RESG: the unit's output was relu(bn(raw)) + res (Recurrent_block's x + x1, RRCNN_block's residual, unet_parts.py:125-146):
+// d(res) = the incoming gradient g1 itself, written (1) or accumulated (2) into `dres` from this pass instead of a separate
+// add pass that reads g1 again (R2UNet: 45 such passes, 2.2 ms per step).
+template <bool POOL, bool ACC, int RESG>
 __global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(const BnBwdArgs A, const float* __restrict__ coef, __nv_bfloat16* __restrict__ draw,
-                    int64_t draw_ld) {
+                    int64_t draw_ld, __nv_bfloat16* __restrict__ dres, int64_t dres_ld) {
   pdl_trigger();
   pdl_wait();
   Lanes L(A.C);
@@ -685,6 +688,20 @@ bn_bwd_apply_kernel(const BnBwdArgs A, const float* __restrict__ coef, __nv_bflo
       for (int j = 0; j < 8; ++j) o[j] = old[j] + bf16_round(o[j]);
     }
     stg16(dst, pack8(o));
+    if constexpr (RESG != 0) {
+      const uint4 ug = ldg16(A.g1 + pix * A.g1_ld + g * 8);   // loaded by the walk a moment ago: an L1 hit
+      __nv_bfloat16* rd = dres + pix * dres_ld + g * 8;
+      if constexpr (RESG == 2) {
+        float a[8], b[8];
+        unpack8(*reinterpret_cast<const uint4*>(rd), a);
+        unpack8(ug, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += b[j];
+        stg16(rd, pack8(a));
+      } else {
+        stg16(rd, ug);
+      }
+    }
   });
 }
 
@@ -937,7 +954,9 @@ int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1
                      const float* scale, const float* shift, const float* mean, const float* invstd,
                      const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
                      float* dconv_bias, void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C,
-                     int relu, cudaStream_t s) {
+                     int relu, cudaStream_t s, void* dres, int64_t dres_ld, int dres_accumulate) {
+  UNETK_CHECK(dres == nullptr || (gp == nullptr && g1 != nullptr && dres_ld % 8 == 0), -1,
+              "bn_bwd_apply: the residual gradient needs g1, no fused pool and a pixel stride that is a multiple of 8");
   BnBwdArgs A;
   if (int rc = bn_bwd_args(&A, raw, raw_ld, g1, g1_ld, gp, gp_ld, scale, shift, mean, invstd, N, H, W, C, relu)) return rc;
   const bool pool = gp != nullptr;
@@ -947,12 +966,20 @@ int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1
   UNETK_LAUNCHED();
   const int grid = bwd_grid(units, C);
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(draw);
+  __nv_bfloat16* rg = static_cast<__nv_bfloat16*>(dres);
+  const int64_t z = 0;
   if (pool) {
-    if (draw_accumulate) UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<true, true>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld));
-    else UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<true, false>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld));
+    if (draw_accumulate) UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<true, true, 0>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld, rg, z));
+    else UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<true, false, 0>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld, rg, z));
+  } else if (dres == nullptr) {
+    if (draw_accumulate) UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<false, true, 0>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld, rg, z));
+    else UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<false, false, 0>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld, rg, z));
+  } else if (dres_accumulate) {
+    if (draw_accumulate) UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<false, true, 2>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld, rg, dres_ld));
+    else UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<false, false, 2>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld, rg, dres_ld));
   } else {
-    if (draw_accumulate) UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<false, true>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld));
-    else UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<false, false>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld));
+    if (draw_accumulate) UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<false, true, 1>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld, rg, dres_ld));
+    else UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel<false, false, 1>, dim3(grid), dim3(kThreads), 0, s, A, coef, d, draw_ld, rg, dres_ld));
   }
   UNETK_LAUNCHED();
   return 0;

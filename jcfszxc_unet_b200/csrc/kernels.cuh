@@ -68,7 +68,7 @@ int bn_bwd_apply_run(const void* raw, int64_t raw_ld, const void* g1, int64_t g1
                      const float* scale, const float* shift, const float* mean, const float* invstd,
                      const double* sums, double count, float* dgamma, float* dbeta, int accumulate, float* coef,
                      float* dconv_bias, void* draw, int64_t draw_ld, int draw_accumulate, int N, int H, int W, int C,
-                     int relu, cudaStream_t s);
+                     int relu, cudaStream_t s, void* dres = nullptr, int64_t dres_ld = 0, int dres_accumulate = 0);
 // loss.cu
 size_t head_partial_floats(int64_t npix, int C);
 int head_loss_fwd_run(const void* x, int64_t ld, const float* w, const float* bias, const float* labels, float* logits,

@@ -535,9 +535,13 @@ class ConvBNReLU:
                 count = P.sync_sums(P.sums[: 2 * self.cout], count)
             # the bias of a conv in front of a train-mode BatchNorm has an identically zero gradient: written by the
             # BN backward's per-channel kernel instead of a column-sum pass over d(raw)
+            # out = relu(bn(raw)) + res: d(res) = g1 leaves this pass too (UNETK_FUSE_RES_GRAD=0: a separate add pass)
+            res_fused = (not self._res_aliases_out() and gp is None
+                         and os.environ.get("UNETK_FUSE_RES_GRAD", "1") != "0")
             ops.bn_bwd_apply(self.raw.t, g1, gp, sc, sh, mu, iv, P.sums, count, self.dgamma, self.dbeta, P.coef,
-                             self.raw.g, self.relu, accumulate=self.acc_bn, dconv_bias=self.dbias)
-            if not self._res_aliases_out():
+                             self.raw.g, self.relu, accumulate=self.acc_bn, dconv_bias=self.dbias,
+                             dres=self.res.g if res_fused else None, dres_accumulate=self.acc_res)
+            if not self._res_aliases_out() and not res_fused:
                 ops.add_n(self.res.g, [g1], accumulate=self.acc_res)
         dy = self.raw.g
         with P.wgrad_stream():

@@ -384,9 +384,20 @@ def bn_bwd_reduce(raw, g1, gp, scale, shift, mean, invstd, partial, sums, relu=T
 
 
 def bn_bwd_apply(raw, g1, gp, scale, shift, mean, invstd, sums, count, dgamma, dbeta, coef, draw, relu=True,
-                 accumulate=False, draw_accumulate=False, dconv_bias=None):
+                 accumulate=False, draw_accumulate=False, dconv_bias=None, dres=None, dres_accumulate=False):
+    """dres (optional, no fused pool): the gradient of the residual input of `out = relu(bn(raw)) + res` — g1 itself —
+    written (or accumulated) by the same pass."""
     n, h, w, c = raw.shape
     rp, rld = nhwc(raw)
+    if dres is not None:
+        assert gp is None and g1 is not None and dres.shape == raw.shape
+        g1p, g1ld = nhwc(g1)
+        dp, dld = nhwc(draw)
+        sp, sld = nhwc(dres)
+        _lib.call("unetk_bn_bwd_apply_res", rp, rld, g1p, g1ld, _f32(scale), _f32(shift), _f32(mean), _f32(invstd),
+                  sums.data_ptr(), float(count), _f32(dgamma), _f32(dbeta), int(accumulate), _f32(coef), _f32(dconv_bias),
+                  dp, dld, int(draw_accumulate), sp, sld, int(dres_accumulate), n, h, w, c, int(relu), _stream())
+        return
     g1p, g1ld = nhwc(g1) if g1 is not None else (None, 0)
     gpp, gpld = nhwc(gp) if gp is not None else (None, 0)
     dp, dld = nhwc(draw)

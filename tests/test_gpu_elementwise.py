@@ -189,6 +189,48 @@ def test_bn_relu_backward(n, h, w, c, pool, skip):
     assert torch.allclose(dbeta, bt.grad, rtol=2e-3, atol=2e-3 * bt.grad.abs().max().item())
 
 
+@pytest.mark.parametrize("n,h,w,c,pad", [(2, 16, 24, 64, 0), (1, 9, 7, 40, 24), (1, 33, 65, 8, 0)])
+def test_bn_backward_with_residual_gradient(n, h, w, c, pad):
+    """out = relu(bn(raw)) + res (Recurrent_block's x + x1, unet_parts.py:125-132): d(res) = the incoming gradient, delivered by
+    the BatchNorm backward's apply pass (write and accumulate, channel-sliced destination) — bit-identical with the separate
+    add pass it replaces, d(raw) / dgamma / dbeta bit-identical with the plain pass."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(23 + c)
+    raw = torch.randn(n, h, w, c, device=DEV, generator=g).bfloat16()
+    gamma = torch.rand(c, device=DEV, generator=g) + 0.5
+    beta = torch.randn(c, device=DEV, generator=g) * 0.3
+    partial, sums = _scratch(ops, n * h * w, c)
+    stat = torch.zeros(4, c, device=DEV)
+    ops.bn_stats(raw, partial, sums)
+    ops.bn_finalize(sums, n * h * w, gamma, beta, 1e-5, 0.1, None, None, None, stat[0], stat[1], stat[2], stat[3])
+    g1 = torch.randn(n, h, w, c, device=DEV, generator=g).bfloat16()
+    coef = torch.zeros(2 * c, device=DEV)
+
+    def run(dres, acc):
+        dgamma, dbeta = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+        draw = torch.empty_like(raw)
+        ops.bn_bwd_reduce(raw, g1, None, stat[0], stat[1], stat[2], stat[3], partial, sums, True)
+        ops.bn_bwd_apply(raw, g1, None, stat[0], stat[1], stat[2], stat[3], sums, n * h * w, dgamma, dbeta, coef, draw, True,
+                         dres=dres, dres_accumulate=acc)
+        return draw, dgamma, dbeta
+
+    plain = run(None, False)
+    buf = torch.full((n, h, w, c + pad), 3.0, device=DEV, dtype=torch.bfloat16)
+    view = buf[..., pad:]
+    fused = run(view, False)
+    for a, b in zip(plain, fused):
+        assert torch.equal(a, b)
+    assert torch.equal(view, g1) and (pad == 0 or bool((buf[..., :pad] == 3.0).all()))
+    base = torch.randn(n, h, w, c, device=DEV, generator=g).bfloat16()
+    view.copy_(base)
+    ref = base.clone()
+    ops.add_n(ref, [g1], accumulate=True)
+    fused = run(view, True)
+    for a, b in zip(plain, fused):
+        assert torch.equal(a, b)
+    assert torch.equal(view, ref)
+
+
 @pytest.mark.parametrize("layout", ["nchw", "channels_last"])
 @pytest.mark.parametrize("cout,bias", [(64, False), (32, True)])
 def test_stem_conv(layout, cout, bias):
