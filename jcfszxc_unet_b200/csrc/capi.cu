@@ -240,6 +240,8 @@ static size_t conv_wgrad_workspace_now(int N, int H, int W, int Cin, int Cout, i
     const size_t need3 = wgrad3x3_workspace_bytes(N, H, W, Cout, Cin), need3f = wgrad3x3_workspace_bytes(N, H, W, Cin, Cout);
     if (need3 > need) need = need3;
     if (need3f > need) need = need3f;
+    const size_t need2 = wgrad3x3_2sm_workspace_bytes(N, H, W, Cout, Cin);
+    if (need2 > need) need = need2;
   }
   return need;
 }
@@ -254,6 +256,11 @@ int unetk_conv3x3_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_
   // Cout <= 64 and more input than output channels: swapped operands (the 128 MMA rows carry input channels, the
   // narrow side goes to N where three taps share one MMA), see wgrad3x3_run
   const bool flip = Cout <= 64 && Cin > Cout && Cin >= 96;
+  if (!flip) {
+    // >= 256 output channels: CTA pairs, one M = 256 MMA per tap over both SMs (wgrad3x3_2sm.cu)
+    const int rc2 = wgrad3x3_2sm_run(dy, dy_ld, x, x_ld, dw, accumulate, N, H, W, Cout, Cin, workspace, ws_bytes, S(stream));
+    if (rc2 <= 0) return rc2;
+  }
   const int rc3 = flip ? wgrad3x3_run(x, x_ld, dy, dy_ld, dw, accumulate, N, H, W, Cin, Cout, workspace, ws_bytes, S(stream), 1)
                        : wgrad3x3_run(dy, dy_ld, x, x_ld, dw, accumulate, N, H, W, Cout, Cin, workspace, ws_bytes, S(stream));
   if (rc3 <= 0) return rc3;

@@ -12,6 +12,9 @@ int pack_upconv_weight_run(const float* src, void* dst_fwd, void* dst_dgrad, int
 // wgrad3x3.cu
 size_t wgrad3x3_workspace_bytes(int N, int H, int W, int M, int Nn);
 size_t wgrad_up_workspace_bytes(int N, int H, int W, int Cin, int Cout);
+size_t wgrad3x3_2sm_workspace_bytes(int N, int H, int W, int M, int Nn);
+int wgrad3x3_2sm_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, float* dw, int accumulate, int N, int H,
+                     int W, int M, int Nn, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int wgrad_up_run(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw, int accumulate, int N, int H, int W,
                  int Cin, int Cout, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int wgrad3x3_run(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, float* dw, int accumulate, int N, int H,
