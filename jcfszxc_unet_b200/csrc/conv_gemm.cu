@@ -25,6 +25,7 @@
 #include "reduce2.cuh"
 
 #include <cstdlib>
+#include <mutex>
 
 namespace unetk {
 
@@ -46,23 +47,36 @@ struct Cfg {
   static constexpr uint32_t kTmemCols = (BN == 192) ? 512 : 2 * BN;  // a power of two >= 32 (two BN-wide accumulators)
   static constexpr uint32_t kPipeBytes = kStages * kStageBytes;
   static constexpr uint32_t kSmemBytes = kPipeBytes + 2 * kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+  // PAIR (cta_group::2, BN = 256): a CTA stages its own A tile and HALF of the B tile (the peer holds the other 128 weight
+  // rows): 32 KB per stage instead of 48, six stages in the same shared memory
+  static constexpr uint32_t kPairStageBytes = kABytes + kBBytes / 2;
+  static constexpr int kPairStages = 6;
+  static constexpr uint32_t kPairSmemBytes = kPairStages * kPairStageBytes + 2 * kStagingBytes + 1024 + 256 + BN * 4;
 };
 
 // AFFINE: the eval-mode BatchNorm fold, out = relu?(acc * scale + shift) — its own instantiation, so the training kernels'
 // epilogue (instruction-fetch bound, see below) does not carry the extra code.
-template <int BN, bool F32OUT, bool AFFINE>
+// PAIR (BN = 256 only): launched as clusters of two CTAs that own two neighbouring M tiles of the same N tile and run ONE
+// M = 256 x N = 256 MMA per k-step over both SMs (tcgen05 cta_group::2): every CTA reads its own A slab and its half of B
+// from its own shared memory (64 B/clk instead of 96) and fetches half of the weights.  Protocol as in wgrad3x3_2sm.cu: all
+// TMA bytes are counted on the leader's full barrier, the leader issues and commits onto both CTAs' empty / tfull barriers,
+// both CTAs' epilogue warps arrive on the leader's tempty barrier.
+template <int BN, bool F32OUT, bool AFFINE, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN>;
+  static_assert(!PAIR || (BN == 256 && !F32OUT), "the CTA-pair form exists for BN = 256 bf16 output");
+  constexpr int kStages = PAIR ? C::kPairStages : C::kStages;
+  constexpr uint32_t kStageBytes = PAIR ? C::kPairStageBytes : C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* staging = smem + C::kPipeBytes;  // 2 x 16 KB, 1024-aligned
+  uint8_t* staging = smem + kStages * kStageBytes;  // 2 x 16 KB, 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
   uint64_t* full_bar = bars;                     // [kStages]
-  uint64_t* empty_bar = bars + C::kStages;       // [kStages]
-  uint64_t* tfull_bar = bars + 2 * C::kStages;   // [2]
+  uint64_t* empty_bar = bars + kStages;          // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;      // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -73,19 +87,27 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     if (!F32OUT) tma_prefetch_desc(&p.tmOut[0]);
-    for (int s = 0; s < C::kStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_2sm<C::kTmemCols>(tmem_slot);
+    else tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  uint32_t rank = 0;
+  if constexpr (PAIR) {
+    rank = cluster_ctarank();
+    cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on global memory
@@ -94,21 +116,34 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kblocks = p.taps * p.kchunks;
+  // Tile walk.  Single CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  PAIR: the cluster walks PAIR tiles (two
+  // neighbouring M tiles x one N tile); rank r takes M tile 2*mp + r, which may lie past the end (odd M tile count):
+  // such a tile is all TMA zero fill, its stores and statistics are skipped.
+  const int walk_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int walk_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int walk_end = PAIR ? ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles : num_tiles;
+  auto tile_of = [&](int wt) -> int {
+    if constexpr (!PAIR) return wt;
+    uint32_t mp, nt;
+    p.fd_n_tiles.divmod(static_cast<uint32_t>(wt), mp, nt);
+    return static_cast<int>((2 * mp + rank) * static_cast<uint32_t>(p.num_n_tiles) + nt);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int wt = walk_first; wt < walk_end; wt += walk_step) {
+        const int tile = tile_of(wt);
         uint32_t nt, mt, tw, th, img, rest, q, ntq;
         p.fd_n_tiles.divmod(tile, mt, nt);
         p.fd_tiles_w.divmod(mt, rest, tw);
         p.fd_tiles_h.divmod(rest, img, th);
         p.fd_tiles_per_q.divmod(nt, q, ntq);
         const int h0 = th * p.TH, w0 = tw * p.TW;
-        const int brow = q * p.rows_per_q + ntq * BN;
-        if (p.l2_prefetch > 0) {
+        const int brow = q * p.rows_per_q + ntq * BN + (PAIR ? static_cast<int>(rank) * (BN / 2) : 0);
+        if (!PAIR && p.l2_prefetch > 0) {
           // Streaming layers are latency-bound (the smem ring cannot hold enough bytes in flight to cover an HBM
           // miss): pull the A box of a tile this CTA will reach `l2_prefetch` rounds from now into L2.
           const int ftile = tile + p.l2_prefetch * gridDim.x;
@@ -126,26 +161,34 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const int bt = p.btap[t];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* sa = smem + stage * C::kStageBytes;
+            uint8_t* sa = smem + stage * kStageBytes;
             uint8_t* sb = sa + kABytes;
-            mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-            tma_load_4d(sa, &p.tmA, &full_bar[stage], kc * kTileK, aw, ah, img);
-            tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kTileK, brow, bt);
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            if constexpr (PAIR) {
+              // the bytes of BOTH CTAs are counted on the leader's barrier (the only one the MMA issuer waits on)
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
+              tma_load_4d_2sm(sa, &p.tmA, &full_bar[stage], kc * kTileK, aw, ah, img);
+              tma_load_3d_2sm(sb, &p.tmB, &full_bar[stage], kc * kTileK, brow, bt);
+            } else {
+              mbar_expect_tx(&full_bar[stage], kStageBytes);
+              tma_load_4d(sa, &p.tmA, &full_bar[stage], kc * kTileK, aw, ah, img);
+              tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kTileK, brow, bt);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    {
-      // ------------------------------------------------------------ MMA issuer (warp-convergent, elected lane issues)
+    if (!PAIR || rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (warp-convergent, elected lane issues;
+      // PAIR: the leader CTA issues for both SMs)
       const bool issue = elect_one();
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, false, false);
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kTileM : kTileM, BN, false, false);
       const uint64_t a_desc0 = make_smem_desc(smem_u32(smem), 16, 1024, kLayoutSW128);  // stage 0, k = 0
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int wt = walk_first; wt < walk_end; wt += walk_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait_p(issue, &tempty_bar[acc], acc_phase ^ 1u);
@@ -155,21 +198,28 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           mbar_wait_p(issue, &full_bar[stage], phase);
           tc_fence_after();
           // descriptors are advanced, not rebuilt: the issuing thread spends ~3 instructions per MMA
-          const uint64_t da0 = desc_advance(a_desc0, static_cast<uint32_t>(stage) * C::kStageBytes);
+          const uint64_t da0 = desc_advance(a_desc0, static_cast<uint32_t>(stage) * kStageBytes);
           const uint64_t db0 = desc_advance(da0, kABytes);
-          if (kb == 0) umma_bf16_p(issue, d_tmem, da0, db0, idesc, 0u);
+          if constexpr (PAIR) umma_bf16_2sm_p(issue, d_tmem, da0, db0, idesc, kb == 0 ? 0u : 1u);
+          else if (kb == 0) umma_bf16_p(issue, d_tmem, da0, db0, idesc, 0u);
           else umma_bf16_acc_p(issue, d_tmem, da0, db0, idesc);
           // K tail: the last 64-channel chunk of every tap holds ksteps_last real 16-channel steps (the rest of the
           // tile is TMA zero fill); K = 32 (UNet++'s 32-channel gradients) would otherwise issue 2x the MMAs
           const int ksteps = ((kb + 1) % p.kchunks == 0) ? p.ksteps_last : kTileK / kUmmaK;
 #pragma unroll
           for (int k = 1; k < kTileK / kUmmaK; ++k)
-            if (k < ksteps)
-              umma_bf16_acc_p(issue, d_tmem, desc_advance(da0, k * kUmmaK * 2), desc_advance(db0, k * kUmmaK * 2), idesc);
-          umma_commit_p(issue, &empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            if (k < ksteps) {
+              if constexpr (PAIR) umma_bf16_2sm_p(issue, d_tmem, desc_advance(da0, k * kUmmaK * 2), desc_advance(db0, k * kUmmaK * 2), idesc, 1u);
+              else umma_bf16_acc_p(issue, d_tmem, desc_advance(da0, k * kUmmaK * 2), desc_advance(db0, k * kUmmaK * 2), idesc);
+            }
+          // frees the smem slot (PAIR: in both CTAs) once these MMAs retire
+          if constexpr (PAIR) umma_commit_2sm_mc_p(issue, &empty_bar[stage], 0x3);
+          else umma_commit_p(issue, &empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_p(issue, &tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (PAIR: of both CTAs)
+        if constexpr (PAIR) umma_commit_2sm_mc_p(issue, &tfull_bar[acc], 0x3);
+        else umma_commit_p(issue, &tfull_bar[acc]);
       }
     }
   } else {
@@ -197,12 +247,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // time: one broadcast transaction); the 227 KB of shared memory are full (BN = 256: 4 stages + 2 staging buffers)
     const float* scale_g = nullptr;
     if (!F32OUT && p.bias != nullptr) {
-      const int co_cta = static_cast<int>(blockIdx.x % p.num_n_tiles % p.tiles_per_q) * BN;
+      const int co_cta = static_cast<int>((PAIR ? (blockIdx.x >> 1) : blockIdx.x) % p.num_n_tiles % p.tiles_per_q) * BN;
       for (int i = et; i < BN; i += kEpiThreads) sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
       if constexpr (AFFINE) scale_g = p.scale + co_cta;
       named_bar_sync(1, kEpiThreads);
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int wt = walk_first; wt < walk_end; wt += walk_step, ++it) {
+      const int tile = tile_of(wt);
+      const bool tile_ok = !PAIR || tile < num_tiles;   // PAIR: the second CTA's M tile past the end (odd tile count)
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       uint32_t nt, mt, tw, th, img, rest, q, ntq;
@@ -262,7 +314,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         const int colbase = co0 + c * 64;
-        const bool live = colbase < p.ncols;  // false: whole chunk beyond the real channels (ragged N tile)
+        const bool live = colbase < p.ncols && tile_ok;  // false: whole chunk beyond the real channels (ragged N tile)
         uint8_t* buf = staging + (chunk_ctr & 1u) * kStagingBytes;
         if (live) {
           // the buffer is free once the TMA store issued two chunks ago has read it (and everybody has passed
@@ -279,7 +331,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         if (c == BN / 64 - 1) {  // accumulator fully drained into registers: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_leader(&tempty_bar[acc]);
+            else mbar_arrive(&tempty_bar[acc]);
+          }
         }
         if (!live) continue;
         ++chunk_ctr;
@@ -368,16 +423,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         red[(st_half * 2 + 1) * BN + c * 64 + st_ch] = ssq[c];
       }
       named_bar_sync(1, kEpiThreads);
+      // PAIR: partial rows [0, pairs) = the leaders, [pairs, 2 pairs) = their peers; the pair count is a multiple of
+      // num_n_tiles, so that row % num_n_tiles is the row's N tile in both halves (conv_stats_sums_kernel)
+      const size_t prow = PAIR ? (blockIdx.x >> 1) + static_cast<size_t>(rank) * (gridDim.x >> 1) : static_cast<size_t>(blockIdx.x);
       for (int i = et; i < 2 * BN; i += kEpiThreads)
-        p.stats_partial[static_cast<size_t>(blockIdx.x) * 2 * BN + i] = red[i] + red[2 * BN + i];
+        p.stats_partial[prow * 2 * BN + i] = red[i] + red[2 * BN + i];
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // nobody frees TMEM or leaves while the peer may still touch this CTA
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_2sm<C::kTmemCols>(tmem_base);
+    else tmem_dealloc<C::kTmemCols>(tmem_base);
   }
 }
 
@@ -432,6 +492,50 @@ template <int BN>
 int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
   if (p.out_f32 != nullptr) return launch_t<BN, true, false>(p, grid, stream);
   return p.scale != nullptr ? launch_t<BN, false, true>(p, grid, stream) : launch_t<BN, false, false>(p, grid, stream);
+}
+
+// CTA pairs the device can keep resident with the pair kernel's shared memory (cached per device; <= 0: unavailable)
+int conv_max_pairs() {
+  static std::mutex mu;
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cached[dev & 63] == 0) {
+    int n = -1;
+    if (cudaFuncSetAttribute(conv_gemm_kernel<256, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg<256>::kPairSmemBytes) == cudaSuccess) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * 148);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = Cfg<256>::kPairSmemBytes;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<256, false, false, true>, &cfg) != cudaSuccess || n <= 0) n = -1;
+    }
+    cudaGetLastError();
+    cached[dev & 63] = n;
+  }
+  return cached[dev & 63];
+}
+
+int launch_pair(const ConvGemmParams& p, int pairs, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg<256>::kPairSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  UNETK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, false, false, true>, p));
+  UNETK_LAUNCHED();
+  return 0;
 }
 
 int pick_bn(int ncols, int q_groups) {
@@ -566,6 +670,22 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   int grid = tiles < num_sms() ? tiles : num_sms();
   grid = grid / p.num_n_tiles * p.num_n_tiles;
   if (grid < p.num_n_tiles) grid = p.num_n_tiles;
+  // BN = 256: CTA pairs (cta_group::2) — two neighbouring M tiles of an N tile share one M = 256 MMA and the weight tile
+  int pairs = 0;
+  {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("UNETK_CONV_2SM"); env = e ? atoi(e) : 1; }
+    if (env && BN == 256 && !d.out_f32 && d.scale == nullptr && p.num_m_tiles >= 2 && p.l2_prefetch == 0) {
+      const int fit = conv_max_pairs();
+      const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+      int n = num_sms() / 2;
+      if (n > fit) n = fit;
+      if (n > pair_tiles) n = pair_tiles;
+      n = n / p.num_n_tiles * p.num_n_tiles;   // every pair keeps one N tile
+      if (n >= p.num_n_tiles && n > 0) pairs = n;
+    }
+    if (pairs) grid = 2 * pairs;
+  }
 
   // ---- tensor maps
   {
@@ -582,7 +702,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
     const uint64_t rows = static_cast<uint64_t>(d.ncols) * d.q_groups;
     uint64_t dims[3] = {static_cast<uint64_t>(d.K), rows, static_cast<uint64_t>(d.b_taps)};
     uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * (d.b_rows ? static_cast<uint64_t>(d.b_rows) : rows)};
-    uint32_t box[3] = {kTileK, static_cast<uint32_t>(BN), 1};
+    uint32_t box[3] = {kTileK, static_cast<uint32_t>(pairs ? BN / 2 : BN), 1};   // pair: each CTA loads half of the rows
     uint32_t es[3] = {1, 1, 1};
     if (int rc = make_tmap_bf16(&p.tmB, d.b, 3, dims, strides, box, es, true)) return rc;
   }
@@ -607,7 +727,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   }
   int rc;
   switch (BN) {
-    case 256: rc = launch<256>(p, grid, stream); break;
+    case 256: rc = pairs ? launch_pair(p, pairs, stream) : launch<256>(p, grid, stream); break;
     case 192: rc = launch<192>(p, grid, stream); break;
     case 128: rc = launch<128>(p, grid, stream); break;
     default: rc = launch<64>(p, grid, stream); break;

@@ -49,6 +49,10 @@ CONV_SHAPES = [
     (1, 20, 24, 72, 72, (0, 0), (0, 0)),       # ragged: H,W not tile multiples; C not a multiple of 64
     (3, 5, 7, 8, 8, (0, 0), (0, 0)),           # tiny
     (1, 32, 32, 512, 320, (0, 0), (0, 0)),     # BN=256 with a masked N tail (320 = 256 + 64)
+    # BN = 256 runs on CTA pairs (cta_group::2, two M tiles per M = 256 MMA): odd M-tile counts leave the second CTA of the
+    # last pair with a tile past the end (all zero fill, nothing stored, nothing counted in the statistics)
+    (1, 24, 16, 64, 256, (0, 0), (0, 0)),      # 3 M tiles
+    (3, 8, 16, 256, 512, (0, 0), (0, 64)),     # 3 M tiles (one per image) x 2 N tiles, sliced output
     # W >= 128 and <= 128 output channels -> the halo kernel (conv3x3_halo.cu): two rows per tile, shifted descriptors
     (1, 5, 200, 64, 64, (0, 0), (0, 0)),       # odd H (last tile has one live row), ragged W, resident weights
     (2, 6, 128, 136, 72, (8, 0), (0, 56)),     # K tail chunk (136 = 2*64 + 8), 72 output channels, sliced in/out
