@@ -22,6 +22,7 @@
 #include "ptx.cuh"
 
 #include <cstdlib>
+#include <mutex>
 
 namespace unetk {
 
@@ -67,15 +68,22 @@ struct HaloParams {
   int8_t dh[9], dw[9], btap[9];
 };
 
-template <int BN, bool AFFINE, int TAPS>
+// PAIR (BN = 128): clusters of two CTAs own two neighbouring tiles (2 rows x 128 columns each) of the same N tile and run
+// every tap as ONE M = 256 x N = 128 MMA over both SMs (tcgen05 cta_group::2).  An N = 128 MMA on one SM re-reads 4 KB of A
+// and 4 KB of B per 64 clocks — all of an SM's shared-memory bandwidth, 55-69 % tensor-pipe activity
+// (profiles/r01_ncu_halo_epilogue.txt); in the pair each CTA reads its own halo and its HALF of the weight tile (64 rows;
+// the peer holds the other 64), 96 B/clk, and fetches half of the weights.  Barrier protocol as in wgrad3x3_2sm.cu.
+template <int BN, bool AFFINE, int TAPS, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_constant__ HaloParams p) {
   using C = HCfg<BN>;
+  static_assert(!PAIR || BN == 128, "the CTA-pair form exists for BN = 128");
+  constexpr uint32_t kBBytes = PAIR ? C::kBBytes / 2 : C::kBBytes;   // this CTA's part of one (tap, chunk) weight tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;                                   // [2][kHaloSlot]
   uint8_t* sB = sA + 2 * kHaloSlot;                     // [kBStages][kBBytes]
-  const uint32_t b_region = p.resident ? static_cast<uint32_t>(TAPS * p.kchunks) * C::kBBytes : C::kBStages * C::kBBytes;
+  const uint32_t b_region = p.resident ? static_cast<uint32_t>(TAPS * p.kchunks) * kBBytes : C::kBStages * kBBytes;
   const int n_staging = p.resident ? 1 : C::kStaging;
   uint8_t* staging = sB + b_region;                     // [n_staging][16 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + n_staging * kStagingBytes);
@@ -97,13 +105,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     tma_prefetch_desc(&p.tmOut[0]);
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 8 : 4); }
     mbar_init(w_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_2sm<C::kTmemCols>(tmem_slot);
+    else tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  uint32_t rank = 0;
+  if constexpr (PAIR) {
+    rank = cluster_ctarank();
+    cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on global memory
@@ -111,19 +127,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   pdl_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // tile walk: single CTA: blockIdx.x, + gridDim.x, ...; PAIR: the cluster walks pair tiles (two neighbouring M tiles x one
+  // N tile), rank r takes M tile 2*mp + r — past the end for the last pair of an odd count: all zero fill, nothing stored
+  const int walk_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int walk_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int walk_end = PAIR ? ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles : num_tiles;
+  const int cta_nt = (PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x)) % p.num_n_tiles;   // this CTA's N tile
+  auto tile_of = [&](int wt) -> int {
+    if constexpr (!PAIR) return wt;
+    uint32_t mp, nt;
+    p.fd_n_tiles.divmod(static_cast<uint32_t>(wt), mp, nt);
+    return static_cast<int>((2 * mp + rank) * static_cast<uint32_t>(p.num_n_tiles) + nt);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int wt = walk_first; wt < walk_end; wt += walk_step) {
+        const int tile = tile_of(wt);
         uint32_t mt, tw, th, img, rest;
         mt = p.fd_n_tiles.div(tile);
         p.fd_tiles_w.divmod(mt, rest, tw);
         p.fd_tiles_h.divmod(rest, img, th);
         const int h0 = th * 2, w0 = tw * kTW;
-        if (p.l2_prefetch > 0) {
+        if (!PAIR && p.l2_prefetch > 0) {
           // optional: pull the halo of the tile this CTA reaches `l2_prefetch` rounds from now into L2
           const int ft = tile + p.l2_prefetch * gridDim.x;
           if (ft < num_tiles) {
@@ -135,8 +164,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         }
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&a_empty[as], aph ^ 1u);
-          mbar_expect_tx(&a_full[as], kHaloBytes);
-          tma_load_4d(sA + as * kHaloSlot, &p.tmA, &a_full[as], kc * 64, w0 - 1, h0 - 1, img);
+          if constexpr (PAIR) {   // both halos are counted on the leader's barrier
+            if (rank == 0) mbar_expect_tx(&a_full[as], 2 * kHaloBytes);
+            tma_load_4d_2sm(sA + as * kHaloSlot, &p.tmA, &a_full[as], kc * 64, w0 - 1, h0 - 1, img);
+          } else {
+            mbar_expect_tx(&a_full[as], kHaloBytes);
+            tma_load_4d(sA + as * kHaloSlot, &p.tmA, &a_full[as], kc * 64, w0 - 1, h0 - 1, img);
+          }
           if (++as == 2) { as = 0; aph ^= 1u; }
         }
       }
@@ -147,21 +181,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       // never delay the next tile's halo load, and vice versa)
       if (p.resident) {
         // grid is a multiple of num_n_tiles => this CTA always works on N tile blockIdx % num_n_tiles
-        const int nt = blockIdx.x % p.num_n_tiles;
-        mbar_expect_tx(w_full, static_cast<uint32_t>(TAPS * p.kchunks) * C::kBBytes);
+        const int nt = cta_nt;
+        const uint32_t w_bytes = static_cast<uint32_t>(TAPS * p.kchunks) * kBBytes;
+        if constexpr (PAIR) {
+          if (rank == 0) mbar_expect_tx(w_full, 2 * w_bytes);
+        } else {
+          mbar_expect_tx(w_full, w_bytes);
+        }
         for (int kc = 0; kc < p.kchunks; ++kc)
-          for (int t = 0; t < TAPS; ++t)
-            tma_load_3d(sB + (kc * TAPS + t) * C::kBBytes, &p.tmB, w_full, kc * 64, nt * BN, p.btap[t]);
+          for (int t = 0; t < TAPS; ++t) {
+            if constexpr (PAIR) tma_load_3d_2sm(sB + (kc * TAPS + t) * kBBytes, &p.tmB, w_full, kc * 64, nt * BN + static_cast<int>(rank) * (BN / 2), p.btap[t]);
+            else tma_load_3d(sB + (kc * TAPS + t) * kBBytes, &p.tmB, w_full, kc * 64, nt * BN, p.btap[t]);
+          }
       } else {
         int bs = 0;
         uint32_t bph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int nt = tile % p.num_n_tiles;
+        for (int wt = walk_first; wt < walk_end; wt += walk_step) {
+          const int nt = cta_nt;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             for (int t = 0; t < TAPS; ++t) {
               mbar_wait(&b_empty[bs], bph ^ 1u);
-              mbar_expect_tx(&b_full[bs], C::kBBytes);
-              tma_load_3d(sB + bs * C::kBBytes, &p.tmB, &b_full[bs], kc * 64, nt * BN, p.btap[t]);
+              if constexpr (PAIR) {
+                if (rank == 0) mbar_expect_tx(&b_full[bs], 2 * kBBytes);
+                tma_load_3d_2sm(sB + bs * kBBytes, &p.tmB, &b_full[bs], kc * 64, nt * BN + static_cast<int>(rank) * (BN / 2), p.btap[t]);
+              } else {
+                mbar_expect_tx(&b_full[bs], kBBytes);
+                tma_load_3d(sB + bs * kBBytes, &p.tmB, &b_full[bs], kc * 64, nt * BN, p.btap[t]);
+              }
               if (++bs == C::kBStages) { bs = 0; bph ^= 1u; }
             }
           }
@@ -169,21 +215,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    {
-      // ------------------------------------------------------------ MMA issuer (warp-convergent, elected lane issues)
+    if (!PAIR || rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (warp-convergent, elected lane issues;
+      // PAIR: the leader issues for both SMs)
       const bool issue = elect_one();
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN, false, false);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
       if (p.resident) { mbar_wait_p(issue, w_full, 0); tc_fence_after(); }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int wt = walk_first; wt < walk_end; wt += walk_step, ++it) {
         const int acc = it & 1;
         mbar_wait_p(issue, &tempty[acc], ((it >> 1) & 1) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 2 * BN * C::kSplit;   // [split][row][BN]
         // output phase of this tile's N tile: its window starts (qy, qx) * q_shift further into the halo
-        const int q = (tile % p.num_n_tiles) / p.tiles_per_q;
+        const int q = cta_nt / p.tiles_per_q;
         const int q_halo = ((q >> 1) * kHaloW + (q & 1)) * p.q_shift;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait_p(issue, &a_full[as], aph);
@@ -203,14 +250,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
               if (s < nset) {
                 const int t = t0 + s;
                 if (p.resident) {
-                  db0[s] = desc_advance(b_desc0, static_cast<uint32_t>(kc * TAPS + t) * C::kBBytes);
+                  db0[s] = desc_advance(b_desc0, static_cast<uint32_t>(kc * TAPS + t) * kBBytes);
                 } else {
                   int st = bs + s;
                   uint32_t ph = bph;
                   if (st >= C::kBStages) { st -= C::kBStages; ph ^= 1u; }
                   mbar_wait_p(issue, &b_full[st], ph);
                   tc_fence_after();
-                  db0[s] = desc_advance(b_desc0, static_cast<uint32_t>(st) * C::kBBytes);
+                  db0[s] = desc_advance(b_desc0, static_cast<uint32_t>(st) * kBBytes);
                 }
                 // halo row of output row u and tap t: (u + dh + 1); halo column of output column 0: (dw + 1)
                 da0[s] = desc_advance(a_desc0, static_cast<uint32_t>(((p.dh[t] + 1) * kHaloW + p.dw[t] + 1 + q_halo) * 128));
@@ -223,7 +270,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
                 if (s < nset) {
                   const uint32_t d_set = d_tmem + static_cast<uint32_t>(s) * 2 * BN;
                   const uint64_t da = desc_advance(da0[s], k * 32), db = desc_advance(db0[s], k * 32);
-                  if (t0 == 0 && k == 0) {   // the first MMA of every accumulator overwrites (first chunk only)
+                  if constexpr (PAIR) {
+                    const uint32_t accf = (t0 == 0 && k == 0 && kc == 0) ? 0u : 1u;
+                    umma_bf16_2sm_p(issue, d_set, da, db, idesc, accf);
+                    umma_bf16_2sm_p(issue, d_set + BN, desc_advance(da, kHaloW * 128), db, idesc, accf);
+                  } else if (t0 == 0 && k == 0) {   // the first MMA of every accumulator overwrites (first chunk only)
                     umma_bf16_p(issue, d_set, da, db, idesc, kc != 0 ? 1u : 0u);
                     umma_bf16_p(issue, d_set + BN, desc_advance(da, kHaloW * 128), db, idesc, kc != 0 ? 1u : 0u);
                   } else {
@@ -237,16 +288,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
 #pragma unroll
               for (int s = 0; s < C::kSplit; ++s) {
                 if (s < nset) {
-                  umma_commit_p(issue, &b_empty[bs]);
+                  if constexpr (PAIR) umma_commit_2sm_mc_p(issue, &b_empty[bs], 0x3);
+                  else umma_commit_p(issue, &b_empty[bs]);
                   if (++bs == C::kBStages) { bs = 0; bph ^= 1u; }
                 }
               }
             }
           }
-          umma_commit_p(issue, &a_empty[as]);  // all taps of this chunk have been issued
+          // all taps of this chunk have been issued
+          if constexpr (PAIR) umma_commit_2sm_mc_p(issue, &a_empty[as], 0x3);
+          else umma_commit_p(issue, &a_empty[as]);
           if (++as == 2) { as = 0; aph ^= 1u; }
         }
-        umma_commit_p(issue, &tfull[acc]);
+        if constexpr (PAIR) umma_commit_2sm_mc_p(issue, &tfull[acc], 0x3);
+        else umma_commit_p(issue, &tfull[acc]);
       }
     }
   } else if (warp >= 2 && warp <= 5) {
@@ -271,12 +326,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     const uint32_t bias_a = smem_u32(bars) + 256;
     const float* scale_g = nullptr;   // AFFINE: read through the read-only cache (see conv_gemm.cu)
     if (p.bias != nullptr) {
-      const int co_cta = static_cast<int>(blockIdx.x % p.num_n_tiles % p.tiles_per_q) * BN;
+      const int co_cta = (cta_nt % p.tiles_per_q) * BN;
       for (int i = et; i < BN; i += kEpiThreads) sts_f32(bias_a + i * 4, (co_cta + i < p.ncols) ? __ldg(p.bias + co_cta + i) : 0.f);
       if constexpr (AFFINE) scale_g = p.scale + co_cta;
       named_bar_sync(1, kEpiThreads);
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int wt = walk_first; wt < walk_end; wt += walk_step, ++it) {
+      const int tile = tile_of(wt);
+      const bool tile_ok = !PAIR || tile < num_tiles;   // PAIR: the second CTA's tile past the end (odd tile count)
       const int acc = it & 1;
       uint32_t nt, mt, tw, th, img, rest;
       p.fd_n_tiles.divmod(tile, mt, nt);
@@ -295,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
 #pragma unroll 1
       for (int uc = 0; uc < 2 * (BN / 64); ++uc) {
         const int u = (BN == 64) ? uc : (uc >> 1);
-        const bool row_ok = (h0 + u) < p.H;
+        const bool row_ok = (h0 + u) < p.H && tile_ok;
         {
           const int c = (BN == 64) ? 0 : (uc & 1);
           const int colbase = co0 + c * 64;
@@ -326,7 +383,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
           if (last) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_leader(&tempty[acc]);
+              else mbar_arrive(&tempty[acc]);
+            }
           }
           if (!live) continue;
           ++chunk_ctr;
@@ -406,16 +466,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         red[(st_half * 2 + 1) * BN + c * 64 + st_ch] = ssq[c];
       }
       named_bar_sync(1, kEpiThreads);
+      // PAIR: partial rows [0, pairs) = the leaders, [pairs, 2 pairs) = their peers (the pair count is a multiple of num_n_tiles)
+      const size_t prow = PAIR ? (blockIdx.x >> 1) + static_cast<size_t>(rank) * (gridDim.x >> 1) : static_cast<size_t>(blockIdx.x);
       for (int i = et; i < 2 * BN; i += kEpiThreads)
-        p.stats_partial[static_cast<size_t>(blockIdx.x) * 2 * BN + i] = red[i] + red[2 * BN + i];
+        p.stats_partial[prow * 2 * BN + i] = red[i] + red[2 * BN + i];
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // nobody frees TMEM or leaves while the peer may still touch this CTA
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_2sm<C::kTmemCols>(tmem_base);
+    else tmem_dealloc<C::kTmemCols>(tmem_base);
   }
 }
 
@@ -433,6 +497,64 @@ int launch_t(HaloParams& p, int grid, cudaStream_t stream) {
   UNETK_LAUNCHED();
   return 0;
 }
+// ---- CTA pairs (BN = 128)
+template <bool AFFINE, int TAPS>
+uint32_t pair_smem(HaloParams& p) {
+  using C = HCfg<128>;
+  const uint32_t w_bytes = static_cast<uint32_t>(TAPS * p.kchunks) * (C::kBBytes / 2);
+  const uint32_t resident_smem = 2 * kHaloSlot + w_bytes + kStagingBytes + 1024 + 256 + 128 * 4;
+  p.resident = (resident_smem <= 227 * 1024) ? 1 : 0;
+  return p.resident ? resident_smem : 2 * kHaloSlot + C::kBStages * (C::kBBytes / 2) + C::kStaging * kStagingBytes + 1024 + 256 + 128 * 4;
+}
+int halo_max_pairs() {
+  static std::mutex mu;
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cached[dev & 63] == 0) {
+    int n = -1;
+    if (cudaFuncSetAttribute(conv3x3_halo_kernel<128, false, 9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * 148);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = 227 * 1024;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&n, conv3x3_halo_kernel<128, false, 9, true>, &cfg) != cudaSuccess || n <= 0) n = -1;
+    }
+    cudaGetLastError();
+    cached[dev & 63] = n;
+  }
+  return cached[dev & 63];
+}
+template <bool AFFINE, int TAPS>
+int launch_pair_t(HaloParams& p, int pairs, cudaStream_t stream) {
+  static DeviceOnce once;
+  UNETK_CUDA(once.run([] { return cudaFuncSetAttribute(conv3x3_halo_kernel<128, AFFINE, TAPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
+  const uint32_t smem_bytes = pair_smem<AFFINE, TAPS>(p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  UNETK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<128, AFFINE, TAPS, true>, p));
+  UNETK_LAUNCHED();
+  return 0;
+}
+int launch_pair(HaloParams& p, int pairs, cudaStream_t stream, int taps) {
+  if (taps == 4) return p.scale != nullptr ? launch_pair_t<true, 4>(p, pairs, stream) : launch_pair_t<false, 4>(p, pairs, stream);
+  return p.scale != nullptr ? launch_pair_t<true, 9>(p, pairs, stream) : launch_pair_t<false, 9>(p, pairs, stream);
+}
+
 template <int BN>
 int launch(HaloParams& p, int grid, cudaStream_t stream, int taps) {
   if (taps == 4) return p.scale != nullptr ? launch_t<BN, true, 4>(p, grid, stream) : launch_t<BN, false, 4>(p, grid, stream);
@@ -499,6 +621,22 @@ int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream) {
   int grid = tiles < num_sms() ? tiles : num_sms();
   grid = grid / p.num_n_tiles * p.num_n_tiles;
   if (grid < p.num_n_tiles) grid = p.num_n_tiles;
+  // BN = 128: CTA pairs (cta_group::2): two neighbouring tiles of an N tile share one M = 256 MMA per tap and the weight tile
+  int pairs = 0;
+  {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("UNETK_HALO_2SM"); env = e ? atoi(e) : 1; }
+    if (env && BN == 128 && p.num_m_tiles >= 2 && p.l2_prefetch == 0) {
+      const int fit = halo_max_pairs();
+      const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+      int n = num_sms() / 2;
+      if (n > fit) n = fit;
+      if (n > pair_tiles) n = pair_tiles;
+      n = n / p.num_n_tiles * p.num_n_tiles;
+      if (n >= p.num_n_tiles && n > 0) pairs = n;
+    }
+    if (pairs) grid = 2 * pairs;
+  }
   {
     uint64_t dims[4] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
                         static_cast<uint64_t>(d.N)};
@@ -512,7 +650,7 @@ int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream) {
     const uint64_t rows = static_cast<uint64_t>(d.ncols) * d.q_groups;   // phased: weight rows q * ncols + co
     uint64_t dims[3] = {static_cast<uint64_t>(d.K), rows, static_cast<uint64_t>(d.b_taps)};
     uint64_t strides[2] = {static_cast<uint64_t>(d.K) * 2, static_cast<uint64_t>(d.K) * 2 * (d.b_rows ? static_cast<uint64_t>(d.b_rows) : rows)};
-    uint32_t box[3] = {64, static_cast<uint32_t>(BN), 1};
+    uint32_t box[3] = {64, static_cast<uint32_t>(pairs ? BN / 2 : BN), 1};   // pair: each CTA loads half of the weight rows
     uint32_t es[3] = {1, 1, 1};
     if (int rc = make_tmap_bf16(&p.tmB, d.b, 3, dims, strides, box, es, true)) return rc;
   }
@@ -531,7 +669,8 @@ int conv3x3_halo_run(const ConvGemmDesc& d, cudaStream_t stream) {
       if (int rc = make_tmap_bf16(&p.tmOut[q], base, 4, dims, strides, box, es, true)) return rc;
     }
   }
-  const int rc = (BN == 128) ? launch<128>(p, grid, stream, d.taps) : launch<64>(p, grid, stream, d.taps);
+  const int rc = pairs ? launch_pair(p, pairs, stream, d.taps)
+                       : ((BN == 128) ? launch<128>(p, grid, stream, d.taps) : launch<64>(p, grid, stream, d.taps));
   if (rc) return rc;
   if (d.stats_sums != nullptr) {
     if (phased) return conv_stats_sums_q_launch(d.stats_partial, grid, p.tiles_per_q, d.q_groups, BN, d.ncols, d.stats_sums, stream);

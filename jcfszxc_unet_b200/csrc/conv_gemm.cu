@@ -522,7 +522,12 @@ int conv_max_pairs() {
   return cached[dev & 63];
 }
 
-int launch_pair(const ConvGemmParams& p, int pairs, cudaStream_t stream) {
+template <bool AFFINE>
+int launch_pair_t(const ConvGemmParams& p, int pairs, cudaStream_t stream) {
+  static DeviceOnce once;
+  UNETK_CUDA(once.run([] {
+    return cudaFuncSetAttribute(conv_gemm_kernel<256, false, AFFINE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kPairSmemBytes);
+  }));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kThreads);
@@ -533,9 +538,12 @@ int launch_pair(const ConvGemmParams& p, int pairs, cudaStream_t stream) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  UNETK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, false, false, true>, p));
+  UNETK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, false, AFFINE, true>, p));
   UNETK_LAUNCHED();
   return 0;
+}
+int launch_pair(const ConvGemmParams& p, int pairs, cudaStream_t stream) {
+  return p.scale != nullptr ? launch_pair_t<true>(p, pairs, stream) : launch_pair_t<false>(p, pairs, stream);
 }
 
 int pick_bn(int ncols, int q_groups) {
@@ -675,7 +683,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
   {
     static int env = -1;
     if (env < 0) { const char* e = getenv("UNETK_CONV_2SM"); env = e ? atoi(e) : 1; }
-    if (env && BN == 256 && !d.out_f32 && d.scale == nullptr && p.num_m_tiles >= 2 && p.l2_prefetch == 0) {
+    if (env && BN == 256 && !d.out_f32 && p.num_m_tiles >= 2 && p.l2_prefetch == 0) {
       const int fit = conv_max_pairs();
       const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
       int n = num_sms() / 2;

@@ -58,6 +58,7 @@ CONV_SHAPES = [
     (2, 6, 128, 136, 72, (8, 0), (0, 56)),     # K tail chunk (136 = 2*64 + 8), 72 output channels, sliced in/out
     (1, 4, 384, 128, 128, (0, 0), (128, 0)),   # BN=128, three column tiles, weight ring (not resident)
     (1, 3, 256, 64, 128, (64, 0), (0, 0)),     # 64 -> 128 (dgrad of it is 128 -> 64)
+    (1, 5, 128, 72, 96, (0, 0), (0, 32)),      # halo kernel on CTA pairs (BN = 128): three tiles, the last pair's second CTA idle
     # <= 64 output channels, K <= 128, W >= 128 -> the row-stacked kernel (conv3x3_rows.cu): 4 output rows per tile,
     # one input row multiplied by up to three filter rows in one N = 192 MMA
     (1, 9, 130, 64, 64, (0, 0), (0, 0)),       # H not a multiple of 4 (last tile: one live row), ragged W
