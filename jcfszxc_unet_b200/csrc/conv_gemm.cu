@@ -686,7 +686,7 @@ int conv_gemm_run(const ConvGemmDesc& d, cudaStream_t stream) {
     if (env && BN == 256 && !d.out_f32 && p.num_m_tiles >= 2 && p.l2_prefetch == 0) {
       const int fit = conv_max_pairs();
       const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
-      int n = num_sms() / 2;
+      int n = num_sm_pairs();
       if (n > fit) n = fit;
       if (n > pair_tiles) n = pair_tiles;
       n = n / p.num_n_tiles * p.num_n_tiles;   // every pair keeps one N tile

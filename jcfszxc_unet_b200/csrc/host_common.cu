@@ -55,6 +55,15 @@ int num_sms() {
   const int real = device_sms();
   return (g_sm_limit > 0 && g_sm_limit < real) ? g_sm_limit : real;
 }
+// CTA pairs (clusters of two = the two SMs of a TPC) a persistent pair kernel may use.  Under an SM limit the SMs left to
+// the other kernel (NCCL's CTAs while gradient buckets are in flight) may sit in as many different TPCs, each of which then
+// cannot host a pair: leave that many more pairs out, so that every launched pair finds a free TPC at once (a pair that has
+// to wait for one runs after all the others and doubles the kernel's time).
+int num_sm_pairs() {
+  const int real = device_sms(), lim = num_sms();
+  const int pairs = lim / 2 - (real - lim);
+  return pairs > 0 ? pairs : 0;
+}
 
 int device_sms() {
   static std::atomic<int> cached[64];   // per device ordinal; 0 = not queried yet

@@ -66,6 +66,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 long long launch_count();
 int device_sms();          // SM count of the CURRENT device (cached per device)
 int num_sms();             // what grids are sized for: device_sms(), or the calling thread's limit (set_sm_limit)
+int num_sm_pairs();        // CTA pairs (clusters of two) a persistent pair kernel may use under that limit
 int set_sm_limit(int n);   // n > 0: persistent kernels launched by THIS thread use at most n SMs; 0: all.  Returns the old limit
 const char* last_error();  // the calling thread's last error text (thread-local, errno-style)
 

@@ -453,7 +453,7 @@ int launch_pair(const W3Params& p, const W3Plan& pl, cudaStream_t stream) {
   const int pairs_fit = max_pairs(pl.smem_bytes);
   if (pairs_fit <= 0) return 1;
   const int pair_items = pl.m_tiles * pl.n_tiles * pl.ksplit;
-  int pairs = num_sms() / 2;
+  int pairs = num_sm_pairs();
   if (pairs > pairs_fit) pairs = pairs_fit;
   if (pairs > pair_items) pairs = pair_items;
   cudaLaunchConfig_t cfg{};

@@ -276,7 +276,7 @@ bool make_plan(int N, int H, int W, int M, int Nn, W2Plan* pl) {
   }
   int pairs = max_pairs(227 * 1024);
   if (pairs <= 0) return false;
-  if (pairs > num_sms() / 2) pairs = num_sms() / 2;
+  if (pairs > num_sm_pairs()) pairs = num_sm_pairs();
   if (pairs < 1) return false;
   // pixel split: the cost rule of wgrad3x3.cu with the pairs in the place of the SMs
   const int base = 3 * pl->m_pairs * pl->n_tiles;
