@@ -57,11 +57,11 @@ int num_sms() {
 }
 // CTA pairs (clusters of two = the two SMs of a TPC) a persistent pair kernel may use.  Under an SM limit the SMs left to
 // the other kernel (NCCL's CTAs while gradient buckets are in flight) may sit in as many different TPCs, each of which then
-// cannot host a pair: leave that many more pairs out, so that every launched pair finds a free TPC at once (a pair that has
-// to wait for one runs after all the others and doubles the kernel's time).
+// cannot host a pair: every reserved SM takes a whole TPC out, so that each launched pair finds a free TPC at once (a pair
+// that has to wait for one runs after all the others and doubles the kernel's time).
 int num_sm_pairs() {
   const int real = device_sms(), lim = num_sms();
-  const int pairs = lim / 2 - (real - lim);
+  const int pairs = real / 2 - (real - lim);
   return pairs > 0 ? pairs : 0;
 }
 
