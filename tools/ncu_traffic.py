@@ -12,7 +12,7 @@ import sys
 
 FAMILY = {"conv_gemm_kernel": "tap_gemm", "conv3x3_halo_kernel": "tap_gemm", "conv3x3_rows_kernel": "tap_gemm", "wgrad3x3_kernel": "wgrad", "wgrad_kernel": "wgrad",
           "wgrad_reduce_kernel": "wgrad", "wgrad_reduce_sliced_kernel": "wgrad", "wgrad_reduce_tiled_kernel": "wgrad",
-          "wgrad_up_kernel": "wgrad", "wgrad_reduce_upfold_kernel": "wgrad", "wgrad_reduce_upfold_sliced_kernel": "wgrad"}
+          "wgrad_up_kernel": "wgrad", "wgrad3x3_2sm_kernel": "wgrad", "wgrad_reduce_upfold_kernel": "wgrad", "wgrad_reduce_upfold_sliced_kernel": "wgrad"}
 TENSOR = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0,
         "usecond": 1e-6, "nsecond": 1e-9, "msecond": 1e-3, "second": 1.0}
