@@ -12,7 +12,8 @@
 //      (h0 - qy, w0 - qx)                                             -> [(TH+1)(TW+1) px][64 ch] per 64 output channels
 // and tap (u, v) is the MMA whose Q descriptor starts (1-u) halo rows and (1-v) pixels into that tile (tcgen05 applies the
 // 128B-swizzle XOR on absolute shared-memory address bits, profiles/r01_umma_descriptor_probe.txt): 4 x 128 fp32
-// accumulator columns = the whole TMEM, 49 B/clk per SM.  Cout <= 64 (the full-resolution up-conv, 128 -> 64): a work item
+// accumulator columns = the whole TMEM, one X tile and one halo tile per four taps (ncu: 73-80 % tensor-pipe activity,
+// bound by the shared-memory reads of its N = 128 MMAs like wgrad3x3_kernel<128>, profiles/r02_ncu_upconv.txt).  Cout <= 64 (the full-resolution up-conv, 128 -> 64): a work item
 // owns the two phases (qy, 0), (qy, 1) instead and the two taps v of a (phase, u) pair are ONE MMA of N = 128 — two
 // overlapping 64-wide N atoms one pixel (128 B) apart — so that the MMA rows are never half empty.
 // Output: fp32 partials [ksplit][16][Cin][Cout], folded to the 3x3 master's gradient by wgrad_reduce_upfold (wgrad.cu).
