@@ -568,7 +568,7 @@ def run_ours(args):
     achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
     step_ms_eager = sum(v["ms"] for v in fam.values())
     roofline = {
-        "bound": "tensor", "kernel": {"tap_gemm": "conv_gemm_kernel / conv3x3_halo_kernel (conv3x3 and 1x1 fwd/dgrad, ConvTranspose fwd/dgrad)",
+        "bound": "tensor", "kernel": {"tap_gemm": "conv_gemm_kernel / conv3x3_halo_kernel / conv3x3_rows_kernel (conv3x3 and 1x1 fwd/dgrad, ConvTranspose fwd/dgrad; BN = 256 and the 128-column halo layers as CTA pairs, tcgen05 cta_group::2)",
                                       "wgrad": "wgrad3x3_kernel / wgrad_kernel (+ordered reduce)"}[dom_name],
         "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic_per_launch(dom_name, args),
