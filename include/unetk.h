@@ -117,10 +117,6 @@ int unetk_conv1x1_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_
  * wgrad: dw[ci,co,a,b] fp32 = sum_{n,h,w} x[n,h,w,ci] * dy[n,2h+a,2w+b,co]. */
 int unetk_convT2x2_fwd(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y,
                        int64_t y_ld, int N, int H, int W, int Cin, int Cout, void* stream);
-/* fwd + fused per-channel (sum, sum of squares) of the bf16 output over all four phases (sums = double [2][Cout], partial >=
- * unetk_conv_stats_partial_floats(Cout) floats): the statistics of a BatchNorm reading the ConvTranspose output. */
-int unetk_convT2x2_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y, int64_t y_ld,
-                               float* partial, double* sums, int N, int H, int W, int Cin, int Cout, void* stream);
 int unetk_convT2x2_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld,
                          int accumulate, int N, int H, int W, int Cin, int Cout, void* stream);
 int unetk_convT2x2_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw,

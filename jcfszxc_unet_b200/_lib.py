@@ -52,7 +52,6 @@ SIGNATURES = {
     "unetk_upconv_wgrad_workspace": (_sz, [_i, _i, _i, _i, _i]),
     "unetk_upconv3x3_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "unetk_convT2x2_fwd": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
-    "unetk_convT2x2_fwd_bnstats": (_i, [_vp, _i64, _vp, _fp, _vp, _i64, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "unetk_convT2x2_dgrad": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "unetk_convT2x2_wgrad": (_i, [_vp, _i64, _vp, _i64, _fp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "unetk_stem_conv3x3_fwd": (_i, [_fp, _i64, _i64, _i64, _i64, _fp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),

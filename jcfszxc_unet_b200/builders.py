@@ -75,20 +75,16 @@ def emit_rrcnn(P: Plan, x, mod, out: Act | None = None) -> Act:
     return emit_recurrent(P, r1, mod.RCNN[1], out=out, res=x0)
 
 
-def emit_residual_conv(P: Plan, x: Act, mod, out: Act | None = None, keep_sums: bool = False, parts: list | None = None,
-                       info: dict | None = None) -> Act:
+def emit_residual_conv(P: Plan, x: Act, mod, out: Act | None = None) -> Act:
     """ResidualConv.forward (unet_parts.py:454-475): conv_block(x) + conv_skip(x) with
-    conv_block = BN -> ReLU -> conv3x3(stride) -> BN -> ReLU -> conv3x3 and conv_skip = conv3x3(stride) -> BN.
-    keep_sums / parts: see engine.BNAct (the pre-activation BatchNorm over x); info["bn"] receives that op."""
+    conv_block = BN -> ReLU -> conv3x3(stride) -> BN -> ReLU -> conv3x3 and conv_skip = conv3x3(stride) -> BN."""
     cb, cs = mod.conv_block, mod.conv_skip
     stride = cb[2].stride[0]
     _require(cb[2].padding == (1, 1) and cs[0].padding == (1, 1), "ResidualConv: only padding=1 is on this path")
     h, w = x.H // stride, x.W // stride
     cout = cb[2].out_channels
     t = P.act(x.H, x.W, x.C)
-    bn0 = BNAct(P, x, cb[0], t, relu=True, keep_sums=keep_sums, parts=parts)
-    if info is not None:
-        info["bn"] = bn0
+    BNAct(P, x, cb[0], t, relu=True)
     u = P.act(h, w, cout)
     ConvBNReLU(P, t, cb[2], cb[3], u)
     out = out if out is not None else P.act(h, w, cout)
@@ -195,21 +191,13 @@ def build_resunet_plan(model, N, H, W, device, training, grad_views=None, with_g
     za = Act(P.act(H, W, c1, grad=False).t, x1.g)
     ConvBNReLU(P, P.image, isk[0], None, za, relu=False)
     AddN(P, [ya, za], x1)
-    # The decoder's pre-activation BatchNorms read cat(upsample(y), x_k) (ResUNet.py:60-71).  The statistics of x_k were
-    # taken by the encoder block that consumed it (kept: keep_sums), those of the ConvTranspose output come out of its
-    # epilogue (want_stats): no statistics pass over the three widest tensors of the model (UNETK_RESUNET_STATS_REUSE=0:
-    # one bn_stats pass per concat buffer, 0.4 ms per step at batch 8).
-    reuse = os.environ.get("UNETK_RESUNET_STATS_REUSE", "1") != "0" and training
-    infos = [{}, {}, {}]
-    x2 = emit_residual_conv(P, x1, rcs[0], skip[1], keep_sums=reuse, info=infos[0])
-    x3 = emit_residual_conv(P, x2, rcs[1], skip[2], keep_sums=reuse, info=infos[1])
-    x4 = emit_residual_conv(P, x3, rcs[2], keep_sums=reuse, info=infos[2])
+    x2 = emit_residual_conv(P, x1, rcs[0], skip[1])
+    x3 = emit_residual_conv(P, x2, rcs[1], skip[2])
+    x4 = emit_residual_conv(P, x3, rcs[2])
     y = x4
     for lvl, up, rc in zip((2, 1, 0), ups, (model.up_residual_conv1, model.up_residual_conv2, model.up_residual_conv3)):
-        ct = ConvT2x2(P, y, up.upsample, cats[lvl].slice(0, cu[2 - lvl]), want_stats=reuse)
-        enc = infos[lvl]["bn"].sums
-        parts = [(0, cu[2 - lvl], ct.sums), (cu[2 - lvl], C[lvl], enc)] if (reuse and ct.sums is not None and enc is not None) else None
-        y = emit_residual_conv(P, cats[lvl], rc, parts=parts)
+        ConvT2x2(P, y, up.upsample, cats[lvl].slice(0, cu[2 - lvl]))
+        y = emit_residual_conv(P, cats[lvl], rc)
     P.head = Head(P, y, model.output_layer[0], post_sigmoid=True)
     return P.finalize(grad_views)
 

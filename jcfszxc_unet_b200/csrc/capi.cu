@@ -284,19 +284,6 @@ int unetk_convT2x2_fwd(const void* x, int64_t x_ld, const void* w_pack, const fl
   d.dh[0] = 0; d.dw[0] = 0; d.btap[0] = 0;
   return conv_gemm_run(d, S(stream));
 }
-// the same with the per-channel (sum, sum of squares) of the stored bf16 output (all four phases) from the epilogue: the
-// statistics of a BatchNorm that reads the ConvTranspose output (ResUNet's pre-activation BN over cat(up, skip))
-int unetk_convT2x2_fwd_bnstats(const void* x, int64_t x_ld, const void* w_pack, const float* bias, void* y, int64_t y_ld,
-                               float* partial, double* sums, int N, int H, int W, int Cin, int Cout, void* stream) {
-  UNETK_CHECK(x && w_pack && y && partial && sums, -1, "convT2x2_fwd_bnstats: null pointer");
-  ConvGemmDesc d{};
-  d.a = x; d.a_ld = x_ld; d.b = w_pack; d.b_taps = 1; d.out = y; d.out_ld = y_ld; d.bias = bias;
-  d.N = N; d.H = H; d.W = W; d.K = Cin; d.ncols = Cout; d.q_groups = 4;
-  d.taps = 1; d.a_step = 1; d.out_step = 2;
-  d.dh[0] = 0; d.dw[0] = 0; d.btap[0] = 0;
-  d.stats_partial = partial; d.stats_sums = sums;
-  return conv_gemm_run(d, S(stream));
-}
 int unetk_convT2x2_dgrad(const void* dy, int64_t dy_ld, const void* w_pack_t, void* dx, int64_t dx_ld, int accumulate,
                          int N, int H, int W, int Cin, int Cout, void* stream) {
   UNETK_CHECK(dy && w_pack_t && dx, -1, "convT2x2_dgrad: null pointer");

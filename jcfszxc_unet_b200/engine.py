@@ -585,19 +585,13 @@ class ConvT2x2:
     """ConvTranspose2d(k=2, s=2) writing straight into a channel slice of the concat buffer.
     Reference: Up.up, unet_parts.py:56-58,62; Upsample :478-487."""
 
-    def __init__(self, plan: Plan, x: Act, mod: torch.nn.ConvTranspose2d, out: Act, want_stats: bool = False):
-        """want_stats: the forward epilogue also returns the per-channel (sum, sum of squares) of `out` in `self.sums`
-        (fp64 [2*Cout]) — for a BatchNorm with batch statistics that reads `out` (BNAct(parts=...))."""
+    def __init__(self, plan: Plan, x: Act, mod: torch.nn.ConvTranspose2d, out: Act):
         assert mod.kernel_size == (2, 2) and mod.stride == (2, 2) and mod.padding == (0, 0)
         self.plan, self.x, self.mod, self.out = plan, x, mod, out
         self.cin, self.cout = mod.in_channels, mod.out_channels
         assert out.H == 2 * x.H and out.W == 2 * x.W and out.C == self.cout
         self.pack = plan.pack_of(mod.weight, 4)   # ab = [4][Cin][Cout] (dgrad), ba = [4][Cout][Cin] (fwd)
         lib = _lib.load()
-        self.sums = None
-        if want_stats and plan.training:
-            self.sums = torch.zeros(2 * self.cout, dtype=torch.float64, device=plan.device)
-            plan.need(lib.unetk_conv_stats_partial_floats(self.cout), 0, self.cout)
         if plan.with_grad:
             plan.need(lib.unetk_chan_partial_floats(out.N * out.H * out.W, self.cout),
                       lib.unetk_conv_wgrad_workspace(x.N, x.H, x.W, self.cin, self.cout, 4), self.cout)
@@ -656,8 +650,7 @@ class ConvT2x2:
 
     def fwd(self):
         b = self.mod.bias
-        ops.convT_fwd(self.x.t, self.pack.ba, b.detach() if b is not None else None, self.out.t,
-                      self.plan.partial if self.sums is not None else None, self.sums)
+        ops.convT_fwd(self.x.t, self.pack.ba, b.detach() if b is not None else None, self.out.t)
 
     def bwd(self):
         P = self.plan
@@ -965,19 +958,9 @@ class BNAct(_Op):
     (unet_parts.py:458-459).  Statistics pass + apply in forward; reduce + apply in backward, accumulating
     into x.g when x has other consumers (ResidualConv.conv_skip reads the same x, :467-470)."""
 
-    def __init__(self, plan: Plan, x: Act, bn: torch.nn.BatchNorm2d, out: Act, relu: bool = True, keep_sums: bool = False,
-                 parts: list | None = None):
-        """keep_sums: the batch statistics of x stay in `self.sums` (fp64 [2*C]) after the forward, for a later BatchNorm
-        over a torch.cat that contains x.  parts: x is such a cat and the (sum, sum of squares) of each member already
-        exist — [(first channel, channels, fp64 sums [2*channels])], e.g. a ConvT2x2(want_stats=True).sums and an
-        earlier BNAct(keep_sums=True).sums (ResUNet: BN(cat(upsample(y), x_k)), ResUNet.py:60-71): no statistics pass."""
+    def __init__(self, plan: Plan, x: Act, bn: torch.nn.BatchNorm2d, out: Act, relu: bool = True):
         assert (x.N, x.H, x.W, x.C) == (out.N, out.H, out.W, out.C) and bn.num_features == x.C
         self.plan, self.x, self.bn, self.out, self.relu = plan, x, bn, out, relu
-        self.parts = parts
-        if parts is not None:
-            assert sum(c for _, c, _ in parts) == x.C and all(t is not None and t.numel() == 2 * c for _, c, t in parts)
-        self.sums = (torch.zeros(2 * x.C, dtype=torch.float64, device=plan.device)
-                     if keep_sums and plan.training and parts is None else None)
         self.stat = plan.vec(x.C, 4)
         plan.need(_lib.load().unetk_chan_partial_floats(x.N * x.H * x.W, x.C), 0, x.C)
         for p in (bn.weight, bn.bias):
@@ -1003,25 +986,13 @@ class BNAct(_Op):
         sc, sh, mu, iv = self.stat[0], self.stat[1], self.stat[2], self.stat[3]
         gamma = bn.weight.detach() if bn.weight is not None else None
         beta = bn.bias.detach() if bn.bias is not None else None
-        if ((P.training or not bn.track_running_stats) and self.parts is not None and P.sync_sums is None
-                and all(t is not None for _, _, t in self.parts)):   # (SyncBN: a member's sums may be global already)
-            # the members' statistics exist already (their producers' epilogues / an earlier BatchNorm over the same tensor)
-            track = bn.track_running_stats and P.training
-            mom = bn_momentum(bn, P.training)
-            for k, (c0, c, sums) in enumerate(self.parts):
-                count = self.x.N * self.x.H * self.x.W
-                sl = slice(c0, c0 + c)
-                ops.bn_finalize(sums, count, gamma[sl] if gamma is not None else None, beta[sl] if beta is not None else None,
-                                bn.eps, mom, bn.running_mean[sl] if track else None, bn.running_var[sl] if track else None,
-                                bn.num_batches_tracked if (track and k == 0) else None, sc[sl], sh[sl], mu[sl], iv[sl])
-        elif P.training or not bn.track_running_stats:
-            sums = self.sums if self.sums is not None else P.sums
-            ops.bn_stats(self.x.t, P.partial, sums)
+        if P.training or not bn.track_running_stats:
+            ops.bn_stats(self.x.t, P.partial, P.sums)
             count = self.x.N * self.x.H * self.x.W
             if P.sync_sums is not None:
-                count = P.sync_sums(sums[: 2 * self.x.C], count)
+                count = P.sync_sums(P.sums[: 2 * self.x.C], count)
             track = bn.track_running_stats and P.training
-            ops.bn_finalize(sums, count, gamma, beta, bn.eps, bn_momentum(bn, P.training),
+            ops.bn_finalize(P.sums, count, gamma, beta, bn.eps, bn_momentum(bn, P.training),
                             bn.running_mean if track else None, bn.running_var if track else None,
                             bn.num_batches_tracked if track else None, sc, sh, mu, iv)
         else:

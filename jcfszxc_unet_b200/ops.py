@@ -158,18 +158,13 @@ def conv_wgrad(x, dy, dw, ksize: int = 3, accumulate: bool = False, stride: int 
     return dw
 
 
-def convT_fwd(x, w_pack, bias, y, partial=None, sums=None):
-    """y [N,2H,2W,Cout] <- ConvTranspose2d(k=2,s=2)(x [N,H,W,Cin]); w_pack bf16 [4,Cout,Cin].
-    partial + sums (fp64 [2,Cout]): the epilogue also returns the per-channel (sum, sum of squares) of y."""
+def convT_fwd(x, w_pack, bias, y):
+    """y [N,2H,2W,Cout] <- ConvTranspose2d(k=2,s=2)(x [N,H,W,Cin]); w_pack bf16 [4,Cout,Cin]."""
     n, h, w, cin = x.shape
     cout = y.shape[3]
     assert w_pack.shape == (4, cout, cin) and y.shape[1] == 2 * h and y.shape[2] == 2 * w
     xp, xld = nhwc(x)
     yp, yld = nhwc(y)
-    if sums is not None:
-        _lib.call("unetk_convT2x2_fwd_bnstats", xp, xld, w_pack.data_ptr(), _f32(bias), yp, yld, partial.data_ptr(),
-                  sums.data_ptr(), n, h, w, cin, cout, _stream())
-        return y
     _lib.call("unetk_convT2x2_fwd", xp, xld, w_pack.data_ptr(), _f32(bias), yp, yld, n, h, w, cin, cout, _stream())
     return y
 
